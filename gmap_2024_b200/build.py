@@ -1,0 +1,27 @@
+"""Builds the in-tree native libraries (sm_100a only; nvcc cross-compiles without a GPU)."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libgmapdp_b200.so")
+SOURCES = ["gmapdp_kernels.cu", "gmapdp_shim.cpp"]
+HEADERS = ["gmapdp_layout.h", "gmapdp_tables.h", "../../include/gmapdp_b200.h", "../../include/gmapdp_shim.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build_native(force=False, verbose=False):
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    if force or _stale(LIB, deps):
+        nvcc = os.environ.get("NVCC", "nvcc")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+        subprocess.check_call(cmd, cwd=CSRC)
+    return LIB

@@ -1,0 +1,699 @@
+/* gmapdp_shim.cpp -- host side of the five reference entry points (see include/gmapdp_shim.h).
+ *
+ * Per call: (1) the reference's argument checks and early exits, (2) its no-fill shortcuts
+ * (single_gap_simple dynprog_single.c:345, genome_gap_simple dynprog_genome.c:3005,
+ * QUERYEND_NOGAPS dynprog_end.c:577/649), (3) otherwise a device box; after the batch has run,
+ * (4) the device's edit script is replayed into the pair list exactly as Dynprog_traceback_*
+ * (dynprog_simd.c:9154-9946) and Pairpool_add_queryskip/_genomeskip/_push_gapholder
+ * (pairpool.c:981/1068/375) would have built it, and (5) the entry point's own post-processing
+ * (leading-indel stripping, nmatches+1<nmismatches, Pair_maxnegscore pair.c:8528, insert pairs
+ * dynprog_cdna.c:1008-1041) is applied.
+ *
+ * This file never computes a DP cell: without a device GmapDP_batch_run fails.
+ */
+#include "../../include/gmapdp_shim.h"
+#include "gmapdp_layout.h"
+#include "gmapdp_tables.h"
+
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cstring>
+
+namespace {
+
+enum { COMP_DYNMATCH = '*', COMP_AMBIG = ':', COMP_MISMATCH = ' ', COMP_INDEL = '-', COMP_SHORTGAP = '~' };
+const int NEG_INFINITY_32 = -32768;
+const int MICROINTRON_LENGTH = 9, LAZY_INDEL = 1, INSERT_PAIRS = 9;
+
+const GdpHostTables &tables () { static GdpHostTables t; return t; }
+const GdpTables &dev_tables () { static GdpTables d; static bool ready = false; if (!ready) { tables().device_tables(&d); ready = true; } return d; }
+double prob_at (const std::vector<double> &v, int k) { return (k >= 0 && (size_t) k < v.size()) ? v[k] : 0.0; }
+
+struct Counts { int score = 0, nmatches = 0, nmismatches = 0, nopens = 0, nindels = 0; };
+
+/* a list under construction: elements in push order (the reference conses, so its head is back()) */
+typedef std::vector<gmapdp_pair> Pushed;
+
+void push_pair (Pushed &l, int querypos, int genomepos, char cdna, char comp, char genome, char genomealt, int dynprogindex) {
+  if (querypos < 0 || genomepos < 0) return;		/* Pairpool_push, pairpool.c:190 */
+  gmapdp_pair p;
+  memset(&p,0,sizeof(p));
+  p.querypos = querypos; p.genomepos = genomepos; p.cdna = cdna; p.comp = comp; p.genome = genome; p.genomealt = genomealt;
+  p.dynprogindex = dynprogindex;
+  l.push_back(p);
+}
+
+gmapdp_pair &push_gapholder (Pushed &l, int queryjump, int genomejump) {
+  gmapdp_pair p;
+  memset(&p,0,sizeof(p));
+  p.querypos = p.genomepos = -1; p.cdna = p.comp = p.genome = p.genomealt = ' ';
+  p.gapp = 1; p.queryjump = queryjump; p.genomejump = genomejump;
+  l.push_back(p);
+  return l.back();
+}
+
+/* one traced side, with the reference's pointer conventions */
+struct Side {
+  const char *rseq, *rsequc, *gseq, *galt;
+  int queryoffset, genomeoffset;
+  bool revp;
+};
+
+struct Replayer {
+  Pushed &l; const Side &sd; int dynprogindex; Counts &n;
+  Replayer (Pushed &l_, const Side &sd_, int dpi, Counts &n_) : l(l_), sd(sd_), dynprogindex(dpi), n(n_) {}
+
+  void diag (int r, int c) {
+    int qc = r - 1, gc = c - 1;
+    if (sd.revp) { qc = -qc; gc = -gc; }
+    const char c1 = sd.rseq[qc], c1uc = sd.rsequc[qc], c2 = sd.gseq[gc], c2a = sd.galt[gc];
+    const GdpHostTables &t = tables();
+    if (c2 == '*') return;
+    if (c1uc == c2 || c1uc == c2a) {
+      n.score += 1; n.nmatches++;
+      push_pair(l,sd.queryoffset + qc,sd.genomeoffset + gc,c1,COMP_DYNMATCH,c2,c2a,dynprogindex);
+    } else if (t.cons[c1uc & 127][c2 & 127] || t.cons[c1uc & 127][c2a & 127]) {
+      n.score += 1; n.nmatches++;
+      push_pair(l,sd.queryoffset + qc,sd.genomeoffset + gc,c1,COMP_AMBIG,c2,c2a,dynprogindex);
+    } else {
+      n.score += -3; n.nmismatches++;
+      push_pair(l,sd.queryoffset + qc,sd.genomeoffset + gc,c1,COMP_MISMATCH,c2,c2a,dynprogindex);
+    }
+  }
+  void hgap (int r, int c, int dist) {		/* Pairpool_add_genomeskip */
+    int qc = r - 1, left = c - dist, right = c - 1, step = -1;
+    if (sd.revp) { qc = -qc; int t = left; left = -right; right = -t; step = +1; }
+    if (dist < MICROINTRON_LENGTH) {
+      int gc = sd.revp ? left : right;
+      for (int j = 0; j < dist; j++, gc += step)
+	push_pair(l,sd.queryoffset + qc,sd.genomeoffset + gc,' ',COMP_INDEL,sd.gseq[gc],sd.galt[gc],dynprogindex);
+      n.score += -3 - dist; n.nopens++; n.nindels += dist;
+    } else {
+      push_gapholder(l,0,dist);
+    }
+  }
+  void vgap (int r, int c, int dist) {		/* Pairpool_add_queryskip */
+    int qc = r - 1, gc = c - 1, step = -1;
+    if (sd.revp) { qc = -qc; gc = -gc; step = +1; }
+    for (int j = 0; j < dist; j++, qc += step)
+      push_pair(l,sd.queryoffset + qc,sd.genomeoffset + gc,sd.rseq[qc],COMP_INDEL,' ',' ',dynprogindex);
+    n.score += -3 - dist; n.nopens++; n.nindels += dist;
+  }
+  /* kind: 0 full, 1 upper, 2 lower */
+  void run (int kind, int r, int c, const uint32_t *ops, int nops) {
+    for (int k = 0; k < nops; k++) {
+      const int len = (int) (ops[k] >> 2), what = (int) (ops[k] & 3u);
+      if (what == 0) { for (int j = 0; j < len; j++) { diag(r,c); r--; c--; } }
+      else if (what == 1) { hgap(r,c,len); c -= len; }
+      else { vgap(r,c,len); r -= len; }
+    }
+    if (kind == 0) {
+      if (r == 0 && c == 0) { }
+      else if (c == 0) vgap(r,0 + LAZY_INDEL,r);
+      else hgap(0 + LAZY_INDEL,c,c);
+    } else if (kind == 1) {
+      if (c != 0) hgap(0 + LAZY_INDEL,c,c);
+    } else {
+      if (r != 0) vgap(r,0 + LAZY_INDEL,r);
+    }
+  }
+};
+
+int maxnegscore_headfirst (const std::vector<gmapdp_pair> &hf) {	/* Pair_maxnegscore, pair.c:8528 */
+  int maxneg = 0, prevhigh = 0, score = 0;
+  size_t i = 0, n = hf.size();
+  while (i < n) {
+    if (hf[i].gapp) i++;
+    else if (hf[i].comp == COMP_MISMATCH) { score += -3; maxneg = std::min(maxneg,score - prevhigh); i++; }
+    else if (hf[i].comp == COMP_INDEL) {
+      score += -3 + -1; i++;
+      while (i < n && hf[i].comp == COMP_INDEL) { score += -1; i++; }
+      maxneg = std::min(maxneg,score - prevhigh);
+    } else { score += 1; prevhigh = std::max(prevhigh,score); i++; }
+  }
+  return maxneg;
+}
+
+int left_dinucl (char a, char aa, char b, char ba) {
+  if ((a == 'G' || aa == 'G') && (b == 'T' || ba == 'T')) return 0x21;
+  if ((a == 'G' || aa == 'G') && (b == 'C' || ba == 'C')) return 0x10;
+  if ((a == 'A' || aa == 'A') && (b == 'T' || ba == 'T')) return 0x08;
+  if ((a == 'C' || aa == 'C') && (b == 'T' || ba == 'T')) return 0x06;
+  return 0;
+}
+int right_dinucl (char r2, char r2a, char r1, char r1a) {
+  if ((r2 == 'A' || r2a == 'A') && (r1 == 'G' || r1a == 'G')) return 0x30;
+  if ((r2 == 'A' || r2a == 'A') && (r1 == 'C' || r1a == 'C')) return 0x0C;
+  if ((r2 == 'G' || r2a == 'G') && (r1 == 'C' || r1a == 'C')) return 0x02;
+  if ((r2 == 'A' || r2a == 'A') && (r1 == 'T' || r1a == 'T')) return 0x01;
+  return 0;
+}
+
+void bump (int &dynprogindex) { dynprogindex += (dynprogindex > 0 ? +1 : -1); }
+int quality (double defect_rate) { return defect_rate < 0.003 ? 0 : (defect_rate < 0.014 ? 1 : 2); }	/* dynprog.h:57-58 */
+
+void compute_bands (int &lband, int &uband, int rlength, int glength, int extraband, bool widebandp) {	/* dynprog.c:1246 */
+  if (!widebandp) { lband = extraband; uband = extraband; }
+  else if (glength >= rlength) { uband = glength - rlength + extraband; lband = extraband; }
+  else { lband = rlength - glength + extraband; uband = extraband; }
+}
+
+struct Call {
+  int mode = 0;
+  bool done = false;		/* resolved on the host */
+  int box = -1;			/* index into the device batch */
+  bool isnull = true;
+  int iout[10]; double dout[2];
+  std::vector<gmapdp_pair> pairs;	/* head first */
+  /* copies of the caller's sequences: forward arrays */
+  std::string q, quc, qR, qRuc, gL, gLa, gR, gRa;
+  std::vector<double> lp, rp;
+  int rlenL = 0, rlenR = 0, glenL = 0, glenR = 0;
+  int roffset = 0, goffset = 0, roffsetR = 0, goffsetR = 0;
+  int endalign = 0, introntype_in = 0;
+  bool require_pos = false, end5 = false;
+  Call () { for (int i = 0; i < 10; i++) iout[i] = 0; dout[0] = dout[1] = 0.0; }
+};
+
+}  // namespace
+
+struct gmapdp_batch {
+  gmapdp_ctx *ctx;
+  int max_rlength, max_glength;
+  std::vector<Call> calls;
+  std::vector<gmapdp_box> boxes;
+  std::vector<int> box_call;
+  std::vector<uint8_t> seqpool;
+  std::vector<double> probpool;
+  std::vector<gmapdp_result> results;
+  std::vector<uint32_t> script;
+  size_t script_used = 0;
+  long cells = 0;
+  int count_mismatch = 0;
+  std::string err;
+  bool uploaded = false;
+
+  int add_bytes (const char *p, int n) {
+    int off = (int) seqpool.size();
+    seqpool.insert(seqpool.end(),(const uint8_t *) p,(const uint8_t *) p + n);
+    while (seqpool.size() & 3) seqpool.push_back(0);
+    return off;
+  }
+};
+
+extern "C" void GmapDP_maxlengths (int *max_rlength, int *max_glength, int maxlookback, int extraquerygap, int maxpeelback,
+				   int extramaterial_end, int extramaterial_paired) {
+  *max_rlength = std::max(maxlookback + maxpeelback,500);
+  *max_glength = std::max(*max_rlength + extraquerygap + std::max(extramaterial_end,extramaterial_paired),2000);
+}
+
+extern "C" gmapdp_batch *GmapDP_batch_new (gmapdp_ctx *ctx, int max_rlength, int max_glength) {
+  gmapdp_batch *b = new gmapdp_batch();
+  b->ctx = ctx; b->max_rlength = max_rlength; b->max_glength = max_glength;
+  return b;
+}
+extern "C" void GmapDP_batch_free (gmapdp_batch *b) { delete b; }
+extern "C" void GmapDP_batch_clear (gmapdp_batch *b) {
+  b->calls.clear(); b->boxes.clear(); b->box_call.clear(); b->seqpool.clear(); b->probpool.clear();
+  b->results.clear(); b->script.clear(); b->script_used = 0; b->cells = 0; b->uploaded = false; b->err.clear();
+}
+extern "C" int GmapDP_batch_ncalls (const gmapdp_batch *b) { return (int) b->calls.size(); }
+extern "C" int GmapDP_batch_nboxes (const gmapdp_batch *b) { return (int) b->boxes.size(); }
+extern "C" long GmapDP_batch_cells (const gmapdp_batch *b) { return b->cells; }
+extern "C" const char *GmapDP_batch_error (const gmapdp_batch *b) { return b->err.c_str(); }
+extern "C" size_t GmapDP_batch_h2d_bytes (const gmapdp_batch *b) {
+  return b->boxes.size() * (sizeof(gmapdp_box) + sizeof(int)) + b->seqpool.size() + b->probpool.size() * sizeof(double);
+}
+extern "C" size_t GmapDP_batch_d2h_bytes (const gmapdp_batch *b) {
+  return b->boxes.size() * sizeof(gmapdp_result) + b->script_used * sizeof(uint32_t) + sizeof(unsigned long long);
+}
+
+static gmapdp_box blank_box () { gmapdp_box x; memset(&x,0,sizeof(x)); return x; }
+
+static void diag_only (Pushed &l, const Side &sd, int dpi, Counts &n, int r, int c) { Replayer rp(l,sd,dpi,n); rp.diag(r,c); }
+
+/* ------------------------------------------------------------------------------------------------ */
+extern "C" int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char *rsequence, const char *rsequenceuc,
+				  int rlength, int glength, int roffset, int goffset,
+				  const char *gsequence, const char *gsequence_alt, int jump_late_p,
+				  int extraband_single, int widebandp, double defect_rate) {
+  static const int opens[3] = {-8,-7,-6}, extends[3] = {-3,-2,-1};		/* dynprog.h:59-68 */
+  b->calls.emplace_back();
+  Call &c = b->calls.back();
+  const int id = (int) b->calls.size() - 1;
+  c.mode = GMAPDP_SINGLE;
+  c.iout[0] = dynprogindex;
+  const int qual = quality(defect_rate), mt = qual;
+  if (rlength <= 0 || glength <= 0 || rlength > b->max_rlength || glength > b->max_glength) {
+    c.iout[1] = NEG_INFINITY_32; bump(c.iout[0]); c.done = true; return id;
+  }
+  if (gsequence[0] == '\0') { c.iout[1] = NEG_INFINITY_32; c.done = true; return id; }
+  c.q.assign(rsequence,rlength); c.quc.assign(rsequenceuc,rlength);
+  c.gL.assign(gsequence,glength); c.gLa.assign(gsequence_alt,glength);
+  c.rlenL = rlength; c.glenL = glength; c.roffset = roffset; c.goffset = goffset;
+
+  if (glength == rlength) {			/* single_gap_simple */
+    Pushed l; Counts n;
+    Side sd = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),roffset,goffset,false};
+    for (int r = 1; r <= rlength; r++) diag_only(l,sd,dynprogindex,n,r,r);
+    if (n.nmismatches <= 1 && !l.empty()) {
+      c.iout[1] = n.score; c.iout[2] = n.nmatches; c.iout[3] = n.nmismatches; c.iout[4] = c.iout[5] = 0;
+      bump(c.iout[0]);
+      c.pairs.assign(l.rbegin(),l.rend()); c.isnull = false; c.done = true;
+      return id;
+    }
+  }
+
+  gmapdp_box x = blank_box();
+  int lband, uband;
+  compute_bands(lband,uband,rlength,glength,extraband_single,widebandp != 0);
+  const bool use8 = rlength < tables().use8p[mt] && glength < tables().use8p[mt];		/* && : dynprog_single.c:596 */
+  x.mode = GMAPDP_SINGLE;
+  x.flags = (jump_late_p ? GMAPDP_F_LATE_L : 0) | (use8 ? GMAPDP_F_USE8 : 0);
+  x.rlenL = x.rlenR = rlength; x.glenL = x.glenR = glength;
+  x.mismatchtype = (int8_t) mt; x.open = (int8_t) opens[qual]; x.extend = (int8_t) extends[qual];
+  x.lbandL = x.lbandR = (int16_t) lband; x.ubandL = x.ubandR = (int16_t) uband;
+  x.qL_off = x.qR_off = b->add_bytes(c.quc.data(),rlength);
+  x.gL_off = x.gR_off = b->add_bytes(c.gL.data(),glength);
+  x.gLalt_off = x.gRalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
+  b->cells += gdp_cells_full(rlength,glength,lband,uband);
+  c.box = (int) b->boxes.size();
+  b->boxes.push_back(x); b->box_call.push_back(id);
+  return id;
+}
+
+static int end_gap (gmapdp_batch *b, bool end5, int dynprogindex, const char *rseq, const char *rsequc,
+		    int rlength, int glength, int roffset, int goffset, const char *gseq, const char *galt,
+		    int jump_late_p, int extraband_end, double defect_rate, int endalign, int require_pos_score_p) {
+  static const int opens[3] = {-10,-8,-6}, extends[3] = {-2,-2,-2};		/* dynprog_end.c:89-95 */
+  b->calls.emplace_back();
+  Call &c = b->calls.back();
+  const int id = (int) b->calls.size() - 1;
+  c.mode = end5 ? GMAPDP_END5 : GMAPDP_END3;
+  c.end5 = end5; c.endalign = endalign; c.require_pos = require_pos_score_p != 0;
+  c.iout[0] = dynprogindex;
+  const int qual = quality(defect_rate);
+  /* early exits leave traceback_score = 0 and the counts = 0, dynprogindex untouched */
+  if (rlength <= 0) { c.done = true; return id; }
+  if (endalign != GMAPDP_QUERYEND_NOGAPS && rlength > b->max_rlength) rlength = b->max_rlength;
+  if (end5 && goffset < 0) { c.done = true; return id; }
+  if (glength <= 0) { c.done = true; return id; }
+  if (endalign != GMAPDP_QUERYEND_NOGAPS && glength > b->max_glength) glength = b->max_glength;
+  if (gseq[0] == '\0') { c.done = true; return id; }
+
+  /* forward copies.  5': the query is read backwards from rseq[0]; the segment array's LAST glength
+     chars are the ones the reference fetches after chopping (it fetches leftwards from rev_goffset). */
+  if (end5) { c.q.assign(rseq - (rlength - 1),rlength); c.quc.assign(rsequc - (rlength - 1),rlength); }
+  else { c.q.assign(rseq,rlength); c.quc.assign(rsequc,rlength); }
+  c.gL.assign(gseq,glength); c.gLa.assign(galt,glength);
+  c.rlenL = rlength; c.glenL = glength; c.roffset = roffset; c.goffset = goffset;
+
+  if (endalign == GMAPDP_QUERYEND_NOGAPS) {
+    /* find_best_endpoint_to_queryend_nogaps + traceback_nogaps: no fill */
+    int best = std::min(rlength,glength);
+    Pushed l; Counts n;
+    Side sd;
+    if (end5) sd = Side{c.q.data() + rlength - 1,c.quc.data() + rlength - 1,c.gL.data() + glength - 1,c.gLa.data() + glength - 1,roffset,goffset,true};
+    else sd = Side{c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),roffset,goffset,false};
+    for (int r = best, cc = best; r > 0 && cc > 0; r--, cc--) diag_only(l,sd,dynprogindex,n,r,cc);
+    c.iout[1] = n.score; c.iout[2] = n.nmatches; c.iout[3] = n.nmismatches;
+    /* no (nmatches+1 < nmismatches) filter for NOGAPS; strip leading INDEL_COMP pairs: there are none */
+    bump(c.iout[0]);
+    if (!l.empty()) {
+      c.isnull = false;
+      if (end5) c.pairs.assign(l.rbegin(),l.rend()); else c.pairs.assign(l.begin(),l.end());
+    }
+    c.done = true;
+    return id;
+  }
+  if (require_pos_score_p) {
+    /* the reference still runs the fills, then skips the traceback because *traceback_score was just
+       zeroed (dynprog_end.c:1558-1574): the result does not depend on the fill, so no box is queued */
+    bump(c.iout[0]); c.done = true; return id;
+  }
+
+  gmapdp_box x = blank_box();
+  int lband, uband;
+  const bool wide = (endalign != GMAPDP_QUERYEND_INDELS);
+  compute_bands(lband,uband,rlength,glength,extraband_end,wide);
+  const int mt = 3;	/* ENDQ */
+  const bool use8 = rlength < tables().use8p[mt] || glength < tables().use8p[mt];		/* || : dynprog_end.c:1414 */
+  const bool late = end5 ? !jump_late_p : (jump_late_p != 0);
+  x.mode = c.mode;
+  x.flags = (late ? GMAPDP_F_LATE_L : 0) | (use8 ? GMAPDP_F_USE8 : 0) | (wide ? 0 : GMAPDP_F_LASTROW);
+  x.rlenL = x.rlenR = rlength; x.glenL = x.glenR = glength;
+  x.mismatchtype = (int8_t) mt; x.open = (int8_t) opens[qual]; x.extend = (int8_t) extends[qual];
+  x.lbandL = x.lbandR = (int16_t) lband; x.ubandL = x.ubandR = (int16_t) uband;
+  x.qL_off = x.qR_off = b->add_bytes(c.quc.data(),rlength);
+  x.gL_off = x.gR_off = b->add_bytes(c.gL.data(),glength);
+  x.gLalt_off = x.gRalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
+  x.revmask = end5 ? 1 : 0;
+  b->cells += gdp_cells_tri(rlength,glength,uband) + gdp_cells_tri(glength,rlength,lband);
+  c.box = (int) b->boxes.size();
+  b->boxes.push_back(x); b->box_call.push_back(id);
+  return id;
+}
+
+extern "C" int GmapDP_end5_gap (gmapdp_batch *b, int dynprogindex, const char *rev_rsequence, const char *rev_rsequenceuc,
+				int rlength, int glength, int rev_roffset, int rev_goffset,
+				const char *rev_gsequence, const char *rev_gsequence_alt, int jump_late_p,
+				int extraband_end, double defect_rate, int endalign, int require_pos_score_p) {
+  return end_gap(b,true,dynprogindex,rev_rsequence,rev_rsequenceuc,rlength,glength,rev_roffset,rev_goffset,
+		 rev_gsequence,rev_gsequence_alt,jump_late_p,extraband_end,defect_rate,endalign,require_pos_score_p);
+}
+extern "C" int GmapDP_end3_gap (gmapdp_batch *b, int dynprogindex, const char *rsequence, const char *rsequenceuc,
+				int rlength, int glength, int roffset, int goffset,
+				const char *gsequence, const char *gsequence_alt, int jump_late_p,
+				int extraband_end, double defect_rate, int endalign, int require_pos_score_p) {
+  return end_gap(b,false,dynprogindex,rsequence,rsequenceuc,rlength,glength,roffset,goffset,
+		 gsequence,gsequence_alt,jump_late_p,extraband_end,defect_rate,endalign,require_pos_score_p);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+extern "C" int GmapDP_genome_gap (gmapdp_batch *b, int dynprogindex, const char *rsequence, const char *rsequenceuc,
+				  int rlength, int glengthL, int glengthR, int roffset, int goffsetL, int rev_goffsetR,
+				  const char *gsequenceL, const char *gsequenceL_alt,
+				  const char *rev_gsequenceR, const char *rev_gsequenceR_alt,
+				  const double *left_probabilities, const double *right_probabilities,
+				  int cdna_direction, int jump_late_p, int extraband_paired, double defect_rate,
+				  int maxpeelback, int halfp, int finalp) {
+  static const int opens[3] = {-8,-7,-6}, extends[3] = {-3,-2,-1};	/* PAIRED_* == SINGLE_*, dynprog.h:59-75 */
+  (void) maxpeelback;
+  b->calls.emplace_back();
+  Call &c = b->calls.back();
+  const int id = (int) b->calls.size() - 1;
+  c.mode = GMAPDP_GENOME;
+  int *dynprogindex_p = &c.iout[0], *new_left = &c.iout[1], *new_right = &c.iout[2], *tbscore = &c.iout[3];
+  int *nmatches = &c.iout[4], *nmismatches = &c.iout[5], *exonhead = &c.iout[8], *introntype = &c.iout[9];
+  /* out-parameters the reference may leave unwritten keep the caller's sentinel */
+  for (int k = 1; k < 10; k++) c.iout[k] = GMAPDP_UNSET;
+  *dynprogindex_p = dynprogindex;
+  c.iout[4] = c.iout[5] = c.iout[6] = c.iout[7] = 0; c.dout[0] = c.dout[1] = 0.0; *introntype = 0;
+  if (rlength <= 1) { *tbscore = NEG_INFINITY_32; c.done = true; return id; }
+  const int qual = quality(defect_rate), mt = qual;
+  if (rlength > b->max_rlength || glengthL > b->max_glength || glengthR > b->max_glength) {
+    *new_left = goffsetL - 1; *new_right = rev_goffsetR + 1; *exonhead = roffset + rlength - 1;
+    bump(*dynprogindex_p); *tbscore = NEG_INFINITY_32; c.done = true; return id;
+  }
+  if (gsequenceL[0] == '\0' || rev_gsequenceR[0] == '\0') { *tbscore = NEG_INFINITY_32; c.done = true; return id; }
+
+  c.q.assign(rsequence,rlength); c.quc.assign(rsequenceuc,rlength);
+  c.gL.assign(gsequenceL,glengthL); c.gLa.assign(gsequenceL_alt,glengthL);
+  c.gR.assign(rev_gsequenceR,glengthR); c.gRa.assign(rev_gsequenceR_alt,glengthR);
+  c.lp.assign(left_probabilities,left_probabilities + std::max(glengthL - 1,0));
+  c.rp.assign(right_probabilities,right_probabilities + std::max(glengthR - 1,0));
+  c.rlenL = rlength; c.glenL = glengthL; c.glenR = glengthR; c.roffset = roffset; c.goffset = goffsetL; c.goffsetR = rev_goffsetR;
+  const int rev_roffset = roffset + rlength - 1;
+  const GdpHostTables &T = tables();
+
+  if (!finalp && defect_rate < 0.014) {
+    /* genome_gap_simple (prelim intron scores; no known splice sites on this path) */
+    const GdpTables &dt = dev_tables();
+    const int *isc = dt.isc[cdna_direction > 0 ? 0 : (cdna_direction < 0 ? 1 : 2)][0];
+    auto pairscore = [&](char q, char g, char ga) { return (int) std::max(T.pd[mt][q & 127][g & 127],T.pd[mt][q & 127][ga & 127]); };
+    const char *ruc = c.quc.data(), *gl = c.gL.data(), *gla = c.gLa.data();
+    const char *rgr = c.gR.data() + glengthR - 1, *rgra = c.gRa.data() + glengthR - 1, *rruc = ruc + rlength - 1;
+    int scoreR = 0, scoreL = 0, bestscore = 0, bestscoreI = 0, bestrL = 0, bestrR = 0, itype = 0;
+    for (int rR = 1; rR < rlength; rR++) scoreR += pairscore(rruc[1-rR],rgr[1-rR],rgra[1-rR]);
+    for (int rL = 1, rR = rlength - 1; rL < rlength; rL++, rR--) {
+      scoreL += pairscore(ruc[rL-1],gl[rL-1],gla[rL-1]);
+      const int ldi = left_dinucl(gl[rL],gla[rL],gl[rL+1],gla[rL+1]);
+      const int rdi = right_dinucl(rgr[-rR-1],rgra[-rR-1],rgr[-rR],rgra[-rR]);
+      itype = ldi & rdi;
+      const int scoreI = itype ? isc[31 - __builtin_clz((unsigned) itype)] : 0;
+      int score;
+      if (itype != 0 && (score = scoreL + scoreI + scoreR) >= bestscore) {
+	bestscore = score; bestscoreI = scoreI; bestrL = rL; bestrR = rR; *introntype = itype;
+      }
+      scoreR -= pairscore(rruc[1-rR],rgr[1-rR],rgra[1-rR]);
+    }
+    const int finalscore = halfp ? bestscore - bestscoreI / 2 : bestscore;
+    bool result = finalscore > 0;
+    if (result) {
+      c.dout[0] = prob_at(c.lp,bestrL); c.dout[1] = prob_at(c.rp,bestrR);		/* get_splicesite_probs at (bestrL, bestrR) */
+      if (c.dout[0] < 0.90 || c.dout[1] < 0.90) result = false;
+    }
+    *tbscore = *nmatches = *nmismatches = 0;
+    if (result) {
+      Pushed l; Counts n;
+      Side sl = {c.q.data(),c.quc.data(),gl,gla,roffset,goffsetL,false};
+      for (int r = 1; r <= bestrL; r++) diag_only(l,sl,dynprogindex,n,r,r);
+      *new_left = goffsetL + (bestrL - 1);
+      *new_right = *exonhead = rev_goffsetR - (bestrR - 1);
+      gmapdp_pair &gp = push_gapholder(l,0,(*new_right) - (*new_left) - 1);
+      gp.introntype = itype;		/* the LAST iteration's introntype (dynprog_genome.c:3230) */
+      gp.donor_prob = c.dout[0]; gp.acceptor_prob = c.dout[1];
+      Side sr = {c.q.data() + rlength - 1,c.quc.data() + rlength - 1,rgr,rgra,rev_roffset,rev_goffsetR,true};
+      for (int r = bestrR; r > 0; r--) diag_only(l,sr,dynprogindex,n,r,r);
+      *tbscore = n.score; *nmatches = n.nmatches; *nmismatches = n.nmismatches;
+      bump(*dynprogindex_p);
+      c.pairs.assign(l.rbegin(),l.rend()); c.isnull = false; c.done = true;
+      return id;
+    }
+  }
+  c.introntype_in = *introntype;
+
+  gmapdp_box x = blank_box();
+  int lbandL, ubandL, lbandR, ubandR;
+  compute_bands(lbandL,ubandL,rlength,glengthL,extraband_paired,true);
+  compute_bands(lbandR,ubandR,rlength,glengthR,extraband_paired,true);
+  const bool use8 = rlength < T.use8p[mt] || (glengthL < T.use8p[mt] && glengthR < T.use8p[mt]);	/* dynprog_genome.c:3503 */
+  x.mode = GMAPDP_GENOME;
+  x.flags = (jump_late_p ? GMAPDP_F_LATE_L : GMAPDP_F_LATE_R) | (use8 ? GMAPDP_F_USE8 : 0) |
+    (finalp ? GMAPDP_F_FINALP : 0) | (halfp ? GMAPDP_F_HALFP : 0);
+  x.rlenL = x.rlenR = rlength; x.glenL = glengthL; x.glenR = glengthR;
+  x.mismatchtype = (int8_t) mt; x.open = (int8_t) opens[qual]; x.extend = (int8_t) extends[qual];
+  x.cdna_direction = (int8_t) cdna_direction;
+  x.lbandL = (int16_t) lbandL; x.ubandL = (int16_t) ubandL; x.lbandR = (int16_t) lbandR; x.ubandR = (int16_t) ubandR;
+  x.qL_off = x.qR_off = b->add_bytes(c.quc.data(),rlength);
+  x.gL_off = b->add_bytes(c.gL.data(),glengthL);
+  x.gLalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glengthL);
+  x.gR_off = b->add_bytes(c.gR.data(),glengthR);
+  x.gRalt_off = (c.gRa == c.gR) ? x.gR_off : b->add_bytes(c.gRa.data(),glengthR);
+  x.probL_off = (int) b->probpool.size(); b->probpool.insert(b->probpool.end(),c.lp.begin(),c.lp.end()); b->probpool.push_back(0.0);
+  x.probR_off = (int) b->probpool.size(); b->probpool.insert(b->probpool.end(),c.rp.begin(),c.rp.end()); b->probpool.push_back(0.0);
+  x.offdiff = rev_goffsetR - goffsetL;
+  x.revmask = 2;
+  b->cells += gdp_cells_tri(rlength,glengthL,ubandL) + gdp_cells_tri(glengthL,rlength,lbandL) +
+    gdp_cells_tri(rlength,glengthR,ubandR) + gdp_cells_tri(glengthR,rlength,lbandR);
+  c.box = (int) b->boxes.size();
+  b->boxes.push_back(x); b->box_call.push_back(id);
+  return id;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+extern "C" int GmapDP_cdna_gap (gmapdp_batch *b, int dynprogindex,
+				const char *rsequenceL, const char *rsequence_ucL,
+				const char *rev_rsequenceR, const char *rev_rsequence_ucR,
+				int rlengthL, int rlengthR, int glength, int roffsetL, int rev_roffsetR, int goffset,
+				const char *gsequence, const char *gsequence_alt,
+				const char *rev_gsequence, const char *rev_gsequence_alt,
+				int jump_late_p, int extraband_paired, double defect_rate) {
+  b->calls.emplace_back();
+  Call &c = b->calls.back();
+  const int id = (int) b->calls.size() - 1;
+  c.mode = GMAPDP_CDNA;
+  c.iout[0] = dynprogindex; c.iout[1] = GMAPDP_UNSET; c.iout[2] = 0;
+  if (glength <= 1) { c.done = true; return id; }
+  const int mt = quality(defect_rate);
+  if (glength > b->max_glength || rlengthR > b->max_rlength || rlengthL > b->max_rlength) { bump(c.iout[0]); c.done = true; return id; }
+  if (gsequence[0] == '\0' || rev_gsequence[0] == '\0') { c.done = true; return id; }
+  const GdpHostTables &T = tables();
+  /* rsequenceL and rev_rsequenceR address the same query: keep the whole span [roffsetL, rev_roffsetR] of the raw chars,
+     which the insert-pairs loop (dynprog_cdna.c:1010-1014) indexes past rlengthL */
+  c.q.assign(rsequenceL,std::max(rlengthL,rev_roffsetR - roffsetL + 1)); c.quc.assign(rsequence_ucL,rlengthL);
+  c.qR.assign(rev_rsequenceR - (rlengthR - 1),rlengthR); c.qRuc.assign(rev_rsequence_ucR - (rlengthR - 1),rlengthR);
+  c.gL.assign(gsequence,glength); c.gLa.assign(gsequence_alt,glength);
+  c.gR.assign(rev_gsequence,glength); c.gRa.assign(rev_gsequence_alt,glength);
+  c.rlenL = rlengthL; c.rlenR = rlengthR; c.glenL = c.glenR = glength;
+  c.roffset = roffsetL; c.roffsetR = rev_roffsetR; c.goffset = goffset;
+
+  gmapdp_box x = blank_box();
+  int lbandL, ubandL, lbandR, ubandR;
+  compute_bands(lbandL,ubandL,rlengthL,glength,extraband_paired,true);
+  compute_bands(lbandR,ubandR,rlengthR,glength,extraband_paired,true);
+  const bool use8 = glength < T.use8p[mt] || (rlengthL < T.use8p[mt] && rlengthR <= T.use8p[mt]);	/* stray <= : dynprog_cdna.c:909 */
+  x.mode = GMAPDP_CDNA;
+  x.flags = (jump_late_p ? (GMAPDP_F_LATE_L | GMAPDP_F_BRIDGE_LATE) : GMAPDP_F_LATE_R) | (use8 ? GMAPDP_F_USE8 : 0);
+  x.rlenL = rlengthL; x.rlenR = rlengthR; x.glenL = x.glenR = glength;
+  x.mismatchtype = (int8_t) mt; x.open = -10; x.extend = -7;			/* CDNA_OPEN / CDNA_EXTEND, dynprog_cdna.c:32-38 */
+  x.lbandL = (int16_t) lbandL; x.ubandL = (int16_t) ubandL; x.lbandR = (int16_t) lbandR; x.ubandR = (int16_t) ubandR;
+  x.qL_off = b->add_bytes(c.quc.data(),rlengthL);
+  x.qR_off = b->add_bytes(c.qRuc.data(),rlengthR);
+  x.gL_off = b->add_bytes(c.gL.data(),glength);
+  x.gLalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
+  x.gR_off = (c.gR == c.gL) ? x.gL_off : b->add_bytes(c.gR.data(),glength);
+  x.gRalt_off = (c.gRa == c.gR) ? x.gR_off : b->add_bytes(c.gRa.data(),glength);
+  x.offdiff = rev_roffsetR - roffsetL;
+  x.revmask = 2;
+  b->cells += gdp_cells_tri(rlengthL,glength,ubandL) + gdp_cells_tri(glength,rlengthL,lbandL) +
+    gdp_cells_tri(rlengthR,glength,ubandR) + gdp_cells_tri(glength,rlengthR,lbandR);
+  c.box = (int) b->boxes.size();
+  b->boxes.push_back(x); b->box_call.push_back(id);
+  return id;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Completion: replay the device results
+ * ---------------------------------------------------------------------------------------------- */
+static void check_counts (gmapdp_batch *b, const gmapdp_result &r, const Counts &n) {
+  if (r.tb_score != n.score || r.nmatches != n.nmatches || r.nmismatches != n.nmismatches || r.nopens != n.nopens || r.nindels != n.nindels)
+    b->count_mismatch++;
+}
+
+static void finish_call (gmapdp_batch *b, Call &c) {
+  const gmapdp_result &r = b->results[c.box];
+  const uint32_t *ops = b->script.data() + r.script_off;
+  const int dpi = c.iout[0];
+  if (c.mode == GMAPDP_SINGLE) {
+    Pushed l; Counts n;
+    Side sd = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
+    Replayer(l,sd,dpi,n).run(0,c.rlenL,c.glenL,ops,r.script_lenA);
+    check_counts(b,r,n);
+    c.iout[1] = n.score; c.iout[2] = n.nmatches; c.iout[3] = n.nmismatches; c.iout[4] = n.nopens; c.iout[5] = n.nindels;
+    bump(c.iout[0]);
+    c.pairs.assign(l.begin(),l.end());		/* List_reverse of the consed list = push order */
+    c.isnull = l.empty();
+
+  } else if (c.mode == GMAPDP_END5 || c.mode == GMAPDP_END3) {
+    Pushed l; Counts n;
+    Side sd;
+    if (c.end5) sd = Side{c.q.data() + c.rlenL - 1,c.quc.data() + c.rlenL - 1,c.gL.data() + c.glenL - 1,c.gLa.data() + c.glenL - 1,c.roffset,c.goffset,true};
+    else sd = Side{c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
+    Replayer(l,sd,dpi,n).run(r.bestcL >= r.bestrL ? 1 : 2,r.bestrL,r.bestcL,ops,r.script_lenA);
+    check_counts(b,r,n);
+    c.iout[1] = n.score; c.iout[2] = n.nmatches; c.iout[3] = n.nmismatches; c.iout[4] = n.nopens; c.iout[5] = n.nindels;
+    if ((c.endalign == GMAPDP_QUERYEND_GAP || c.endalign == GMAPDP_BEST_LOCAL) && (n.nmatches + 1) < n.nmismatches) {
+      c.iout[1] = 0; l.clear();
+    } else {
+      size_t k = 0;
+      while (k < l.size() && l[k].comp == COMP_INDEL) k++;	/* leading indels of the reversed list */
+      l.erase(l.begin(),l.begin() + k);
+    }
+    bump(c.iout[0]);
+    c.isnull = l.empty();
+    if (c.end5) c.pairs.assign(l.rbegin(),l.rend()); else c.pairs.assign(l.begin(),l.end());
+
+  } else if (c.mode == GMAPDP_GENOME) {
+    if (r.status != 0) { c.iout[3] = -100; c.isnull = true; return; }
+    const int rlength = c.rlenL, rev_roffset = c.roffset + rlength - 1;
+    const int bestrL = r.bestrL, bestrR = r.bestrR, bestcL = r.bestcL, bestcR = r.bestcR;
+    c.dout[0] = prob_at(c.lp,bestcL); c.dout[1] = prob_at(c.rp,bestcR);
+    c.iout[1] = c.goffset + (bestcL - 1);
+    c.iout[2] = c.goffsetR - (bestcR - 1);
+    c.iout[8] = rev_roffset - (bestrR - 1);
+    Pushed l; Counts n;
+    Side sr = {c.q.data() + rlength - 1,c.quc.data() + rlength - 1,c.gR.data() + c.glenR - 1,c.gRa.data() + c.glenR - 1,rev_roffset,c.goffsetR,true};
+    Replayer(l,sr,dpi,n).run(bestcR >= bestrR ? 1 : 2,bestrR,bestcR,ops,r.script_lenA);
+    std::reverse(l.begin(),l.end());
+    gmapdp_pair &gp = push_gapholder(l,(rev_roffset - bestrR) - (c.roffset + bestrL) + 1,c.iout[2] - c.iout[1] - 1);
+    gp.introntype = c.introntype_in; gp.donor_prob = c.dout[0]; gp.acceptor_prob = c.dout[1];
+    Side sl = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
+    Replayer(l,sl,dpi,n).run(bestcL >= bestrL ? 1 : 2,bestrL,bestcL,ops + r.script_lenA,r.script_lenB);
+    check_counts(b,r,n);
+    c.iout[3] = n.score; c.iout[4] = n.nmatches; c.iout[5] = n.nmismatches; c.iout[6] = n.nopens; c.iout[7] = n.nindels;
+    if (l.size() == 1) l.clear();
+    bump(c.iout[0]);
+    std::vector<gmapdp_pair> hf(l.rbegin(),l.rend());
+    if (maxnegscore_headfirst(hf) < -10) { c.iout[3] = -100; c.isnull = true; return; }
+    c.pairs.assign(l.begin(),l.end());
+    c.isnull = l.empty();
+
+  } else {	/* cdna */
+    const int bestrL = r.bestrL, bestrR = r.bestrR, bestcL = r.bestcL, bestcR = r.bestcR;
+    const int rev_goffset = c.goffset + c.glenL - 1;
+    Pushed l; Counts n;
+    Side sr = {c.qR.data() + c.rlenR - 1,c.qRuc.data() + c.rlenR - 1,c.gR.data() + c.glenL - 1,c.gRa.data() + c.glenL - 1,c.roffsetR,rev_goffset,true};
+    Replayer(l,sr,dpi,n).run(bestcR >= bestrR ? 1 : 2,bestrR,bestcR,ops,r.script_lenA);
+    std::reverse(l.begin(),l.end());
+    const int queryjump = (c.roffsetR - bestrR) - (c.roffset + bestrL) + 1;
+    const int genomejump = (rev_goffset - bestcR) - (c.goffset + bestcL) + 1;
+    if (queryjump == INSERT_PAIRS && genomejump == INSERT_PAIRS) {
+      for (int k = c.roffsetR - bestrR; k >= c.roffset + bestrL; k--)
+	push_pair(l,k,rev_goffset - bestcR + 1,c.q[k - c.roffset],COMP_SHORTGAP,' ',' ',dpi);
+      for (int k = rev_goffset - bestcR; k >= c.goffset + bestcL; k--)
+	push_pair(l,c.roffset + bestrL,k,' ',COMP_SHORTGAP,c.gL[k - c.goffset],c.gLa[k - c.goffset],dpi);
+    } else {
+      push_gapholder(l,queryjump,genomejump);
+      c.iout[2] = 1;
+    }
+    Side sl = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
+    Replayer(l,sl,dpi,n).run(bestcL >= bestrL ? 1 : 2,bestrL,bestcL,ops + r.script_lenA,r.script_lenB);
+    check_counts(b,r,n);
+    c.iout[1] = n.score;
+    if (l.size() == 1) l.clear();
+    bump(c.iout[0]);
+    c.pairs.assign(l.begin(),l.end());
+    c.isnull = l.empty();
+  }
+}
+
+static int finish_all (gmapdp_batch *b) {
+  for (size_t k = 0; k < b->results.size(); k++) b->results[k].cells = 0;
+  for (size_t i = 0; i < b->calls.size(); i++) {
+    Call &c = b->calls[i];
+    if (!c.done && c.box >= 0) { finish_call(b,c); c.done = true; }
+  }
+  if (b->count_mismatch) { b->err = "device traceback counts disagree with the host replay"; return GMAPDP_ERR_ARG; }
+  return GMAPDP_OK;
+}
+
+extern "C" int GmapDP_batch_upload (gmapdp_batch *b) {
+  if (b->boxes.empty()) { b->uploaded = true; return GMAPDP_OK; }
+  if (!b->ctx) { b->err = "no device context: the DP engine has no CPU fallback"; return GMAPDP_ERR_CUDA; }
+  int rc = gmapdp_upload(b->ctx,b->boxes.data(),(int) b->boxes.size(),b->seqpool.data(),b->seqpool.size(),
+			 b->probpool.data(),b->probpool.size());
+  if (rc) { b->err = gmapdp_last_error(b->ctx); return rc; }
+  b->uploaded = true;
+  return GMAPDP_OK;
+}
+
+extern "C" int GmapDP_batch_run_resident (gmapdp_batch *b, float *kernel_ms) {
+  if (kernel_ms) *kernel_ms = 0.f;
+  if (b->boxes.empty()) return GMAPDP_OK;
+  if (!b->uploaded) { b->err = "batch not uploaded"; return GMAPDP_ERR_ARG; }
+  int rc = gmapdp_run_resident(b->ctx,kernel_ms);
+  if (rc) b->err = gmapdp_last_error(b->ctx);
+  return rc;
+}
+
+extern "C" int GmapDP_batch_finish (gmapdp_batch *b) {
+  if (!b->boxes.empty()) {
+    size_t need = 0;
+    for (const gmapdp_box &x : b->boxes) need += (size_t) x.rlenL + x.glenL + x.rlenR + x.glenR + 8;
+    b->results.resize(b->boxes.size());
+    b->script.resize(need + 64);
+    int rc = gmapdp_download(b->ctx,b->results.data(),b->script.data(),b->script.size(),&b->script_used);
+    if (rc) { b->err = gmapdp_last_error(b->ctx); return rc; }
+  }
+  return finish_all(b);
+}
+
+extern "C" int GmapDP_batch_run (gmapdp_batch *b) {
+  int rc = GmapDP_batch_upload(b);
+  if (rc) return rc;
+  rc = GmapDP_batch_run_resident(b,NULL);
+  if (rc) return rc;
+  return GmapDP_batch_finish(b);
+}
+
+extern "C" int GmapDP_result (const gmapdp_batch *b, int id, int *iout, double *dout, gmapdp_pair *pairs, int maxpairs) {
+  if (id < 0 || id >= (int) b->calls.size()) return -2;
+  const Call &c = b->calls[id];
+  if (!c.done) return -3;
+  const int ni = (c.mode == GMAPDP_GENOME) ? 10 : (c.mode == GMAPDP_CDNA ? 3 : 6);
+  if (iout) for (int k = 0; k < ni; k++) iout[k] = c.iout[k];
+  if (dout && c.mode == GMAPDP_GENOME) { dout[0] = c.dout[0]; dout[1] = c.dout[1]; }
+  if (c.isnull || c.pairs.empty()) return -1;
+  const int n = (int) c.pairs.size();
+  for (int k = 0; k < n && k < maxpairs; k++) pairs[k] = c.pairs[k];
+  return n;
+}
+
+extern "C" const gmapdp_result *GmapDP_device_result (const gmapdp_batch *b, int id) {
+  if (id < 0 || id >= (int) b->calls.size()) return NULL;
+  const Call &c = b->calls[id];
+  if (c.box < 0 || (size_t) c.box >= b->results.size()) return NULL;
+  return &b->results[c.box];
+}

@@ -1,0 +1,189 @@
+"""ctypes binding of libgmapdp_b200.so: :class:`Engine` = one device context (``gmapdp_ctx``),
+:class:`Batch` = the batch form of the five reference entry points (``gmapdp_shim.h``)."""
+import ctypes as C
+import os
+
+from .build import LIB
+
+MODE_IDS = {"single": 0, "genome": 1, "cdna": 2, "end5": 3, "end3": 4}
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Pair(C.Structure):
+    _fields_ = [("querypos", C.c_int), ("genomepos", C.c_int), ("queryjump", C.c_int),
+                ("genomejump", C.c_int), ("dynprogindex", C.c_int), ("introntype", C.c_int),
+                ("gapp", C.c_int), ("cdna", C.c_char), ("comp", C.c_char), ("genome", C.c_char),
+                ("genomealt", C.c_char), ("donor_prob", C.c_double), ("acceptor_prob", C.c_double)]
+
+
+class DeviceResult(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("status", "finalscore", "bestrL", "bestcL", "bestrR", "bestcR", "tb_score",
+                                         "nmatches", "nmismatches", "nopens", "nindels", "script_off", "script_lenA",
+                                         "script_lenB", "cells", "reserved")]
+
+
+_lib = None
+
+
+def load_library():
+    """Loads the native library; raises if it has not been built (``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise EngineError("native library %s is missing: run __graft_entry__.build() (nvcc, sm_100a)" % LIB)
+        lib = C.CDLL(LIB)
+        lib.gmapdp_last_error.restype = C.c_char_p
+        lib.gmapdp_launch_count.restype = C.c_long
+        lib.GmapDP_batch_new.restype = C.c_void_p
+        lib.GmapDP_batch_error.restype = C.c_char_p
+        lib.GmapDP_batch_cells.restype = C.c_long
+        lib.GmapDP_batch_h2d_bytes.restype = C.c_size_t
+        lib.GmapDP_batch_d2h_bytes.restype = C.c_size_t
+        lib.GmapDP_device_result.restype = C.POINTER(DeviceResult)
+        for fn in ("gmapdp_destroy", "gmapdp_last_error", "gmapdp_launch_count", "gmapdp_device_info"):
+            getattr(lib, fn).argtypes = None
+        _lib = lib
+    return _lib
+
+
+def _b(s):
+    return s if isinstance(s, bytes) else s.encode("latin1")
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        rc = self.lib.gmapdp_create(C.byref(self.ctx), int(device))
+        if rc != 0:
+            msg = self.lib.gmapdp_last_error(self.ctx).decode() if self.ctx else "gmapdp_create failed"
+            raise EngineError(msg)
+        self.device = device
+
+    def close(self):
+        if self.ctx:
+            self.lib.gmapdp_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def launch_count(self):
+        return self.lib.gmapdp_launch_count(self.ctx)
+
+    def device_info(self):
+        sm, grid, bt = C.c_int(), C.c_int(), C.c_int()
+        self.lib.gmapdp_device_info(self.ctx, C.byref(sm), C.byref(grid), C.byref(bt))
+        return {"sm_count": sm.value, "grid_blocks": grid.value, "block_threads": bt.value}
+
+    def batch(self, max_rlength=2000, max_glength=2030):
+        return Batch(self, max_rlength, max_glength)
+
+
+class Batch:
+    """Queue calls with add(box) (box dicts as produced by tests/dpgen.py), run(), then result(id)."""
+    MAXPAIRS = 12000
+
+    def __init__(self, engine, max_rlength, max_glength):
+        self.e = engine
+        self.lib = engine.lib
+        self.h = C.c_void_p(self.lib.GmapDP_batch_new(engine.ctx, max_rlength, max_glength))
+        self.buf = (Pair * self.MAXPAIRS)()
+        self._keep = []
+
+    def free(self):
+        if self.h:
+            self.lib.GmapDP_batch_free(self.h)
+            self.h = C.c_void_p()
+
+    def clear(self):
+        self.lib.GmapDP_batch_clear(self.h)
+        self._keep = []
+
+    def add(self, box):
+        m = box["mode"]
+        q = _b(box["queryseq"])
+        quc = q.upper()
+        qb, qucb = C.create_string_buffer(q, len(q) + 1), C.create_string_buffer(quc, len(quc) + 1)
+        base, baseuc = C.addressof(qb), C.addressof(qucb)
+        self._keep.append((qb, qucb))
+        dr = C.c_double(box["defect_rate"])
+        if m == "single":
+            return self.lib.GmapDP_single_gap(self.h, box["dynprogindex"], C.c_void_p(base + box["roffset"]),
+                                              C.c_void_p(baseuc + box["roffset"]), box["rlength"], box["glength"],
+                                              box["roffset"], box["goffset"], _b(box["gseg"]), _b(box["gseg_alt"]),
+                                              box["jump_late_p"], box["extraband"], box["widebandp"], dr)
+        if m in ("end5", "end3"):
+            fn = self.lib.GmapDP_end5_gap if m == "end5" else self.lib.GmapDP_end3_gap
+            return fn(self.h, box["dynprogindex"], C.c_void_p(base + box["roffset"]), C.c_void_p(baseuc + box["roffset"]),
+                      box["rlength_orig"], box["glength_orig"], box["roffset"], box["goffset"], _b(box["gseg"]),
+                      _b(box["gseg_alt"]), box["jump_late_p"], box["extraband"], dr, box["endalign"],
+                      box["require_pos_score_p"])
+        if m == "genome":
+            lp = (C.c_double * len(box["left_probs"]))(*box["left_probs"])
+            rp = (C.c_double * len(box["right_probs"]))(*box["right_probs"])
+            return self.lib.GmapDP_genome_gap(self.h, box["dynprogindex"], C.c_void_p(base + box["roffset"]),
+                                              C.c_void_p(baseuc + box["roffset"]), box["rlength"], box["glengthL"],
+                                              box["glengthR"], box["roffset"], box["goffsetL"], box["rev_goffsetR"],
+                                              _b(box["gsegL"]), _b(box["gsegL_alt"]), _b(box["gsegR"]), _b(box["gsegR_alt"]),
+                                              lp, rp, box["cdna_direction"], box["jump_late_p"], box["extraband"], dr,
+                                              box["maxpeelback"], box["halfp"], box["finalp"])
+        if m == "cdna":
+            return self.lib.GmapDP_cdna_gap(self.h, box["dynprogindex"], C.c_void_p(base + box["roffsetL"]),
+                                            C.c_void_p(baseuc + box["roffsetL"]), C.c_void_p(base + box["rev_roffsetR"]),
+                                            C.c_void_p(baseuc + box["rev_roffsetR"]), box["rlengthL"], box["rlengthR"],
+                                            box["glength"], box["roffsetL"], box["rev_roffsetR"], box["goffset"],
+                                            _b(box["gseg"]), _b(box["gseg_alt"]), _b(box["rev_gseg"]), _b(box["rev_gseg_alt"]),
+                                            box["jump_late_p"], box["extraband"], dr)
+        raise ValueError(m)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(self.lib.GmapDP_batch_error(self.h).decode())
+
+    def run(self):
+        self._check(self.lib.GmapDP_batch_run(self.h))
+
+    def upload(self):
+        self._check(self.lib.GmapDP_batch_upload(self.h))
+
+    def run_resident(self):
+        ms = C.c_float()
+        self._check(self.lib.GmapDP_batch_run_resident(self.h, C.byref(ms)))
+        return ms.value
+
+    def finish(self):
+        self._check(self.lib.GmapDP_batch_finish(self.h))
+
+    def ncalls(self):
+        return self.lib.GmapDP_batch_ncalls(self.h)
+
+    def nboxes(self):
+        return self.lib.GmapDP_batch_nboxes(self.h)
+
+    def cells(self):
+        return self.lib.GmapDP_batch_cells(self.h)
+
+    def h2d_bytes(self):
+        return self.lib.GmapDP_batch_h2d_bytes(self.h)
+
+    def d2h_bytes(self):
+        return self.lib.GmapDP_batch_d2h_bytes(self.h)
+
+    def result(self, cid, mode):
+        ni = 10 if mode == "genome" else (3 if mode == "cdna" else 6)
+        iout = (C.c_int * ni)()
+        dout = (C.c_double * 2)()
+        n = self.lib.GmapDP_result(self.h, cid, iout, dout, self.buf, self.MAXPAIRS)
+        if n < -1:
+            raise EngineError("GmapDP_result(%d) = %d" % (cid, n))
+        pairs = []
+        for i in range(max(n, 0)):
+            p = self.buf[i]
+            pairs.append((p.querypos, p.genomepos, p.cdna, p.comp, p.genome, p.genomealt, p.gapp,
+                          p.queryjump, p.genomejump, p.introntype, p.dynprogindex, p.donor_prob, p.acceptor_prob))
+        return n, list(iout), (list(dout) if mode == "genome" else []), pairs
+
+    def device_result(self, cid):
+        p = self.lib.GmapDP_device_result(self.h, cid)
+        return p.contents if p else None

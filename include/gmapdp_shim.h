@@ -1,0 +1,118 @@
+/* gmapdp_shim -- host side of the boundary: the reference's five DP entry points as a batch API.
+ *
+ * Each GmapDP_*_gap call mirrors one reference function (same argument meaning, same exits, same
+ * out-parameters) but, instead of filling matrices on the CPU, queues a device box:
+ *
+ *   GmapDP_single_gap  <-> Dynprog_single_gap  /root/reference/src/dynprog_single.c:428  (dynprog_single.h:23)
+ *   GmapDP_genome_gap  <-> Dynprog_genome_gap  dynprog_genome.c:3287                     (dynprog_genome.h:23)
+ *   GmapDP_cdna_gap    <-> Dynprog_cdna_gap    dynprog_cdna.c:786                        (dynprog_cdna.h:17)
+ *   GmapDP_end5_gap    <-> Dynprog_end5_gap    dynprog_end.c:1293                        (dynprog_end.h:24)
+ *   GmapDP_end3_gap    <-> Dynprog_end3_gap    dynprog_end.c:1924                        (dynprog_end.h:46)
+ *
+ * Differences from the reference signatures, all forced by the process boundary:
+ *   - Genome_T/chroffset/chrhigh/watsonp are replaced by the genomic segment chars the reference
+ *     itself would fetch with Genome_get_segment_right/left (genome.c:11023/11079); the caller
+ *     (the stage3-side binding) fetches them with the reference's own code.
+ *   - Dynprog_T is replaced by the two limits the entry points read from it (max_rlength,
+ *     max_glength; dynprog.c:602-627), given once per batch.
+ *   - for genome gaps the MaxEnt splice-site probabilities (dynprog_genome.c:970-1061, generated
+ *     table code in maxent_hr.c) are passed in as two arrays.
+ *   - results are not returned at once: the call returns an id; GmapDP_batch_run() executes every
+ *     queued box in one device batch and GmapDP_result() hands back the out-parameters and the pair
+ *     list (head first, as the reference's List_T).  Calls that the reference resolves without a
+ *     fill (size checks, single_gap_simple, genome_gap_simple, QUERYEND_NOGAPS, require_pos_score_p)
+ *     are resolved on the host exactly as there and never reach the device.
+ *
+ * iout / dout layouts (the reference's out-parameters in order):
+ *   single, end5, end3: iout[6] = dynprogindex, traceback_score, nmatches, nmismatches, nopens, nindels
+ *   genome: iout[10] = dynprogindex, new_leftgenomepos, new_rightgenomepos, traceback_score, nmatches,
+ *           nmismatches, nopens, nindels, exonhead, introntype ; dout[2] = left_prob, right_prob
+ *   cdna:   iout[3] = dynprogindex, traceback_score, incompletep
+ * Out-parameters that the reference leaves unwritten on an exit path read GMAPDP_UNSET.
+ */
+#ifndef GMAPDP_SHIM_H
+#define GMAPDP_SHIM_H
+
+#include "gmapdp_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* the observable fields of struct Pair_T (pairdef.h:12-51) */
+typedef struct gmapdp_pair {
+  int querypos, genomepos, queryjump, genomejump, dynprogindex, introntype, gapp;
+  char cdna, comp, genome, genomealt;
+  double donor_prob, acceptor_prob;
+} gmapdp_pair;
+
+#define GMAPDP_UNSET (-999)
+
+/* Endalign_T, dynprog.h:27 */
+enum { GMAPDP_QUERYEND_GAP = 0, GMAPDP_QUERYEND_INDELS = 1, GMAPDP_QUERYEND_NOGAPS = 2, GMAPDP_BEST_LOCAL = 3 };
+
+typedef struct gmapdp_batch gmapdp_batch;
+
+/* max_rlength / max_glength: what Dynprog_new(maxlookback,extraquerygap,maxpeelback,extramaterial_end,
+ * extramaterial_paired) would compute (dynprog.c:602-627); GmapDP_maxlengths does that arithmetic. */
+void GmapDP_maxlengths (int *max_rlength, int *max_glength, int maxlookback, int extraquerygap, int maxpeelback,
+			int extramaterial_end, int extramaterial_paired);
+gmapdp_batch *GmapDP_batch_new (gmapdp_ctx *ctx, int max_rlength, int max_glength);
+void GmapDP_batch_free (gmapdp_batch *b);
+void GmapDP_batch_clear (gmapdp_batch *b);
+
+int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char *rsequence, const char *rsequenceuc,
+		       int rlength, int glength, int roffset, int goffset,
+		       const char *gsequence, const char *gsequence_alt, int jump_late_p,
+		       int extraband_single, int widebandp, double defect_rate);
+
+/* rev_rsequence / rev_rsequenceuc point at the LAST char of the query part, as in the reference;
+ * rev_gsequence is the fetched array (glength chars, ascending), read from its end. */
+int GmapDP_end5_gap (gmapdp_batch *b, int dynprogindex, const char *rev_rsequence, const char *rev_rsequenceuc,
+		     int rlength, int glength, int rev_roffset, int rev_goffset,
+		     const char *rev_gsequence, const char *rev_gsequence_alt, int jump_late_p,
+		     int extraband_end, double defect_rate, int endalign, int require_pos_score_p);
+int GmapDP_end3_gap (gmapdp_batch *b, int dynprogindex, const char *rsequence, const char *rsequenceuc,
+		     int rlength, int glength, int roffset, int goffset,
+		     const char *gsequence, const char *gsequence_alt, int jump_late_p,
+		     int extraband_end, double defect_rate, int endalign, int require_pos_score_p);
+
+int GmapDP_genome_gap (gmapdp_batch *b, int dynprogindex, const char *rsequence, const char *rsequenceuc,
+		       int rlength, int glengthL, int glengthR, int roffset, int goffsetL, int rev_goffsetR,
+		       const char *gsequenceL, const char *gsequenceL_alt,
+		       const char *rev_gsequenceR, const char *rev_gsequenceR_alt,
+		       const double *left_probabilities, const double *right_probabilities,
+		       int cdna_direction, int jump_late_p, int extraband_paired, double defect_rate,
+		       int maxpeelback, int halfp, int finalp);
+
+int GmapDP_cdna_gap (gmapdp_batch *b, int dynprogindex,
+		     const char *rsequenceL, const char *rsequence_ucL,
+		     const char *rev_rsequenceR, const char *rev_rsequence_ucR,
+		     int rlengthL, int rlengthR, int glength, int roffsetL, int rev_roffsetR, int goffset,
+		     const char *gsequence, const char *gsequence_alt,
+		     const char *rev_gsequence, const char *rev_gsequence_alt,
+		     int jump_late_p, int extraband_paired, double defect_rate);
+
+/* Runs every queued device box (one gmapdp_run_batch) and completes all calls. */
+int GmapDP_batch_run (gmapdp_batch *b);
+/* resident variant for benchmarks: pack + upload once, then time the kernel alone */
+int GmapDP_batch_upload (gmapdp_batch *b);
+int GmapDP_batch_run_resident (gmapdp_batch *b, float *kernel_ms);
+int GmapDP_batch_finish (gmapdp_batch *b);	/* download + replay after run_resident */
+
+int GmapDP_batch_ncalls (const gmapdp_batch *b);
+int GmapDP_batch_nboxes (const gmapdp_batch *b);	/* calls that reached the device */
+long GmapDP_batch_cells (const gmapdp_batch *b);	/* algorithmic in-band cells of the queued boxes */
+size_t GmapDP_batch_h2d_bytes (const gmapdp_batch *b);
+size_t GmapDP_batch_d2h_bytes (const gmapdp_batch *b);
+const char *GmapDP_batch_error (const gmapdp_batch *b);
+
+/* Returns the number of pairs (list head first), or -1 for the reference's NULL list. */
+int GmapDP_result (const gmapdp_batch *b, int id, int *iout, double *dout, gmapdp_pair *pairs, int maxpairs);
+/* device-side view of one call (NULL if it never reached the device) */
+const gmapdp_result *GmapDP_device_result (const gmapdp_batch *b, int id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

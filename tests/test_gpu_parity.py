@@ -1,0 +1,100 @@
+"""GPU parity: the CUDA path (through the C ABI / shim) against the CPU oracle, bit for bit.
+
+Every out-parameter and the complete pair list of each call must be equal.  Runs only on a box
+with a B200 (`-m gpu`); the oracle is the checker, never the thing under test.
+"""
+import collections
+
+import pytest
+
+import dpgen
+from harness import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from gmap_2024_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+def run_and_compare(engine, oracle, boxes, label):
+    batch = engine.batch()
+    ids = [batch.add(b) for b in boxes]
+    batch.run()
+    stats = collections.Counter()
+    bad = []
+    for b, cid in zip(boxes, ids):
+        got = batch.result(cid, b["mode"])
+        want = oracle.run(b)
+        stats[b["mode"]] += 1
+        if got != want:
+            bad.append((b, got, want))
+    batch.free()
+    if bad:
+        b, got, want = bad[0]
+        desc = {k: v for k, v in b.items() if k not in ("queryseq", "left_probs", "right_probs", "world") and "gseg" not in k}
+        first = next((i for i, (x, y) in enumerate(zip(got[3], want[3])) if x != y), None)
+        pytest.fail("%s: %d / %d boxes differ; first: %r\n got  n=%s iout=%s dout=%s\n want n=%s iout=%s dout=%s\n first differing pair %s: %s vs %s"
+                    % (label, len(bad), len(boxes), desc, got[0], got[1], got[2], want[0], want[1], want[2], first,
+                       got[3][first] if first is not None and first < len(got[3]) else None,
+                       want[3][first] if first is not None and first < len(want[3]) else None))
+    return stats
+
+
+@pytest.mark.parametrize("mode", ["end3", "end5", "single", "genome", "cdna"])
+def test_small_boxes_per_mode(engine, oracle, mode):
+    boxes = dpgen.synth_boxes(seed=100 + len(mode), n=600, mode=mode, rmin=4, rmax=150)
+    run_and_compare(engine, oracle, boxes, mode)
+
+
+def test_mixed_batch(engine, oracle):
+    boxes = dpgen.synth_boxes(seed=7, n=3000, rmin=10, rmax=200)
+    stats = run_and_compare(engine, oracle, boxes, "mixed")
+    assert len(stats) == 5
+
+
+def test_medium_boxes(engine, oracle):
+    """16-bit paths, multi-stripe fills, wide bands"""
+    boxes = dpgen.synth_boxes(seed=11, n=250, rmin=150, rmax=700)
+    run_and_compare(engine, oracle, boxes, "medium")
+
+
+def test_large_single_and_end(engine, oracle):
+    boxes = []
+    for mode in ("single", "end3", "end5", "genome"):
+        boxes += dpgen.synth_boxes(seed=13 + len(boxes), n=6, mode=mode, rmin=1200, rmax=1990)
+    run_and_compare(engine, oracle, boxes, "large")
+
+
+def test_batch_composition_independence(engine, oracle):
+    """a box's result must not depend on what else is in the batch (threading)"""
+    boxes = dpgen.synth_boxes(seed=21, n=300)
+    b1 = engine.batch()
+    ids = [b1.add(b) for b in boxes]
+    b1.run()
+    full = [b1.result(i, b["mode"]) for i, b in zip(ids, boxes)]
+    b1.free()
+    for k in (0, 17, 150, 299):
+        b2 = engine.batch()
+        cid = b2.add(boxes[k])
+        b2.run()
+        assert b2.result(cid, boxes[k]["mode"]) == full[k]
+        b2.free()
+
+
+def test_empty_and_degenerate(engine, oracle):
+    e = engine.batch()
+    e.run()                      # empty batch is legal
+    assert e.ncalls() == 0
+    e.free()
+    boxes = dpgen.synth_boxes(seed=5, n=40, rmin=2, rmax=6)
+    run_and_compare(engine, oracle, boxes, "tiny")
