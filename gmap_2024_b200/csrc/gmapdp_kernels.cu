@@ -52,8 +52,11 @@ __device__ __forceinline__ int nt_class (int ch) {
 }
 
 __device__ __forceinline__ int prof_pick (uint32_t plo, uint32_t p4, int k) {
-  /* sign-extended byte k (0..4) of the 8-byte profile: one PRMT */
-  return (int) __byte_perm(plo,p4,(uint32_t) k * 0x1111u + 0x8880u);
+  /* sign-extended byte k (0..4) of the 8-byte profile: one PRMT.  Raw prmt.b32: the msb of a selector
+     nibble replicates the selected byte's sign (the __byte_perm intrinsic masks that bit off). */
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(plo), "r"(p4), "r"((uint32_t) k * 0x1111u + 0x8880u));
+  return (int) d;
 }
 
 __device__ __forceinline__ int clampi (int v, int lo, int hi) { return min(max(v,lo),hi); }
