@@ -145,7 +145,9 @@ def gen_spec(rng, mode=None, rmin=15, rmax=150, large=False):
                  cdna_direction=rng.choice([1, 1, -1, 0]), extraband=rng.choice([14, 14, 14, 16, 20]),
                  maxpeelback=60, halfp=0, finalp=1 if rng.random() < 0.2 else 0, junction=(a, b))
     elif mode == "cdna":
-        g = rng.randrange(max(4, rmin // 2), min(rmax, 140))
+        # the cDNA bridge is O(g^2 band^2) on the CPU (dynprog_cdna.c:149-375): keep g small
+        glo = min(max(4, rmin // 2), 100)
+        g = rng.randrange(glo, max(glo + 1, min(rmax, 140)))
         core = rand_dna(rng, g)
         k = rng.randrange(1, g)
         ins = rand_dna(rng, rng.randrange(10, 40), 0)

@@ -1,0 +1,71 @@
+"""Pins the CPU oracle against the compiled reference itself, live (only where oracle/_ref exists,
+i.e. in the build container; the committed golden vectors cover the other machines)."""
+import random
+
+import numpy as np
+import pytest
+
+import dpgen
+from harness import Oracle, Ref, ref_available
+
+pytestmark = pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+@pytest.fixture(scope="module")
+def pair():
+    return Oracle(), Ref()
+
+
+def test_tables_identical(pair):
+    o, r = pair
+    for mt in range(4):
+        assert o.use8p_size(mt) == r.use8p_size(mt)
+        for a in range(128):
+            for b in range(128):
+                assert o.pairdistance(mt, a, b) == r.pairdistance(mt, a, b)
+    for a in range(128):
+        for b in range(128):
+            assert o.consistent(a, b) == r.consistent(a, b)
+
+
+def test_fills_cell_for_cell(pair):
+    o, r = pair
+    rng = random.Random(5)
+    cells = 0
+    for it in range(150):
+        kind, bits = rng.randrange(3), rng.choice([8, 16])
+        rl = rng.randrange(1, 100 if bits == 8 else 260)
+        gl = rng.randrange(1, 110 if bits == 8 else 280)
+        g = dpgen.rand_dna(rng, gl, 0.005)
+        alt = bytearray(g)
+        for _ in range(gl // 100 + (1 if rng.random() < 0.3 else 0)):
+            alt[rng.randrange(gl)] = rng.choice(b"ACGT")
+        alt = bytes(alt)
+        q = dpgen.decorate_query(rng, dpgen.mutate(rng, g, rng.choice([0, 0.03, 0.1, 0.3])))
+        q = (q + dpgen.rand_dna(rng, rl, 0))[:rl]
+        mt, op, ex = rng.randrange(4), rng.randrange(-10, -5), rng.randrange(-3, 0)
+        extra, wide = rng.randrange(0, 20), rng.randrange(2)
+        if wide:
+            lb, ub = (extra, gl - rl + extra) if gl >= rl else (rl - gl + extra, extra)
+        else:
+            lb = ub = extra
+        late, revp = rng.randrange(2), rng.randrange(2)
+        A = o.fill(kind, bits, q, g, alt, mt, op, ex, lb, ub, late, revp)
+        B = r.fill(kind, bits, q, g, alt, mt, op, ex, lb, ub, late, revp)
+        R, C = np.meshgrid(np.arange(rl + 1), np.arange(gl + 1), indexing="ij")
+        mask = ((R >= C - ub) & (R <= C + lb)) if kind == 0 else (((C >= R) & (C <= R + ub)) if kind == 1 else ((R >= C) & (R <= C + lb)))
+        cells += int(mask.sum())
+        for k in range(4 if kind == 0 else 3):
+            assert np.array_equal(A[k][mask], B[k][mask]), (it, kind, bits, k)
+    assert cells > 200000
+
+
+@pytest.mark.parametrize("seed,edge", [(11, False), (12, True), (13, False)])
+def test_entry_points_identical(pair, seed, edge):
+    o, r = pair
+    boxes, _ = dpgen.ref_boxes(r, seed, 250, edge=edge)
+    seen = set()
+    for b in boxes:
+        assert o.run(b) == r.run(b), b["mode"]
+        seen.add(b["mode"])
+    assert len(seen) == 5
