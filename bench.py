@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- DP GCUPS of the B200 alignment-DP engine on BASELINE.json config 2
+("dynprog microbench: 1M synthetic DP boxes, 50-2000 bp per side, single/cdna/genome/end5/end3").
+
+  python bench.py --gpus 1 --steps K --warmup W             our CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus 1 --steps K ...   the reference's own CPU DP on the host cores
+
+A step = one pass of the hot path over the rank's batch of synthetic boxes (weak scaling: every rank
+gets its own `--boxes` boxes).  `value` = algorithmic in-band cells of all ranks / device time of a
+step (max over ranks), inputs resident in HBM.  `e2e` = the same through the C-ABI call from pinned
+host buffers (H2D of boxes + sequences, kernel, D2H of results + edit scripts inside the timed region).
+Cells are counted as SURVEY.md section 8(d) defines them; calls that the reference resolves without a
+fill (single_gap_simple, genome_gap_simple, QUERYEND_NOGAPS) count zero cells.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "dp_gcups"
+UNIT = "GCUPS"
+WORKLOAD = "dynprog microbench: synthetic DP boxes, 50-2000 bp per side, modes single/genome/cdna/end5/end3 in fifths (BASELINE.json configs[1])"
+BYTES_PER_CELL_8, BYTES_PER_CELL_16 = 2, 3          # score + packed directions
+OPS_PER_CELL_TRI, OPS_PER_CELL_FULL = 12, 18        # algorithmic integer ops
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, n in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own DP on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, seed, start, stride, budget_s, small = args
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import benchgen
+    from harness import Oracle, Ref
+    runner = Ref() if kind == "reference" else Oracle()
+    cells_of = _cell_counter()
+    t0 = time.perf_counter()
+    i, nboxes, cells, busy = start, 0, 0, 0.0
+    while True:
+        box = benchgen.make(seed, i, small)
+        cells += cells_of(box)
+        if kind == "reference":
+            box = benchgen.attach_ref_world(runner, box)
+        t1 = time.perf_counter()
+        runner.run(box)
+        busy += time.perf_counter() - t1
+        nboxes += 1
+        i += stride
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return nboxes, cells, busy, time.perf_counter() - t0
+
+
+def _cell_counter():
+    """algorithmic cells of one box, counted by the product's own host shim (no device needed)"""
+    import ctypes as C
+    from gmap_2024_b200.engine import Batch, load_library
+
+    class _NoDev:
+        pass
+    nd = _NoDev()
+    nd.lib, nd.ctx = load_library(), C.c_void_p()
+    batch = Batch(nd, 2000, 2030)
+
+    def count(box):
+        batch.clear()
+        batch.add(box)
+        return batch.cells()
+    return count
+
+
+def cpu_arm(seed, budget_s, small, offset=0):
+    import multiprocessing as mp
+    from harness import ref_available
+    kind = "reference" if ref_available() else "port"
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(kind, seed, offset + w, cores, budget_s, small) for w in range(cores)])
+    nboxes = sum(r[0] for r in res)
+    cells = sum(r[1] for r in res)
+    wall = max(r[3] for r in res)
+    busy = sum(r[2] for r in res)
+    # throughput of the DP calls alone on all cores (box generation / genome set-up of the harness excluded)
+    dp_s = busy / cores if busy > 0 else wall
+    return {"kind": kind, "cores": cores, "boxes": nboxes, "cells": cells, "wall_s": dp_s, "harness_wall_s": wall,
+            "gcups": cells / dp_s / 1e9}
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    vals = []
+    last = None
+    for step in range(args.warmup + args.steps):
+        last = cpu_arm(args.seed, args.ref_step_seconds, args.small, offset=step * 100003)
+        if step >= args.warmup:
+            vals.append(last)
+    cells = sum(v["cells"] for v in vals)
+    wall = sum(v["wall_s"] for v in vals)
+    value = cells / wall / 1e9
+    sample = "%d boxes of the same generator per step (%.0f s per step on %d processes)" % (
+        sum(v["boxes"] for v in vals) // max(1, len(vals)), args.ref_step_seconds, last["cores"])
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(1, len(vals)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int8/int16 saturating (AVX2)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "seed": args.seed, "note": "stock reference DP incl. its per-column _mm_clflush (SURVEY.md F5)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import benchgen
+    from gmap_2024_b200 import Engine
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the DP engine has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allreduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    eng = Engine(local)
+    batch = eng.batch(2000, 2030)
+    t0 = time.time()
+    benchgen.fill_batch(batch, args.seed, rank * args.boxes, args.boxes, 1, args.small)    # untimed: synthetic input
+    gen_s = time.time() - t0
+    cells, cells8 = batch.cells(), batch.cells8()
+    batch.upload()                                      # inputs resident in HBM from here on
+    for _ in range(args.warmup):
+        batch.run_resident()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = eng.launch_count()
+    barrier()
+    w0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        dev_ms += batch.run_resident()                  # CUDA events on the launching stream, kernel only
+    barrier()
+    wall_ms = (time.perf_counter() - w0) * 1000.0
+    launches = eng.launch_count() - launches0
+    batch.download()
+    digest = batch.digest()
+    d2h = batch.d2h_bytes()
+
+    # end to end through the C-ABI call, host buffers -> host results
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch.run_device()
+    barrier()
+    e2e_ms = (time.perf_counter() - e0) * 1000.0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    assert batch.digest() == digest, "results changed between repetitions"
+
+    import torch.distributed as d2
+    MAX, SUM = (d2.ReduceOp.MAX, d2.ReduceOp.SUM) if world > 1 else (None, None)
+    dev_ms_max = allreduce(dev_ms, MAX)
+    wall_ms_max = allreduce(wall_ms, MAX)
+    e2e_ms_max = allreduce(e2e_ms, MAX)
+    tot_cells = allreduce(cells, SUM)
+    tot_cells8 = allreduce(cells8, SUM)
+    tot_launches = allreduce(launches, SUM)
+    tot_boxes = allreduce(batch.nboxes(), SUM)
+    tot_calls = allreduce(batch.ncalls(), SUM)
+
+    if rank == 0:
+        ms_per_step = dev_ms_max / args.steps
+        value = tot_cells / (ms_per_step / 1e3) / 1e9
+        e2e_value = tot_cells / (e2e_ms_max / args.steps / 1e3) / 1e9
+        peak, peak_src = measured_peaks()
+        # roofline of the one kernel of a step (gmapdp_dp_kernel): algorithmic bytes of THIS rank's launch / its duration
+        algo_bytes = cells8 * BYTES_PER_CELL_8 + (cells - cells8) * BYTES_PER_CELL_16
+        achieved = algo_bytes / (dev_ms / args.steps / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        info = eng.device_info()
+        clocks = sampler.summary()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int8/int16 saturating (int32 lanes)", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "boxes_per_gpu": args.boxes, "calls": int(tot_calls), "device_boxes": int(tot_boxes),
+                           "cells_per_step": int(tot_cells), "seed": args.seed, "l2": "inputs_exceed_l2" if not args.small else "small",
+                           "grid_blocks": info["grid_blocks"], "block_threads": info["block_threads"], "parallelism": "shard%d" % world,
+                           "wall_ms_per_step": wall_ms_max / args.steps, "input_generation_s": gen_s},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "gmapdp_dp_kernel",
+                             "algorithmic_bytes_per_launch": int(algo_bytes),
+                             "int_ops_per_s": (tot_cells / world) * OPS_PER_CELL_FULL / (ms_per_step / 1e3)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(batch.h2d_bytes()),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps},
+                "gpu_launches": int(tot_launches), "clocks": clocks, "digest": "%016x" % digest}
+        if world == 1 and not args.no_cpu_baseline:
+            c = cpu_arm(args.seed, args.cpu_seconds, args.small)
+            line["cpu_baseline"] = {"value": c["gcups"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"],
+                                    "sample": "first %d boxes of the same generator and seed, %.0f s on %d processes%s" % (
+                                        c["boxes"], args.cpu_seconds, c["cores"],
+                                        " (stock reference DP incl. its per-column _mm_clflush, SURVEY.md F5)" if c["kind"] == "reference" else "")}
+        print(json.dumps(line))
+    batch.free()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--boxes", type=int, default=1000000, help="boxes per GPU (BASELINE.json configs[1]: 1M)")
+    ap.add_argument("--seed", type=int, default=20241018)
+    ap.add_argument("--small", action="store_true", help="15-150 bp boxes (debugging only; not the benchmark config)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-step-seconds", type=float, default=8.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -685,10 +685,10 @@ struct gmapdp_ctx {
   GdpTables *d_tables;
   /* device buffers (grown on demand) */
   gmapdp_box *d_boxes; size_t cap_boxes;
-  int *d_order;
+  int *d_order; size_t cap_order;
   uint8_t *d_seq; size_t cap_seq;
   double *d_probs; size_t cap_probs;
-  gmapdp_result *d_results;
+  gmapdp_result *d_results; size_t cap_results;
   uint32_t *d_script; size_t cap_script;
   unsigned long long *d_cursor;
   int *d_queue;
@@ -718,7 +718,7 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   gmapdp_ctx *ctx = new gmapdp_ctx();
   *out = ctx;
   ctx->device = device; ctx->launches = 0; ctx->nboxes = 0;
-  ctx->d_tables = NULL; ctx->d_boxes = NULL; ctx->cap_boxes = 0; ctx->d_order = NULL; ctx->d_seq = NULL; ctx->cap_seq = 0;
+  ctx->d_tables = NULL; ctx->d_boxes = NULL; ctx->cap_boxes = 0; ctx->d_order = NULL; ctx->cap_order = 0; ctx->cap_results = 0; ctx->d_seq = NULL; ctx->cap_seq = 0;
   ctx->d_probs = NULL; ctx->cap_probs = 0; ctx->d_results = NULL; ctx->d_script = NULL; ctx->cap_script = 0;
   ctx->d_cursor = NULL; ctx->d_queue = NULL; ctx->d_ws = NULL; ctx->cap_ws = 0; ctx->h_pin = NULL; ctx->cap_pin = 0;
   ctx->stream = 0; ctx->ev0 = ctx->ev1 = 0;
@@ -820,10 +820,8 @@ extern "C" int gmapdp_upload (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nbox
   ctx->grid = grid;
 
   if (grow(ctx,&ctx->d_boxes,&ctx->cap_boxes,(size_t) nboxes)) return GMAPDP_ERR_CUDA;
-  if (ctx->d_order) { CK(cudaFree(ctx->d_order)); ctx->d_order = NULL; }
-  if (ctx->d_results) { CK(cudaFree(ctx->d_results)); ctx->d_results = NULL; }
-  CK(cudaMalloc((void **) &ctx->d_order,(size_t) nboxes * sizeof(int)));
-  CK(cudaMalloc((void **) &ctx->d_results,(size_t) nboxes * sizeof(gmapdp_result)));
+  if (grow(ctx,&ctx->d_order,&ctx->cap_order,(size_t) nboxes)) return GMAPDP_ERR_CUDA;
+  if (grow(ctx,&ctx->d_results,&ctx->cap_results,(size_t) nboxes)) return GMAPDP_ERR_CUDA;
   if (grow(ctx,&ctx->d_seq,&ctx->cap_seq,seqbytes + 16)) return GMAPDP_ERR_CUDA;
   if (grow(ctx,&ctx->d_probs,&ctx->cap_probs,nprobs + 2)) return GMAPDP_ERR_CUDA;
   if (grow(ctx,&ctx->d_script,&ctx->cap_script,script_need + 64)) return GMAPDP_ERR_CUDA;
@@ -884,4 +882,22 @@ extern "C" int gmapdp_run_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int n
   rc = gmapdp_run_resident(ctx,NULL);
   if (rc) return rc;
   return gmapdp_download(ctx,results,script,script_cap,script_used);
+}
+
+/* pinned host memory helpers (so that the shim's pools are DMA-able without a staging copy) */
+extern "C" void *gmapdp_host_alloc (size_t bytes) {
+  void *p = NULL;
+  if (cudaHostAlloc(&p,bytes ? bytes : 1,cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return NULL; }
+  return p;
+}
+extern "C" void gmapdp_host_free (void *p) { if (p) cudaFreeHost(p); }
+extern "C" int gmapdp_host_register (void *p, size_t bytes) {
+  if (!p || !bytes) return GMAPDP_OK;
+  if (cudaHostRegister(p,bytes,cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return GMAPDP_ERR_CUDA; }
+  return GMAPDP_OK;
+}
+extern "C" int gmapdp_host_unregister (void *p) {
+  if (!p) return GMAPDP_OK;
+  if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return GMAPDP_ERR_CUDA; }
+  return GMAPDP_OK;
 }

@@ -186,16 +186,18 @@ struct gmapdp_batch {
   std::vector<int> box_call;
   std::vector<uint8_t> seqpool;
   std::vector<double> probpool;
-  std::vector<gmapdp_result> results;
-  std::vector<uint32_t> script;
+  gmapdp_result *results = NULL; size_t nresults = 0;	/* pinned */
+  uint32_t *script = NULL; size_t script_cap = 0;	/* pinned */
   size_t script_used = 0;
-  long cells = 0;
+  long cells = 0, cells8 = 0;
+  bool pinned = false;
   int count_mismatch = 0;
   std::string err;
-  bool uploaded = false;
+  bool uploaded = false, overflow = false;
 
-  int add_bytes (const char *p, int n) {
-    int off = (int) seqpool.size();
+  uint32_t add_bytes (const char *p, int n) {
+    if (seqpool.size() + (size_t) n + 4 > 0xFFFFFFF0ull) { err = "sequence pool exceeds 4 GiB: split the batch"; overflow = true; return 0; }
+    uint32_t off = (uint32_t) seqpool.size();
     seqpool.insert(seqpool.end(),(const uint8_t *) p,(const uint8_t *) p + n);
     while (seqpool.size() & 3) seqpool.push_back(0);
     return off;
@@ -213,11 +215,22 @@ extern "C" gmapdp_batch *GmapDP_batch_new (gmapdp_ctx *ctx, int max_rlength, int
   b->ctx = ctx; b->max_rlength = max_rlength; b->max_glength = max_glength;
   return b;
 }
-extern "C" void GmapDP_batch_free (gmapdp_batch *b) { delete b; }
-extern "C" void GmapDP_batch_clear (gmapdp_batch *b) {
-  b->calls.clear(); b->boxes.clear(); b->box_call.clear(); b->seqpool.clear(); b->probpool.clear();
-  b->results.clear(); b->script.clear(); b->script_used = 0; b->cells = 0; b->uploaded = false; b->err.clear();
+static void unpin (gmapdp_batch *b) {
+  if (b->pinned) {
+    gmapdp_host_unregister(b->boxes.data()); gmapdp_host_unregister(b->seqpool.data());
+    if (!b->probpool.empty()) gmapdp_host_unregister(b->probpool.data());
+    b->pinned = false;
+  }
+  gmapdp_host_free(b->results); b->results = NULL; b->nresults = 0;
+  gmapdp_host_free(b->script); b->script = NULL; b->script_cap = 0;
 }
+extern "C" void GmapDP_batch_clear (gmapdp_batch *b) {
+  unpin(b);
+  b->calls.clear(); b->boxes.clear(); b->box_call.clear(); b->seqpool.clear(); b->probpool.clear();
+  b->script_used = 0; b->cells = 0; b->cells8 = 0; b->uploaded = false; b->overflow = false; b->err.clear();
+}
+extern "C" void GmapDP_batch_free (gmapdp_batch *b) { if (b) { unpin(b); delete b; } }
+extern "C" long GmapDP_batch_cells8 (const gmapdp_batch *b) { return b->cells8; }
 extern "C" int GmapDP_batch_ncalls (const gmapdp_batch *b) { return (int) b->calls.size(); }
 extern "C" int GmapDP_batch_nboxes (const gmapdp_batch *b) { return (int) b->boxes.size(); }
 extern "C" long GmapDP_batch_cells (const gmapdp_batch *b) { return b->cells; }
@@ -228,6 +241,7 @@ extern "C" size_t GmapDP_batch_h2d_bytes (const gmapdp_batch *b) {
 extern "C" size_t GmapDP_batch_d2h_bytes (const gmapdp_batch *b) {
   return b->boxes.size() * sizeof(gmapdp_result) + b->script_used * sizeof(uint32_t) + sizeof(unsigned long long);
 }
+static void add_cells (gmapdp_batch *b, long n, bool use8) { b->cells += n; if (use8) b->cells8 += n; }
 
 static gmapdp_box blank_box () { gmapdp_box x; memset(&x,0,sizeof(x)); return x; }
 
@@ -277,7 +291,7 @@ extern "C" int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char 
   x.qL_off = x.qR_off = b->add_bytes(c.quc.data(),rlength);
   x.gL_off = x.gR_off = b->add_bytes(c.gL.data(),glength);
   x.gLalt_off = x.gRalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
-  b->cells += gdp_cells_full(rlength,glength,lband,uband);
+  add_cells(b,gdp_cells_full(rlength,glength,lband,uband),use8);
   c.box = (int) b->boxes.size();
   b->boxes.push_back(x); b->box_call.push_back(id);
   return id;
@@ -349,7 +363,7 @@ static int end_gap (gmapdp_batch *b, bool end5, int dynprogindex, const char *rs
   x.gL_off = x.gR_off = b->add_bytes(c.gL.data(),glength);
   x.gLalt_off = x.gRalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
   x.revmask = end5 ? 1 : 0;
-  b->cells += gdp_cells_tri(rlength,glength,uband) + gdp_cells_tri(glength,rlength,lband);
+  add_cells(b,gdp_cells_tri(rlength,glength,uband) + gdp_cells_tri(glength,rlength,lband),use8);
   c.box = (int) b->boxes.size();
   b->boxes.push_back(x); b->box_call.push_back(id);
   return id;
@@ -471,12 +485,12 @@ extern "C" int GmapDP_genome_gap (gmapdp_batch *b, int dynprogindex, const char 
   x.gLalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glengthL);
   x.gR_off = b->add_bytes(c.gR.data(),glengthR);
   x.gRalt_off = (c.gRa == c.gR) ? x.gR_off : b->add_bytes(c.gRa.data(),glengthR);
-  x.probL_off = (int) b->probpool.size(); b->probpool.insert(b->probpool.end(),c.lp.begin(),c.lp.end()); b->probpool.push_back(0.0);
-  x.probR_off = (int) b->probpool.size(); b->probpool.insert(b->probpool.end(),c.rp.begin(),c.rp.end()); b->probpool.push_back(0.0);
+  x.probL_off = (uint32_t) b->probpool.size(); b->probpool.insert(b->probpool.end(),c.lp.begin(),c.lp.end()); b->probpool.push_back(0.0);
+  x.probR_off = (uint32_t) b->probpool.size(); b->probpool.insert(b->probpool.end(),c.rp.begin(),c.rp.end()); b->probpool.push_back(0.0);
   x.offdiff = rev_goffsetR - goffsetL;
   x.revmask = 2;
-  b->cells += gdp_cells_tri(rlength,glengthL,ubandL) + gdp_cells_tri(glengthL,rlength,lbandL) +
-    gdp_cells_tri(rlength,glengthR,ubandR) + gdp_cells_tri(glengthR,rlength,lbandR);
+  add_cells(b,gdp_cells_tri(rlength,glengthL,ubandL) + gdp_cells_tri(glengthL,rlength,lbandL) +
+	    gdp_cells_tri(rlength,glengthR,ubandR) + gdp_cells_tri(glengthR,rlength,lbandR),use8);
   c.box = (int) b->boxes.size();
   b->boxes.push_back(x); b->box_call.push_back(id);
   return id;
@@ -527,8 +541,8 @@ extern "C" int GmapDP_cdna_gap (gmapdp_batch *b, int dynprogindex,
   x.gRalt_off = (c.gRa == c.gR) ? x.gR_off : b->add_bytes(c.gRa.data(),glength);
   x.offdiff = rev_roffsetR - roffsetL;
   x.revmask = 2;
-  b->cells += gdp_cells_tri(rlengthL,glength,ubandL) + gdp_cells_tri(glength,rlengthL,lbandL) +
-    gdp_cells_tri(rlengthR,glength,ubandR) + gdp_cells_tri(glength,rlengthR,lbandR);
+  add_cells(b,gdp_cells_tri(rlengthL,glength,ubandL) + gdp_cells_tri(glength,rlengthL,lbandL) +
+	    gdp_cells_tri(rlengthR,glength,ubandR) + gdp_cells_tri(glength,rlengthR,lbandR),use8);
   c.box = (int) b->boxes.size();
   b->boxes.push_back(x); b->box_call.push_back(id);
   return id;
@@ -544,7 +558,7 @@ static void check_counts (gmapdp_batch *b, const gmapdp_result &r, const Counts 
 
 static void finish_call (gmapdp_batch *b, Call &c) {
   const gmapdp_result &r = b->results[c.box];
-  const uint32_t *ops = b->script.data() + r.script_off;
+  const uint32_t *ops = b->script + r.script_off;
   const int dpi = c.iout[0];
   if (c.mode == GMAPDP_SINGLE) {
     Pushed l; Counts n;
@@ -630,7 +644,6 @@ static void finish_call (gmapdp_batch *b, Call &c) {
 }
 
 static int finish_all (gmapdp_batch *b) {
-  for (size_t k = 0; k < b->results.size(); k++) b->results[k].cells = 0;
   for (size_t i = 0; i < b->calls.size(); i++) {
     Call &c = b->calls[i];
     if (!c.done && c.box >= 0) { finish_call(b,c); c.done = true; }
@@ -639,11 +652,41 @@ static int finish_all (gmapdp_batch *b) {
   return GMAPDP_OK;
 }
 
+static int ensure_host_buffers (gmapdp_batch *b) {
+  if (b->overflow) { b->err = "sequence pool exceeds 4 GiB: split the batch"; return GMAPDP_ERR_CAPACITY; }
+  if (!b->pinned) {
+    /* the pools are complete: pin them in place so every H2D is a straight DMA */
+    gmapdp_host_register(b->boxes.data(),b->boxes.size() * sizeof(gmapdp_box));
+    gmapdp_host_register(b->seqpool.data(),b->seqpool.size());
+    if (!b->probpool.empty()) gmapdp_host_register(b->probpool.data(),b->probpool.size() * sizeof(double));
+    b->pinned = true;
+  }
+  if (b->nresults < b->boxes.size()) {
+    gmapdp_host_free(b->results);
+    b->results = (gmapdp_result *) gmapdp_host_alloc(b->boxes.size() * sizeof(gmapdp_result));
+    b->nresults = b->results ? b->boxes.size() : 0;
+  }
+  size_t need = 64;
+  for (const gmapdp_box &x : b->boxes) {
+    need += (size_t) x.rlenL + x.glenL + 4;
+    if (x.mode == GMAPDP_GENOME || x.mode == GMAPDP_CDNA) need += (size_t) x.rlenR + x.glenR + 4;
+  }
+  if (b->script_cap < need) {
+    gmapdp_host_free(b->script);
+    b->script = (uint32_t *) gmapdp_host_alloc(need * sizeof(uint32_t));
+    b->script_cap = b->script ? need : 0;
+  }
+  if (!b->results || !b->script) { b->err = "pinned host allocation failed"; return GMAPDP_ERR_CUDA; }
+  return GMAPDP_OK;
+}
+
 extern "C" int GmapDP_batch_upload (gmapdp_batch *b) {
   if (b->boxes.empty()) { b->uploaded = true; return GMAPDP_OK; }
   if (!b->ctx) { b->err = "no device context: the DP engine has no CPU fallback"; return GMAPDP_ERR_CUDA; }
-  int rc = gmapdp_upload(b->ctx,b->boxes.data(),(int) b->boxes.size(),b->seqpool.data(),b->seqpool.size(),
-			 b->probpool.data(),b->probpool.size());
+  int rc = ensure_host_buffers(b);
+  if (rc) return rc;
+  rc = gmapdp_upload(b->ctx,b->boxes.data(),(int) b->boxes.size(),b->seqpool.data(),b->seqpool.size(),
+		     b->probpool.data(),b->probpool.size());
   if (rc) { b->err = gmapdp_last_error(b->ctx); return rc; }
   b->uploaded = true;
   return GMAPDP_OK;
@@ -658,24 +701,53 @@ extern "C" int GmapDP_batch_run_resident (gmapdp_batch *b, float *kernel_ms) {
   return rc;
 }
 
+/* device boundary only: H2D + kernel + D2H of results and scripts, no pair-list replay */
+extern "C" int GmapDP_batch_run_device (gmapdp_batch *b) {
+  if (b->boxes.empty()) return GMAPDP_OK;
+  if (!b->ctx) { b->err = "no device context: the DP engine has no CPU fallback"; return GMAPDP_ERR_CUDA; }
+  int rc = ensure_host_buffers(b);
+  if (rc) return rc;
+  rc = gmapdp_run_batch(b->ctx,b->boxes.data(),(int) b->boxes.size(),b->seqpool.data(),b->seqpool.size(),
+			b->probpool.data(),b->probpool.size(),b->results,b->script,b->script_cap,&b->script_used);
+  if (rc) b->err = gmapdp_last_error(b->ctx);
+  b->uploaded = (rc == 0);
+  return rc;
+}
+
+extern "C" int GmapDP_batch_download (gmapdp_batch *b) {
+  if (b->boxes.empty()) return GMAPDP_OK;
+  int rc = ensure_host_buffers(b);
+  if (rc) return rc;
+  rc = gmapdp_download(b->ctx,b->results,b->script,b->script_cap,&b->script_used);
+  if (rc) b->err = gmapdp_last_error(b->ctx);
+  return rc;
+}
+
 extern "C" int GmapDP_batch_finish (gmapdp_batch *b) {
-  if (!b->boxes.empty()) {
-    size_t need = 0;
-    for (const gmapdp_box &x : b->boxes) need += (size_t) x.rlenL + x.glenL + x.rlenR + x.glenR + 8;
-    b->results.resize(b->boxes.size());
-    b->script.resize(need + 64);
-    int rc = gmapdp_download(b->ctx,b->results.data(),b->script.data(),b->script.size(),&b->script_used);
-    if (rc) { b->err = gmapdp_last_error(b->ctx); return rc; }
-  }
+  int rc = GmapDP_batch_download(b);
+  if (rc) return rc;
   return finish_all(b);
 }
 
 extern "C" int GmapDP_batch_run (gmapdp_batch *b) {
-  int rc = GmapDP_batch_upload(b);
+  int rc = GmapDP_batch_run_device(b);
   if (rc) return rc;
-  rc = GmapDP_batch_run_resident(b,NULL);
-  if (rc) return rc;
-  return GmapDP_batch_finish(b);
+  return finish_all(b);
+}
+
+/* order-independent digest of the device results (scores, best cells, counts, scripts): what the
+   1M-box runs compare between repetitions / ranks without materialising pair lists */
+extern "C" unsigned long long GmapDP_batch_digest (const gmapdp_batch *b) {
+  unsigned long long h = 1469598103934665603ull;
+  for (size_t k = 0; k < b->boxes.size(); k++) {
+    const gmapdp_result &r = b->results[k];
+    const int v[12] = {r.status,r.finalscore,r.bestrL,r.bestcL,r.bestrR,r.bestcR,r.tb_score,r.nmatches,r.nmismatches,r.nopens,r.nindels,r.script_lenA + 4096 * r.script_lenB};
+    unsigned long long hb = 1099511628211ull * (k + 1);
+    for (int j = 0; j < 12; j++) hb = (hb ^ (unsigned) v[j]) * 1099511628211ull;
+    for (int j = 0; j < r.script_lenA + r.script_lenB; j++) hb = (hb ^ b->script[r.script_off + j]) * 1099511628211ull;
+    h += hb;
+  }
+  return h;
 }
 
 extern "C" int GmapDP_result (const gmapdp_batch *b, int id, int *iout, double *dout, gmapdp_pair *pairs, int maxpairs) {
@@ -694,6 +766,6 @@ extern "C" int GmapDP_result (const gmapdp_batch *b, int id, int *iout, double *
 extern "C" const gmapdp_result *GmapDP_device_result (const gmapdp_batch *b, int id) {
   if (id < 0 || id >= (int) b->calls.size()) return NULL;
   const Call &c = b->calls[id];
-  if (c.box < 0 || (size_t) c.box >= b->results.size()) return NULL;
+  if (c.box < 0 || (size_t) c.box >= b->nresults) return NULL;
   return &b->results[c.box];
 }

@@ -40,6 +40,8 @@ def load_library():
         lib.GmapDP_batch_new.restype = C.c_void_p
         lib.GmapDP_batch_error.restype = C.c_char_p
         lib.GmapDP_batch_cells.restype = C.c_long
+        lib.GmapDP_batch_cells8.restype = C.c_long
+        lib.GmapDP_batch_digest.restype = C.c_ulonglong
         lib.GmapDP_batch_h2d_bytes.restype = C.c_size_t
         lib.GmapDP_batch_d2h_bytes.restype = C.c_size_t
         lib.GmapDP_device_result.restype = C.POINTER(DeviceResult)
@@ -154,6 +156,19 @@ class Batch:
 
     def finish(self):
         self._check(self.lib.GmapDP_batch_finish(self.h))
+
+    def run_device(self):
+        """gmapdp_run_batch from host buffers: H2D + kernel + D2H (no pair-list replay)"""
+        self._check(self.lib.GmapDP_batch_run_device(self.h))
+
+    def download(self):
+        self._check(self.lib.GmapDP_batch_download(self.h))
+
+    def digest(self):
+        return self.lib.GmapDP_batch_digest(self.h)
+
+    def cells8(self):
+        return self.lib.GmapDP_batch_cells8(self.h)
 
     def ncalls(self):
         return self.lib.GmapDP_batch_ncalls(self.h)

@@ -50,7 +50,7 @@ enum { GMAPDP_SINGLE = 0, GMAPDP_GENOME = 1, GMAPDP_CDNA = 2, GMAPDP_END5 = 3, G
 #define GMAPDP_F_NOTRACE     0x40	/* end modes: require_pos_score_p => the reference skips the traceback */
 #define GMAPDP_F_BRIDGE_LATE 0x80	/* cdna bridge tie rule: >= (jump_late_p) instead of > */
 
-/* One DP box (64 bytes).  Sequences live in one byte pool; every *_off is a byte offset into it.
+/* One DP box (80 bytes).  Sequences live in one byte pool; every *_off is an unsigned byte offset into it (pool < 4 GiB).
  * All sequence arrays are stored FORWARD (ascending memory = ascending coordinate); sides that the
  * reference addresses through "rev_" pointers set the corresponding REV flag bit in `revmask` and
  * are read from their last element backwards, exactly like rev_rsequence / rev_gsequence. */
@@ -61,10 +61,10 @@ typedef struct gmapdp_box {
   int32_t glenL, glenR;		/* glength (single/end/cdna: glenR == glenL); genome: glengthL, glengthR */
   int8_t  mismatchtype, open, extend, cdna_direction;	/* Mismatchtype_T dynprog.h:54; penalties are negative */
   int16_t lbandL, ubandL, lbandR, ubandR;		/* Dynprog_compute_bands dynprog.c:1246 */
-  int32_t qL_off, qR_off;	/* upper-cased query chars of the L / R side (rlenL / rlenR bytes) */
-  int32_t gL_off, gLalt_off;	/* genomic segment of the L (or only) side and its alt-genome twin (== gL_off if none) */
-  int32_t gR_off, gRalt_off;	/* genomic segment of the R side */
-  int32_t probL_off, probR_off;	/* genome mode: offsets (in doubles) of left/right MaxEnt probabilities, glen-1 entries each */
+  uint32_t qL_off, qR_off;	/* upper-cased query chars of the L / R side (rlenL / rlenR bytes) */
+  uint32_t gL_off, gLalt_off;	/* genomic segment of the L (or only) side and its alt-genome twin (== gL_off if none) */
+  uint32_t gR_off, gRalt_off;	/* genomic segment of the R side */
+  uint32_t probL_off, probR_off;	/* genome mode: offsets (in doubles) of left/right MaxEnt probabilities, glen-1 entries each */
   int32_t offdiff;		/* genome: rev_goffsetR - goffsetL ; cdna: rev_roffsetR - roffsetL (bridge constraint) */
   int32_t revmask;		/* bit0: L side is read reversed (end5) ; bit1: R side is read reversed (genome, cdna) */
 } gmapdp_box;
@@ -111,6 +111,12 @@ int gmapdp_run_resident (gmapdp_ctx *ctx, float *kernel_ms);
 int gmapdp_download (gmapdp_ctx *ctx, gmapdp_result *results, uint32_t *script, size_t script_cap, size_t *script_used);
 /* number of kernel launches issued by this context so far */
 long gmapdp_launch_count (const gmapdp_ctx *ctx);
+
+/* Pinned host memory for the batch buffers (optional: pageable buffers work, through a staging copy). */
+void *gmapdp_host_alloc (size_t bytes);
+void gmapdp_host_free (void *p);
+int gmapdp_host_register (void *p, size_t bytes);
+int gmapdp_host_unregister (void *p);
 
 #ifdef __cplusplus
 }

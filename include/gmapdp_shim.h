@@ -99,6 +99,10 @@ int GmapDP_batch_run (gmapdp_batch *b);
 int GmapDP_batch_upload (gmapdp_batch *b);
 int GmapDP_batch_run_resident (gmapdp_batch *b, float *kernel_ms);
 int GmapDP_batch_finish (gmapdp_batch *b);	/* download + replay after run_resident */
+int GmapDP_batch_run_device (gmapdp_batch *b);	/* gmapdp_run_batch only: H2D + kernel + D2H, no pair replay */
+int GmapDP_batch_download (gmapdp_batch *b);	/* D2H of results + scripts after run_resident */
+unsigned long long GmapDP_batch_digest (const gmapdp_batch *b);	/* checksum of all device results + scripts */
+long GmapDP_batch_cells8 (const gmapdp_batch *b);	/* the share of GmapDP_batch_cells filled in 8-bit mode */
 
 int GmapDP_batch_ncalls (const gmapdp_batch *b);
 int GmapDP_batch_nboxes (const gmapdp_batch *b);	/* calls that reached the device */
