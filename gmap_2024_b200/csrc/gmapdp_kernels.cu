@@ -433,38 +433,60 @@ __device__ int bridge_genome (const gmapdp_box &b, const TriPlanes &LU, const Tr
   return bestscore;
 }
 
-/* bridge_cdna_gap_{8,16}_ud, dynprog_cdna.c:123-375 */
+/* bridge_cdna_gap_{8,16}_ud, dynprog_cdna.c:123-375.
+ *
+ * The reference scans (cL asc, cR desc, rL asc, rR asc) keeping the best score with >= (jump late:
+ * the LAST maximum in scan order wins) or > (the FIRST wins), subject to rR < lim - rL.  That is an
+ * argmax with a positional tie-break, so it is evaluated here as
+ *   phase 1: for every cR a prefix-best table over rR (best score and its rR for rR <= k), which
+ *            answers "best rR under the constraint" in O(1);
+ *   phase 2: for every (cL, rL, cR) one table lookup; candidates carry their scan position as a key.
+ * O(g^2 * band) instead of O(g^2 * band^2). */
 __device__ int bridge_cdna (const gmapdp_box &b, const TriPlanes &LU, const TriPlanes &LL, const TriPlanes &RU,
-			    const TriPlanes &RL, int NEG, int *bestcL, int *bestcR, int *bestrL, int *bestrR) {
+			    const TriPlanes &RL, int NEG, uint32_t *pb, int *bestcL, int *bestcR, int *bestrL, int *bestrR) {
   const int lane = threadIdx.x & 31;
   const int glength = b.glenL, rlengthL = b.rlenL, rlengthR = b.rlenR;
   const int lbandL = b.lbandL, ubandL = b.ubandL, lbandR = b.lbandR, ubandR = b.ubandR;
-  const int open = b.open, extend = b.extend, lim = b.offdiff;
+  const int open = b.open, lim = b.offdiff;
   const bool late = (b.flags & GMAPDP_F_BRIDGE_LATE) != 0;
-  int bs = NEG, bcL = 0, bcR = 0, brL = 0, brR = 0;
-  bool have = false;
+  const int PBW = lbandR + ubandR + 1;
 
-  for (int cL = 1 + lane; cL < glength; cL += 32) {
-    int pen = 0;
-    for (int cR = glength - cL; cR >= 0; cR--, pen += extend) {
-      const int rloL = max(cL - ubandL,1), rhighL = min(cL + lbandL,rlengthL - 1);
-      const int rloR = max(cR - ubandR,1), rhighR = min(cR + lbandR,rlengthR - 1);
-      for (int rL = rloL; rL <= rhighL; rL++) {
-	const int scoreL = (rL < cL) ? tri_score(LU,rL,cL) : tri_score(LL,cL,rL);
-	int rR;
-	for (rR = rloR; rR < cR && rR < lim - rL; rR++) {
-	  const int score = scoreL + tri_score(RU,rR,cR) + pen;
-	  if (late ? score >= bs : score > bs) { bs = score; bcL = cL; bcR = cR; brL = rL; brR = rR; have = true; }
-	}
-	for ( ; rR <= rhighR && rR < lim - rL; rR++) {
-	  const int score = scoreL + tri_score(RL,cR,rR) + pen;
-	  if (late ? score >= bs : score > bs) { bs = score; bcL = cL; bcR = cR; brL = rL; brR = rR; have = true; }
-	}
-      }
-      pen = open - extend;
+  for (int cR = lane; cR <= glength; cR += 32) {
+    const int lo = max(cR - ubandR,1), hi = min(cR + lbandR,rlengthR - 1);
+    uint32_t *row = pb + (size_t) cR * PBW - (cR - ubandR);
+    int bs = 0, br = 0; bool have = false;
+    for (int rR = lo; rR <= hi; rR++) {
+      const int sc = (rR < cR) ? tri_score(RU,rR,cR) : tri_score(RL,cR,rR);
+      if (!have || (late ? sc >= bs : sc > bs)) { bs = sc; br = rR; have = true; }
+      row[rR] = ((uint32_t) (bs + 32768) << 16) | (uint32_t) br;
     }
   }
-  /* lanes partition cL; scan order is cL ascending: late keeps the largest cL on ties, early the smallest */
+  __syncwarp();
+
+  int bs = NEG; unsigned long long bk = 0; bool have = false;
+  int bcL = 0, bcR = 0, brL = 0, brR = 0;
+  for (int cL = 1 + lane; cL < glength; cL += 32) {
+    const int rloL = max(cL - ubandL,1), rhighL = min(cL + lbandL,rlengthL - 1);
+    for (int rL = rloL; rL <= rhighL; rL++) {
+      const int scoreL = (rL < cL) ? tri_score(LU,rL,cL) : tri_score(LL,cL,rL);
+      const int rcap = lim - rL - 1;
+      for (int cR = glength - cL; cR >= 0; cR--) {
+	const int lo = max(cR - ubandR,1);
+	const int k = min(min(cR + lbandR,rlengthR - 1),rcap);
+	if (k < lo) continue;
+	const uint32_t e = pb[(size_t) cR * PBW + (k - (cR - ubandR))];
+	const int score = scoreL + ((int) (e >> 16) - 32768) + ((cR == glength - cL) ? 0 : open);
+	const int rR = (int) (e & 0xffffu);
+	const unsigned long long key = ((unsigned long long) (glength - cR) << 32) | ((unsigned long long) rL << 16) | (unsigned long long) rR;
+	bool take;
+	if (!have) take = late ? (score >= bs) : (score > bs);
+	else if (score != bs) take = score > bs;
+	else take = late ? (key > bk) : (key < bk);
+	if (take) { bs = score; bk = key; bcL = cL; bcR = cR; brL = rL; brR = rR; have = true; }
+      }
+    }
+  }
+  /* lanes partition cL, which leads the scan order: late keeps the largest cL on ties, early the smallest */
   for (int off = 16; off > 0; off >>= 1) {
     const int os = __shfl_xor_sync(FULLMASK,bs,off), ocL = __shfl_xor_sync(FULLMASK,bcL,off), ocR = __shfl_xor_sync(FULLMASK,bcR,off);
     const int orL = __shfl_xor_sync(FULLMASK,brL,off), orR = __shfl_xor_sync(FULLMASK,brR,off);
@@ -618,7 +640,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, short *
 			 tb->isc[di][(b.flags & GMAPDP_F_FINALP) ? 1 : 0],&brL,&brR,&bcL,&bcR);
       if (fs < 0) res.status = 1;
     } else {
-      fs = bridge_cdna(b,LU,LL,RU,RL,NEG,&bcL,&bcR,&brL,&brR);
+      fs = bridge_cdna(b,LU,LL,RU,RL,NEG,wp,&bcL,&bcR,&brL,&brR);
     }
     res.finalscore = fs; res.bestrL = brL; res.bestcL = bcL; res.bestrR = brR; res.bestcR = bcR;
     if (lane == 0 && res.status == 0) {

@@ -77,6 +77,7 @@ GDP_HD size_t gdp_ws_words (const gmapdp_box &b) {
       EGeom ru = egeom(b.rlenR,b.glenR,b.ubandR), rl = egeom(b.glenR,b.rlenR,b.lbandR);
       w += (size_t) ru.nstripes * (ru.dirW + ru.scW);
       w += (size_t) rl.nstripes * (rl.dirW + rl.scW);
+      if (b.mode == GMAPDP_CDNA) w += (size_t) (b.glenL + 1) * (b.lbandR + b.ubandR + 1);	/* prefix-best table of the cDNA bridge */
     }
   }
   return w + 64;
