@@ -202,7 +202,7 @@ def run_ours(args):
     eng = Engine(local)
     batch = eng.batch(2000, 2030)
     t0 = time.time()
-    benchgen.fill_batch(batch, args.seed, rank * args.boxes, args.boxes, 1, args.small)    # untimed: synthetic input
+    benchgen.fill_batch(batch, args.seed, rank * args.boxes, args.boxes, 1, args.small, args.modemask)    # untimed: synthetic input
     gen_s = time.time() - t0
     cells, cells8 = batch.cells(), batch.cells8()
     batch.upload()                                      # inputs resident in HBM from here on
@@ -267,7 +267,7 @@ def run_ours(args):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int8/int16 saturating (int32 lanes)", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "boxes_per_gpu": args.boxes, "calls": int(tot_calls), "device_boxes": int(tot_boxes),
-                           "cells_per_step": int(tot_cells), "seed": args.seed, "l2": "inputs_exceed_l2" if not args.small else "small",
+                           "cells_per_step": int(tot_cells), "seed": args.seed, "modemask": args.modemask, "l2": "inputs_exceed_l2" if not args.small else "small",
                            "grid_blocks": info["grid_blocks"], "block_threads": info["block_threads"], "parallelism": "shard%d" % world,
                            "wall_ms_per_step": wall_ms_max / args.steps, "input_generation_s": gen_s},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -303,6 +303,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-step-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--modemask", type=int, default=31, help="diagnostics: bit k keeps mode k (single,genome,cdna,end5,end3); 31 = the benchmark config")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

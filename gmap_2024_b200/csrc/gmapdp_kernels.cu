@@ -63,116 +63,237 @@ __device__ __forceinline__ int clampi (int v, int lo, int hi) { return min(max(v
 
 struct BestTrack { int bs, bk; };
 
-struct TriPlanes {		/* output of one E-only fill */
-  uint32_t *dirs, *sc;		/* sc may be NULL */
-  EGeom g;
+/* One E-only fill (upper or lower triangle) and where its planes live; see TriPacking (gmapdp_layout.h). */
+struct TriFill {
+  int nA, nB, band, lane0, pass0, npass;
+  int lateadd;			/* 1: ties go to the gap (jump late, >=), 0: > */
+  bool lower;
+  const uint2 *prof;		/* [0..nA] 8-byte score profiles of the lane-axis positions */
+  const uint8_t *code;		/* [0..nB] class codes of the step-axis positions */
+  uint32_t *dirs, *sc;		/* planes of pass `pass0'; the fill's further passes follow at dirPW / scPW */
+  int dirPW, scPW;
 };
 
-/* E-only fill.  LOWER=false: upper triangle, lane axis = query rows, step axis = genome columns.
- *               LOWER=true : lower triangle, lane axis = genome columns, step axis = query rows. */
-template <bool LOWER>
-__device__ void fill_tri (const SideSeq &sd, const uint8_t *stepcode, int band, int mt, int open, int extend,
-			  bool late, int NEG, int POS, bool bits8, const TriPlanes &pl,
-			  BestTrack *bt, bool lastrow, short *brow, const GdpTables *tb) {
+/* 2-bit direction cell; (i,j) = (lane-axis index, step-axis index).  Out of band -> 0. */
+__device__ __forceinline__ uint32_t tri_dir (const TriFill &f, int i, int j) {
+  const int d = j - i;
+  if (i < 0 || i > f.nA || d < 0 || d > f.band || j > f.nB) return 0;
+  const uint32_t w = f.dirs[(size_t) (d >> 5) * f.dirPW + (j >> 4) * 32 + f.lane0 + (d & 31)];
+  return (w >> (2 * (j & 15))) & 3u;
+}
+__device__ __forceinline__ int tri_score (const TriFill &f, int i, int j) {
+  const int d = j - i;
+  const uint32_t w = f.sc[(size_t) (d >> 5) * f.scPW + (j >> 1) * 32 + f.lane0 + (d & 31)];
+  return (int) (short) (w >> (16 * (j & 1)));
+}
+
+/* score profiles of the lane axis: upper = raw query char x genome class (dynprog_simd.c:4424-4449),
+   lower = query class x raw genome char with the alt genome folded in (:5459-5524, :8690) */
+__device__ void tri_profiles (const TriFill &f, const SideSeq &sd, int mt, bool bits8, uint2 *prof, const GdpTables *tb) {
   const int lane = threadIdx.x & 31;
-  const int nA = pl.g.nA, nB = pl.g.nB;
-  int s = 0;
-  for (int i0 = 0; i0 <= nA; i0 += 32, s++) {
-    const int i = i0 + lane;
-    const bool rowact = (i <= nA);
-    const int jlo = i0;
-    int jhi = i0 + 31 + band; if (jhi > nB) jhi = nB;
-    if (jlo > jhi) break;
-    int jend = i + band; if (jend > nB) jend = nB;
-
-    uint32_t plo = 0, p4 = 0;
-    if (rowact) {
-      if (!LOWER) {
-	int q = (i == 0) ? 'N' : sd.q(i);
-	const uint2 p = *reinterpret_cast<const uint2 *>(&tb->U[mt][q & 127][0]);
-	plo = p.x; p4 = p.y;
-      } else if (i == 0) {
-	const uint2 p = *reinterpret_cast<const uint2 *>(&tb->Lw[mt][bits8 ? 4 : 'N'][0]);
-	plo = p.x; p4 = p.y;
-      } else {
-	const uint2 p = *reinterpret_cast<const uint2 *>(&tb->Lw[mt][sd.g(i) & 127][0]);
-	const uint2 pa = *reinterpret_cast<const uint2 *>(&tb->Lw[mt][sd.ga(i) & 127][0]);
-	plo = __vmaxs4(p.x,pa.x); p4 = __vmaxs4(p.y,pa.y);
-      }
+  for (int i = lane; i <= f.nA; i += 32) {
+    uint2 p;
+    if (!f.lower) {
+      const int q = (i == 0) ? 'N' : sd.q(i);
+      p = *reinterpret_cast<const uint2 *>(&tb->U[mt][q & 127][0]);
+    } else if (i == 0) {
+      p = *reinterpret_cast<const uint2 *>(&tb->Lw[mt][bits8 ? 4 : 'N'][0]);
+    } else {
+      const uint2 a = *reinterpret_cast<const uint2 *>(&tb->Lw[mt][sd.g(i) & 127][0]);
+      const uint2 c = *reinterpret_cast<const uint2 *>(&tb->Lw[mt][sd.ga(i) & 127][0]);
+      p.x = __vmaxs4(a.x,c.x); p.y = __vmaxs4(a.y,c.y);
     }
-
-    int E = NEG, Hcur = NEG, H = NEG;
-    int bprev = (lane == 0 && i0 > 0) ? (int) brow[i0 - 1] : 0, bnext = 0;
-    uint32_t dacc = 0, sacc = 0;
-    uint32_t *dst = pl.dirs + (size_t) s * pl.g.dirW + lane;
-    uint32_t *sst = pl.sc ? pl.sc + (size_t) s * pl.g.scW + lane : NULL;
-
-    for (int j = jlo; j <= jhi; j++) {
-      const int tt = j - jlo;
-      int up = __shfl_up_sync(FULLMASK,Hcur,1);
-      if (lane == 0) { up = bprev; if (i0 > 0) bnext = brow[j]; }
-      const int code = stepcode[j];
-      const bool act = rowact && j >= i && j <= jend;
-      uint32_t bits = 0;
-      if (act) {
-	const int diag = (j == 0) ? 0 : (i == 0 ? NEG : up);
-	const int sc = max(prof_pick(plo,p4,code & 15),prof_pick(plo,p4,code >> 4));
-	const int Hd = clampi(diag + sc,NEG,POS);
-	if (j == i) {
-	  E = NEG; H = Hd;
-	} else {
-	  const int T1 = max(Hcur + open,NEG);
-	  const bool dE = late ? (E >= T1) : (E > T1);
-	  E = max(max(E,T1) + extend,NEG);
-	  const bool dN = late ? (E >= Hd) : (E > Hd);
-	  H = max(Hd,E);
-	  bits = (dN ? 1u : 0u) | (dE ? 2u : 0u);
-	}
-	Hcur = H;
-	if (bt) {
-	  const int r = LOWER ? j : i, c = LOWER ? i : j;
-	  if (r >= 1 && c >= 1 && (!LOWER || j > i) && (!lastrow || r == sd.rlen)) {
-	    const int key = (r << 16) | c;
-	    if (H > bt->bs || (H == bt->bs && (late ? key > bt->bk : key < bt->bk))) { bt->bs = H; bt->bk = key; }
-	  }
-	}
-      }
-      __syncwarp();
-      if (lane == 31 && act) brow[j] = (short) H;
-      if (lane == 0) bprev = bnext;
-      dacc |= bits << (2 * (tt & 15));
-      if ((tt & 15) == 15) { dst[(tt >> 4) * 32] = dacc; dacc = 0; }
-      if (sst) {
-	sacc |= ((uint32_t) H & 0xffffu) << (16 * (tt & 1));
-	if (tt & 1) { sst[(tt >> 1) * 32] = sacc; sacc = 0; }
-      }
-    }
-    const int nsteps = jhi - jlo + 1;
-    if (nsteps & 15) dst[(nsteps >> 4) * 32] = dacc;
-    if (sst && (nsteps & 1)) sst[(nsteps >> 1) * 32] = sacc;
-    __syncwarp();
+    prof[i] = p;
   }
 }
 
-/* 2-bit direction cell of an E-only fill; (i,j) = (lane-axis index, step-axis index).  Out of band -> 0. */
-__device__ __forceinline__ uint32_t tri_dir (const TriPlanes &pl, int i, int j) {
-  if (i < 0 || i > pl.g.nA || j < i || j > i + pl.g.band || j > pl.g.nB) return 0;
-  const int s = i >> 5, l = i & 31, tt = j - (s << 5);
-  const uint32_t w = pl.dirs[(size_t) s * pl.g.dirW + (tt >> 4) * 32 + l];
-  return (w >> (2 * (tt & 15))) & 3u;
-}
-__device__ __forceinline__ int tri_score (const TriPlanes &pl, int i, int j) {
-  const int s = i >> 5, l = i & 31, tt = j - (s << 5);
-  const uint32_t w = pl.sc[(size_t) s * pl.g.scW + (tt >> 1) * 32 + l];
-  return (int) (short) (w >> (16 * (tt & 1)));
+/* One pass: every lane owns one band diagonal of one of the (up to GDP_MAXFILLS) fills packed into it. */
+template <bool SCORES, bool TRACK>
+__device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
+			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge) {
+  const int lane = threadIdx.x & 31;
+  /* lane configuration */
+  int d = -1, nA = -1, nB = -1, lateadd = 0, thi = -1, tlo = 0x7fffffff;
+  bool lower = false, edge_in = false, edge_out = false;
+  const uint2 *prof = NULL; const uint8_t *code = NULL;
+  uint32_t *dplane = NULL, *splane = NULL;
+#pragma unroll
+  for (int f = 0; f < GDP_MAXFILLS; f++) {
+    if (f < nf && pass >= F[f].pass0 && pass < F[f].pass0 + F[f].npass) {
+      const int p = pass - F[f].pass0;
+      const int dd = (lane - F[f].lane0) + 32 * p;
+      thi = max(thi,F[f].nB);
+      tlo = min(tlo,32 * p);
+      if (lane >= F[f].lane0 && dd <= F[f].band && (F[f].npass > 1 || lane - F[f].lane0 <= F[f].band)) {
+	d = dd; nA = F[f].nA; nB = F[f].nB; lateadd = F[f].lateadd; lower = F[f].lower;
+	prof = F[f].prof; code = F[f].code;
+	dplane = F[f].dirs + (size_t) p * F[f].dirPW;
+	splane = SCORES ? F[f].sc + (size_t) p * F[f].scPW : NULL;
+	edge_in = (p > 0 && lane == 0);
+	edge_out = (p + 1 < F[f].npass && lane == 31);
+      }
+    }
+  }
+  if (thi < 0) return;
+  /* planes are shared by the fills of the pass: all lanes store, inactive lanes store zeros */
+  if (dplane == NULL) {
+#pragma unroll
+    for (int f = 0; f < GDP_MAXFILLS; f++)
+      if (f < nf && pass >= F[f].pass0 && pass < F[f].pass0 + F[f].npass) {
+	dplane = F[f].dirs + (size_t) (pass - F[f].pass0) * F[f].dirPW;
+	splane = SCORES ? F[f].sc + (size_t) (pass - F[f].pass0) * F[f].scPW : NULL;
+      }
+  }
+  dplane += lane; if (SCORES) splane += lane;
+
+  int Hprev = NEG, E = NEG, H = NEG;
+  uint32_t pk_out = 0, dacc = 0, sacc = 0;
+  for (int t = tlo; t <= thi; t++) {
+    uint32_t pk_in = __shfl_up_sync(FULLMASK,pk_out,1);
+    const int i = t - d;
+    const bool act = (d >= 0) && i >= 0 && i <= nA && t <= nB;
+    uint32_t bits = 0;
+    if (act) {
+      if (edge_in) pk_in = edge[i];
+      const uint2 p = prof[i];
+      const int cd = code[t];
+      const int diag = (t == 0) ? 0 : (i == 0 ? NEG : Hprev);
+      const int sc = max(prof_pick(p.x,p.y,cd & 15),prof_pick(p.x,p.y,cd >> 4));
+      const int Hd = clampi(diag + sc,NEG,POS);
+      if (d == 0) {
+	E = NEG; H = Hd;
+      } else {
+	const int Hl = (int) (short) (pk_in & 0xffffu), El = ((int) pk_in) >> 16;
+	const int T1 = max(Hl + open,NEG);
+	const bool dE = (El + lateadd > T1);
+	E = max(max(El,T1) + extend,NEG);
+	const bool dN = (E + lateadd > Hd);
+	H = max(Hd,E);
+	bits = (dN ? 1u : 0u) | (dE ? 2u : 0u);
+      }
+      Hprev = H;
+      pk_out = ((uint32_t) H & 0xffffu) | ((uint32_t) E << 16);
+      if (edge_out) edge[i] = pk_out;
+      if (TRACK) {
+	const int r = lower ? t : i, c = lower ? i : t;
+	if (r >= 1 && c >= 1 && (!lower || d > 0) && (!lastrow || r == track_rlen)) {
+	  const int key = (r << 16) | c;
+	  if (H > bt->bs || (H == bt->bs && (lateadd ? key > bt->bk : key < bt->bk))) { bt->bs = H; bt->bk = key; }
+	}
+      }
+    }
+    dacc |= bits << (2 * (t & 15));
+    if ((t & 15) == 15) { dplane[(t >> 4) * 32] = dacc; dacc = 0; }
+    if (SCORES) {
+      sacc |= ((uint32_t) H & 0xffffu) << (16 * (t & 1));
+      if (t & 1) { splane[(t >> 1) * 32] = sacc; sacc = 0; }
+    }
+  }
+  if ((thi & 15) != 15) dplane[(thi >> 4) * 32] = dacc;
+  if (SCORES && !(thi & 1)) splane[(thi >> 1) * 32] = sacc;
+  __syncwarp();
 }
 
-/* Full fill: Dynprog_simd_8 / _16, stripe-faithful. */
-__device__ void fill_full (const SideSeq &sd, const uint8_t *gcode, int lband, int uband, int mt, int open, int extend,
-			   bool late, int NEG, int POS, uint32_t *dirs, const FGeom &fg,
-			   short *Hrow, int *FF, int *corner, const GdpTables *tb) {
+/* all passes of a box's E-only fills */
+template <bool SCORES, bool TRACK>
+__device__ void tri_fill_all (const TriFill (&F)[GDP_MAXFILLS], int nf, int npasses, int open, int extend, int NEG, int POS,
+			      BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge) {
+  for (int pass = 0; pass < npasses; pass++) tri_pass<SCORES,TRACK>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge);
+}
+
+/* Full fill: Dynprog_simd_8 / _16, stripe-faithful.
+ *
+ * Per-warp shared memory holds one 8-byte boundary entry per genome column c:
+ *   .x = (H of the previous stripe's last row at column c, 16 bits) | (class code of column c << 16),  .y = FF[c]
+ * (FF = the reference's int carry of the vertical gap between stripes, dynprog_simd.c:3422-3432,3471).
+ * Lane 0 reads its column's entry, lane 31 rewrites it for the next stripe; the class code travels down
+ * the lanes packed into the same shuffle as H, so only lanes 0 and 31 touch memory in the inner loop.
+ *
+ * Each stripe's steps are split into edge steps (some lane is outside the band, on its edge, on column 0
+ * or past the last row: the literal restatement of :3257-3478) and interior steps (every lane strictly
+ * inside the band), which need none of the edge logic. */
+struct FullLane { int E, Hl, diag, cg_out, pk_out, bprevH; };
+
+template <bool LATE, bool FAST>
+__device__ __forceinline__ uint32_t full_step (FullLane &st, const int lane, const int c, const int r, const bool rowact,
+					       const int rlo, const int c0, const int chigh, const int lband, const int uband,
+					       const int open, const int extend, const int NEG, const int POS,
+					       const uint32_t plo, const uint32_t p4, uint2 *bnd) {
+  int cg_in = __shfl_up_sync(FULLMASK,st.cg_out,1);
+  const int pk_in = __shfl_up_sync(FULLMASK,st.pk_out,1);
+  const bool act = FAST ? true : (rowact && c >= c0 && c <= chigh);
+  uint32_t nib = 0;
+  if (act) {
+    int last_in = (int) (short) (pk_in & 0xffff);	/* final H(r-1,c) = the F pass's last_nogap */
+    int code = (int) ((uint32_t) pk_in >> 16);
+    int Hs = st.diag;
+    if (lane == 0) {
+      const uint2 e = bnd[c];
+      const int bH = (int) (short) (e.x & 0xffffu);
+      code = (int) (e.x >> 16);
+      if (rlo == 0) {
+	Hs = (!FAST && c == 0) ? 0 : NEG;
+	cg_in = NEG32; last_in = NEG32;
+      } else {
+	Hs = (!FAST && c == 0) ? NEG : st.bprevH;
+	if (FAST || c < rlo + uband) { cg_in = (int) e.y; last_in = bH; }
+	else { cg_in = NEG32; last_in = NEG32; }
+      }
+      st.bprevH = bH;
+    }
+    /* E (horizontal gap), dynprog_simd.c:3318-3334 */
+    const int T1 = max(st.Hl + open,NEG);
+    bool dE = LATE ? (st.E >= T1) : (st.E > T1);
+    st.E = max(max(st.E,T1) + extend,NEG);
+    /* H, :3350-3389 */
+    int sc;
+    if (!FAST && c == 0) sc = (r == 0) ? 0 : NEG;
+    else sc = max(prof_pick(plo,p4,code & 15),prof_pick(plo,p4,(code >> 4) & 15));
+    const int Hd = clampi(Hs + sc,NEG,POS);
+    uint32_t dN = (LATE ? (st.E >= Hd) : (st.E > Hd)) ? 1u : 0u;
+    int H = max(Hd,st.E);
+    bool dF = false;
+    if (FAST) {
+      /* F (vertical gap), :3449-3469 */
+      const int score = last_in + open;
+      dF = LATE ? (cg_in >= score) : (cg_in > score);
+      const int cg = (dF ? cg_in : score) + extend;
+      const bool tV = LATE ? (cg >= H) : (cg > H);
+      H = tV ? cg : H; dN = tV ? 2u : dN;
+      st.cg_out = cg;
+    } else if (r >= c - uband && r <= c + lband) {
+      if (r == c + lband && c > 0) { H = Hd; dE = false; dN = 0; }	/* bottom of band forced DIAG, :3395-3417 */
+      if (r == c - uband) {						/* top of band, :3434-3446 */
+	st.cg_out = NEG32 + open + extend;
+      } else {
+	const int score = last_in + open;
+	dF = LATE ? (cg_in >= score) : (cg_in > score);
+	const int cg = (dF ? cg_in : score) + extend;
+	const bool tV = LATE ? (cg >= H) : (cg > H);
+	H = tV ? max(cg,NEG) : H; dN = tV ? 2u : dN;
+	st.cg_out = cg;
+      }
+    }
+    st.diag = last_in;
+    st.Hl = H;
+    st.pk_out = (H & 0xffff) | (code << 16);
+    if (lane == 31) bnd[c] = make_uint2((uint32_t) st.pk_out,(uint32_t) st.cg_out);
+    nib = dN | (dE ? 4u : 0u) | (dF ? 8u : 0u);
+  }
+  return nib;
+}
+
+template <bool LATE>
+__device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int open, int extend,
+			   int NEG, int POS, uint32_t *dirs, const FGeom &fg, uint2 *bnd, const GdpTables *tb) {
   const int lane = threadIdx.x & 31;
   const int rlen = sd.rlen, glen = sd.glen;
+  /* class codes of the genome columns into the boundary entries */
+  for (int c = lane; c <= glen; c += 32) {
+    const uint32_t code = (c == 0) ? 0x44u : (uint32_t) (nt_class(sd.g(c)) | (nt_class(sd.ga(c)) << 4));
+    bnd[c] = make_uint2(code << 16,0u);
+  }
+  __syncwarp();
   int s = 0;
   for (int rlo = 0; rlo <= rlen; rlo += 32, s++) {
     const int rhigh = min(rlo + 31,rlen);
@@ -182,74 +303,37 @@ __device__ void fill_full (const SideSeq &sd, const uint8_t *gcode, int lband, i
     const int chigh = min(rhigh + uband,glen);
     if (c0 > chigh) continue;
     const int nsteps = (chigh - c0 + 1) + 31;
+    /* interior steps: every lane has 1 <= c, c0 <= c <= chigh and r - lband < c < r + uband */
+    int fs = nsteps, fe = -1;
+    if (rhigh == rlo + 31) {
+      fs = max(max(c0,1),rlo + 31 - lband + 1) - c0 + 31;
+      fe = min(chigh,rlo + uband - 1) - c0;
+      if (fs > fe) { fs = nsteps; fe = -1; }
+    }
 
     uint32_t plo = 0, p4 = 0;
     if (rowact) {
-      int q = (r == 0) ? 'N' : sd.q(r);
+      const int q = (r == 0) ? 'N' : sd.q(r);
       const uint2 p = *reinterpret_cast<const uint2 *>(&tb->U[mt][q & 127][0]);
       plo = p.x; p4 = p.y;
     }
-    int E = late ? NEG : NEG + 1;
-    int Hl = NEG - open;
-    int diag = NEG - open;
-    int cg_out = NEG32, last_out = NEG32;
+    FullLane st;
+    st.E = LATE ? NEG : NEG + 1;
+    st.Hl = NEG - open; st.diag = NEG - open;
+    st.cg_out = NEG32; st.pk_out = 0;
+    st.bprevH = (lane == 0 && rlo > 0 && c0 > 0) ? (int) (short) (bnd[c0 - 1].x & 0xffffu) : NEG;
     uint32_t acc = 0;
     uint32_t *dst = dirs + (size_t) s * fg.dirW + lane;
-
-    for (int tt = 0; tt < nsteps; tt++) {
-      const int c = c0 + tt - lane;
-      int cg_in = __shfl_up_sync(FULLMASK,cg_out,1);
-      int last_in = __shfl_up_sync(FULLMASK,last_out,1);
-      const bool act = rowact && c >= c0 && c <= chigh;
-      uint32_t nib = 0;
-      if (act) {
-	int Hs;
-	if (lane == 0) {
-	  if (c == 0) Hs = (rlo == 0) ? 0 : NEG;
-	  else Hs = (rlo == 0) ? NEG : (int) Hrow[c - 1];
-	  if (rlo == 0 || c >= rlo + uband) { cg_in = NEG32; last_in = NEG32; }
-	  else { cg_in = FF[c]; last_in = (int) Hrow[c]; }
-	} else {
-	  Hs = diag;
-	}
-	/* E (horizontal gap), dynprog_simd.c:3318-3334 */
-	const int T1 = max(Hl + open,NEG);
-	bool dE = late ? (E >= T1) : (E > T1);
-	E = max(max(E,T1) + extend,NEG);
-	/* H, :3350-3389 */
-	int sc;
-	if (c == 0) sc = (r == 0) ? 0 : NEG;
-	else { const int code = gcode[c]; sc = max(prof_pick(plo,p4,code & 15),prof_pick(plo,p4,code >> 4)); }
-	const int Hd = clampi(Hs + sc,NEG,POS);
-	uint32_t dN = (late ? (E >= Hd) : (E > Hd)) ? 1u : 0u;
-	int H = max(Hd,E);
-	uint32_t dF = 0;
-	const bool inband = (r >= c - uband) && (r <= c + lband);
-	if (inband) {
-	  if (r == c + lband && c > 0) { H = Hd; dE = false; dN = 0; }	/* bottom of band forced DIAG, :3395-3417 */
-	  int cg, last;
-	  if (r == c - uband) {						/* top of band, :3434-3446 */
-	    cg = NEG32 + open + extend; last = H;
-	  } else {
-	    const int score = last_in + open;
-	    if (late ? (cg_in >= score) : (cg_in > score)) { cg = cg_in + extend; dF = 1; }
-	    else cg = score + extend;
-	    last = H;
-	    if (late ? (cg >= last) : (cg > last)) { last = cg; H = max(cg,NEG); dN = 2; }
-	  }
-	  cg_out = cg; last_out = last;
-	} else {
-	  last_out = H;
-	}
-	diag = last_in;
-	Hl = H;
-	if (lane == 31) { Hrow[c] = (short) H; FF[c] = cg_out; }
-	if (r == rlen && c == glen) *corner = H;
-	nib = dN | (dE ? 4u : 0u) | (dF ? 8u : 0u);
-      }
-      acc |= nib << (4 * (tt & 7));
-      if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; }
-    }
+    int tt = 0, c = c0 - lane;
+#define FULL_STEP(FASTFLAG) do { \
+      const uint32_t nib = full_step<LATE,FASTFLAG>(st,lane,c,r,rowact,rlo,c0,chigh,lband,uband,open,extend,NEG,POS,plo,p4,bnd); \
+      acc |= nib << (4 * (tt & 7)); \
+      if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; } } while (0)
+    const int e1 = min(fs,nsteps);
+    for ( ; tt < e1; tt++, c++) FULL_STEP(false);
+    for ( ; tt <= fe; tt++, c++) FULL_STEP(true);
+    for ( ; tt < nsteps; tt++, c++) FULL_STEP(false);
+#undef FULL_STEP
     if (nsteps & 7) dst[(nsteps >> 3) * 32] = acc;
     __syncwarp();
   }
@@ -265,67 +349,127 @@ __device__ __forceinline__ uint32_t full_dir (const uint32_t *dirs, const FGeom 
 }
 
 /* ------------------------------------------------------------------------------------------------
- * Tracebacks (lane 0).  Literal replays of the reference's loops, including the post-decrement
- * conditions (dynprog_simd.c:9175,9342,9459).
+ * Tracebacks, warp-cooperative.  The reference walks one cell at a time (dynprog_simd.c:9154-9946);
+ * here the 32 lanes look at 32 consecutive cells of the current diagonal at once: a ballot finds
+ * the first non-DIAG cell, the diagonal run before it is emitted and scored in one go (matches and
+ * mismatches by popcount), then the gap run is measured with a second ballot along the row / column,
+ * replaying the reference's post-decrement loop conditions (:9175,9342,9459) exactly.
+ * All lanes hold the same (r, c) and counters; lane 0 writes the edit script.
  * ---------------------------------------------------------------------------------------------- */
 struct TbAcc {
   int score, nmatches, nmismatches, nopens, nindels;
   uint32_t *ops; int nops; int pend;
-  __device__ __forceinline__ void flush () { if (pend) { ops[nops++] = ((uint32_t) pend << 2); pend = 0; } }
+  __device__ __forceinline__ void flush () {
+    if (pend) { if ((threadIdx.x & 31) == 0) ops[nops] = ((uint32_t) pend << 2); nops++; pend = 0; }
+  }
   __device__ __forceinline__ void gap (int kind, int dist, bool scored) {
-    flush(); ops[nops++] = ((uint32_t) dist << 2) | (uint32_t) kind;
+    flush();
+    if ((threadIdx.x & 31) == 0) ops[nops] = ((uint32_t) dist << 2) | (uint32_t) kind;
+    nops++;
     if (scored) { score += -3 - dist; nopens += 1; nindels += dist; }
   }
 };
 
-__device__ __forceinline__ void tb_diag (TbAcc &a, const SideSeq &sd, int r, int c, const GdpTables *tb) {
-  const int c1 = sd.q(r) & 127, c2 = sd.g(c) & 127, c2a = sd.ga(c) & 127;
-  a.pend++;
-  if (c2 == '*') return;
-  if (c1 == c2 || c1 == c2a || ((tb->cons[c1][c2 >> 5] >> (c2 & 31)) & 1u) || ((tb->cons[c1][c2a >> 5] >> (c2a & 31)) & 1u)) {
-    a.score += 1; a.nmatches += 1;
-  } else {
-    a.score += -3; a.nmismatches += 1;
+/* scores the n leading cells (r-k, c-k), k < n, of the diagonal; lane k looks at cell k */
+__device__ __forceinline__ void tb_diag_run (TbAcc &a, const SideSeq &sd, int r, int c, int n, const GdpTables *tb) {
+  const int k = threadIdx.x & 31;
+  bool isM = false, isX = false;
+  if (k < n) {
+    const int c1 = sd.q(r - k) & 127, c2 = sd.g(c - k) & 127, c2a = sd.ga(c - k) & 127;
+    if (c2 != '*') {
+      isM = (c1 == c2 || c1 == c2a || ((tb->cons[c1][c2 >> 5] >> (c2 & 31)) & 1u) || ((tb->cons[c1][c2a >> 5] >> (c2a & 31)) & 1u));
+      isX = !isM;
+    }
   }
+  const int nm = __popc(__ballot_sync(FULLMASK,isM)), nx = __popc(__ballot_sync(FULLMASK,isX));
+  a.score += nm - 3 * nx; a.nmatches += nm; a.nmismatches += nx;
+  a.pend += n;
 }
 
-__device__ void tb_upper (TbAcc &a, const SideSeq &sd, const TriPlanes &pl, int r, int c, const GdpTables *tb) {
+__device__ __forceinline__ int first_set (uint32_t m) { return m ? (__ffs(m) - 1) : 32; }
+
+__device__ void tb_upper (TbAcc &a, const SideSeq &sd, const TriFill &pl, int r, int c, const GdpTables *tb) {
+  const int k = threadIdx.x & 31;
   while (r > 0 && c > 0) {
-    if (tri_dir(pl,r,c) & 1u) {
+    const bool valid = (r - k > 0) && (c - k > 0);
+    const bool stop = !valid || (tri_dir(pl,r - k,c - k) & 1u);
+    const uint32_t m = __ballot_sync(FULLMASK,stop);
+    const int n = first_set(m);
+    if (n > 0) { tb_diag_run(a,sd,r,c,n,tb); r -= n; c -= n; }
+    if (n < 32 && r > 0 && c > 0) {
+      /* horizontal gap: dist = 1; while (dirE[c--][r] != DIAG) dist++; */
       int dist = 1;
-      for (;;) { const uint32_t e = tri_dir(pl,r,c) & 2u; c--; if (!e || c < 0) break; dist++; }
+      for (;;) {
+	const bool z = (c - k < 0) || !(tri_dir(pl,r,c - k) & 2u);
+	const int kz = first_set(__ballot_sync(FULLMASK,z));
+	if (kz < 32) { dist += kz; c -= kz + 1; break; }
+	dist += 32; c -= 32;
+      }
       a.gap(1,dist,dist < 9);
-    } else { tb_diag(a,sd,r,c,tb); r--; c--; }
+    }
   }
   a.flush();
-  if (c > 0) { a.score += (c < 9) ? (-3 - c) : 0; if (c < 9) { a.nopens += 1; a.nindels += c; } }
+  if (c > 0 && c < 9) { a.score += -3 - c; a.nopens += 1; a.nindels += c; }
 }
 
-__device__ void tb_lower (TbAcc &a, const SideSeq &sd, const TriPlanes &pl, int r, int c, const GdpTables *tb) {
+__device__ void tb_lower (TbAcc &a, const SideSeq &sd, const TriFill &pl, int r, int c, const GdpTables *tb) {
+  const int k = threadIdx.x & 31;
   while (r > 0 && c > 0) {
-    if (tri_dir(pl,c,r) & 1u) {
+    const bool valid = (r - k > 0) && (c - k > 0);
+    const bool stop = !valid || (tri_dir(pl,c - k,r - k) & 1u);
+    const uint32_t m = __ballot_sync(FULLMASK,stop);
+    const int n = first_set(m);
+    if (n > 0) { tb_diag_run(a,sd,r,c,n,tb); r -= n; c -= n; }
+    if (n < 32 && r > 0 && c > 0) {
       int dist = 1;
-      for (;;) { const uint32_t e = tri_dir(pl,c,r) & 2u; r--; if (!e || r < 0) break; dist++; }
+      for (;;) {
+	const bool z = (r - k < 0) || !(tri_dir(pl,c,r - k) & 2u);
+	const int kz = first_set(__ballot_sync(FULLMASK,z));
+	if (kz < 32) { dist += kz; r -= kz + 1; break; }
+	dist += 32; r -= 32;
+      }
       a.gap(2,dist,true);
-    } else { tb_diag(a,sd,r,c,tb); r--; c--; }
+    }
   }
   a.flush();
   if (r > 0) { a.score += -3 - r; a.nopens += 1; a.nindels += r; }
 }
 
 __device__ void tb_full (TbAcc &a, const SideSeq &sd, const uint32_t *dirs, const FGeom &fg, int r, int c, const GdpTables *tb) {
+  const int k = threadIdx.x & 31;
   while (r > 0 && c > 0) {
-    const uint32_t nib = full_dir(dirs,fg,r,c);
-    const uint32_t dir = nib & 3u;
-    if (dir == 1u) {
+    const bool valid = (r - k > 0) && (c - k > 0);
+    const uint32_t nib = valid ? full_dir(dirs,fg,r - k,c - k) : 0u;
+    const bool stop = !valid || (nib & 3u);
+    const uint32_t m = __ballot_sync(FULLMASK,stop);
+    const int n = first_set(m);
+    if (n > 0) { tb_diag_run(a,sd,r,c,n,tb); r -= n; c -= n; }
+    if (n < 32 && r > 0 && c > 0) {
+      const uint32_t dir = __shfl_sync(FULLMASK,nib,n) & 3u;
       int dist = 1;
-      for (;;) { if (!(c > 0)) break; const uint32_t e = full_dir(dirs,fg,r,c) & 4u; c--; if (!e) break; dist++; }
-      a.gap(1,dist,dist < 9);
-    } else if (dir == 2u) {
-      int dist = 1;
-      for (;;) { if (!(r > 0)) break; const uint32_t f = full_dir(dirs,fg,r,c) & 8u; r--; if (!f) break; dist++; }
-      a.gap(2,dist,true);
-    } else { tb_diag(a,sd,r,c,tb); r--; c--; }
+      if (dir == 1u) {
+	/* dist = 1; while (c > 0 && dirE[c--][r] != DIAG) dist++; */
+	for (;;) {
+	  const bool cond = (c - k > 0);
+	  const bool z = !cond || !(full_dir(dirs,fg,r,c - k) & 4u);
+	  const uint32_t zm = __ballot_sync(FULLMASK,z);
+	  const int kz = first_set(zm);
+	  if (kz < 32) { const bool condz = (c - kz > 0); dist += kz; c -= condz ? kz + 1 : kz; break; }
+	  dist += 32; c -= 32;
+	}
+	a.gap(1,dist,dist < 9);
+      } else {
+	for (;;) {
+	  const bool cond = (r - k > 0);
+	  const bool z = !cond || !(full_dir(dirs,fg,r - k,c) & 8u);
+	  const uint32_t zm = __ballot_sync(FULLMASK,z);
+	  const int kz = first_set(zm);
+	  if (kz < 32) { const bool condz = (r - kz > 0); dist += kz; r -= condz ? kz + 1 : kz; break; }
+	  dist += 32; r -= 32;
+	}
+	a.gap(2,dist,true);
+      }
+    }
   }
   a.flush();
   if (r == 0 && c == 0) {
@@ -359,8 +503,8 @@ __device__ __forceinline__ int intron_points (const int *isc, int ldi, int rdi) 
 }
 
 /* bridge_intron_gap_{8,16}_site_level, dynprog_genome.c:866-1386.  Returns finalscore. */
-__device__ int bridge_genome (const gmapdp_box &b, const TriPlanes &LU, const TriPlanes &LL, const TriPlanes &RU,
-			      const TriPlanes &RL, const uint8_t *ldi, const uint8_t *rdi, const double *lp,
+__device__ int bridge_genome (const gmapdp_box &b, const TriFill &LU, const TriFill &LL, const TriFill &RU,
+			      const TriFill &RL, const uint8_t *ldi, const uint8_t *rdi, const double *lp,
 			      const double *rp, int NEG, const int *isc, int *bestrL, int *bestrR, int *bestcL, int *bestcR) {
   const int lane = threadIdx.x & 31;
   const int rlength = b.rlenL, glengthL = b.glenL, glengthR = b.glenR;
@@ -436,20 +580,25 @@ __device__ int bridge_genome (const gmapdp_box &b, const TriPlanes &LU, const Tr
 /* bridge_cdna_gap_{8,16}_ud, dynprog_cdna.c:123-375.
  *
  * The reference scans (cL asc, cR desc, rL asc, rR asc) keeping the best score with >= (jump late:
- * the LAST maximum in scan order wins) or > (the FIRST wins), subject to rR < lim - rL.  That is an
- * argmax with a positional tie-break, so it is evaluated here as
- *   phase 1: for every cR a prefix-best table over rR (best score and its rR for rR <= k), which
- *            answers "best rR under the constraint" in O(1);
- *   phase 2: for every (cL, rL, cR) one table lookup; candidates carry their scan position as a key.
- * O(g^2 * band) instead of O(g^2 * band^2). */
-__device__ int bridge_cdna (const gmapdp_box &b, const TriPlanes &LU, const TriPlanes &LL, const TriPlanes &RU,
-			    const TriPlanes &RL, int NEG, uint32_t *pb, int *bestcL, int *bestcR, int *bestrL, int *bestrR) {
+ * the LAST maximum in scan order wins) or > (the FIRST wins), subject to rR < lim - rL.  The score is
+ * scoreL(cL,rL) + scoreR(cR,rR) + pen(cL,cR) with pen = 0 for cR = glength-cL and `open' otherwise, so
+ * the scan is an argmax with a positional tie-break and is evaluated from three tables:
+ *   pb[cR][k]  best scoreR over rR <= k (and its rR)                       -- handles the rR constraint
+ *   M[cR]      = pb[cR][all rR]                                            -- the unconstrained column best
+ *   Q[j]       best of M[cR] over cR <= j (and its cR), tie rule on cR     -- the unconstrained cR best
+ * For one (cL,rL): the pen = 0 column and the (at most lbandR+ubandR) columns whose rR range is cut by
+ * the constraint are looked up in pb, all other columns are answered by one Q lookup.
+ * O(g * band * (1 + cut columns)) instead of O(g^2 * band^2). */
+__device__ int bridge_cdna (const gmapdp_box &b, const TriFill &LU, const TriFill &LL, const TriFill &RU,
+			    const TriFill &RL, int NEG, uint32_t *pb, uint32_t *smemMQ, int *bestcL, int *bestcR, int *bestrL, int *bestrR) {
   const int lane = threadIdx.x & 31;
   const int glength = b.glenL, rlengthL = b.rlenL, rlengthR = b.rlenR;
   const int lbandL = b.lbandL, ubandL = b.ubandL, lbandR = b.lbandR, ubandR = b.ubandR;
   const int open = b.open, lim = b.offdiff;
   const bool late = (b.flags & GMAPDP_F_BRIDGE_LATE) != 0;
   const int PBW = lbandR + ubandR + 1;
+  uint32_t *M = smemMQ, *Q = smemMQ + (glength + 1);	/* packed (score+32768)<<16 | rR  and  (score+32768)<<16 | cR */
+  const uint32_t NONE = 0u;				/* score field 0 = "no rR in range" (a real score is >= -32768+... > field 0 only if > -32768) */
 
   for (int cR = lane; cR <= glength; cR += 32) {
     const int lo = max(cR - ubandR,1), hi = min(cR + lbandR,rlengthR - 1);
@@ -460,32 +609,68 @@ __device__ int bridge_cdna (const gmapdp_box &b, const TriPlanes &LU, const TriP
       if (!have || (late ? sc >= bs : sc > bs)) { bs = sc; br = rR; have = true; }
       row[rR] = ((uint32_t) (bs + 32768) << 16) | (uint32_t) br;
     }
+    M[cR] = have ? (((uint32_t) (bs + 32768) << 16) | (uint32_t) br) : NONE;
+  }
+  __syncwarp();
+  /* Q: prefix best over cR.  The scan visits cR in DESCENDING order, so "late" (last wins) keeps the
+     smallest cR among equal scores and "early" the largest. */
+  if (lane == 0) {
+    int bs = 0, bc = -1;
+    for (int cR = 0; cR <= glength; cR++) {
+      const uint32_t m = M[cR];
+      const bool valid = (m != NONE) || (min(cR + lbandR,rlengthR - 1) >= max(cR - ubandR,1));
+      if (valid) {
+	const int sc = (int) (m >> 16) - 32768;
+	if (bc < 0 || (late ? sc > bs : sc >= bs)) { bs = sc; bc = cR; }
+      }
+      Q[cR] = (bc < 0) ? 0xffffffffu : (((uint32_t) (bs + 32768) << 16) | (uint32_t) bc);
+    }
   }
   __syncwarp();
 
   int bs = NEG; unsigned long long bk = 0; bool have = false;
   int bcL = 0, bcR = 0, brL = 0, brR = 0;
+#define CDNA_CAND(CR,SCORE_R,RR,PEN) do { \
+    const int score_ = scoreL + (SCORE_R) + (PEN); \
+    const unsigned long long key_ = ((unsigned long long) (glength - (CR)) << 32) | ((unsigned long long) rL << 16) | (unsigned long long) (RR); \
+    bool take_; \
+    if (!have) take_ = late ? (score_ >= bs) : (score_ > bs); \
+    else if (score_ != bs) take_ = score_ > bs; \
+    else take_ = late ? (key_ > bk) : (key_ < bk); \
+    if (take_) { bs = score_; bk = key_; bcL = cL; bcR = (CR); brL = rL; brR = (RR); have = true; } } while (0)
+
   for (int cL = 1 + lane; cL < glength; cL += 32) {
     const int rloL = max(cL - ubandL,1), rhighL = min(cL + lbandL,rlengthL - 1);
+    const int cR0 = glength - cL;
     for (int rL = rloL; rL <= rhighL; rL++) {
       const int scoreL = (rL < cL) ? tri_score(LU,rL,cL) : tri_score(LL,cL,rL);
-      const int rcap = lim - rL - 1;
-      for (int cR = glength - cL; cR >= 0; cR--) {
-	const int lo = max(cR - ubandR,1);
-	const int k = min(min(cR + lbandR,rlengthR - 1),rcap);
-	if (k < lo) continue;
+      const int rcap = lim - rL - 1;			/* rR <= rcap */
+      /* the pen = 0 column */
+      {
+	const int lo = max(cR0 - ubandR,1), k = min(min(cR0 + lbandR,rlengthR - 1),rcap);
+	if (k >= lo) {
+	  const uint32_t e = pb[(size_t) cR0 * PBW + (k - (cR0 - ubandR))];
+	  CDNA_CAND(cR0,(int) (e >> 16) - 32768,(int) (e & 0xffffu),0);
+	}
+      }
+      /* columns cR < cR0 (pen = open): those with cR + lbandR <= rcap are unconstrained */
+      int junc = min(cR0 - 1,(rcap >= rlengthR - 1) ? cR0 - 1 : rcap - lbandR);
+      if (junc >= 0) {
+	const uint32_t qe = Q[junc];
+	if (qe != 0xffffffffu) {
+	  const int cR = (int) (qe & 0xffffu);
+	  CDNA_CAND(cR,(int) (qe >> 16) - 32768,(int) (M[cR] & 0xffffu),open);
+	}
+      }
+      for (int cR = max(junc + 1,0); cR <= cR0 - 1; cR++) {
+	const int lo = max(cR - ubandR,1), k = min(min(cR + lbandR,rlengthR - 1),rcap);
+	if (k < lo) break;				/* lo grows with cR: nothing further can qualify */
 	const uint32_t e = pb[(size_t) cR * PBW + (k - (cR - ubandR))];
-	const int score = scoreL + ((int) (e >> 16) - 32768) + ((cR == glength - cL) ? 0 : open);
-	const int rR = (int) (e & 0xffffu);
-	const unsigned long long key = ((unsigned long long) (glength - cR) << 32) | ((unsigned long long) rL << 16) | (unsigned long long) rR;
-	bool take;
-	if (!have) take = late ? (score >= bs) : (score > bs);
-	else if (score != bs) take = score > bs;
-	else take = late ? (key > bk) : (key < bk);
-	if (take) { bs = score; bk = key; bcL = cL; bcR = cR; brL = rL; brR = rR; have = true; }
+	CDNA_CAND(cR,(int) (e >> 16) - 32768,(int) (e & 0xffffu),open);
       }
     }
   }
+#undef CDNA_CAND
   /* lanes partition cL, which leads the scan order: late keeps the largest cL on ties, early the smallest */
   for (int off = 16; off > 0; off >>= 1) {
     const int os = __shfl_xor_sync(FULLMASK,bs,off), ocL = __shfl_xor_sync(FULLMASK,bcL,off), ocR = __shfl_xor_sync(FULLMASK,bcR,off);
@@ -521,7 +706,8 @@ struct KernelArgs {
   const GdpTables *tables;
 };
 
-__device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, short *Hrow, int *FF, const GdpTables *tb) {
+__device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *bnd, const GdpTables *tb) {
+
   const int lane = threadIdx.x & 31;
   const gmapdp_box b = ka.boxes[bi];
   const bool use8 = (b.flags & GMAPDP_F_USE8) != 0;
@@ -547,9 +733,10 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, short *
   const bool twosided = (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA);
 
   /* pre-pass: class codes in DP coordinates */
-  for (int c = lane; c <= b.glenL; c += 32) gcodeL[c] = (c == 0) ? 0x44 : (uint8_t) (nt_class(L.g(c)) | (nt_class(L.ga(c)) << 4));
-  if (b.mode != GMAPDP_SINGLE)
+  if (b.mode != GMAPDP_SINGLE) {
+    for (int c = lane; c <= b.glenL; c += 32) gcodeL[c] = (c == 0) ? 0x44 : (uint8_t) (nt_class(L.g(c)) | (nt_class(L.ga(c)) << 4));
     for (int r = lane; r <= b.rlenL; r += 32) { const int k = (r == 0) ? 4 : nt_class(L.q(r)); qcodeL[r] = (uint8_t) (k | (k << 4)); }
+  }
   if (twosided) {
     for (int c = lane; c <= b.glenR; c += 32) gcodeR[c] = (c == 0) ? 0x44 : (uint8_t) (nt_class(R.g(c)) | (nt_class(R.ga(c)) << 4));
     for (int r = lane; r <= b.rlenR; r += 32) { const int k = (r == 0) ? 4 : nt_class(R.q(r)); qcodeR[r] = (uint8_t) (k | (k << 4)); }
@@ -591,68 +778,84 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, short *
   if (b.mode == GMAPDP_SINGLE) {
     FGeom fg = fgeom(b.rlenL,b.glenL,b.lbandL,b.ubandL);
     uint32_t *dirs = wp;
-    int corner = NEG;
-    fill_full(L,gcodeL,b.lbandL,b.ubandL,mt,open,extend,lateL,NEG,POS,dirs,fg,Hrow,FF,&corner,tb);
-    /* the corner cell's owner broadcasts it */
-    {
-      const int owner = b.rlenL & 31;
-      res.finalscore = __shfl_sync(FULLMASK,corner,owner);
-    }
+    if (lateL) fill_full<true>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb);
+    else fill_full<false>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb);
     __syncwarp();
-    if (lane == 0) { tb_full(acc,L,dirs,fg,b.rlenL,b.glenL,tb); lenA = acc.nops; }
-
-  } else if (b.mode == GMAPDP_END5 || b.mode == GMAPDP_END3) {
-    TriPlanes U, Lo;
-    U.g = egeom(b.rlenL,b.glenL,b.ubandL); U.dirs = wp; U.sc = NULL; wp += (size_t) U.g.nstripes * U.g.dirW;
-    Lo.g = egeom(b.glenL,b.rlenL,b.lbandL); Lo.dirs = wp; Lo.sc = NULL; wp += (size_t) Lo.g.nstripes * Lo.g.dirW;
-    const bool lastrow = (b.flags & GMAPDP_F_LASTROW) != 0;
-    BestTrack bt;
-    if (lastrow) { bt.bs = NEG; bt.bk = (b.rlenL << 16); } else { bt.bs = 0; bt.bk = 0; }
-    fill_tri<false>(L,gcodeL,b.ubandL,mt,open,extend,lateL,NEG,POS,use8,U,&bt,lastrow,Hrow,tb);
-    fill_tri<true>(L,qcodeL,b.lbandL,mt,open,extend,lateL,NEG,POS,use8,Lo,&bt,lastrow,Hrow,tb);
-    for (int off = 16; off > 0; off >>= 1) {
-      const int os = __shfl_xor_sync(FULLMASK,bt.bs,off), ok = __shfl_xor_sync(FULLMASK,bt.bk,off);
-      if (os > bt.bs || (os == bt.bs && (lateL ? ok > bt.bk : ok < bt.bk))) { bt.bs = os; bt.bk = ok; }
-    }
-    res.finalscore = bt.bs; res.bestrL = bt.bk >> 16; res.bestcL = bt.bk & 0xffff;
-    __syncwarp();
-    if (lane == 0 && !(b.flags & GMAPDP_F_NOTRACE)) {
-      if (res.bestcL >= res.bestrL) tb_upper(acc,L,U,res.bestrL,res.bestcL,tb);
-      else tb_lower(acc,L,Lo,res.bestrL,res.bestcL,tb);
-      lenA = acc.nops;
-    }
+    tb_full(acc,L,dirs,fg,b.rlenL,b.glenL,tb); lenA = acc.nops;
 
   } else {
-    TriPlanes LU, LL, RU, RL;
-    LU.g = egeom(b.rlenL,b.glenL,b.ubandL); LU.dirs = wp; wp += (size_t) LU.g.nstripes * LU.g.dirW; LU.sc = wp; wp += (size_t) LU.g.nstripes * LU.g.scW;
-    LL.g = egeom(b.glenL,b.rlenL,b.lbandL); LL.dirs = wp; wp += (size_t) LL.g.nstripes * LL.g.dirW; LL.sc = wp; wp += (size_t) LL.g.nstripes * LL.g.scW;
-    RU.g = egeom(b.rlenR,b.glenR,b.ubandR); RU.dirs = wp; wp += (size_t) RU.g.nstripes * RU.g.dirW; RU.sc = wp; wp += (size_t) RU.g.nstripes * RU.g.scW;
-    RL.g = egeom(b.glenR,b.rlenR,b.lbandR); RL.dirs = wp; wp += (size_t) RL.g.nstripes * RL.g.dirW; RL.sc = wp; wp += (size_t) RL.g.nstripes * RL.g.scW;
-    fill_tri<false>(L,gcodeL,b.ubandL,mt,open,extend,lateL,NEG,POS,use8,LU,NULL,false,Hrow,tb);
-    fill_tri<true>(L,qcodeL,b.lbandL,mt,open,extend,lateL,NEG,POS,use8,LL,NULL,false,Hrow,tb);
-    fill_tri<false>(R,gcodeR,b.ubandR,mt,open,extend,lateR,NEG,POS,use8,RU,NULL,false,Hrow,tb);
-    fill_tri<true>(R,qcodeR,b.lbandR,mt,open,extend,lateR,NEG,POS,use8,RL,NULL,false,Hrow,tb);
-    __syncwarp();
-    int brL, brR, bcL, bcR, fs;
-    if (b.mode == GMAPDP_GENOME) {
-      const int di = b.cdna_direction > 0 ? 0 : (b.cdna_direction < 0 ? 1 : 2);
-      fs = bridge_genome(b,LU,LL,RU,RL,ldi,rdi,ka.probs + b.probL_off,ka.probs + b.probR_off,NEG,
-			 tb->isc[di][(b.flags & GMAPDP_F_FINALP) ? 1 : 0],&brL,&brR,&bcL,&bcR);
-      if (fs < 0) res.status = 1;
-    } else {
-      fs = bridge_cdna(b,LU,LL,RU,RL,NEG,wp,&bcL,&bcR,&brL,&brR);
+    /* E-only fills on the diagonal lane mapping: L lower, [R lower], L upper, [R upper] */
+    TriPacking tp;
+    tri_fills_of(b,tp);
+    TriFill F[GDP_MAXFILLS];
+    if ((reinterpret_cast<uintptr_t>(wp) & 7) != 0) wp++;
+    for (int f = 0; f < GDP_MAXFILLS; f++) {
+      if (f >= tp.nf) { F[f] = F[0]; continue; }
+      const bool lower = twosided ? (f < 2) : (f == 0);
+      const bool right = twosided && (f & 1);
+      F[f].nA = tp.nA[f]; F[f].nB = tp.nB[f]; F[f].band = tp.band[f];
+      F[f].lane0 = tp.lane0[f]; F[f].pass0 = tp.pass0[f]; F[f].npass = tp.npass[f];
+      F[f].lateadd = (right ? lateR : lateL) ? 1 : 0;
+      F[f].lower = lower;
+      F[f].code = lower ? (right ? qcodeR : qcodeL) : (right ? gcodeR : gcodeL);
+      F[f].prof = reinterpret_cast<const uint2 *>(wp);
+      F[f].dirPW = tp.dirPW; F[f].scPW = tp.scPW;
+      tri_profiles(F[f],right ? R : L,mt,use8,reinterpret_cast<uint2 *>(wp),tb);
+      wp += 2 * (size_t) (tp.nA[f] + 2);
     }
-    res.finalscore = fs; res.bestrL = brL; res.bestcL = bcL; res.bestrR = brR; res.bestcR = bcR;
-    if (lane == 0 && res.status == 0) {
-      if (bcR >= brR) tb_upper(acc,R,RU,brR,bcR,tb); else tb_lower(acc,R,RL,brR,bcR,tb);
-      lenA = acc.nops;
-      if (bcL >= brL) tb_upper(acc,L,LU,brL,bcL,tb); else tb_lower(acc,L,LL,brL,bcL,tb);
-      lenB = acc.nops - lenA;
+    uint32_t *dbase = wp; wp += (size_t) tp.npasses * tp.dirPW;
+    uint32_t *sbase = NULL;
+    if (twosided) { sbase = wp; wp += (size_t) tp.npasses * tp.scPW; }
+    uint32_t *edge = wp; wp += tp.maxA + 2;
+    for (int f = 0; f < tp.nf; f++) {
+      F[f].dirs = dbase + (size_t) tp.pass0[f] * tp.dirPW;
+      F[f].sc = sbase ? sbase + (size_t) tp.pass0[f] * tp.scPW : NULL;
+    }
+    __syncwarp();
+
+    if (!twosided) {
+      const TriFill &Lo = F[0], &U = F[1];
+      const bool lastrow = (b.flags & GMAPDP_F_LASTROW) != 0;
+      BestTrack bt;
+      if (lastrow) { bt.bs = NEG; bt.bk = (b.rlenL << 16); } else { bt.bs = 0; bt.bk = 0; }
+      tri_fill_all<false,true>(F,tp.nf,tp.npasses,open,extend,NEG,POS,&bt,b.rlenL,lastrow,edge);
+      for (int off = 16; off > 0; off >>= 1) {
+	const int os = __shfl_xor_sync(FULLMASK,bt.bs,off), ok = __shfl_xor_sync(FULLMASK,bt.bk,off);
+	if (os > bt.bs || (os == bt.bs && (lateL ? ok > bt.bk : ok < bt.bk))) { bt.bs = os; bt.bk = ok; }
+      }
+      res.finalscore = bt.bs; res.bestrL = bt.bk >> 16; res.bestcL = bt.bk & 0xffff;
+      __syncwarp();
+      if (!(b.flags & GMAPDP_F_NOTRACE)) {
+	if (res.bestcL >= res.bestrL) tb_upper(acc,L,U,res.bestrL,res.bestcL,tb);
+	else tb_lower(acc,L,Lo,res.bestrL,res.bestcL,tb);
+	lenA = acc.nops;
+      }
+    } else {
+      const TriFill &LL = F[0], &RL = F[1], &LU = F[2], &RU = F[3];
+      tri_fill_all<true,false>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge);
+      __syncwarp();
+      int brL, brR, bcL, bcR, fs;
+      if (b.mode == GMAPDP_GENOME) {
+	const int di = b.cdna_direction > 0 ? 0 : (b.cdna_direction < 0 ? 1 : 2);
+	fs = bridge_genome(b,LU,LL,RU,RL,ldi,rdi,ka.probs + b.probL_off,ka.probs + b.probR_off,NEG,
+			   tb->isc[di][(b.flags & GMAPDP_F_FINALP) ? 1 : 0],&brL,&brR,&bcL,&bcR);
+	if (fs < 0) res.status = 1;
+      } else {
+	fs = bridge_cdna(b,LU,LL,RU,RL,NEG,wp,reinterpret_cast<uint32_t *>(bnd),&bcL,&bcR,&brL,&brR);
+      }
+      res.finalscore = fs; res.bestrL = brL; res.bestcL = bcL; res.bestrR = brR; res.bestcR = bcR;
+      if (res.status == 0) {
+	if (bcR >= brR) tb_upper(acc,R,RU,brR,bcR,tb); else tb_lower(acc,R,RL,brR,bcR,tb);
+	lenA = acc.nops;
+	if (bcL >= brL) tb_upper(acc,L,LU,brL,bcL,tb); else tb_lower(acc,L,LL,brL,bcL,tb);
+	lenB = acc.nops - lenA;
+      }
     }
   }
 
   /* publish: allocate script space, copy, write the result */
-  const int ntot = __shfl_sync(FULLMASK,lenA + lenB,0);
+  __syncwarp();
+  const int ntot = lenA + lenB;
   unsigned long long off = 0;
   if (lane == 0) off = atomicAdd(ka.script_cursor,(unsigned long long) ntot);
   off = __shfl_sync(FULLMASK,off,0);
@@ -672,18 +875,10 @@ extern __shared__ __align__(16) unsigned char dyn_smem[];
 
 __global__ void __launch_bounds__(BLOCK_THREADS)
 gmapdp_dp_kernel (KernelArgs ka) {
-  /* shared: tables, then per-warp boundary rows */
-  GdpTables *tb = reinterpret_cast<GdpTables *>(dyn_smem);
-  {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(ka.tables);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(tb);
-    for (int k = threadIdx.x; k < (int) (sizeof(GdpTables) / 4); k += blockDim.x) dst[k] = src[k];
-  }
-  __syncthreads();
+  /* shared: one 8-byte boundary entry per column and warp */
+  const GdpTables *tb = ka.tables;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char *wbase = dyn_smem + ((sizeof(GdpTables) + 15) & ~15) + (size_t) warp * ((size_t) ka.smem_cols * 6);
-  int *FF = reinterpret_cast<int *>(wbase);
-  short *Hrow = reinterpret_cast<short *>(wbase + (size_t) ka.smem_cols * 4);
+  uint2 *bnd = reinterpret_cast<uint2 *>(dyn_smem) + (size_t) warp * ka.smem_cols;
   const int gwarp = blockIdx.x * WARPS_PER_BLOCK + warp;
   uint32_t *ws = ka.ws + (size_t) gwarp * ka.ws_words;
 
@@ -692,7 +887,7 @@ gmapdp_dp_kernel (KernelArgs ka) {
     if (lane == 0) idx = atomicAdd(ka.queue,1);
     idx = __shfl_sync(FULLMASK,idx,0);
     if (idx >= ka.nboxes) break;
-    process_box(ka,ka.order[idx],ws,Hrow,FF,tb);
+    process_box(ka,ka.order[idx],ws,bnd,tb);
   }
 }
 
@@ -830,7 +1025,7 @@ extern "C" int gmapdp_upload (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nbox
   ctx->script_need = script_need;
 
   /* persistent grid: as many blocks per SM as shared memory allows (<= 4), on every SM */
-  size_t smem = ((sizeof(GdpTables) + 15) & ~15) + (size_t) WARPS_PER_BLOCK * ctx->smem_cols * 6;
+  size_t smem = (size_t) WARPS_PER_BLOCK * ctx->smem_cols * 8;
   if ((int) smem > ctx->max_smem) { ctx->err = "box too long for the shared-memory boundary rows"; return GMAPDP_ERR_ARG; }
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel,BLOCK_THREADS,smem));
@@ -866,7 +1061,7 @@ extern "C" int gmapdp_run_resident (gmapdp_ctx *ctx, float *kernel_ms) {
   ka.boxes = ctx->d_boxes; ka.order = ctx->d_order; ka.nboxes = ctx->nboxes; ka.seq = ctx->d_seq; ka.probs = ctx->d_probs;
   ka.results = ctx->d_results; ka.script = ctx->d_script; ka.script_cap = ctx->cap_script; ka.script_cursor = ctx->d_cursor;
   ka.queue = ctx->d_queue; ka.ws = ctx->d_ws; ka.ws_words = ctx->ws_words; ka.smem_cols = ctx->smem_cols; ka.tables = ctx->d_tables;
-  size_t smem = ((sizeof(GdpTables) + 15) & ~15) + (size_t) WARPS_PER_BLOCK * ctx->smem_cols * 6;
+  size_t smem = (size_t) WARPS_PER_BLOCK * ctx->smem_cols * 8;
   CK(cudaMemsetAsync(ctx->d_cursor,0,sizeof(unsigned long long),ctx->stream));
   CK(cudaMemsetAsync(ctx->d_queue,0,sizeof(int),ctx->stream));
   CK(cudaEventRecord(ctx->ev0,ctx->stream));

@@ -4,11 +4,9 @@
  * bridged modes, score planes) are laid out STRIPE-MAJOR so that each wavefront step of a warp
  * is one coalesced store:
  *
- *   E-only fill (upper / lower triangle): lanes = 32 consecutive positions of the lane axis
- *     (rows for upper, columns for lower), step tt = j - 32*s.  Per stripe
- *        dirs  : ceil(T/16) x 32 words, 2 bits per cell  (bit0 directions_nogap != DIAG, bit1 directions_Egap != DIAG)
- *        scores: ceil(T/2)  x 32 words, int16 per cell
- *     with T = 32 + band.
+ *   E-only fills (upper / lower triangle): diagonal lane mapping, see TriPacking below.
+ *        dirs  : 2 bits per cell  (bit0 directions_nogap != DIAG, bit1 directions_Egap != DIAG)
+ *        scores: int16 per cell
  *   Full fill: lanes = 32 rows, skewed by one column per lane (systolic), step tt = (c - c0) + lane.
  *        dirs  : ceil(T/8) x 32 words, 4 bits per cell (bits0-1 nogap: 0 DIAG 1 HORIZ 2 VERT, bit2 Egap, bit3 Fgap)
  *     with T = min(glength+1, 32 + lband + uband) + 31.
@@ -24,19 +22,54 @@
 #define GDP_HD inline
 #endif
 
-struct EGeom {		/* one E-only fill */
-  int nA, nB, band;	/* lane-axis length, step-axis length, band width on the step axis */
-  int nstripes, T, dirW, scW;
+/* E-only fills (upper / lower triangle) run on a DIAGONAL lane mapping: lane = band diagonal
+ * d = j - i (i = lane-axis index: row for upper, column for lower; j = step-axis index), all lanes of a
+ * fill sit on the same step-axis index j = t at time t, lane d on lane-axis index i = t - d.
+ * H(i-1,j-1) is the lane's own previous value, (H,E)(i,j-1) arrives from lane d-1 by one shuffle.
+ * Several fills of one box share a pass when their widths (band+1) fit into 32 lanes; a fill wider
+ * than 32 diagonals takes ceil((band+1)/32) passes of its own, chained through an edge array.
+ * One pass owns one plane pair:  dirs [t>>4][32 lanes] (2 bits per cell), scores [t>>1][32 lanes] (int16). */
+#define GDP_MAXFILLS 4
+
+struct TriPacking {
+  int nf;
+  int band[GDP_MAXFILLS], nA[GDP_MAXFILLS], nB[GDP_MAXFILLS];
+  int pass0[GDP_MAXFILLS], npass[GDP_MAXFILLS], lane0[GDP_MAXFILLS];
+  int npasses, Tmax, maxA;
+  int dirPW, scPW;		/* words per pass plane */
 };
 
-GDP_HD EGeom egeom (int nA, int nB, int band) {
-  EGeom g;
-  g.nA = nA; g.nB = nB; g.band = band;
-  g.nstripes = (nA + 32) / 32;
-  g.T = 32 + band;
-  g.dirW = ((g.T + 15) / 16) * 32;
-  g.scW = ((g.T + 1) / 2) * 32;
-  return g;
+GDP_HD void tri_pack (TriPacking &tp) {
+  int used = 0, pass = -1;
+  tp.Tmax = 0; tp.maxA = 0;
+  for (int f = 0; f < tp.nf; f++) {
+    const int w = tp.band[f] + 1;
+    if (tp.nB[f] > tp.Tmax) tp.Tmax = tp.nB[f];
+    if (tp.nA[f] > tp.maxA) tp.maxA = tp.nA[f];
+    if (w > 32) {
+      tp.pass0[f] = pass + 1; tp.npass[f] = (w + 31) / 32; tp.lane0[f] = 0;
+      pass += tp.npass[f]; used = 32;
+    } else if (pass >= 0 && used + w <= 32) {
+      tp.pass0[f] = pass; tp.npass[f] = 1; tp.lane0[f] = used; used += w;
+    } else {
+      pass++; tp.pass0[f] = pass; tp.npass[f] = 1; tp.lane0[f] = 0; used = w;
+    }
+  }
+  tp.npasses = pass + 1;
+  tp.dirPW = ((tp.Tmax >> 4) + 1) * 32;
+  tp.scPW = ((tp.Tmax >> 1) + 1) * 32;
+}
+
+/* the fills of a box, in packing order: lower fills first (they are the narrow ones in production) */
+GDP_HD void tri_fills_of (const gmapdp_box &b, TriPacking &tp) {
+  const bool two = (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA);
+  int f = 0;
+  tp.band[f] = b.lbandL; tp.nA[f] = b.glenL; tp.nB[f] = b.rlenL; f++;		/* L lower */
+  if (two) { tp.band[f] = b.lbandR; tp.nA[f] = b.glenR; tp.nB[f] = b.rlenR; f++; }	/* R lower */
+  tp.band[f] = b.ubandL; tp.nA[f] = b.rlenL; tp.nB[f] = b.glenL; f++;		/* L upper */
+  if (two) { tp.band[f] = b.ubandR; tp.nA[f] = b.rlenR; tp.nB[f] = b.glenR; f++; }	/* R upper */
+  tp.nf = f;
+  tri_pack(tp);
 }
 
 struct FGeom {		/* one full fill */
@@ -69,16 +102,13 @@ GDP_HD size_t gdp_ws_words (const gmapdp_box &b) {
     FGeom f = fgeom(b.rlenL,b.glenL,b.lbandL,b.ubandL);
     w += (size_t) f.nstripes * f.dirW;
   } else {
-    bool scores = (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA);
-    EGeom lu = egeom(b.rlenL,b.glenL,b.ubandL), ll = egeom(b.glenL,b.rlenL,b.lbandL);
-    w += (size_t) lu.nstripes * (lu.dirW + (scores ? lu.scW : 0));
-    w += (size_t) ll.nstripes * (ll.dirW + (scores ? ll.scW : 0));
-    if (scores) {
-      EGeom ru = egeom(b.rlenR,b.glenR,b.ubandR), rl = egeom(b.glenR,b.rlenR,b.lbandR);
-      w += (size_t) ru.nstripes * (ru.dirW + ru.scW);
-      w += (size_t) rl.nstripes * (rl.dirW + rl.scW);
-      if (b.mode == GMAPDP_CDNA) w += (size_t) (b.glenL + 1) * (b.lbandR + b.ubandR + 1);	/* prefix-best table of the cDNA bridge */
-    }
+    const bool scores = (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA);
+    TriPacking tp;
+    tri_fills_of(b,tp);
+    for (int f = 0; f < tp.nf; f++) w += 2 * (size_t) (tp.nA[f] + 2);		/* profile tables */
+    w += (size_t) tp.npasses * (tp.dirPW + (scores ? tp.scPW : 0));
+    w += (size_t) tp.maxA + 2;							/* edge array of wide fills */
+    if (b.mode == GMAPDP_CDNA) w += (size_t) (b.glenL + 1) * (b.lbandR + b.ubandR + 1);	/* prefix-best table of the cDNA bridge */
   }
   return w + 64;
 }

@@ -44,8 +44,9 @@ def lib():
     return _lib
 
 
-def fill_batch(batch, seed, i0, n, stride=1, small=False):
-    return lib().benchgen_fill_batch(batch.h, C.c_uint64(seed), C.c_long(i0), C.c_long(n), C.c_long(stride), int(small))
+def fill_batch(batch, seed, i0, n, stride=1, small=False, modemask=31):
+    return lib().benchgen_fill_batch(batch.h, C.c_uint64(seed), C.c_long(i0), C.c_long(n), C.c_long(stride), int(small),
+                                     int(modemask))
 
 
 def make(seed, i, small=False, max_r=2000, max_g=2030):
