@@ -212,31 +212,42 @@ __device__ void tri_fill_all (const TriFill (&F)[GDP_MAXFILLS], int nf, int npas
  * Each stripe's steps are split into edge steps (some lane is outside the band, on its edge, on column 0
  * or past the last row: the literal restatement of :3257-3478) and interior steps (every lane strictly
  * inside the band), which need none of the edge logic. */
-struct FullLane { int E, Hl, diag, cg_out, pk_out, bprevH; };
+struct FullLane { int E, Hl, diag, cg_out; uint32_t pk_out; int bprevH; };
 
-template <bool LATE, bool FAST>
-__device__ __forceinline__ uint32_t full_step (FullLane &st, const int lane, const int c, const int r, const bool rowact,
+/* The 16-bit "field" that travels with H: without an alt genome it is the ready-made PRMT selector of
+   the column's class (k*0x1111+0x8880), with one it is the class pair k | kalt<<4. */
+template <bool ALT>
+__device__ __forceinline__ int field_score (uint32_t plo, uint32_t p4, uint32_t field) {
+  if (ALT) return max(prof_pick(plo,p4,(int) (field & 15u)),prof_pick(plo,p4,(int) ((field >> 4) & 15u)));
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(plo), "r"(p4), "r"(field));
+  return (int) d;
+}
+
+/* edge step: the literal restatement, any lane may be inactive / on a band edge / on column 0 */
+template <bool LATE, bool ALT>
+__device__ __forceinline__ uint32_t full_edge (FullLane &st, const int lane, const int c, const int r, const bool rowact,
 					       const int rlo, const int c0, const int chigh, const int lband, const int uband,
 					       const int open, const int extend, const int NEG, const int POS,
 					       const uint32_t plo, const uint32_t p4, uint2 *bnd) {
   int cg_in = __shfl_up_sync(FULLMASK,st.cg_out,1);
-  const int pk_in = __shfl_up_sync(FULLMASK,st.pk_out,1);
-  const bool act = FAST ? true : (rowact && c >= c0 && c <= chigh);
+  const uint32_t pk_in = __shfl_up_sync(FULLMASK,st.pk_out,1);
+  const bool act = rowact && c >= c0 && c <= chigh;
   uint32_t nib = 0;
   if (act) {
-    int last_in = (int) (short) (pk_in & 0xffff);	/* final H(r-1,c) = the F pass's last_nogap */
-    int code = (int) ((uint32_t) pk_in >> 16);
+    int last_in = (int) (short) (pk_in & 0xffffu);	/* final H(r-1,c) = the F pass's last_nogap */
+    uint32_t field = pk_in >> 16;
     int Hs = st.diag;
     if (lane == 0) {
       const uint2 e = bnd[c];
       const int bH = (int) (short) (e.x & 0xffffu);
-      code = (int) (e.x >> 16);
+      field = e.x >> 16;
       if (rlo == 0) {
-	Hs = (!FAST && c == 0) ? 0 : NEG;
+	Hs = (c == 0) ? 0 : NEG;
 	cg_in = NEG32; last_in = NEG32;
       } else {
-	Hs = (!FAST && c == 0) ? NEG : st.bprevH;
-	if (FAST || c < rlo + uband) { cg_in = (int) e.y; last_in = bH; }
+	Hs = (c == 0) ? NEG : st.bprevH;
+	if (c < rlo + uband) { cg_in = (int) e.y; last_in = bH; }
 	else { cg_in = NEG32; last_in = NEG32; }
       }
       st.bprevH = bH;
@@ -247,25 +258,17 @@ __device__ __forceinline__ uint32_t full_step (FullLane &st, const int lane, con
     st.E = max(max(st.E,T1) + extend,NEG);
     /* H, :3350-3389 */
     int sc;
-    if (!FAST && c == 0) sc = (r == 0) ? 0 : NEG;
-    else sc = max(prof_pick(plo,p4,code & 15),prof_pick(plo,p4,(code >> 4) & 15));
+    if (c == 0) sc = (r == 0) ? 0 : NEG;
+    else sc = field_score<ALT>(plo,p4,field);
     const int Hd = clampi(Hs + sc,NEG,POS);
     uint32_t dN = (LATE ? (st.E >= Hd) : (st.E > Hd)) ? 1u : 0u;
     int H = max(Hd,st.E);
     bool dF = false;
-    if (FAST) {
-      /* F (vertical gap), :3449-3469 */
-      const int score = last_in + open;
-      dF = LATE ? (cg_in >= score) : (cg_in > score);
-      const int cg = (dF ? cg_in : score) + extend;
-      const bool tV = LATE ? (cg >= H) : (cg > H);
-      H = tV ? cg : H; dN = tV ? 2u : dN;
-      st.cg_out = cg;
-    } else if (r >= c - uband && r <= c + lband) {
+    if (r >= c - uband && r <= c + lband) {
       if (r == c + lband && c > 0) { H = Hd; dE = false; dN = 0; }	/* bottom of band forced DIAG, :3395-3417 */
       if (r == c - uband) {						/* top of band, :3434-3446 */
 	st.cg_out = NEG32 + open + extend;
-      } else {
+      } else {							/* F (vertical gap), :3449-3469 */
 	const int score = last_in + open;
 	dF = LATE ? (cg_in >= score) : (cg_in > score);
 	const int cg = (dF ? cg_in : score) + extend;
@@ -276,22 +279,69 @@ __device__ __forceinline__ uint32_t full_step (FullLane &st, const int lane, con
     }
     st.diag = last_in;
     st.Hl = H;
-    st.pk_out = (H & 0xffff) | (code << 16);
-    if (lane == 31) bnd[c] = make_uint2((uint32_t) st.pk_out,(uint32_t) st.cg_out);
+    st.pk_out = ((uint32_t) H & 0xffffu) | (field << 16);
+    if (lane == 31) bnd[c] = make_uint2(st.pk_out,(uint32_t) st.cg_out);
     nib = dN | (dE ? 4u : 0u) | (dF ? 8u : 0u);
   }
   return nib;
 }
 
-template <bool LATE>
+/* interior step: every lane is active and strictly inside the band, c >= 1.  Branch-free: all lanes
+   read their column's boundary entry, lane 0 selects it; FIRST = the stripe starts at row 0. */
+template <bool LATE, bool ALT, bool FIRST>
+__device__ __forceinline__ uint32_t full_fast (FullLane &st, const bool isl0, const bool isl31, const int open, const int extend,
+					       const int NEG, const int POS, const uint32_t plo, const uint32_t p4, uint2 *bp) {
+  const int cg_sh = __shfl_up_sync(FULLMASK,st.cg_out,1);
+  const uint32_t pk_sh = __shfl_up_sync(FULLMASK,st.pk_out,1);
+  int cg_in, last_in, Hs;
+  uint32_t field;
+  if (FIRST) {
+    const uint32_t ex = bp->x;
+    field = isl0 ? (ex >> 16) : (pk_sh >> 16);
+    Hs = isl0 ? NEG : st.diag;
+    cg_in = isl0 ? NEG32 : cg_sh;
+    last_in = isl0 ? NEG32 : (int) (short) (pk_sh & 0xffffu);
+  } else {
+    const uint2 e = *bp;
+    const int bH = (int) (short) (e.x & 0xffffu);
+    field = isl0 ? (e.x >> 16) : (pk_sh >> 16);
+    Hs = isl0 ? st.bprevH : st.diag;
+    cg_in = isl0 ? (int) e.y : cg_sh;
+    last_in = isl0 ? bH : (int) (short) (pk_sh & 0xffffu);
+    st.bprevH = bH;
+  }
+  const int T1 = max(st.Hl + open,NEG);
+  const bool dE = LATE ? (st.E >= T1) : (st.E > T1);
+  st.E = max(max(st.E,T1) + extend,NEG);
+  const int Hd = clampi(Hs + field_score<ALT>(plo,p4,field),NEG,POS);
+  const bool dNh = LATE ? (st.E >= Hd) : (st.E > Hd);
+  int H = max(Hd,st.E);
+  const int score = last_in + open;
+  const bool dF = LATE ? (cg_in >= score) : (cg_in > score);
+  const int cg = (dF ? cg_in : score) + extend;
+  const bool tV = LATE ? (cg >= H) : (cg > H);
+  H = tV ? cg : H;
+  st.cg_out = cg;
+  st.diag = last_in;
+  st.Hl = H;
+  st.pk_out = ((uint32_t) H & 0xffffu) | (field << 16);
+  if (isl31) *bp = make_uint2(st.pk_out,(uint32_t) cg);
+  return (tV ? 2u : (dNh ? 1u : 0u)) | (dE ? 4u : 0u) | (dF ? 8u : 0u);
+}
+
+template <bool LATE, bool ALT>
 __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int open, int extend,
 			   int NEG, int POS, uint32_t *dirs, const FGeom &fg, uint2 *bnd, const GdpTables *tb) {
   const int lane = threadIdx.x & 31;
+  const bool isl0 = (lane == 0), isl31 = (lane == 31);
   const int rlen = sd.rlen, glen = sd.glen;
-  /* class codes of the genome columns into the boundary entries */
+  /* the columns' class fields into the boundary entries */
   for (int c = lane; c <= glen; c += 32) {
-    const uint32_t code = (c == 0) ? 0x44u : (uint32_t) (nt_class(sd.g(c)) | (nt_class(sd.ga(c)) << 4));
-    bnd[c] = make_uint2(code << 16,0u);
+    uint32_t field;
+    if (c == 0) field = ALT ? 0x44u : (4u * 0x1111u + 0x8880u);
+    else if (ALT) field = (uint32_t) (nt_class(sd.g(c)) | (nt_class(sd.ga(c)) << 4));
+    else field = (uint32_t) nt_class(sd.g(c)) * 0x1111u + 0x8880u;
+    bnd[c] = make_uint2(field << 16,0u);
   }
   __syncwarp();
   int s = 0;
@@ -325,15 +375,30 @@ __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int 
     uint32_t acc = 0;
     uint32_t *dst = dirs + (size_t) s * fg.dirW + lane;
     int tt = 0, c = c0 - lane;
-#define FULL_STEP(FASTFLAG) do { \
-      const uint32_t nib = full_step<LATE,FASTFLAG>(st,lane,c,r,rowact,rlo,c0,chigh,lband,uband,open,extend,NEG,POS,plo,p4,bnd); \
+#define EDGE_STEP() do { \
+      const uint32_t nib = full_edge<LATE,ALT>(st,lane,c,r,rowact,rlo,c0,chigh,lband,uband,open,extend,NEG,POS,plo,p4,bnd); \
       acc |= nib << (4 * (tt & 7)); \
-      if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; } } while (0)
+      if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; } tt++; c++; } while (0)
+#define FAST_STEP(FIRSTFLAG) do { \
+      const uint32_t nib = full_fast<LATE,ALT,FIRSTFLAG>(st,isl0,isl31,open,extend,NEG,POS,plo,p4,bnd + c); \
+      acc |= nib << (4 * (tt & 7)); \
+      if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; } tt++; c++; } while (0)
+#define FAST_CHUNKS(FIRSTFLAG) do { \
+      while (tt <= fe && (tt & 7)) FAST_STEP(FIRSTFLAG); \
+      uint2 *bp = bnd + c; uint32_t *dp = dst + (tt >> 3) * 32; \
+      while (tt + 7 <= fe) { \
+	uint32_t a8 = 0; \
+	_Pragma("unroll") for (int u = 0; u < 8; u++) a8 |= full_fast<LATE,ALT,FIRSTFLAG>(st,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + u) << (4 * u); \
+	*dp = a8; dp += 32; bp += 8; tt += 8; c += 8; \
+      } \
+      while (tt <= fe) FAST_STEP(FIRSTFLAG); } while (0)
     const int e1 = min(fs,nsteps);
-    for ( ; tt < e1; tt++, c++) FULL_STEP(false);
-    for ( ; tt <= fe; tt++, c++) FULL_STEP(true);
-    for ( ; tt < nsteps; tt++, c++) FULL_STEP(false);
-#undef FULL_STEP
+    while (tt < e1) EDGE_STEP();
+    if (rlo == 0) FAST_CHUNKS(true); else FAST_CHUNKS(false);
+    while (tt < nsteps) EDGE_STEP();
+#undef EDGE_STEP
+#undef FAST_STEP
+#undef FAST_CHUNKS
     if (nsteps & 7) dst[(nsteps >> 3) * 32] = acc;
     __syncwarp();
   }
@@ -778,8 +843,11 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
   if (b.mode == GMAPDP_SINGLE) {
     FGeom fg = fgeom(b.rlenL,b.glenL,b.lbandL,b.ubandL);
     uint32_t *dirs = wp;
-    if (lateL) fill_full<true>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb);
-    else fill_full<false>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb);
+    const bool alt = (b.gLalt_off != b.gL_off);
+    if (lateL) { if (alt) fill_full<true,true>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb);
+		 else fill_full<true,false>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb); }
+    else { if (alt) fill_full<false,true>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb);
+	   else fill_full<false,false>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb); }
     __syncwarp();
     tb_full(acc,L,dirs,fg,b.rlenL,b.glenL,tb); lenA = acc.nops;
 

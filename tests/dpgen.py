@@ -186,11 +186,32 @@ def synthetic_probs(rng, n, hot=()):
     return p
 
 
+def _alt_of(rng, seg):
+    """an alt-genome (SNP) twin of a segment: a few differing ACGT positions"""
+    a = bytearray(seg.encode("latin1"))
+    for _ in range(1 + len(a) // 80):
+        k = rng.randrange(len(a))
+        if a[k] in b"ACGT":
+            a[k] = rng.choice(b"ACGT")
+    return a.decode("latin1")
+
+
 def finalize_synthetic(rng, s, max_r=2000, max_g=2030):
     """Segments cut straight from the locus text (box orientation)."""
     q, qoff = _query(rng, s)
     b = _common(s, q, max_r, max_g)
     T, x, m = s["T"], s["x"], s["mode"]
+    b = _finalize_synthetic(rng, s, b, qoff, T, x, m, max_r, max_g)
+    if rng.random() < 0.15:        # exercise the max(std, alt) genome paths
+        for k in ("gseg", "gsegL", "gsegR", "rev_gseg"):
+            if k in b:
+                b[k + "_alt"] = _alt_of(rng, b[k])
+        if m == "cdna":
+            b["rev_gseg_alt"] = b["gseg_alt"]
+    return b
+
+
+def _finalize_synthetic(rng, s, b, qoff, T, x, m, max_r, max_g):
 
     def fwd(off, n):
         return T[off:off + n].decode("latin1")
