@@ -107,8 +107,10 @@ __device__ void tri_profiles (const TriFill &f, const SideSeq &sd, int mt, bool 
   }
 }
 
-/* One pass: every lane owns one band diagonal of one of the (up to GDP_MAXFILLS) fills packed into it. */
-template <bool SCORES, bool TRACK>
+/* One pass: every lane owns one band diagonal of one of the (up to GDP_MAXFILLS) fills packed into it.
+ * Profile / class-code loads run one step ahead of their use; the profile tables are padded by 32
+ * entries in front so that the look-ahead of a not-yet-active lane stays inside the allocation. */
+template <bool SCORES, bool TRACK, bool WIDE>
 __device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
 			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge) {
   const int lane = threadIdx.x & 31;
@@ -124,73 +126,71 @@ __device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, in
       const int dd = (lane - F[f].lane0) + 32 * p;
       thi = max(thi,F[f].nB);
       tlo = min(tlo,32 * p);
+      dplane = F[f].dirs + (size_t) p * F[f].dirPW;		/* the pass's planes are shared by its fills */
+      splane = SCORES ? F[f].sc + (size_t) p * F[f].scPW : NULL;
       if (lane >= F[f].lane0 && dd <= F[f].band && (F[f].npass > 1 || lane - F[f].lane0 <= F[f].band)) {
 	d = dd; nA = F[f].nA; nB = F[f].nB; lateadd = F[f].lateadd; lower = F[f].lower;
 	prof = F[f].prof; code = F[f].code;
-	dplane = F[f].dirs + (size_t) p * F[f].dirPW;
-	splane = SCORES ? F[f].sc + (size_t) p * F[f].scPW : NULL;
-	edge_in = (p > 0 && lane == 0);
-	edge_out = (p + 1 < F[f].npass && lane == 31);
+	edge_in = WIDE && (p > 0 && lane == 0);
+	edge_out = WIDE && (p + 1 < F[f].npass && lane == 31);
       }
     }
   }
   if (thi < 0) return;
-  /* planes are shared by the fills of the pass: all lanes store, inactive lanes store zeros */
-  if (dplane == NULL) {
-#pragma unroll
-    for (int f = 0; f < GDP_MAXFILLS; f++)
-      if (f < nf && pass >= F[f].pass0 && pass < F[f].pass0 + F[f].npass) {
-	dplane = F[f].dirs + (size_t) (pass - F[f].pass0) * F[f].dirPW;
-	splane = SCORES ? F[f].sc + (size_t) (pass - F[f].pass0) * F[f].scPW : NULL;
-      }
-  }
-  dplane += lane; if (SCORES) splane += lane;
+  dplane += lane + (size_t) (tlo >> 4) * 32;
+  if (SCORES) splane += lane + (size_t) (tlo >> 1) * 32;
+  const int tstart = (d >= 0) ? d : 0x7fffffff, tend = (d >= 0) ? min(nA + d,nB) : -1;
+  const bool isd0 = (d == 0);
+  const uint2 *pp = prof - d;				/* pp[t] = prof[t - d] */
+  const uint32_t negpair = ((uint32_t) NEG & 0xffffu) | ((uint32_t) NEG << 16);
 
-  int Hprev = NEG, E = NEG, H = NEG;
+  int Hprev = isd0 ? 0 : NEG, H = NEG;
   uint32_t pk_out = 0, dacc = 0, sacc = 0;
-  for (int t = tlo; t <= thi; t++) {
-    uint32_t pk_in = __shfl_up_sync(FULLMASK,pk_out,1);
-    const int i = t - d;
-    const bool act = (d >= 0) && i >= 0 && i <= nA && t <= nB;
-    uint32_t bits = 0;
-    if (act) {
-      if (edge_in) pk_in = edge[i];
-      const uint2 p = prof[i];
-      const int cd = code[t];
-      const int diag = (t == 0) ? 0 : (i == 0 ? NEG : Hprev);
-      const int sc = max(prof_pick(p.x,p.y,cd & 15),prof_pick(p.x,p.y,cd >> 4));
-      const int Hd = clampi(diag + sc,NEG,POS);
-      if (d == 0) {
-	E = NEG; H = Hd;
-      } else {
+  bool act_n = (tlo >= tstart && tlo <= tend);
+  uint2 p_n = make_uint2(0u,0u); int cd_n = 0;
+  if (act_n) { p_n = pp[tlo]; cd_n = code[tlo]; }
+
+  for (int t = tlo; t <= thi; t += 2) {
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int tc = t + u;
+      uint32_t pk_in = __shfl_up_sync(FULLMASK,pk_out,1);
+      const bool act = act_n;
+      const uint2 p = p_n; const int cd = cd_n;
+      act_n = (tc + 1 >= tstart) && (tc + 1 <= tend);
+      if (act_n) { p_n = pp[tc + 1]; cd_n = code[tc + 1]; }
+      uint32_t bits = 0;
+      if (act) {
+	if (WIDE && edge_in) pk_in = edge[tc - d];
+	if (isd0) pk_in = negpair;
+	const int sc = max(prof_pick(p.x,p.y,cd & 15),prof_pick(p.x,p.y,cd >> 4));
+	const int Hd = clampi(Hprev + sc,NEG,POS);
 	const int Hl = (int) (short) (pk_in & 0xffffu), El = ((int) pk_in) >> 16;
 	const int T1 = max(Hl + open,NEG);
 	const bool dE = (El + lateadd > T1);
-	E = max(max(El,T1) + extend,NEG);
+	const int E = max(max(El,T1) + extend,NEG);
 	const bool dN = (E + lateadd > Hd);
 	H = max(Hd,E);
-	bits = (dN ? 1u : 0u) | (dE ? 2u : 0u);
-      }
-      Hprev = H;
-      pk_out = ((uint32_t) H & 0xffffu) | ((uint32_t) E << 16);
-      if (edge_out) edge[i] = pk_out;
-      if (TRACK) {
-	const int r = lower ? t : i, c = lower ? i : t;
-	if (r >= 1 && c >= 1 && (!lower || d > 0) && (!lastrow || r == track_rlen)) {
-	  const int key = (r << 16) | c;
-	  if (H > bt->bs || (H == bt->bs && (lateadd ? key > bt->bk : key < bt->bk))) { bt->bs = H; bt->bk = key; }
+	bits = isd0 ? 0u : ((dN ? 1u : 0u) | (dE ? 2u : 0u));
+	Hprev = H;
+	pk_out = ((uint32_t) H & 0xffffu) | ((uint32_t) E << 16);
+	if (WIDE && edge_out) edge[tc - d] = pk_out;
+	if (TRACK) {
+	  const int i = tc - d;
+	  const int r = lower ? tc : i, c = lower ? i : tc;
+	  if (r >= 1 && c >= 1 && (!lower || d > 0) && (!lastrow || r == track_rlen)) {
+	    const int key = (r << 16) | c;
+	    if (H > bt->bs || (H == bt->bs && (lateadd ? key > bt->bk : key < bt->bk))) { bt->bs = H; bt->bk = key; }
+	  }
 	}
       }
+      dacc |= bits << (2 * (tc & 15));
+      if (SCORES) sacc |= ((uint32_t) H & 0xffffu) << (16 * u);
     }
-    dacc |= bits << (2 * (t & 15));
-    if ((t & 15) == 15) { dplane[(t >> 4) * 32] = dacc; dacc = 0; }
-    if (SCORES) {
-      sacc |= ((uint32_t) H & 0xffffu) << (16 * (t & 1));
-      if (t & 1) { splane[(t >> 1) * 32] = sacc; sacc = 0; }
-    }
+    if (SCORES) { *splane = sacc; splane += 32; sacc = 0; }
+    if ((t & 15) == 14) { *dplane = dacc; dplane += 32; dacc = 0; }
   }
-  if ((thi & 15) != 15) dplane[(thi >> 4) * 32] = dacc;
-  if (SCORES && !(thi & 1)) splane[(thi >> 1) * 32] = sacc;
+  if (((thi & ~1) & 15) != 14) *dplane = dacc;
   __syncwarp();
 }
 
@@ -198,7 +198,13 @@ __device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, in
 template <bool SCORES, bool TRACK>
 __device__ void tri_fill_all (const TriFill (&F)[GDP_MAXFILLS], int nf, int npasses, int open, int extend, int NEG, int POS,
 			      BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge) {
-  for (int pass = 0; pass < npasses; pass++) tri_pass<SCORES,TRACK>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge);
+  bool wide = false;
+#pragma unroll
+  for (int f = 0; f < GDP_MAXFILLS; f++) if (f < nf && F[f].npass > 1) wide = true;
+  for (int pass = 0; pass < npasses; pass++) {
+    if (wide) tri_pass<SCORES,TRACK,true>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge);
+    else tri_pass<SCORES,TRACK,false>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge);
+  }
 }
 
 /* Full fill: Dynprog_simd_8 / _16, stripe-faithful.
@@ -586,38 +592,41 @@ __device__ int bridge_genome (const gmapdp_box &b, const TriFill &LU, const TriF
     int cloR = max(rR - lbandR,1), chighR = min(rR + ubandR,glengthR - 1);
     int cL, cR, score, scoreL, scoreR, scoreI;
     double probL, probR;
-#define CONSIDER() do { score = scoreL + scoreI + scoreR; ord++; \
-      if (score > best.s || (score == best.s && probL + probR > best.p)) { \
-	best.s = score; best.p = probL + probR; best.ord = ord; best.rL = rL; best.rR = rR; best.cL = cL; best.cR = cR; } } while (0)
+/* a candidate matters only if its score reaches the running best: the probabilities (double loads and
+   an add) are fetched only then */
+#define CONSIDER(PL,PR) do { score = scoreL + scoreI + scoreR; ord++; \
+      if (score >= best.s) { \
+	const double ps_ = (PL) + (PR); \
+	if (score > best.s || ps_ > best.p) { \
+	  best.s = score; best.p = ps_; best.ord = ord; best.rL = rL; best.rR = rR; best.cL = cL; best.cR = cR; } } } while (0)
 
     cL = rL; probL = lp[cL]; scoreL = tri_score(LU,rL,cL);
     cR = rR; probR = rp[cR]; scoreR = tri_score(RU,rR,cR);
     scoreI = intron_points(isc,ldi[cL],rdi[cR]);
-    CONSIDER();
+    CONSIDER(probL,probR);
     if (scoreI > 0 && probL + probR > dn.p) {
       dn.s = scoreL + scoreI + scoreR; dn.p = probL + probR; dn.ord = ord; dn.rL = rL; dn.rR = rR; dn.cL = cL; dn.cR = cR;
     }
     const int ldiL = ldi[cL];
-    const int scoreLdiag = scoreL, scoreRdiag = scoreR;
+    const int scoreRdiag = scoreR;
     const double probLdiag = probL, probRdiag = probR;
 
     /* indel on right */
     for (cR = cloR; cR < rR && cR < lim - cL; cR++) {
-      probR = rp[cR]; scoreR = tri_score(RL,cR,rR); scoreI = intron_points(isc,ldiL,rdi[cR]); CONSIDER();
+      scoreR = tri_score(RL,cR,rR); scoreI = intron_points(isc,ldiL,rdi[cR]); CONSIDER(probLdiag,rp[cR]);
     }
     for (cR++; cR < chighR && cR < lim - cL; cR++) {
-      probR = rp[cR]; scoreR = tri_score(RU,rR,cR); scoreI = intron_points(isc,ldiL,rdi[cR]); CONSIDER();
+      scoreR = tri_score(RU,rR,cR); scoreI = intron_points(isc,ldiL,rdi[cR]); CONSIDER(probLdiag,rp[cR]);
     }
     /* indel on left */
-    cR = rR; probR = probRdiag; scoreR = scoreRdiag;
+    cR = rR; scoreR = scoreRdiag;
     const int rdiR = rdi[cR];
     for (cL = cloL; cL < rL && cL < lim - cR; cL++) {
-      probL = lp[cL]; scoreL = tri_score(LL,cL,rL); scoreI = intron_points(isc,ldi[cL],rdiR); CONSIDER();
+      scoreL = tri_score(LL,cL,rL); scoreI = intron_points(isc,ldi[cL],rdiR); CONSIDER(lp[cL],probRdiag);
     }
     for (cL++; cL < chighL && cL < lim - cR; cL++) {
-      probL = lp[cL]; scoreL = tri_score(LU,rL,cL); scoreI = intron_points(isc,ldi[cL],rdiR); CONSIDER();
+      scoreL = tri_score(LU,rL,cL); scoreI = intron_points(isc,ldi[cL],rdiR); CONSIDER(lp[cL],probRdiag);
     }
-    (void) scoreLdiag; (void) probLdiag;
 #undef CONSIDER
   }
 
@@ -866,10 +875,10 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
       F[f].lateadd = (right ? lateR : lateL) ? 1 : 0;
       F[f].lower = lower;
       F[f].code = lower ? (right ? qcodeR : qcodeL) : (right ? gcodeR : gcodeL);
-      F[f].prof = reinterpret_cast<const uint2 *>(wp);
+      F[f].prof = reinterpret_cast<const uint2 *>(wp) + 32;	/* 32 entries of look-ahead padding in front */
       F[f].dirPW = tp.dirPW; F[f].scPW = tp.scPW;
-      tri_profiles(F[f],right ? R : L,mt,use8,reinterpret_cast<uint2 *>(wp),tb);
-      wp += 2 * (size_t) (tp.nA[f] + 2);
+      tri_profiles(F[f],right ? R : L,mt,use8,reinterpret_cast<uint2 *>(wp) + 32,tb);
+      wp += 2 * (size_t) (tp.nA[f] + 2 + 32);
     }
     uint32_t *dbase = wp; wp += (size_t) tp.npasses * tp.dirPW;
     uint32_t *sbase = NULL;

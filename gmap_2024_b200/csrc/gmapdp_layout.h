@@ -105,7 +105,7 @@ GDP_HD size_t gdp_ws_words (const gmapdp_box &b) {
     const bool scores = (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA);
     TriPacking tp;
     tri_fills_of(b,tp);
-    for (int f = 0; f < tp.nf; f++) w += 2 * (size_t) (tp.nA[f] + 2);		/* profile tables */
+    for (int f = 0; f < tp.nf; f++) w += 2 * (size_t) (tp.nA[f] + 2 + 32);	/* profile tables (+ look-ahead padding) */
     w += (size_t) tp.npasses * (tp.dirPW + (scores ? tp.scPW : 0));
     w += (size_t) tp.maxA + 2;							/* edge array of wide fills */
     if (b.mode == GMAPDP_CDNA) w += (size_t) (b.glenL + 1) * (b.lbandR + b.ubandR + 1);	/* prefix-best table of the cDNA bridge */
