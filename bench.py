@@ -202,7 +202,9 @@ def run_ours(args):
     eng = Engine(local)
     batch = eng.batch(2000, 2030)
     t0 = time.time()
-    benchgen.fill_batch(batch, args.seed, rank * args.boxes, args.boxes, 1, args.small, args.modemask)    # untimed: synthetic input
+    from gmap_2024_b200.sharding import shard_range
+    i0, i1 = shard_range(rank, world, args.boxes)
+    benchgen.fill_batch(batch, args.seed, i0, i1 - i0, 1, args.small, args.modemask)    # untimed: synthetic input
     gen_s = time.time() - t0
     cells, cells8 = batch.cells(), batch.cells8()
     batch.upload()                                      # inputs resident in HBM from here on
