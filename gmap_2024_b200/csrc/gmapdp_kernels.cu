@@ -780,6 +780,7 @@ struct KernelArgs {
   const GdpTables *tables;
 };
 
+template <bool FULLK>
 __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *bnd, const GdpTables *tb) {
 
   const int lane = threadIdx.x & 31;
@@ -807,15 +808,15 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
   const bool twosided = (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA);
 
   /* pre-pass: class codes in DP coordinates */
-  if (b.mode != GMAPDP_SINGLE) {
+  if (!FULLK) {
     for (int c = lane; c <= b.glenL; c += 32) gcodeL[c] = (c == 0) ? 0x44 : (uint8_t) (nt_class(L.g(c)) | (nt_class(L.ga(c)) << 4));
     for (int r = lane; r <= b.rlenL; r += 32) { const int k = (r == 0) ? 4 : nt_class(L.q(r)); qcodeL[r] = (uint8_t) (k | (k << 4)); }
   }
-  if (twosided) {
+  if (!FULLK && twosided) {
     for (int c = lane; c <= b.glenR; c += 32) gcodeR[c] = (c == 0) ? 0x44 : (uint8_t) (nt_class(R.g(c)) | (nt_class(R.ga(c)) << 4));
     for (int r = lane; r <= b.rlenR; r += 32) { const int k = (r == 0) ? 4 : nt_class(R.q(r)); qcodeR[r] = (uint8_t) (k | (k << 4)); }
   }
-  if (b.mode == GMAPDP_GENOME) {
+  if (!FULLK && b.mode == GMAPDP_GENOME) {
     /* dinucleotide classes, dynprog_genome.c:919-967 (forward arrays: rev_gsequenceR[-cR] = GR[glenR-1-cR]) */
     for (int cL = lane; cL <= b.glenL; cL += 32) {
       int v = 0;
@@ -849,7 +850,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
   acc.ops = stage; acc.nops = 0; acc.pend = 0;
   int lenA = 0, lenB = 0;
 
-  if (b.mode == GMAPDP_SINGLE) {
+  if (FULLK) {
     FGeom fg = fgeom(b.rlenL,b.glenL,b.lbandL,b.ubandL);
     uint32_t *dirs = wp;
     const bool alt = (b.gLalt_off != b.gL_off);
@@ -950,7 +951,17 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 
 extern __shared__ __align__(16) unsigned char dyn_smem[];
 
-__global__ void __launch_bounds__(BLOCK_THREADS)
+/* Two specialisations of one persistent kernel: FULLK = single-gap boxes (full fill: needs the big
+   shared-memory boundary rows, 3 blocks/SM), !FULLK = every other mode (E-only fills, bridges: almost no
+   shared memory, 5 blocks/SM).  They are launched on two streams and share the SMs. */
+#ifndef GMAPDP_FULL_MINB
+#define GMAPDP_FULL_MINB 3
+#endif
+#ifndef GMAPDP_TRI_MINB
+#define GMAPDP_TRI_MINB 5
+#endif
+template <bool FULLK>
+__global__ void __launch_bounds__(BLOCK_THREADS,FULLK ? GMAPDP_FULL_MINB : GMAPDP_TRI_MINB)
 gmapdp_dp_kernel (KernelArgs ka) {
   /* shared: one 8-byte boundary entry per column and warp */
   const GdpTables *tb = ka.tables;
@@ -964,7 +975,7 @@ gmapdp_dp_kernel (KernelArgs ka) {
     if (lane == 0) idx = atomicAdd(ka.queue,1);
     idx = __shfl_sync(FULLMASK,idx,0);
     if (idx >= ka.nboxes) break;
-    process_box(ka,ka.order[idx],ws,bnd,tb);
+    process_box<FULLK>(ka,ka.order[idx],ws,bnd,tb);
   }
 }
 
@@ -973,7 +984,12 @@ gmapdp_dp_kernel (KernelArgs ka) {
  * ---------------------------------------------------------------------------------------------- */
 struct gmapdp_ctx {
   int device, sm_count, grid, max_smem;
-  cudaStream_t stream;
+  int kgrid[2], ksmem_cols[2]; size_t kws_words[2];	/* per kernel kind: 0 = full, 1 = tri */
+  uint32_t *d_kws[2]; size_t cap_kws[2];
+  cudaStream_t stream2; cudaEvent_t evj, evk[2][2]; float last_ms[2];
+  std::vector<int> chunk_nfull;
+  cudaStream_t stream, copy_stream;
+  std::vector<cudaEvent_t> chunk_events;
   cudaEvent_t ev0, ev1;
   std::string err;
   GdpTables *d_tables;
@@ -1015,7 +1031,8 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   ctx->d_tables = NULL; ctx->d_boxes = NULL; ctx->cap_boxes = 0; ctx->d_order = NULL; ctx->cap_order = 0; ctx->cap_results = 0; ctx->d_seq = NULL; ctx->cap_seq = 0;
   ctx->d_probs = NULL; ctx->cap_probs = 0; ctx->d_results = NULL; ctx->d_script = NULL; ctx->cap_script = 0;
   ctx->d_cursor = NULL; ctx->d_queue = NULL; ctx->d_ws = NULL; ctx->cap_ws = 0; ctx->h_pin = NULL; ctx->cap_pin = 0;
-  ctx->stream = 0; ctx->ev0 = ctx->ev1 = 0;
+  ctx->stream = 0; ctx->copy_stream = 0; ctx->stream2 = 0; ctx->evj = 0; ctx->ev0 = ctx->ev1 = 0;
+  ctx->d_kws[0] = ctx->d_kws[1] = NULL; ctx->cap_kws[0] = ctx->cap_kws[1] = 0;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     ctx->err = "no CUDA device: the gmapdp engine has no CPU fallback";
@@ -1027,19 +1044,24 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->max_smem = (int) prop.sharedMemPerBlockOptin;
   cudaFuncAttributes fa;
-  cudaError_t fe = cudaFuncGetAttributes(&fa,gmapdp_dp_kernel);
+  cudaError_t fe = cudaFuncGetAttributes(&fa,gmapdp_dp_kernel<true>);
   if (fe != cudaSuccess) {
     ctx->err = std::string("no sm_100a kernel image for this device (") + prop.name + "): " + cudaGetErrorString(fe);
     return GMAPDP_ERR_CUDA;
   }
   CK(cudaStreamCreateWithFlags(&ctx->stream,cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->stream2,cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->evj,cudaEventDisableTiming));
+  for (int a = 0; a < 2; a++) for (int b2 = 0; b2 < 2; b2++) CK(cudaEventCreate(&ctx->evk[a][b2]));
+  ctx->last_ms[0] = ctx->last_ms[1] = 0.f;
   CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
   GdpHostTables ht; GdpTables t; ht.device_tables(&t);
   CK(cudaMalloc((void **) &ctx->d_tables,sizeof(GdpTables)));
   CK(cudaMemcpy(ctx->d_tables,&t,sizeof(GdpTables),cudaMemcpyHostToDevice));
   CK(cudaMalloc((void **) &ctx->d_cursor,sizeof(unsigned long long)));
-  CK(cudaMalloc((void **) &ctx->d_queue,sizeof(int)));
-  CK(cudaFuncSetAttribute(gmapdp_dp_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
+  CK(cudaMalloc((void **) &ctx->d_queue,2 * sizeof(int)));
+  CK(cudaFuncSetAttribute(gmapdp_dp_kernel<true>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
+  CK(cudaFuncSetAttribute(gmapdp_dp_kernel<false>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
   ctx->grid = 0;
   return GMAPDP_OK;
 }
@@ -1048,10 +1070,14 @@ extern "C" void gmapdp_destroy (gmapdp_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaFree(ctx->d_tables); cudaFree(ctx->d_boxes); cudaFree(ctx->d_order); cudaFree(ctx->d_seq); cudaFree(ctx->d_probs);
-  cudaFree(ctx->d_results); cudaFree(ctx->d_script); cudaFree(ctx->d_cursor); cudaFree(ctx->d_queue); cudaFree(ctx->d_ws);
+  cudaFree(ctx->d_results); cudaFree(ctx->d_script); cudaFree(ctx->d_cursor); cudaFree(ctx->d_queue); cudaFree(ctx->d_ws); cudaFree(ctx->d_kws[0]); cudaFree(ctx->d_kws[1]);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->evj) { cudaEventDestroy(ctx->evj); for (int a = 0; a < 2; a++) for (int b2 = 0; b2 < 2; b2++) cudaEventDestroy(ctx->evk[a][b2]); }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1074,44 +1100,66 @@ static double box_work (const gmapdp_box &b) {
   return w;
 }
 
-extern "C" int gmapdp_upload (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes,
-			      const uint8_t *seqpool, size_t seqbytes, const double *probpool, size_t nprobs) {
-  if (!ctx || nboxes < 0 || (nboxes > 0 && (!boxes || !seqpool))) { if (ctx) ctx->err = "bad argument"; return GMAPDP_ERR_ARG; }
-  CK(cudaSetDevice(ctx->device));
-  ctx->nboxes = nboxes;
-  if (nboxes == 0) return GMAPDP_OK;
+/* geometry, sorting and device allocations of a batch (no copies).  `order' receives the box ids of
+   every chunk [chunk_begin[k], chunk_begin[k+1]) sorted by decreasing work. */
+/* Sort key: kind (full boxes first, then the E-only modes), then decreasing work (LPT). */
+static inline void sort_chunk (std::vector<std::pair<double,int> > &work, int b0, int b1) {
+  std::sort(work.begin() + b0,work.begin() + b1);
+}
 
-  /* geometry of the batch */
-  size_t ws_words = 0, script_need = 0; int maxcols = 0;
-  std::vector<std::pair<double,int> > work(nboxes);
-  for (int i = 0; i < nboxes; i++) {
-    const gmapdp_box &b = boxes[i];
-    if (b.rlenL < 0 || b.glenL < 0 || b.rlenR < 0 || b.glenR < 0 || b.open >= 0 || b.extend >= 0 || b.mode < 0 || b.mode > 4 ||
-	(unsigned) b.mismatchtype > 3u) { ctx->err = "bad box"; return GMAPDP_ERR_ARG; }
-    ws_words = std::max(ws_words,gdp_ws_words(b));
-    script_need += (size_t) b.rlenL + b.glenL + 4;
-    if (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA) script_need += (size_t) b.rlenR + b.glenR + 4;
-    maxcols = std::max(maxcols,std::max(std::max((int) b.glenL,(int) b.glenR),std::max((int) b.rlenL,(int) b.rlenR)) + 2);
-    work[i] = std::make_pair(-box_work(b),i);
+/* geometry and device allocations of a batch (no copies).  work[i] = (key, box id); within a chunk
+   the sorted order lists the single-gap boxes first (key offset by -1e12) and chunk_nfull[k] counts them. */
+static int plan_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, size_t seqbytes, size_t nprobs,
+		       const std::vector<int> &chunk_begin, std::vector<int> &order, std::vector<std::pair<double,int> > &work,
+		       bool sort_now) {
+  size_t ws_words[2] = {0,0}, script_need = 0; int maxcols[2] = {8,8};
+  work.resize(nboxes);
+  const int nchunks = (int) chunk_begin.size() - 1;
+  ctx->chunk_nfull.assign(nchunks,0);
+  int largest[2] = {0,0};
+  for (int k = 0; k < nchunks; k++) {
+    int nfull = 0;
+    for (int i = chunk_begin[k]; i < chunk_begin[k+1]; i++) {
+      const gmapdp_box &b = boxes[i];
+      if (b.rlenL < 0 || b.glenL < 0 || b.rlenR < 0 || b.glenR < 0 || b.open >= 0 || b.extend >= 0 || b.mode < 0 || b.mode > 4 ||
+	  (unsigned) b.mismatchtype > 3u) { ctx->err = "bad box"; return GMAPDP_ERR_ARG; }
+      const int kind = (b.mode == GMAPDP_SINGLE) ? 0 : 1;
+      ws_words[kind] = std::max(ws_words[kind],gdp_ws_words(b));
+      script_need += (size_t) b.rlenL + b.glenL + 4;
+      if (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA) script_need += (size_t) b.rlenR + b.glenR + 4;
+      if (b.mode == GMAPDP_SINGLE) maxcols[0] = std::max(maxcols[0],(int) b.glenL + 2);
+      else if (b.mode == GMAPDP_CDNA) maxcols[1] = std::max(maxcols[1],(int) b.glenL + 2);	/* M and Q tables: 2 words per column */
+      work[i] = std::make_pair(-box_work(b) - (kind == 0 ? 1e12 : 0.0),i);	/* box_work < 1e10: the offset keeps full precision */
+      nfull += (kind == 0);
+    }
+    ctx->chunk_nfull[k] = nfull;
+    largest[0] = std::max(largest[0],nfull);
+    largest[1] = std::max(largest[1],chunk_begin[k+1] - chunk_begin[k] - nfull);
   }
-  std::sort(work.begin(),work.end());
-  std::vector<int> order(nboxes);
-  for (int i = 0; i < nboxes; i++) order[i] = work[i].second;
-  ctx->ws_words = (ws_words + 31) & ~(size_t) 31;
-  ctx->smem_cols = (maxcols + 7) & ~7;
+  order.resize(nboxes);
+  if (sort_now) {
+    for (int k = 0; k < nchunks; k++) sort_chunk(work,chunk_begin[k],chunk_begin[k+1]);
+    for (int i = 0; i < nboxes; i++) order[i] = work[i].second;
+  }
   ctx->script_need = script_need;
 
-  /* persistent grid: as many blocks per SM as shared memory allows (<= 4), on every SM */
-  size_t smem = (size_t) WARPS_PER_BLOCK * ctx->smem_cols * 8;
-  if ((int) smem > ctx->max_smem) { ctx->err = "box too long for the shared-memory boundary rows"; return GMAPDP_ERR_ARG; }
-  int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel,BLOCK_THREADS,smem));
-  if (occ < 1) occ = 1;
-  if (occ > 6) occ = 6;
-  int grid = ctx->sm_count * occ;
-  int needed_blocks = (nboxes + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-  if (grid > needed_blocks) grid = needed_blocks;
-  ctx->grid = grid;
+  /* persistent grids: as many blocks per SM as shared memory and registers allow, on every SM */
+  for (int kind = 0; kind < 2; kind++) {
+    ctx->kws_words[kind] = (ws_words[kind] + 31) & ~(size_t) 31;
+    ctx->ksmem_cols[kind] = (maxcols[kind] + 7) & ~7;
+    size_t smem = (size_t) WARPS_PER_BLOCK * ctx->ksmem_cols[kind] * 8;
+    if ((int) smem > ctx->max_smem) { ctx->err = "box too long for the shared-memory boundary rows"; return GMAPDP_ERR_ARG; }
+    int occ = 0;
+    if (kind == 0) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<true>,BLOCK_THREADS,smem));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<false>,BLOCK_THREADS,smem));
+    occ = std::min(std::max(occ,1),8);
+    int grid = ctx->sm_count * occ;
+    int needed_blocks = (largest[kind] + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    ctx->kgrid[kind] = std::max(std::min(grid,needed_blocks),1);
+    if (largest[kind] > 0 &&
+	grow(ctx,&ctx->d_kws[kind],&ctx->cap_kws[kind],(size_t) ctx->kgrid[kind] * WARPS_PER_BLOCK * ctx->kws_words[kind])) return GMAPDP_ERR_CUDA;
+  }
+  ctx->grid = ctx->kgrid[0] + ctx->kgrid[1];
 
   if (grow(ctx,&ctx->d_boxes,&ctx->cap_boxes,(size_t) nboxes)) return GMAPDP_ERR_CUDA;
   if (grow(ctx,&ctx->d_order,&ctx->cap_order,(size_t) nboxes)) return GMAPDP_ERR_CUDA;
@@ -1119,8 +1167,45 @@ extern "C" int gmapdp_upload (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nbox
   if (grow(ctx,&ctx->d_seq,&ctx->cap_seq,seqbytes + 16)) return GMAPDP_ERR_CUDA;
   if (grow(ctx,&ctx->d_probs,&ctx->cap_probs,nprobs + 2)) return GMAPDP_ERR_CUDA;
   if (grow(ctx,&ctx->d_script,&ctx->cap_script,script_need + 64)) return GMAPDP_ERR_CUDA;
-  if (grow(ctx,&ctx->d_ws,&ctx->cap_ws,(size_t) grid * WARPS_PER_BLOCK * ctx->ws_words)) return GMAPDP_ERR_CUDA;
+  return GMAPDP_OK;
+}
 
+/* launches the (up to) two kernels of one chunk: the full-fill kernel on `stream', the E-only kernel on
+   `stream2'; both must already be ordered after the chunk's uploads */
+static int launch_chunk (gmapdp_ctx *ctx, int first, int nfull, int ntri, bool timed = false) {
+  for (int kind = 0; kind < 2; kind++) {
+    const int count = kind == 0 ? nfull : ntri;
+    if (timed) ctx->last_ms[kind] = 0.f;
+    if (count == 0) continue;
+    cudaStream_t st = kind == 0 ? ctx->stream : ctx->stream2;
+    KernelArgs ka;
+    ka.boxes = ctx->d_boxes; ka.order = ctx->d_order + first + (kind == 0 ? 0 : nfull); ka.nboxes = count;
+    ka.seq = ctx->d_seq; ka.probs = ctx->d_probs; ka.results = ctx->d_results;
+    ka.script = ctx->d_script; ka.script_cap = ctx->cap_script; ka.script_cursor = ctx->d_cursor;
+    ka.queue = ctx->d_queue + kind; ka.ws = ctx->d_kws[kind]; ka.ws_words = ctx->kws_words[kind];
+    ka.smem_cols = ctx->ksmem_cols[kind]; ka.tables = ctx->d_tables;
+    const size_t smem = (size_t) WARPS_PER_BLOCK * ctx->ksmem_cols[kind] * 8;
+    CK(cudaMemsetAsync(ctx->d_queue + kind,0,sizeof(int),st));
+    if (timed) CK(cudaEventRecord(ctx->evk[kind][0],st));
+    if (kind == 0) gmapdp_dp_kernel<true><<<ctx->kgrid[0],BLOCK_THREADS,smem,st>>>(ka);
+    else gmapdp_dp_kernel<false><<<ctx->kgrid[1],BLOCK_THREADS,smem,st>>>(ka);
+    CK(cudaGetLastError());
+    if (timed) CK(cudaEventRecord(ctx->evk[kind][1],st));
+    ctx->launches++;
+  }
+  return GMAPDP_OK;
+}
+
+extern "C" int gmapdp_upload (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes,
+			      const uint8_t *seqpool, size_t seqbytes, const double *probpool, size_t nprobs) {
+  if (!ctx || nboxes < 0 || (nboxes > 0 && (!boxes || !seqpool))) { if (ctx) ctx->err = "bad argument"; return GMAPDP_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  ctx->nboxes = nboxes;
+  if (nboxes == 0) return GMAPDP_OK;
+  std::vector<int> chunk_begin = {0, nboxes}, order;
+  std::vector<std::pair<double,int> > work;
+  int rc = plan_batch(ctx,boxes,nboxes,seqbytes,nprobs,chunk_begin,order,work,true);
+  if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->d_boxes,boxes,(size_t) nboxes * sizeof(gmapdp_box),cudaMemcpyHostToDevice,ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_order,order.data(),(size_t) nboxes * sizeof(int),cudaMemcpyHostToDevice,ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_seq,seqpool,seqbytes,cudaMemcpyHostToDevice,ctx->stream));
@@ -1134,20 +1219,27 @@ extern "C" int gmapdp_run_resident (gmapdp_ctx *ctx, float *kernel_ms) {
   CK(cudaSetDevice(ctx->device));
   if (kernel_ms) *kernel_ms = 0.f;
   if (ctx->nboxes == 0) return GMAPDP_OK;
-  KernelArgs ka;
-  ka.boxes = ctx->d_boxes; ka.order = ctx->d_order; ka.nboxes = ctx->nboxes; ka.seq = ctx->d_seq; ka.probs = ctx->d_probs;
-  ka.results = ctx->d_results; ka.script = ctx->d_script; ka.script_cap = ctx->cap_script; ka.script_cursor = ctx->d_cursor;
-  ka.queue = ctx->d_queue; ka.ws = ctx->d_ws; ka.ws_words = ctx->ws_words; ka.smem_cols = ctx->smem_cols; ka.tables = ctx->d_tables;
-  size_t smem = (size_t) WARPS_PER_BLOCK * ctx->smem_cols * 8;
+  const int nfull = ctx->chunk_nfull.empty() ? 0 : ctx->chunk_nfull[0];
   CK(cudaMemsetAsync(ctx->d_cursor,0,sizeof(unsigned long long),ctx->stream));
-  CK(cudaMemsetAsync(ctx->d_queue,0,sizeof(int),ctx->stream));
+  /* fork: stream2 starts after ev0; join: ev1 is recorded on `stream' after stream2's kernel has finished */
   CK(cudaEventRecord(ctx->ev0,ctx->stream));
-  gmapdp_dp_kernel<<<ctx->grid,BLOCK_THREADS,smem,ctx->stream>>>(ka);
-  CK(cudaGetLastError());
+  CK(cudaStreamWaitEvent(ctx->stream2,ctx->ev0,0));
+  int rc = launch_chunk(ctx,0,nfull,ctx->nboxes - nfull,true);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->evj,ctx->stream2));
+  CK(cudaStreamWaitEvent(ctx->stream,ctx->evj,0));
   CK(cudaEventRecord(ctx->ev1,ctx->stream));
-  ctx->launches++;
   CK(cudaStreamSynchronize(ctx->stream));
   if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms,ctx->ev0,ctx->ev1));
+  if (nfull > 0) CK(cudaEventElapsedTime(&ctx->last_ms[0],ctx->evk[0][0],ctx->evk[0][1]));
+  if (ctx->nboxes - nfull > 0) CK(cudaEventElapsedTime(&ctx->last_ms[1],ctx->evk[1][0],ctx->evk[1][1]));
+  return GMAPDP_OK;
+}
+
+/* CUDA-event durations of the two kernels of the last gmapdp_run_resident (they overlap in time) */
+extern "C" int gmapdp_last_kernel_ms (const gmapdp_ctx *ctx, float *full_ms, float *tri_ms) {
+  if (full_ms) *full_ms = ctx->last_ms[0];
+  if (tri_ms) *tri_ms = ctx->last_ms[1];
   return GMAPDP_OK;
 }
 
@@ -1168,13 +1260,72 @@ extern "C" int gmapdp_download (gmapdp_ctx *ctx, gmapdp_result *results, uint32_
   return GMAPDP_OK;
 }
 
+/* Host-buffer path.  Large batches are cut into chunks of consecutive boxes: the H2D copy of chunk
+   k+1 (copy stream) overlaps the kernels of chunk k (compute streams); each chunk uploads only the span
+   of the pools its boxes reference.  Small batches are one chunk. */
 extern "C" int gmapdp_run_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes,
 				 const uint8_t *seqpool, size_t seqbytes, const double *probpool, size_t nprobs,
 				 gmapdp_result *results, uint32_t *script, size_t script_cap, size_t *script_used) {
-  int rc = gmapdp_upload(ctx,boxes,nboxes,seqpool,seqbytes,probpool,nprobs);
+  if (!ctx || nboxes < 0 || (nboxes > 0 && (!boxes || !seqpool))) { if (ctx) ctx->err = "bad argument"; return GMAPDP_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  ctx->nboxes = nboxes;
+  if (script_used) *script_used = 0;
+  if (nboxes == 0) return GMAPDP_OK;
+
+  /* chunk boundaries by referenced bytes */
+  const size_t CHUNK_BYTES = (size_t) 192 << 20;
+  std::vector<int> chunk_begin(1,0);
+  std::vector<size_t> slo, shi, plo, phi;
+  {
+    size_t acc = 0, a = (size_t) -1, bnd = 0, pa = (size_t) -1, pb = 0;
+    for (int i = 0; i < nboxes; i++) {
+      const gmapdp_box &x = boxes[i];
+      const size_t offs[6] = {x.qL_off, x.qR_off, x.gL_off, x.gLalt_off, x.gR_off, x.gRalt_off};
+      const size_t lens[6] = {(size_t) x.rlenL, (size_t) x.rlenR, (size_t) x.glenL, (size_t) x.glenL, (size_t) x.glenR, (size_t) x.glenR};
+      for (int k = 0; k < 6; k++) { a = std::min(a,offs[k]); bnd = std::max(bnd,offs[k] + lens[k]); acc += (k == 3 || k == 5) ? 0 : lens[k]; }
+      if (x.mode == GMAPDP_GENOME) {
+	pa = std::min(pa,std::min((size_t) x.probL_off,(size_t) x.probR_off));
+	pb = std::max(pb,std::max((size_t) x.probL_off + x.glenL,(size_t) x.probR_off + x.glenR));
+	acc += 8 * ((size_t) x.glenL + x.glenR);
+      }
+      if (acc >= CHUNK_BYTES || i == nboxes - 1) {
+	chunk_begin.push_back(i + 1);
+	slo.push_back(a); shi.push_back(std::min(bnd,seqbytes)); plo.push_back(pa); phi.push_back(std::min(pb,nprobs));
+	acc = 0; a = (size_t) -1; bnd = 0; pa = (size_t) -1; pb = 0;
+      }
+    }
+  }
+  const int nchunks = (int) chunk_begin.size() - 1;
+  std::vector<int> order;
+  std::vector<std::pair<double,int> > work;
+  int rc = plan_batch(ctx,boxes,nboxes,seqbytes,nprobs,chunk_begin,order,work,false);	/* chunks are sorted just in time, below */
   if (rc) return rc;
-  rc = gmapdp_run_resident(ctx,NULL);
-  if (rc) return rc;
+  if (ctx->copy_stream == 0) CK(cudaStreamCreateWithFlags(&ctx->copy_stream,cudaStreamNonBlocking));
+  while ((int) ctx->chunk_events.size() < nchunks) {
+    cudaEvent_t e; CK(cudaEventCreateWithFlags(&e,cudaEventDisableTiming)); ctx->chunk_events.push_back(e);
+  }
+  CK(cudaMemsetAsync(ctx->d_cursor,0,sizeof(unsigned long long),ctx->stream));
+  CK(cudaEventRecord(ctx->evj,ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->stream2,ctx->evj,0));
+  for (int k = 0; k < nchunks; k++) {
+    const int b0 = chunk_begin[k], n = chunk_begin[k+1] - b0;
+    cudaStream_t cs = ctx->copy_stream;
+    sort_chunk(work,b0,b0 + n);				/* overlaps the previous chunk's kernels */
+    for (int i = b0; i < b0 + n; i++) order[i] = work[i].second;
+    CK(cudaMemcpyAsync(ctx->d_boxes + b0,boxes + b0,(size_t) n * sizeof(gmapdp_box),cudaMemcpyHostToDevice,cs));
+    CK(cudaMemcpyAsync(ctx->d_order + b0,order.data() + b0,(size_t) n * sizeof(int),cudaMemcpyHostToDevice,cs));
+    if (shi[k] > slo[k]) CK(cudaMemcpyAsync(ctx->d_seq + slo[k],seqpool + slo[k],shi[k] - slo[k],cudaMemcpyHostToDevice,cs));
+    if (phi[k] > plo[k] && plo[k] != (size_t) -1)
+      CK(cudaMemcpyAsync(ctx->d_probs + plo[k],probpool + plo[k],(phi[k] - plo[k]) * sizeof(double),cudaMemcpyHostToDevice,cs));
+    CK(cudaEventRecord(ctx->chunk_events[k],cs));
+    CK(cudaStreamWaitEvent(ctx->stream,ctx->chunk_events[k],0));
+    CK(cudaStreamWaitEvent(ctx->stream2,ctx->chunk_events[k],0));
+    rc = launch_chunk(ctx,b0,ctx->chunk_nfull[k],n - ctx->chunk_nfull[k]);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream2));
+  CK(cudaStreamSynchronize(ctx->copy_stream));
   return gmapdp_download(ctx,results,script,script_cap,script_used);
 }
 

@@ -189,8 +189,8 @@ struct gmapdp_batch {
   gmapdp_result *results = NULL; size_t nresults = 0;	/* pinned */
   uint32_t *script = NULL; size_t script_cap = 0;	/* pinned */
   size_t script_used = 0;
-  long cells = 0, cells8 = 0;
-  bool pinned = false;
+  long cells = 0, cells8 = 0, cells_full = 0, cells8_full = 0;	/* _full: the single-gap (full fill) share */
+  bool pinned = false, bufs_pinned = false;
   int count_mismatch = 0;
   std::string err;
   bool uploaded = false, overflow = false;
@@ -215,21 +215,24 @@ extern "C" gmapdp_batch *GmapDP_batch_new (gmapdp_ctx *ctx, int max_rlength, int
   b->ctx = ctx; b->max_rlength = max_rlength; b->max_glength = max_glength;
   return b;
 }
-static void unpin (gmapdp_batch *b) {
+static void host_free (gmapdp_batch *b, void *p) { if (b->bufs_pinned) gmapdp_host_free(p); else free(p); }
+static void unpin (gmapdp_batch *b, bool release_buffers) {
   if (b->pinned) {
     gmapdp_host_unregister(b->boxes.data()); gmapdp_host_unregister(b->seqpool.data());
     if (!b->probpool.empty()) gmapdp_host_unregister(b->probpool.data());
     b->pinned = false;
   }
-  gmapdp_host_free(b->results); b->results = NULL; b->nresults = 0;
-  gmapdp_host_free(b->script); b->script = NULL; b->script_cap = 0;
+  if (release_buffers) {
+    host_free(b,b->results); b->results = NULL; b->nresults = 0;
+    host_free(b,b->script); b->script = NULL; b->script_cap = 0;
+  }
 }
 extern "C" void GmapDP_batch_clear (gmapdp_batch *b) {
-  unpin(b);
+  unpin(b,/*release_buffers*/false);		/* result / script buffers are reused by the next batch */
   b->calls.clear(); b->boxes.clear(); b->box_call.clear(); b->seqpool.clear(); b->probpool.clear();
-  b->script_used = 0; b->cells = 0; b->cells8 = 0; b->uploaded = false; b->overflow = false; b->err.clear();
+  b->script_used = 0; b->cells = 0; b->cells8 = 0; b->cells_full = 0; b->cells8_full = 0; b->uploaded = false; b->overflow = false; b->err.clear();
 }
-extern "C" void GmapDP_batch_free (gmapdp_batch *b) { if (b) { unpin(b); delete b; } }
+extern "C" void GmapDP_batch_free (gmapdp_batch *b) { if (b) { unpin(b,true); delete b; } }
 extern "C" long GmapDP_batch_cells8 (const gmapdp_batch *b) { return b->cells8; }
 extern "C" int GmapDP_batch_ncalls (const gmapdp_batch *b) { return (int) b->calls.size(); }
 extern "C" int GmapDP_batch_nboxes (const gmapdp_batch *b) { return (int) b->boxes.size(); }
@@ -241,7 +244,12 @@ extern "C" size_t GmapDP_batch_h2d_bytes (const gmapdp_batch *b) {
 extern "C" size_t GmapDP_batch_d2h_bytes (const gmapdp_batch *b) {
   return b->boxes.size() * sizeof(gmapdp_result) + b->script_used * sizeof(uint32_t) + sizeof(unsigned long long);
 }
-static void add_cells (gmapdp_batch *b, long n, bool use8) { b->cells += n; if (use8) b->cells8 += n; }
+static void add_cells (gmapdp_batch *b, long n, bool use8, bool full = false) {
+  b->cells += n; if (use8) b->cells8 += n;
+  if (full) { b->cells_full += n; if (use8) b->cells8_full += n; }
+}
+extern "C" long GmapDP_batch_cells_full (const gmapdp_batch *b) { return b->cells_full; }
+extern "C" long GmapDP_batch_cells8_full (const gmapdp_batch *b) { return b->cells8_full; }
 
 static gmapdp_box blank_box () { gmapdp_box x; memset(&x,0,sizeof(x)); return x; }
 
@@ -291,7 +299,7 @@ extern "C" int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char 
   x.qL_off = x.qR_off = b->add_bytes(c.quc.data(),rlength);
   x.gL_off = x.gR_off = b->add_bytes(c.gL.data(),glength);
   x.gLalt_off = x.gRalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
-  add_cells(b,gdp_cells_full(rlength,glength,lband,uband),use8);
+  add_cells(b,gdp_cells_full(rlength,glength,lband,uband),use8,true);
   c.box = (int) b->boxes.size();
   b->boxes.push_back(x); b->box_call.push_back(id);
   return id;
@@ -654,27 +662,36 @@ static int finish_all (gmapdp_batch *b) {
 
 static int ensure_host_buffers (gmapdp_batch *b) {
   if (b->overflow) { b->err = "sequence pool exceeds 4 GiB: split the batch"; return GMAPDP_ERR_CAPACITY; }
-  if (!b->pinned) {
+  size_t need = 64;
+  for (const gmapdp_box &x : b->boxes) {
+    need += (size_t) x.rlenL + x.glenL + 4;
+    if (x.mode == GMAPDP_GENOME || x.mode == GMAPDP_CDNA) need += (size_t) x.rlenR + x.glenR + 4;
+  }
+  /* pinning pays off only for large batches: page-locking costs far more than a small staged copy */
+  const bool big = (b->seqpool.size() + need * sizeof(uint32_t) > ((size_t) 8 << 20));
+  if (big && !b->pinned) {
     /* the pools are complete: pin them in place so every H2D is a straight DMA */
     gmapdp_host_register(b->boxes.data(),b->boxes.size() * sizeof(gmapdp_box));
     gmapdp_host_register(b->seqpool.data(),b->seqpool.size());
     if (!b->probpool.empty()) gmapdp_host_register(b->probpool.data(),b->probpool.size() * sizeof(double));
     b->pinned = true;
   }
-  if (b->nresults < b->boxes.size()) {
-    gmapdp_host_free(b->results);
-    b->results = (gmapdp_result *) gmapdp_host_alloc(b->boxes.size() * sizeof(gmapdp_result));
-    b->nresults = b->results ? b->boxes.size() : 0;
+  if (big != b->bufs_pinned && (b->results || b->script)) {
+    host_free(b,b->results); b->results = NULL; b->nresults = 0;
+    host_free(b,b->script); b->script = NULL; b->script_cap = 0;
   }
-  size_t need = 64;
-  for (const gmapdp_box &x : b->boxes) {
-    need += (size_t) x.rlenL + x.glenL + 4;
-    if (x.mode == GMAPDP_GENOME || x.mode == GMAPDP_CDNA) need += (size_t) x.rlenR + x.glenR + 4;
+  b->bufs_pinned = big;
+  if (b->nresults < b->boxes.size()) {
+    host_free(b,b->results);
+    const size_t n = b->boxes.size() + b->boxes.size() / 2 + 16;
+    b->results = (gmapdp_result *) (big ? gmapdp_host_alloc(n * sizeof(gmapdp_result)) : malloc(n * sizeof(gmapdp_result)));
+    b->nresults = b->results ? n : 0;
   }
   if (b->script_cap < need) {
-    gmapdp_host_free(b->script);
-    b->script = (uint32_t *) gmapdp_host_alloc(need * sizeof(uint32_t));
-    b->script_cap = b->script ? need : 0;
+    host_free(b,b->script);
+    const size_t n = need + need / 2;
+    b->script = (uint32_t *) (big ? gmapdp_host_alloc(n * sizeof(uint32_t)) : malloc(n * sizeof(uint32_t)));
+    b->script_cap = b->script ? n : 0;
   }
   if (!b->results || !b->script) { b->err = "pinned host allocation failed"; return GMAPDP_ERR_CUDA; }
   return GMAPDP_OK;

@@ -41,6 +41,8 @@ def load_library():
         lib.GmapDP_batch_error.restype = C.c_char_p
         lib.GmapDP_batch_cells.restype = C.c_long
         lib.GmapDP_batch_cells8.restype = C.c_long
+        lib.GmapDP_batch_cells_full.restype = C.c_long
+        lib.GmapDP_batch_cells8_full.restype = C.c_long
         lib.GmapDP_batch_digest.restype = C.c_ulonglong
         lib.GmapDP_batch_h2d_bytes.restype = C.c_size_t
         lib.GmapDP_batch_d2h_bytes.restype = C.c_size_t
@@ -72,6 +74,12 @@ class Engine:
 
     def launch_count(self):
         return self.lib.gmapdp_launch_count(self.ctx)
+
+    def last_kernel_ms(self):
+        """(full-fill kernel ms, E-only kernel ms) of the last resident run"""
+        a, b = C.c_float(), C.c_float()
+        self.lib.gmapdp_last_kernel_ms(self.ctx, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def device_info(self):
         sm, grid, bt = C.c_int(), C.c_int(), C.c_int()
@@ -169,6 +177,10 @@ class Batch:
 
     def cells8(self):
         return self.lib.GmapDP_batch_cells8(self.h)
+
+    def cells_full(self):
+        """(cells, 8-bit cells) of the single-gap boxes, i.e. of the full-fill kernel"""
+        return self.lib.GmapDP_batch_cells_full(self.h), self.lib.GmapDP_batch_cells8_full(self.h)
 
     def ncalls(self):
         return self.lib.GmapDP_batch_ncalls(self.h)

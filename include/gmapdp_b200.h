@@ -109,6 +109,10 @@ int gmapdp_upload (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes,
 		   const uint8_t *seqpool, size_t seqbytes, const double *probpool, size_t nprobs);
 int gmapdp_run_resident (gmapdp_ctx *ctx, float *kernel_ms);
 int gmapdp_download (gmapdp_ctx *ctx, gmapdp_result *results, uint32_t *script, size_t script_cap, size_t *script_used);
+/* A batch is served by two specialisations of the DP kernel running side by side: one for the single-gap
+ * boxes (full fills) and one for every other mode (E-only fills + bridges).  Their own CUDA-event
+ * durations for the last gmapdp_run_resident (they overlap in time): */
+int gmapdp_last_kernel_ms (const gmapdp_ctx *ctx, float *full_ms, float *tri_ms);
 /* number of kernel launches issued by this context so far */
 long gmapdp_launch_count (const gmapdp_ctx *ctx);
 

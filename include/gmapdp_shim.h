@@ -102,6 +102,8 @@ int GmapDP_batch_finish (gmapdp_batch *b);	/* download + replay after run_reside
 int GmapDP_batch_run_device (gmapdp_batch *b);	/* gmapdp_run_batch only: H2D + kernel + D2H, no pair replay */
 int GmapDP_batch_download (gmapdp_batch *b);	/* D2H of results + scripts after run_resident */
 unsigned long long GmapDP_batch_digest (const gmapdp_batch *b);	/* checksum of all device results + scripts */
+long GmapDP_batch_cells_full (const gmapdp_batch *b);	/* cells of the single-gap boxes (full fills) ... */
+long GmapDP_batch_cells8_full (const gmapdp_batch *b);	/* ... and their 8-bit share */
 long GmapDP_batch_cells8 (const gmapdp_batch *b);	/* the share of GmapDP_batch_cells filled in 8-bit mode */
 
 int GmapDP_batch_ncalls (const gmapdp_batch *b);
