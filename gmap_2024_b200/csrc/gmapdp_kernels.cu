@@ -611,21 +611,51 @@ __device__ int bridge_genome (const gmapdp_box &b, const TriFill &LU, const TriF
     const int scoreRdiag = scoreR;
     const double probLdiag = probL, probRdiag = probR;
 
-    /* indel on right */
-    for (cR = cloR; cR < rR && cR < lim - cL; cR++) {
-      scoreR = tri_score(RL,cR,rR); scoreI = intron_points(isc,ldiL,rdi[cR]); CONSIDER(probLdiag,rp[cR]);
+    /* The four scans below visit their candidates in the reference's order; the score and dinucleotide
+       loads of four consecutive candidates are issued together so that their latencies overlap. */
+
+    /* indel on right: cL = rL fixed */
+    {
+      const int ldiX_ = ldiL;
+      const int endlo = min(rR,lim - cL), endhi = min(chighR,lim - cL);
+      for (int base_ = cloR; base_ < endlo; base_ += 4) {
+	int s4_[4], d4_[4];
+#pragma unroll
+	for (int u_ = 0; u_ < 4; u_++) { const int cc = min(base_ + u_,endlo - 1); s4_[u_] = tri_score(RL,cc,rR); d4_[u_] = rdi[cc]; }
+#pragma unroll
+	for (int u_ = 0; u_ < 4; u_++) if (base_ + u_ < endlo) {
+	  cR = base_ + u_; scoreR = s4_[u_]; scoreI = intron_points(isc,ldiX_,d4_[u_]); CONSIDER(probLdiag,rp[cR]); }
+      }
+      for (int base_ = rR + 1; base_ < endhi; base_ += 4) {
+	int s4_[4], d4_[4];
+#pragma unroll
+	for (int u_ = 0; u_ < 4; u_++) { const int cc = min(base_ + u_,endhi - 1); s4_[u_] = tri_score(RU,rR,cc); d4_[u_] = rdi[cc]; }
+#pragma unroll
+	for (int u_ = 0; u_ < 4; u_++) if (base_ + u_ < endhi) {
+	  cR = base_ + u_; scoreR = s4_[u_]; scoreI = intron_points(isc,ldiX_,d4_[u_]); CONSIDER(probLdiag,rp[cR]); }
+      }
     }
-    for (cR++; cR < chighR && cR < lim - cL; cR++) {
-      scoreR = tri_score(RU,rR,cR); scoreI = intron_points(isc,ldiL,rdi[cR]); CONSIDER(probLdiag,rp[cR]);
-    }
-    /* indel on left */
+    /* indel on left: cR = rR fixed */
     cR = rR; scoreR = scoreRdiag;
-    const int rdiR = rdi[cR];
-    for (cL = cloL; cL < rL && cL < lim - cR; cL++) {
-      scoreL = tri_score(LL,cL,rL); scoreI = intron_points(isc,ldi[cL],rdiR); CONSIDER(lp[cL],probRdiag);
-    }
-    for (cL++; cL < chighL && cL < lim - cR; cL++) {
-      scoreL = tri_score(LU,rL,cL); scoreI = intron_points(isc,ldi[cL],rdiR); CONSIDER(lp[cL],probRdiag);
+    {
+      const int rdiR = rdi[cR];
+      const int endlo = min(rL,lim - cR), endhi = min(chighL,lim - cR);
+      for (int base_ = cloL; base_ < endlo; base_ += 4) {
+	int s4_[4], d4_[4];
+#pragma unroll
+	for (int u_ = 0; u_ < 4; u_++) { const int cc = min(base_ + u_,endlo - 1); s4_[u_] = tri_score(LL,cc,rL); d4_[u_] = ldi[cc]; }
+#pragma unroll
+	for (int u_ = 0; u_ < 4; u_++) if (base_ + u_ < endlo) {
+	  cL = base_ + u_; scoreL = s4_[u_]; scoreI = intron_points(isc,d4_[u_],rdiR); CONSIDER(lp[cL],probRdiag); }
+      }
+      for (int base_ = rL + 1; base_ < endhi; base_ += 4) {
+	int s4_[4], d4_[4];
+#pragma unroll
+	for (int u_ = 0; u_ < 4; u_++) { const int cc = min(base_ + u_,endhi - 1); s4_[u_] = tri_score(LU,rL,cc); d4_[u_] = ldi[cc]; }
+#pragma unroll
+	for (int u_ = 0; u_ < 4; u_++) if (base_ + u_ < endhi) {
+	  cL = base_ + u_; scoreL = s4_[u_]; scoreI = intron_points(isc,d4_[u_],rdiR); CONSIDER(lp[cL],probRdiag); }
+      }
     }
 #undef CONSIDER
   }
