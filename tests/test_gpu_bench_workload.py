@@ -1,0 +1,63 @@
+"""Parity ON THE BENCHMARK WORKLOAD ITSELF (BASELINE.json config 2, full sizes up to 2000 bp per side):
+boxes of tests/benchgen (the generator bench.py uses) through the CUDA path vs the CPU oracle, and
+size-independent properties of a larger slice: repeatability (checksum of all device results and
+scripts), independence of batch composition / chunking, traceback consistency with the fill."""
+import pytest
+
+import benchgen
+from harness import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from gmap_2024_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def test_benchmark_boxes_bit_exact_vs_oracle(engine):
+    o = Oracle()
+    boxes = [benchgen.make(20241018, i, small=False) for i in range(300)]
+    batch = engine.batch()
+    ids = [batch.add(b) for b in boxes]
+    batch.run()
+    big = 0
+    for b, cid in zip(boxes, ids):
+        assert batch.result(cid, b["mode"]) == o.run(b), (b["mode"], b.get("rlength"), b.get("glength"))
+        big += b.get("rlength", 0) > 1000
+    assert big > 50
+    batch.free()
+
+
+def test_checksum_repeatable_and_chunking_independent(engine):
+    seed, n = 7, 6000
+    def digest_of(lo, hi):
+        b = engine.batch()
+        benchgen.fill_batch(b, seed, lo, hi - lo, 1, False)
+        b.run_device()                      # host-buffer path (chunked for large batches)
+        d1 = b.digest()
+        b.upload()
+        b.run_resident()                    # resident path (single launch pair)
+        b.download()
+        d2 = b.digest()
+        cells = b.cells()
+        b.free()
+        return d1, d2, cells
+    d1, d2, cells = digest_of(0, n)
+    assert d1 == d2                          # chunked == unchunked
+    e1, e2, _ = digest_of(0, n)
+    assert (e1, e2) == (d1, d2)              # repeatable
+    assert cells > 10 ** 8
+
+
+def test_device_counts_match_host_replay(engine):
+    """the device tracebacks' score / match / mismatch / open / indel counts are recomputed by the host
+    replay of the edit script for every call; GmapDP_batch_finish fails if any differs"""
+    b = engine.batch()
+    benchgen.fill_batch(b, 11, 0, 3000, 1, False)
+    b.run()                                  # raises EngineError on a count mismatch
+    assert b.nboxes() > 2000
+    b.free()
