@@ -1017,6 +1017,7 @@ struct gmapdp_ctx {
   int kgrid[2], ksmem_cols[2]; size_t kws_words[2];	/* per kernel kind: 0 = full, 1 = tri */
   uint32_t *d_kws[2]; size_t cap_kws[2];
   cudaStream_t stream2; cudaEvent_t evj, evk[2][2]; float last_ms[2];
+  size_t chunk_bytes;			/* pipelining granularity of gmapdp_run_batch (GMAPDP_CHUNK_MB, default 192) */
   std::vector<int> chunk_nfull;
   cudaStream_t stream, copy_stream;
   std::vector<cudaEvent_t> chunk_events;
@@ -1084,6 +1085,11 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   CK(cudaEventCreateWithFlags(&ctx->evj,cudaEventDisableTiming));
   for (int a = 0; a < 2; a++) for (int b2 = 0; b2 < 2; b2++) CK(cudaEventCreate(&ctx->evk[a][b2]));
   ctx->last_ms[0] = ctx->last_ms[1] = 0.f;
+  {
+    const char *cm = getenv("GMAPDP_CHUNK_MB");
+    long mb = cm ? atol(cm) : 192;
+    ctx->chunk_bytes = (size_t) (mb > 0 ? mb : 192) << 20;
+  }
   CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
   GdpHostTables ht; GdpTables t; ht.device_tables(&t);
   CK(cudaMalloc((void **) &ctx->d_tables,sizeof(GdpTables)));
@@ -1303,7 +1309,7 @@ extern "C" int gmapdp_run_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int n
   if (nboxes == 0) return GMAPDP_OK;
 
   /* chunk boundaries by referenced bytes */
-  const size_t CHUNK_BYTES = (size_t) 192 << 20;
+  const size_t CHUNK_BYTES = ctx->chunk_bytes;
   std::vector<int> chunk_begin(1,0);
   std::vector<size_t> slo, shi, plo, phi;
   {

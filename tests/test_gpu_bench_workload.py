@@ -33,9 +33,15 @@ def test_benchmark_boxes_bit_exact_vs_oracle(engine):
 
 
 def test_checksum_repeatable_and_chunking_independent(engine):
+    import os
+    from gmap_2024_b200 import Engine
     seed, n = 7, 6000
-    def digest_of(lo, hi):
-        b = engine.batch()
+    os.environ["GMAPDP_CHUNK_MB"] = "2"     # ~24 MB of inputs -> a dozen pipelined chunks
+    chunky = Engine(0)
+    del os.environ["GMAPDP_CHUNK_MB"]
+
+    def digest_of(lo, hi, eng=None):
+        b = (eng or engine).batch()
         benchgen.fill_batch(b, seed, lo, hi - lo, 1, False)
         b.run_device()                      # host-buffer path (chunked for large batches)
         d1 = b.digest()
@@ -47,9 +53,14 @@ def test_checksum_repeatable_and_chunking_independent(engine):
         b.free()
         return d1, d2, cells
     d1, d2, cells = digest_of(0, n)
-    assert d1 == d2                          # chunked == unchunked
+    assert d1 == d2                          # host-buffer path == resident path
     e1, e2, _ = digest_of(0, n)
     assert (e1, e2) == (d1, d2)              # repeatable
+    launches0 = chunky.launch_count()
+    c1, c2, _ = digest_of(0, n, chunky)
+    assert chunky.launch_count() - launches0 > 10      # really ran as many chunks
+    assert (c1, c2) == (d1, d2)              # chunked == unchunked
+    chunky.close()
     assert cells > 10 ** 8
 
 
