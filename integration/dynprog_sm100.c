@@ -6,8 +6,8 @@
  * definitions of those five symbols are renamed to ref_* in the object files by the build recipe
  * (integration/Makefile), nothing in /root/reference is edited or copied.
  *
- * This first binding runs one device batch per call (GmapDP_batch_run on a per-thread batch): the
- * simplest correct rendezvous.  What it does on the host is exactly what
+ * The DP calls of all worker threads meet in one shared device batch (rendezvous, below): with
+ * `gmap -t N` the batches hold up to N boxes.  What the binding does on the host is exactly what
  * the reference entry points do before and after their fills: fetch the genomic segments with
  * Genome_get_segment_* and, for genome gaps, the MaxEnt splice-site probabilities with Maxent_hr_*.
  */
@@ -30,38 +30,117 @@
 #include "dynprog_end.h"
 #include "gmapdp_shim.h"
 
+/* ---- rendezvous: DP calls of all worker threads are gathered into one device batch ---------------
+ * A thread queues its call in the shared batch and waits.  The first thread of a generation is its
+ * leader: it waits (bounded) until every thread that is currently inside a DP entry point has queued
+ * its call, runs the batch on the GPU, hands each waiter its result, and wakes them.  With one thread
+ * this degenerates to one batch per call, with `gmap -t N` (N >> cores: workers only block here) the
+ * batches hold up to N boxes.  Results do not depend on batch composition. */
 static gmapdp_ctx *sm100_ctx = NULL;
+static gmapdp_batch *sm100_shared = NULL;
 static pthread_once_t sm100_once = PTHREAD_ONCE_INIT;
-static __thread gmapdp_batch *sm100_batch = NULL;
-static __thread gmapdp_pair *sm100_pairs = NULL;
-static __thread int sm100_npairs = 0;
+static pthread_mutex_t sm100_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t sm100_cv_done = PTHREAD_COND_INITIALIZER, sm100_cv_submit = PTHREAD_COND_INITIALIZER;
+static volatile int sm100_inflight = 0;		/* threads inside a DP entry point */
+static long sm100_wait_us = 300;
+static unsigned long sm100_nbatches = 0, sm100_ncalls = 0;
+static double sm100_t_wait = 0.0, sm100_t_run = 0.0, sm100_t_result = 0.0, sm100_cells = 0.0;
+
+static double now_s (void) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC,&t);
+  return (double) t.tv_sec + 1e-9 * (double) t.tv_nsec;
+}
+
+typedef struct sm100_slot {
+  int id, done, n, cap, mode;
+  int iout[10];
+  double dout[2];
+  gmapdp_pair *pairs;
+} sm100_slot;
+
+#define SM100_MAXPENDING 4096
+static sm100_slot *sm100_pending[SM100_MAXPENDING];
+static int sm100_npending = 0, sm100_leader = 0;
+static __thread sm100_slot sm100_my = {0,0,0,0,0,{0},{0},NULL};
+
+static void sm100_report (void) {
+  if (getenv("GMAP_SM100_STATS"))
+    fprintf(stderr,"gmap.sm100: %lu DP calls in %lu device batches (%.1f calls per batch)\n",sm100_ncalls,sm100_nbatches,
+	    sm100_nbatches ? (double) sm100_ncalls / (double) sm100_nbatches : 0.0);
+  if (getenv("GMAP_SM100_STATS"))
+    fprintf(stderr,"gmap.sm100 timing: leader wait %.3f s, device batches %.3f s, result replay %.3f s, %.0f DP cells\n",
+	    sm100_t_wait,sm100_t_run,sm100_t_result,sm100_cells);
+}
 
 static void sm100_init (void) {
-  const char *dev = getenv("GMAP_SM100_DEVICE");
+  const char *dev = getenv("GMAP_SM100_DEVICE"), *w = getenv("GMAP_SM100_WAIT_US");
+  if (w) sm100_wait_us = atol(w);
   if (gmapdp_create(&sm100_ctx,dev ? atoi(dev) : 0) != GMAPDP_OK) {
     fprintf(stderr,"gmap.sm100: %s\n",gmapdp_last_error(sm100_ctx));
     exit(9);
   }
+  atexit(sm100_report);
 }
 
-static gmapdp_batch *get_batch (Dynprog_T dynprog, int need_pairs) {
-  pthread_once(&sm100_once,sm100_init);
-  if (sm100_batch == NULL) sm100_batch = GmapDP_batch_new(sm100_ctx,dynprog->max_rlength,dynprog->max_glength);
-  GmapDP_batch_clear(sm100_batch);
-  if (need_pairs > sm100_npairs) {
-    free(sm100_pairs);
-    sm100_npairs = need_pairs + 1024;
-    sm100_pairs = (gmapdp_pair *) malloc((size_t) sm100_npairs * sizeof(gmapdp_pair));
-  }
-  return sm100_batch;
+/* called with the mutex held, before queueing: the shared batch is created from the first caller's limits
+   (all Dynprog_T of a gmap run have the same max_rlength / max_glength, gmap.c:4898-4903) */
+static gmapdp_batch *shared_batch (Dynprog_T dynprog) {
+  if (sm100_shared == NULL) sm100_shared = GmapDP_batch_new(sm100_ctx,dynprog->max_rlength,dynprog->max_glength);
+  return sm100_shared;
 }
 
-static void run_batch (gmapdp_batch *b) {
-  if (GmapDP_batch_run(b) != GMAPDP_OK) {
-    fprintf(stderr,"gmap.sm100: %s\n",GmapDP_batch_error(b));
-    exit(9);
+static void slot_reserve (int need_pairs) {
+  if (need_pairs > sm100_my.cap) {
+    free(sm100_my.pairs);
+    sm100_my.cap = need_pairs + 1024;
+    sm100_my.pairs = (gmapdp_pair *) malloc((size_t) sm100_my.cap * sizeof(gmapdp_pair));
   }
 }
+
+/* called with the mutex held and the call queued under `id`; returns with the result in sm100_my */
+static void rendezvous (int id, int mode) {
+  sm100_slot *me = &sm100_my;
+  int k;
+  me->id = id; me->done = 0; me->mode = mode;
+  if (sm100_npending >= SM100_MAXPENDING) { fprintf(stderr,"gmap.sm100: too many waiting threads\n"); exit(9); }
+  sm100_pending[sm100_npending++] = me;
+  if (!sm100_leader) {
+    struct timespec dl;
+    double t0 = now_s(), t1, t2;
+    sm100_leader = 1;
+    clock_gettime(CLOCK_REALTIME,&dl);
+    dl.tv_nsec += sm100_wait_us * 1000L;
+    while (dl.tv_nsec >= 1000000000L) { dl.tv_nsec -= 1000000000L; dl.tv_sec++; }
+    while (sm100_npending < sm100_inflight && sm100_npending < SM100_MAXPENDING) {
+      if (pthread_cond_timedwait(&sm100_cv_submit,&sm100_mu,&dl) != 0) break;	/* timeout */
+    }
+    t1 = now_s();
+    if (GmapDP_batch_run(sm100_shared) != GMAPDP_OK) {
+      fprintf(stderr,"gmap.sm100: %s\n",GmapDP_batch_error(sm100_shared));
+      exit(9);
+    }
+    t2 = now_s();
+    sm100_cells += (double) GmapDP_batch_cells(sm100_shared);
+    sm100_nbatches++; sm100_ncalls += sm100_npending;
+    for (k = 0; k < sm100_npending; k++) {
+      sm100_slot *s = sm100_pending[k];
+      s->n = GmapDP_result(sm100_shared,s->id,s->iout,s->dout,s->pairs,s->cap);
+      s->done = 1;
+    }
+    sm100_npending = 0;
+    GmapDP_batch_clear(sm100_shared);
+    sm100_t_wait += t1 - t0; sm100_t_run += t2 - t1; sm100_t_result += now_s() - t2;
+    sm100_leader = 0;
+    pthread_cond_broadcast(&sm100_cv_done);
+  } else {
+    pthread_cond_signal(&sm100_cv_submit);
+    while (!me->done) pthread_cond_wait(&sm100_cv_done,&sm100_mu);
+  }
+}
+
+#define ENTER() do { pthread_once(&sm100_once,sm100_init); __sync_fetch_and_add(&sm100_inflight,1); } while (0)
+#define LEAVE() __sync_fetch_and_sub(&sm100_inflight,1)
 
 /* records come head first: cons them from the tail */
 static List_T pairs_to_list (Pairpool_T pool, const gmapdp_pair *p, int n) {
@@ -90,11 +169,14 @@ Dynprog_single_gap (int *dynprogindex, int *traceback_score, int *nmatches, int 
 		    bool watsonp, int genestrand, bool jump_late_p,
 		    Genome_T genome, Genome_T genomealt, Pairpool_T pairpool,
 		    int extraband_single, bool widebandp, double defect_rate) {
-  gmapdp_batch *b = get_batch(dynprog,rlength + glength + 8);
   char *gseq, *galt, empty[1] = {'\0'};
-  int iout[6], id, n;
+  int id;
+  const int *iout;
+  List_T l;
   bool fetch = (rlength > 0 && glength > 0 && rlength <= dynprog->max_rlength && glength <= dynprog->max_glength);
 
+  ENTER();
+  slot_reserve(rlength + glength + 8);
   if (fetch) {
     gseq = (char *) malloc(glength + 1); galt = (char *) malloc(glength + 1);
     if (watsonp) Genome_get_segment_right(gseq,galt,genome,genomealt,chroffset+goffset,glength,chrhigh,/*revcomp*/false);
@@ -102,14 +184,18 @@ Dynprog_single_gap (int *dynprogindex, int *traceback_score, int *nmatches, int 
   } else {
     gseq = galt = empty;
   }
-  id = GmapDP_single_gap(b,*dynprogindex,rsequence,rsequenceuc,rlength,glength,roffset,goffset,gseq,galt,
+  pthread_mutex_lock(&sm100_mu);
+  id = GmapDP_single_gap(shared_batch(dynprog),*dynprogindex,rsequence,rsequenceuc,rlength,glength,roffset,goffset,gseq,galt,
 			 jump_late_p,extraband_single,widebandp,defect_rate);
-  run_batch(b);
-  n = GmapDP_result(b,id,iout,NULL,sm100_pairs,sm100_npairs);
+  rendezvous(id,GMAPDP_SINGLE);
+  pthread_mutex_unlock(&sm100_mu);
+  LEAVE();
+  iout = sm100_my.iout;
   *dynprogindex = iout[0]; *traceback_score = iout[1]; *nmatches = iout[2]; *nmismatches = iout[3];
   *nopens = iout[4]; *nindels = iout[5];
   if (fetch) { free(galt); free(gseq); }
-  return (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,sm100_pairs,n);
+  l = (sm100_my.n < 0) ? (List_T) NULL : pairs_to_list(pairpool,sm100_my.pairs,sm100_my.n);
+  return l;
 }
 
 static List_T
@@ -118,11 +204,13 @@ end_gap (bool end5, int *dynprogindex, int *traceback_score, int *nmatches, int 
 	 Univcoord_T chroffset, Univcoord_T chrhigh, bool watsonp, bool jump_late_p,
 	 Genome_T genome, Genome_T genomealt, Pairpool_T pairpool, int extraband_end, double defect_rate,
 	 Endalign_T endalign, bool require_pos_score_p) {
-  gmapdp_batch *b = get_batch(dynprog,rlength + glength + 8);
   char *gseq, *galt, empty[1] = {'\0'};
-  int iout[6], id, n, gl = glength;
+  int id, gl = glength;
+  const int *iout;
   bool fetch;
 
+  ENTER();
+  slot_reserve(rlength + glength + 8);
   /* the reference chops before it fetches (dynprog_end.c:1357-1378 / :1986-1999) */
   if (endalign != QUERYEND_NOGAPS && gl > dynprog->max_glength) gl = dynprog->max_glength;
   fetch = (rlength > 0 && gl > 0 && !(end5 && goffset < 0));
@@ -138,16 +226,19 @@ end_gap (bool end5, int *dynprogindex, int *traceback_score, int *nmatches, int 
   } else {
     gseq = galt = empty;
   }
-  if (end5) id = GmapDP_end5_gap(b,*dynprogindex,rseq,rsequc,rlength,glength,roffset,goffset,gseq,galt,jump_late_p,
+  pthread_mutex_lock(&sm100_mu);
+  if (end5) id = GmapDP_end5_gap(shared_batch(dynprog),*dynprogindex,rseq,rsequc,rlength,glength,roffset,goffset,gseq,galt,jump_late_p,
 				 extraband_end,defect_rate,(int) endalign,require_pos_score_p);
-  else id = GmapDP_end3_gap(b,*dynprogindex,rseq,rsequc,rlength,glength,roffset,goffset,gseq,galt,jump_late_p,
+  else id = GmapDP_end3_gap(shared_batch(dynprog),*dynprogindex,rseq,rsequc,rlength,glength,roffset,goffset,gseq,galt,jump_late_p,
 			    extraband_end,defect_rate,(int) endalign,require_pos_score_p);
-  run_batch(b);
-  n = GmapDP_result(b,id,iout,NULL,sm100_pairs,sm100_npairs);
+  rendezvous(id,end5 ? GMAPDP_END5 : GMAPDP_END3);
+  pthread_mutex_unlock(&sm100_mu);
+  LEAVE();
+  iout = sm100_my.iout;
   *dynprogindex = iout[0]; *traceback_score = iout[1]; *nmatches = iout[2]; *nmismatches = iout[3];
   *nopens = iout[4]; *nindels = iout[5];
   if (fetch) { free(galt); free(gseq); }
-  return (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,sm100_pairs,n);
+  return (sm100_my.n < 0) ? (List_T) NULL : pairs_to_list(pairpool,sm100_my.pairs,sm100_my.n);
 }
 
 List_T
@@ -192,14 +283,17 @@ Dynprog_genome_gap (int *dynprogindex, int *new_leftgenomepos, int *new_rightgen
 		    int cdna_direction, bool watsonp, int genestrand, bool jump_late_p,
 		    Genome_T genome, Genome_T genomealt, Pairpool_T pairpool, int extraband_paired,
 		    double defect_rate, int maxpeelback, bool halfp, bool finalp) {
-  gmapdp_batch *b = get_batch(dynprogL,2 * rlength + glengthL + glengthR + 16);
   char *gL, *gLa, *gR, *gRa, empty[1] = {'\0'};
-  double *lp = NULL, *rp = NULL, dout[2];
-  int iout[10], id, n, c;
+  double *lp = NULL, *rp = NULL;
+  const double *dout;
+  const int *iout;
+  int id, c;
   Univcoord_T pos;
   bool fetch = (rlength > 1 && rlength <= dynprogL->max_rlength && glengthL <= dynprogL->max_glength &&
 		rlength <= dynprogR->max_rlength && glengthR <= dynprogR->max_glength && glengthL > 0 && glengthR > 0);
 
+  ENTER();
+  slot_reserve(2 * rlength + glengthL + glengthR + 16);
   if (fetch) {
     gL = (char *) malloc(glengthL + 1); gLa = (char *) malloc(glengthL + 1);
     gR = (char *) malloc(glengthR + 1); gRa = (char *) malloc(glengthR + 1);
@@ -234,17 +328,20 @@ Dynprog_genome_gap (int *dynprogindex, int *new_leftgenomepos, int *new_rightgen
   } else {
     gL = gLa = gR = gRa = empty;
   }
-  id = GmapDP_genome_gap(b,*dynprogindex,rsequence,rsequenceuc,rlength,glengthL,glengthR,roffset,goffsetL,rev_goffsetR,
+  pthread_mutex_lock(&sm100_mu);
+  id = GmapDP_genome_gap(shared_batch(dynprogL),*dynprogindex,rsequence,rsequenceuc,rlength,glengthL,glengthR,roffset,goffsetL,rev_goffsetR,
 			 gL,gLa,gR,gRa,lp,rp,cdna_direction,jump_late_p,extraband_paired,defect_rate,maxpeelback,halfp,finalp);
-  run_batch(b);
-  n = GmapDP_result(b,id,iout,dout,sm100_pairs,sm100_npairs);
+  rendezvous(id,GMAPDP_GENOME);
+  pthread_mutex_unlock(&sm100_mu);
+  LEAVE();
+  iout = sm100_my.iout; dout = sm100_my.dout;
   *dynprogindex = iout[0];
   SET(new_leftgenomepos,iout[1]); SET(new_rightgenomepos,iout[2]); SET(traceback_score,iout[3]);
   *nmatches = iout[4]; *nmismatches = iout[5]; *nopens = iout[6]; *nindels = iout[7];
   SET(exonhead,iout[8]); *introntype = iout[9];
   *left_prob = dout[0]; *right_prob = dout[1];
   if (fetch) { free(rp); free(lp); free(gRa); free(gR); free(gLa); free(gL); }
-  return (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,sm100_pairs,n);
+  return (sm100_my.n < 0) ? (List_T) NULL : pairs_to_list(pairpool,sm100_my.pairs,sm100_my.n);
 }
 
 List_T
@@ -257,12 +354,14 @@ Dynprog_cdna_gap (int *dynprogindex, int *traceback_score, bool *incompletep,
 		  bool watsonp, int genestrand, bool jump_late_p,
 		  Genome_T genome, Genome_T genomealt, Pairpool_T pairpool,
 		  int extraband_paired, double defect_rate) {
-  gmapdp_batch *b = get_batch(dynprogL,rlengthL + rlengthR + 2 * glength + 32);
   char *g, *ga, *rg, *rga, empty[1] = {'\0'};
-  int iout[3], id, n, rev_goffset = goffset + glength - 1;
+  const int *iout;
+  int id, rev_goffset = goffset + glength - 1;
   bool fetch = (glength > 1 && glength <= dynprogR->max_glength && rlengthR <= dynprogR->max_rlength &&
 		glength <= dynprogL->max_glength && rlengthL <= dynprogL->max_rlength);
 
+  ENTER();
+  slot_reserve(rlengthL + rlengthR + 2 * glength + 32);
   if (fetch) {
     g = (char *) malloc(glength + 1); ga = (char *) malloc(glength + 1);
     rg = (char *) malloc(glength + 1); rga = (char *) malloc(glength + 1);
@@ -276,13 +375,16 @@ Dynprog_cdna_gap (int *dynprogindex, int *traceback_score, bool *incompletep,
   } else {
     g = ga = rg = rga = empty;
   }
-  id = GmapDP_cdna_gap(b,*dynprogindex,rsequenceL,rsequence_ucL,rev_rsequenceR,rev_rsequence_ucR,rlengthL,rlengthR,glength,
+  pthread_mutex_lock(&sm100_mu);
+  id = GmapDP_cdna_gap(shared_batch(dynprogL),*dynprogindex,rsequenceL,rsequence_ucL,rev_rsequenceR,rev_rsequence_ucR,rlengthL,rlengthR,glength,
 		       roffsetL,rev_roffsetR,goffset,g,ga,rg,rga,jump_late_p,extraband_paired,defect_rate);
-  run_batch(b);
-  n = GmapDP_result(b,id,iout,NULL,sm100_pairs,sm100_npairs);
+  rendezvous(id,GMAPDP_CDNA);
+  pthread_mutex_unlock(&sm100_mu);
+  LEAVE();
+  iout = sm100_my.iout;
   *dynprogindex = iout[0];
   SET(traceback_score,iout[1]);
   if (iout[2]) *incompletep = true;
   if (fetch) { free(rga); free(rg); free(ga); free(g); }
-  return (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,sm100_pairs,n);
+  return (sm100_my.n < 0) ? (List_T) NULL : pairs_to_list(pairpool,sm100_my.pairs,sm100_my.n);
 }
