@@ -5,8 +5,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libgmapdp_b200.so")
-SOURCES = ["gmapdp_kernels.cu", "gmapdp_shim.cpp"]
-HEADERS = ["gmapdp_layout.h", "gmapdp_tables.h", "../../include/gmapdp_b200.h", "../../include/gmapdp_shim.h"]
+SOURCES = ["gmapdp_kernels.cu", "gmapdp_shim.cpp", "gmapchain_kernels.cu", "gmapchain_shim.cpp"]
+HEADERS = ["gmapdp_layout.h", "gmapdp_tables.h", "gmapdp_internal.h", "../../include/gmapdp_b200.h", "../../include/gmapdp_shim.h",
+           "../../include/gmapchain_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

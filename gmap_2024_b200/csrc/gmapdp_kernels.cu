@@ -1012,6 +1012,8 @@ gmapdp_dp_kernel (KernelArgs ka) {
 /* ------------------------------------------------------------------------------------------------
  * Host side: context, memory, launches (the C ABI of include/gmapdp_b200.h)
  * ---------------------------------------------------------------------------------------------- */
+#include "gmapdp_internal.h"
+
 struct gmapdp_ctx {
   int device, sm_count, grid, max_smem;
   int kgrid[2], ksmem_cols[2]; size_t kws_words[2];	/* per kernel kind: 0 = full, 1 = tri */
@@ -1039,7 +1041,16 @@ struct gmapdp_ctx {
   /* resident batch */
   int nboxes; size_t ws_words; int smem_cols; size_t script_need;
   long launches;
+  /* the chaining engine (gmapchain_kernels.cu) hangs its state here */
+  void *chain; void (*chain_free) (void *);
 };
+
+GdpCtxView gmapdp_ctx_view (gmapdp_ctx *ctx) {
+  GdpCtxView v;
+  v.device = ctx->device; v.sm_count = ctx->sm_count; v.err = &ctx->err; v.launches = &ctx->launches;
+  v.chain = &ctx->chain; v.chain_free = &ctx->chain_free;
+  return v;
+}
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return GMAPDP_ERR_CUDA; } } while (0)
@@ -1058,7 +1069,7 @@ static int grow (gmapdp_ctx *ctx, T **p, size_t *cap, size_t need) {
 extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   gmapdp_ctx *ctx = new gmapdp_ctx();
   *out = ctx;
-  ctx->device = device; ctx->launches = 0; ctx->nboxes = 0;
+  ctx->device = device; ctx->launches = 0; ctx->nboxes = 0; ctx->chain = NULL; ctx->chain_free = NULL;
   ctx->d_tables = NULL; ctx->d_boxes = NULL; ctx->cap_boxes = 0; ctx->d_order = NULL; ctx->cap_order = 0; ctx->cap_results = 0; ctx->d_seq = NULL; ctx->cap_seq = 0;
   ctx->d_probs = NULL; ctx->cap_probs = 0; ctx->d_results = NULL; ctx->d_script = NULL; ctx->cap_script = 0;
   ctx->d_cursor = NULL; ctx->d_queue = NULL; ctx->d_ws = NULL; ctx->cap_ws = 0; ctx->h_pin = NULL; ctx->cap_pin = 0;
@@ -1105,6 +1116,7 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
 extern "C" void gmapdp_destroy (gmapdp_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->chain && ctx->chain_free) ctx->chain_free(ctx->chain);
   cudaFree(ctx->d_tables); cudaFree(ctx->d_boxes); cudaFree(ctx->d_order); cudaFree(ctx->d_seq); cudaFree(ctx->d_probs);
   cudaFree(ctx->d_results); cudaFree(ctx->d_script); cudaFree(ctx->d_cursor); cudaFree(ctx->d_queue); cudaFree(ctx->d_ws); cudaFree(ctx->d_kws[0]); cudaFree(ctx->d_kws[1]);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);

@@ -47,6 +47,12 @@ def load_library():
         lib.GmapDP_batch_h2d_bytes.restype = C.c_size_t
         lib.GmapDP_batch_d2h_bytes.restype = C.c_size_t
         lib.GmapDP_device_result.restype = C.POINTER(DeviceResult)
+        lib.GmapChain_batch_new.restype = C.c_void_p
+        lib.GmapChain_batch_error.restype = C.c_char_p
+        lib.GmapChain_batch_nhits.restype = C.c_long
+        lib.GmapChain_batch_h2d_bytes.restype = C.c_long
+        lib.GmapChain_batch_d2h_bytes.restype = C.c_long
+        lib.GmapChain_batch_digest.restype = C.c_ulonglong
         for fn in ("gmapdp_destroy", "gmapdp_last_error", "gmapdp_launch_count", "gmapdp_device_info"):
             getattr(lib, fn).argtypes = None
         _lib = lib
@@ -88,6 +94,16 @@ class Engine:
 
     def batch(self, max_rlength=2000, max_glength=2030):
         return Batch(self, max_rlength, max_glength)
+
+    def chain_setup(self, splicingp=1, cross_species_p=0, sufflookback=60, nsufflookback=5, maxintronlen=500000):
+        """Stage2_setup (stage2.c:129) for the chaining engine; defaults are gmap's (gmap.c:269,270,347)."""
+        rc = self.lib.gmapchain_setup(self.ctx, int(splicingp), int(cross_species_p), int(sufflookback), int(nsufflookback),
+                                      int(maxintronlen))
+        if rc != 0:
+            raise EngineError(self.lib.gmapdp_last_error(self.ctx).decode())
+
+    def chain_batch(self):
+        return ChainBatch(self)
 
 
 class Batch:
@@ -214,3 +230,111 @@ class Batch:
     def device_result(self, cid):
         p = self.lib.GmapDP_device_result(self.h, cid)
         return p.contents if p else None
+
+
+class ChainBatch:
+    """Batch form of align_compute_lookback (stage2.c:4402): add(problem) with the dicts of tests/chaingen.py
+    (positions CSR, npositions, minactive, maxactive, ...), run(), then paths(id)."""
+
+    def __init__(self, engine):
+        import numpy as np
+        self.np = np
+        self.e = engine
+        self.lib = engine.lib
+        self.h = C.c_void_p(self.lib.GmapChain_batch_new(engine.ctx))
+        self._keep = []
+
+    def free(self):
+        if self.h:
+            self.lib.GmapChain_batch_free(self.h)
+            self.h = C.c_void_p()
+
+    def clear(self):
+        self.lib.GmapChain_batch_clear(self.h)
+        self._keep = []
+
+    def _check(self, rc):
+        if rc < 0:
+            raise EngineError(self.lib.GmapChain_batch_error(self.h).decode() or "gmapchain error %d" % rc)
+        return rc
+
+    def add(self, pb, use_canonical_p=0):
+        np = self.np
+        L = int(pb["querylength"])
+        pos = np.ascontiguousarray(pb["positions"], dtype=np.uint32)
+        npos = np.ascontiguousarray(pb["npositions"], dtype=np.int32)
+        mina = np.ascontiguousarray(pb["minactive"], dtype=np.uint32)
+        maxa = np.ascontiguousarray(pb["maxactive"], dtype=np.uint32)
+        if len(pos) == 0:
+            pos = np.zeros(1, dtype=np.uint32)
+        base = pos.ctypes.data
+        cum = np.concatenate([[0], np.cumsum(np.maximum(npos, 0))[:-1]]).astype(np.int64) if L else np.zeros(0, dtype=np.int64)
+        ptrs = (C.c_void_p * max(L, 1))(*[base + 4 * int(c) for c in cum])
+        rc = self.lib.GmapChain_lookback(
+            self.h, ptrs, npos.ctypes.data_as(C.c_void_p), C.c_int(int(np.maximum(npos, 0).sum())),
+            mina.ctypes.data_as(C.c_void_p), maxa.ctypes.data_as(C.c_void_p), C.c_int(L), C.c_int(int(pb["querystart"])),
+            C.c_int(int(pb["queryend"])), C.c_int(int(pb["indexsize"])), C.c_int(int(pb["localp"])),
+            C.c_int(int(pb["skip_repetitive_p"])), C.c_int(int(use_canonical_p)), C.c_int(4), C.c_int(int(pb["favor_right_p"])),
+            C.c_int(int(pb["middlep"])), C.c_int(int(pb["max_nalignments"])))
+        return self._check(rc)
+
+    def run(self):
+        self._check(self.lib.GmapChain_batch_run(self.h))
+
+    def upload(self):
+        self._check(self.lib.GmapChain_batch_upload(self.h))
+
+    def run_resident(self):
+        ms = C.c_float()
+        self._check(self.lib.GmapChain_batch_run_resident(self.h, C.byref(ms)))
+        return ms.value
+
+    def download(self):
+        self._check(self.lib.GmapChain_batch_download(self.h))
+
+    def ncalls(self):
+        return self.lib.GmapChain_batch_ncalls(self.h)
+
+    def nhits(self):
+        return self.lib.GmapChain_batch_nhits(self.h)
+
+    def h2d_bytes(self):
+        return self.lib.GmapChain_batch_h2d_bytes(self.h)
+
+    def d2h_bytes(self):
+        return self.lib.GmapChain_batch_d2h_bytes(self.h)
+
+    def digest(self):
+        return self.lib.GmapChain_batch_digest(self.h)
+
+    def paths(self, cid):
+        """[(cell[5], pairs (n,2) int32: querypos, position)] in the reference's order"""
+        np = self.np
+        n = self._check(self.lib.GmapChain_npaths(self.h, cid))
+        out = []
+        cell = (C.c_int * 5)()
+        cap = 4096
+        for k in range(n):
+            while True:
+                q = np.zeros(cap, dtype=np.int32)
+                p = np.zeros(cap, dtype=np.uint32)
+                m = self.lib.GmapChain_path(self.h, cid, k, cell, q.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), cap)
+                if m >= 0:
+                    break
+                if m > -16:     # an error code, not a size
+                    self._check(m)
+                cap = -m
+            out.append((list(cell), np.stack([q[:m], p[:m].astype(np.int32)], axis=1)))
+        return out
+
+    def links(self):
+        """(links (tot,5) with the trace label zeroed, scores (tot,)) of the last run, in batch hit order"""
+        np = self.np
+        tot = self.nhits()
+        links = np.zeros((max(tot, 1), 5), dtype=np.int32)
+        scores = np.zeros(max(tot, 1), dtype=np.int32)
+        rc = self.lib.gmapchain_download_links(self.e.ctx, links.ctypes.data_as(C.c_void_p), scores.ctypes.data_as(C.c_void_p),
+                                               C.c_size_t(tot))
+        if rc != 0:
+            raise EngineError(self.lib.gmapdp_last_error(self.e.ctx).decode())
+        return links[:tot], scores[:tot]

@@ -24,16 +24,16 @@ def lib():
 
 def declared_symbols():
     names = []
-    for h in ("gmapdp_b200.h", "gmapdp_shim.h"):
+    for h in ("gmapdp_b200.h", "gmapdp_shim.h", "gmapchain_b200.h"):
         text = open(os.path.join(ROOT, "include", h)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-        names += re.findall(r"\b((?:gmapdp|GmapDP)_\w+)\s*\(", text)
+        names += re.findall(r"\b((?:gmapdp|GmapDP|gmapchain|GmapChain)_\w+)\s*\(", text)
     return sorted(set(names))
 
 
 def test_exports_every_declared_symbol(lib):
     names = declared_symbols()
-    assert len(names) >= 25
+    assert len(names) >= 45 and "gmapchain_run_batch" in names and "GmapChain_lookback" in names
     for n in names:
         assert hasattr(lib, n), "missing export " + n
 
