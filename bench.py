@@ -188,6 +188,77 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# second kernel: stage-2 chaining, reported under the "chain" key
+# ------------------------------------------------------------------------------------------------
+CHAIN_BYTES_PER_HIT = 28        # 4 B position + 4 B score + 20 B link per (querypos, hit)
+
+
+def chain_section(eng, args, rank, world, barrier, allreduce, MAX, SUM):
+    """`--chain-problems` synthetic chaining problems per GPU (cDNAs of 2-11 exons, 1 % error, against 50-200 kb
+    regions, k = 8: tests/chaingen.py), `--chain-distinct` distinct ones tiled.  Device-resident time per step from CUDA
+    events around zeroing + kernel; e2e through GmapChain_batch_run from host buffers."""
+    import numpy as np
+    import chaingen
+    import chain_harness
+    nd = min(args.chain_distinct, args.chain_problems)
+    rng = np.random.default_rng(args.seed + 7919 * rank)
+    base = [chaingen.make_problem(rng, glen=int(rng.integers(50000, 200000)), nexons=int(rng.integers(2, 12)), exon_len=(80, 400),
+                                  err=0.01, k=8, window="full" if i % 2 else "2000", max_nalignments=10) for i in range(nd)]
+    eng.chain_setup(**chain_harness.SETUP)
+    b = eng.chain_batch()
+    n = 0
+    while n < args.chain_problems:
+        b.add(base[n % nd])
+        n += 1
+    b.upload()
+    for _ in range(max(args.warmup, 3)):
+        b.run_resident()
+    launches0 = eng.launch_count()
+    barrier()
+    dev_ms = sum(b.run_resident() for _ in range(args.steps))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        b.run()                                         # H2D of the pools, kernel, D2H of paths
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0
+    launches = eng.launch_count() - launches0
+    digest = b.digest()
+    hits, h2d, d2h = b.nhits(), b.h2d_bytes(), b.d2h_bytes()
+    dev_ms_max, e2e_ms_max = allreduce(dev_ms, MAX), allreduce(e2e_ms, MAX)
+    tot_problems, tot_hits = allreduce(n, SUM), allreduce(hits, SUM)
+    out = None
+    if rank == 0:
+        ms = dev_ms_max / args.steps
+        peak, peak_src = measured_peaks()
+        achieved = hits * CHAIN_BYTES_PER_HIT / (dev_ms / args.steps / 1e3) / 1e9
+        out = {"metric": "chain_problems_per_s", "value": tot_problems / (ms / 1e3), "unit": "align_compute_lookback calls/s",
+               "hits_per_s": tot_hits / (ms / 1e3), "ms_per_step": ms,
+               "config": {"workload": "stage-2 chaining: synthetic spliced cDNAs (2-11 exons of 80-400 nt, 1 % error) against 50-200 kb "
+                                      "regions, 8-mer hits, lookback direction, gmap defaults", "problems_per_gpu": n,
+                          "distinct_problems": nd, "hits_per_gpu": int(hits), "kernel": "gmapchain_kernel (one warp per problem)"},
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": None, "peak_source": peak_src,
+                            "note": "latency-bound pointer walk: algorithmic bytes = hits x 28 B (SURVEY.md section 8d)"},
+               "e2e": {"value": tot_problems / (e2e_ms_max / args.steps / 1e3), "unit": "align_compute_lookback calls/s",
+                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps},
+               "gpu_launches": int(launches), "digest": "%016x" % digest}
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = chain_harness.RefChain() if chain_harness.have_ref() else chain_harness.OracleChain()
+            t0 = time.perf_counter()
+            k = 0
+            while k < nd and time.perf_counter() - t0 < args.chain_cpu_seconds:
+                cpu.paths(base[k])
+                k += 1
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": k / dt, "unit": "align_compute_lookback calls/s", "cores": 1,
+                                   "kind": "reference" if chain_harness.have_ref() else "port",
+                                   "sample": "first %d of the distinct problems, one thread, through ctypes (%.1f s)" % (k, dt)}
+    b.free()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -267,6 +338,10 @@ def run_ours(args):
     tot_boxes = allreduce(batch.nboxes(), SUM)
     tot_calls = allreduce(batch.ncalls(), SUM)
 
+    chain = None
+    if args.chain_problems > 0:
+        chain = chain_section(eng, args, rank, world, barrier, allreduce, MAX, SUM)
+
     if rank == 0:
         ms_per_step = dev_ms_max / args.steps
         value = tot_cells / (ms_per_step / 1e3) / 1e9
@@ -307,6 +382,9 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(batch.h2d_bytes()),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps},
                 "gpu_launches": int(tot_launches), "clocks": clocks, "digest": "%016x" % digest}
+        if chain is not None:
+            line["chain"] = chain
+            line["gpu_launches"] += chain["gpu_launches"]
         if world == 1 and not args.no_cpu_baseline:
             c = cpu_arm(args.seed, args.cpu_seconds, args.small)
             line["cpu_baseline"] = {"value": c["gcups"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"],
@@ -333,6 +411,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-step-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chain-problems", type=int, default=8192, help="stage-2 chaining problems per GPU for the \"chain\" key (0 = skip)")
+    ap.add_argument("--chain-distinct", type=int, default=256)
+    ap.add_argument("--chain-cpu-seconds", type=float, default=5.0)
     ap.add_argument("--modemask", type=int, default=31, help="diagnostics: bit k keeps mode k (single,genome,cdna,end5,end3); 31 = the benchmark config")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -607,6 +607,7 @@ extern "C" int gmapchain_run_resident (gmapdp_ctx *ctx, float *kernel_ms) {
   if (kernel_ms) *kernel_ms = 0.f;
   s->used[1] = s->used[2] = 0;
   if (s->nproblems == 0) return GMAPDP_OK;
+  CKC(cudaEventRecord(s->ev0,s->stream));
   /* the link matrix starts zeroed (CALLOC in Linkmatrix_1d_new / intmatrix_1d_new, stage2.c:403 / :3112) */
   for (int a = 0; a < 7; a++) CKC(cudaMemsetAsync(s->d_hit[a],0,(s->np + 1) * sizeof(int),s->stream));
   CKC(cudaMemsetAsync(s->d_first,0,(s->nq + 1) * sizeof(int),s->stream));
@@ -621,7 +622,6 @@ extern "C" int gmapchain_run_resident (gmapdp_ctx *ctx, float *kernel_ms) {
   D.paths_cap = s->cap_paths; D.pairs_cap = s->cap_pairs / 2;
   D.counters = s->d_counters; D.prm = s->prm;
   const int grid = std::max(1,std::min(s->grid,(s->nproblems + CH_WARPS - 1) / CH_WARPS));
-  CKC(cudaEventRecord(s->ev0,s->stream));
   gmapchain_kernel<<<grid,CH_BLOCK,0,s->stream>>>(D);
   CKC(cudaGetLastError());
   (*v.launches)++;
