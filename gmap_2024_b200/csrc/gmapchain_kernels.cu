@@ -3,15 +3,22 @@
  * What the reference computes (stage2.c:3667-4120, :1073-2020, :2956, :3437, :4140, :4402) is a chain DP over the k-mer
  * hits of one (query, genomic region): queryposes in ascending order, each hit choosing its best predecessor among
  * the active hits of the queryposes processed before it.  The recurrence is sequential in querypos AND in the hits of
- * one querypos (the frontier of score_querypos_lookback_mult is carried from hit to hit), so the parallel axis is the
- * problem: a persistent grid, ONE WARP PER PROBLEM pulled from a work-sorted queue.  Lane 0 walks the recurrence; all
- * 32 lanes do the data-parallel parts (frontier set-up, active-list revision of wide queryposes, best-score reduction,
- * candidate compaction, ranking by repeated arg-min, one traceback per lane).  Many resident warps hide the dependent
- * HBM/L2 latency of the walk.
+ * one querypos (the frontier of score_querypos_lookback_mult is carried from hit to hit), so the outer parallel axis
+ * is the problem: a persistent grid, ONE WARP PER PROBLEM pulled from a work-sorted queue, thousands in flight.
  *
- * State in HBM, structure-of-arrays over the batch's hit pool (seven int32 per hit: consecutive, rootposition,
- * prev querypos, prev hit, trace label, score, next-active) plus two per querypos (first-active, processed stack).
- * After the fill the trace-label and next-active arrays are dead and are reused by the ranking (candidates, kept cells).
+ * Inside a problem the warp runs the recurrence in lock step (every lane holds the same scalars; same-address loads
+ * are one broadcast transaction), and fans out where the reference has independent work:
+ *   section D of a hit (stage2.c:1190-1425 / :1690-1920) looks at up to ~68 earlier queryposes.  Lane j takes the
+ *   j-th of them: it walks that querypos's active list through ranges 1, 2 and 3+4 and keeps its first best
+ *   candidate; the trace-label skip of "range 0" (the only thing that links the lists) is resolved beforehand from
+ *   the list heads, and an ordered prefix-max over the lanes reproduces the strict ">" of the sequential scan and
+ *   its ENOUGH_CONSECUTIVE early exit (lanes past the exit are discarded, their frontier left untouched).
+ *   ranking: best-score reduction, compaction of the cells within FINAL_SCORE_TOLERANCE, repeated arg-min;
+ *   tracebacks: one path per lane.
+ *
+ * State in HBM, two int4 per hit: hot {position, score, next-active, trace label} -- all a list walk touches, one
+ * 16-byte load per candidate -- and cold {consecutive, rootposition, prev querypos, prev hit}; per querypos the
+ * first-active hit and the stack of processed queryposes.
  */
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -27,6 +34,7 @@
 #define CH_BLOCK 128
 #define CH_WARPS (CH_BLOCK / 32)
 #define CH_FRONTIER 256
+#define FULL 0xffffffffu
 
 /* stage2.c:34-110 */
 #define ENOUGH_CONSECUTIVE 32
@@ -45,8 +53,9 @@ struct ChainParams { int splicingp, sufflookback, nsufflookback, maxintronlen; }
 struct ChainDev {
   const gmapchain_problem *problems; const int *order; int nproblems;
   const int *npos; const uint32_t *cum, *mina, *maxa, *pos;
-  int *consec, *root, *ppos, *phit, *trace, *score, *next;
-  int *first, *proc;
+  int4 *hot, *cold;			/* per hit */
+  int *cand, *kept;			/* per hit: ranking scratch */
+  int *first, *proc;			/* per querypos */
   gmapchain_result *results; gmapchain_path *paths; int *pairs;
   unsigned long long paths_cap, pairs_cap;
   unsigned long long *counters;		/* [0] queue cursor, [1] path records used, [2] pairs used */
@@ -55,273 +64,318 @@ struct ChainDev {
 
 struct Prob {
   const int *npos; const uint32_t *cum, *mina, *maxa, *pos;
-  int *consec, *root, *ppos, *phit, *trace, *score, *next, *first, *proc;
+  int4 *hot, *cold; int *cand, *kept, *first, *proc;
   int L, tot, qs, qe, k, localp, skiprep, favor_right, middlep, max_nal;
   int nproc, tracei;
 };
 
 struct Best { int consec, root, score, pp, ph, trace; };
 
-/* ranges 2 and 3+4 of section D for one earlier querypos, from active hit `ph` on (stage2.c:1236-1420, :1712-1915) */
-__device__ __forceinline__ void scan_prev (const Prob &P, const ChainParams &prm, Best &b, int &tracei,
-					   uint32_t position, int qd, int pq, int ph) {
-  const int o = (int) P.cum[pq], credit = -qd / P.k;
-  uint32_t pp;
-  while (ph != -1 && (pp = P.pos[o + ph]) + EQUAL_DISTANCE_NOT_SPLICING + qd < position) {
-    const int diff = (int) (position - pp) - qd;
-    int s = P.score[o + ph] + credit;
-    s -= prm.splicingp ? (diff / TEN_THOUSAND + 1) : (diff + 1);
-    if (s > b.score) {
-      b.consec = 0;			/* diff > EQUAL_DISTANCE_FOR_CONSECUTIVE (0) in this range */
-      b.root = P.root[o + ph]; b.score = s; b.pp = pq; b.ph = ph; b.trace = ++tracei;
+#define H_POS(v) ((uint32_t) (v).x)
+#define H_SCORE(v) ((v).y)
+#define H_NEXT(v) ((v).z)
+#define H_TRACE(v) ((v).w)
+
+/* Everything below is executed by all 32 lanes with identical arguments unless it says otherwise; stores are
+   issued by every lane with the same value (one transaction), so each lane always reads back its own writes. */
+
+__device__ __forceinline__ void commit (Prob &P, int i, uint32_t position, const Best &b) {	/* stage2.c:1428-1450 */
+  int trace, score;
+  if (b.pp >= 0) { trace = b.trace; score = b.score; }
+  else if (P.localp) { trace = ++P.tracei; score = P.k; }
+  else { trace = ++P.tracei; score = b.score; }
+  P.cold[i] = make_int4(b.consec,b.root,b.pp,b.ph);
+  P.hot[i] = make_int4((int) position,score,0,trace);
+}
+
+/* Section D for one hit at `position` of querypos q: the entries ns = 0..nlast of the processed stack (newest first).
+   frontier != NULL (the several-hits case) carries each entry's list position from hit to hit and applies range 1
+   unconditionally (stage2.c:1722); frontier == NULL starts from first[] and applies it only when splicing (:1217). */
+__device__ void section_d (Prob &P, const ChainParams &prm, Best &b, int q, uint32_t position, int nlast, int *frontier, int lane) {
+  int last_trace = -1;
+  for (int ns0 = 0; ns0 <= nlast && b.consec < ENOUGH_CONSECUTIVE; ns0 += 32) {
+    const int ns = ns0 + lane;
+    const bool valid = ns <= nlast;
+    int pq = 0, qd = 0, o = 0, head = -1;
+    int4 hv = make_int4(0,0,-1,0);
+    if (valid) {
+      pq = P.proc[P.nproc - 1 - ns]; qd = q - pq; o = (int) P.cum[pq];
+      head = frontier ? frontier[ns] : P.first[pq];
+      if (head != -1) hv = P.hot[o + head];
     }
-    ph = P.next[o + ph];
-  }
-  while (ph != -1 && (pp = P.pos[o + ph]) + P.k <= position) {
-    const int gd = (int) (position - pp);
-    const int s = P.score[o + ph] + 1;
-    if (s > b.score) {
-      b.consec = (gd == qd) ? P.consec[o + ph] + qd : 0;
-      b.root = P.root[o + ph]; b.score = s; b.pp = pq; b.ph = ph; b.trace = P.trace[o + ph];
+    /* range 0, in stack order: skip the leading hits whose label equals the label the previous list started with.
+       Only list heads are involved; a deeper walk (rare) is done by all lanes together. */
+    int start = -1; int4 sv = hv;
+    const unsigned havemask = __ballot_sync(FULL,head != -1);
+    for (unsigned m = havemask; m; m &= m - 1) {
+      const int j = __ffs(m) - 1;
+      int cur = __shfl_sync(FULL,head,j);
+      const int oj = __shfl_sync(FULL,o,j);
+      int4 cv;
+      cv.x = __shfl_sync(FULL,hv.x,j); cv.y = __shfl_sync(FULL,hv.y,j); cv.z = __shfl_sync(FULL,hv.z,j); cv.w = __shfl_sync(FULL,hv.w,j);
+      while (cur != -1 && H_TRACE(cv) == last_trace) {
+	cur = H_NEXT(cv);
+	if (cur != -1) cv = P.hot[oj + cur];
+      }
+      if (cur != -1) last_trace = H_TRACE(cv);
+      if (lane == j) { start = cur; sv = cv; }
     }
-    ph = P.next[o + ph];
+    /* ranges 1, 2, 3+4: each lane on its own list */
+    int ph = start, newfront = start;
+    int m_score = INT_MIN, m_ph = -1, m_kind = 0, m_same = 0;
+    if (ph != -1) {
+      const int credit = -qd / P.k;
+      if (frontier || prm.splicingp) {
+	while (ph != -1 && H_POS(sv) + prm.maxintronlen + qd <= position) { ph = H_NEXT(sv); if (ph != -1) sv = P.hot[o + ph]; }
+      }
+      newfront = ph;
+      while (ph != -1 && H_POS(sv) + EQUAL_DISTANCE_NOT_SPLICING + qd < position) {	/* range 2 */
+	const int diff = (int) (position - H_POS(sv)) - qd;
+	int s = H_SCORE(sv) + credit;
+	s -= prm.splicingp ? (diff / TEN_THOUSAND + 1) : (diff + 1);
+	if (s > m_score) { m_score = s; m_ph = ph; m_kind = 2; m_same = 0; }
+	ph = H_NEXT(sv); if (ph != -1) sv = P.hot[o + ph];
+      }
+      while (ph != -1 && H_POS(sv) + P.k <= position) {					/* ranges 3+4 */
+	const int s = H_SCORE(sv) + 1;
+	if (s > m_score) { m_score = s; m_ph = ph; m_kind = 4; m_same = ((int) (position - H_POS(sv)) == qd); }
+	ph = H_NEXT(sv); if (ph != -1) sv = P.hot[o + ph];
+      }
+    }
+    /* consecutive count the hit would get from this lane's candidate (diff <= EQUAL_DISTANCE_FOR_CONSECUTIVE == 0) */
+    int m_consec = 0;
+    if (m_ph != -1 && m_same) m_consec = P.cold[o + m_ph].x + qd;
+    /* ordered prefix max: highest score, earliest lane */
+    long long key = (m_ph != -1) ? ((long long) m_score * 256 + (long long) (31 - lane)) : LLONG_MIN;
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long up = __shfl_up_sync(FULL,key,d);
+      if (lane >= d && up > key) key = up;
+    }
+    const bool beats = (key != LLONG_MIN) && ((int) (key >> 8) > b.score);
+    const int wl = 31 - (int) (key & 0xff);			/* lane holding the running best, if it beats b */
+    const int wc = __shfl_sync(FULL,m_consec,beats ? wl : 0);
+    const int consec_after = beats ? wc : b.consec;
+    const unsigned stopmask = __ballot_sync(FULL,valid && consec_after >= ENOUGH_CONSECUTIVE);
+    const unsigned validmask = __ballot_sync(FULL,valid);
+    const int jlast = 31 - __clz(validmask);
+    const int jstop = stopmask ? (__ffs(stopmask) - 1) : jlast;
+    if (frontier) {
+      if (valid && lane <= jstop && head != -1) frontier[ns] = newfront;
+      __syncwarp();
+    }
+    const int fbeats = __shfl_sync(FULL,(int) beats,jstop);
+    if (fbeats) {
+      const int w = __shfl_sync(FULL,wl,jstop);
+      const int wo = __shfl_sync(FULL,o,w), wph = __shfl_sync(FULL,m_ph,w), wkind = __shfl_sync(FULL,m_kind,w);
+      b.score = __shfl_sync(FULL,m_score,w); b.consec = __shfl_sync(FULL,m_consec,w);
+      b.pp = __shfl_sync(FULL,pq,w); b.ph = wph;
+      b.root = P.cold[wo + wph].y;
+      b.trace = (wkind == 2) ? ++P.tracei : H_TRACE(P.hot[wo + wph]);
+    }
+    if (stopmask) break;
   }
 }
 
-__device__ __forceinline__ void commit (Prob &P, int i, const Best &b) {	/* stage2.c:1428-1450 */
-  P.consec[i] = b.consec; P.root[i] = b.root; P.ppos[i] = b.pp; P.phit[i] = b.ph;
-  if (b.pp >= 0) { P.trace[i] = b.trace; P.score[i] = b.score; }
-  else if (P.localp) { P.trace[i] = ++P.tracei; P.score[i] = P.k; }
-  else { P.trace[i] = ++P.tracei; P.score[i] = b.score; }
+/* how many leading entries of the processed stack satisfy (ns <= a || qd - k <= b): the distance grows along the
+   stack (queryposes are processed in ascending order), so the test of stage2.c:1204 / :1626-1631 holds on a prefix */
+__device__ int reach (const Prob &P, int q, int a, int b, int lane) {
+  int n = 0;
+  for (int s0 = 0; s0 < P.nproc; s0 += 32) {
+    const int ns = s0 + lane;
+    bool ok = false;
+    if (ns < P.nproc) { const int qd = q - P.proc[P.nproc - 1 - ns]; ok = (ns <= a || qd - P.k <= b); }
+    const unsigned m = __ballot_sync(FULL,ok);
+    n += __popc(m);
+    if (m != FULL) break;
+  }
+  return n;
 }
 
-/* lane 0: one querypos with a single hit in its window (score_querypos_lookback_one, stage2.c:1073) */
-__device__ void score_one (Prob &P, const ChainParams &prm, int q, int h) {
+/* adjacent hit on the newest processed querypos: first active hit with pos + qd >= position, from `ph` on */
+__device__ __forceinline__ int adjacent (const Prob &P, int o, int qd, uint32_t position, int ph, int4 &v, bool &found) {
+  uint32_t pp = position;
+  while (ph != -1) {
+    v = P.hot[o + ph];
+    pp = H_POS(v);
+    if (pp + qd < position) ph = H_NEXT(v); else break;
+  }
+  found = (pp + qd == position);
+  return ph;
+}
+
+/* score_querypos_lookback_one (stage2.c:1073) */
+__device__ void score_one (Prob &P, const ChainParams &prm, int q, int h, int lane) {
   const int i = (int) P.cum[q] + h;
   const uint32_t position = P.pos[i];
   Best b = { P.k, (int) position, 0, -1, -1, 0 };
   int nlookback = prm.nsufflookback, lookback = prm.sufflookback;
   if (P.nproc > 0) {
     const int pq = P.proc[P.nproc - 1], o = (int) P.cum[pq], qd = q - pq;
-    int ph = P.first[pq];
-    uint32_t pp = position;
-    while (ph != -1 && (pp = P.pos[o + ph]) + qd < position) ph = P.next[o + ph];
-    if (pp + qd == position) {
-      b.consec = P.consec[o + ph] + qd; b.root = P.root[o + ph]; b.score = P.score[o + ph] + qd;
-      b.pp = pq; b.ph = ph; b.trace = P.trace[o + ph];
+    int4 v; bool found;
+    const int ph = adjacent(P,o,qd,position,P.first[pq],v,found);
+    if (found) {
+      const int4 c = P.cold[o + ph];
+      b.consec = c.x + qd; b.root = c.y; b.score = H_SCORE(v) + qd; b.pp = pq; b.ph = ph; b.trace = H_TRACE(v);
       nlookback = 1; lookback = prm.sufflookback / 2;
     }
-  }
-  bool donep = false;
-  int nseen = 0, last_trace = -1;
-  for (int j = P.nproc - 1; j >= 0 && b.consec < ENOUGH_CONSECUTIVE && !donep; j--, nseen++) {
-    const int pq = P.proc[j], qd = q - pq;
-    if (nseen > nlookback && qd - P.k > lookback) donep = true;
-    int ph = P.first[pq];
-    if (ph != -1) {
-      const int o = (int) P.cum[pq];
-      while (ph != -1 && P.trace[o + ph] == last_trace) ph = P.next[o + ph];
-      if (ph != -1) last_trace = P.trace[o + ph];
-      if (prm.splicingp) {
-	while (ph != -1 && P.pos[o + ph] + prm.maxintronlen + qd <= position) ph = P.next[o + ph];
-      }
-      scan_prev(P,prm,b,P.tracei,position,qd,pq,ph);
+    if (b.consec < ENOUGH_CONSECUTIVE) {
+      /* the loop of :1196 runs through the first entry that fails the reach test, inclusive */
+      const int n = reach(P,q,nlookback,lookback,lane);
+      section_d(P,prm,b,q,position,min(n,P.nproc - 1),NULL,lane);
     }
   }
-  commit(P,i,b);
+  commit(P,i,position,b);
 }
 
-/* one querypos with several hits in its window (score_querypos_lookback_mult, stage2.c:1470).  All lanes enter;
-   lane 0 walks, the others help with the frontier. */
+/* score_querypos_lookback_mult (stage2.c:1470) */
 __device__ void score_mult (Prob &P, const ChainParams &prm, int q, int lo, int hi, int *frontier, int lane) {
   const int base = (int) P.cum[q];
   if (P.nproc == 0) {
-    if (lane == 0) {
-      for (int h = lo; h < hi; h++) {
-	const int i = base + h;
-	P.consec[i] = P.k; P.root[i] = (int) P.pos[i]; P.ppos[i] = -1; P.phit[i] = -1;
-	if (P.localp) { P.trace[i] = ++P.tracei; P.score[i] = P.k; }
-	else P.score[i] = 0;
-      }
+    for (int h = lo; h < hi; h++) {
+      const int i = base + h;
+      const uint32_t position = P.pos[i];
+      int4 hv = P.hot[i];
+      P.cold[i] = make_int4(P.k,(int) position,-1,-1);
+      hv.x = (int) position;
+      if (P.localp) { hv.w = ++P.tracei; hv.y = P.k; } else hv.y = 0;
+      P.hot[i] = hv;
     }
     return;
   }
-  /* how far back to look (queryposes are processed in ascending order, so the distance grows along the stack and
-     both tests of stage2.c:1626-1631 hold on a prefix): the last index of each prefix, and the frontier of that many */
-  int max_adj = 0, max_nonadj = 0;
-  {
-    int n_adj = 0, n_non = 0;		/* number of leading stack entries that satisfy each test */
-    for (int s0 = 0; s0 < P.nproc; s0 += 32) {
-      const int ns = s0 + lane;
-      bool a = false, b2 = false;
-      if (ns < P.nproc) {
-	const int pq = P.proc[P.nproc - 1 - ns], qd = q - pq;
-	a = (ns <= 1 || qd - P.k <= prm.sufflookback / 2);
-	b2 = (ns <= prm.nsufflookback || qd - P.k <= prm.sufflookback);
-	if (b2 && ns < CH_FRONTIER) frontier[ns] = P.first[pq];
-      }
-      const unsigned ma = __ballot_sync(0xffffffffu,a), mb = __ballot_sync(0xffffffffu,b2);
-      n_adj += __popc(ma); n_non += __popc(mb);
-      if (mb != 0xffffffffu) break;	/* the wider test failed somewhere in this group: nothing further back counts */
-    }
-    max_adj = n_adj - 1; max_nonadj = n_non - 1;
-    __syncwarp();
-  }
-  if (lane != 0) return;
+  const int max_adj = reach(P,q,1,prm.sufflookback / 2,lane) - 1;
+  const int max_nonadj = reach(P,q,prm.nsufflookback,prm.sufflookback,lane) - 1;
+  __syncwarp();
+  for (int ns = lane; ns <= max_nonadj && ns < CH_FRONTIER; ns += 32) frontier[ns] = P.first[P.proc[P.nproc - 1 - ns]];
+  __syncwarp();
   const int adjq = P.proc[P.nproc - 1], adjo = (int) P.cum[adjq], adjqd = q - adjq;
   int overall = 0, adjf = P.first[adjq];
   for (int h = lo; h < hi; h++) {
-    const uint32_t position = P.pos[base + h];
-    int ph = adjf;
-    uint32_t pp = position;
-    while (ph != -1 && (pp = P.pos[adjo + ph]) + adjqd < position) ph = P.next[adjo + ph];
-    adjf = ph;
-    if (pp + adjqd == position) overall = max(overall,P.consec[adjo + ph] + adjqd);
+    int4 v; bool found;
+    adjf = adjacent(P,adjo,adjqd,P.pos[base + h],adjf,v,found);
+    if (found) overall = max(overall,P.cold[adjo + adjf].x + adjqd);
   }
   adjf = P.first[adjq];
   for (int h = lo; h < hi; h++) {
     const uint32_t position = P.pos[base + h];
     Best b;
-    int ph = adjf, max_nseen;
-    uint32_t pp = position;
-    while (ph != -1 && (pp = P.pos[adjo + ph]) + adjqd < position) ph = P.next[adjo + ph];
-    adjf = ph;
-    if (pp + adjqd == position) {
-      b.consec = P.consec[adjo + ph] + adjqd; b.root = P.root[adjo + ph]; b.pp = adjq; b.ph = ph;
-      b.score = P.score[adjo + ph] + adjqd; b.trace = P.trace[adjo + ph];
+    int4 v; bool found;
+    int max_nseen;
+    adjf = adjacent(P,adjo,adjqd,position,adjf,v,found);
+    if (found) {
+      const int4 c = P.cold[adjo + adjf];
+      b.consec = c.x + adjqd; b.root = c.y; b.pp = adjq; b.ph = adjf; b.score = H_SCORE(v) + adjqd; b.trace = H_TRACE(v);
       max_nseen = max_adj;
     } else {
       b.consec = P.k; b.root = (int) position; b.pp = -1; b.ph = -1; b.score = 0; b.trace = -1;
       max_nseen = max_nonadj;
     }
-    if (overall < GREEDY_NCONSECUTIVE) {
-      int last_trace = -1;
-      for (int nseen = 0; nseen < P.nproc && b.consec < ENOUGH_CONSECUTIVE && nseen <= max_nseen; nseen++) {
-	ph = frontier[nseen];
-	if (ph != -1) {
-	  const int pq = P.proc[P.nproc - 1 - nseen], o = (int) P.cum[pq], qd = q - pq;
-	  while (ph != -1 && P.trace[o + ph] == last_trace) ph = P.next[o + ph];
-	  if (ph != -1) last_trace = P.trace[o + ph];
-	  while (ph != -1 && P.pos[o + ph] + prm.maxintronlen + qd <= position) ph = P.next[o + ph];
-	  frontier[nseen] = ph;
-	  scan_prev(P,prm,b,P.tracei,position,qd,pq,ph);
-	}
-      }
-    }
-    commit(P,base + h,b);
+    if (overall < GREEDY_NCONSECUTIVE && b.consec < ENOUGH_CONSECUTIVE) section_d(P,prm,b,q,position,max_nseen,frontier,lane);
+    commit(P,base + h,position,b);
   }
 }
 
-/* active list of a querypos = its hits within SCORE_FOR_RESTRICT of its best (revise_active_lookback, stage2.c:2956) */
+/* revise_active_lookback (stage2.c:2956): the hits within SCORE_FOR_RESTRICT of the querypos's best, linked in order */
 __device__ void revise_active (Prob &P, int q, int lo, int hi) {
-  int *sc = P.score + P.cum[q], *nx = P.next + P.cum[q];
+  const int base = (int) P.cum[q];
   if (lo >= hi) { P.first[q] = -1; return; }
-  int best = sc[lo];
-  for (int h = lo + 1; h < hi; h++) best = max(best,sc[h]);
+  int best = P.hot[base + lo].y;
+  for (int h = lo + 1; h < hi; h++) best = max(best,P.hot[base + h].y);
   const int thr = max(best - SCORE_FOR_RESTRICT,0);
   int prev = -1, firsth = -1;
   for (int h = lo; h < hi; h++) {
-    if (sc[h] > thr) {
-      if (prev < 0) firsth = h; else nx[prev] = h;
+    if (P.hot[base + h].y > thr) {
+      if (prev < 0) firsth = h; else P.hot[base + prev].z = h;
       prev = h;
     }
   }
-  if (prev >= 0) nx[prev] = -1;
+  if (prev >= 0) P.hot[base + prev].z = -1;
   P.first[q] = firsth;
 }
 
-__device__ void new_start (Prob &P, int q) {	/* stage2.c:3793-3812, :3941-3964 */
+__device__ void new_start (Prob &P, int q) {	/* stage2.c:3793-3812, :3941-3964 (rootposition is left alone) */
   const int base = (int) P.cum[q];
   for (int h = 0; h < P.npos[q]; h++) {
     const int i = base + h;
-    P.ppos[i] = P.phit[i] = -1; P.consec[i] = P.k; P.trace[i] = -1; P.score[i] = P.k;
+    int4 c = P.cold[i], v = P.hot[i];
+    c.x = P.k; c.z = -1; c.w = -1;
+    v.x = (int) P.pos[i]; v.y = P.k; v.w = -1;
+    P.cold[i] = c; P.hot[i] = v;
   }
 }
 
-/* align_compute_scores_lookback (stage2.c:3667).  The loop state lives in lane 0 and is broadcast where the other
-   lanes are asked to help. */
+/* align_compute_scores_lookback (stage2.c:3667) */
 __device__ void chain_fill (Prob &P, const ChainParams &prm, int *frontier, int lane) {
-  int q = 0, nskipped = 0, min_hits = 1000000, specific_q = -1, specific_lo = 0, specific_hi = 0;
+  int q, nskipped = 0, min_hits = 1000000, specific_q = -1, specific_lo = 0, specific_hi = 0;
   int grand_score = 0, grand_q = -1, grand_h = -1;
 
-  if (lane == 0) {
-    for (q = 0; q < P.qs && q < P.L; q++) P.first[q] = -1;
-    while (q <= P.qe && P.npos[q] <= 0) { P.first[q] = -1; q++; }
-    if (q <= P.qe) { new_start(P,q); revise_active(P,q,0,P.npos[q]); }
-  }
-  q = __shfl_sync(0xffffffffu,q,0);
+  for (q = lane; q < P.qs && q < P.L; q += 32) P.first[q] = -1;
+  q = min(P.qs,P.L);
+  while (q <= P.qe && P.npos[q] <= 0) { P.first[q] = -1; q++; }
+  if (q <= P.qe) { new_start(P,q); revise_active(P,q,0,P.npos[q]); }
   while (q <= P.qe) {
-    int lo = 0, hi = 0, next_q = 0, mode = 0;	/* mode 0: skipped, 1: single hit / none, 2: several hits */
-    if (lane == 0) {
-      const uint32_t *m = P.pos + P.cum[q];
-      const int n = P.npos[q];
-      const uint32_t lo_b = P.mina[q], hi_b = P.maxa[q];
+    const uint32_t *m = P.pos + P.cum[q];
+    const int n = P.npos[q];
+    const uint32_t lo_b = P.mina[q], hi_b = P.maxa[q];
+    int lo, hi, next_q;
+    if (n > 8) {	/* sorted ascending: the two linear scans of stage2.c:3838-3846 as binary searches */
+      int a = 0, b2 = n;
+      while (a < b2) { const int mid = (a + b2) >> 1; if (m[mid] < lo_b) a = mid + 1; else b2 = mid; }
+      lo = a; b2 = n;
+      while (a < b2) { const int mid = (a + b2) >> 1; if (m[mid] <= hi_b) a = mid + 1; else b2 = mid; }
+      hi = a;
+    } else {
       int h = 0;
-      if (n > 8) {	/* sorted ascending: the two linear scans of stage2.c:3838-3846 as binary searches */
-	int a = 0, b2 = n;
-	while (a < b2) { const int mid = (a + b2) >> 1; if (m[mid] < lo_b) a = mid + 1; else b2 = mid; }
-	lo = a; b2 = n;
-	while (a < b2) { const int mid = (a + b2) >> 1; if (m[mid] <= hi_b) a = mid + 1; else b2 = mid; }
-	hi = a;
-      } else {
-	while (h < n && m[h] < lo_b) h++;
-	lo = h;
-	while (h < n && m[h] <= hi_b) h++;
-	hi = h;
-      }
-      if (P.skiprep && hi - lo >= MAX_NACTIVE && nskipped <= MAX_SKIPPED) {
-	P.first[q] = -1;
-	nskipped++;
-	if (hi - lo < min_hits) { min_hits = hi - lo; specific_q = q; specific_lo = lo; specific_hi = hi; }
-	mode = 0; next_q = q + 1;
-      } else {
-	if (nskipped > MAX_SKIPPED) { next_q = q; q = specific_q; lo = specific_lo; hi = specific_hi; }
-	else next_q = q + 1;
-	mode = (hi - lo > 1) ? 2 : 1;
-      }
+      while (h < n && m[h] < lo_b) h++;
+      lo = h;
+      while (h < n && m[h] <= hi_b) h++;
+      hi = h;
     }
-    mode = __shfl_sync(0xffffffffu,mode,0);
-    if (mode == 2) {
-      q = __shfl_sync(0xffffffffu,q,0); lo = __shfl_sync(0xffffffffu,lo,0); hi = __shfl_sync(0xffffffffu,hi,0);
-      score_mult(P,prm,q,lo,hi,frontier,lane);
-      __syncwarp();
+    if (P.skiprep && hi - lo >= MAX_NACTIVE && nskipped <= MAX_SKIPPED) {
+      P.first[q] = -1;
+      nskipped++;
+      if (hi - lo < min_hits) { min_hits = hi - lo; specific_q = q; specific_lo = lo; specific_hi = hi; }
+      q++;
+      continue;
     }
-    if (lane == 0 && mode != 0) {
-      const int base = (int) P.cum[q], nhits = hi - lo;
+    if (nskipped > MAX_SKIPPED) { next_q = q; q = specific_q; lo = specific_lo; hi = specific_hi; }
+    else next_q = q + 1;
+    const int base = (int) P.cum[q], nhits = hi - lo;
+    if (nhits > 0) {
       int best_s = 0, best_h = -1;
-      if (nhits > 0) {
-	if (nhits == 1) {
-	  score_one(P,prm,q,lo);
-	  if (P.score[base + lo] > 0) { best_s = P.score[base + lo]; best_h = lo; }
-	} else {
-	  for (int h = lo; h < hi; h++) if (P.score[base + h] > best_s) { best_s = P.score[base + h]; best_h = h; }
-	}
-	nskipped = 0; min_hits = 1000000; specific_q = -1;
-	if (!P.middlep && best_h < 0) new_start(P,q);
-	if (prm.splicingp && best_h >= 0 && P.phit[base + best_h] < 0 && grand_q >= 0 && q >= grand_q + P.k) {	/* :3966-3990 */
-	  if ((best_s = P.score[P.cum[grand_q] + grand_h] - (q - grand_q)) > 0) {
-	    const uint32_t pp = P.pos[P.cum[grand_q] + grand_h];
-	    for (int h = lo; h < hi; h++) {
-	      const uint32_t position = P.pos[base + h];
-	      if (position > pp + prm.maxintronlen) {
-	      } else if (position >= pp + P.k) {
-		const int i = base + h;
-		P.consec[i] = P.k; P.ppos[i] = grand_q; P.phit[i] = grand_h; P.trace[i] = ++P.tracei; P.score[i] = best_s;
-	      }
+      if (nhits == 1) {
+	score_one(P,prm,q,lo,lane);
+	const int s = P.hot[base + lo].y;
+	if (s > 0) { best_s = s; best_h = lo; }
+      } else {
+	score_mult(P,prm,q,lo,hi,frontier,lane);
+	for (int h = lo; h < hi; h++) { const int s = P.hot[base + h].y; if (s > best_s) { best_s = s; best_h = h; } }
+      }
+      nskipped = 0; min_hits = 1000000; specific_q = -1;
+      if (!P.middlep && best_h < 0) new_start(P,q);
+      if (prm.splicingp && best_h >= 0 && P.cold[base + best_h].w < 0 && grand_q >= 0 && q >= grand_q + P.k) {	/* :3966-3990 */
+	const int4 gv = P.hot[P.cum[grand_q] + grand_h];
+	if ((best_s = H_SCORE(gv) - (q - grand_q)) > 0) {
+	  const uint32_t pp = H_POS(gv);
+	  for (int h = lo; h < hi; h++) {
+	    const uint32_t position = P.pos[base + h];
+	    if (position > pp + prm.maxintronlen) {
+	    } else if (position >= pp + P.k) {
+	      const int i = base + h;
+	      int4 c = P.cold[i], v = P.hot[i];
+	      c.x = P.k; c.z = grand_q; c.w = grand_h;
+	      v.y = best_s; v.w = ++P.tracei;
+	      P.cold[i] = c; P.hot[i] = v;
 	    }
 	  }
 	}
-	if (best_h >= 0 && best_s >= grand_score && P.consec[base + best_h] > EXON_DEFN) {
-	  grand_score = best_s; grand_q = q; grand_h = best_h;
-	}
       }
-      revise_active(P,q,lo,hi);
-      if (P.npos[q] > 0) P.proc[P.nproc++] = q;
+      if (best_h >= 0 && best_s >= grand_score && P.cold[base + best_h].x > EXON_DEFN) {
+	grand_score = best_s; grand_q = q; grand_h = best_h;
+      }
     }
-    P.nproc = __shfl_sync(0xffffffffu,P.nproc,0);
-    P.tracei = __shfl_sync(0xffffffffu,P.tracei,0);
-    q = __shfl_sync(0xffffffffu,next_q,0);
-    __syncwarp();
+    revise_active(P,q,lo,hi);
+    if (P.npos[q] > 0) P.proc[P.nproc++] = q;
+    q = next_q;
   }
 }
 
@@ -345,23 +399,24 @@ __device__ __forceinline__ bool cell_before (const Prob &P, unsigned long long k
   return P.favor_right ? (ia > ib) : (ia < ib);
 }
 
-__device__ void rank_and_trace (const ChainDev &D, Prob &P, gmapchain_result &res, int *sh, int lane) {
-  const int start = (int) P.cum[P.qs < P.L ? P.qs : P.L - 1];
+__device__ void rank_and_trace (const ChainDev &D, Prob &P, gmapchain_result &res, int lane) {
+  int *cand = P.cand, *kept = P.kept;
+  res.status = 0; res.npaths = 0; res.bestscore = 0; res.ncandidates = 0; res.path_off = 0;
+  if (P.qs > P.qe) return;
+  const int start = (int) P.cum[P.qs];
   const int end = (P.qe + 1 < P.L) ? (int) P.cum[P.qe + 1] : P.tot;
-  int *cand = P.next, *kept = P.trace;	/* dead after the fill */
   int B = 0;
-  for (int i = start + lane; i < end; i += 32) B = max(B,P.score[i]);
-  for (int o = 16; o > 0; o >>= 1) B = max(B,__shfl_xor_sync(0xffffffffu,B,o));
-  res.status = 0; res.npaths = 0; res.bestscore = B; res.ncandidates = 0; res.path_off = 0;
-  if (B <= 0 || P.qs > P.qe) { res.bestscore = B > 0 ? B : 0; return; }
+  for (int i = start + lane; i < end; i += 32) B = max(B,P.hot[i].y);
+  for (int o = 16; o > 0; o >>= 1) B = max(B,__shfl_xor_sync(FULL,B,o));
+  if (B <= 0) return;
+  res.bestscore = B;
   const int T = max(B - FINAL_SCORE_TOLERANCE,0);
-  /* compaction (order does not matter: the selection below uses a total order) */
   int ncand = 0;
   for (int i0 = start; i0 < end; i0 += 32) {
     const int i = i0 + lane;
-    const bool c = (i < end) && P.score[i] > T;
-    const unsigned m = __ballot_sync(0xffffffffu,c);
-    if (c) cand[start + ncand + __popc(m & ((1u << lane) - 1))] = i;	/* write index <= read index: in place is safe */
+    const bool c = (i < end) && P.hot[i].y > T;
+    const unsigned m = __ballot_sync(FULL,c);
+    if (c) cand[ncand + __popc(m & ((1u << lane) - 1))] = i;
     ncand += __popc(m);
   }
   __syncwarp();
@@ -370,55 +425,62 @@ __device__ void rank_and_trace (const ChainDev &D, Prob &P, gmapchain_result &re
   for (int p = 0; p < ncand; p++) {
     unsigned long long bk = ~0ull; int bi = -1, bslot = -1;
     for (int s = p + lane; s < ncand; s += 32) {
-      const int idx = cand[start + s];
-      const unsigned long long key = ((unsigned long long) (unsigned) (0x7fffffff - P.score[idx]) << 32) | ((unsigned) P.root[idx] ^ 0x80000000u);
+      const int idx = cand[s];
+      const unsigned long long key = ((unsigned long long) (unsigned) (0x7fffffff - P.hot[idx].y) << 32) | ((unsigned) P.cold[idx].y ^ 0x80000000u);
       if (bi < 0 || cell_before(P,key,idx,bk,bi)) { bk = key; bi = idx; bslot = s; }
     }
     for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long ok = __shfl_xor_sync(0xffffffffu,bk,o);
-      const int oi = __shfl_xor_sync(0xffffffffu,bi,o), os = __shfl_xor_sync(0xffffffffu,bslot,o);
+      const unsigned long long ok = __shfl_xor_sync(FULL,bk,o);
+      const int oi = __shfl_xor_sync(FULL,bi,o), os = __shfl_xor_sync(FULL,bslot,o);
       if (oi >= 0 && (bi < 0 || cell_before(P,ok,oi,bk,bi))) { bk = ok; bi = oi; bslot = os; }
     }
-    if (lane == 0) { cand[start + bslot] = cand[start + p]; cand[start + p] = bi; }
+    if (lane == 0) { cand[bslot] = cand[p]; cand[p] = bi; }
     __syncwarp();
-    const int s = P.score[bi], r = P.root[bi];
+    const int s = P.hot[bi].y, r = P.cold[bi].y;
     if (nk >= P.max_nal && s < B) break;
-    /* was this root seen?  (first appearance carries the root's best score) */
-    int seen_score = -1;
-    for (int j = lane; j < nk; j += 32) { const int kj = kept[start + j]; if (P.root[kj] == r) seen_score = P.score[kj]; }
-    for (int o = 16; o > 0; o >>= 1) seen_score = max(seen_score,__shfl_xor_sync(0xffffffffu,seen_score,o));
+    int seen_score = -1;		/* was this root seen?  (its first appearance carries the root's best score) */
+    for (int j = lane; j < nk; j += 32) { const int kj = kept[j]; if (P.cold[kj].y == r) seen_score = P.hot[kj].y; }
+    for (int o = 16; o > 0; o >>= 1) seen_score = max(seen_score,__shfl_xor_sync(FULL,seen_score,o));
     if (seen_score >= 0 && seen_score != s) continue;		/* not the best end of its root */
     if (!((nk < P.max_nal || s == B) && s > B - FINAL_SCORE_TOLERANCE)) break;
-    if (lane == 0) kept[start + nk] = bi;
+    if (lane == 0) kept[nk] = bi;
     nk++;
     __syncwarp();
   }
   /* path records, then one traceback per lane (traceback_one, stage2.c:4140) */
   unsigned long long poff = 0;
   if (lane == 0) poff = atomicAdd(&D.counters[1],(unsigned long long) nk);
-  poff = __shfl_sync(0xffffffffu,poff,0);
+  poff = __shfl_sync(FULL,poff,0);
   res.npaths = nk; res.path_off = (uint32_t) poff;
   for (int j = lane; j < nk; j += 32) {
-    const int idx = kept[start + j];
+    const int idx = kept[j];
     const int q0 = qpos_of(P,idx), h0 = idx - (int) P.cum[q0];
     int q = q0, h = h0, n = 0;
-    while (q >= 0 && P.consec[P.cum[q] + h] < MIN_TERMINAL_NCONSECUTIVE) { const int i = (int) P.cum[q] + h; q = P.ppos[i]; h = P.phit[i]; }
+    while (q >= 0) {
+      const int4 c = P.cold[P.cum[q] + h];
+      if (c.x >= MIN_TERMINAL_NCONSECUTIVE) break;
+      q = c.z; h = c.w;
+    }
     const int q1 = q, h1 = h;
-    while (q >= 0) { const int i = (int) P.cum[q] + h; n++; q = P.ppos[i]; h = P.phit[i]; }
+    while (q >= 0) { const int4 c = P.cold[P.cum[q] + h]; n++; q = c.z; h = c.w; }
     const unsigned long long off = atomicAdd(&D.counters[2],(unsigned long long) n);
     if (poff + j < D.paths_cap) {
       gmapchain_path pr;
-      pr.score = P.score[idx]; pr.rootposition = P.root[idx]; pr.endposition = (int) P.pos[idx]; pr.querypos = q0; pr.hit = h0;
+      pr.score = P.hot[idx].y; pr.rootposition = P.cold[idx].y; pr.endposition = (int) P.pos[idx]; pr.querypos = q0; pr.hit = h0;
       pr.npairs = n; pr.pair_off = (uint32_t) off; pr.reserved = 0;
       D.paths[poff + j] = pr;
     }
     if (off + n <= D.pairs_cap) {
       int2 *out = reinterpret_cast<int2 *>(D.pairs) + off;
       q = q1; h = h1;
-      for (int t = 0; q >= 0; t++) { const int i = (int) P.cum[q] + h; out[t] = make_int2(q,(int) P.pos[i]); q = P.ppos[i]; h = P.phit[i]; }
+      for (int t = 0; q >= 0; t++) {
+	const int i = (int) P.cum[q] + h;
+	const int4 c = P.cold[i];
+	out[t] = make_int2(q,(int) P.pos[i]);
+	q = c.z; h = c.w;
+      }
     }
   }
-  (void) sh;
 }
 
 __global__ void __launch_bounds__(CH_BLOCK) gmapchain_kernel (ChainDev D) {
@@ -428,27 +490,25 @@ __global__ void __launch_bounds__(CH_BLOCK) gmapchain_kernel (ChainDev D) {
   for (;;) {
     unsigned long long slot = 0;
     if (lane == 0) slot = atomicAdd(&D.counters[0],1ull);
-    slot = __shfl_sync(0xffffffffu,slot,0);
+    slot = __shfl_sync(FULL,slot,0);
     if (slot >= (unsigned long long) D.nproblems) break;
     const int pi = D.order[slot];
     const gmapchain_problem pb = D.problems[pi];
     Prob P;
     P.npos = D.npos + pb.q_off; P.cum = D.cum + pb.q_off; P.mina = D.mina + pb.q_off; P.maxa = D.maxa + pb.q_off;
     P.first = D.first + pb.q_off; P.proc = D.proc + pb.q_off;
-    P.pos = D.pos + pb.p_off; P.consec = D.consec + pb.p_off; P.root = D.root + pb.p_off; P.ppos = D.ppos + pb.p_off;
-    P.phit = D.phit + pb.p_off; P.trace = D.trace + pb.p_off; P.score = D.score + pb.p_off; P.next = D.next + pb.p_off;
+    P.pos = D.pos + pb.p_off; P.hot = D.hot + pb.p_off; P.cold = D.cold + pb.p_off; P.cand = D.cand + pb.p_off; P.kept = D.kept + pb.p_off;
     P.L = pb.querylength; P.tot = pb.totalpositions; P.qs = pb.querystart; P.qe = pb.queryend; P.k = pb.indexsize;
     P.localp = (pb.flags & GMAPCHAIN_F_LOCALP) != 0; P.skiprep = (pb.flags & GMAPCHAIN_F_SKIP_REPETITIVE) != 0;
     P.favor_right = (pb.flags & GMAPCHAIN_F_FAVOR_RIGHT) != 0; P.middlep = (pb.flags & GMAPCHAIN_F_MIDDLEP) != 0;
     P.max_nal = pb.max_nalignments; P.nproc = 0; P.tracei = 0;
     gmapchain_result res;
+    res.status = 0; res.npaths = 0; res.bestscore = 0; res.ncandidates = 0; res.path_off = 0;
     res.reserved[0] = res.reserved[1] = res.reserved[2] = 0;
-    if (P.L <= 0) { res.status = 0; res.npaths = 0; res.bestscore = 0; res.ncandidates = 0; res.path_off = 0; }
-    else {
+    if (P.L > 0) {
       chain_fill(P,D.prm,frontier,lane);
       __syncwarp();
-      __threadfence_block();
-      rank_and_trace(D,P,res,frontier,lane);
+      rank_and_trace(D,P,res,lane);
     }
     if (lane == 0) D.results[pi] = res;
     __syncwarp();
@@ -467,7 +527,8 @@ struct ChainState {
   int *d_npos; uint32_t *d_cum, *d_mina, *d_maxa; size_t cap_q;
   int *d_first, *d_proc;
   uint32_t *d_pos; size_t cap_p;
-  int *d_hit[7];			/* consec, root, ppos, phit, trace, score, next */
+  int4 *d_hot, *d_cold;			/* two int4 per hit */
+  int *d_cand, *d_kept;
   gmapchain_result *d_results; size_t cap_results;
   gmapchain_path *d_paths; size_t cap_paths;
   int *d_pairs; size_t cap_pairs;
@@ -484,7 +545,7 @@ static void chain_state_free (void *p) {
   ChainState *s = (ChainState *) p;
   cudaFree(s->d_problems); cudaFree(s->d_order); cudaFree(s->d_npos); cudaFree(s->d_cum); cudaFree(s->d_mina); cudaFree(s->d_maxa);
   cudaFree(s->d_first); cudaFree(s->d_proc); cudaFree(s->d_pos);
-  for (int a = 0; a < 7; a++) cudaFree(s->d_hit[a]);
+  cudaFree(s->d_hot); cudaFree(s->d_cold); cudaFree(s->d_cand); cudaFree(s->d_kept);
   cudaFree(s->d_results); cudaFree(s->d_paths); cudaFree(s->d_pairs); cudaFree(s->d_counters);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -576,7 +637,10 @@ extern "C" int gmapchain_upload (gmapdp_ctx *ctx, const gmapchain_problem *probl
   if (npositions_total + 1 > cp || !s->d_pos) {
     size_t c = cp;
     if ((rc = growc(v,&s->d_pos,&c,npositions_total + 1))) return rc;
-    for (int a = 0; a < 7; a++) { c = cp; if ((rc = growc(v,&s->d_hit[a],&c,npositions_total + 1))) return rc; }
+    c = cp; if ((rc = growc(v,&s->d_hot,&c,npositions_total + 1))) return rc;
+    c = cp; if ((rc = growc(v,&s->d_cold,&c,npositions_total + 1))) return rc;
+    c = cp; if ((rc = growc(v,&s->d_cand,&c,npositions_total + 1))) return rc;
+    c = cp; if ((rc = growc(v,&s->d_kept,&c,npositions_total + 1))) return rc;
     s->cap_p = c;
   }
   /* longest first (LPT): work grows with the hits and with the query length */
@@ -609,14 +673,13 @@ extern "C" int gmapchain_run_resident (gmapdp_ctx *ctx, float *kernel_ms) {
   if (s->nproblems == 0) return GMAPDP_OK;
   CKC(cudaEventRecord(s->ev0,s->stream));
   /* the link matrix starts zeroed (CALLOC in Linkmatrix_1d_new / intmatrix_1d_new, stage2.c:403 / :3112) */
-  for (int a = 0; a < 7; a++) CKC(cudaMemsetAsync(s->d_hit[a],0,(s->np + 1) * sizeof(int),s->stream));
-  CKC(cudaMemsetAsync(s->d_first,0,(s->nq + 1) * sizeof(int),s->stream));
+  CKC(cudaMemsetAsync(s->d_hot,0,(s->np + 1) * sizeof(int4),s->stream));
+  CKC(cudaMemsetAsync(s->d_cold,0,(s->np + 1) * sizeof(int4),s->stream));
   CKC(cudaMemsetAsync(s->d_counters,0,4 * sizeof(unsigned long long),s->stream));
   ChainDev D;
   D.problems = s->d_problems; D.order = s->d_order; D.nproblems = s->nproblems;
   D.npos = s->d_npos; D.cum = s->d_cum; D.mina = s->d_mina; D.maxa = s->d_maxa; D.pos = s->d_pos;
-  D.consec = s->d_hit[0]; D.root = s->d_hit[1]; D.ppos = s->d_hit[2]; D.phit = s->d_hit[3]; D.trace = s->d_hit[4];
-  D.score = s->d_hit[5]; D.next = s->d_hit[6];
+  D.hot = s->d_hot; D.cold = s->d_cold; D.cand = s->d_cand; D.kept = s->d_kept;
   D.first = s->d_first; D.proc = s->d_proc;
   D.results = s->d_results; D.paths = s->d_paths; D.pairs = s->d_pairs;
   D.paths_cap = s->cap_paths; D.pairs_cap = s->cap_pairs / 2;
@@ -671,12 +734,12 @@ extern "C" int gmapchain_download_links (gmapdp_ctx *ctx, int32_t *links, int32_
   if ((rc = chain_state(ctx,&s)) != GMAPDP_OK) return rc;
   if (npositions_total != s->np) { *v.err = "gmapchain: link download size mismatch"; return GMAPDP_ERR_ARG; }
   CKC(cudaSetDevice(v.device));
-  std::vector<int> tmp(s->np + 1);
-  for (int a = 0; a < 4; a++) {
-    CKC(cudaMemcpy(tmp.data(),s->d_hit[a],s->np * sizeof(int),cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < s->np; i++) links[5 * i + a] = tmp[i];
+  std::vector<int4> tmp(s->np + 1);
+  CKC(cudaMemcpy(tmp.data(),s->d_cold,s->np * sizeof(int4),cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < s->np; i++) {
+    links[5 * i + 0] = tmp[i].x; links[5 * i + 1] = tmp[i].y; links[5 * i + 2] = tmp[i].z; links[5 * i + 3] = tmp[i].w; links[5 * i + 4] = 0;
   }
-  for (size_t i = 0; i < s->np; i++) links[5 * i + 4] = 0;
-  CKC(cudaMemcpy(scores,s->d_hit[5],s->np * sizeof(int),cudaMemcpyDeviceToHost));
+  CKC(cudaMemcpy(tmp.data(),s->d_hot,s->np * sizeof(int4),cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < s->np; i++) scores[i] = tmp[i].y;
   return GMAPDP_OK;
 }
