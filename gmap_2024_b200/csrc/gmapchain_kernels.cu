@@ -71,6 +71,14 @@ struct Prob {
 
 struct Best { int consec, root, score, pp, ph, trace; };
 
+/* the lookforward twins (stage2.c:2020, :2404, :3034, :4610) are the same code with the query axis and the genomic
+   comparisons mirrored: "pp lies more than x before position", in the direction of the walk (unsigned, as the reference) */
+template <bool FWD> __device__ __forceinline__ bool before_lt (uint32_t pp, uint32_t x, uint32_t position) { return FWD ? (pp > position + x) : (pp + x < position); }
+template <bool FWD> __device__ __forceinline__ bool before_le (uint32_t pp, uint32_t x, uint32_t position) { return FWD ? (pp >= position + x) : (pp + x <= position); }
+template <bool FWD> __device__ __forceinline__ bool at_dist (uint32_t pp, uint32_t x, uint32_t position) { return FWD ? (pp == position + x) : (pp + x == position); }
+template <bool FWD> __device__ __forceinline__ int gdist (uint32_t pp, uint32_t position) { return FWD ? (int) (pp - position) : (int) (position - pp); }
+template <bool FWD> __device__ __forceinline__ int qdist (int q, int pq) { return FWD ? pq - q : q - pq; }
+
 #define H_POS(v) ((uint32_t) (v).x)
 #define H_SCORE(v) ((v).y)
 #define H_NEXT(v) ((v).z)
@@ -91,7 +99,7 @@ __device__ __forceinline__ void commit (Prob &P, int i, uint32_t position, const
 /* Section D for one hit at `position` of querypos q: the entries ns = 0..nlast of the processed stack (newest first).
    frontier != NULL (the several-hits case) carries each entry's list position from hit to hit and applies range 1
    unconditionally (stage2.c:1722); frontier == NULL starts from first[] and applies it only when splicing (:1217). */
-__device__ void section_d (Prob &P, const ChainParams &prm, Best &b, int q, uint32_t position, int nlast, int *frontier, int lane) {
+template <bool FWD> __device__ void section_d (Prob &P, const ChainParams &prm, Best &b, int q, uint32_t position, int nlast, int *frontier, int lane) {
   int last_trace = -1;
   for (int ns0 = 0; ns0 <= nlast && b.consec < ENOUGH_CONSECUTIVE; ns0 += 32) {
     const int ns = ns0 + lane;
@@ -99,7 +107,7 @@ __device__ void section_d (Prob &P, const ChainParams &prm, Best &b, int q, uint
     int pq = 0, qd = 0, o = 0, head = -1;
     int4 hv = make_int4(0,0,-1,0);
     if (valid) {
-      pq = P.proc[P.nproc - 1 - ns]; qd = q - pq; o = (int) P.cum[pq];
+      pq = P.proc[P.nproc - 1 - ns]; qd = qdist<FWD>(q,pq); o = (int) P.cum[pq];
       head = frontier ? frontier[ns] : P.first[pq];
       if (head != -1) hv = P.hot[o + head];
     }
@@ -126,19 +134,19 @@ __device__ void section_d (Prob &P, const ChainParams &prm, Best &b, int q, uint
     if (ph != -1) {
       const int credit = -qd / P.k;
       if (frontier || prm.splicingp) {
-	while (ph != -1 && H_POS(sv) + prm.maxintronlen + qd <= position) { ph = H_NEXT(sv); if (ph != -1) sv = P.hot[o + ph]; }
+	while (ph != -1 && before_le<FWD>(H_POS(sv),(uint32_t) (prm.maxintronlen + qd),position)) { ph = H_NEXT(sv); if (ph != -1) sv = P.hot[o + ph]; }
       }
       newfront = ph;
-      while (ph != -1 && H_POS(sv) + EQUAL_DISTANCE_NOT_SPLICING + qd < position) {	/* range 2 */
-	const int diff = (int) (position - H_POS(sv)) - qd;
+      while (ph != -1 && before_lt<FWD>(H_POS(sv),(uint32_t) (EQUAL_DISTANCE_NOT_SPLICING + qd),position)) {	/* range 2 */
+	const int diff = gdist<FWD>(H_POS(sv),position) - qd;
 	int s = H_SCORE(sv) + credit;
 	s -= prm.splicingp ? (diff / TEN_THOUSAND + 1) : (diff + 1);
 	if (s > m_score) { m_score = s; m_ph = ph; m_kind = 2; m_same = 0; }
 	ph = H_NEXT(sv); if (ph != -1) sv = P.hot[o + ph];
       }
-      while (ph != -1 && H_POS(sv) + P.k <= position) {					/* ranges 3+4 */
+      while (ph != -1 && before_le<FWD>(H_POS(sv),(uint32_t) P.k,position)) {				/* ranges 3+4 */
 	const int s = H_SCORE(sv) + 1;
-	if (s > m_score) { m_score = s; m_ph = ph; m_kind = 4; m_same = ((int) (position - H_POS(sv)) == qd); }
+	if (s > m_score) { m_score = s; m_ph = ph; m_kind = 4; m_same = (gdist<FWD>(H_POS(sv),position) == qd); }
 	ph = H_NEXT(sv); if (ph != -1) sv = P.hot[o + ph];
       }
     }
@@ -178,12 +186,12 @@ __device__ void section_d (Prob &P, const ChainParams &prm, Best &b, int q, uint
 
 /* how many leading entries of the processed stack satisfy (ns <= a || qd - k <= b): the distance grows along the
    stack (queryposes are processed in ascending order), so the test of stage2.c:1204 / :1626-1631 holds on a prefix */
-__device__ int reach (const Prob &P, int q, int a, int b, int lane) {
+template <bool FWD> __device__ int reach (const Prob &P, int q, int a, int b, int lane) {
   int n = 0;
   for (int s0 = 0; s0 < P.nproc; s0 += 32) {
     const int ns = s0 + lane;
     bool ok = false;
-    if (ns < P.nproc) { const int qd = q - P.proc[P.nproc - 1 - ns]; ok = (ns <= a || qd - P.k <= b); }
+    if (ns < P.nproc) { const int qd = qdist<FWD>(q,P.proc[P.nproc - 1 - ns]); ok = (ns <= a || qd - P.k <= b); }
     const unsigned m = __ballot_sync(FULL,ok);
     n += __popc(m);
     if (m != FULL) break;
@@ -192,27 +200,27 @@ __device__ int reach (const Prob &P, int q, int a, int b, int lane) {
 }
 
 /* adjacent hit on the newest processed querypos: first active hit with pos + qd >= position, from `ph` on */
-__device__ __forceinline__ int adjacent (const Prob &P, int o, int qd, uint32_t position, int ph, int4 &v, bool &found) {
+template <bool FWD> __device__ __forceinline__ int adjacent (const Prob &P, int o, int qd, uint32_t position, int ph, int4 &v, bool &found) {
   uint32_t pp = position;
   while (ph != -1) {
     v = P.hot[o + ph];
     pp = H_POS(v);
-    if (pp + qd < position) ph = H_NEXT(v); else break;
+    if (before_lt<FWD>(pp,(uint32_t) qd,position)) ph = H_NEXT(v); else break;
   }
-  found = (pp + qd == position);
+  found = at_dist<FWD>(pp,(uint32_t) qd,position);
   return ph;
 }
 
 /* score_querypos_lookback_one (stage2.c:1073) */
-__device__ void score_one (Prob &P, const ChainParams &prm, int q, int h, int lane) {
+template <bool FWD> __device__ void score_one (Prob &P, const ChainParams &prm, int q, int h, int lane) {
   const int i = (int) P.cum[q] + h;
   const uint32_t position = P.pos[i];
   Best b = { P.k, (int) position, 0, -1, -1, 0 };
   int nlookback = prm.nsufflookback, lookback = prm.sufflookback;
   if (P.nproc > 0) {
-    const int pq = P.proc[P.nproc - 1], o = (int) P.cum[pq], qd = q - pq;
+    const int pq = P.proc[P.nproc - 1], o = (int) P.cum[pq], qd = qdist<FWD>(q,pq);
     int4 v; bool found;
-    const int ph = adjacent(P,o,qd,position,P.first[pq],v,found);
+    const int ph = adjacent<FWD>(P,o,qd,position,P.first[pq],v,found);
     if (found) {
       const int4 c = P.cold[o + ph];
       b.consec = c.x + qd; b.root = c.y; b.score = H_SCORE(v) + qd; b.pp = pq; b.ph = ph; b.trace = H_TRACE(v);
@@ -220,15 +228,15 @@ __device__ void score_one (Prob &P, const ChainParams &prm, int q, int h, int la
     }
     if (b.consec < ENOUGH_CONSECUTIVE) {
       /* the loop of :1196 runs through the first entry that fails the reach test, inclusive */
-      const int n = reach(P,q,nlookback,lookback,lane);
-      section_d(P,prm,b,q,position,min(n,P.nproc - 1),NULL,lane);
+      const int n = reach<FWD>(P,q,nlookback,lookback,lane);
+      section_d<FWD>(P,prm,b,q,position,min(n,P.nproc - 1),NULL,lane);
     }
   }
   commit(P,i,position,b);
 }
 
 /* score_querypos_lookback_mult (stage2.c:1470) */
-__device__ void score_mult (Prob &P, const ChainParams &prm, int q, int lo, int hi, int *frontier, int lane) {
+template <bool FWD> __device__ void score_mult (Prob &P, const ChainParams &prm, int q, int lo, int hi, int *frontier, int lane) {
   const int base = (int) P.cum[q];
   if (P.nproc == 0) {
     for (int h = lo; h < hi; h++) {
@@ -242,25 +250,26 @@ __device__ void score_mult (Prob &P, const ChainParams &prm, int q, int lo, int 
     }
     return;
   }
-  const int max_adj = reach(P,q,1,prm.sufflookback / 2,lane) - 1;
-  const int max_nonadj = reach(P,q,prm.nsufflookback,prm.sufflookback,lane) - 1;
+  const int max_adj = reach<FWD>(P,q,1,prm.sufflookback / 2,lane) - 1;
+  const int max_nonadj = reach<FWD>(P,q,prm.nsufflookback,prm.sufflookback,lane) - 1;
   __syncwarp();
   for (int ns = lane; ns <= max_nonadj && ns < CH_FRONTIER; ns += 32) frontier[ns] = P.first[P.proc[P.nproc - 1 - ns]];
   __syncwarp();
-  const int adjq = P.proc[P.nproc - 1], adjo = (int) P.cum[adjq], adjqd = q - adjq;
+  const int adjq = P.proc[P.nproc - 1], adjo = (int) P.cum[adjq], adjqd = qdist<FWD>(q,adjq);
+  const int h0 = FWD ? hi - 1 : lo, hstep = FWD ? -1 : 1;	/* hits are walked away from the processed side */
   int overall = 0, adjf = P.first[adjq];
-  for (int h = lo; h < hi; h++) {
+  for (int h = h0, cnt = lo; cnt < hi; h += hstep, cnt++) {
     int4 v; bool found;
-    adjf = adjacent(P,adjo,adjqd,P.pos[base + h],adjf,v,found);
+    adjf = adjacent<FWD>(P,adjo,adjqd,P.pos[base + h],adjf,v,found);
     if (found) overall = max(overall,P.cold[adjo + adjf].x + adjqd);
   }
   adjf = P.first[adjq];
-  for (int h = lo; h < hi; h++) {
+  for (int h = h0, cnt = lo; cnt < hi; h += hstep, cnt++) {
     const uint32_t position = P.pos[base + h];
     Best b;
     int4 v; bool found;
     int max_nseen;
-    adjf = adjacent(P,adjo,adjqd,position,adjf,v,found);
+    adjf = adjacent<FWD>(P,adjo,adjqd,position,adjf,v,found);
     if (found) {
       const int4 c = P.cold[adjo + adjf];
       b.consec = c.x + adjqd; b.root = c.y; b.pp = adjq; b.ph = adjf; b.score = H_SCORE(v) + adjqd; b.trace = H_TRACE(v);
@@ -269,20 +278,20 @@ __device__ void score_mult (Prob &P, const ChainParams &prm, int q, int lo, int 
       b.consec = P.k; b.root = (int) position; b.pp = -1; b.ph = -1; b.score = 0; b.trace = -1;
       max_nseen = max_nonadj;
     }
-    if (overall < GREEDY_NCONSECUTIVE && b.consec < ENOUGH_CONSECUTIVE) section_d(P,prm,b,q,position,max_nseen,frontier,lane);
+    if (overall < GREEDY_NCONSECUTIVE && b.consec < ENOUGH_CONSECUTIVE) section_d<FWD>(P,prm,b,q,position,max_nseen,frontier,lane);
     commit(P,base + h,position,b);
   }
 }
 
 /* revise_active_lookback (stage2.c:2956): the hits within SCORE_FOR_RESTRICT of the querypos's best, linked in order */
-__device__ void revise_active (Prob &P, int q, int lo, int hi) {
+template <bool FWD> __device__ void revise_active (Prob &P, int q, int lo, int hi) {
   const int base = (int) P.cum[q];
   if (lo >= hi) { P.first[q] = -1; return; }
   int best = P.hot[base + lo].y;
   for (int h = lo + 1; h < hi; h++) best = max(best,P.hot[base + h].y);
   const int thr = max(best - SCORE_FOR_RESTRICT,0);
   int prev = -1, firsth = -1;
-  for (int h = lo; h < hi; h++) {
+  for (int h = FWD ? hi - 1 : lo, cnt = lo; cnt < hi; h += FWD ? -1 : 1, cnt++) {
     if (P.hot[base + h].y > thr) {
       if (prev < 0) firsth = h; else P.hot[base + prev].z = h;
       prev = h;
@@ -303,26 +312,34 @@ __device__ void new_start (Prob &P, int q) {	/* stage2.c:3793-3812, :3941-3964 (
   }
 }
 
-/* align_compute_scores_lookback (stage2.c:3667) */
-__device__ void chain_fill (Prob &P, const ChainParams &prm, int *frontier, int lane) {
+/* align_compute_scores_lookback (stage2.c:3667) / align_compute_scores_lookforward (:4610) */
+template <bool FWD> __device__ void chain_fill (Prob &P, const ChainParams &prm, int *frontier, int lane) {
+  const int step = FWD ? -1 : 1;
   int q, nskipped = 0, min_hits = 1000000, specific_q = -1, specific_lo = 0, specific_hi = 0;
   int grand_score = 0, grand_q = -1, grand_h = -1;
+#define INRANGE(q) (FWD ? (q) >= P.qs : (q) <= P.qe)
 
-  for (q = lane; q < P.qs && q < P.L; q += 32) P.first[q] = -1;
-  q = min(P.qs,P.L);
-  while (q <= P.qe && P.npos[q] <= 0) { P.first[q] = -1; q++; }
-  if (q <= P.qe) { new_start(P,q); revise_active(P,q,0,P.npos[q]); }
-  while (q <= P.qe) {
+  if (FWD) { for (q = P.L - 1 - lane; q > P.qe; q -= 32) P.first[q] = -1; q = P.qe < P.L - 1 ? P.qe : P.L - 1; }
+  else { for (q = lane; q < P.qs && q < P.L; q += 32) P.first[q] = -1; q = min(P.qs,P.L); }
+  while (INRANGE(q) && P.npos[q] <= 0) { P.first[q] = -1; q += step; }
+  if (INRANGE(q)) { new_start(P,q); revise_active<FWD>(P,q,0,P.npos[q]); }
+  while (INRANGE(q)) {
     const uint32_t *m = P.pos + P.cum[q];
     const int n = P.npos[q];
     const uint32_t lo_b = P.mina[q], hi_b = P.maxa[q];
     int lo, hi, next_q;
-    if (n > 8) {	/* sorted ascending: the two linear scans of stage2.c:3838-3846 as binary searches */
+    if (n > 8 && lo_b <= hi_b) {	/* sorted ascending: the linear scans of stage2.c:3838-3846 / :4781-4790 as binary searches */
       int a = 0, b2 = n;
       while (a < b2) { const int mid = (a + b2) >> 1; if (m[mid] < lo_b) a = mid + 1; else b2 = mid; }
       lo = a; b2 = n;
       while (a < b2) { const int mid = (a + b2) >> 1; if (m[mid] <= hi_b) a = mid + 1; else b2 = mid; }
       hi = a;
+    } else if (FWD) {
+      int h = n - 1;
+      while (h >= 0 && m[h] > hi_b) h--;
+      hi = h + 1;
+      while (h >= 0 && m[h] >= lo_b) h--;
+      lo = h + 1;
     } else {
       int h = 0;
       while (h < n && m[h] < lo_b) h++;
@@ -334,32 +351,36 @@ __device__ void chain_fill (Prob &P, const ChainParams &prm, int *frontier, int 
       P.first[q] = -1;
       nskipped++;
       if (hi - lo < min_hits) { min_hits = hi - lo; specific_q = q; specific_lo = lo; specific_hi = hi; }
-      q++;
+      q += step;
       continue;
     }
     if (nskipped > MAX_SKIPPED) { next_q = q; q = specific_q; lo = specific_lo; hi = specific_hi; }
-    else next_q = q + 1;
+    else next_q = q + step;
     const int base = (int) P.cum[q], nhits = hi - lo;
     if (nhits > 0) {
       int best_s = 0, best_h = -1;
       if (nhits == 1) {
-	score_one(P,prm,q,lo,lane);
+	score_one<FWD>(P,prm,q,lo,lane);
 	const int s = P.hot[base + lo].y;
 	if (s > 0) { best_s = s; best_h = lo; }
       } else {
-	score_mult(P,prm,q,lo,hi,frontier,lane);
-	for (int h = lo; h < hi; h++) { const int s = P.hot[base + h].y; if (s > best_s) { best_s = s; best_h = h; } }
+	score_mult<FWD>(P,prm,q,lo,hi,frontier,lane);
+	for (int h = FWD ? hi - 1 : lo, cnt = lo; cnt < hi; h += step, cnt++) {
+	  const int s = P.hot[base + h].y;
+	  if (s > best_s) { best_s = s; best_h = h; }
+	}
       }
       nskipped = 0; min_hits = 1000000; specific_q = -1;
       if (!P.middlep && best_h < 0) new_start(P,q);
-      if (prm.splicingp && best_h >= 0 && P.cold[base + best_h].w < 0 && grand_q >= 0 && q >= grand_q + P.k) {	/* :3966-3990 */
+      if (prm.splicingp && best_h >= 0 && P.cold[base + best_h].w < 0 &&
+	  (FWD ? (grand_q <= P.L - P.k && q + P.k <= grand_q) : (grand_q >= 0 && q >= grand_q + P.k))) {	/* :3966-3990 / :4905-4930 */
 	const int4 gv = P.hot[P.cum[grand_q] + grand_h];
-	if ((best_s = H_SCORE(gv) - (q - grand_q)) > 0) {
+	if ((best_s = H_SCORE(gv) - qdist<FWD>(q,grand_q)) > 0) {
 	  const uint32_t pp = H_POS(gv);
 	  for (int h = lo; h < hi; h++) {
 	    const uint32_t position = P.pos[base + h];
-	    if (position > pp + prm.maxintronlen) {
-	    } else if (position >= pp + P.k) {
+	    if (FWD ? (position + prm.maxintronlen < pp) : (position > pp + prm.maxintronlen)) {
+	    } else if (FWD ? (position + P.k <= pp) : (position >= pp + P.k)) {
 	      const int i = base + h;
 	      int4 c = P.cold[i], v = P.hot[i];
 	      c.x = P.k; c.z = grand_q; c.w = grand_h;
@@ -373,10 +394,11 @@ __device__ void chain_fill (Prob &P, const ChainParams &prm, int *frontier, int 
 	grand_score = best_s; grand_q = q; grand_h = best_h;
       }
     }
-    revise_active(P,q,lo,hi);
+    revise_active<FWD>(P,q,lo,hi);
     if (P.npos[q] > 0) P.proc[P.nproc++] = q;
     q = next_q;
   }
+#undef INRANGE
 }
 
 /* ---- ranking (get_cells_fwd, stage2.c:3437) without the two sorts ----------------------------------------------
@@ -483,7 +505,10 @@ __device__ void rank_and_trace (const ChainDev &D, Prob &P, gmapchain_result &re
   }
 }
 
-__global__ void __launch_bounds__(CH_BLOCK) gmapchain_kernel (ChainDev D) {
+#ifndef CH_MINB
+#define CH_MINB 8
+#endif
+__global__ void __launch_bounds__(CH_BLOCK,CH_MINB) gmapchain_kernel (ChainDev D) {
   __shared__ int frontier_s[CH_WARPS][CH_FRONTIER];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int *frontier = frontier_s[warp];
@@ -506,7 +531,8 @@ __global__ void __launch_bounds__(CH_BLOCK) gmapchain_kernel (ChainDev D) {
     res.status = 0; res.npaths = 0; res.bestscore = 0; res.ncandidates = 0; res.path_off = 0;
     res.reserved[0] = res.reserved[1] = res.reserved[2] = 0;
     if (P.L > 0) {
-      chain_fill(P,D.prm,frontier,lane);
+      if (pb.flags & GMAPCHAIN_F_LOOKFORWARD) chain_fill<true>(P,D.prm,frontier,lane);
+      else chain_fill<false>(P,D.prm,frontier,lane);
       __syncwarp();
       rank_and_trace(D,P,res,lane);
     }

@@ -32,12 +32,12 @@ extern "C" void GmapChain_batch_clear (gmapchain_batch *b) {
   b->results.clear(); b->paths_used = b->pairs_used = 0; b->have_results = false; b->err.clear();
 }
 
-extern "C" int GmapChain_lookback (gmapchain_batch *b, uint32_t *const *mappings, const int *npositions, int totalpositions,
+static int queue_call (gmapchain_batch *b, int forwardp, uint32_t *const *mappings, const int *npositions, int totalpositions,
 				   const uint32_t *minactive, const uint32_t *maxactive, int querylength, int querystart, int queryend,
 				   int indexsize, int localp, int skip_repetitive_p, int use_canonical_p, int non_canonical_penalty,
 				   int favor_right_p, int middlep, int max_nalignments) {
   (void) non_canonical_penalty;
-  if (use_canonical_p) { b->err = "GmapChain_lookback: use_canonical_p is not supported by this version"; return GMAPDP_ERR_ARG; }
+  if (use_canonical_p) { b->err = "GmapChain: use_canonical_p is not supported by this version"; return GMAPDP_ERR_ARG; }
   if (querylength < 0 || totalpositions < 0 || querystart < 0 || queryend >= querylength || indexsize <= 0) {
     b->err = "GmapChain_lookback: bad sizes"; return GMAPDP_ERR_ARG;
   }
@@ -45,7 +45,7 @@ extern "C" int GmapChain_lookback (gmapchain_batch *b, uint32_t *const *mappings
   memset(&p,0,sizeof(p));
   p.querylength = querylength; p.querystart = querystart; p.queryend = queryend; p.indexsize = indexsize;
   p.flags = (localp ? GMAPCHAIN_F_LOCALP : 0) | (skip_repetitive_p ? GMAPCHAIN_F_SKIP_REPETITIVE : 0) |
-    (favor_right_p ? GMAPCHAIN_F_FAVOR_RIGHT : 0) | (middlep ? GMAPCHAIN_F_MIDDLEP : 0);
+    (favor_right_p ? GMAPCHAIN_F_FAVOR_RIGHT : 0) | (middlep ? GMAPCHAIN_F_MIDDLEP : 0) | (forwardp ? GMAPCHAIN_F_LOOKFORWARD : 0);
   p.max_nalignments = max_nalignments;
   p.q_off = b->npos.size(); p.p_off = b->pos.size();
   uint32_t run = 0;
@@ -65,6 +65,21 @@ extern "C" int GmapChain_lookback (gmapchain_batch *b, uint32_t *const *mappings
   b->problems.push_back(p);
   b->have_results = false;
   return (int) b->problems.size() - 1;
+}
+
+extern "C" int GmapChain_lookback (gmapchain_batch *b, uint32_t *const *mappings, const int *npositions, int totalpositions,
+				   const uint32_t *minactive, const uint32_t *maxactive, int querylength, int querystart, int queryend,
+				   int indexsize, int localp, int skip_repetitive_p, int use_canonical_p, int non_canonical_penalty,
+				   int favor_right_p, int middlep, int max_nalignments) {
+  return queue_call(b,0,mappings,npositions,totalpositions,minactive,maxactive,querylength,querystart,queryend,indexsize,localp,
+		    skip_repetitive_p,use_canonical_p,non_canonical_penalty,favor_right_p,middlep,max_nalignments);
+}
+extern "C" int GmapChain_lookforward (gmapchain_batch *b, uint32_t *const *mappings, const int *npositions, int totalpositions,
+				      const uint32_t *minactive, const uint32_t *maxactive, int querylength, int querystart, int queryend,
+				      int indexsize, int localp, int skip_repetitive_p, int use_canonical_p, int non_canonical_penalty,
+				      int favor_right_p, int middlep, int max_nalignments) {
+  return queue_call(b,1,mappings,npositions,totalpositions,minactive,maxactive,querylength,querystart,queryend,indexsize,localp,
+		    skip_repetitive_p,use_canonical_p,non_canonical_penalty,favor_right_p,middlep,max_nalignments);
 }
 
 static int fail (gmapchain_batch *b, int rc) { b->err = gmapdp_last_error(b->ctx); return rc; }

@@ -258,7 +258,7 @@ class ChainBatch:
             raise EngineError(self.lib.GmapChain_batch_error(self.h).decode() or "gmapchain error %d" % rc)
         return rc
 
-    def add(self, pb, use_canonical_p=0):
+    def add(self, pb, use_canonical_p=0, forward=False):
         np = self.np
         L = int(pb["querylength"])
         pos = np.ascontiguousarray(pb["positions"], dtype=np.uint32)
@@ -270,7 +270,7 @@ class ChainBatch:
         base = pos.ctypes.data
         cum = np.concatenate([[0], np.cumsum(np.maximum(npos, 0))[:-1]]).astype(np.int64) if L else np.zeros(0, dtype=np.int64)
         ptrs = (C.c_void_p * max(L, 1))(*[base + 4 * int(c) for c in cum])
-        rc = self.lib.GmapChain_lookback(
+        rc = (self.lib.GmapChain_lookforward if forward else self.lib.GmapChain_lookback)(
             self.h, ptrs, npos.ctypes.data_as(C.c_void_p), C.c_int(int(np.maximum(npos, 0).sum())),
             mina.ctypes.data_as(C.c_void_p), maxa.ctypes.data_as(C.c_void_p), C.c_int(L), C.c_int(int(pb["querystart"])),
             C.c_int(int(pb["queryend"])), C.c_int(int(pb["indexsize"])), C.c_int(int(pb["localp"])),

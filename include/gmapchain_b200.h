@@ -11,7 +11,10 @@
  *   traceback_one                  stage2.c:4140   (path of (querypos, position), 3' end pruned)
  *
  * One *problem* = one call of align_compute_lookback.  Results are identical to the reference's: the same
- * paths in the same order.  Scope of this version: the non-PMAP build, lookback direction, use_canonical_p == false
+ * paths in the same order.  Both directions are served: the lookforward twins (align_compute_lookforward stage2.c:5062,
+ * align_compute_scores_lookforward :4610, score_querypos_lookforward_one :2020, _mult :2404, revise_active_lookforward
+ * :3034; call site :7020 Stage2_compute_starts) are the same engine with the GMAPCHAIN_F_LOOKFORWARD flag.
+ * Scope of this version: the non-PMAP build, use_canonical_p == false
  * (gmap's default; the cross-species canonical test needs the genome on the device).
  * There is no CPU fallback: every compute entry point fails with GMAPDP_ERR_CUDA without an sm_100 device.
  *
@@ -30,6 +33,7 @@ extern "C" {
 #define GMAPCHAIN_F_SKIP_REPETITIVE 0x2
 #define GMAPCHAIN_F_FAVOR_RIGHT     0x4
 #define GMAPCHAIN_F_MIDDLEP         0x8
+#define GMAPCHAIN_F_LOOKFORWARD     0x10	/* align_compute_lookforward (stage2.c:5062): queryposes descending */
 
 /* One chaining problem (48 bytes).  Per-querypos arrays live in four parallel pools indexed from q_off
  * (npositions, cumulative hit offset, minactive, maxactive); the hits of all queryposes, each sorted
@@ -93,12 +97,18 @@ int GmapChain_lookback (gmapchain_batch *b, uint32_t *const *mappings, const int
 			const uint32_t *minactive, const uint32_t *maxactive, int querylength, int querystart, int queryend,
 			int indexsize, int localp, int skip_repetitive_p, int use_canonical_p, int non_canonical_penalty,
 			int favor_right_p, int middlep, int max_nalignments);
+/* The same for align_compute_lookforward (stage2.c:5062; Stage2_compute_starts): the paths then come with their
+ * HIGHEST querypos first, which is the order of the List_T the reference returns in that direction. */
+int GmapChain_lookforward (gmapchain_batch *b, uint32_t *const *mappings, const int *npositions, int totalpositions,
+			   const uint32_t *minactive, const uint32_t *maxactive, int querylength, int querystart, int queryend,
+			   int indexsize, int localp, int skip_repetitive_p, int use_canonical_p, int non_canonical_penalty,
+			   int favor_right_p, int middlep, int max_nalignments);
 int GmapChain_batch_run (gmapchain_batch *b);		/* gmapchain_run_batch, growing the output pools as needed */
 int GmapChain_batch_upload (gmapchain_batch *b);
 int GmapChain_batch_run_resident (gmapchain_batch *b, float *kernel_ms);
 int GmapChain_batch_download (gmapchain_batch *b);
 int GmapChain_npaths (const gmapchain_batch *b, int id);
-/* Path k of call id in the reference's list order (lowest querypos first); cell[5] = rootposition, endposition,
+/* Path k of call id in the reference's list order (lookback: lowest querypos first); cell[5] = rootposition, endposition,
  * querypos, hit, score of the Cell_T it was traced from.  Returns the number of pairs (or -needed if cap is short). */
 int GmapChain_path (const gmapchain_batch *b, int id, int k, int *cell, int *querypos, uint32_t *position, int cap);
 int GmapChain_batch_ncalls (const gmapchain_batch *b);

@@ -1,6 +1,9 @@
 /* TEST INFRASTRUCTURE ONLY -- never linked into the product (only tests/, smoke() and bench.py's CPU leg).
  *
- * Scalar restatement of the reference's stage-2 chaining, lookback direction:
+ * Scalar restatement of the reference's stage-2 chaining.  The lookforward twins
+ * (align_compute_scores_lookforward stage2.c:4610, score_querypos_lookforward_one :2020, _mult :2404,
+ * revise_active_lookforward :3034, align_compute_lookforward :5062) are the same code with the query axis and the
+ * genomic comparisons mirrored (c->fwd below); ranking and traceback are shared.  Lookback direction:
  *   align_compute_scores_lookback   /root/reference/src/stage2.c:3667
  *   score_querypos_lookback_one     stage2.c:1073
  *   score_querypos_lookback_mult    stage2.c:1470
@@ -34,7 +37,7 @@ void orcs2_setup (int splicingp, int cross_species_p, int sufflookback, int nsuf
 
 typedef struct {
   const unsigned int *pos; const int *npos; const unsigned int *mina, *maxa;
-  int L, tot, qs, qe, k, localp, skiprep, favor_right, middlep;
+  int L, tot, qs, qe, k, localp, skiprep, favor_right, middlep, fwd;
   int *off;				/* CSR offset of each querypos */
   int *consec, *root, *ppos, *phit, *trace, *score, *next;	/* per hit */
   int *first;				/* per querypos: head of its active chain */
@@ -43,6 +46,12 @@ typedef struct {
 } chain_t;
 
 #define P(c,q,h) ((c)->pos[(c)->off[q] + (h)])
+/* "pp lies more than x before position" and friends, in the direction of the walk (unsigned, as the reference) */
+#define BEFORE_LT(c,pp,x,position) ((c)->fwd ? ((pp) > (position) + (x)) : ((pp) + (x) < (position)))
+#define BEFORE_LE(c,pp,x,position) ((c)->fwd ? ((pp) >= (position) + (x)) : ((pp) + (x) <= (position)))
+#define AT(c,pp,x,position) ((c)->fwd ? ((pp) == (position) + (x)) : ((pp) + (x) == (position)))
+#define GDIST(c,pp,position) ((c)->fwd ? (int) ((pp) - (position)) : (int) ((position) - (pp)))
+#define QDIST(c,q,pq) ((c)->fwd ? (pq) - (q) : (q) - (pq))
 
 static void revise_active (chain_t *c, int q, int lo, int hi) {	/* stage2.c:2956 */
   int *sc = c->score + c->off[q], *nx = c->next + c->off[q], *ptr, best, thr, h;
@@ -53,8 +62,10 @@ static void revise_active (chain_t *c, int q, int lo, int hi) {	/* stage2.c:2956
   if (thr < 0) thr = 0;
   c->first[q] = -1;
   ptr = &c->first[q];
-  for (h = lo; h < hi; h++) {
-    if (sc[h] > thr) { *ptr = h; ptr = &nx[h]; }
+  if (c->fwd) {
+    for (h = hi - 1; h >= lo; h--) if (sc[h] > thr) { *ptr = h; ptr = &nx[h]; }
+  } else {
+    for (h = lo; h < hi; h++) if (sc[h] > thr) { *ptr = h; ptr = &nx[h]; }
   }
   *ptr = -1;
 }
@@ -63,13 +74,13 @@ static void revise_active (chain_t *c, int q, int lo, int hi) {	/* stage2.c:2956
 typedef struct { int consec, root, score, pp, ph, trace; } best_t;
 
 static void scan_prev (chain_t *c, best_t *b, unsigned int position, int q, int pq, int ph, int range1) {
-  const int o = c->off[pq], qd = q - pq, credit = -qd / c->k;
+  const int o = c->off[pq], qd = QDIST(c,q,pq), credit = -qd / c->k;
   unsigned int pp;
   int s, diff;
   (void) range1;
   /* range 2 (stage2.c:1236-1350 / :1712-1850): intron-sized jumps */
-  while (ph != -1 && (pp = c->pos[o + ph]) + EQUAL_DISTANCE_NOT_SPLICING + qd < position) {
-    diff = (int) (position - pp) - qd;
+  while (ph != -1 && (pp = c->pos[o + ph], BEFORE_LT(c,pp,EQUAL_DISTANCE_NOT_SPLICING + qd,position))) {
+    diff = GDIST(c,pp,position) - qd;
     s = c->score[o + ph] + credit;
     s -= g_splicingp ? (diff / TEN_THOUSAND + 1) : (diff + 1);
     if (s > b->score) {
@@ -79,8 +90,8 @@ static void scan_prev (chain_t *c, best_t *b, unsigned int position, int q, int 
     ph = c->next[o + ph];
   }
   /* ranges 3+4 (:1357-1420 / :1860-1915): near the diagonal, down to one k-mer apart */
-  while (ph != -1 && (pp = c->pos[o + ph]) + c->k <= position) {
-    int gd = (int) (position - pp);
+  while (ph != -1 && (pp = c->pos[o + ph], BEFORE_LE(c,pp,c->k,position))) {
+    int gd = GDIST(c,pp,position);
     diff = gd > qd ? gd - qd : qd - gd;
     s = c->score[o + ph] + 1;
     if (s > b->score) {
@@ -106,11 +117,11 @@ static void score_one (chain_t *c, int q, int h) {	/* stage2.c:1073 */
   unsigned int pp;
 
   if (c->nproc > 0) {	/* A: the adjacent (last processed) querypos */
-    pq = c->proc[c->nproc - 1]; o = c->off[pq]; qd = q - pq;
+    pq = c->proc[c->nproc - 1]; o = c->off[pq]; qd = QDIST(c,q,pq);
     ph = c->first[pq];
     pp = position;
-    while (ph != -1 && (pp = c->pos[o + ph]) + qd < position) ph = c->next[o + ph];
-    if (pp + qd == position) {
+    while (ph != -1 && (pp = c->pos[o + ph], BEFORE_LT(c,pp,qd,position))) ph = c->next[o + ph];
+    if (AT(c,pp,qd,position)) {
       b.consec = c->consec[o + ph] + qd; b.root = c->root[o + ph]; b.score = c->score[o + ph] + qd;
       b.pp = pq; b.ph = ph; b.trace = c->trace[o + ph];
       nlookback = 1; lookback = g_sufflookback / 2;
@@ -119,13 +130,13 @@ static void score_one (chain_t *c, int q, int h) {	/* stage2.c:1073 */
   /* D: earlier queryposes */
   donep = 0; nseen = 0; last_trace = -1;
   for (i = c->nproc - 1; i >= 0 && b.consec < ENOUGH_CONSECUTIVE && !donep; i--, nseen++) {
-    pq = c->proc[i]; o = c->off[pq]; qd = q - pq;
+    pq = c->proc[i]; o = c->off[pq]; qd = QDIST(c,q,pq);
     if (nseen > nlookback && qd - c->k > lookback) donep = 1;
     if ((ph = c->first[pq]) != -1) {
       while (ph != -1 && c->trace[o + ph] == last_trace) ph = c->next[o + ph];	/* range 0 */
       if (ph != -1) last_trace = c->trace[o + ph];
       if (g_splicingp) {								/* range 1 */
-        while (ph != -1 && c->pos[o + ph] + g_maxintronlen + qd <= position) ph = c->next[o + ph];
+        while (ph != -1 && BEFORE_LE(c,c->pos[o + ph],g_maxintronlen + qd,position)) ph = c->next[o + ph];
       }
       scan_prev(c,&b,position,q,pq,ph,0);
     }
@@ -146,36 +157,38 @@ static void score_mult (chain_t *c, int q, int lo, int hi) {	/* stage2.c:1470 */
   int hiti, *frontier, nseen, i, max_adj = 0, max_nonadj = 0, overall = 0, adjq, adjo, adjqd, adjf, ph, max_nseen, last_trace;
   unsigned int position, pp;
 
+  const int h0 = c->fwd ? nhits - 1 : 0, hstep = c->fwd ? -1 : 1;	/* hits are walked away from the processed side */
+  int cnt;
   if (c->nproc == 0) {
     for (hiti = 0; hiti < nhits; hiti++) fresh_start(c,q,lo + hiti,positions[hiti]);
     return;
   }
-  adjq = c->proc[c->nproc - 1]; adjo = c->off[adjq]; adjqd = q - adjq;
+  adjq = c->proc[c->nproc - 1]; adjo = c->off[adjq]; adjqd = QDIST(c,q,adjq);
   frontier = (int *) malloc((size_t) c->nproc * sizeof(int));
   nseen = 0;
   for (i = c->nproc - 1; i >= 0; i--) {
-    int pq = c->proc[i], qd = q - pq;
+    int pq = c->proc[i], qd = QDIST(c,q,pq);
     if (nseen <= 1 || qd - c->k <= g_sufflookback / 2) max_adj = nseen;
     if (nseen <= g_nsufflookback || qd - c->k <= g_sufflookback) max_nonadj = nseen;
     frontier[nseen++] = c->first[pq];
   }
   /* can we be greedy? (:1640-1660) */
   adjf = c->first[adjq];
-  for (hiti = 0; hiti < nhits; hiti++) {
+  for (hiti = h0, cnt = 0; cnt < nhits; hiti += hstep, cnt++) {
     position = positions[hiti];
     ph = adjf; pp = position;
-    while (ph != -1 && (pp = c->pos[adjo + ph]) + adjqd < position) ph = c->next[adjo + ph];
+    while (ph != -1 && (pp = c->pos[adjo + ph], BEFORE_LT(c,pp,adjqd,position))) ph = c->next[adjo + ph];
     adjf = ph;
-    if (pp + adjqd == position && c->consec[adjo + ph] + adjqd > overall) overall = c->consec[adjo + ph] + adjqd;
+    if (AT(c,pp,adjqd,position) && c->consec[adjo + ph] + adjqd > overall) overall = c->consec[adjo + ph] + adjqd;
   }
   adjf = c->first[adjq];
-  for (hiti = 0; hiti < nhits; hiti++) {
+  for (hiti = h0, cnt = 0; cnt < nhits; hiti += hstep, cnt++) {
     best_t b;
     position = positions[hiti];
     ph = adjf; pp = position;
-    while (ph != -1 && (pp = c->pos[adjo + ph]) + adjqd < position) ph = c->next[adjo + ph];
+    while (ph != -1 && (pp = c->pos[adjo + ph], BEFORE_LT(c,pp,adjqd,position))) ph = c->next[adjo + ph];
     adjf = ph;
-    if (pp + adjqd == position) {
+    if (AT(c,pp,adjqd,position)) {
       b.consec = c->consec[adjo + ph] + adjqd; b.root = c->root[adjo + ph]; b.pp = adjq; b.ph = ph;
       b.score = c->score[adjo + ph] + adjqd; b.trace = c->trace[adjo + ph];
       max_nseen = max_adj;
@@ -187,10 +200,10 @@ static void score_mult (chain_t *c, int q, int lo, int hi) {	/* stage2.c:1470 */
       nseen = 0; last_trace = -1;
       for (i = c->nproc - 1; i >= 0 && b.consec < ENOUGH_CONSECUTIVE && nseen <= max_nseen; i--, nseen++) {
 	if ((ph = frontier[nseen]) != -1) {
-	  int pq = c->proc[i], o = c->off[pq], qd = q - pq;
+	  int pq = c->proc[i], o = c->off[pq], qd = QDIST(c,q,pq);
 	  while (ph != -1 && c->trace[o + ph] == last_trace) ph = c->next[o + ph];		/* range 0 */
 	  if (ph != -1) last_trace = c->trace[o + ph];
-	  while (ph != -1 && c->pos[o + ph] + g_maxintronlen + qd <= position) ph = c->next[o + ph];	/* range 1, unconditional here */
+	  while (ph != -1 && BEFORE_LE(c,c->pos[o + ph],g_maxintronlen + qd,position)) ph = c->next[o + ph];	/* range 1, unconditional here */
 	  frontier[nseen] = ph;
 	  scan_prev(c,&b,position,q,pq,ph,1);
 	}
@@ -209,35 +222,46 @@ static void new_start (chain_t *c, int q) {	/* stage2.c:3793-3812 and :3941-3964
   }
 }
 
-static void chain_fill (chain_t *c) {	/* stage2.c:3667 */
+static void chain_fill (chain_t *c) {	/* stage2.c:3667 (lookback) / :4610 (lookforward) */
+  const int step = c->fwd ? -1 : 1;
   int q, h, lo, hi, nhits, nskipped = 0, min_hits = 1000000, specific_q = -1, specific_lo = 0, specific_hi = 0, next_q;
   int grand_score = 0, grand_q = -1, grand_h = -1, best_h, best_s;
+#define INRANGE(q) (c->fwd ? (q) >= c->qs : (q) <= c->qe)
 
-  for (q = 0; q < c->qs && q < c->L; q++) c->first[q] = -1;
-  while (q <= c->qe && c->npos[q] <= 0) { c->first[q] = -1; q++; }
-  if (q <= c->qe) {
+  if (c->fwd) { for (q = c->L - 1; q > c->qe; q--) c->first[q] = -1; }
+  else { for (q = 0; q < c->qs && q < c->L; q++) c->first[q] = -1; }
+  while (INRANGE(q) && c->npos[q] <= 0) { c->first[q] = -1; q += step; }
+  if (INRANGE(q)) {
     new_start(c,q);
     revise_active(c,q,0,c->npos[q]);
   }
-  while (q <= c->qe) {
+  while (INRANGE(q)) {
     const unsigned int *m = c->pos + c->off[q];
     best_s = 0; best_h = -1;
-    h = 0;
-    while (h < c->npos[q] && m[h] < c->mina[q]) h++;
-    lo = h;
-    while (h < c->npos[q] && m[h] <= c->maxa[q]) h++;
-    hi = h;
+    if (c->fwd) {			/* :4781-4790 */
+      h = c->npos[q] - 1;
+      while (h >= 0 && m[h] > c->maxa[q]) h--;
+      hi = h + 1;
+      while (h >= 0 && m[h] >= c->mina[q]) h--;
+      lo = h + 1;
+    } else {				/* :3838-3846 */
+      h = 0;
+      while (h < c->npos[q] && m[h] < c->mina[q]) h++;
+      lo = h;
+      while (h < c->npos[q] && m[h] <= c->maxa[q]) h++;
+      hi = h;
+    }
     if (c->skiprep && hi - lo >= MAX_NACTIVE && nskipped <= MAX_SKIPPED) {
       c->first[q] = -1;
       nskipped++;
       if (hi - lo < min_hits) { min_hits = hi - lo; specific_q = q; specific_lo = lo; specific_hi = hi; }
-      q++;
+      q += step;
       continue;
     }
     if (nskipped > MAX_SKIPPED) {
       next_q = q; q = specific_q; lo = specific_lo; hi = specific_hi;
     } else {
-      next_q = q + 1;
+      next_q = q + step;
     }
     if ((nhits = hi - lo) > 0) {
       if (nhits == 1) {
@@ -245,16 +269,19 @@ static void chain_fill (chain_t *c) {	/* stage2.c:3667 */
 	if (c->score[c->off[q] + lo] > 0) { best_s = c->score[c->off[q] + lo]; best_h = lo; }
       } else {
 	score_mult(c,q,lo,hi);
-	for (h = lo; h < hi; h++) if (c->score[c->off[q] + h] > best_s) { best_s = c->score[c->off[q] + h]; best_h = h; }
+	if (c->fwd) { for (h = hi - 1; h >= lo; h--) if (c->score[c->off[q] + h] > best_s) { best_s = c->score[c->off[q] + h]; best_h = h; } }
+	else { for (h = lo; h < hi; h++) if (c->score[c->off[q] + h] > best_s) { best_s = c->score[c->off[q] + h]; best_h = h; } }
       }
       nskipped = 0; min_hits = 1000000; specific_q = -1;
       if (!c->middlep && best_h < 0) new_start(c,q);
-      if (g_splicingp && best_h >= 0 && c->phit[c->off[q] + best_h] < 0 && grand_q >= 0 && q >= grand_q + c->k) {	/* :3966-3990 */
-	if ((best_s = c->score[c->off[grand_q] + grand_h] - (q - grand_q)) > 0) {
+      if (g_splicingp && best_h >= 0 && c->phit[c->off[q] + best_h] < 0 &&
+	  (c->fwd ? (grand_q <= c->L - c->k && q + c->k <= grand_q) : (grand_q >= 0 && q >= grand_q + c->k))) {	/* :3966-3990 / :4905-4930 */
+	if ((best_s = c->score[c->off[grand_q] + grand_h] - QDIST(c,q,grand_q)) > 0) {
 	  unsigned int pp = P(c,grand_q,grand_h), position;
 	  for (h = lo; h < hi; h++) {
-	    if ((position = c->pos[c->off[q] + h]) > pp + g_maxintronlen) {
-	    } else if (position >= pp + c->k) {
+	    position = c->pos[c->off[q] + h];
+	    if (c->fwd ? (position + g_maxintronlen < pp) : (position > pp + g_maxintronlen)) {
+	    } else if (c->fwd ? (position + c->k <= pp) : (position >= pp + c->k)) {
 	      int i = c->off[q] + h;
 	      c->consec[i] = c->k; c->ppos[i] = grand_q; c->phit[i] = grand_h; c->trace[i] = ++c->tracei; c->score[i] = best_s;
 	    }
@@ -269,6 +296,7 @@ static void chain_fill (chain_t *c) {	/* stage2.c:3667 */
     if (c->npos[q] > 0) c->proc[c->nproc++] = q;
     q = next_q;
   }
+#undef INRANGE
 }
 
 /* ---- ranking (get_cells_fwd) ------------------------------------------------------------------------ */
@@ -312,13 +340,13 @@ static cell_t *rank_cells (chain_t *c, int *nunique) {
 
 static void chain_init (chain_t *c, const unsigned int *positions, const int *npositions, int querylength, int totalpositions,
 			const unsigned int *minactive, const unsigned int *maxactive, int querystart, int queryend, int indexsize,
-			int localp, int skip_repetitive_p, int favor_right_p, int middlep) {
+			int localp, int skip_repetitive_p, int favor_right_p, int middlep, int fwd) {
   int q, o = 0;
   size_t n = (size_t) totalpositions + 1;
   memset(c,0,sizeof(*c));
   c->pos = positions; c->npos = npositions; c->mina = minactive; c->maxa = maxactive;
   c->L = querylength; c->tot = totalpositions; c->qs = querystart; c->qe = queryend; c->k = indexsize;
-  c->localp = localp; c->skiprep = skip_repetitive_p; c->favor_right = favor_right_p; c->middlep = middlep;
+  c->localp = localp; c->skiprep = skip_repetitive_p; c->favor_right = favor_right_p; c->middlep = middlep; c->fwd = fwd;
   c->off = (int *) malloc((size_t) (querylength + 1) * sizeof(int));
   for (q = 0; q < querylength; q++) { c->off[q] = o; if (npositions[q] > 0) o += npositions[q]; }
   c->off[querylength] = o;
@@ -333,7 +361,7 @@ static void chain_free (chain_t *c) {
   free(c->first); free(c->proc);
 }
 
-int orcs2_scores (const unsigned int *positions, const int *npositions, int querylength, int totalpositions,
+static int scores_dir (int fwd, const unsigned int *positions, const int *npositions, int querylength, int totalpositions,
 		  const unsigned int *minactive, const unsigned int *maxactive, int querystart, int queryend, int indexsize,
 		  int localp, int skip_repetitive_p, int favor_right_p, int middlep,
 		  int *links_out, int *scores_out, int *cells_out, int cells_cap) {
@@ -341,7 +369,7 @@ int orcs2_scores (const unsigned int *positions, const int *npositions, int quer
   cell_t *cells;
   int n, i;
   chain_init(&c,positions,npositions,querylength,totalpositions,minactive,maxactive,querystart,queryend,indexsize,
-	     localp,skip_repetitive_p,favor_right_p,middlep);
+	     localp,skip_repetitive_p,favor_right_p,middlep,fwd);
   chain_fill(&c);
   cells = rank_cells(&c,&n);
   for (i = 0; i < totalpositions; i++) {
@@ -360,7 +388,7 @@ int orcs2_scores (const unsigned int *positions, const int *npositions, int quer
   return n;
 }
 
-int orcs2_paths (const unsigned int *positions, const int *npositions, int querylength, int totalpositions,
+static int paths_dir (int fwd, const unsigned int *positions, const int *npositions, int querylength, int totalpositions,
 		 const unsigned int *minactive, const unsigned int *maxactive, int querystart, int queryend, int indexsize,
 		 int localp, int skip_repetitive_p, int favor_right_p, int middlep, int max_nalignments,
 		 const char *queryseq, const char *queryuc, int *path_len, int maxpaths, int *pairs_out, int pairs_cap) {
@@ -369,7 +397,7 @@ int orcs2_paths (const unsigned int *positions, const int *npositions, int query
   int n, i, npaths = 0, npairs = 0, best;
   (void) queryseq; (void) queryuc;
   chain_init(&c,positions,npositions,querylength,totalpositions,minactive,maxactive,querystart,queryend,indexsize,
-	     localp,skip_repetitive_p,favor_right_p,middlep);
+	     localp,skip_repetitive_p,favor_right_p,middlep,fwd);
   chain_fill(&c);
   cells = rank_cells(&c,&n);
   if (n > 0) {
@@ -385,7 +413,7 @@ int orcs2_paths (const unsigned int *positions, const int *npositions, int query
 	npairs++; k++;
 	q = c.ppos[j]; h = c.phit[j];
       }
-      if (npairs <= pairs_cap) {		/* list head = lowest querypos: reverse what the walk produced */
+      if (npairs <= pairs_cap) {		/* list head = the far end of the walk (the last pair pushed): reverse what the walk produced */
 	for (j = start, t = npairs - 1; j < t; j++, t--) {
 	  int a = pairs_out[2*j], b = pairs_out[2*j+1];
 	  pairs_out[2*j] = pairs_out[2*t]; pairs_out[2*j+1] = pairs_out[2*t+1];
@@ -400,3 +428,20 @@ int orcs2_paths (const unsigned int *positions, const int *npositions, int query
   chain_free(&c);
   return (npairs > pairs_cap) ? -npairs : npaths;
 }
+
+#define SCORES_ARGS const unsigned int *positions, const int *npositions, int querylength, int totalpositions, \
+    const unsigned int *minactive, const unsigned int *maxactive, int querystart, int queryend, int indexsize, \
+    int localp, int skip_repetitive_p, int favor_right_p, int middlep, int *links_out, int *scores_out, int *cells_out, int cells_cap
+#define SCORES_PASS positions,npositions,querylength,totalpositions,minactive,maxactive,querystart,queryend,indexsize, \
+    localp,skip_repetitive_p,favor_right_p,middlep,links_out,scores_out,cells_out,cells_cap
+#define PATHS_ARGS const unsigned int *positions, const int *npositions, int querylength, int totalpositions, \
+    const unsigned int *minactive, const unsigned int *maxactive, int querystart, int queryend, int indexsize, \
+    int localp, int skip_repetitive_p, int favor_right_p, int middlep, int max_nalignments, \
+    const char *queryseq, const char *queryuc, int *path_len, int maxpaths, int *pairs_out, int pairs_cap
+#define PATHS_PASS positions,npositions,querylength,totalpositions,minactive,maxactive,querystart,queryend,indexsize, \
+    localp,skip_repetitive_p,favor_right_p,middlep,max_nalignments,queryseq,queryuc,path_len,maxpaths,pairs_out,pairs_cap
+
+int orcs2_scores (SCORES_ARGS) { return scores_dir(0,SCORES_PASS); }
+int orcs2_scores_fwd (SCORES_ARGS) { return scores_dir(1,SCORES_PASS); }
+int orcs2_paths (PATHS_ARGS) { return paths_dir(0,PATHS_PASS); }
+int orcs2_paths_fwd (PATHS_ARGS) { return paths_dir(1,PATHS_PASS); }

@@ -5,8 +5,8 @@
  * (the #include below resolves through -I/root/reference/src; nothing is copied) and adds plain-C entry
  * points after it:
  *
- *   refs2_scores : align_compute_scores_lookback (stage2.c:3667) -> links, fwd_scores, ranked cells
- *   refs2_paths  : align_compute_lookback        (stage2.c:4402) -> the traced paths (querypos, position)
+ *   refs2_scores[_fwd] : align_compute_scores_lookback / _lookforward (stage2.c:3667 / :4610) -> links, fwd_scores, ranked cells
+ *   refs2_paths[_fwd]  : align_compute_lookback / _lookforward        (stage2.c:4402 / :5062) -> the traced paths (querypos, position)
  */
 #include "stage2.c"
 
@@ -35,7 +35,7 @@ static Chrpos_T **make_mappings (const unsigned int *positions, const int *nposi
 
 /* links_out: 5 ints per position (fwd_consecutive, fwd_rootposition, fwd_pos, fwd_hit, fwd_tracei), CSR order;
    cells_out: 5 ints per ranked cell (rootposition, endposition, querypos, hit, score).  Returns ncells. */
-int refs2_scores (const unsigned int *positions, const int *npositions, int querylength, int totalpositions,
+static int scores_dir (int forwardp, const unsigned int *positions, const int *npositions, int querylength, int totalpositions,
 		  const unsigned int *minactive, const unsigned int *maxactive, int querystart, int queryend, int indexsize,
 		  int localp, int skip_repetitive_p, int favor_right_p, int middlep,
 		  int *links_out, int *scores_out, int *cells_out, int cells_cap) {
@@ -47,13 +47,23 @@ int refs2_scores (const unsigned int *positions, const int *npositions, int quer
   Cell_T *cells;
 
   Cellpool_reset(s2_cellpool);
-  cells = align_compute_scores_lookback(&ncells,links,fwd_scores,mappings,(int *) npositions,totalpositions,
-					/*oned_matrix_p*/true,(Chrpos_T *) minactive,(Chrpos_T *) maxactive,firstactive,nactive,s2_cellpool,
-					querystart,queryend,querylength,/*genome*/NULL,/*genomealt*/NULL,
-					/*chroffset*/0,/*chrhigh*/0,/*plusp*/true,indexsize,
-					localp ? true : false,skip_repetitive_p ? true : false,
-					/*use_canonical_p*/false,/*non_canonical_penalty*/NON_CANONICAL_PENALTY_MIDDLE,
-					favor_right_p ? true : false,middlep ? true : false);
+  if (forwardp) {
+    cells = align_compute_scores_lookforward(&ncells,links,fwd_scores,mappings,(int *) npositions,totalpositions,
+					     /*oned_matrix_p*/true,(Chrpos_T *) minactive,(Chrpos_T *) maxactive,firstactive,nactive,s2_cellpool,
+					     querystart,queryend,querylength,/*genome*/NULL,/*genomealt*/NULL,
+					     /*chroffset*/0,/*chrhigh*/0,/*plusp*/true,indexsize,
+					     localp ? true : false,skip_repetitive_p ? true : false,
+					     /*use_canonical_p*/false,/*non_canonical_penalty*/NON_CANONICAL_PENALTY_MIDDLE,
+					     favor_right_p ? true : false,middlep ? true : false);
+  } else {
+    cells = align_compute_scores_lookback(&ncells,links,fwd_scores,mappings,(int *) npositions,totalpositions,
+					  /*oned_matrix_p*/true,(Chrpos_T *) minactive,(Chrpos_T *) maxactive,firstactive,nactive,s2_cellpool,
+					  querystart,queryend,querylength,/*genome*/NULL,/*genomealt*/NULL,
+					  /*chroffset*/0,/*chrhigh*/0,/*plusp*/true,indexsize,
+					  localp ? true : false,skip_repetitive_p ? true : false,
+					  /*use_canonical_p*/false,/*non_canonical_penalty*/NON_CANONICAL_PENALTY_MIDDLE,
+					  favor_right_p ? true : false,middlep ? true : false);
+  }
   for (i = 0; i < totalpositions; i++) {
     if (links_out) {
       links_out[5*i+0] = links[0][i].fwd_consecutive; links_out[5*i+1] = links[0][i].fwd_rootposition;
@@ -74,7 +84,7 @@ int refs2_scores (const unsigned int *positions, const int *npositions, int quer
 
 /* path_len[k] = pairs of path k (k in cell-rank order); pairs_out = (querypos, genomepos) per pair, paths
    concatenated, each from its lowest querypos upwards.  Returns npaths (or -needed pairs if pairs_cap is short). */
-int refs2_paths (const unsigned int *positions, const int *npositions, int querylength, int totalpositions,
+static int paths_dir (int forwardp, const unsigned int *positions, const int *npositions, int querylength, int totalpositions,
 		 const unsigned int *minactive, const unsigned int *maxactive, int querystart, int queryend, int indexsize,
 		 int localp, int skip_repetitive_p, int favor_right_p, int middlep, int max_nalignments,
 		 const char *queryseq, const char *queryuc, int *path_len, int maxpaths, int *pairs_out, int pairs_cap) {
@@ -86,13 +96,23 @@ int refs2_paths (const unsigned int *positions, const int *npositions, int query
 
   Pairpool_reset(s2_pairpool);
   Cellpool_reset(s2_cellpool);
-  all_paths = align_compute_lookback(mappings,(int *) npositions,totalpositions,/*oned_matrix_p*/true,
-				     (Chrpos_T *) minactive,(Chrpos_T *) maxactive,firstactive,nactive,s2_cellpool,
-				     (char *) queryseq,(char *) queryuc,querylength,querystart,queryend,
-				     /*genome*/NULL,/*genomealt*/NULL,/*chroffset*/0,/*chrhigh*/0,/*plusp*/true,indexsize,s2_pairpool,
-				     localp ? true : false,skip_repetitive_p ? true : false,
-				     /*use_canonical_p*/false,NON_CANONICAL_PENALTY_MIDDLE,
-				     favor_right_p ? true : false,middlep ? true : false,max_nalignments);
+  if (forwardp) {
+    all_paths = align_compute_lookforward(mappings,(int *) npositions,totalpositions,/*oned_matrix_p*/true,
+					  (Chrpos_T *) minactive,(Chrpos_T *) maxactive,firstactive,nactive,s2_cellpool,
+					  (char *) queryseq,(char *) queryuc,querylength,querystart,queryend,
+					  /*genome*/NULL,/*genomealt*/NULL,/*chroffset*/0,/*chrhigh*/0,/*plusp*/true,indexsize,s2_pairpool,
+					  localp ? true : false,skip_repetitive_p ? true : false,
+					  /*use_canonical_p*/false,NON_CANONICAL_PENALTY_MIDDLE,
+					  favor_right_p ? true : false,middlep ? true : false,max_nalignments);
+  } else {
+    all_paths = align_compute_lookback(mappings,(int *) npositions,totalpositions,/*oned_matrix_p*/true,
+				       (Chrpos_T *) minactive,(Chrpos_T *) maxactive,firstactive,nactive,s2_cellpool,
+				       (char *) queryseq,(char *) queryuc,querylength,querystart,queryend,
+				       /*genome*/NULL,/*genomealt*/NULL,/*chroffset*/0,/*chrhigh*/0,/*plusp*/true,indexsize,s2_pairpool,
+				       localp ? true : false,skip_repetitive_p ? true : false,
+				       /*use_canonical_p*/false,NON_CANONICAL_PENALTY_MIDDLE,
+				       favor_right_p ? true : false,middlep ? true : false,max_nalignments);
+  }
   all_paths = List_reverse(all_paths);		/* pushed in rank order, so the list came out last first */
   for (p = all_paths; p != NULL; p = List_next(p)) {
     k = 0;
@@ -108,3 +128,20 @@ int refs2_paths (const unsigned int *positions, const int *npositions, int query
   free(nactive); free(firstactive); free(mappings);
   return (npairs > pairs_cap) ? -npairs : npaths;
 }
+
+#define SCORES_ARGS const unsigned int *positions, const int *npositions, int querylength, int totalpositions, \
+    const unsigned int *minactive, const unsigned int *maxactive, int querystart, int queryend, int indexsize, \
+    int localp, int skip_repetitive_p, int favor_right_p, int middlep, int *links_out, int *scores_out, int *cells_out, int cells_cap
+#define SCORES_PASS positions,npositions,querylength,totalpositions,minactive,maxactive,querystart,queryend,indexsize, \
+    localp,skip_repetitive_p,favor_right_p,middlep,links_out,scores_out,cells_out,cells_cap
+#define PATHS_ARGS const unsigned int *positions, const int *npositions, int querylength, int totalpositions, \
+    const unsigned int *minactive, const unsigned int *maxactive, int querystart, int queryend, int indexsize, \
+    int localp, int skip_repetitive_p, int favor_right_p, int middlep, int max_nalignments, \
+    const char *queryseq, const char *queryuc, int *path_len, int maxpaths, int *pairs_out, int pairs_cap
+#define PATHS_PASS positions,npositions,querylength,totalpositions,minactive,maxactive,querystart,queryend,indexsize, \
+    localp,skip_repetitive_p,favor_right_p,middlep,max_nalignments,queryseq,queryuc,path_len,maxpaths,pairs_out,pairs_cap
+
+int refs2_scores (SCORES_ARGS) { return scores_dir(0,SCORES_PASS); }		/* align_compute_scores_lookback */
+int refs2_scores_fwd (SCORES_ARGS) { return scores_dir(1,SCORES_PASS); }	/* align_compute_scores_lookforward, stage2.c:4610 */
+int refs2_paths (PATHS_ARGS) { return paths_dir(0,PATHS_PASS); }		/* align_compute_lookback */
+int refs2_paths_fwd (PATHS_ARGS) { return paths_dir(1,PATHS_PASS); }		/* align_compute_lookforward, stage2.c:5062 */

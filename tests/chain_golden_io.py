@@ -7,7 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SCALARS = ("querylength", "querystart", "queryend", "indexsize", "localp", "skip_repetitive_p", "favor_right_p", "middlep", "max_nalignments")
 
 
-def load():
+def load(fwd=False):
+    """[(problem, links, scores, cells, paths)] of the lookback (default) or lookforward run of the reference"""
+    f = "f_" if fwd else ""
     z = np.load(os.path.join(HERE, "golden", "chain_golden.npz"))
     out = []
     for i in range(int(z["n"])):
@@ -15,11 +17,11 @@ def load():
         for k, v in zip(SCALARS, z["p%d_scalars" % i].tolist()):
             pb[k] = int(v)
         pb["queryseq"] = z["p%d_queryseq" % i].tobytes()
-        plen = z["p%d_pathlen" % i]
-        pairs = z["p%d_pairs" % i]
+        plen = z["p%d_%spathlen" % (i, f)]
+        pairs = z["p%d_%spairs" % (i, f)]
         paths, o = [], 0
         for n in plen.tolist():
             paths.append(pairs[o:o + n])
             o += n
-        out.append((pb, z["p%d_links" % i], z["p%d_scores" % i], z["p%d_cells" % i], paths))
+        out.append((pb, z["p%d_%slinks" % (i, f)], z["p%d_%sscores" % (i, f)], z["p%d_%scells" % (i, f)], paths))
     return out

@@ -35,23 +35,28 @@ class _Chain:
         f = getattr(self.lib, self.prefix + "_setup")
         f.argtypes = [C.c_int] * 5
         f(SETUP["splicingp"], SETUP["cross_species_p"], SETUP["sufflookback"], SETUP["nsufflookback"], SETUP["maxintronlen"])
-        s = getattr(self.lib, self.prefix + "_scores")
+        self._s, self._p = {}, {}
+        for fwd, suffix in ((False, ""), (True, "_fwd")):
+            self._bind(fwd, suffix)
+
+    def _bind(self, fwd, suffix):
+        s = getattr(self.lib, self.prefix + "_scores" + suffix)
         s.argtypes = [u32p, i32p, C.c_int, C.c_int, u32p, u32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                       i32p, i32p, i32p, C.c_int]
         s.restype = C.c_int
-        p = getattr(self.lib, self.prefix + "_paths")
+        p = getattr(self.lib, self.prefix + "_paths" + suffix)
         p.argtypes = [u32p, i32p, C.c_int, C.c_int, u32p, u32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                       C.c_char_p, C.c_char_p, i32p, C.c_int, i32p, C.c_int]
         p.restype = C.c_int
-        self._s, self._p = s, p
+        self._s[fwd], self._p[fwd] = s, p
 
-    def scores(self, pb):
+    def scores(self, pb, fwd=False):
         tot = len(pb["positions"])
         pos = pb["positions"] if tot else np.zeros(1, dtype=np.uint32)
         links = np.zeros(5 * max(tot, 1), dtype=np.int32)
         sc = np.zeros(max(tot, 1), dtype=np.int32)
         cells = np.zeros(5 * max(tot, 1), dtype=np.int32)
-        n = self._s(pos, pb["npositions"], pb["querylength"], tot, pb["minactive"], pb["maxactive"], pb["querystart"],
+        n = self._s[fwd](pos, pb["npositions"], pb["querylength"], tot, pb["minactive"], pb["maxactive"], pb["querystart"],
                     pb["queryend"], pb["indexsize"], pb["localp"], pb["skip_repetitive_p"], pb["favor_right_p"], pb["middlep"],
                     links, sc, cells, max(tot, 1))
         links = links[:5 * tot].reshape(-1, 5).copy()
@@ -59,14 +64,14 @@ class _Chain:
             links[:, 4] = canon_labels(links[:, 4])
         return links, sc[:tot].copy(), cells[:5 * n].reshape(-1, 5).copy()
 
-    def paths(self, pb):
+    def paths(self, pb, fwd=False):
         tot = len(pb["positions"])
         pos = pb["positions"] if tot else np.zeros(1, dtype=np.uint32)
         cap = 4 * pb["querylength"] + 16
         plen = np.zeros(tot + 1, dtype=np.int32)
         while True:
             pairs = np.zeros(2 * cap, dtype=np.int32)
-            n = self._p(pos, pb["npositions"], pb["querylength"], tot, pb["minactive"], pb["maxactive"], pb["querystart"],
+            n = self._p[fwd](pos, pb["npositions"], pb["querylength"], tot, pb["minactive"], pb["maxactive"], pb["querystart"],
                         pb["queryend"], pb["indexsize"], pb["localp"], pb["skip_repetitive_p"], pb["favor_right_p"], pb["middlep"],
                         pb["max_nalignments"], pb["queryseq"], pb["queryseq"], plen, tot + 1, pairs, cap)
             if n >= 0:

@@ -22,6 +22,8 @@ def main():
     for i, pb in enumerate(problems):
         links, scores, cells = ref.scores(pb)
         paths = ref.paths(pb)
+        flinks, fscores, fcells = ref.scores(pb, fwd=True)        # align_compute_scores_lookforward
+        fpaths = ref.paths(pb, fwd=True)
         for k in KEYS_IN:
             out["p%d_%s" % (i, k)] = pb[k]
         out["p%d_scalars" % i] = np.array([pb[k] for k in SCALARS], dtype=np.int64)
@@ -31,6 +33,11 @@ def main():
         out["p%d_cells" % i] = cells
         out["p%d_pathlen" % i] = np.array([len(p) for p in paths], dtype=np.int32)
         out["p%d_pairs" % i] = np.concatenate(paths) if paths else np.zeros((0, 2), dtype=np.int32)
+        out["p%d_f_links" % i] = flinks
+        out["p%d_f_scores" % i] = fscores
+        out["p%d_f_cells" % i] = fcells
+        out["p%d_f_pathlen" % i] = np.array([len(p) for p in fpaths], dtype=np.int32)
+        out["p%d_f_pairs" % i] = np.concatenate(fpaths) if fpaths else np.zeros((0, 2), dtype=np.int32)
     path = os.path.join(HERE, "chain_golden.npz")
     np.savez_compressed(path, **out)
     print(len(problems), "problems ->", path, os.path.getsize(path), "bytes")

@@ -16,14 +16,15 @@ def same(a, b):
     return np.array_equal(la, lb) and np.array_equal(sa, sb) and np.array_equal(ca, cb)
 
 
-def test_chain_oracle_matches_reference_golden():
+@pytest.mark.parametrize("fwd", [False, True])
+def test_chain_oracle_matches_reference_golden(fwd):
     orc = ch.OracleChain()
-    gold = chain_golden_io.load()
+    gold = chain_golden_io.load(fwd)
     assert len(gold) >= 50
     npaths = 0
     for pb, links, scores, cells, paths in gold:
-        assert same(orc.scores(pb), (links, scores, cells))
-        got = orc.paths(pb)
+        assert same(orc.scores(pb, fwd), (links, scores, cells))
+        got = orc.paths(pb, fwd)
         assert len(got) == len(paths)
         for x, y in zip(got, paths):
             assert np.array_equal(x, y)
@@ -32,12 +33,13 @@ def test_chain_oracle_matches_reference_golden():
 
 
 @pytest.mark.skipif(not ch.have_ref(), reason="oracle/_ref/ref_stage2.so not built (needs /root/reference)")
-def test_chain_oracle_matches_compiled_reference():
+@pytest.mark.parametrize("fwd", [False, True])
+def test_chain_oracle_matches_compiled_reference(fwd):
     ref, orc = ch.RefChain(), ch.OracleChain()
     for seed, n, small in ((5, 40, True), (6, 12, False)):
         for pb in chaingen.make_set(seed, n, small=small):
-            assert same(ref.scores(pb), orc.scores(pb))
-            a, b = ref.paths(pb), orc.paths(pb)
+            assert same(ref.scores(pb, fwd), orc.scores(pb, fwd))
+            a, b = ref.paths(pb, fwd), orc.paths(pb, fwd)
             assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
 
 
@@ -59,3 +61,7 @@ def test_chain_oracle_edge_cases():
     assert len(paths) >= 1 and len(paths[0]) >= pb["querylength"] - 2 * pb["indexsize"] - 8
     q = paths[0][:, 0]
     assert (np.diff(q) > 0).all()
+    # lookforward: the same chain found from the other end, list order = highest querypos first (stage2.c:5062)
+    fpaths = orc.paths(pb, fwd=True)
+    assert len(fpaths) >= 1 and (np.diff(fpaths[0][:, 0]) < 0).all()
+    assert len(set(map(tuple, fpaths[0].tolist())) & set(map(tuple, paths[0].tolist()))) >= len(paths[0]) - 16

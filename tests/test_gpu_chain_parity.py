@@ -20,10 +20,10 @@ def engine():
     e.close()
 
 
-def check_against(engine, problems, expected):
+def check_against(engine, problems, expected, fwd=False):
     """expected[i] = (links, scores, cells, paths) with the oracle's / reference's conventions"""
     b = engine.chain_batch()
-    ids = [b.add(pb) for pb in problems]
+    ids = [b.add(pb, forward=fwd) for pb in problems]
     b.run()
     links, scores = b.links()
     off = 0
@@ -40,20 +40,35 @@ def check_against(engine, problems, expected):
     b.free()
 
 
-def test_chain_matches_reference_golden(engine):
-    gold = chain_golden_io.load()
-    check_against(engine, [g[0] for g in gold], [(g[1], g[2], g[3], g[4]) for g in gold])
+@pytest.mark.parametrize("fwd", [False, True])
+def test_chain_matches_reference_golden(engine, fwd):
+    gold = chain_golden_io.load(fwd)
+    check_against(engine, [g[0] for g in gold], [(g[1], g[2], g[3], g[4]) for g in gold], fwd)
 
 
+@pytest.mark.parametrize("fwd", [False, True])
 @pytest.mark.parametrize("seed,n,small", [(11, 120, True), (12, 40, False)])
-def test_chain_matches_oracle(engine, seed, n, small):
+def test_chain_matches_oracle(engine, seed, n, small, fwd):
     orc = ch.OracleChain()
     problems = chaingen.make_set(seed, n, small=small)
     exp = []
     for pb in problems:
-        links, scores, cells = orc.scores(pb)
-        exp.append((links, scores, cells, orc.paths(pb)))
-    check_against(engine, problems, exp)
+        links, scores, cells = orc.scores(pb, fwd)
+        exp.append((links, scores, cells, orc.paths(pb, fwd)))
+    check_against(engine, problems, exp, fwd)
+
+
+def test_chain_mixed_directions_in_one_batch(engine):
+    orc = ch.OracleChain()
+    problems = chaingen.make_set(21, 30, small=True)
+    b = engine.chain_batch()
+    ids = [b.add(pb, forward=bool(i & 1)) for i, pb in enumerate(problems)]
+    b.run()
+    for i, (cid, pb) in enumerate(zip(ids, problems)):
+        want = orc.paths(pb, bool(i & 1))
+        got = b.paths(cid)
+        assert len(got) == len(want) and all(np.array_equal(g[1], w) for g, w in zip(got, want))
+    b.free()
 
 
 def test_chain_edge_cases_and_batch_independence(engine):
