@@ -111,22 +111,54 @@ template <bool FWD> __device__ void section_d (Prob &P, const ChainParams &prm, 
       head = frontier ? frontier[ns] : P.first[pq];
       if (head != -1) hv = P.hot[o + head];
     }
-    /* range 0, in stack order: skip the leading hits whose label equals the label the previous list started with.
-       Only list heads are involved; a deeper walk (rare) is done by all lanes together. */
+    /* range 0, in stack order: a list skips its leading hits whose label equals the label the previous non-empty
+       list started with (stage2.c:1209-1214).  With a = label of a list's head and b = label of its second hit (a if
+       there is none), a list maps the incoming label lt to (lt == a ? b : a): whatever comes in, what goes out is a or
+       b, so along the stack the state is ONE BIT per list ("left on its second hit") and the lists compose as 2-state
+       maps -- a 5-step prefix scan instead of a 32-step walk.  Lists whose first two hits share a label (then a third
+       hit could matter) take the literal walk below. */
     int start = -1; int4 sv = hv;
     const unsigned havemask = __ballot_sync(FULL,head != -1);
-    for (unsigned m = havemask; m; m &= m - 1) {
-      const int j = __ffs(m) - 1;
-      int cur = __shfl_sync(FULL,head,j);
-      const int oj = __shfl_sync(FULL,o,j);
-      int4 cv;
-      cv.x = __shfl_sync(FULL,hv.x,j); cv.y = __shfl_sync(FULL,hv.y,j); cv.z = __shfl_sync(FULL,hv.z,j); cv.w = __shfl_sync(FULL,hv.w,j);
-      while (cur != -1 && H_TRACE(cv) == last_trace) {
-	cur = H_NEXT(cv);
-	if (cur != -1) cv = P.hot[oj + cur];
+    int4 h2 = make_int4(0,0,-1,0);
+    const bool second = (head != -1) && (H_NEXT(hv) != -1);
+    if (second) h2 = P.hot[o + H_NEXT(hv)];
+    const bool odd = second && (H_TRACE(h2) == H_TRACE(hv));
+    if (havemask == 0) {
+    } else if (!__any_sync(FULL,odd)) {
+      const int ta = H_TRACE(hv), tb = second ? H_TRACE(h2) : H_TRACE(hv);
+      const unsigned below = havemask & ((1u << lane) - 1);
+      const int prev = below ? 31 - __clz(below) : 0;
+      const int pa = __shfl_sync(FULL,ta,prev), pb = __shfl_sync(FULL,tb,prev);
+      unsigned map = 2u;				/* identity: bit s = image of state s */
+      if (head != -1) {
+	if (!below) map = (last_trace == ta) ? 3u : 0u;	/* first non-empty list of the chunk: the carried label decides */
+	else map = (unsigned) (pa == ta) | ((unsigned) (pb == ta) << 1);
       }
-      if (cur != -1) last_trace = H_TRACE(cv);
-      if (lane == j) { start = cur; sv = cv; }
+      for (int d = 1; d < 32; d <<= 1) {
+	const unsigned g = __shfl_up_sync(FULL,map,d);
+	if (lane >= d) map = ((map >> (g & 1)) & 1) | (((map >> ((g >> 1) & 1)) & 1) << 1);
+      }
+      const int st = (int) (map & 1);			/* constant map from the first non-empty list on */
+      if (head != -1) {
+	if (!st) { start = head; sv = hv; }
+	else if (second) { start = H_NEXT(hv); sv = h2; }
+      }
+      const int lastl = 31 - __clz(havemask);
+      last_trace = __shfl_sync(FULL,st ? tb : ta,lastl);
+    } else {
+      for (unsigned m = havemask; m; m &= m - 1) {
+	const int j = __ffs(m) - 1;
+	int cur = __shfl_sync(FULL,head,j);
+	const int oj = __shfl_sync(FULL,o,j);
+	int4 cv;
+	cv.x = __shfl_sync(FULL,hv.x,j); cv.y = __shfl_sync(FULL,hv.y,j); cv.z = __shfl_sync(FULL,hv.z,j); cv.w = __shfl_sync(FULL,hv.w,j);
+	while (cur != -1 && H_TRACE(cv) == last_trace) {
+	  cur = H_NEXT(cv);
+	  if (cur != -1) cv = P.hot[oj + cur];
+	}
+	if (cur != -1) last_trace = H_TRACE(cv);
+	if (lane == j) { start = cur; sv = cv; }
+      }
     }
     /* ranges 1, 2, 3+4: each lane on its own list */
     int ph = start, newfront = start;
