@@ -83,6 +83,12 @@ static void sm100_init (void) {
   atexit(sm100_report);
 }
 
+/* the process-wide engine, also used by the stage 2 binding (stage2_sm100.c) */
+gmapdp_ctx *sm100_context (void) {
+  pthread_once(&sm100_once,sm100_init);
+  return sm100_ctx;
+}
+
 /* called with the mutex held, before queueing: the shared batch is created from the first caller's limits
    (all Dynprog_T of a gmap run have the same max_rlength / max_glength, gmap.c:4898-4903) */
 static gmapdp_batch *shared_batch (Dynprog_T dynprog) {
