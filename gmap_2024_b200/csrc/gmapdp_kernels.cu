@@ -26,6 +26,8 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <thread>
+#include <chrono>
 #include <algorithm>
 
 #include "gmapdp_layout.h"
@@ -1157,29 +1159,72 @@ static inline void sort_chunk (std::vector<std::pair<double,int> > &work, int b0
 
 /* geometry and device allocations of a batch (no copies).  work[i] = (key, box id); within a chunk
    the sorted order lists the single-gap boxes first (key offset by -1e12) and chunk_nfull[k] counts them. */
-static int plan_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, size_t seqbytes, size_t nprobs,
-		       const std::vector<int> &chunk_begin, std::vector<int> &order, std::vector<std::pair<double,int> > &work,
-		       bool sort_now) {
+struct PlanScan { size_t ws_words[2], script_need; int maxcols[2]; };
+
+/* bytes a box makes the end-to-end path upload (sequences once, alt twins are shared; MaxEnt doubles) */
+static inline uint32_t box_upload_bytes (const gmapdp_box &x) {
+  size_t acc = (size_t) x.rlenL + x.rlenR + x.glenL + x.glenR;
+  if (x.mode == GMAPDP_GENOME) acc += 8 * ((size_t) x.glenL + x.glenR);
+  return (uint32_t) acc;
+}
+
+static int plan_scan (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, std::vector<std::pair<double,int> > &work,
+		      std::vector<uint32_t> *upload_bytes, PlanScan &ps) {
   size_t ws_words[2] = {0,0}, script_need = 0; int maxcols[2] = {8,8};
   work.resize(nboxes);
+  if (upload_bytes) upload_bytes->resize(nboxes);
+  {
+    /* per-box geometry (workspace words, script bound, work estimate) is the host's serial cost in front of the
+       first launch of the end-to-end path: spread it over a few threads for large batches */
+    struct Part { size_t ws[2], script; int cols[2]; bool bad; };
+    const int nthreads = (nboxes >= 65536) ? (int) std::min<unsigned>(8u,std::max(1u,std::thread::hardware_concurrency())) : 1;
+    std::vector<Part> parts(nthreads);
+    auto scan = [&](int t) {
+      Part &pt = parts[t];
+      pt.ws[0] = pt.ws[1] = 0; pt.script = 0; pt.cols[0] = pt.cols[1] = 8; pt.bad = false;
+      const int i0 = (int) ((long long) nboxes * t / nthreads), i1 = (int) ((long long) nboxes * (t + 1) / nthreads);
+      for (int i = i0; i < i1; i++) {
+	const gmapdp_box &b = boxes[i];
+	if (b.rlenL < 0 || b.glenL < 0 || b.rlenR < 0 || b.glenR < 0 || b.open >= 0 || b.extend >= 0 || b.mode < 0 || b.mode > 4 ||
+	    (unsigned) b.mismatchtype > 3u) { pt.bad = true; return; }
+	const int kind = (b.mode == GMAPDP_SINGLE) ? 0 : 1;
+	pt.ws[kind] = std::max(pt.ws[kind],gdp_ws_words(b));
+	pt.script += (size_t) b.rlenL + b.glenL + 4;
+	if (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA) pt.script += (size_t) b.rlenR + b.glenR + 4;
+	if (b.mode == GMAPDP_SINGLE) pt.cols[0] = std::max(pt.cols[0],(int) b.glenL + 2);
+	else if (b.mode == GMAPDP_CDNA) pt.cols[1] = std::max(pt.cols[1],(int) b.glenL + 2);	/* M and Q tables: 2 words per column */
+	work[i] = std::make_pair(-box_work(b) - (kind == 0 ? 1e12 : 0.0),i);	/* box_work < 1e10: the offset keeps full precision */
+	if (upload_bytes) (*upload_bytes)[i] = box_upload_bytes(b);
+      }
+    };
+    if (nthreads == 1) scan(0);
+    else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nthreads; t++) th.emplace_back(scan,t);
+      for (auto &x : th) x.join();
+    }
+    for (const Part &pt : parts) {
+      if (pt.bad) { ctx->err = "bad box"; return GMAPDP_ERR_ARG; }
+      for (int kind = 0; kind < 2; kind++) { ws_words[kind] = std::max(ws_words[kind],pt.ws[kind]); maxcols[kind] = std::max(maxcols[kind],pt.cols[kind]); }
+      script_need += pt.script;
+    }
+  }
+  ps.ws_words[0] = ws_words[0]; ps.ws_words[1] = ws_words[1]; ps.script_need = script_need;
+  ps.maxcols[0] = maxcols[0]; ps.maxcols[1] = maxcols[1];
+  return GMAPDP_OK;
+}
+
+static int plan_finish (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, size_t seqbytes, size_t nprobs,
+			const std::vector<int> &chunk_begin, std::vector<int> &order, std::vector<std::pair<double,int> > &work,
+			bool sort_now, const PlanScan &ps) {
+  const size_t ws_words[2] = {ps.ws_words[0],ps.ws_words[1]}, script_need = ps.script_need;
+  const int maxcols[2] = {ps.maxcols[0],ps.maxcols[1]};
   const int nchunks = (int) chunk_begin.size() - 1;
   ctx->chunk_nfull.assign(nchunks,0);
   int largest[2] = {0,0};
   for (int k = 0; k < nchunks; k++) {
     int nfull = 0;
-    for (int i = chunk_begin[k]; i < chunk_begin[k+1]; i++) {
-      const gmapdp_box &b = boxes[i];
-      if (b.rlenL < 0 || b.glenL < 0 || b.rlenR < 0 || b.glenR < 0 || b.open >= 0 || b.extend >= 0 || b.mode < 0 || b.mode > 4 ||
-	  (unsigned) b.mismatchtype > 3u) { ctx->err = "bad box"; return GMAPDP_ERR_ARG; }
-      const int kind = (b.mode == GMAPDP_SINGLE) ? 0 : 1;
-      ws_words[kind] = std::max(ws_words[kind],gdp_ws_words(b));
-      script_need += (size_t) b.rlenL + b.glenL + 4;
-      if (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA) script_need += (size_t) b.rlenR + b.glenR + 4;
-      if (b.mode == GMAPDP_SINGLE) maxcols[0] = std::max(maxcols[0],(int) b.glenL + 2);
-      else if (b.mode == GMAPDP_CDNA) maxcols[1] = std::max(maxcols[1],(int) b.glenL + 2);	/* M and Q tables: 2 words per column */
-      work[i] = std::make_pair(-box_work(b) - (kind == 0 ? 1e12 : 0.0),i);	/* box_work < 1e10: the offset keeps full precision */
-      nfull += (kind == 0);
-    }
+    for (int i = chunk_begin[k]; i < chunk_begin[k+1]; i++) nfull += (boxes[i].mode == GMAPDP_SINGLE);
     ctx->chunk_nfull[k] = nfull;
     largest[0] = std::max(largest[0],nfull);
     largest[1] = std::max(largest[1],chunk_begin[k+1] - chunk_begin[k] - nfull);
@@ -1216,6 +1261,15 @@ static int plan_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, siz
   if (grow(ctx,&ctx->d_probs,&ctx->cap_probs,nprobs + 2)) return GMAPDP_ERR_CUDA;
   if (grow(ctx,&ctx->d_script,&ctx->cap_script,script_need + 64)) return GMAPDP_ERR_CUDA;
   return GMAPDP_OK;
+}
+
+static int plan_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, size_t seqbytes, size_t nprobs,
+		       const std::vector<int> &chunk_begin, std::vector<int> &order, std::vector<std::pair<double,int> > &work,
+		       bool sort_now) {
+  PlanScan ps;
+  int rc = plan_scan(ctx,boxes,nboxes,work,NULL,ps);
+  if (rc) return rc;
+  return plan_finish(ctx,boxes,nboxes,seqbytes,nprobs,chunk_begin,order,work,sort_now,ps);
 }
 
 /* launches the (up to) two kernels of one chunk: the full-fill kernel on `stream', the E-only kernel on
@@ -1320,34 +1374,35 @@ extern "C" int gmapdp_run_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int n
   if (script_used) *script_used = 0;
   if (nboxes == 0) return GMAPDP_OK;
 
-  /* chunk boundaries by referenced bytes */
+  /* GMAPDP_TRACE=1: host-side timeline of this call on stderr */
+  static const bool trace = getenv("GMAPDP_TRACE") != NULL;
+  const auto T0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (trace) fprintf(stderr,"gmapdp_run_batch: %-22s %8.2f ms\n",what,
+		       std::chrono::duration<double,std::milli>(std::chrono::steady_clock::now() - T0).count());
+  };
+  /* per-box geometry in parallel, then chunk boundaries by uploaded bytes (a short first chunk lets the device start
+     early); the pool extents of a chunk are found just before its upload, under the previous chunk's kernels */
   const size_t CHUNK_BYTES = ctx->chunk_bytes;
+  std::vector<int> order;
+  std::vector<std::pair<double,int> > work;
+  std::vector<uint32_t> upbytes;
+  PlanScan ps;
+  int rc = plan_scan(ctx,boxes,nboxes,work,&upbytes,ps);
+  if (rc) return rc;
+  lap("box scan");
   std::vector<int> chunk_begin(1,0);
-  std::vector<size_t> slo, shi, plo, phi;
   {
-    size_t acc = 0, a = (size_t) -1, bnd = 0, pa = (size_t) -1, pb = 0;
+    size_t acc = 0;
     for (int i = 0; i < nboxes; i++) {
-      const gmapdp_box &x = boxes[i];
-      const size_t offs[6] = {x.qL_off, x.qR_off, x.gL_off, x.gLalt_off, x.gR_off, x.gRalt_off};
-      const size_t lens[6] = {(size_t) x.rlenL, (size_t) x.rlenR, (size_t) x.glenL, (size_t) x.glenL, (size_t) x.glenR, (size_t) x.glenR};
-      for (int k = 0; k < 6; k++) { a = std::min(a,offs[k]); bnd = std::max(bnd,offs[k] + lens[k]); acc += (k == 3 || k == 5) ? 0 : lens[k]; }
-      if (x.mode == GMAPDP_GENOME) {
-	pa = std::min(pa,std::min((size_t) x.probL_off,(size_t) x.probR_off));
-	pb = std::max(pb,std::max((size_t) x.probL_off + x.glenL,(size_t) x.probR_off + x.glenR));
-	acc += 8 * ((size_t) x.glenL + x.glenR);
-      }
-      if (acc >= CHUNK_BYTES || i == nboxes - 1) {
-	chunk_begin.push_back(i + 1);
-	slo.push_back(a); shi.push_back(std::min(bnd,seqbytes)); plo.push_back(pa); phi.push_back(std::min(pb,nprobs));
-	acc = 0; a = (size_t) -1; bnd = 0; pa = (size_t) -1; pb = 0;
-      }
+      acc += upbytes[i];
+      if (acc >= (chunk_begin.size() == 1 ? CHUNK_BYTES / 4 : CHUNK_BYTES) || i == nboxes - 1) { chunk_begin.push_back(i + 1); acc = 0; }
     }
   }
   const int nchunks = (int) chunk_begin.size() - 1;
-  std::vector<int> order;
-  std::vector<std::pair<double,int> > work;
-  int rc = plan_batch(ctx,boxes,nboxes,seqbytes,nprobs,chunk_begin,order,work,false);	/* chunks are sorted just in time, below */
+  rc = plan_finish(ctx,boxes,nboxes,seqbytes,nprobs,chunk_begin,order,work,false,ps);	/* chunks are sorted just in time, below */
   if (rc) return rc;
+  lap("plan");
   if (ctx->copy_stream == 0) CK(cudaStreamCreateWithFlags(&ctx->copy_stream,cudaStreamNonBlocking));
   while ((int) ctx->chunk_events.size() < nchunks) {
     cudaEvent_t e; CK(cudaEventCreateWithFlags(&e,cudaEventDisableTiming)); ctx->chunk_events.push_back(e);
@@ -1358,23 +1413,40 @@ extern "C" int gmapdp_run_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int n
   for (int k = 0; k < nchunks; k++) {
     const int b0 = chunk_begin[k], n = chunk_begin[k+1] - b0;
     cudaStream_t cs = ctx->copy_stream;
+    size_t slo = (size_t) -1, shi = 0, plo = (size_t) -1, phi = 0;	/* extents of this chunk in the two pools */
+    for (int i = b0; i < b0 + n; i++) {
+      const gmapdp_box &x = boxes[i];
+      const size_t offs[6] = {x.qL_off, x.qR_off, x.gL_off, x.gLalt_off, x.gR_off, x.gRalt_off};
+      const size_t lens[6] = {(size_t) x.rlenL, (size_t) x.rlenR, (size_t) x.glenL, (size_t) x.glenL, (size_t) x.glenR, (size_t) x.glenR};
+      for (int j = 0; j < 6; j++) { slo = std::min(slo,offs[j]); shi = std::max(shi,offs[j] + lens[j]); }
+      if (x.mode == GMAPDP_GENOME) {
+	plo = std::min(plo,std::min((size_t) x.probL_off,(size_t) x.probR_off));
+	phi = std::max(phi,std::max((size_t) x.probL_off + x.glenL,(size_t) x.probR_off + x.glenR));
+      }
+    }
+    shi = std::min(shi,seqbytes); phi = std::min(phi,nprobs);
     sort_chunk(work,b0,b0 + n);				/* overlaps the previous chunk's kernels */
     for (int i = b0; i < b0 + n; i++) order[i] = work[i].second;
     CK(cudaMemcpyAsync(ctx->d_boxes + b0,boxes + b0,(size_t) n * sizeof(gmapdp_box),cudaMemcpyHostToDevice,cs));
     CK(cudaMemcpyAsync(ctx->d_order + b0,order.data() + b0,(size_t) n * sizeof(int),cudaMemcpyHostToDevice,cs));
-    if (shi[k] > slo[k]) CK(cudaMemcpyAsync(ctx->d_seq + slo[k],seqpool + slo[k],shi[k] - slo[k],cudaMemcpyHostToDevice,cs));
-    if (phi[k] > plo[k] && plo[k] != (size_t) -1)
-      CK(cudaMemcpyAsync(ctx->d_probs + plo[k],probpool + plo[k],(phi[k] - plo[k]) * sizeof(double),cudaMemcpyHostToDevice,cs));
+    if (shi > slo) CK(cudaMemcpyAsync(ctx->d_seq + slo,seqpool + slo,shi - slo,cudaMemcpyHostToDevice,cs));
+    if (phi > plo && plo != (size_t) -1)
+      CK(cudaMemcpyAsync(ctx->d_probs + plo,probpool + plo,(phi - plo) * sizeof(double),cudaMemcpyHostToDevice,cs));
     CK(cudaEventRecord(ctx->chunk_events[k],cs));
     CK(cudaStreamWaitEvent(ctx->stream,ctx->chunk_events[k],0));
     CK(cudaStreamWaitEvent(ctx->stream2,ctx->chunk_events[k],0));
     rc = launch_chunk(ctx,b0,ctx->chunk_nfull[k],n - ctx->chunk_nfull[k]);
     if (rc) return rc;
+    if (k == 0) lap("first chunk launched");
   }
+  lap("all chunks launched");
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream2));
   CK(cudaStreamSynchronize(ctx->copy_stream));
-  return gmapdp_download(ctx,results,script,script_cap,script_used);
+  lap("kernels done");
+  rc = gmapdp_download(ctx,results,script,script_cap,script_used);
+  lap("results downloaded");
+  return rc;
 }
 
 /* pinned host memory helpers (so that the shim's pools are DMA-able without a staging copy) */
