@@ -2,14 +2,30 @@
  * device batch, run together, and read back per call in the reference's own order (paths by cell rank, pairs of a
  * path from its lowest querypos upwards, the order of the List_T that traceback_one returns). */
 #include <cstdint>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/gmapchain_b200.h"
 
+/* page-locks a pool for the duration of its use when it is large enough for DMA speed to matter */
+struct Pinned {
+  void *p; size_t bytes;
+  Pinned () : p(NULL), bytes(0) {}
+  void release () { if (p) gmapdp_host_unregister(p); p = NULL; bytes = 0; }
+  void ensure (const void *q, size_t n) {
+    if (q == p && n <= bytes) return;
+    release();
+    if (q && n >= ((size_t) 8 << 20) && gmapdp_host_register((void *) q,n) == GMAPDP_OK) { p = (void *) q; bytes = n; }
+  }
+};
+
 struct gmapchain_batch {
   gmapdp_ctx *ctx;
+  Pinned pin[8];
   std::vector<gmapchain_problem> problems;
   std::vector<int32_t> npos;
   std::vector<uint32_t> cum, mina, maxa, pos;
@@ -26,7 +42,8 @@ extern "C" gmapchain_batch *GmapChain_batch_new (gmapdp_ctx *ctx) {
   b->ctx = ctx; b->paths_used = b->pairs_used = 0; b->have_results = false;
   return b;
 }
-extern "C" void GmapChain_batch_free (gmapchain_batch *b) { delete b; }
+static void unpin_all (gmapchain_batch *b) { for (int i = 0; i < 8; i++) b->pin[i].release(); }
+extern "C" void GmapChain_batch_free (gmapchain_batch *b) { unpin_all(b); delete b; }
 extern "C" void GmapChain_batch_clear (gmapchain_batch *b) {
   b->problems.clear(); b->npos.clear(); b->cum.clear(); b->mina.clear(); b->maxa.clear(); b->pos.clear();
   b->results.clear(); b->paths_used = b->pairs_used = 0; b->have_results = false; b->err.clear();
@@ -41,6 +58,7 @@ static int queue_call (gmapchain_batch *b, int forwardp, uint32_t *const *mappin
   if (querylength < 0 || totalpositions < 0 || querystart < 0 || queryend >= querylength || indexsize <= 0) {
     b->err = "GmapChain_lookback: bad sizes"; return GMAPDP_ERR_ARG;
   }
+  for (int i = 0; i < 5; i++) b->pin[i].release();		/* the pools may move while they grow */
   gmapchain_problem p;
   memset(&p,0,sizeof(p));
   p.querylength = querylength; p.querystart = querystart; p.queryend = queryend; p.indexsize = indexsize;
@@ -86,6 +104,9 @@ static int fail (gmapchain_batch *b, int rc) { b->err = gmapdp_last_error(b->ctx
 
 extern "C" int GmapChain_batch_upload (gmapchain_batch *b) {
   static const int32_t z32 = 0; static const uint32_t zu = 0;
+  b->pin[0].ensure(b->npos.data(),b->npos.size() * 4); b->pin[1].ensure(b->cum.data(),b->cum.size() * 4);
+  b->pin[2].ensure(b->mina.data(),b->mina.size() * 4); b->pin[3].ensure(b->maxa.data(),b->maxa.size() * 4);
+  b->pin[4].ensure(b->pos.data(),b->pos.size() * 4);
   const int rc = gmapchain_upload(b->ctx,b->problems.data(),(int) b->problems.size(),
 				  b->npos.empty() ? &z32 : b->npos.data(),b->cum.empty() ? &zu : b->cum.data(),
 				  b->mina.empty() ? &zu : b->mina.data(),b->maxa.empty() ? &zu : b->maxa.data(),b->npos.size(),
@@ -101,19 +122,32 @@ extern "C" int GmapChain_batch_download (gmapchain_batch *b) {
   for (int attempt = 0; attempt < 2; attempt++) {
     if (b->paths.size() < 64) b->paths.resize(64);
     if (b->pairs.size() < 128) b->pairs.resize(128);
+    b->pin[5].ensure(b->paths.data(),b->paths.size() * sizeof(gmapchain_path));
+    b->pin[6].ensure(b->pairs.data(),b->pairs.size() * sizeof(int32_t));
     const int rc = gmapchain_download(b->ctx,b->results.data(),b->paths.data(),b->paths.size(),&b->paths_used,
 				      b->pairs.data(),b->pairs.size() / 2,&b->pairs_used);
     if (rc == GMAPDP_OK) { b->have_results = true; return GMAPDP_OK; }
     if (rc != GMAPDP_ERR_CAPACITY) return fail(b,rc);
+    b->pin[5].release(); b->pin[6].release();
     b->paths.resize(b->paths_used + 64); b->pairs.resize(2 * b->pairs_used + 128);
   }
   return fail(b,GMAPDP_ERR_CAPACITY);
 }
 extern "C" int GmapChain_batch_run (gmapchain_batch *b) {
+  static const bool trace = getenv("GMAPDP_TRACE") != NULL;	/* host-side timeline on stderr */
+  const auto T0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (trace) fprintf(stderr,"GmapChain_batch_run: %-12s %8.2f ms\n",what,
+		       std::chrono::duration<double,std::milli>(std::chrono::steady_clock::now() - T0).count());
+  };
   int rc;
   if ((rc = GmapChain_batch_upload(b))) return rc;
+  lap("uploaded");
   if ((rc = GmapChain_batch_run_resident(b,NULL))) return rc;
-  return GmapChain_batch_download(b);
+  lap("kernel done");
+  rc = GmapChain_batch_download(b);
+  lap("downloaded");
+  return rc;
 }
 
 extern "C" int GmapChain_npaths (const gmapchain_batch *b, int id) {

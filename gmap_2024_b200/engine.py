@@ -269,9 +269,9 @@ class ChainBatch:
             pos = np.zeros(1, dtype=np.uint32)
         base = pos.ctypes.data
         cum = np.concatenate([[0], np.cumsum(np.maximum(npos, 0))[:-1]]).astype(np.int64) if L else np.zeros(0, dtype=np.int64)
-        ptrs = (C.c_void_p * max(L, 1))(*[base + 4 * int(c) for c in cum])
+        ptrs = (np.uint64(base) + np.uint64(4) * cum.astype(np.uint64)) if L else np.zeros(1, dtype=np.uint64)   # Chrpos_T *mappings[q]
         rc = (self.lib.GmapChain_lookforward if forward else self.lib.GmapChain_lookback)(
-            self.h, ptrs, npos.ctypes.data_as(C.c_void_p), C.c_int(int(np.maximum(npos, 0).sum())),
+            self.h, ptrs.ctypes.data_as(C.c_void_p), npos.ctypes.data_as(C.c_void_p), C.c_int(int(np.maximum(npos, 0).sum())),
             mina.ctypes.data_as(C.c_void_p), maxa.ctypes.data_as(C.c_void_p), C.c_int(L), C.c_int(int(pb["querystart"])),
             C.c_int(int(pb["queryend"])), C.c_int(int(pb["indexsize"])), C.c_int(int(pb["localp"])),
             C.c_int(int(pb["skip_repetitive_p"])), C.c_int(int(use_canonical_p)), C.c_int(4), C.c_int(int(pb["favor_right_p"])),
