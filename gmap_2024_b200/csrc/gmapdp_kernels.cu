@@ -71,7 +71,8 @@ struct TriFill {
   int lateadd;			/* 1: ties go to the gap (jump late, >=), 0: > */
   bool lower;
   const uint2 *prof;		/* [0..nA] 8-byte score profiles of the lane-axis positions */
-  const uint8_t *code;		/* [0..nB] class codes of the step-axis positions */
+  const uint8_t *code;		/* [0..nB] class codes of the step-axis positions (class | alt class << 4) */
+  const uint16_t *sel;		/* [0..nB] the same as ready-made PRMT selectors (no alt genome), 16-byte aligned */
   uint32_t *dirs, *sc;		/* planes of pass `pass0'; the fill's further passes follow at dirPW / scPW */
   int dirPW, scPW;
 };
@@ -110,17 +111,107 @@ __device__ void tri_profiles (const TriFill &f, const SideSeq &sd, int mt, bool 
 }
 
 /* One pass: every lane owns one band diagonal of one of the (up to GDP_MAXFILLS) fills packed into it.
- * Profile / class-code loads run one step ahead of their use; the profile tables are padded by 32
- * entries in front so that the look-ahead of a not-yet-active lane stays inside the allocation. */
+ *
+ * Steps come in two kinds.  The general step (head and tail of a pass, wide fills, boxes with an alt genome)
+ * checks per lane whether its diagonal has started / ended; its profile and class-code loads run one step
+ * ahead of their use (the profile tables are padded by 32 entries in front so that the look-ahead of a
+ * not-yet-active lane stays inside the allocation).  The interior step -- every lane of the pass is inside
+ * its diagonal, which is > 90 % of the steps of a long box -- needs no such checks: 16 steps are unrolled
+ * around one direction word, the column's score is ONE PRMT with a ready-made selector (16 selectors arrive
+ * in two 16-byte loads), loads use immediate offsets, the tie rule is a template parameter when the fills of
+ * the pass agree on it, and the best-endpoint search keeps (score, step) instead of (score, key). */
+struct TriLane {
+  int d, tstart, tend, lateadd;
+  bool isd0, lower, edge_in, edge_out, trk;
+  const uint2 *pp;			/* pp[t] = prof[t - d] */
+  const uint8_t *code;
+  const uint16_t *sel;
+  int Hprev, H;
+  uint32_t pk_out, dacc, sacc;
+  uint32_t *dplane, *splane;
+};
+
+__device__ __forceinline__ uint32_t pack_lo16 (int lo, int hi) {	/* (lo & 0xffff) | (hi << 16): one PRMT */
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ int sext_lo16 (uint32_t w) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %1, 0x9910;" : "=r"(d) : "r"(w));
+  return (int) d;
+}
+
+/* LM: tie rule of the pass's fills -- 0 all `>' (jump early), 1 all `>=' (jump late), 2 per lane */
+template <bool SCORES, bool TRACK, int LM>
+__device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, const int open, const int extend, const int NEG,
+					  const int POS, const uint32_t negpair, BestTrack *bt) {
+  const uint2 *pq = s.pp + t;
+  const uint4 *sq = reinterpret_cast<const uint4 *>(s.sel + t);
+  const int la = s.lateadd;
+  const bool isd0 = s.isd0;
+  int H = s.Hprev;
+  uint32_t pk_out = s.pk_out;
+  uint32_t *dplane = s.dplane, *splane = s.splane;
+  int bs = 0, btt = -1;
+  if (TRACK) bs = bt->bs;
+  for (; t + 16 <= tstop; t += 16) {
+    const uint4 s0 = sq[0], s1 = sq[1];
+    const uint32_t sw[8] = {s0.x,s0.y,s0.z,s0.w,s1.x,s1.y,s1.z,s1.w};
+    uint32_t dacc = 0;
+    int Heven = 0;
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      uint32_t pk_in = __shfl_up_sync(FULLMASK,pk_out,1);
+      if (isd0) pk_in = negpair;
+      const uint2 p = pq[u];
+      const uint32_t selw = (u & 1) ? (sw[u >> 1] >> 16) : sw[u >> 1];
+      uint32_t scu;
+      asm("prmt.b32 %0, %1, %2, %3;" : "=r"(scu) : "r"(p.x), "r"(p.y), "r"(selw));
+      const int Hd = clampi(H + (int) scu,NEG,POS);
+      const int Hl = sext_lo16(pk_in), El = ((int) pk_in) >> 16;
+      const int T1 = max(Hl + open,NEG);
+      const bool dE = (LM == 0) ? (El > T1) : ((LM == 1) ? (El >= T1) : (El + la > T1));
+      const int E = max(max(El,T1) + extend,NEG);
+      const bool dN = (LM == 0) ? (E > Hd) : ((LM == 1) ? (E >= Hd) : (E + la > Hd));
+      const int Hn = max(Hd,E);
+      pk_out = pack_lo16(Hn,E);
+      dacc |= (dN ? (1u << (2 * u)) : 0u) | (dE ? (2u << (2 * u)) : 0u);
+      if (SCORES) {
+	if (u & 1) { *splane = pack_lo16(Heven,Hn); splane += 32; }
+	else Heven = Hn;
+      }
+      if (TRACK) {
+	const bool up = s.trk && ((LM == 0) ? (Hn > bs) : ((LM == 1) ? (Hn >= bs) : (Hn + la > bs)));
+	bs = up ? Hn : bs; btt = up ? t + u : btt;
+      }
+      H = Hn;
+    }
+    pq += 16; sq += 2;
+    *dplane = isd0 ? 0u : dacc; dplane += 32;
+  }
+  s.Hprev = H; s.H = H; s.pk_out = pk_out; s.dplane = dplane; s.splane = splane;
+  if (TRACK) {
+    if (btt >= 0) {
+      const int i = btt - s.d;
+      const int r = s.lower ? btt : i, c = s.lower ? i : btt;
+      bt->bs = bs; bt->bk = (r << 16) | c;
+    }
+  }
+}
+
 template <bool SCORES, bool TRACK, bool WIDE>
 __device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
-			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge) {
+			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok) {
   const int lane = threadIdx.x & 31;
   /* lane configuration */
-  int d = -1, nA = -1, nB = -1, lateadd = 0, thi = -1, tlo = 0x7fffffff;
-  bool lower = false, edge_in = false, edge_out = false;
-  const uint2 *prof = NULL; const uint8_t *code = NULL;
-  uint32_t *dplane = NULL, *splane = NULL;
+  TriLane s;
+  int nA = -1, nB = -1, thi = -1, tlo = 0x7fffffff;
+  int maxstart = 0, minend = 0x7fffffff, lm = -1;
+  s.d = -1; s.lateadd = 0; s.lower = false; s.edge_in = false; s.edge_out = false;
+  const uint2 *prof = NULL; s.code = NULL; s.sel = NULL;
+  const uint2 *prof0 = NULL; const uint16_t *sel0 = NULL;
+  s.dplane = NULL; s.splane = NULL;
 #pragma unroll
   for (int f = 0; f < GDP_MAXFILLS; f++) {
     if (f < nf && pass >= F[f].pass0 && pass < F[f].pass0 + F[f].npass) {
@@ -128,84 +219,104 @@ __device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, in
       const int dd = (lane - F[f].lane0) + 32 * p;
       thi = max(thi,F[f].nB);
       tlo = min(tlo,32 * p);
-      dplane = F[f].dirs + (size_t) p * F[f].dirPW;		/* the pass's planes are shared by its fills */
-      splane = SCORES ? F[f].sc + (size_t) p * F[f].scPW : NULL;
+      maxstart = max(maxstart,F[f].band);
+      minend = min(minend,min(F[f].nA,F[f].nB));
+      lm = (lm < 0 || lm == F[f].lateadd) ? F[f].lateadd : 2;
+      prof0 = F[f].prof; sel0 = F[f].sel;
+      s.dplane = F[f].dirs + (size_t) p * F[f].dirPW;		/* the pass's planes are shared by its fills */
+      s.splane = SCORES ? F[f].sc + (size_t) p * F[f].scPW : NULL;
       if (lane >= F[f].lane0 && dd <= F[f].band && (F[f].npass > 1 || lane - F[f].lane0 <= F[f].band)) {
-	d = dd; nA = F[f].nA; nB = F[f].nB; lateadd = F[f].lateadd; lower = F[f].lower;
-	prof = F[f].prof; code = F[f].code;
-	edge_in = WIDE && (p > 0 && lane == 0);
-	edge_out = WIDE && (p + 1 < F[f].npass && lane == 31);
+	s.d = dd; nA = F[f].nA; nB = F[f].nB; s.lateadd = F[f].lateadd; s.lower = F[f].lower;
+	prof = F[f].prof; s.code = F[f].code; s.sel = F[f].sel;
+	s.edge_in = WIDE && (p > 0 && lane == 0);
+	s.edge_out = WIDE && (p + 1 < F[f].npass && lane == 31);
       }
     }
   }
   if (thi < 0) return;
-  dplane += lane + (size_t) (tlo >> 4) * 32;
-  if (SCORES) splane += lane + (size_t) (tlo >> 1) * 32;
-  const int tstart = (d >= 0) ? d : 0x7fffffff, tend = (d >= 0) ? min(nA + d,nB) : -1;
-  const bool isd0 = (d == 0);
-  const uint2 *pp = prof - d;				/* pp[t] = prof[t - d] */
+  s.dplane += lane + (size_t) (tlo >> 4) * 32;
+  if (SCORES) s.splane += lane + (size_t) (tlo >> 1) * 32;
+  s.tstart = (s.d >= 0) ? s.d : 0x7fffffff; s.tend = (s.d >= 0) ? min(nA + s.d,nB) : -1;
+  s.isd0 = (s.d <= 0);
+  s.pp = prof - s.d;
+  if (s.d < 0) { s.pp = prof0; s.sel = sel0; }		/* idle lanes of the interior steps read (and discard) a valid diagonal */
+  s.trk = TRACK && s.d >= 0 && (!s.lower || s.d > 0) && !lastrow;
   const uint32_t negpair = ((uint32_t) NEG & 0xffffu) | ((uint32_t) NEG << 16);
 
-  int Hprev = isd0 ? 0 : NEG, H = NEG;
-  uint32_t pk_out = 0, dacc = 0, sacc = 0;
-  bool act_n = (tlo >= tstart && tlo <= tend);
-  uint2 p_n = make_uint2(0u,0u); int cd_n = 0;
-  if (act_n) { p_n = pp[tlo]; cd_n = code[tlo]; }
+  s.Hprev = (s.d == 0) ? 0 : NEG; s.H = NEG;
+  s.pk_out = 0; s.dacc = 0; s.sacc = 0;
 
-  for (int t = tlo; t <= thi; t += 2) {
+  /* interior steps [F0, F1): F0 a multiple of 16 past every lane's start, F1 before any lane's last step */
+  int F0 = (maxstart + 1 + 15) & ~15, F1 = F0;
+  if (!WIDE && fastok) while (F1 + 16 <= minend) F1 += 16;
+  const bool hasfast = (F1 > F0);
+
+  int t = tlo;
+  for (int phase = 0; phase < 2; phase++) {
+    const int tlast = (phase == 0 && hasfast) ? F0 - 1 : thi;
+    bool act_n = (t >= s.tstart && t <= s.tend);
+    uint2 p_n = make_uint2(0u,0u); int cd_n = 0;
+    if (act_n) { p_n = s.pp[t]; cd_n = s.code[t]; }
+    for (; t <= tlast; t += 2) {
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int tc = t + u;
-      uint32_t pk_in = __shfl_up_sync(FULLMASK,pk_out,1);
-      const bool act = act_n;
-      const uint2 p = p_n; const int cd = cd_n;
-      act_n = (tc + 1 >= tstart) && (tc + 1 <= tend);
-      if (act_n) { p_n = pp[tc + 1]; cd_n = code[tc + 1]; }
-      uint32_t bits = 0;
-      if (act) {
-	if (WIDE && edge_in) pk_in = edge[tc - d];
-	if (isd0) pk_in = negpair;
-	const int sc = max(prof_pick(p.x,p.y,cd & 15),prof_pick(p.x,p.y,cd >> 4));
-	const int Hd = clampi(Hprev + sc,NEG,POS);
-	const int Hl = (int) (short) (pk_in & 0xffffu), El = ((int) pk_in) >> 16;
-	const int T1 = max(Hl + open,NEG);
-	const bool dE = (El + lateadd > T1);
-	const int E = max(max(El,T1) + extend,NEG);
-	const bool dN = (E + lateadd > Hd);
-	H = max(Hd,E);
-	bits = isd0 ? 0u : ((dN ? 1u : 0u) | (dE ? 2u : 0u));
-	Hprev = H;
-	pk_out = ((uint32_t) H & 0xffffu) | ((uint32_t) E << 16);
-	if (WIDE && edge_out) edge[tc - d] = pk_out;
-	if (TRACK) {
-	  const int i = tc - d;
-	  const int r = lower ? tc : i, c = lower ? i : tc;
-	  if (r >= 1 && c >= 1 && (!lower || d > 0) && (!lastrow || r == track_rlen)) {
-	    const int key = (r << 16) | c;
-	    if (H > bt->bs || (H == bt->bs && (lateadd ? key > bt->bk : key < bt->bk))) { bt->bs = H; bt->bk = key; }
+      for (int u = 0; u < 2; u++) {
+	const int tc = t + u;
+	uint32_t pk_in = __shfl_up_sync(FULLMASK,s.pk_out,1);
+	const bool act = act_n;
+	const uint2 p = p_n; const int cd = cd_n;
+	act_n = (tc + 1 >= s.tstart) && (tc + 1 <= s.tend);
+	if (act_n) { p_n = s.pp[tc + 1]; cd_n = s.code[tc + 1]; }
+	uint32_t bits = 0;
+	if (act) {
+	  if (WIDE && s.edge_in) pk_in = edge[tc - s.d];
+	  if (s.d == 0) pk_in = negpair;
+	  const int sc = max(prof_pick(p.x,p.y,cd & 15),prof_pick(p.x,p.y,cd >> 4));
+	  const int Hd = clampi(s.Hprev + sc,NEG,POS);
+	  const int Hl = (int) (short) (pk_in & 0xffffu), El = ((int) pk_in) >> 16;
+	  const int T1 = max(Hl + open,NEG);
+	  const bool dE = (El + s.lateadd > T1);
+	  const int E = max(max(El,T1) + extend,NEG);
+	  const bool dN = (E + s.lateadd > Hd);
+	  s.H = max(Hd,E);
+	  bits = (s.d == 0) ? 0u : ((dN ? 1u : 0u) | (dE ? 2u : 0u));
+	  s.Hprev = s.H;
+	  s.pk_out = ((uint32_t) s.H & 0xffffu) | ((uint32_t) E << 16);
+	  if (WIDE && s.edge_out) edge[tc - s.d] = s.pk_out;
+	  if (TRACK) {
+	    const int i = tc - s.d;
+	    const int r = s.lower ? tc : i, c = s.lower ? i : tc;
+	    if (r >= 1 && c >= 1 && (!s.lower || s.d > 0) && (!lastrow || r == track_rlen)) {
+	      const int key = (r << 16) | c;
+	      if (s.H > bt->bs || (s.H == bt->bs && (s.lateadd ? key > bt->bk : key < bt->bk))) { bt->bs = s.H; bt->bk = key; }
+	    }
 	  }
 	}
+	s.dacc |= bits << (2 * (tc & 15));
+	if (SCORES) s.sacc |= ((uint32_t) s.H & 0xffffu) << (16 * u);
       }
-      dacc |= bits << (2 * (tc & 15));
-      if (SCORES) sacc |= ((uint32_t) H & 0xffffu) << (16 * u);
+      if (SCORES) { *s.splane = s.sacc; s.splane += 32; s.sacc = 0; }
+      if ((t & 15) == 14) { *s.dplane = s.dacc; s.dplane += 32; s.dacc = 0; }
     }
-    if (SCORES) { *splane = sacc; splane += 32; sacc = 0; }
-    if ((t & 15) == 14) { *dplane = dacc; dplane += 32; dacc = 0; }
+    if (phase == 0 && hasfast) {
+      if (lm == 0) tri_fast<SCORES,TRACK,0>(s,t,F1,open,extend,NEG,POS,negpair,bt);
+      else if (lm == 1) tri_fast<SCORES,TRACK,1>(s,t,F1,open,extend,NEG,POS,negpair,bt);
+      else tri_fast<SCORES,TRACK,2>(s,t,F1,open,extend,NEG,POS,negpair,bt);
+    } else break;
   }
-  if (((thi & ~1) & 15) != 14) *dplane = dacc;
+  if (((thi & ~1) & 15) != 14) *s.dplane = s.dacc;
   __syncwarp();
 }
 
 /* all passes of a box's E-only fills */
 template <bool SCORES, bool TRACK>
 __device__ void tri_fill_all (const TriFill (&F)[GDP_MAXFILLS], int nf, int npasses, int open, int extend, int NEG, int POS,
-			      BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge) {
+			      BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok) {
   bool wide = false;
 #pragma unroll
   for (int f = 0; f < GDP_MAXFILLS; f++) if (f < nf && F[f].npass > 1) wide = true;
   for (int pass = 0; pass < npasses; pass++) {
-    if (wide) tri_pass<SCORES,TRACK,true>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge);
-    else tri_pass<SCORES,TRACK,false>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge);
+    if (wide) tri_pass<SCORES,TRACK,true>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,false);
+    else tri_pass<SCORES,TRACK,false>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok);
   }
 }
 
@@ -812,8 +923,11 @@ struct KernelArgs {
   const GdpTables *tables;
 };
 
-template <bool FULLK>
+/* KIND: 0 single gaps (full fill), 1 end5/end3 (E-only fills + endpoint search), 2 genome gaps, 3 cdna gaps */
+template <int KIND>
 __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *bnd, const GdpTables *tb) {
+  constexpr bool FULLK = (KIND == 0);
+  constexpr bool twosided = (KIND >= 2);
 
   const int lane = threadIdx.x & 31;
   const gmapdp_box b = ka.boxes[bi];
@@ -828,27 +942,42 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 
   /* carve the workspace */
   uint8_t *bytes = reinterpret_cast<uint8_t *>(ws);
-  uint8_t *qcodeL = bytes; bytes += gdp_align4(b.rlenL + 2);
-  uint8_t *qcodeR = bytes; bytes += gdp_align4(b.rlenR + 2);
-  uint8_t *gcodeL = bytes; bytes += gdp_align4(b.glenL + 2);
-  uint8_t *ldi = bytes; bytes += gdp_align4(b.glenL + 2);
-  uint8_t *gcodeR = bytes; bytes += gdp_align4(b.glenR + 2);
-  uint8_t *rdi = bytes; bytes += gdp_align4(b.glenR + 2);
+  uint8_t *qcodeL = bytes; bytes += gdp_align16(b.rlenL + 2);
+  uint8_t *qcodeR = bytes; bytes += gdp_align16(b.rlenR + 2);
+  uint8_t *gcodeL = bytes; bytes += gdp_align16(b.glenL + 2);
+  uint8_t *ldi = bytes; bytes += gdp_align16(b.glenL + 2);
+  uint8_t *gcodeR = bytes; bytes += gdp_align16(b.glenR + 2);
+  uint8_t *rdi = bytes; bytes += gdp_align16(b.glenR + 2);
+  uint16_t *qselL = reinterpret_cast<uint16_t *>(bytes); bytes += gdp_align16(2 * (size_t) (b.rlenL + 2));
+  uint16_t *qselR = reinterpret_cast<uint16_t *>(bytes); bytes += gdp_align16(2 * (size_t) (b.rlenR + 2));
+  uint16_t *gselL = reinterpret_cast<uint16_t *>(bytes); bytes += gdp_align16(2 * (size_t) (b.glenL + 2));
+  uint16_t *gselR = reinterpret_cast<uint16_t *>(bytes); bytes += gdp_align16(2 * (size_t) (b.glenR + 2));
   uint32_t *wp = reinterpret_cast<uint32_t *>(bytes);
   uint32_t *stage = wp; wp += b.rlenL + b.glenL + b.rlenR + b.glenR + 16;
 
-  const bool twosided = (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA);
 
   /* pre-pass: class codes in DP coordinates */
   if (!FULLK) {
-    for (int c = lane; c <= b.glenL; c += 32) gcodeL[c] = (c == 0) ? 0x44 : (uint8_t) (nt_class(L.g(c)) | (nt_class(L.ga(c)) << 4));
-    for (int r = lane; r <= b.rlenL; r += 32) { const int k = (r == 0) ? 4 : nt_class(L.q(r)); qcodeL[r] = (uint8_t) (k | (k << 4)); }
+    for (int c = lane; c <= b.glenL; c += 32) {
+      const int k = (c == 0) ? 4 : nt_class(L.g(c)), ka = (c == 0) ? 4 : nt_class(L.ga(c));
+      gcodeL[c] = (uint8_t) (k | (ka << 4)); gselL[c] = (uint16_t) (k * 0x1111 + 0x8880);
+    }
+    for (int r = lane; r <= b.rlenL; r += 32) {
+      const int k = (r == 0) ? 4 : nt_class(L.q(r));
+      qcodeL[r] = (uint8_t) (k | (k << 4)); qselL[r] = (uint16_t) (k * 0x1111 + 0x8880);
+    }
   }
   if (!FULLK && twosided) {
-    for (int c = lane; c <= b.glenR; c += 32) gcodeR[c] = (c == 0) ? 0x44 : (uint8_t) (nt_class(R.g(c)) | (nt_class(R.ga(c)) << 4));
-    for (int r = lane; r <= b.rlenR; r += 32) { const int k = (r == 0) ? 4 : nt_class(R.q(r)); qcodeR[r] = (uint8_t) (k | (k << 4)); }
+    for (int c = lane; c <= b.glenR; c += 32) {
+      const int k = (c == 0) ? 4 : nt_class(R.g(c)), ka = (c == 0) ? 4 : nt_class(R.ga(c));
+      gcodeR[c] = (uint8_t) (k | (ka << 4)); gselR[c] = (uint16_t) (k * 0x1111 + 0x8880);
+    }
+    for (int r = lane; r <= b.rlenR; r += 32) {
+      const int k = (r == 0) ? 4 : nt_class(R.q(r));
+      qcodeR[r] = (uint8_t) (k | (k << 4)); qselR[r] = (uint16_t) (k * 0x1111 + 0x8880);
+    }
   }
-  if (!FULLK && b.mode == GMAPDP_GENOME) {
+  if (KIND == 2) {
     /* dinucleotide classes, dynprog_genome.c:919-967 (forward arrays: rev_gsequenceR[-cR] = GR[glenR-1-cR]) */
     for (int cL = lane; cL <= b.glenL; cL += 32) {
       int v = 0;
@@ -898,6 +1027,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
     TriPacking tp;
     tri_fills_of(b,tp);
     TriFill F[GDP_MAXFILLS];
+    const bool noalt = (b.gLalt_off == b.gL_off) && (!twosided || b.gRalt_off == b.gR_off);	/* selectors carry one class */
     if ((reinterpret_cast<uintptr_t>(wp) & 7) != 0) wp++;
     for (int f = 0; f < GDP_MAXFILLS; f++) {
       if (f >= tp.nf) { F[f] = F[0]; continue; }
@@ -908,6 +1038,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
       F[f].lateadd = (right ? lateR : lateL) ? 1 : 0;
       F[f].lower = lower;
       F[f].code = lower ? (right ? qcodeR : qcodeL) : (right ? gcodeR : gcodeL);
+      F[f].sel = lower ? (right ? qselR : qselL) : (right ? gselR : gselL);
       F[f].prof = reinterpret_cast<const uint2 *>(wp) + 32;	/* 32 entries of look-ahead padding in front */
       F[f].dirPW = tp.dirPW; F[f].scPW = tp.scPW;
       tri_profiles(F[f],right ? R : L,mt,use8,reinterpret_cast<uint2 *>(wp) + 32,tb);
@@ -928,7 +1059,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
       const bool lastrow = (b.flags & GMAPDP_F_LASTROW) != 0;
       BestTrack bt;
       if (lastrow) { bt.bs = NEG; bt.bk = (b.rlenL << 16); } else { bt.bs = 0; bt.bk = 0; }
-      tri_fill_all<false,true>(F,tp.nf,tp.npasses,open,extend,NEG,POS,&bt,b.rlenL,lastrow,edge);
+      tri_fill_all<false,true>(F,tp.nf,tp.npasses,open,extend,NEG,POS,&bt,b.rlenL,lastrow,edge,noalt);
       for (int off = 16; off > 0; off >>= 1) {
 	const int os = __shfl_xor_sync(FULLMASK,bt.bs,off), ok = __shfl_xor_sync(FULLMASK,bt.bk,off);
 	if (os > bt.bs || (os == bt.bs && (lateL ? ok > bt.bk : ok < bt.bk))) { bt.bs = os; bt.bk = ok; }
@@ -942,10 +1073,10 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
       }
     } else {
       const TriFill &LL = F[0], &RL = F[1], &LU = F[2], &RU = F[3];
-      tri_fill_all<true,false>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge);
+      tri_fill_all<true,false>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt);
       __syncwarp();
       int brL, brR, bcL, bcR, fs;
-      if (b.mode == GMAPDP_GENOME) {
+      if (KIND == 2) {
 	const int di = b.cdna_direction > 0 ? 0 : (b.cdna_direction < 0 ? 1 : 2);
 	fs = bridge_genome(b,LU,LL,RU,RL,ldi,rdi,ka.probs + b.probL_off,ka.probs + b.probR_off,NEG,
 			   tb->isc[di][(b.flags & GMAPDP_F_FINALP) ? 1 : 0],&brL,&brR,&bcL,&bcR);
@@ -983,17 +1114,27 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 
 extern __shared__ __align__(16) unsigned char dyn_smem[];
 
-/* Two specialisations of one persistent kernel: FULLK = single-gap boxes (full fill: needs the big
-   shared-memory boundary rows, 3 blocks/SM), !FULLK = every other mode (E-only fills, bridges: almost no
-   shared memory, 5 blocks/SM).  They are launched on two streams and share the SMs. */
+/* Four specialisations of one persistent kernel, one per kind of box: single gaps (full fill: needs the big
+   shared-memory boundary rows, 3 blocks/SM), end gaps, genome gaps, cdna gaps (E-only fills, bridges: almost
+   no shared memory).  A specialisation carries only its own mode's code, so the warps of an SM share their
+   instruction-cache footprint; the four are launched on four streams and share the SMs. */
 #ifndef GMAPDP_FULL_MINB
 #define GMAPDP_FULL_MINB 3
 #endif
 #ifndef GMAPDP_TRI_MINB
 #define GMAPDP_TRI_MINB 5
 #endif
-template <bool FULLK>
-__global__ void __launch_bounds__(BLOCK_THREADS,FULLK ? GMAPDP_FULL_MINB : GMAPDP_TRI_MINB)
+#ifndef GMAPDP_END_MINB
+#define GMAPDP_END_MINB GMAPDP_TRI_MINB
+#endif
+#ifndef GMAPDP_GENOME_MINB
+#define GMAPDP_GENOME_MINB GMAPDP_TRI_MINB
+#endif
+#ifndef GMAPDP_CDNA_MINB
+#define GMAPDP_CDNA_MINB GMAPDP_TRI_MINB
+#endif
+template <int KIND>
+__global__ void __launch_bounds__(BLOCK_THREADS,KIND == 0 ? GMAPDP_FULL_MINB : (KIND == 1 ? GMAPDP_END_MINB : (KIND == 2 ? GMAPDP_GENOME_MINB : GMAPDP_CDNA_MINB)))
 gmapdp_dp_kernel (KernelArgs ka) {
   /* shared: one 8-byte boundary entry per column and warp */
   const GdpTables *tb = ka.tables;
@@ -1007,7 +1148,7 @@ gmapdp_dp_kernel (KernelArgs ka) {
     if (lane == 0) idx = atomicAdd(ka.queue,1);
     idx = __shfl_sync(FULLMASK,idx,0);
     if (idx >= ka.nboxes) break;
-    process_box<FULLK>(ka,ka.order[idx],ws,bnd,tb);
+    process_box<KIND>(ka,ka.order[idx],ws,bnd,tb);
   }
 }
 
@@ -1016,13 +1157,17 @@ gmapdp_dp_kernel (KernelArgs ka) {
  * ---------------------------------------------------------------------------------------------- */
 #include "gmapdp_internal.h"
 
+#define GDP_NK 4
+static inline int kind_of (int mode) { return mode == GMAPDP_SINGLE ? 0 : (mode == GMAPDP_GENOME ? 2 : (mode == GMAPDP_CDNA ? 3 : 1)); }
+
 struct gmapdp_ctx {
   int device, sm_count, grid, max_smem;
-  int kgrid[2], ksmem_cols[2]; size_t kws_words[2];	/* per kernel kind: 0 = full, 1 = tri */
-  uint32_t *d_kws[2]; size_t cap_kws[2];
-  cudaStream_t stream2; cudaEvent_t evj, evk[2][2]; float last_ms[2];
+  int kgrid[GDP_NK], ksmem_cols[GDP_NK]; size_t kws_words[GDP_NK];	/* per kernel kind: 0 single, 1 end, 2 genome, 3 cdna */
+  uint32_t *d_kws[GDP_NK]; size_t cap_kws[GDP_NK];
+  cudaStream_t kstream[GDP_NK];		/* kstream[0] == stream */
+  cudaEvent_t evj[GDP_NK], evk[GDP_NK][2]; float last_ms[GDP_NK];
   size_t chunk_bytes;			/* pipelining granularity of gmapdp_run_batch (GMAPDP_CHUNK_MB, default 192) */
-  std::vector<int> chunk_nfull;
+  std::vector<int> chunk_count;		/* [chunk][kind] boxes */
   cudaStream_t stream, copy_stream;
   std::vector<cudaEvent_t> chunk_events;
   cudaEvent_t ev0, ev1;
@@ -1075,8 +1220,8 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   ctx->d_tables = NULL; ctx->d_boxes = NULL; ctx->cap_boxes = 0; ctx->d_order = NULL; ctx->cap_order = 0; ctx->cap_results = 0; ctx->d_seq = NULL; ctx->cap_seq = 0;
   ctx->d_probs = NULL; ctx->cap_probs = 0; ctx->d_results = NULL; ctx->d_script = NULL; ctx->cap_script = 0;
   ctx->d_cursor = NULL; ctx->d_queue = NULL; ctx->d_ws = NULL; ctx->cap_ws = 0; ctx->h_pin = NULL; ctx->cap_pin = 0;
-  ctx->stream = 0; ctx->copy_stream = 0; ctx->stream2 = 0; ctx->evj = 0; ctx->ev0 = ctx->ev1 = 0;
-  ctx->d_kws[0] = ctx->d_kws[1] = NULL; ctx->cap_kws[0] = ctx->cap_kws[1] = 0;
+  ctx->stream = 0; ctx->copy_stream = 0; ctx->ev0 = ctx->ev1 = 0;
+  for (int k = 0; k < GDP_NK; k++) { ctx->d_kws[k] = NULL; ctx->cap_kws[k] = 0; ctx->kstream[k] = 0; ctx->evj[k] = 0; ctx->evk[k][0] = ctx->evk[k][1] = 0; ctx->last_ms[k] = 0.f; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     ctx->err = "no CUDA device: the gmapdp engine has no CPU fallback";
@@ -1088,16 +1233,18 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->max_smem = (int) prop.sharedMemPerBlockOptin;
   cudaFuncAttributes fa;
-  cudaError_t fe = cudaFuncGetAttributes(&fa,gmapdp_dp_kernel<true>);
+  cudaError_t fe = cudaFuncGetAttributes(&fa,gmapdp_dp_kernel<0>);
   if (fe != cudaSuccess) {
     ctx->err = std::string("no sm_100a kernel image for this device (") + prop.name + "): " + cudaGetErrorString(fe);
     return GMAPDP_ERR_CUDA;
   }
   CK(cudaStreamCreateWithFlags(&ctx->stream,cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&ctx->stream2,cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&ctx->evj,cudaEventDisableTiming));
-  for (int a = 0; a < 2; a++) for (int b2 = 0; b2 < 2; b2++) CK(cudaEventCreate(&ctx->evk[a][b2]));
-  ctx->last_ms[0] = ctx->last_ms[1] = 0.f;
+  ctx->kstream[0] = ctx->stream;
+  for (int k = 1; k < GDP_NK; k++) CK(cudaStreamCreateWithFlags(&ctx->kstream[k],cudaStreamNonBlocking));
+  for (int k = 0; k < GDP_NK; k++) {
+    CK(cudaEventCreateWithFlags(&ctx->evj[k],cudaEventDisableTiming));
+    CK(cudaEventCreate(&ctx->evk[k][0])); CK(cudaEventCreate(&ctx->evk[k][1]));
+  }
   {
     const char *cm = getenv("GMAPDP_CHUNK_MB");
     long mb = cm ? atol(cm) : 192;
@@ -1108,9 +1255,11 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   CK(cudaMalloc((void **) &ctx->d_tables,sizeof(GdpTables)));
   CK(cudaMemcpy(ctx->d_tables,&t,sizeof(GdpTables),cudaMemcpyHostToDevice));
   CK(cudaMalloc((void **) &ctx->d_cursor,sizeof(unsigned long long)));
-  CK(cudaMalloc((void **) &ctx->d_queue,2 * sizeof(int)));
-  CK(cudaFuncSetAttribute(gmapdp_dp_kernel<true>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
-  CK(cudaFuncSetAttribute(gmapdp_dp_kernel<false>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
+  CK(cudaMalloc((void **) &ctx->d_queue,GDP_NK * sizeof(int)));
+  CK(cudaFuncSetAttribute(gmapdp_dp_kernel<0>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
+  CK(cudaFuncSetAttribute(gmapdp_dp_kernel<1>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
+  CK(cudaFuncSetAttribute(gmapdp_dp_kernel<2>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
+  CK(cudaFuncSetAttribute(gmapdp_dp_kernel<3>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
   ctx->grid = 0;
   return GMAPDP_OK;
 }
@@ -1120,14 +1269,19 @@ extern "C" void gmapdp_destroy (gmapdp_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->chain && ctx->chain_free) ctx->chain_free(ctx->chain);
   cudaFree(ctx->d_tables); cudaFree(ctx->d_boxes); cudaFree(ctx->d_order); cudaFree(ctx->d_seq); cudaFree(ctx->d_probs);
-  cudaFree(ctx->d_results); cudaFree(ctx->d_script); cudaFree(ctx->d_cursor); cudaFree(ctx->d_queue); cudaFree(ctx->d_ws); cudaFree(ctx->d_kws[0]); cudaFree(ctx->d_kws[1]);
+  cudaFree(ctx->d_results); cudaFree(ctx->d_script); cudaFree(ctx->d_cursor); cudaFree(ctx->d_queue); cudaFree(ctx->d_ws);
+  for (int k = 0; k < GDP_NK; k++) cudaFree(ctx->d_kws[k]);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
-  if (ctx->evj) { cudaEventDestroy(ctx->evj); for (int a = 0; a < 2; a++) for (int b2 = 0; b2 < 2; b2++) cudaEventDestroy(ctx->evk[a][b2]); }
+  for (int k = 0; k < GDP_NK; k++) {
+    if (k > 0 && ctx->kstream[k]) cudaStreamDestroy(ctx->kstream[k]);
+    if (ctx->evj[k]) cudaEventDestroy(ctx->evj[k]);
+    if (ctx->evk[k][0]) cudaEventDestroy(ctx->evk[k][0]);
+    if (ctx->evk[k][1]) cudaEventDestroy(ctx->evk[k][1]);
+  }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1146,20 +1300,20 @@ static double box_work (const gmapdp_box &b) {
   if (b.mode == GMAPDP_SINGLE) return (double) (b.rlenL + 32) * (double) (std::min((int) b.glenL + 1,32 + b.lbandL + b.ubandL) + 31);
   double w = (double) (b.rlenL + 32) * (64 + b.ubandL) + (double) (b.glenL + 32) * (64 + b.lbandL);
   if (b.mode == GMAPDP_GENOME) w = 2 * w + (double) b.rlenL * 3 * (b.lbandL + b.ubandL + b.lbandR + b.ubandR);
-  if (b.mode == GMAPDP_CDNA) w = 2 * w + 0.5 * (double) b.glenL * b.glenL * (b.lbandL + b.ubandL) * (b.lbandR + b.ubandR) * 0.25;
+  if (b.mode == GMAPDP_CDNA) w = 2 * w + (double) b.glenL * (b.lbandL + b.ubandL) * (b.lbandR + b.ubandR) * 0.25;
   return w;
 }
 
 /* geometry, sorting and device allocations of a batch (no copies).  `order' receives the box ids of
    every chunk [chunk_begin[k], chunk_begin[k+1]) sorted by decreasing work. */
-/* Sort key: kind (full boxes first, then the E-only modes), then decreasing work (LPT). */
+/* Sort key: kind (single, end, genome, cdna), then decreasing work (LPT). */
 static inline void sort_chunk (std::vector<std::pair<double,int> > &work, int b0, int b1) {
   std::sort(work.begin() + b0,work.begin() + b1);
 }
 
 /* geometry and device allocations of a batch (no copies).  work[i] = (key, box id); within a chunk
-   the sorted order lists the single-gap boxes first (key offset by -1e12) and chunk_nfull[k] counts them. */
-struct PlanScan { size_t ws_words[2], script_need; int maxcols[2]; };
+   the sorted order lists the boxes kind by kind (key offset by -1e12 per kind) and chunk_count[k][kind] counts them. */
+struct PlanScan { size_t ws_words[GDP_NK], script_need; int maxcols[GDP_NK]; };
 
 /* bytes a box makes the end-to-end path upload (sequences once, alt twins are shared; MaxEnt doubles) */
 static inline uint32_t box_upload_bytes (const gmapdp_box &x) {
@@ -1170,30 +1324,31 @@ static inline uint32_t box_upload_bytes (const gmapdp_box &x) {
 
 static int plan_scan (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, std::vector<std::pair<double,int> > &work,
 		      std::vector<uint32_t> *upload_bytes, PlanScan &ps) {
-  size_t ws_words[2] = {0,0}, script_need = 0; int maxcols[2] = {8,8};
+  size_t ws_words[GDP_NK] = {0,0,0,0}, script_need = 0; int maxcols[GDP_NK] = {8,8,8,8};
   work.resize(nboxes);
   if (upload_bytes) upload_bytes->resize(nboxes);
   {
     /* per-box geometry (workspace words, script bound, work estimate) is the host's serial cost in front of the
        first launch of the end-to-end path: spread it over a few threads for large batches */
-    struct Part { size_t ws[2], script; int cols[2]; bool bad; };
+    struct Part { size_t ws[GDP_NK], script; int cols[GDP_NK]; bool bad; };
     const int nthreads = (nboxes >= 65536) ? (int) std::min<unsigned>(8u,std::max(1u,std::thread::hardware_concurrency())) : 1;
     std::vector<Part> parts(nthreads);
     auto scan = [&](int t) {
       Part &pt = parts[t];
-      pt.ws[0] = pt.ws[1] = 0; pt.script = 0; pt.cols[0] = pt.cols[1] = 8; pt.bad = false;
+      for (int k = 0; k < GDP_NK; k++) { pt.ws[k] = 0; pt.cols[k] = 8; }
+      pt.script = 0; pt.bad = false;
       const int i0 = (int) ((long long) nboxes * t / nthreads), i1 = (int) ((long long) nboxes * (t + 1) / nthreads);
       for (int i = i0; i < i1; i++) {
 	const gmapdp_box &b = boxes[i];
 	if (b.rlenL < 0 || b.glenL < 0 || b.rlenR < 0 || b.glenR < 0 || b.open >= 0 || b.extend >= 0 || b.mode < 0 || b.mode > 4 ||
 	    (unsigned) b.mismatchtype > 3u) { pt.bad = true; return; }
-	const int kind = (b.mode == GMAPDP_SINGLE) ? 0 : 1;
+	const int kind = kind_of(b.mode);
 	pt.ws[kind] = std::max(pt.ws[kind],gdp_ws_words(b));
 	pt.script += (size_t) b.rlenL + b.glenL + 4;
 	if (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA) pt.script += (size_t) b.rlenR + b.glenR + 4;
 	if (b.mode == GMAPDP_SINGLE) pt.cols[0] = std::max(pt.cols[0],(int) b.glenL + 2);
-	else if (b.mode == GMAPDP_CDNA) pt.cols[1] = std::max(pt.cols[1],(int) b.glenL + 2);	/* M and Q tables: 2 words per column */
-	work[i] = std::make_pair(-box_work(b) - (kind == 0 ? 1e12 : 0.0),i);	/* box_work < 1e10: the offset keeps full precision */
+	else if (b.mode == GMAPDP_CDNA) pt.cols[3] = std::max(pt.cols[3],(int) b.glenL + 2);	/* M and Q tables: 2 words per column */
+	work[i] = std::make_pair(-box_work(b) - 1e12 * (GDP_NK - 1 - kind),i);	/* box_work < 1e10: the offset keeps full precision */
 	if (upload_bytes) (*upload_bytes)[i] = box_upload_bytes(b);
       }
     };
@@ -1205,29 +1360,27 @@ static int plan_scan (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, std:
     }
     for (const Part &pt : parts) {
       if (pt.bad) { ctx->err = "bad box"; return GMAPDP_ERR_ARG; }
-      for (int kind = 0; kind < 2; kind++) { ws_words[kind] = std::max(ws_words[kind],pt.ws[kind]); maxcols[kind] = std::max(maxcols[kind],pt.cols[kind]); }
+      for (int kind = 0; kind < GDP_NK; kind++) { ws_words[kind] = std::max(ws_words[kind],pt.ws[kind]); maxcols[kind] = std::max(maxcols[kind],pt.cols[kind]); }
       script_need += pt.script;
     }
   }
-  ps.ws_words[0] = ws_words[0]; ps.ws_words[1] = ws_words[1]; ps.script_need = script_need;
-  ps.maxcols[0] = maxcols[0]; ps.maxcols[1] = maxcols[1];
+  for (int k = 0; k < GDP_NK; k++) { ps.ws_words[k] = ws_words[k]; ps.maxcols[k] = maxcols[k]; }
+  ps.script_need = script_need;
   return GMAPDP_OK;
 }
 
 static int plan_finish (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, size_t seqbytes, size_t nprobs,
 			const std::vector<int> &chunk_begin, std::vector<int> &order, std::vector<std::pair<double,int> > &work,
 			bool sort_now, const PlanScan &ps) {
-  const size_t ws_words[2] = {ps.ws_words[0],ps.ws_words[1]}, script_need = ps.script_need;
-  const int maxcols[2] = {ps.maxcols[0],ps.maxcols[1]};
+  const size_t *ws_words = ps.ws_words, script_need = ps.script_need;
+  const int *maxcols = ps.maxcols;
   const int nchunks = (int) chunk_begin.size() - 1;
-  ctx->chunk_nfull.assign(nchunks,0);
-  int largest[2] = {0,0};
+  ctx->chunk_count.assign((size_t) nchunks * GDP_NK,0);
+  int largest[GDP_NK] = {0,0,0,0};
   for (int k = 0; k < nchunks; k++) {
-    int nfull = 0;
-    for (int i = chunk_begin[k]; i < chunk_begin[k+1]; i++) nfull += (boxes[i].mode == GMAPDP_SINGLE);
-    ctx->chunk_nfull[k] = nfull;
-    largest[0] = std::max(largest[0],nfull);
-    largest[1] = std::max(largest[1],chunk_begin[k+1] - chunk_begin[k] - nfull);
+    int *cnt = &ctx->chunk_count[(size_t) k * GDP_NK];
+    for (int i = chunk_begin[k]; i < chunk_begin[k+1]; i++) cnt[kind_of(boxes[i].mode)]++;
+    for (int kind = 0; kind < GDP_NK; kind++) largest[kind] = std::max(largest[kind],cnt[kind]);
   }
   order.resize(nboxes);
   if (sort_now) {
@@ -1237,22 +1390,25 @@ static int plan_finish (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, si
   ctx->script_need = script_need;
 
   /* persistent grids: as many blocks per SM as shared memory and registers allow, on every SM */
-  for (int kind = 0; kind < 2; kind++) {
+  ctx->grid = 0;
+  for (int kind = 0; kind < GDP_NK; kind++) {
     ctx->kws_words[kind] = (ws_words[kind] + 31) & ~(size_t) 31;
     ctx->ksmem_cols[kind] = (maxcols[kind] + 7) & ~7;
     size_t smem = (size_t) WARPS_PER_BLOCK * ctx->ksmem_cols[kind] * 8;
     if ((int) smem > ctx->max_smem) { ctx->err = "box too long for the shared-memory boundary rows"; return GMAPDP_ERR_ARG; }
     int occ = 0;
-    if (kind == 0) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<true>,BLOCK_THREADS,smem));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<false>,BLOCK_THREADS,smem));
+    if (kind == 0) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<0>,BLOCK_THREADS,smem));
+    else if (kind == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<1>,BLOCK_THREADS,smem));
+    else if (kind == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<2>,BLOCK_THREADS,smem));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<3>,BLOCK_THREADS,smem));
     occ = std::min(std::max(occ,1),8);
     int grid = ctx->sm_count * occ;
     int needed_blocks = (largest[kind] + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     ctx->kgrid[kind] = std::max(std::min(grid,needed_blocks),1);
     if (largest[kind] > 0 &&
 	grow(ctx,&ctx->d_kws[kind],&ctx->cap_kws[kind],(size_t) ctx->kgrid[kind] * WARPS_PER_BLOCK * ctx->kws_words[kind])) return GMAPDP_ERR_CUDA;
+    if (largest[kind] > 0) ctx->grid += ctx->kgrid[kind];
   }
-  ctx->grid = ctx->kgrid[0] + ctx->kgrid[1];
 
   if (grow(ctx,&ctx->d_boxes,&ctx->cap_boxes,(size_t) nboxes)) return GMAPDP_ERR_CUDA;
   if (grow(ctx,&ctx->d_order,&ctx->cap_order,(size_t) nboxes)) return GMAPDP_ERR_CUDA;
@@ -1272,28 +1428,50 @@ static int plan_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, siz
   return plan_finish(ctx,boxes,nboxes,seqbytes,nprobs,chunk_begin,order,work,sort_now,ps);
 }
 
-/* launches the (up to) two kernels of one chunk: the full-fill kernel on `stream', the E-only kernel on
-   `stream2'; both must already be ordered after the chunk's uploads */
-static int launch_chunk (gmapdp_ctx *ctx, int first, int nfull, int ntri, bool timed = false) {
-  for (int kind = 0; kind < 2; kind++) {
-    const int count = kind == 0 ? nfull : ntri;
-    if (timed) ctx->last_ms[kind] = 0.f;
+/* launches the (up to) four kernels of one chunk, each on its own stream (kstream[0] == stream); all four
+   streams must already be ordered after the chunk's uploads.  cnt[kind] boxes of each kind, laid out kind
+   by kind in `order' from `first'. */
+static int launch_chunk (gmapdp_ctx *ctx, int first, const int *cnt, bool timed = false) {
+  static const bool serial = getenv("GMAPDP_SERIAL") != NULL;	/* diagnostics: all kernels on one stream */
+  static const char *korder = getenv("GMAPDP_ORDER") ? getenv("GMAPDP_ORDER") : "2130";	/* launch order of the kinds: the E-only kernels first, the single-gap kernel fills in as they drain (co-resident kernels of different kinds slow each other down) */
+  int start[GDP_NK], acc = first;
+  for (int kind = 0; kind < GDP_NK; kind++) { start[kind] = acc; acc += cnt[kind]; if (timed) ctx->last_ms[kind] = 0.f; }
+  for (int q = 0; q < GDP_NK; q++) {
+    const int kind = (korder[q] - '0') & 3;
+    const int count = cnt[kind];
     if (count == 0) continue;
-    cudaStream_t st = kind == 0 ? ctx->stream : ctx->stream2;
+    cudaStream_t st = serial ? ctx->stream : ctx->kstream[kind];
     KernelArgs ka;
-    ka.boxes = ctx->d_boxes; ka.order = ctx->d_order + first + (kind == 0 ? 0 : nfull); ka.nboxes = count;
+    ka.boxes = ctx->d_boxes; ka.order = ctx->d_order + start[kind]; ka.nboxes = count;
     ka.seq = ctx->d_seq; ka.probs = ctx->d_probs; ka.results = ctx->d_results;
     ka.script = ctx->d_script; ka.script_cap = ctx->cap_script; ka.script_cursor = ctx->d_cursor;
     ka.queue = ctx->d_queue + kind; ka.ws = ctx->d_kws[kind]; ka.ws_words = ctx->kws_words[kind];
     ka.smem_cols = ctx->ksmem_cols[kind]; ka.tables = ctx->d_tables;
     const size_t smem = (size_t) WARPS_PER_BLOCK * ctx->ksmem_cols[kind] * 8;
+    const int grid = std::max(1,std::min(ctx->kgrid[kind],(count + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
     CK(cudaMemsetAsync(ctx->d_queue + kind,0,sizeof(int),st));
     if (timed) CK(cudaEventRecord(ctx->evk[kind][0],st));
-    if (kind == 0) gmapdp_dp_kernel<true><<<ctx->kgrid[0],BLOCK_THREADS,smem,st>>>(ka);
-    else gmapdp_dp_kernel<false><<<ctx->kgrid[1],BLOCK_THREADS,smem,st>>>(ka);
+    if (kind == 0) gmapdp_dp_kernel<0><<<grid,BLOCK_THREADS,smem,st>>>(ka);
+    else if (kind == 1) gmapdp_dp_kernel<1><<<grid,BLOCK_THREADS,smem,st>>>(ka);
+    else if (kind == 2) gmapdp_dp_kernel<2><<<grid,BLOCK_THREADS,smem,st>>>(ka);
+    else gmapdp_dp_kernel<3><<<grid,BLOCK_THREADS,smem,st>>>(ka);
     CK(cudaGetLastError());
     if (timed) CK(cudaEventRecord(ctx->evk[kind][1],st));
     ctx->launches++;
+  }
+  return GMAPDP_OK;
+}
+
+/* fork: the other kernel streams start after an event on `stream' */
+static int fork_streams (gmapdp_ctx *ctx, cudaEvent_t ev) {
+  for (int k = 1; k < GDP_NK; k++) CK(cudaStreamWaitEvent(ctx->kstream[k],ev,0));
+  return GMAPDP_OK;
+}
+/* join: `stream' continues after everything queued on the other kernel streams */
+static int join_streams (gmapdp_ctx *ctx) {
+  for (int k = 1; k < GDP_NK; k++) {
+    CK(cudaEventRecord(ctx->evj[k],ctx->kstream[k]));
+    CK(cudaStreamWaitEvent(ctx->stream,ctx->evj[k],0));
   }
   return GMAPDP_OK;
 }
@@ -1321,27 +1499,36 @@ extern "C" int gmapdp_run_resident (gmapdp_ctx *ctx, float *kernel_ms) {
   CK(cudaSetDevice(ctx->device));
   if (kernel_ms) *kernel_ms = 0.f;
   if (ctx->nboxes == 0) return GMAPDP_OK;
-  const int nfull = ctx->chunk_nfull.empty() ? 0 : ctx->chunk_nfull[0];
+  if (ctx->chunk_count.size() < GDP_NK) return GMAPDP_OK;
+  const int *cnt = &ctx->chunk_count[0];
   CK(cudaMemsetAsync(ctx->d_cursor,0,sizeof(unsigned long long),ctx->stream));
-  /* fork: stream2 starts after ev0; join: ev1 is recorded on `stream' after stream2's kernel has finished */
+  /* fork: the other kernel streams start after ev0; join: ev1 is recorded on `stream' after their kernels have finished */
   CK(cudaEventRecord(ctx->ev0,ctx->stream));
-  CK(cudaStreamWaitEvent(ctx->stream2,ctx->ev0,0));
-  int rc = launch_chunk(ctx,0,nfull,ctx->nboxes - nfull,true);
+  int rc = fork_streams(ctx,ctx->ev0);
   if (rc) return rc;
-  CK(cudaEventRecord(ctx->evj,ctx->stream2));
-  CK(cudaStreamWaitEvent(ctx->stream,ctx->evj,0));
+  rc = launch_chunk(ctx,0,cnt,true);
+  if (rc) return rc;
+  rc = join_streams(ctx);
+  if (rc) return rc;
   CK(cudaEventRecord(ctx->ev1,ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms,ctx->ev0,ctx->ev1));
-  if (nfull > 0) CK(cudaEventElapsedTime(&ctx->last_ms[0],ctx->evk[0][0],ctx->evk[0][1]));
-  if (ctx->nboxes - nfull > 0) CK(cudaEventElapsedTime(&ctx->last_ms[1],ctx->evk[1][0],ctx->evk[1][1]));
+  for (int kind = 0; kind < GDP_NK; kind++)
+    if (cnt[kind] > 0) CK(cudaEventElapsedTime(&ctx->last_ms[kind],ctx->evk[kind][0],ctx->evk[kind][1]));
   return GMAPDP_OK;
 }
 
-/* CUDA-event durations of the two kernels of the last gmapdp_run_resident (they overlap in time) */
+/* CUDA-event durations of the kernels of the last gmapdp_run_resident (they overlap in time):
+   full_ms = the single-gap kernel, tri_ms = the longest of the three E-only kernels */
 extern "C" int gmapdp_last_kernel_ms (const gmapdp_ctx *ctx, float *full_ms, float *tri_ms) {
   if (full_ms) *full_ms = ctx->last_ms[0];
-  if (tri_ms) *tri_ms = ctx->last_ms[1];
+  if (tri_ms) *tri_ms = std::max(ctx->last_ms[1],std::max(ctx->last_ms[2],ctx->last_ms[3]));
+  return GMAPDP_OK;
+}
+
+/* the same per kind: ms[0..3] = single, end, genome, cdna */
+extern "C" int gmapdp_last_kernel_ms4 (const gmapdp_ctx *ctx, float *ms) {
+  for (int kind = 0; kind < GDP_NK; kind++) ms[kind] = ctx->last_ms[kind];
   return GMAPDP_OK;
 }
 
@@ -1408,8 +1595,9 @@ extern "C" int gmapdp_run_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int n
     cudaEvent_t e; CK(cudaEventCreateWithFlags(&e,cudaEventDisableTiming)); ctx->chunk_events.push_back(e);
   }
   CK(cudaMemsetAsync(ctx->d_cursor,0,sizeof(unsigned long long),ctx->stream));
-  CK(cudaEventRecord(ctx->evj,ctx->stream));
-  CK(cudaStreamWaitEvent(ctx->stream2,ctx->evj,0));
+  CK(cudaEventRecord(ctx->evj[0],ctx->stream));
+  rc = fork_streams(ctx,ctx->evj[0]);
+  if (rc) return rc;
   for (int k = 0; k < nchunks; k++) {
     const int b0 = chunk_begin[k], n = chunk_begin[k+1] - b0;
     cudaStream_t cs = ctx->copy_stream;
@@ -1433,15 +1621,13 @@ extern "C" int gmapdp_run_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int n
     if (phi > plo && plo != (size_t) -1)
       CK(cudaMemcpyAsync(ctx->d_probs + plo,probpool + plo,(phi - plo) * sizeof(double),cudaMemcpyHostToDevice,cs));
     CK(cudaEventRecord(ctx->chunk_events[k],cs));
-    CK(cudaStreamWaitEvent(ctx->stream,ctx->chunk_events[k],0));
-    CK(cudaStreamWaitEvent(ctx->stream2,ctx->chunk_events[k],0));
-    rc = launch_chunk(ctx,b0,ctx->chunk_nfull[k],n - ctx->chunk_nfull[k]);
+    for (int kk = 0; kk < GDP_NK; kk++) CK(cudaStreamWaitEvent(ctx->kstream[kk],ctx->chunk_events[k],0));
+    rc = launch_chunk(ctx,b0,&ctx->chunk_count[(size_t) k * GDP_NK]);
     if (rc) return rc;
     if (k == 0) lap("first chunk launched");
   }
   lap("all chunks launched");
-  CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream2));
+  for (int kk = 0; kk < GDP_NK; kk++) CK(cudaStreamSynchronize(ctx->kstream[kk]));
   CK(cudaStreamSynchronize(ctx->copy_stream));
   lap("kernels done");
   rc = gmapdp_download(ctx,results,script,script_cap,script_used);

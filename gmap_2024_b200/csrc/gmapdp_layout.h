@@ -89,12 +89,15 @@ GDP_HD FGeom fgeom (int rlen, int glen, int lband, int uband) {
 }
 
 GDP_HD size_t gdp_align4 (size_t x) { return (x + 3) & ~(size_t) 3; }
+GDP_HD size_t gdp_align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
 
 /* words of per-warp workspace one box needs */
 GDP_HD size_t gdp_ws_words (const gmapdp_box &b) {
   size_t w = 0;
   /* class-code arrays (bytes): step-axis codes for both sides, query and genome; dinucleotide arrays */
-  size_t bytes = gdp_align4(b.rlenL + 2) + gdp_align4(b.rlenR + 2) + 2 * gdp_align4(b.glenL + 2) + 2 * gdp_align4(b.glenR + 2);
+  size_t bytes = gdp_align16(b.rlenL + 2) + gdp_align16(b.rlenR + 2) + 2 * gdp_align16(b.glenL + 2) + 2 * gdp_align16(b.glenR + 2);
+  /* ready-made PRMT selectors (uint16) of the same positions, read 16 at a time by the interior steps of the E-only fills */
+  bytes += gdp_align16(2 * (size_t) (b.rlenL + 2)) + gdp_align16(2 * (size_t) (b.rlenR + 2)) + gdp_align16(2 * (size_t) (b.glenL + 2)) + gdp_align16(2 * (size_t) (b.glenR + 2));
   w += bytes / 4;
   /* script staging */
   w += (size_t) (b.rlenL + b.glenL + b.rlenR + b.glenR + 16);

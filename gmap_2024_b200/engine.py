@@ -34,7 +34,7 @@ def load_library():
     if _lib is None:
         if not os.path.exists(LIB):
             raise EngineError("native library %s is missing: run __graft_entry__.build() (nvcc, sm_100a)" % LIB)
-        lib = C.CDLL(LIB)
+        lib = C.CDLL(os.environ.get("GMAPDP_LIB", LIB))	# GMAPDP_LIB: tuning builds of the same sources
         lib.gmapdp_last_error.restype = C.c_char_p
         lib.gmapdp_launch_count.restype = C.c_long
         lib.GmapDP_batch_new.restype = C.c_void_p
@@ -86,6 +86,12 @@ class Engine:
         a, b = C.c_float(), C.c_float()
         self.lib.gmapdp_last_kernel_ms(self.ctx, C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def last_kernel_ms4(self):
+        """per-kind kernel ms of the last resident run: single, end, genome, cdna"""
+        ms = (C.c_float * 4)()
+        self.lib.gmapdp_last_kernel_ms4(self.ctx, ms)
+        return [float(x) for x in ms]
 
     def device_info(self):
         sm, grid, bt = C.c_int(), C.c_int(), C.c_int()
