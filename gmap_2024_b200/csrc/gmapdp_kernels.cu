@@ -69,7 +69,7 @@ struct BestTrack { int bs, bk; };
 struct TriFill {
   int nA, nB, band, lane0, pass0, npass;
   int lateadd;			/* 1: ties go to the gap (jump late, >=), 0: > */
-  bool lower;
+  bool lower, right;
   const uint2 *prof;		/* [0..nA] 8-byte score profiles of the lane-axis positions */
   const uint8_t *code;		/* [0..nB] class codes of the step-axis positions (class | alt class << 4) */
   const uint16_t *sel;		/* [0..nB] the same as ready-made PRMT selectors (no alt genome), 16-byte aligned */
@@ -120,7 +120,61 @@ __device__ void tri_profiles (const TriFill &f, const SideSeq &sd, int mt, bool 
  * around one direction word, the column's score is ONE PRMT with a ready-made selector (16 selectors arrive
  * in two 16-byte loads), loads use immediate offsets, the tie rule is a template parameter when the fills of
  * the pass agree on it, and the best-endpoint search keeps (score, step) instead of (score, key). */
+/* Genome gaps: the splice-site bridge (bridge_intron_gap_{8,16}_site_level, dynprog_genome.c:866-1386) is evaluated
+ * INSIDE the fills.  Every candidate of the reference's scan pairs one cell (row, col) of one of the four matrices
+ * with the main-diagonal cell of the opposite side on the partner row rP = rlength - row:
+ *   score = H(row,col) + intron score(dinucleotide at col on this side, at rP on the other) + diagonal score of the other side at rP
+ * The two diagonals are computed beforehand (a sequential clamp-add scan, one lane per side), so a cell is
+ * scored the moment the fill produces it and no score plane is written or read back.  "Higher score, then
+ * higher probability sum, then first in scan order" is an argmax: every lane keeps its own best under that
+ * order and the lanes are combined at the end.  key = rL << 15 | segment << 12 | col orders the candidates as
+ * the reference visits them (segment: 0 diagonal, 1 / 2 right lower / upper, 3 / 4 left lower / upper).
+ * The probability sum (two doubles) matters only between candidates that tie on the score: inside the fills a lane
+ * just appends the key of a candidate that ties with its current best to a small per-lane list (a predicated
+ * store: the steps stay branch-free) and restarts the list on a strict improvement; the list is resolved once,
+ * after the fills, and only for the lanes that reached the warp's best score (flat stretches far from the splice
+ * site tie all the time, but cannot win).  If the list of such a lane overflowed (long runs of equal best scores:
+ * low-complexity sequence) the warp repeats the fills with every tie resolved on the spot (gen_tie). */
+#define GEN_TIECAP 8
+struct GenBest { int s, key, cnt; double p; uint32_t *ties; };	/* p < 0: not fetched yet; ties[j * 32]: j-th tied key of this lane */
+struct GenCtx {
+  const uint8_t *ldi, *rdi;		/* dinucleotide classes per genomic position */
+  const short *dgL, *dgR;		/* main-diagonal scores of the upper fills */
+  const double *lp, *rp;
+  int rlength, lim;
+  uint32_t it0, it1;			/* intron scores as a byte table: byte k+1 = score of bit k, byte 0 = 0 */
+};
+
+__device__ __forceinline__ int gen_points (const GenCtx &g, int di) {
+  uint32_t pos, d;
+  asm("bfind.u32 %0, %1;" : "=r"(pos) : "r"(di));		/* 0xffffffff if di == 0 */
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(g.it0), "r"(g.it1), "r"((pos + 1u) & 7u));
+  return (int) d;
+}
+
+/* probability sum of the candidate behind a key */
+__device__ __forceinline__ double gen_key_prob (const GenCtx &g, int key) {
+  const int rL = key >> 15, seg = (key >> 12) & 7, col = key & 4095;
+  if (seg == 0) return g.lp[rL] + g.rp[g.rlength - rL];
+  if (seg <= 2) return g.lp[rL] + g.rp[col];
+  return g.lp[col] + g.rp[g.rlength - rL];
+}
+
+__device__ __forceinline__ void gen_tie (const GenCtx &g, GenBest &b, int key) {	/* same score as the lane's best */
+  if (b.key < 0) {				/* nothing yet: the reference takes a candidate only if its probability sum is > 0 */
+    const double pc = gen_key_prob(g,key);
+    if (pc > 0.0) { b.key = key; b.p = pc; }
+    return;
+  }
+  const double pc = gen_key_prob(g,key);
+  if (b.p < 0.0) b.p = gen_key_prob(g,b.key);
+  if (pc > b.p || (pc == b.p && key < b.key)) { b.key = key; b.p = pc; }
+}
+
 struct TriLane {
+  /* genome gaps: this lane's side of the bridge */
+  const uint8_t *own_di, *oth_di; const short *oth_dg;
+  int ev_lo, ev_hi, key0, kstep; bool ev_ok;
   int d, tstart, tend, lateadd;
   bool isd0, lower, edge_in, edge_out, trk;
   const uint2 *pp;			/* pp[t] = prof[t - d] */
@@ -143,9 +197,11 @@ __device__ __forceinline__ int sext_lo16 (uint32_t w) {
 }
 
 /* LM: tie rule of the pass's fills -- 0 all `>' (jump early), 1 all `>=' (jump late), 2 per lane */
-template <bool SCORES, bool TRACK, int LM>
+/* MODE: 0 end gaps (endpoint search), 1 cdna gaps (score planes for the bridge), 2 genome gaps (bridge inside the fill) */
+template <int MODE, int LM>
 __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, const int open, const int extend, const int NEG,
-					  const int POS, const uint32_t negpair, BestTrack *bt) {
+					  const int POS, const uint32_t negpair, BestTrack *bt, const GenCtx *gc, GenBest *gb) {
+  constexpr bool SCORES = (MODE == 1), TRACK = (MODE == 0), EVAL = (MODE == 2);
   const uint2 *pq = s.pp + t;
   const uint4 *sq = reinterpret_cast<const uint4 *>(s.sel + t);
   const int la = s.lateadd;
@@ -155,6 +211,16 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
   uint32_t *dplane = s.dplane, *splane = s.splane;
   int bs = 0, btt = -1;
   if (TRACK) bs = bt->bs;
+  /* genome gaps: col advances with t, the partner row goes down */
+  const uint8_t *odi = NULL, *pdi = NULL; const short *pdg = NULL;
+  int key = 0;
+  GenBest g; g.s = 0; g.key = -1; g.cnt = 0; g.p = 0.0; g.ties = NULL;
+  if (EVAL) {
+    g = *gb;
+    const int col = s.lower ? t - s.d : t, rP = gc->rlength - (s.lower ? t : t - s.d);
+    odi = s.own_di + col; pdi = s.oth_di + rP; pdg = s.oth_dg + rP;
+    key = s.key0 + t * s.kstep;
+  }
   for (; t + 16 <= tstop; t += 16) {
     const uint4 s0 = sq[0], s1 = sq[1];
     const uint32_t sw[8] = {s0.x,s0.y,s0.z,s0.w,s1.x,s1.y,s1.z,s1.w};
@@ -185,12 +251,22 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
 	const bool up = s.trk && ((LM == 0) ? (Hn > bs) : ((LM == 1) ? (Hn >= bs) : (Hn + la > bs)));
 	bs = up ? Hn : bs; btt = up ? t + u : btt;
       }
+      if (EVAL) {
+	const int tot = Hn + gen_points(*gc,(int) odi[u] & (int) pdi[-u]) + (int) pdg[-u];
+	const int ku = key + u * s.kstep;
+	const bool gt = s.ev_ok && tot > g.s, eq = s.ev_ok && tot == g.s;
+	if (eq && g.cnt < GEN_TIECAP) g.ties[g.cnt * 32] = (uint32_t) ku;
+	g.cnt = gt ? 0 : g.cnt + (eq ? 1 : 0);
+	g.key = gt ? ku : g.key; g.s = gt ? tot : g.s;
+      }
       H = Hn;
     }
     pq += 16; sq += 2;
+    if (EVAL) { odi += 16; pdi -= 16; pdg -= 16; key += 16 * s.kstep; }
     *dplane = isd0 ? 0u : dacc; dplane += 32;
   }
   s.Hprev = H; s.H = H; s.pk_out = pk_out; s.dplane = dplane; s.splane = splane;
+  if (EVAL) *gb = g;
   if (TRACK) {
     if (btt >= 0) {
       const int i = btt - s.d;
@@ -200,15 +276,18 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
   }
 }
 
-template <bool SCORES, bool TRACK, bool WIDE>
+template <int MODE, bool WIDE>
 __device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
-			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok) {
+			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok, const GenCtx *gc, GenBest *gb,
+			  bool ev_now) {
+  constexpr bool SCORES = (MODE == 1), TRACK = (MODE == 0), EVAL = (MODE == 2);
   const int lane = threadIdx.x & 31;
   /* lane configuration */
   TriLane s;
   int nA = -1, nB = -1, thi = -1, tlo = 0x7fffffff;
   int maxstart = 0, minend = 0x7fffffff, lm = -1;
   s.d = -1; s.lateadd = 0; s.lower = false; s.edge_in = false; s.edge_out = false;
+  s.ev_ok = false; s.ev_lo = 0x7fffffff; s.ev_hi = -1; s.key0 = 0; s.kstep = 0; s.own_di = NULL; s.oth_di = NULL; s.oth_dg = NULL;
   const uint2 *prof = NULL; s.code = NULL; s.sel = NULL;
   const uint2 *prof0 = NULL; const uint16_t *sel0 = NULL;
   s.dplane = NULL; s.splane = NULL;
@@ -230,6 +309,20 @@ __device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, in
 	prof = F[f].prof; s.code = F[f].code; s.sel = F[f].sel;
 	s.edge_in = WIDE && (p > 0 && lane == 0);
 	s.edge_out = WIDE && (p + 1 < F[f].npass && lane == 31);
+	if (EVAL) {
+	  const bool right = F[f].right, lower = F[f].lower;
+	  const int rlength = gc->rlength, glen = lower ? F[f].nA : F[f].nB;
+	  s.own_di = right ? gc->rdi : gc->ldi; s.oth_di = right ? gc->ldi : gc->rdi; s.oth_dg = right ? gc->dgL : gc->dgR;
+	  /* the reference's scan ranges: not the main diagonal, not the top edge of the band, inside the offset
+	     limit (col + partner col < lim: constant along a diagonal), rows 1 .. rlength-1, columns 1 .. glength-2 */
+	  s.ev_ok = dd >= 1 && (lower || dd <= F[f].band - 1) && ((lower ? rlength - dd : rlength + dd) < gc->lim);
+	  s.ev_lo = dd + 1; s.ev_hi = lower ? rlength - 1 : min(rlength - 1 + dd,glen - 2);
+	  const int seg = right ? (lower ? 1 : 2) : (lower ? 3 : 4);
+	  /* key(t) = rL * 32768 + seg * 4096 + col, with row = lower ? t : t - dd, col = lower ? t - dd : t */
+	  const int row0 = lower ? 0 : -dd, col0 = lower ? -dd : 0;
+	  s.key0 = (right ? rlength - row0 : row0) * 32768 + seg * 4096 + col0;
+	  s.kstep = right ? 1 - 32768 : 1 + 32768;
+	}
       }
     }
   }
@@ -239,7 +332,10 @@ __device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, in
   s.tstart = (s.d >= 0) ? s.d : 0x7fffffff; s.tend = (s.d >= 0) ? min(nA + s.d,nB) : -1;
   s.isd0 = (s.d <= 0);
   s.pp = prof - s.d;
-  if (s.d < 0) { s.pp = prof0; s.sel = sel0; }		/* idle lanes of the interior steps read (and discard) a valid diagonal */
+  if (s.d < 0) {					/* idle lanes of the interior steps read (and discard) a valid diagonal */
+    s.pp = prof0; s.sel = sel0;
+    if (EVAL) { s.own_di = gc->ldi; s.oth_di = gc->rdi; s.oth_dg = gc->dgR; s.lower = true; s.d = -1; }
+  }
   s.trk = TRACK && s.d >= 0 && (!s.lower || s.d > 0) && !lastrow;
   const uint32_t negpair = ((uint32_t) NEG & 0xffffu) | ((uint32_t) NEG << 16);
 
@@ -248,6 +344,7 @@ __device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, in
 
   /* interior steps [F0, F1): F0 a multiple of 16 past every lane's start, F1 before any lane's last step */
   int F0 = (maxstart + 1 + 15) & ~15, F1 = F0;
+  if (EVAL) minend -= 1;				/* keeps the interior steps inside columns <= glength - 2 */
   if (!WIDE && fastok) while (F1 + 16 <= minend) F1 += 16;
   const bool hasfast = (F1 > F0);
 
@@ -290,6 +387,18 @@ __device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, in
 	      if (s.H > bt->bs || (s.H == bt->bs && (s.lateadd ? key > bt->bk : key < bt->bk))) { bt->bs = s.H; bt->bk = key; }
 	    }
 	  }
+	  if (EVAL) {
+	    if (s.ev_ok && tc >= s.ev_lo && tc <= s.ev_hi) {
+	      const int col = s.lower ? tc - s.d : tc, rP = gc->rlength - (s.lower ? tc : tc - s.d);
+	      const int tot = s.H + gen_points(*gc,(int) s.own_di[col] & (int) s.oth_di[rP]) + (int) s.oth_dg[rP];
+	      const int kt = s.key0 + tc * s.kstep;
+	      if (tot > gb->s) { gb->s = tot; gb->key = kt; gb->p = -1.0; gb->cnt = 0; }
+	      else if (tot == gb->s) {
+		if (ev_now) gen_tie(*gc,*gb,kt);
+		else { if (gb->cnt < GEN_TIECAP) gb->ties[gb->cnt * 32] = (uint32_t) kt; gb->cnt++; }
+	      }
+	    }
+	  }
 	}
 	s.dacc |= bits << (2 * (tc & 15));
 	if (SCORES) s.sacc |= ((uint32_t) s.H & 0xffffu) << (16 * u);
@@ -298,9 +407,9 @@ __device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, in
       if ((t & 15) == 14) { *s.dplane = s.dacc; s.dplane += 32; s.dacc = 0; }
     }
     if (phase == 0 && hasfast) {
-      if (lm == 0) tri_fast<SCORES,TRACK,0>(s,t,F1,open,extend,NEG,POS,negpair,bt);
-      else if (lm == 1) tri_fast<SCORES,TRACK,1>(s,t,F1,open,extend,NEG,POS,negpair,bt);
-      else tri_fast<SCORES,TRACK,2>(s,t,F1,open,extend,NEG,POS,negpair,bt);
+      if (lm == 0) tri_fast<MODE,0>(s,t,F1,open,extend,NEG,POS,negpair,bt,gc,gb);
+      else if (lm == 1) tri_fast<MODE,1>(s,t,F1,open,extend,NEG,POS,negpair,bt,gc,gb);
+      else tri_fast<MODE,2>(s,t,F1,open,extend,NEG,POS,negpair,bt,gc,gb);
     } else break;
   }
   if (((thi & ~1) & 15) != 14) *s.dplane = s.dacc;
@@ -308,15 +417,16 @@ __device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, in
 }
 
 /* all passes of a box's E-only fills */
-template <bool SCORES, bool TRACK>
+template <int MODE>
 __device__ void tri_fill_all (const TriFill (&F)[GDP_MAXFILLS], int nf, int npasses, int open, int extend, int NEG, int POS,
-			      BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok) {
+			      BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok, const GenCtx *gc, GenBest *gb,
+			      bool ev_now = false) {
   bool wide = false;
 #pragma unroll
   for (int f = 0; f < GDP_MAXFILLS; f++) if (f < nf && F[f].npass > 1) wide = true;
   for (int pass = 0; pass < npasses; pass++) {
-    if (wide) tri_pass<SCORES,TRACK,true>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,false);
-    else tri_pass<SCORES,TRACK,false>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok);
+    if (wide) tri_pass<MODE,true>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,false,gc,gb,ev_now);
+    else tri_pass<MODE,false>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok && !ev_now,gc,gb,ev_now);
   }
 }
 
@@ -448,6 +558,52 @@ __device__ __forceinline__ uint32_t full_fast (FullLane &st, const bool isl0, co
   return (tV ? 2u : (dNh ? 1u : 0u)) | (dE ? 4u : 0u) | (dF ? 8u : 0u);
 }
 
+/* general step, branch-free: any lane may be inactive (before its first / after its last column, past the
+   last row), outside the band or on one of its edges -- everything full_edge handles except column 0.  Same
+   arithmetic as full_edge, with the cases turned into predicates: dd = c - r locates the lane in the band
+   (bottom edge dd == -lband, top edge dd == uband), `first' = the stripe starts at row 0, cF = rlo + uband =
+   the first column whose vertical-gap carry from the previous stripe is out of reach. */
+template <bool LATE, bool ALT>
+__device__ __forceinline__ uint32_t full_gen (FullLane &st, const bool isl0, const bool isl31, const int c, const int dd, const bool act,
+					      const bool first, const int cF, const int lband, const int uband,
+					      const int open, const int extend, const int NEG, const int POS,
+					      const uint32_t plo, const uint32_t p4, uint2 *bnd) {
+  const int cg_sh = __shfl_up_sync(FULLMASK,st.cg_out,1);
+  const uint32_t pk_sh = __shfl_up_sync(FULLMASK,st.pk_out,1);
+  uint2 e = make_uint2(0u,0u);
+  if (isl0 && act) e = bnd[c];
+  const int bH = sext_lo16(e.x);
+  const bool carry = !first && (c < cF);
+  const uint32_t field = isl0 ? (e.x >> 16) : (pk_sh >> 16);
+  const int Hs = isl0 ? (first ? NEG : st.bprevH) : st.diag;
+  const int cg_in = isl0 ? (carry ? (int) e.y : NEG32) : cg_sh;
+  const int last_in = isl0 ? (carry ? bH : NEG32) : sext_lo16(pk_sh);
+  /* E (horizontal gap), H */
+  const int T1 = max(st.Hl + open,NEG);
+  const bool dEr = LATE ? (st.E >= T1) : (st.E > T1);
+  const int En = max(max(st.E,T1) + extend,NEG);
+  const int Hd = clampi(Hs + field_score<ALT>(plo,p4,field),NEG,POS);
+  const bool dNr = LATE ? (En >= Hd) : (En > Hd);
+  const bool bottom = (dd == -lband), top = (dd == uband);
+  const bool doF = (dd < uband) && (dd >= -lband);		/* inside the band and not on its top edge */
+  int H = bottom ? Hd : max(Hd,En);
+  const bool dE = dEr && !bottom, dNh = dNr && !bottom;
+  /* F (vertical gap) */
+  const int score = last_in + open;
+  const bool dFr = LATE ? (cg_in >= score) : (cg_in > score);
+  const int cg = (dFr ? cg_in : score) + extend;
+  const bool tV = doF && (LATE ? (cg >= H) : (cg > H));
+  const bool dF = doF && dFr;
+  H = tV ? max(cg,NEG) : H;
+  const int cgo = top ? (NEG32 + open + extend) : (doF ? cg : st.cg_out);
+  const uint32_t pk = pack_lo16(H,(int) field);
+  if (act) { st.E = En; st.cg_out = cgo; st.diag = last_in; st.Hl = H; st.pk_out = pk; }
+  if (isl0 && act) st.bprevH = bH;
+  if (isl31 && act) bnd[c] = make_uint2(pk,(uint32_t) cgo);
+  const uint32_t nib = (tV ? 2u : (dNh ? 1u : 0u)) | (dE ? 4u : 0u) | (dF ? 8u : 0u);
+  return act ? nib : 0u;
+}
+
 template <bool LATE, bool ALT>
 __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int open, int extend,
 			   int NEG, int POS, uint32_t *dirs, const FGeom &fg, uint2 *bnd, const GdpTables *tb) {
@@ -511,10 +667,45 @@ __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int 
 	*dp = a8; dp += 32; bp += 8; tt += 8; c += 8; \
       } \
       while (tt <= fe) FAST_STEP(FIRSTFLAG); } while (0)
+#define GEN_ONE(U) full_gen<LATE,ALT>(st,isl0,isl31,c + (U),c + (U) - r,rowact && c + (U) >= c0 && c + (U) <= chigh,rlo == 0,rlo + uband, \
+				     lband,uband,open,extend,NEG,POS,plo,p4,bnd)
+#define GEN_STEPS(END) do { \
+      while (tt < (END) && (tt & 7)) { acc |= GEN_ONE(0) << (4 * (tt & 7)); if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; } tt++; c++; } \
+      while (tt + 8 <= (END)) { \
+	uint32_t a8 = 0; \
+	_Pragma("unroll") for (int u = 0; u < 8; u++) a8 |= GEN_ONE(u) << (4 * u); \
+	dst[(tt >> 3) * 32] = a8; tt += 8; c += 8; \
+      } \
+      while (tt < (END)) { acc |= GEN_ONE(0) << (4 * (tt & 7)); if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; } tt++; c++; } } while (0)
+    /* column 0 needs the literal step: it is reached only by the first 32 steps of a stripe with c0 == 0 */
+#ifndef GMAPDP_GEN_MODE
+#define GMAPDP_GEN_MODE 1
+#endif
+#if GMAPDP_GEN_MODE == 0
     const int e1 = min(fs,nsteps);
     while (tt < e1) EDGE_STEP();
     if (rlo == 0) FAST_CHUNKS(true); else FAST_CHUNKS(false);
     while (tt < nsteps) EDGE_STEP();
+#elif GMAPDP_GEN_MODE == 1
+    const int e0 = min((c0 >= 1) ? 0 : 32,nsteps);
+    while (tt < e0) EDGE_STEP();
+    const int e1 = min(fs,nsteps);
+    for (int seg = 0; seg < 2; seg++) {		/* one copy of the general step: before and after the interior steps */
+      const int gend = seg ? nsteps : e1;
+      _Pragma("unroll 1")
+      while (tt < gend) { acc |= GEN_ONE(0) << (4 * (tt & 7)); if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; } tt++; c++; }
+      if (seg == 0) { if (rlo == 0) FAST_CHUNKS(true); else FAST_CHUNKS(false); }
+    }
+#else
+    const int e0 = min((c0 >= 1) ? 0 : 32,nsteps);
+    while (tt < e0) EDGE_STEP();
+    const int e1 = min(fs,nsteps);
+    GEN_STEPS(e1);
+    if (rlo == 0) FAST_CHUNKS(true); else FAST_CHUNKS(false);
+    GEN_STEPS(nsteps);
+#endif
+#undef GEN_ONE
+#undef GEN_STEPS
 #undef EDGE_STEP
 #undef FAST_STEP
 #undef FAST_CHUNKS
@@ -686,111 +877,80 @@ __device__ __forceinline__ int intron_points (const int *isc, int ldi, int rdi) 
   return t ? isc[31 - __clz(t)] : 0;
 }
 
-/* bridge_intron_gap_{8,16}_site_level, dynprog_genome.c:866-1386.  Returns finalscore. */
-__device__ int bridge_genome (const gmapdp_box &b, const TriFill &LU, const TriFill &LL, const TriFill &RU,
-			      const TriFill &RL, const uint8_t *ldi, const uint8_t *rdi, const double *lp,
-			      const double *rp, int NEG, const int *isc, int *bestrL, int *bestrR, int *bestcL, int *bestcR) {
+/* Main-diagonal scores of the two upper fills (what the d == 0 lane of tri_pass computes: H(i,i) =
+   clamp(H(i-1,i-1) + score(i,i)), no gap can reach the diagonal): lane 0 scans the left side, lane 1 the right. */
+__device__ void gen_diagonals (const TriFill &LU, const TriFill &RU, short *dgL, short *dgR, int NEG, int POS) {
   const int lane = threadIdx.x & 31;
-  const int rlength = b.rlenL, glengthL = b.glenL, glengthR = b.glenR;
-  const int lbandL = b.lbandL, ubandL = b.ubandL, lbandR = b.lbandR, ubandR = b.ubandR;
-  const int lim = b.offdiff;		/* rightoffset - leftoffset */
-  Cand best, dn;			/* dn: best "with dinucleotide" candidate: p = prob sum, s = its score */
-  best.s = NEG; best.p = 0.0; best.ord = 0; best.rL = best.rR = best.cL = best.cR = 0;
-  dn = best; dn.p = 0.0;
+  if (lane < 2) {
+    const TriFill &f = lane ? RU : LU;
+    short *dg = lane ? dgR : dgL;
+    const int n = min(f.nA,f.nB);
+    int H = 0;
+    uint2 p = f.prof[0]; int cd = f.code[0];
+    for (int i = 0; i <= n; i++) {
+      const uint2 pc = p; const int cc = cd;
+      if (i < n) { p = f.prof[i + 1]; cd = f.code[i + 1]; }
+      H = clampi(H + max(prof_pick(pc.x,pc.y,cc & 15),prof_pick(pc.x,pc.y,cc >> 4)),NEG,POS);
+      dg[i] = (short) H;
+    }
+  }
+  __syncwarp();
+}
 
+/* bridge_intron_gap_{8,16}_site_level, dynprog_genome.c:866-1386, after the fills: the main-diagonal candidates
+   (cL = rL, cR = rR) and the best "with dinucleotide" candidate, the combination of the lanes' bests, and the
+   reference's choice between the two.  Returns finalscore. */
+__device__ int bridge_genome_finish (const gmapdp_box &b, const GenCtx &g, GenBest gb, int NEG, const int *isc,
+				     int *bestrL, int *bestrR, int *bestcL, int *bestcR) {
+  const int lane = threadIdx.x & 31;
+  const int rlength = g.rlength;
+  /* the keys that tied with this lane's best inside the fills */
+  {
+    const int n = min(gb.cnt,GEN_TIECAP);
+    for (int j = 0; j < n; j++) gen_tie(g,gb,(int) gb.ties[j * 32]);
+    gb.cnt = 0;
+  }
+  int dns = NEG, dnkey = -1; double dnp = 0.0;		/* best diagonal candidate with a dinucleotide pair: by probability sum */
   for (int rL = 1 + lane; rL < rlength; rL += 32) {
     const int rR = rlength - rL;
-    unsigned long long ord = ((unsigned long long) rL << 32) + 1;
-    int cloL = max(rL - lbandL,1), chighL = min(rL + ubandL,glengthL - 1);
-    int cloR = max(rR - lbandR,1), chighR = min(rR + ubandR,glengthR - 1);
-    int cL, cR, score, scoreL, scoreR, scoreI;
-    double probL, probR;
-/* a candidate matters only if its score reaches the running best: the probabilities (double loads and
-   an add) are fetched only then */
-#define CONSIDER(PL,PR) do { score = scoreL + scoreI + scoreR; ord++; \
-      if (score >= best.s) { \
-	const double ps_ = (PL) + (PR); \
-	if (score > best.s || ps_ > best.p) { \
-	  best.s = score; best.p = ps_; best.ord = ord; best.rL = rL; best.rR = rR; best.cL = cL; best.cR = cR; } } } while (0)
-
-    cL = rL; probL = lp[cL]; scoreL = tri_score(LU,rL,cL);
-    cR = rR; probR = rp[cR]; scoreR = tri_score(RU,rR,cR);
-    scoreI = intron_points(isc,ldi[cL],rdi[cR]);
-    CONSIDER(probL,probR);
-    if (scoreI > 0 && probL + probR > dn.p) {
-      dn.s = scoreL + scoreI + scoreR; dn.p = probL + probR; dn.ord = ord; dn.rL = rL; dn.rR = rR; dn.cL = cL; dn.cR = cR;
+    const int scoreI = gen_points(g,(int) g.ldi[rL] & (int) g.rdi[rR]);
+    const int score = (int) g.dgL[rL] + scoreI + (int) g.dgR[rR];
+    const int key = rL << 15;
+    if (score > gb.s) { gb.s = score; gb.key = key; gb.p = -1.0; }
+    else if (score == gb.s) gen_tie(g,gb,key);
+    if (scoreI > 0) {
+      const double ps = g.lp[rL] + g.rp[rR];
+      if (ps > dnp) { dns = score; dnp = ps; dnkey = key; }
     }
-    const int ldiL = ldi[cL];
-    const int scoreRdiag = scoreR;
-    const double probLdiag = probL, probRdiag = probR;
-
-    /* The four scans below visit their candidates in the reference's order; the score and dinucleotide
-       loads of four consecutive candidates are issued together so that their latencies overlap. */
-
-    /* indel on right: cL = rL fixed */
-    {
-      const int ldiX_ = ldiL;
-      const int endlo = min(rR,lim - cL), endhi = min(chighR,lim - cL);
-      for (int base_ = cloR; base_ < endlo; base_ += 4) {
-	int s4_[4], d4_[4];
-#pragma unroll
-	for (int u_ = 0; u_ < 4; u_++) { const int cc = min(base_ + u_,endlo - 1); s4_[u_] = tri_score(RL,cc,rR); d4_[u_] = rdi[cc]; }
-#pragma unroll
-	for (int u_ = 0; u_ < 4; u_++) if (base_ + u_ < endlo) {
-	  cR = base_ + u_; scoreR = s4_[u_]; scoreI = intron_points(isc,ldiX_,d4_[u_]); CONSIDER(probLdiag,rp[cR]); }
-      }
-      for (int base_ = rR + 1; base_ < endhi; base_ += 4) {
-	int s4_[4], d4_[4];
-#pragma unroll
-	for (int u_ = 0; u_ < 4; u_++) { const int cc = min(base_ + u_,endhi - 1); s4_[u_] = tri_score(RU,rR,cc); d4_[u_] = rdi[cc]; }
-#pragma unroll
-	for (int u_ = 0; u_ < 4; u_++) if (base_ + u_ < endhi) {
-	  cR = base_ + u_; scoreR = s4_[u_]; scoreI = intron_points(isc,ldiX_,d4_[u_]); CONSIDER(probLdiag,rp[cR]); }
-      }
-    }
-    /* indel on left: cR = rR fixed */
-    cR = rR; scoreR = scoreRdiag;
-    {
-      const int rdiR = rdi[cR];
-      const int endlo = min(rL,lim - cR), endhi = min(chighL,lim - cR);
-      for (int base_ = cloL; base_ < endlo; base_ += 4) {
-	int s4_[4], d4_[4];
-#pragma unroll
-	for (int u_ = 0; u_ < 4; u_++) { const int cc = min(base_ + u_,endlo - 1); s4_[u_] = tri_score(LL,cc,rL); d4_[u_] = ldi[cc]; }
-#pragma unroll
-	for (int u_ = 0; u_ < 4; u_++) if (base_ + u_ < endlo) {
-	  cL = base_ + u_; scoreL = s4_[u_]; scoreI = intron_points(isc,d4_[u_],rdiR); CONSIDER(lp[cL],probRdiag); }
-      }
-      for (int base_ = rL + 1; base_ < endhi; base_ += 4) {
-	int s4_[4], d4_[4];
-#pragma unroll
-	for (int u_ = 0; u_ < 4; u_++) { const int cc = min(base_ + u_,endhi - 1); s4_[u_] = tri_score(LU,rL,cc); d4_[u_] = ldi[cc]; }
-#pragma unroll
-	for (int u_ = 0; u_ < 4; u_++) if (base_ + u_ < endhi) {
-	  cL = base_ + u_; scoreL = s4_[u_]; scoreI = intron_points(isc,d4_[u_],rdiR); CONSIDER(lp[cL],probRdiag); }
-      }
-    }
-#undef CONSIDER
   }
-
+  if (gb.key >= 0 && gb.p < 0.0) gb.p = gen_key_prob(g,gb.key);
+  if (gb.key < 0) gb.p = 0.0;
   /* combine: max score, then max probability, then earliest in the reference's scan order */
   for (int off = 16; off > 0; off >>= 1) {
-    Cand o = cand_shfl(best,lane ^ off);
-    if (cand_better(o,best)) best = o;
-    Cand d = cand_shfl(dn,lane ^ off);
-    if (d.p > dn.p || (d.p == dn.p && d.p > 0.0 && d.ord < dn.ord)) dn = d;
+    const int os = __shfl_xor_sync(FULLMASK,gb.s,off), ok = __shfl_xor_sync(FULLMASK,gb.key,off);
+    const double op = __shfl_xor_sync(FULLMASK,gb.p,off);
+    if (os > gb.s || (os == gb.s && (op > gb.p || (op == gb.p && ok < gb.key)))) { gb.s = os; gb.key = ok; gb.p = op; }
+    const int ds = __shfl_xor_sync(FULLMASK,dns,off), dk = __shfl_xor_sync(FULLMASK,dnkey,off);
+    const double dp = __shfl_xor_sync(FULLMASK,dnp,off);
+    if (dp > dnp || (dp == dnp && dp > 0.0 && dk < dnkey)) { dns = ds; dnkey = dk; dnp = dp; }
   }
 
-  int bestscore = best.s;
+  int bestscore = gb.s, key = gb.key;
   bool use_dinucl;
-  if (best.p > 2 * 0.85) use_dinucl = false;
-  else if (dn.p == 0.0) use_dinucl = false;
-  else if (dn.s < 0 || dn.s < bestscore - 9) use_dinucl = false;
+  if (gb.p > 2 * 0.85) use_dinucl = false;
+  else if (dnp == 0.0) use_dinucl = false;
+  else if (dns < 0 || dns < bestscore - 9) use_dinucl = false;
   else use_dinucl = true;
-  if (use_dinucl) { best = dn; bestscore = dn.s; }
-  *bestrL = best.rL; *bestrR = best.rR; *bestcL = best.cL; *bestcR = best.cR;
+  if (use_dinucl) { key = dnkey; bestscore = dns; }
+  int rL = 0, rR = 0, cL = 0, cR = 0;
+  if (key >= 0) {
+    const int seg = (key >> 12) & 7, col = key & 4095;
+    rL = key >> 15; rR = rlength - rL;
+    cL = (seg >= 3) ? col : rL; cR = (seg == 1 || seg == 2) ? col : rR;
+  }
+  *bestrL = rL; *bestrR = rR; *bestcL = cL; *bestcR = cR;
   if (bestscore < 0) return bestscore;
-  if (b.flags & GMAPDP_F_HALFP) return bestscore - intron_points(isc,ldi[best.cL],rdi[best.cR]) / 2;
+  if (b.flags & GMAPDP_F_HALFP) return bestscore - intron_points(isc,g.ldi[cL],g.rdi[cR]) / 2;
   return bestscore;
 }
 
@@ -803,11 +963,12 @@ __device__ int bridge_genome (const gmapdp_box &b, const TriFill &LU, const TriF
  *   pb[cR][k]  best scoreR over rR <= k (and its rR)                       -- handles the rR constraint
  *   M[cR]      = pb[cR][all rR]                                            -- the unconstrained column best
  *   Q[j]       best of M[cR] over cR <= j (and its cR), tie rule on cR     -- the unconstrained cR best
- * For one (cL,rL): the pen = 0 column and the (at most lbandR+ubandR) columns whose rR range is cut by
- * the constraint are looked up in pb, all other columns are answered by one Q lookup.
- * O(g * band * (1 + cut columns)) instead of O(g^2 * band^2). */
+ *   V[rL][j]   best of pb[cR][rcap(rL)] over the first j+1 columns whose rR range is cut by the constraint
+ *              rR <= rcap = lim - rL - 1 (they depend on rL only: cR in (rcap - lbandR, rcap + ubandR])
+ * For one (cL,rL): the pen = 0 column is looked up in pb, the cut columns below cR0 = glength - cL in V, and all
+ * other columns are answered by one Q lookup.  O(g * band) instead of O(g^2 * band^2). */
 __device__ int bridge_cdna (const gmapdp_box &b, const TriFill &LU, const TriFill &LL, const TriFill &RU,
-			    const TriFill &RL, int NEG, uint32_t *pb, uint32_t *smemMQ, int *bestcL, int *bestcR, int *bestrL, int *bestrR) {
+			    const TriFill &RL, int NEG, uint32_t *pb, uint32_t *V, uint32_t *smemMQ, int *bestcL, int *bestcR, int *bestrL, int *bestrR) {
   const int lane = threadIdx.x & 31;
   const int glength = b.glenL, rlengthL = b.rlenL, rlengthR = b.rlenR;
   const int lbandL = b.lbandL, ubandL = b.ubandL, lbandR = b.lbandR, ubandR = b.ubandR;
@@ -845,11 +1006,27 @@ __device__ int bridge_cdna (const gmapdp_box &b, const TriFill &LU, const TriFil
   }
   __syncwarp();
 
+  /* V: per rL, prefix best over its cut columns (same tie rule on cR as Q) */
+  for (int rL = 1 + lane; rL < rlengthL; rL += 32) {
+    const int rcap = lim - rL - 1;
+    if (rcap >= rlengthR - 1 || rcap < 1) continue;
+    const int s0 = max(rcap - lbandR + 1,0), e0 = min(rcap + ubandR,glength);
+    uint32_t *row = V + (size_t) rL * PBW;
+    int vs = 0, vc = -1;
+    for (int cR = s0; cR <= e0; cR++) {
+      const uint32_t e = pb[(size_t) cR * PBW + (rcap - (cR - ubandR))];
+      const int sc = (int) (e >> 16) - 32768;
+      if (vc < 0 || (late ? sc > vs : sc >= vs)) { vs = sc; vc = cR; }
+      row[cR - s0] = ((uint32_t) (vs + 32768) << 16) | (uint32_t) vc;
+    }
+  }
+  __syncwarp();
+
   int bs = NEG; unsigned long long bk = 0; bool have = false;
   int bcL = 0, bcR = 0, brL = 0, brR = 0;
 #define CDNA_CAND(CR,SCORE_R,RR,PEN) do { \
     const int score_ = scoreL + (SCORE_R) + (PEN); \
-    const unsigned long long key_ = ((unsigned long long) (glength - (CR)) << 32) | ((unsigned long long) rL << 16) | (unsigned long long) (RR); \
+    const unsigned long long key_ = ((unsigned long long) cL << 48) | ((unsigned long long) (glength - (CR)) << 32) | ((unsigned long long) rL << 16) | (unsigned long long) (RR); \
     bool take_; \
     if (!have) take_ = late ? (score_ >= bs) : (score_ > bs); \
     else if (score_ != bs) take_ = score_ > bs; \
@@ -879,11 +1056,15 @@ __device__ int bridge_cdna (const gmapdp_box &b, const TriFill &LU, const TriFil
 	  CDNA_CAND(cR,(int) (qe >> 16) - 32768,(int) (M[cR] & 0xffffu),open);
 	}
       }
-      for (int cR = max(junc + 1,0); cR <= cR0 - 1; cR++) {
-	const int lo = max(cR - ubandR,1), k = min(min(cR + lbandR,rlengthR - 1),rcap);
-	if (k < lo) break;				/* lo grows with cR: nothing further can qualify */
-	const uint32_t e = pb[(size_t) cR * PBW + (k - (cR - ubandR))];
-	CDNA_CAND(cR,(int) (e >> 16) - 32768,(int) (e & 0xffffu),open);
+      /* columns cut by the constraint: cR in [max(junc+1,0), min(cR0-1, rcap+ubandR)], answered by V */
+      if (rcap < rlengthR - 1 && rcap >= 1) {
+	const int s0 = max(rcap - lbandR + 1,0), jhi = min(cR0 - 1,rcap + ubandR) - s0;
+	if (jhi >= 0) {
+	  const uint32_t v = V[(size_t) rL * PBW + jhi];
+	  const int cR = (int) (v & 0xffffu);
+	  const uint32_t e = pb[(size_t) cR * PBW + (rcap - (cR - ubandR))];
+	  CDNA_CAND(cR,(int) (v >> 16) - 32768,(int) (e & 0xffffu),open);
+	}
       }
     }
   }
@@ -952,6 +1133,8 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
   uint16_t *qselR = reinterpret_cast<uint16_t *>(bytes); bytes += gdp_align16(2 * (size_t) (b.rlenR + 2));
   uint16_t *gselL = reinterpret_cast<uint16_t *>(bytes); bytes += gdp_align16(2 * (size_t) (b.glenL + 2));
   uint16_t *gselR = reinterpret_cast<uint16_t *>(bytes); bytes += gdp_align16(2 * (size_t) (b.glenR + 2));
+  short *dgL = reinterpret_cast<short *>(bytes); bytes += gdp_align16(2 * (size_t) (b.rlenL + 2));
+  short *dgR = reinterpret_cast<short *>(bytes); bytes += gdp_align16(2 * (size_t) (b.rlenR + 2));
   uint32_t *wp = reinterpret_cast<uint32_t *>(bytes);
   uint32_t *stage = wp; wp += b.rlenL + b.glenL + b.rlenR + b.glenR + 16;
 
@@ -1036,7 +1219,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
       F[f].nA = tp.nA[f]; F[f].nB = tp.nB[f]; F[f].band = tp.band[f];
       F[f].lane0 = tp.lane0[f]; F[f].pass0 = tp.pass0[f]; F[f].npass = tp.npass[f];
       F[f].lateadd = (right ? lateR : lateL) ? 1 : 0;
-      F[f].lower = lower;
+      F[f].lower = lower; F[f].right = right;
       F[f].code = lower ? (right ? qcodeR : qcodeL) : (right ? gcodeR : gcodeL);
       F[f].sel = lower ? (right ? qselR : qselL) : (right ? gselR : gselL);
       F[f].prof = reinterpret_cast<const uint2 *>(wp) + 32;	/* 32 entries of look-ahead padding in front */
@@ -1046,7 +1229,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
     }
     uint32_t *dbase = wp; wp += (size_t) tp.npasses * tp.dirPW;
     uint32_t *sbase = NULL;
-    if (twosided) { sbase = wp; wp += (size_t) tp.npasses * tp.scPW; }
+    if (KIND == 3) { sbase = wp; wp += (size_t) tp.npasses * tp.scPW; }
     uint32_t *edge = wp; wp += tp.maxA + 2;
     for (int f = 0; f < tp.nf; f++) {
       F[f].dirs = dbase + (size_t) tp.pass0[f] * tp.dirPW;
@@ -1059,7 +1242,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
       const bool lastrow = (b.flags & GMAPDP_F_LASTROW) != 0;
       BestTrack bt;
       if (lastrow) { bt.bs = NEG; bt.bk = (b.rlenL << 16); } else { bt.bs = 0; bt.bk = 0; }
-      tri_fill_all<false,true>(F,tp.nf,tp.npasses,open,extend,NEG,POS,&bt,b.rlenL,lastrow,edge,noalt);
+      tri_fill_all<0>(F,tp.nf,tp.npasses,open,extend,NEG,POS,&bt,b.rlenL,lastrow,edge,noalt,NULL,NULL);
       for (int off = 16; off > 0; off >>= 1) {
 	const int os = __shfl_xor_sync(FULLMASK,bt.bs,off), ok = __shfl_xor_sync(FULLMASK,bt.bk,off);
 	if (os > bt.bs || (os == bt.bs && (lateL ? ok > bt.bk : ok < bt.bk))) { bt.bs = os; bt.bk = ok; }
@@ -1073,16 +1256,36 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
       }
     } else {
       const TriFill &LL = F[0], &RL = F[1], &LU = F[2], &RU = F[3];
-      tri_fill_all<true,false>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt);
-      __syncwarp();
       int brL, brR, bcL, bcR, fs;
       if (KIND == 2) {
 	const int di = b.cdna_direction > 0 ? 0 : (b.cdna_direction < 0 ? 1 : 2);
-	fs = bridge_genome(b,LU,LL,RU,RL,ldi,rdi,ka.probs + b.probL_off,ka.probs + b.probR_off,NEG,
-			   tb->isc[di][(b.flags & GMAPDP_F_FINALP) ? 1 : 0],&brL,&brR,&bcL,&bcR);
+	const int *isc = tb->isc[di][(b.flags & GMAPDP_F_FINALP) ? 1 : 0];
+	GenCtx gc;
+	gc.ldi = ldi; gc.rdi = rdi; gc.dgL = dgL; gc.dgR = dgR;
+	gc.lp = ka.probs + b.probL_off; gc.rp = ka.probs + b.probR_off;
+	gc.rlength = b.rlenL; gc.lim = b.offdiff;
+	gc.it0 = ((uint32_t) isc[0] << 8) | ((uint32_t) isc[1] << 16) | ((uint32_t) isc[2] << 24);
+	gc.it1 = (uint32_t) isc[3] | ((uint32_t) isc[4] << 8) | ((uint32_t) isc[5] << 16);
+	GenBest gb; gb.s = NEG; gb.key = -1; gb.cnt = 0; gb.p = 0.0; gb.ties = wp + lane; wp += GEN_TIECAP * 32;
+	gen_diagonals(LU,RU,dgL,dgR,NEG,POS);
+	tri_fill_all<2>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,&gc,&gb);
+	__syncwarp();
+	if (gb.key >= 0) gb.p = -1.0;				/* no probability has been fetched inside the fills */
+	/* only the lanes that reached the warp's best score can win: their tie lists are the ones that count */
+	int smax = gb.s;
+	for (int off = 16; off > 0; off >>= 1) smax = max(smax,__shfl_xor_sync(FULLMASK,smax,off));
+	if (gb.s < smax) gb.cnt = 0;
+	if (__any_sync(FULLMASK,gb.cnt > GEN_TIECAP)) {		/* such a list overflowed: once more, ties resolved on the spot */
+	  gb.s = NEG; gb.key = -1; gb.cnt = 0; gb.p = 0.0;
+	  tri_fill_all<2>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,&gc,&gb,true);
+	  __syncwarp();
+	}
+	fs = bridge_genome_finish(b,gc,gb,NEG,isc,&brL,&brR,&bcL,&bcR);
 	if (fs < 0) res.status = 1;
       } else {
-	fs = bridge_cdna(b,LU,LL,RU,RL,NEG,wp,reinterpret_cast<uint32_t *>(bnd),&bcL,&bcR,&brL,&brR);
+	tri_fill_all<1>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,NULL,NULL);
+	__syncwarp();
+	fs = bridge_cdna(b,LU,LL,RU,RL,NEG,wp,wp + (size_t) (b.glenL + 1) * (b.lbandR + b.ubandR + 1),reinterpret_cast<uint32_t *>(bnd),&bcL,&bcR,&brL,&brR);
       }
       res.finalscore = fs; res.bestrL = brL; res.bestcL = bcL; res.bestrR = brR; res.bestcR = bcR;
       if (res.status == 0) {

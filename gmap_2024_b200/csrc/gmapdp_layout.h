@@ -98,6 +98,8 @@ GDP_HD size_t gdp_ws_words (const gmapdp_box &b) {
   size_t bytes = gdp_align16(b.rlenL + 2) + gdp_align16(b.rlenR + 2) + 2 * gdp_align16(b.glenL + 2) + 2 * gdp_align16(b.glenR + 2);
   /* ready-made PRMT selectors (uint16) of the same positions, read 16 at a time by the interior steps of the E-only fills */
   bytes += gdp_align16(2 * (size_t) (b.rlenL + 2)) + gdp_align16(2 * (size_t) (b.rlenR + 2)) + gdp_align16(2 * (size_t) (b.glenL + 2)) + gdp_align16(2 * (size_t) (b.glenR + 2));
+  /* genome gaps: main-diagonal scores of the two upper fills (int16) */
+  bytes += gdp_align16(2 * (size_t) (b.rlenL + 2)) + gdp_align16(2 * (size_t) (b.rlenR + 2));
   w += bytes / 4;
   /* script staging */
   w += (size_t) (b.rlenL + b.glenL + b.rlenR + b.glenR + 16);
@@ -105,13 +107,14 @@ GDP_HD size_t gdp_ws_words (const gmapdp_box &b) {
     FGeom f = fgeom(b.rlenL,b.glenL,b.lbandL,b.ubandL);
     w += (size_t) f.nstripes * f.dirW;
   } else {
-    const bool scores = (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA);
+    const bool scores = (b.mode == GMAPDP_CDNA);	/* genome gaps evaluate their bridge inside the fills */
     TriPacking tp;
     tri_fills_of(b,tp);
     for (int f = 0; f < tp.nf; f++) w += 2 * (size_t) (tp.nA[f] + 2 + 32);	/* profile tables (+ look-ahead padding) */
     w += (size_t) tp.npasses * (tp.dirPW + (scores ? tp.scPW : 0));
     w += (size_t) tp.maxA + 2;							/* edge array of wide fills */
-    if (b.mode == GMAPDP_CDNA) w += (size_t) (b.glenL + 1) * (b.lbandR + b.ubandR + 1);	/* prefix-best table of the cDNA bridge */
+    if (b.mode == GMAPDP_GENOME) w += 8 * 32;					/* tie lists of the bridge (GEN_TIECAP keys per lane) */
+    if (b.mode == GMAPDP_CDNA) w += (size_t) (b.glenL + 1 + b.rlenL + 1) * (b.lbandR + b.ubandR + 1);	/* prefix-best tables of the cDNA bridge: per column, per rL */
   }
   return w + 64;
 }
