@@ -221,50 +221,60 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
     odi = s.own_di + col; pdi = s.oth_di + rP; pdg = s.oth_dg + rP;
     key = s.key0 + t * s.kstep;
   }
+  uint32_t tieoff = (uint32_t) g.cnt * 128u;		/* byte offset of the lane's next tie slot */
+  int tb = t;
   for (; t + 16 <= tstop; t += 16) {
-    const uint4 s0 = sq[0], s1 = sq[1];
-    const uint32_t sw[8] = {s0.x,s0.y,s0.z,s0.w,s1.x,s1.y,s1.z,s1.w};
     uint32_t dacc = 0;
-    int Heven = 0;
+    /* two halves of 8 unrolled steps (one copy of the code: the kernels live in the instruction cache) */
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+      const uint4 s4 = sq[h];
+      const uint32_t sw[4] = {s4.x,s4.y,s4.z,s4.w};
+      uint32_t d8 = 0;
+      int Heven = 0;
 #pragma unroll
-    for (int u = 0; u < 16; u++) {
-      uint32_t pk_in = __shfl_up_sync(FULLMASK,pk_out,1);
-      if (isd0) pk_in = negpair;
-      const uint2 p = pq[u];
-      const uint32_t selw = (u & 1) ? (sw[u >> 1] >> 16) : sw[u >> 1];
-      uint32_t scu;
-      asm("prmt.b32 %0, %1, %2, %3;" : "=r"(scu) : "r"(p.x), "r"(p.y), "r"(selw));
-      const int Hd = clampi(H + (int) scu,NEG,POS);
-      const int Hl = sext_lo16(pk_in), El = ((int) pk_in) >> 16;
-      const int T1 = max(Hl + open,NEG);
-      const bool dE = (LM == 0) ? (El > T1) : ((LM == 1) ? (El >= T1) : (El + la > T1));
-      const int E = max(max(El,T1) + extend,NEG);
-      const bool dN = (LM == 0) ? (E > Hd) : ((LM == 1) ? (E >= Hd) : (E + la > Hd));
-      const int Hn = max(Hd,E);
-      pk_out = pack_lo16(Hn,E);
-      dacc |= (dN ? (1u << (2 * u)) : 0u) | (dE ? (2u << (2 * u)) : 0u);
-      if (SCORES) {
-	if (u & 1) { *splane = pack_lo16(Heven,Hn); splane += 32; }
-	else Heven = Hn;
+      for (int u = 0; u < 8; u++) {
+	uint32_t pk_in = __shfl_up_sync(FULLMASK,pk_out,1);
+	if (isd0) pk_in = negpair;
+	const uint2 p = pq[u];
+	const uint32_t selw = (u & 1) ? (sw[u >> 1] >> 16) : sw[u >> 1];
+	uint32_t scu;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(scu) : "r"(p.x), "r"(p.y), "r"(selw));
+	const int Hd = clampi(H + (int) scu,NEG,POS);
+	const int Hl = sext_lo16(pk_in), El = ((int) pk_in) >> 16;
+	const int T1 = max(Hl + open,NEG);
+	const bool dE = (LM == 0) ? (El > T1) : ((LM == 1) ? (El >= T1) : (El + la > T1));
+	const int E = max(max(El,T1) + extend,NEG);
+	const bool dN = (LM == 0) ? (E > Hd) : ((LM == 1) ? (E >= Hd) : (E + la > Hd));
+	const int Hn = max(Hd,E);
+	pk_out = pack_lo16(Hn,E);
+	d8 |= (dN ? (1u << (2 * u)) : 0u) | (dE ? (2u << (2 * u)) : 0u);
+	if (SCORES) {
+	  if (u & 1) { *splane = pack_lo16(Heven,Hn); splane += 32; }
+	  else Heven = Hn;
+	}
+	if (TRACK) {
+	  const bool up = s.trk && ((LM == 0) ? (Hn > bs) : ((LM == 1) ? (Hn >= bs) : (Hn + la > bs)));
+	  bs = up ? Hn : bs; btt = up ? tb + u : btt;
+	}
+	if (EVAL) {
+	  const int tot = Hn + gen_points(*gc,(int) odi[u] & (int) pdi[-u]) + (int) pdg[-u];
+	  const int ku = key + u * s.kstep;
+	  const bool gt = s.ev_ok && tot > g.s, eq = s.ev_ok && tot == g.s;
+	  if (eq && tieoff < GEN_TIECAP * 128u) *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(g.ties) + tieoff) = (uint32_t) ku;
+	  tieoff = gt ? 0u : tieoff + (eq ? 128u : 0u);
+	  g.key = gt ? ku : g.key; g.s = gt ? tot : g.s;
+	}
+	H = Hn;
       }
-      if (TRACK) {
-	const bool up = s.trk && ((LM == 0) ? (Hn > bs) : ((LM == 1) ? (Hn >= bs) : (Hn + la > bs)));
-	bs = up ? Hn : bs; btt = up ? t + u : btt;
-      }
-      if (EVAL) {
-	const int tot = Hn + gen_points(*gc,(int) odi[u] & (int) pdi[-u]) + (int) pdg[-u];
-	const int ku = key + u * s.kstep;
-	const bool gt = s.ev_ok && tot > g.s, eq = s.ev_ok && tot == g.s;
-	if (eq && g.cnt < GEN_TIECAP) g.ties[g.cnt * 32] = (uint32_t) ku;
-	g.cnt = gt ? 0 : g.cnt + (eq ? 1 : 0);
-	g.key = gt ? ku : g.key; g.s = gt ? tot : g.s;
-      }
-      H = Hn;
+      pq += 8; tb += 8;
+      if (EVAL) { odi += 8; pdi -= 8; pdg -= 8; key += 8 * s.kstep; }
+      dacc |= d8 << (16 * h);
     }
-    pq += 16; sq += 2;
-    if (EVAL) { odi += 16; pdi -= 16; pdg -= 16; key += 16 * s.kstep; }
+    sq += 2;
     *dplane = isd0 ? 0u : dacc; dplane += 32;
   }
+  if (EVAL) g.cnt = (int) (tieoff >> 7);
   s.Hprev = H; s.H = H; s.pk_out = pk_out; s.dplane = dplane; s.splane = splane;
   if (EVAL) *gb = g;
   if (TRACK) {
@@ -277,7 +287,7 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
 }
 
 template <int MODE, bool WIDE>
-__device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
+__device__ __noinline__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
 			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok, const GenCtx *gc, GenBest *gb,
 			  bool ev_now) {
   constexpr bool SCORES = (MODE == 1), TRACK = (MODE == 0), EVAL = (MODE == 2);
@@ -407,8 +417,9 @@ __device__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, in
       if ((t & 15) == 14) { *s.dplane = s.dacc; s.dplane += 32; s.dacc = 0; }
     }
     if (phase == 0 && hasfast) {
-      if (lm == 0) tri_fast<MODE,0>(s,t,F1,open,extend,NEG,POS,negpair,bt,gc,gb);
-      else if (lm == 1) tri_fast<MODE,1>(s,t,F1,open,extend,NEG,POS,negpair,bt,gc,gb);
+      /* end gaps have one tie rule per box: two lean copies; the two-sided modes mix the rules: one copy, rule per lane */
+      if (MODE == 0 && lm == 0) tri_fast<MODE,0>(s,t,F1,open,extend,NEG,POS,negpair,bt,gc,gb);
+      else if (MODE == 0 && lm == 1) tri_fast<MODE,1>(s,t,F1,open,extend,NEG,POS,negpair,bt,gc,gb);
       else tri_fast<MODE,2>(s,t,F1,open,extend,NEG,POS,negpair,bt,gc,gb);
     } else break;
   }
@@ -763,7 +774,7 @@ __device__ __forceinline__ void tb_diag_run (TbAcc &a, const SideSeq &sd, int r,
 
 __device__ __forceinline__ int first_set (uint32_t m) { return m ? (__ffs(m) - 1) : 32; }
 
-__device__ void tb_upper (TbAcc &a, const SideSeq &sd, const TriFill &pl, int r, int c, const GdpTables *tb) {
+__device__ __noinline__ void tb_upper (TbAcc &a, const SideSeq &sd, const TriFill &pl, int r, int c, const GdpTables *tb) {
   const int k = threadIdx.x & 31;
   while (r > 0 && c > 0) {
     const bool valid = (r - k > 0) && (c - k > 0);
@@ -787,7 +798,7 @@ __device__ void tb_upper (TbAcc &a, const SideSeq &sd, const TriFill &pl, int r,
   if (c > 0 && c < 9) { a.score += -3 - c; a.nopens += 1; a.nindels += c; }
 }
 
-__device__ void tb_lower (TbAcc &a, const SideSeq &sd, const TriFill &pl, int r, int c, const GdpTables *tb) {
+__device__ __noinline__ void tb_lower (TbAcc &a, const SideSeq &sd, const TriFill &pl, int r, int c, const GdpTables *tb) {
   const int k = threadIdx.x & 31;
   while (r > 0 && c > 0) {
     const bool valid = (r - k > 0) && (c - k > 0);
