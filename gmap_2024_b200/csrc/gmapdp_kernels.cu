@@ -135,7 +135,9 @@ __device__ void tri_profiles (const TriFill &f, const SideSeq &sd, int mt, bool 
  * after the fills, and only for the lanes that reached the warp's best score (flat stretches far from the splice
  * site tie all the time, but cannot win).  If the list of such a lane overflowed (long runs of equal best scores:
  * low-complexity sequence) the warp repeats the fills with every tie resolved on the spot (gen_tie). */
-#define GEN_TIECAP 8
+#ifndef GEN_TIECAP
+#define GEN_TIECAP 8		/* at most 8: the workspace reserves 8 x 32 words */
+#endif
 struct GenBest { int s, key, cnt; double p; uint32_t *ties; };	/* p < 0: not fetched yet; ties[j * 32]: j-th tied key of this lane */
 struct GenCtx {
   const uint8_t *ldi, *rdi;		/* dinucleotide classes per genomic position */
@@ -202,6 +204,10 @@ template <int MODE, int LM>
 __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, const int open, const int extend, const int NEG,
 					  const int POS, const uint32_t negpair, BestTrack *bt, const GenCtx *gc, GenBest *gb) {
   constexpr bool SCORES = (MODE == 1), TRACK = (MODE == 0), EVAL = (MODE == 2);
+#ifndef GMAPDP_END_UNROLL
+#define GMAPDP_END_UNROLL 1
+#endif
+  constexpr int HALVES_UNROLLED = (MODE == 0) ? GMAPDP_END_UNROLL : 1;
   const uint2 *pq = s.pp + t;
   const uint4 *sq = reinterpret_cast<const uint4 *>(s.sel + t);
   const int la = s.lateadd;
@@ -225,8 +231,9 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
   int tb = t;
   for (; t + 16 <= tstop; t += 16) {
     uint32_t dacc = 0;
-    /* two halves of 8 unrolled steps (one copy of the code: the kernels live in the instruction cache) */
-#pragma unroll 1
+    /* two halves of 8 unrolled steps; the big two-sided kernels keep ONE copy of the half (instruction-cache
+       footprint), the small end-gap kernel unrolls both */
+#pragma unroll HALVES_UNROLLED
     for (int h = 0; h < 2; h++) {
       const uint4 s4 = sq[h];
       const uint32_t sw[4] = {s4.x,s4.y,s4.z,s4.w};
@@ -287,7 +294,7 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
 }
 
 template <int MODE, bool WIDE>
-__device__ __noinline__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
+__device__ __forceinline__ void tri_pass_body (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
 			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok, const GenCtx *gc, GenBest *gb,
 			  bool ev_now) {
   constexpr bool SCORES = (MODE == 1), TRACK = (MODE == 0), EVAL = (MODE == 2);
@@ -425,6 +432,24 @@ __device__ __noinline__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf,
   }
   if (((thi & ~1) & 15) != 14) *s.dplane = s.dacc;
   __syncwarp();
+}
+
+/* out of line for the two-sided kernels (called from several places: one copy of the code) */
+template <int MODE, bool WIDE>
+__device__ __noinline__ void tri_pass_call (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
+			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok, const GenCtx *gc, GenBest *gb,
+			  bool ev_now) {
+  tri_pass_body<MODE,WIDE>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok,gc,gb,ev_now);
+}
+#ifndef GMAPDP_END_INLINE
+#define GMAPDP_END_INLINE 1
+#endif
+template <int MODE, bool WIDE>
+__device__ __forceinline__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
+			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok, const GenCtx *gc, GenBest *gb,
+			  bool ev_now) {
+  if (MODE == 0 && GMAPDP_END_INLINE) tri_pass_body<MODE,WIDE>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok,gc,gb,ev_now);
+  else tri_pass_call<MODE,WIDE>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok,gc,gb,ev_now);
 }
 
 /* all passes of a box's E-only fills */
@@ -889,20 +914,34 @@ __device__ __forceinline__ int intron_points (const int *isc, int ldi, int rdi) 
 }
 
 /* Main-diagonal scores of the two upper fills (what the d == 0 lane of tri_pass computes: H(i,i) =
-   clamp(H(i-1,i-1) + score(i,i)), no gap can reach the diagonal): lane 0 scans the left side, lane 1 the right. */
+   clamp(H(i-1,i-1) + score(i,i)), no gap can reach the diagonal).  A clamped add x -> min(max(x + a, l), u) is
+   closed under composition -- (a1,l1,u1) then (a2,l2,u2) = (a1 + a2, clamp(l1 + a2), clamp(u1 + a2)) with clamp
+   to [l2,u2] -- so the recurrence is a warp prefix scan over 32 positions at a time. */
 __device__ void gen_diagonals (const TriFill &LU, const TriFill &RU, short *dgL, short *dgR, int NEG, int POS) {
   const int lane = threadIdx.x & 31;
-  if (lane < 2) {
-    const TriFill &f = lane ? RU : LU;
-    short *dg = lane ? dgR : dgL;
+  for (int side = 0; side < 2; side++) {
+    const TriFill &f = side ? RU : LU;
+    short *dg = side ? dgR : dgL;
     const int n = min(f.nA,f.nB);
-    int H = 0;
-    uint2 p = f.prof[0]; int cd = f.code[0];
-    for (int i = 0; i <= n; i++) {
-      const uint2 pc = p; const int cc = cd;
-      if (i < n) { p = f.prof[i + 1]; cd = f.code[i + 1]; }
-      H = clampi(H + max(prof_pick(pc.x,pc.y,cc & 15),prof_pick(pc.x,pc.y,cc >> 4)),NEG,POS);
-      dg[i] = (short) H;
+    int carry = 0;
+    for (int base = 0; base <= n; base += 32) {
+      const int i = base + lane;
+      int a = 0, lo = -(1 << 30), hi = (1 << 30);		/* identity past the end */
+      if (i <= n) {
+	const uint2 p = f.prof[i]; const int cd = f.code[i];
+	a = max(prof_pick(p.x,p.y,cd & 15),prof_pick(p.x,p.y,cd >> 4)); lo = NEG; hi = POS;
+      }
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+	const int a1 = __shfl_up_sync(FULLMASK,a,off), l1 = __shfl_up_sync(FULLMASK,lo,off), u1 = __shfl_up_sync(FULLMASK,hi,off);
+	if (lane >= off) {
+	  const int nl = min(max(l1 + a,lo),hi), nu = min(max(u1 + a,lo),hi);
+	  a += a1; lo = nl; hi = nu;
+	}
+      }
+      const int H = min(max(carry + a,lo),hi);
+      if (i <= n) dg[i] = (short) H;
+      carry = __shfl_sync(FULLMASK,H,31);
     }
   }
   __syncwarp();
@@ -1024,66 +1063,63 @@ __device__ int bridge_cdna (const gmapdp_box &b, const TriFill &LU, const TriFil
     const int s0 = max(rcap - lbandR + 1,0), e0 = min(rcap + ubandR,glength);
     uint32_t *row = V + (size_t) rL * PBW;
     int vs = 0, vc = -1;
-    for (int cR = s0; cR <= e0; cR++) {
-      const uint32_t e = pb[(size_t) cR * PBW + (rcap - (cR - ubandR))];
-      const int sc = (int) (e >> 16) - 32768;
-      if (vc < 0 || (late ? sc > vs : sc >= vs)) { vs = sc; vc = cR; }
-      row[cR - s0] = ((uint32_t) (vs + 32768) << 16) | (uint32_t) vc;
+    /* consecutive columns sit PBW - 1 words apart: four loads in flight per round */
+    const uint32_t *src = pb + (size_t) s0 * PBW + (rcap - (s0 - ubandR));
+    for (int cR = s0; cR <= e0; cR += 4) {
+      uint32_t e4[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) e4[u] = src[(size_t) min(u,e0 - cR) * (PBW - 1)];
+      src += 4 * (size_t) (PBW - 1);
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (cR + u <= e0) {
+	const int sc = (int) (e4[u] >> 16) - 32768;
+	if (vc < 0 || (late ? sc > vs : sc >= vs)) { vs = sc; vc = cR + u; }
+	row[cR + u - s0] = ((uint32_t) (vs + 32768) << 16) | (uint32_t) vc;
+      }
     }
   }
   __syncwarp();
 
+  /* rR of a candidate never decides a comparison (one candidate per (cL, cR, rL)): the winner's rR is looked up
+     at the end from the table its candidate came from (kind 0: pen = 0 column, 1: Q, 2: V) */
   int bs = NEG; unsigned long long bk = 0; bool have = false;
-  int bcL = 0, bcR = 0, brL = 0, brR = 0;
-#define CDNA_CAND(CR,SCORE_R,RR,PEN) do { \
+  int bcL = 0, bcR = 0, brL = 0, bkind = 0;
+#define CDNA_CAND(OK,CR,SCORE_R,KIND,PEN) do { \
     const int score_ = scoreL + (SCORE_R) + (PEN); \
-    const unsigned long long key_ = ((unsigned long long) cL << 48) | ((unsigned long long) (glength - (CR)) << 32) | ((unsigned long long) rL << 16) | (unsigned long long) (RR); \
+    const unsigned long long key_ = ((unsigned long long) cL << 48) | ((unsigned long long) (glength - (CR)) << 32) | ((unsigned long long) rL << 16); \
     bool take_; \
     if (!have) take_ = late ? (score_ >= bs) : (score_ > bs); \
     else if (score_ != bs) take_ = score_ > bs; \
     else take_ = late ? (key_ > bk) : (key_ < bk); \
-    if (take_) { bs = score_; bk = key_; bcL = cL; bcR = (CR); brL = rL; brR = (RR); have = true; } } while (0)
+    if ((OK) && take_) { bs = score_; bk = key_; bcL = cL; bcR = (CR); brL = rL; bkind = (KIND); have = true; } } while (0)
 
   for (int cL = 1 + lane; cL < glength; cL += 32) {
     const int rloL = max(cL - ubandL,1), rhighL = min(cL + lbandL,rlengthL - 1);
     const int cR0 = glength - cL;
+    const int lo0 = max(cR0 - ubandR,1), hi0 = min(cR0 + lbandR,rlengthR - 1);
+#pragma unroll 2
     for (int rL = rloL; rL <= rhighL; rL++) {
-      const int scoreL = (rL < cL) ? tri_score(LU,rL,cL) : tri_score(LL,cL,rL);
       const int rcap = lim - rL - 1;			/* rR <= rcap */
-      /* the pen = 0 column */
-      {
-	const int lo = max(cR0 - ubandR,1), k = min(min(cR0 + lbandR,rlengthR - 1),rcap);
-	if (k >= lo) {
-	  const uint32_t e = pb[(size_t) cR0 * PBW + (k - (cR0 - ubandR))];
-	  CDNA_CAND(cR0,(int) (e >> 16) - 32768,(int) (e & 0xffffu),0);
-	}
-      }
-      /* columns cR < cR0 (pen = open): those with cR + lbandR <= rcap are unconstrained */
-      int junc = min(cR0 - 1,(rcap >= rlengthR - 1) ? cR0 - 1 : rcap - lbandR);
-      if (junc >= 0) {
-	const uint32_t qe = Q[junc];
-	if (qe != 0xffffffffu) {
-	  const int cR = (int) (qe & 0xffffu);
-	  CDNA_CAND(cR,(int) (qe >> 16) - 32768,(int) (M[cR] & 0xffffu),open);
-	}
-      }
-      /* columns cut by the constraint: cR in [max(junc+1,0), min(cR0-1, rcap+ubandR)], answered by V */
-      if (rcap < rlengthR - 1 && rcap >= 1) {
-	const int s0 = max(rcap - lbandR + 1,0), jhi = min(cR0 - 1,rcap + ubandR) - s0;
-	if (jhi >= 0) {
-	  const uint32_t v = V[(size_t) rL * PBW + jhi];
-	  const int cR = (int) (v & 0xffffu);
-	  const uint32_t e = pb[(size_t) cR * PBW + (rcap - (cR - ubandR))];
-	  CDNA_CAND(cR,(int) (v >> 16) - 32768,(int) (e & 0xffffu),open);
-	}
-      }
+      /* every lookup of the iteration is issued before any is used (indices clamped into the tables) */
+      const int k0 = min(hi0,rcap);
+      const bool ok0 = (k0 >= lo0);						/* the pen = 0 column */
+      const int junc = min(cR0 - 1,(rcap >= rlengthR - 1) ? cR0 - 1 : rcap - lbandR);	/* columns <= junc are unconstrained */
+      const int s0 = max(rcap - lbandR + 1,0), jhi = min(cR0 - 1,rcap + ubandR) - s0;
+      const bool okV = (rcap < rlengthR - 1 && rcap >= 1 && jhi >= 0);		/* columns cut by the constraint */
+      const int scoreL = (rL < cL) ? tri_score(LU,rL,cL) : tri_score(LL,cL,rL);
+      const uint32_t e0 = pb[(size_t) cR0 * PBW + (max(k0,lo0) - (cR0 - ubandR))];
+      const uint32_t qe = Q[max(junc,0)];
+      const uint32_t v = V[(size_t) rL * PBW + max(jhi,0)];
+      CDNA_CAND(ok0,cR0,(int) (e0 >> 16) - 32768,0,0);
+      CDNA_CAND(junc >= 0 && qe != 0xffffffffu,(int) (qe & 0xffffu),(int) (qe >> 16) - 32768,1,open);
+      CDNA_CAND(okV,(int) (v & 0xffffu),(int) (v >> 16) - 32768,2,open);
     }
   }
 #undef CDNA_CAND
   /* lanes partition cL, which leads the scan order: late keeps the largest cL on ties, early the smallest */
   for (int off = 16; off > 0; off >>= 1) {
     const int os = __shfl_xor_sync(FULLMASK,bs,off), ocL = __shfl_xor_sync(FULLMASK,bcL,off), ocR = __shfl_xor_sync(FULLMASK,bcR,off);
-    const int orL = __shfl_xor_sync(FULLMASK,brL,off), orR = __shfl_xor_sync(FULLMASK,brR,off);
+    const int orL = __shfl_xor_sync(FULLMASK,brL,off), ok = __shfl_xor_sync(FULLMASK,bkind,off);
     const int oh = __shfl_xor_sync(FULLMASK,(int) have,off);
     bool take = false;
     if (oh) {
@@ -1091,7 +1127,16 @@ __device__ int bridge_cdna (const gmapdp_box &b, const TriFill &LU, const TriFil
       else if (os != bs) take = os > bs;
       else take = late ? (ocL > bcL) : (ocL < bcL);
     }
-    if (take) { bs = os; bcL = ocL; bcR = ocR; brL = orL; brR = orR; have = true; }
+    if (take) { bs = os; bcL = ocL; bcR = ocR; brL = orL; bkind = ok; have = true; }
+  }
+  int brR = 0;
+  if (have) {
+    const int rcap = lim - brL - 1;
+    if (bkind == 1) brR = (int) (M[bcR] & 0xffffu);
+    else {
+      const int k = (bkind == 0) ? min(min(bcR + lbandR,rlengthR - 1),rcap) : rcap;
+      brR = (int) (pb[(size_t) bcR * PBW + (k - (bcR - ubandR))] & 0xffffu);
+    }
   }
   *bestcL = bcL; *bestcR = bcR; *bestrL = brL; *bestrR = brR;
   return bs;
@@ -1380,7 +1425,7 @@ struct gmapdp_ctx {
   uint32_t *d_kws[GDP_NK]; size_t cap_kws[GDP_NK];
   cudaStream_t kstream[GDP_NK];		/* kstream[0] == stream */
   cudaEvent_t evj[GDP_NK], evk[GDP_NK][2]; float last_ms[GDP_NK];
-  size_t chunk_bytes;			/* pipelining granularity of gmapdp_run_batch (GMAPDP_CHUNK_MB, default 192) */
+  size_t chunk_bytes;			/* pipelining granularity of gmapdp_run_batch (GMAPDP_CHUNK_MB, default 384) */
   std::vector<int> chunk_count;		/* [chunk][kind] boxes */
   cudaStream_t stream, copy_stream;
   std::vector<cudaEvent_t> chunk_events;
@@ -1461,8 +1506,8 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   }
   {
     const char *cm = getenv("GMAPDP_CHUNK_MB");
-    long mb = cm ? atol(cm) : 192;
-    ctx->chunk_bytes = (size_t) (mb > 0 ? mb : 192) << 20;
+    long mb = cm ? atol(cm) : 384;
+    ctx->chunk_bytes = (size_t) (mb > 0 ? mb : 384) << 20;
   }
   CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
   GdpHostTables ht; GdpTables t; ht.device_tables(&t);

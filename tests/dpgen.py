@@ -26,7 +26,18 @@ def revcomp(s):
     return s.translate(COMP)[::-1]
 
 
+LOW_COMPLEXITY = False      # set by lowcomplexity_boxes(): repeats of short units, quantised probabilities
+
+
 def rand_dna(rng, n, nfrac=0.003):
+    if LOW_COMPLEXITY and n > 0:
+        # homopolymers / di- and trinucleotide repeats with rare breaks: long runs of equal scores, the
+        # stress case for every tie rule (bridge candidates, endpoint search, traceback)
+        unit = bytes(rng.choices(b"ACGT", k=rng.choice([1, 1, 2, 2, 3, 5])))
+        out = bytearray((unit * (n // len(unit) + 1))[:n])
+        for _ in range(n // 40):
+            out[rng.randrange(n)] = rng.choice(b"ACGT")
+        return bytes(out)
     out = bytearray(rng.choices(b"ACGT", k=n))
     if nfrac > 0:
         for _ in range(int(n * nfrac)):
@@ -179,6 +190,8 @@ def _chop(s, max_r, max_g):
 
 
 def synthetic_probs(rng, n, hot=()):
+    if LOW_COMPLEXITY:
+        return [rng.choice([0.0, 0.0, 0.25, 0.5, 0.9, 0.95]) for _ in range(n)]
     p = [rng.random() ** 3 for _ in range(n)]
     for h in hot:
         if 0 <= h < n:
@@ -256,6 +269,16 @@ def _finalize_synthetic(rng, s, b, qoff, T, x, m, max_r, max_g):
 def synth_boxes(seed, n, mode=None, rmin=15, rmax=150, max_r=2000, max_g=2030):
     rng = random.Random(seed)
     return [finalize_synthetic(rng, gen_spec(rng, mode, rmin, rmax), max_r, max_g) for _ in range(n)]
+
+
+def lowcomplexity_boxes(seed, n, mode=None, rmin=15, rmax=150):
+    """synth_boxes over low-complexity sequence with quantised splice probabilities (many exact ties)"""
+    global LOW_COMPLEXITY
+    LOW_COMPLEXITY = True
+    try:
+        return synth_boxes(seed, n, mode, rmin, rmax)
+    finally:
+        LOW_COMPLEXITY = False
 
 
 # ---------------------------------------------------------------------------------------------

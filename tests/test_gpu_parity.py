@@ -98,3 +98,17 @@ def test_empty_and_degenerate(engine, oracle):
     e.free()
     boxes = dpgen.synth_boxes(seed=5, n=40, rmin=2, rmax=6)
     run_and_compare(engine, oracle, boxes, "tiny")
+
+
+@pytest.mark.parametrize("mode", ["genome", "cdna", "end3", "end5", "single"])
+def test_low_complexity_ties(engine, oracle, mode):
+    """repeats and quantised probabilities: long runs of equal scores exercise every tie rule -- the bridge's
+    "score, then probability sum, then scan order" (tie lists and their overflow path), the cDNA bridge's
+    positional tie-break across columns, the endpoint search and the tracebacks"""
+    boxes = dpgen.lowcomplexity_boxes(seed=900 + len(mode), n=400, mode=mode, rmin=8, rmax=260)
+    run_and_compare(engine, oracle, boxes, "low-complexity " + mode)
+
+
+def test_low_complexity_large_genome(engine, oracle):
+    boxes = dpgen.lowcomplexity_boxes(seed=77, n=40, mode="genome", rmin=600, rmax=1600)
+    run_and_compare(engine, oracle, boxes, "low-complexity large genome")

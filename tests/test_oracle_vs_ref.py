@@ -69,3 +69,18 @@ def test_entry_points_identical(pair, seed, edge):
         assert o.run(b) == r.run(b), b["mode"]
         seen.add(b["mode"])
     assert len(seen) == 5
+
+
+def test_entry_points_identical_low_complexity(pair):
+    """repeats (homopolymers, short tandem units): long runs of equal scores, every tie rule of the entry points"""
+    o, r = pair
+    dpgen.LOW_COMPLEXITY = True
+    try:
+        boxes, _ = dpgen.ref_boxes(r, 31, 300, rmin=8, rmax=260)
+    finally:
+        dpgen.LOW_COMPLEXITY = False
+    seen = set()
+    for b in boxes:
+        assert o.run(b) == r.run(b), b["mode"]
+        seen.add(b["mode"])
+    assert len(seen) == 5
