@@ -387,8 +387,8 @@ def run_ours(args):
                              "other_kernels": {"names": ["gmapdp_dp_kernel<1> (end gaps)", "gmapdp_dp_kernel<2> (genome gaps)",
                                                          "gmapdp_dp_kernel<3> (cdna gaps)"],
                                                "ms": [x / args.steps for x in kind_ms[1:]],
-                                               "note": "E-only fills, searches and bridges; each on its own stream, concurrently with "
-                                                       "the single-gap kernel (durations overlap)"},
+                                               "note": "E-only fills, searches and bridges; the four kernels of a step run back to back "
+                                                       "on one stream, each bracketed by its own CUDA events"},
                              "int": int_roofline(cf * OPS_PER_CELL_FULL / (dom_ms / 1e3) if full_ms > 0 else None)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(batch.h2d_bytes()),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps},

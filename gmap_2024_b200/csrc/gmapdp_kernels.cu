@@ -479,6 +479,16 @@ __device__ void tri_fill_all (const TriFill (&F)[GDP_MAXFILLS], int nf, int npas
  * inside the band), which need none of the edge logic. */
 struct FullLane { int E, Hl, diag, cg_out; uint32_t pk_out; int bprevH; };
 
+/* The word that travels down the lanes (and sits in the boundary entries): H in the HIGH half, the column's
+   class field in the low half.  Packing is one PRMT (of H and the incoming word: the field is never extracted --
+   the score's PRMT reads only the low 16 bits of its selector) and H comes back with one arithmetic shift. */
+__device__ __forceinline__ uint32_t full_pack (int H, uint32_t fieldword) {	/* (H << 16) | (fieldword & 0xffff) */
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(d) : "r"(fieldword), "r"(H));
+  return d;
+}
+__device__ __forceinline__ int full_H (uint32_t pk) { return ((int) pk) >> 16; }
+
 /* The 16-bit "field" that travels with H: without an alt genome it is the ready-made PRMT selector of
    the column's class (k*0x1111+0x8880), with one it is the class pair k | kalt<<4. */
 template <bool ALT>
@@ -500,13 +510,13 @@ __device__ __forceinline__ uint32_t full_edge (FullLane &st, const int lane, con
   const bool act = rowact && c >= c0 && c <= chigh;
   uint32_t nib = 0;
   if (act) {
-    int last_in = (int) (short) (pk_in & 0xffffu);	/* final H(r-1,c) = the F pass's last_nogap */
-    uint32_t field = pk_in >> 16;
+    int last_in = full_H(pk_in);			/* final H(r-1,c) = the F pass's last_nogap */
+    uint32_t field = pk_in & 0xffffu;
     int Hs = st.diag;
     if (lane == 0) {
       const uint2 e = bnd[c];
-      const int bH = (int) (short) (e.x & 0xffffu);
-      field = e.x >> 16;
+      const int bH = full_H(e.x);
+      field = e.x & 0xffffu;
       if (rlo == 0) {
 	Hs = (c == 0) ? 0 : NEG;
 	cg_in = NEG32; last_in = NEG32;
@@ -544,17 +554,28 @@ __device__ __forceinline__ uint32_t full_edge (FullLane &st, const int lane, con
     }
     st.diag = last_in;
     st.Hl = H;
-    st.pk_out = ((uint32_t) H & 0xffffu) | (field << 16);
+    st.pk_out = full_pack(H,field);
     if (lane == 31) bnd[c] = make_uint2(st.pk_out,(uint32_t) st.cg_out);
     nib = dN | (dE ? 4u : 0u) | (dF ? 8u : 0u);
   }
   return nib;
 }
 
+/* acc += (a >= b or a > b) ? c : 0 as a compare (ALU pipe) and a predicated multiply-add (FMA pipe): the
+   full-fill kernel saturates the ALU pipe, so the direction bits are accumulated on the other one.  The bits of
+   one word are distinct, so adding is or-ing. */
+/* `one' is the value 1 read from the kernel arguments: a multiplier the assembler cannot fold, which keeps the
+   operation a real IMAD (with a literal 1 it is turned back into an ALU add). */
+template <bool GE, uint32_t C>
+__device__ __forceinline__ void add_if (uint32_t &acc, int a, int b, uint32_t one) {
+  if (GE) asm("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %1, %2;\n\t@q mad.lo.u32 %0, %3, %4, %0;\n\t}" : "+r"(acc) : "r"(a), "r"(b), "r"(one), "n"(C));
+  else asm("{\n\t.reg .pred q;\n\tsetp.gt.s32 q, %1, %2;\n\t@q mad.lo.u32 %0, %3, %4, %0;\n\t}" : "+r"(acc) : "r"(a), "r"(b), "r"(one), "n"(C));
+}
+
 /* interior step: every lane is active and strictly inside the band, c >= 1.  Branch-free: all lanes
    read their column's boundary entry, lane 0 selects it; FIRST = the stripe starts at row 0. */
-template <bool LATE, bool ALT, bool FIRST>
-__device__ __forceinline__ uint32_t full_fast (FullLane &st, const bool isl0, const bool isl31, const int open, const int extend,
+template <bool LATE, bool ALT, bool FIRST, int U>
+__device__ __forceinline__ void full_fast (FullLane &st, uint32_t &a8, const uint32_t one, const bool isl0, const bool isl31, const int open, const int extend,
 					       const int NEG, const int POS, const uint32_t plo, const uint32_t p4, uint2 *bp) {
   const int cg_sh = __shfl_up_sync(FULLMASK,st.cg_out,1);
   const uint32_t pk_sh = __shfl_up_sync(FULLMASK,st.pk_out,1);
@@ -562,36 +583,36 @@ __device__ __forceinline__ uint32_t full_fast (FullLane &st, const bool isl0, co
   uint32_t field;
   if (FIRST) {
     const uint32_t ex = bp->x;
-    field = isl0 ? (ex >> 16) : (pk_sh >> 16);
+    field = isl0 ? ex : pk_sh;				/* low half; the high half is ignored downstream */
     Hs = isl0 ? NEG : st.diag;
     cg_in = isl0 ? NEG32 : cg_sh;
-    last_in = isl0 ? NEG32 : (int) (short) (pk_sh & 0xffffu);
+    last_in = isl0 ? NEG32 : full_H(pk_sh);
   } else {
     const uint2 e = *bp;
-    const int bH = (int) (short) (e.x & 0xffffu);
-    field = isl0 ? (e.x >> 16) : (pk_sh >> 16);
-    Hs = isl0 ? st.bprevH : st.diag;
+    const uint32_t src = isl0 ? e.x : pk_sh;		/* lane 0 takes the previous stripe's last row */
+    field = src;					/* low half; the high half is ignored downstream */
+    Hs = st.diag;					/* lane 0: the boundary H of the previous column = its previous last_in */
     cg_in = isl0 ? (int) e.y : cg_sh;
-    last_in = isl0 ? bH : (int) (short) (pk_sh & 0xffffu);
-    st.bprevH = bH;
+    last_in = full_H(src);
   }
+  /* direction bits of this step's nibble: bit 0 E beats the diagonal, bit 1 F beats both (a set bit 1 means VERT
+     whatever bit 0 says: tb_full), bit 2 Egap, bit 3 Fgap */
   const int T1 = max(st.Hl + open,NEG);
-  const bool dE = LATE ? (st.E >= T1) : (st.E > T1);
+  add_if<LATE,(4u << (4 * U))>(a8,st.E,T1,one);
   st.E = max(max(st.E,T1) + extend,NEG);
   const int Hd = clampi(Hs + field_score<ALT>(plo,p4,field),NEG,POS);
-  const bool dNh = LATE ? (st.E >= Hd) : (st.E > Hd);
+  add_if<LATE,(1u << (4 * U))>(a8,st.E,Hd,one);
   int H = max(Hd,st.E);
   const int score = last_in + open;
-  const bool dF = LATE ? (cg_in >= score) : (cg_in > score);
-  const int cg = (dF ? cg_in : score) + extend;
-  const bool tV = LATE ? (cg >= H) : (cg > H);
-  H = tV ? cg : H;
+  add_if<LATE,(8u << (4 * U))>(a8,cg_in,score,one);
+  const int cg = max(cg_in,score) + extend;
+  add_if<LATE,(2u << (4 * U))>(a8,cg,H,one);
+  H = max(H,cg);
   st.cg_out = cg;
   st.diag = last_in;
   st.Hl = H;
-  st.pk_out = ((uint32_t) H & 0xffffu) | (field << 16);
+  st.pk_out = full_pack(H,field);
   if (isl31) *bp = make_uint2(st.pk_out,(uint32_t) cg);
-  return (tV ? 2u : (dNh ? 1u : 0u)) | (dE ? 4u : 0u) | (dF ? 8u : 0u);
 }
 
 /* general step, branch-free: any lane may be inactive (before its first / after its last column, past the
@@ -608,12 +629,12 @@ __device__ __forceinline__ uint32_t full_gen (FullLane &st, const bool isl0, con
   const uint32_t pk_sh = __shfl_up_sync(FULLMASK,st.pk_out,1);
   uint2 e = make_uint2(0u,0u);
   if (isl0 && act) e = bnd[c];
-  const int bH = sext_lo16(e.x);
+  const int bH = full_H(e.x);
   const bool carry = !first && (c < cF);
-  const uint32_t field = isl0 ? (e.x >> 16) : (pk_sh >> 16);
+  const uint32_t field = (isl0 ? e.x : pk_sh) & 0xffffu;
   const int Hs = isl0 ? (first ? NEG : st.bprevH) : st.diag;
   const int cg_in = isl0 ? (carry ? (int) e.y : NEG32) : cg_sh;
-  const int last_in = isl0 ? (carry ? bH : NEG32) : sext_lo16(pk_sh);
+  const int last_in = isl0 ? (carry ? bH : NEG32) : full_H(pk_sh);
   /* E (horizontal gap), H */
   const int T1 = max(st.Hl + open,NEG);
   const bool dEr = LATE ? (st.E >= T1) : (st.E > T1);
@@ -632,7 +653,7 @@ __device__ __forceinline__ uint32_t full_gen (FullLane &st, const bool isl0, con
   const bool dF = doF && dFr;
   H = tV ? max(cg,NEG) : H;
   const int cgo = top ? (NEG32 + open + extend) : (doF ? cg : st.cg_out);
-  const uint32_t pk = pack_lo16(H,(int) field);
+  const uint32_t pk = full_pack(H,field);
   if (act) { st.E = En; st.cg_out = cgo; st.diag = last_in; st.Hl = H; st.pk_out = pk; }
   if (isl0 && act) st.bprevH = bH;
   if (isl31 && act) bnd[c] = make_uint2(pk,(uint32_t) cgo);
@@ -642,7 +663,7 @@ __device__ __forceinline__ uint32_t full_gen (FullLane &st, const bool isl0, con
 
 template <bool LATE, bool ALT>
 __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int open, int extend,
-			   int NEG, int POS, uint32_t *dirs, const FGeom &fg, uint2 *bnd, const GdpTables *tb) {
+			   int NEG, int POS, uint32_t *dirs, const FGeom &fg, uint2 *bnd, const GdpTables *tb, const uint32_t one) {
   const int lane = threadIdx.x & 31;
   const bool isl0 = (lane == 0), isl31 = (lane == 31);
   const int rlen = sd.rlen, glen = sd.glen;
@@ -652,7 +673,7 @@ __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int 
     if (c == 0) field = ALT ? 0x44u : (4u * 0x1111u + 0x8880u);
     else if (ALT) field = (uint32_t) (nt_class(sd.g(c)) | (nt_class(sd.ga(c)) << 4));
     else field = (uint32_t) nt_class(sd.g(c)) * 0x1111u + 0x8880u;
-    bnd[c] = make_uint2(field << 16,0u);
+    bnd[c] = make_uint2(field,0u);
   }
   __syncwarp();
   int s = 0;
@@ -682,7 +703,7 @@ __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int 
     st.E = LATE ? NEG : NEG + 1;
     st.Hl = NEG - open; st.diag = NEG - open;
     st.cg_out = NEG32; st.pk_out = 0;
-    st.bprevH = (lane == 0 && rlo > 0 && c0 > 0) ? (int) (short) (bnd[c0 - 1].x & 0xffffu) : NEG;
+    st.bprevH = (lane == 0 && rlo > 0 && c0 > 0) ? full_H(bnd[c0 - 1].x) : NEG;
     uint32_t acc = 0;
     uint32_t *dst = dirs + (size_t) s * fg.dirW + lane;
     int tt = 0, c = c0 - lane;
@@ -691,7 +712,7 @@ __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int 
       acc |= nib << (4 * (tt & 7)); \
       if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; } tt++; c++; } while (0)
 #define FAST_STEP(FIRSTFLAG) do { \
-      const uint32_t nib = full_fast<LATE,ALT,FIRSTFLAG>(st,isl0,isl31,open,extend,NEG,POS,plo,p4,bnd + c); \
+      uint32_t nib = 0; full_fast<LATE,ALT,FIRSTFLAG,0>(st,nib,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bnd + c); \
       acc |= nib << (4 * (tt & 7)); \
       if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; } tt++; c++; } while (0)
 #define FAST_CHUNKS(FIRSTFLAG) do { \
@@ -699,7 +720,14 @@ __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int 
       uint2 *bp = bnd + c; uint32_t *dp = dst + (tt >> 3) * 32; \
       while (tt + 7 <= fe) { \
 	uint32_t a8 = 0; \
-	_Pragma("unroll") for (int u = 0; u < 8; u++) a8 |= full_fast<LATE,ALT,FIRSTFLAG>(st,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + u) << (4 * u); \
+	full_fast<LATE,ALT,FIRSTFLAG,0>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 0); \
+	full_fast<LATE,ALT,FIRSTFLAG,1>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 1); \
+	full_fast<LATE,ALT,FIRSTFLAG,2>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 2); \
+	full_fast<LATE,ALT,FIRSTFLAG,3>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 3); \
+	full_fast<LATE,ALT,FIRSTFLAG,4>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 4); \
+	full_fast<LATE,ALT,FIRSTFLAG,5>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 5); \
+	full_fast<LATE,ALT,FIRSTFLAG,6>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 6); \
+	full_fast<LATE,ALT,FIRSTFLAG,7>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 7); \
 	*dp = a8; dp += 32; bp += 8; tt += 8; c += 8; \
       } \
       while (tt <= fe) FAST_STEP(FIRSTFLAG); } while (0)
@@ -720,7 +748,7 @@ __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int 
 #if GMAPDP_GEN_MODE == 0
     const int e1 = min(fs,nsteps);
     while (tt < e1) EDGE_STEP();
-    if (rlo == 0) FAST_CHUNKS(true); else FAST_CHUNKS(false);
+    { const int tt0_ = tt; if (rlo == 0) FAST_CHUNKS(true); else FAST_CHUNKS(false); if (tt > tt0_) st.bprevH = st.diag;	/* the interior steps keep lane 0's previous boundary H in diag */ }
     while (tt < nsteps) EDGE_STEP();
 #elif GMAPDP_GEN_MODE == 1
     const int e0 = min((c0 >= 1) ? 0 : 32,nsteps);
@@ -730,14 +758,14 @@ __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int 
       const int gend = seg ? nsteps : e1;
       _Pragma("unroll 1")
       while (tt < gend) { acc |= GEN_ONE(0) << (4 * (tt & 7)); if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; } tt++; c++; }
-      if (seg == 0) { if (rlo == 0) FAST_CHUNKS(true); else FAST_CHUNKS(false); }
+      if (seg == 0) { { const int tt0_ = tt; if (rlo == 0) FAST_CHUNKS(true); else FAST_CHUNKS(false); if (tt > tt0_) st.bprevH = st.diag;	/* the interior steps keep lane 0's previous boundary H in diag */ } }
     }
 #else
     const int e0 = min((c0 >= 1) ? 0 : 32,nsteps);
     while (tt < e0) EDGE_STEP();
     const int e1 = min(fs,nsteps);
     GEN_STEPS(e1);
-    if (rlo == 0) FAST_CHUNKS(true); else FAST_CHUNKS(false);
+    { const int tt0_ = tt; if (rlo == 0) FAST_CHUNKS(true); else FAST_CHUNKS(false); if (tt > tt0_) st.bprevH = st.diag;	/* the interior steps keep lane 0's previous boundary H in diag */ }
     GEN_STEPS(nsteps);
 #endif
 #undef GEN_ONE
@@ -1157,6 +1185,7 @@ struct KernelArgs {
   int *queue;
   uint32_t *ws; unsigned long long ws_words;	/* per warp */
   int smem_cols;		/* boundary-row capacity per warp */
+  uint32_t one;			/* the value 1 (see add_if) */
   const GdpTables *tables;
 };
 
@@ -1254,10 +1283,10 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
     FGeom fg = fgeom(b.rlenL,b.glenL,b.lbandL,b.ubandL);
     uint32_t *dirs = wp;
     const bool alt = (b.gLalt_off != b.gL_off);
-    if (lateL) { if (alt) fill_full<true,true>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb);
-		 else fill_full<true,false>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb); }
-    else { if (alt) fill_full<false,true>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb);
-	   else fill_full<false,false>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb); }
+    if (lateL) { if (alt) fill_full<true,true>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb,ka.one);
+		 else fill_full<true,false>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb,ka.one); }
+    else { if (alt) fill_full<false,true>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb,ka.one);
+	   else fill_full<false,false>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb,ka.one); }
     __syncwarp();
     tb_full(acc,L,dirs,fg,b.rlenL,b.glenL,tb); lenA = acc.nops;
 
@@ -1691,7 +1720,12 @@ static int plan_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, siz
    streams must already be ordered after the chunk's uploads.  cnt[kind] boxes of each kind, laid out kind
    by kind in `order' from `first'. */
 static int launch_chunk (gmapdp_ctx *ctx, int first, const int *cnt, bool timed = false) {
-  static const bool serial = getenv("GMAPDP_SERIAL") != NULL;	/* diagnostics: all kernels on one stream */
+  /* The resident (timed) path queues the four kernels on ONE stream: a persistent grid fills every SM, so the
+     kernels run one after the other either way, and on one stream each kernel's events bracket exactly its own
+     execution.  The chunked host-buffer path uses the four streams: its kernels are short and the next kind's
+     blocks fill in while the previous kind's last boxes drain. */
+  static const bool force_serial = getenv("GMAPDP_SERIAL") != NULL;
+  const bool serial = timed || force_serial;
   static const char *korder = getenv("GMAPDP_ORDER") ? getenv("GMAPDP_ORDER") : "2130";	/* launch order of the kinds: the E-only kernels first, the single-gap kernel fills in as they drain (co-resident kernels of different kinds slow each other down) */
   int start[GDP_NK], acc = first;
   for (int kind = 0; kind < GDP_NK; kind++) { start[kind] = acc; acc += cnt[kind]; if (timed) ctx->last_ms[kind] = 0.f; }
@@ -1705,7 +1739,7 @@ static int launch_chunk (gmapdp_ctx *ctx, int first, const int *cnt, bool timed 
     ka.seq = ctx->d_seq; ka.probs = ctx->d_probs; ka.results = ctx->d_results;
     ka.script = ctx->d_script; ka.script_cap = ctx->cap_script; ka.script_cursor = ctx->d_cursor;
     ka.queue = ctx->d_queue + kind; ka.ws = ctx->d_kws[kind]; ka.ws_words = ctx->kws_words[kind];
-    ka.smem_cols = ctx->ksmem_cols[kind]; ka.tables = ctx->d_tables;
+    ka.smem_cols = ctx->ksmem_cols[kind]; ka.tables = ctx->d_tables; ka.one = 1u;
     const size_t smem = (size_t) WARPS_PER_BLOCK * ctx->ksmem_cols[kind] * 8;
     const int grid = std::max(1,std::min(ctx->kgrid[kind],(count + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
     CK(cudaMemsetAsync(ctx->d_queue + kind,0,sizeof(int),st));
@@ -1761,13 +1795,8 @@ extern "C" int gmapdp_run_resident (gmapdp_ctx *ctx, float *kernel_ms) {
   if (ctx->chunk_count.size() < GDP_NK) return GMAPDP_OK;
   const int *cnt = &ctx->chunk_count[0];
   CK(cudaMemsetAsync(ctx->d_cursor,0,sizeof(unsigned long long),ctx->stream));
-  /* fork: the other kernel streams start after ev0; join: ev1 is recorded on `stream' after their kernels have finished */
   CK(cudaEventRecord(ctx->ev0,ctx->stream));
-  int rc = fork_streams(ctx,ctx->ev0);
-  if (rc) return rc;
-  rc = launch_chunk(ctx,0,cnt,true);
-  if (rc) return rc;
-  rc = join_streams(ctx);
+  int rc = launch_chunk(ctx,0,cnt,true);		/* all on `stream', in launch order */
   if (rc) return rc;
   CK(cudaEventRecord(ctx->ev1,ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1777,11 +1806,11 @@ extern "C" int gmapdp_run_resident (gmapdp_ctx *ctx, float *kernel_ms) {
   return GMAPDP_OK;
 }
 
-/* CUDA-event durations of the kernels of the last gmapdp_run_resident (they overlap in time):
-   full_ms = the single-gap kernel, tri_ms = the longest of the three E-only kernels */
+/* CUDA-event durations of the kernels of the last gmapdp_run_resident (one stream, back to back):
+   full_ms = the single-gap kernel, tri_ms = the three E-only kernels together */
 extern "C" int gmapdp_last_kernel_ms (const gmapdp_ctx *ctx, float *full_ms, float *tri_ms) {
   if (full_ms) *full_ms = ctx->last_ms[0];
-  if (tri_ms) *tri_ms = std::max(ctx->last_ms[1],std::max(ctx->last_ms[2],ctx->last_ms[3]));
+  if (tri_ms) *tri_ms = ctx->last_ms[1] + ctx->last_ms[2] + ctx->last_ms[3];
   return GMAPDP_OK;
 }
 

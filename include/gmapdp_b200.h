@@ -109,10 +109,11 @@ int gmapdp_upload (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes,
 		   const uint8_t *seqpool, size_t seqbytes, const double *probpool, size_t nprobs);
 int gmapdp_run_resident (gmapdp_ctx *ctx, float *kernel_ms);
 int gmapdp_download (gmapdp_ctx *ctx, gmapdp_result *results, uint32_t *script, size_t script_cap, size_t *script_used);
-/* A batch is served by four specialisations of the DP kernel running side by side on four streams: one for
- * the single-gap boxes (full fills) and one each for the end, genome and cdna boxes (E-only fills + searches /
- * bridges).  Their own CUDA-event durations for the last gmapdp_run_resident (they overlap in time):
- * full_ms = the single-gap kernel, tri_ms = the longest of the other three; ms[4] = single, end, genome, cdna. */
+/* A batch is served by four specialisations of the DP kernel: one for the single-gap boxes (full fills) and
+ * one each for the end, genome and cdna boxes (E-only fills + searches / bridges).  gmapdp_run_resident queues
+ * them back to back on one stream (each is a persistent grid over all SMs), so their CUDA-event durations are
+ * exact: full_ms = the single-gap kernel, tri_ms = the other three together; ms[4] = single, end, genome, cdna.
+ * gmapdp_run_batch launches the kernels of its chunks on four streams. */
 int gmapdp_last_kernel_ms (const gmapdp_ctx *ctx, float *full_ms, float *tri_ms);
 int gmapdp_last_kernel_ms4 (const gmapdp_ctx *ctx, float *ms);
 /* number of kernel launches issued by this context so far */

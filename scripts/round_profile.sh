@@ -1,12 +1,19 @@
-# Round profile: bench line, ncu launch list of the SAME command, DRAM bytes of one full-size launch,
-# and one --set full capture of the DP kernel on a 100k-box batch (B200_PROFILING.md recipe).
+# Round profile: bench line, ncu launch list of the SAME command, DRAM bytes of one full-size launch of the dominant
+# kernel (gmapdp_dp_kernel<0>, the single-gap full fills), and --set full captures on 100k-box batches
+# (B200_PROFILING.md recipe: every ncu pass only after the same command has exited 0 without ncu).
 set -x
 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err
 tail -c 300 gpurun_out/bench_full.err
-CMD="python bench.py --no-cpu-baseline"
-$CMD > gpurun_out/plain_launch.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 50 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
-CMD1="python bench.py --no-cpu-baseline --steps 1 --warmup 0"
-$CMD1 > gpurun_out/plain_dram.log 2>&1 && ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -c 1 --csv --log-file gpurun_out/dram_1m.csv $CMD1 > gpurun_out/ncu_dram.log 2>&1
-CMD2="python bench.py --boxes 100000 --steps 1 --warmup 0 --no-cpu-baseline"
-$CMD2 > gpurun_out/plain_full.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gmapdp -c 1 -o gpurun_out/prof_full $CMD2 > gpurun_out/ncu_full.log 2>&1
+CMD="python bench.py --no-cpu-baseline --chain-problems 0"
+$CMD > gpurun_out/plain_launch.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+CMD1="python bench.py --no-cpu-baseline --chain-problems 0 --steps 1 --warmup 0"
+$CMD1 > gpurun_out/plain_dram.log 2>&1 && ncu --kernel-name-base mangled -k regex:ILi0E --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -c 1 --csv --log-file gpurun_out/dram_1m.csv $CMD1 > gpurun_out/ncu_dram.log 2>&1
+for spec in "1 full" "2 genome"; do
+  set -- $spec
+  CMD2="python bench.py --boxes 100000 --steps 1 --warmup 0 --no-cpu-baseline --chain-problems 0 --modemask $1"
+  $CMD2 > gpurun_out/plain_$2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gmapdp -c 1 -o gpurun_out/prof_$2 $CMD2 > gpurun_out/ncu_$2.log 2>&1
+done
+# the overflow path of the bridge's tie lists: the same parity tests against a build with one-entry lists
+GMAPDP_LIB=build/variants/lib_tiecap1.so python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py tests/test_gpu_bench_workload.py -x -q -k "genome or mixed or golden or workload or medium" 2>&1 | tail -3 > gpurun_out/tiecap1_tests.log
+cat gpurun_out/tiecap1_tests.log
 ls -la gpurun_out
