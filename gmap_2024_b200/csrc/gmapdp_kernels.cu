@@ -574,8 +574,13 @@ __device__ __forceinline__ void add_if (uint32_t &acc, int a, int b, uint32_t on
 
 /* interior step: every lane is active and strictly inside the band, c >= 1.  Branch-free: all lanes
    read their column's boundary entry, lane 0 selects it; FIRST = the stripe starts at row 0. */
+/* Per-lane multipliers that turn selects and the repacking of the travelling word into multiply-adds (FMA pipe):
+   m0 = 1 on lane 0 else 0, m1 = 1 - m0, k64 = 65536, nk64 = -65536 -- all derived from the kernel argument `one',
+   so the assembler has to keep them as IMADs (each ALU-pipe instruction moved over shortens the critical pipe). */
+struct FullMul { uint32_t m0, m1, k64, nk64; };
+
 template <bool LATE, bool ALT, bool FIRST, int U>
-__device__ __forceinline__ void full_fast (FullLane &st, uint32_t &a8, const uint32_t one, const bool isl0, const bool isl31, const int open, const int extend,
+__device__ __forceinline__ void full_fast (FullLane &st, uint32_t &a8, const uint32_t one, const FullMul &fm, const bool isl0, const bool isl31, const int open, const int extend,
 					       const int NEG, const int POS, const uint32_t plo, const uint32_t p4, uint2 *bp) {
   const int cg_sh = __shfl_up_sync(FULLMASK,st.cg_out,1);
   const uint32_t pk_sh = __shfl_up_sync(FULLMASK,st.pk_out,1);
@@ -589,10 +594,10 @@ __device__ __forceinline__ void full_fast (FullLane &st, uint32_t &a8, const uin
     last_in = isl0 ? NEG32 : full_H(pk_sh);
   } else {
     const uint2 e = *bp;
-    const uint32_t src = isl0 ? e.x : pk_sh;		/* lane 0 takes the previous stripe's last row */
+    const uint32_t src = e.x * fm.m0 + pk_sh * fm.m1;	/* lane 0 takes the previous stripe's last row */
     field = src;					/* low half; the high half is ignored downstream */
     Hs = st.diag;					/* lane 0: the boundary H of the previous column = its previous last_in */
-    cg_in = isl0 ? (int) e.y : cg_sh;
+    cg_in = (int) (e.y * fm.m0 + (uint32_t) cg_sh * fm.m1);
     last_in = full_H(src);
   }
   /* direction bits of this step's nibble: bit 0 E beats the diagonal, bit 1 F beats both (a set bit 1 means VERT
@@ -611,7 +616,9 @@ __device__ __forceinline__ void full_fast (FullLane &st, uint32_t &a8, const uin
   st.cg_out = cg;
   st.diag = last_in;
   st.Hl = H;
-  st.pk_out = full_pack(H,field);
+  /* same field, H instead of last_in in the high half: src + (H - last_in) * 65536 */
+  if (FIRST) st.pk_out = full_pack(H,field);
+  else st.pk_out = (uint32_t) H * fm.k64 + ((uint32_t) last_in * fm.nk64 + field);
   if (isl31) *bp = make_uint2(st.pk_out,(uint32_t) cg);
 }
 
@@ -667,6 +674,8 @@ __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int 
   const int lane = threadIdx.x & 31;
   const bool isl0 = (lane == 0), isl31 = (lane == 31);
   const int rlen = sd.rlen, glen = sd.glen;
+  FullMul fm;
+  fm.m0 = isl0 ? one : 0u; fm.m1 = one - fm.m0; fm.k64 = one << 16; fm.nk64 = 0u - fm.k64;
   /* the columns' class fields into the boundary entries */
   for (int c = lane; c <= glen; c += 32) {
     uint32_t field;
@@ -712,7 +721,7 @@ __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int 
       acc |= nib << (4 * (tt & 7)); \
       if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; } tt++; c++; } while (0)
 #define FAST_STEP(FIRSTFLAG) do { \
-      uint32_t nib = 0; full_fast<LATE,ALT,FIRSTFLAG,0>(st,nib,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bnd + c); \
+      uint32_t nib = 0; full_fast<LATE,ALT,FIRSTFLAG,0>(st,nib,one,fm,isl0,isl31,open,extend,NEG,POS,plo,p4,bnd + c); \
       acc |= nib << (4 * (tt & 7)); \
       if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; } tt++; c++; } while (0)
 #define FAST_CHUNKS(FIRSTFLAG) do { \
@@ -720,14 +729,14 @@ __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int 
       uint2 *bp = bnd + c; uint32_t *dp = dst + (tt >> 3) * 32; \
       while (tt + 7 <= fe) { \
 	uint32_t a8 = 0; \
-	full_fast<LATE,ALT,FIRSTFLAG,0>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 0); \
-	full_fast<LATE,ALT,FIRSTFLAG,1>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 1); \
-	full_fast<LATE,ALT,FIRSTFLAG,2>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 2); \
-	full_fast<LATE,ALT,FIRSTFLAG,3>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 3); \
-	full_fast<LATE,ALT,FIRSTFLAG,4>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 4); \
-	full_fast<LATE,ALT,FIRSTFLAG,5>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 5); \
-	full_fast<LATE,ALT,FIRSTFLAG,6>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 6); \
-	full_fast<LATE,ALT,FIRSTFLAG,7>(st,a8,one,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 7); \
+	full_fast<LATE,ALT,FIRSTFLAG,0>(st,a8,one,fm,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 0); \
+	full_fast<LATE,ALT,FIRSTFLAG,1>(st,a8,one,fm,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 1); \
+	full_fast<LATE,ALT,FIRSTFLAG,2>(st,a8,one,fm,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 2); \
+	full_fast<LATE,ALT,FIRSTFLAG,3>(st,a8,one,fm,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 3); \
+	full_fast<LATE,ALT,FIRSTFLAG,4>(st,a8,one,fm,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 4); \
+	full_fast<LATE,ALT,FIRSTFLAG,5>(st,a8,one,fm,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 5); \
+	full_fast<LATE,ALT,FIRSTFLAG,6>(st,a8,one,fm,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 6); \
+	full_fast<LATE,ALT,FIRSTFLAG,7>(st,a8,one,fm,isl0,isl31,open,extend,NEG,POS,plo,p4,bp + 7); \
 	*dp = a8; dp += 32; bp += 8; tt += 8; c += 8; \
       } \
       while (tt <= fe) FAST_STEP(FIRSTFLAG); } while (0)
@@ -1297,8 +1306,10 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
     TriFill F[GDP_MAXFILLS];
     const bool noalt = (b.gLalt_off == b.gL_off) && (!twosided || b.gRalt_off == b.gR_off);	/* selectors carry one class */
     if ((reinterpret_cast<uintptr_t>(wp) & 7) != 0) wp++;
+    constexpr int NF = twosided ? 4 : 2;		/* = tp.nf; constant indices keep tp in registers */
+#pragma unroll
     for (int f = 0; f < GDP_MAXFILLS; f++) {
-      if (f >= tp.nf) { F[f] = F[0]; continue; }
+      if (f >= NF) { F[f] = F[0]; continue; }
       const bool lower = twosided ? (f < 2) : (f == 0);
       const bool right = twosided && (f & 1);
       F[f].nA = tp.nA[f]; F[f].nB = tp.nB[f]; F[f].band = tp.band[f];
@@ -1316,7 +1327,8 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
     uint32_t *sbase = NULL;
     if (KIND == 3) { sbase = wp; wp += (size_t) tp.npasses * tp.scPW; }
     uint32_t *edge = wp; wp += tp.maxA + 2;
-    for (int f = 0; f < tp.nf; f++) {
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
       F[f].dirs = dbase + (size_t) tp.pass0[f] * tp.dirPW;
       F[f].sc = sbase ? sbase + (size_t) tp.pass0[f] * tp.scPW : NULL;
     }
@@ -1413,10 +1425,10 @@ extern __shared__ __align__(16) unsigned char dyn_smem[];
 #define GMAPDP_TRI_MINB 5
 #endif
 #ifndef GMAPDP_END_MINB
-#define GMAPDP_END_MINB GMAPDP_TRI_MINB
+#define GMAPDP_END_MINB 8		/* measured: 8 blocks/SM (64 registers) beat 5 for the end-gap kernel, 6 for genome gaps */
 #endif
 #ifndef GMAPDP_GENOME_MINB
-#define GMAPDP_GENOME_MINB GMAPDP_TRI_MINB
+#define GMAPDP_GENOME_MINB 6
 #endif
 #ifndef GMAPDP_CDNA_MINB
 #define GMAPDP_CDNA_MINB GMAPDP_TRI_MINB
@@ -1720,12 +1732,12 @@ static int plan_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, siz
    streams must already be ordered after the chunk's uploads.  cnt[kind] boxes of each kind, laid out kind
    by kind in `order' from `first'. */
 static int launch_chunk (gmapdp_ctx *ctx, int first, const int *cnt, bool timed = false) {
-  /* The resident (timed) path queues the four kernels on ONE stream: a persistent grid fills every SM, so the
-     kernels run one after the other either way, and on one stream each kernel's events bracket exactly its own
-     execution.  The chunked host-buffer path uses the four streams: its kernels are short and the next kind's
-     blocks fill in while the previous kind's last boxes drain. */
-  static const bool force_serial = getenv("GMAPDP_SERIAL") != NULL;
-  const bool serial = timed || force_serial;
+  /* The four kernels are queued on ONE stream: a persistent grid fills every SM, so the kernels run one after
+     the other either way, co-resident kernels of different kinds slow each other down, and on one stream each
+     kernel's events bracket exactly its own execution.  GMAPDP_STREAMS=1 puts the kernels of the chunked
+     host-buffer path on four streams (measured slower: 292 vs 279 ms end to end). */
+  static const bool use_streams = getenv("GMAPDP_STREAMS") != NULL;
+  const bool serial = timed || !use_streams;
   static const char *korder = getenv("GMAPDP_ORDER") ? getenv("GMAPDP_ORDER") : "2130";	/* launch order of the kinds: the E-only kernels first, the single-gap kernel fills in as they drain (co-resident kernels of different kinds slow each other down) */
   int start[GDP_NK], acc = first;
   for (int kind = 0; kind < GDP_NK; kind++) { start[kind] = acc; acc += cnt[kind]; if (timed) ctx->last_ms[kind] = 0.f; }
@@ -1866,12 +1878,15 @@ extern "C" int gmapdp_run_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int n
   int rc = plan_scan(ctx,boxes,nboxes,work,&upbytes,ps);
   if (rc) return rc;
   lap("box scan");
+  /* Chunks grow geometrically from CHUNK_BYTES / 4: a short first chunk lets the device start early, and since a
+     chunk uploads faster than it computes, the next one may be larger and still arrive in time -- fewer chunk
+     boundaries, where the persistent grids drain and refill. */
   std::vector<int> chunk_begin(1,0);
   {
-    size_t acc = 0;
+    size_t acc = 0, limit = CHUNK_BYTES / 4;
     for (int i = 0; i < nboxes; i++) {
       acc += upbytes[i];
-      if (acc >= (chunk_begin.size() == 1 ? CHUNK_BYTES / 4 : CHUNK_BYTES) || i == nboxes - 1) { chunk_begin.push_back(i + 1); acc = 0; }
+      if (acc >= limit || i == nboxes - 1) { chunk_begin.push_back(i + 1); acc = 0; limit = std::min(limit * 2,CHUNK_BYTES * 8); }
     }
   }
   const int nchunks = (int) chunk_begin.size() - 1;

@@ -42,17 +42,24 @@ struct TriPacking {
 GDP_HD void tri_pack (TriPacking &tp) {
   int used = 0, pass = -1;
   tp.Tmax = 0; tp.maxA = 0;
-  for (int f = 0; f < tp.nf; f++) {
-    const int w = tp.band[f] + 1;
-    if (tp.nB[f] > tp.Tmax) tp.Tmax = tp.nB[f];
-    if (tp.nA[f] > tp.maxA) tp.maxA = tp.nA[f];
-    if (w > 32) {
-      tp.pass0[f] = pass + 1; tp.npass[f] = (w + 31) / 32; tp.lane0[f] = 0;
-      pass += tp.npass[f]; used = 32;
-    } else if (pass >= 0 && used + w <= 32) {
-      tp.pass0[f] = pass; tp.npass[f] = 1; tp.lane0[f] = used; used += w;
-    } else {
-      pass++; tp.pass0[f] = pass; tp.npass[f] = 1; tp.lane0[f] = 0; used = w;
+  /* fixed trip count and guards instead of `f < tp.nf' in the loop header: on the device the arrays then
+     stay in registers (every index is a compile-time constant after unrolling) */
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int f = 0; f < GDP_MAXFILLS; f++) {
+    if (f < tp.nf) {
+      const int w = tp.band[f] + 1;
+      if (tp.nB[f] > tp.Tmax) tp.Tmax = tp.nB[f];
+      if (tp.nA[f] > tp.maxA) tp.maxA = tp.nA[f];
+      if (w > 32) {
+	tp.pass0[f] = pass + 1; tp.npass[f] = (w + 31) / 32; tp.lane0[f] = 0;
+	pass += tp.npass[f]; used = 32;
+      } else if (pass >= 0 && used + w <= 32) {
+	tp.pass0[f] = pass; tp.npass[f] = 1; tp.lane0[f] = used; used += w;
+      } else {
+	pass++; tp.pass0[f] = pass; tp.npass[f] = 1; tp.lane0[f] = 0; used = w;
+      }
     }
   }
   tp.npasses = pass + 1;
@@ -63,12 +70,19 @@ GDP_HD void tri_pack (TriPacking &tp) {
 /* the fills of a box, in packing order: lower fills first (they are the narrow ones in production) */
 GDP_HD void tri_fills_of (const gmapdp_box &b, TriPacking &tp) {
   const bool two = (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA);
-  int f = 0;
-  tp.band[f] = b.lbandL; tp.nA[f] = b.glenL; tp.nB[f] = b.rlenL; f++;		/* L lower */
-  if (two) { tp.band[f] = b.lbandR; tp.nA[f] = b.glenR; tp.nB[f] = b.rlenR; f++; }	/* R lower */
-  tp.band[f] = b.ubandL; tp.nA[f] = b.rlenL; tp.nB[f] = b.glenL; f++;		/* L upper */
-  if (two) { tp.band[f] = b.ubandR; tp.nA[f] = b.rlenR; tp.nB[f] = b.glenR; f++; }	/* R upper */
-  tp.nf = f;
+  /* constant indices (see tri_pack): two-sided boxes L lower, R lower, L upper, R upper; else L lower, L upper */
+  tp.band[0] = b.lbandL; tp.nA[0] = b.glenL; tp.nB[0] = b.rlenL;
+  if (two) {
+    tp.band[1] = b.lbandR; tp.nA[1] = b.glenR; tp.nB[1] = b.rlenR;
+    tp.band[2] = b.ubandL; tp.nA[2] = b.rlenL; tp.nB[2] = b.glenL;
+    tp.band[3] = b.ubandR; tp.nA[3] = b.rlenR; tp.nB[3] = b.glenR;
+    tp.nf = 4;
+  } else {
+    tp.band[1] = b.ubandL; tp.nA[1] = b.rlenL; tp.nB[1] = b.glenL;
+    tp.band[2] = 0; tp.nA[2] = 0; tp.nB[2] = 0; tp.band[3] = 0; tp.nA[3] = 0; tp.nB[3] = 0;
+    tp.pass0[2] = tp.pass0[3] = 0; tp.npass[2] = tp.npass[3] = 0; tp.lane0[2] = tp.lane0[3] = 0;
+    tp.nf = 2;
+  }
   tri_pack(tp);
 }
 

@@ -34,7 +34,7 @@ def load_library():
     if _lib is None:
         if not os.path.exists(LIB):
             raise EngineError("native library %s is missing: run __graft_entry__.build() (nvcc, sm_100a)" % LIB)
-        lib = C.CDLL(os.environ.get("GMAPDP_LIB", LIB))	# GMAPDP_LIB: tuning builds of the same sources
+        lib = C.CDLL(os.environ.get("GMAPDP_LIB") or LIB)	# GMAPDP_LIB: tuning builds of the same sources
         lib.gmapdp_last_error.restype = C.c_char_p
         lib.gmapdp_launch_count.restype = C.c_long
         lib.GmapDP_batch_new.restype = C.c_void_p

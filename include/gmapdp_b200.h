@@ -113,7 +113,7 @@ int gmapdp_download (gmapdp_ctx *ctx, gmapdp_result *results, uint32_t *script, 
  * one each for the end, genome and cdna boxes (E-only fills + searches / bridges).  gmapdp_run_resident queues
  * them back to back on one stream (each is a persistent grid over all SMs), so their CUDA-event durations are
  * exact: full_ms = the single-gap kernel, tri_ms = the other three together; ms[4] = single, end, genome, cdna.
- * gmapdp_run_batch launches the kernels of its chunks on four streams. */
+ * gmapdp_run_batch queues the kernels of its chunks the same way, behind each chunk's upload. */
 int gmapdp_last_kernel_ms (const gmapdp_ctx *ctx, float *full_ms, float *tri_ms);
 int gmapdp_last_kernel_ms4 (const gmapdp_ctx *ctx, float *ms);
 /* number of kernel launches issued by this context so far */
