@@ -34,6 +34,12 @@
 #include "gmapdp_tables.h"
 
 #define WARPS_PER_BLOCK 4
+#ifndef GMAPDP_BND_GLOBAL
+#define GMAPDP_BND_GLOBAL 0	/* 1: single-gap kernel keeps its stripe boundary rows in the HBM workspace (L1) instead of shared
+				   memory, which lifts its occupancy from 3 to 4-6 blocks/SM.  Measured (500 k single-gap boxes):
+				   shared 69.3 ms; workspace 75.0 (4 blocks, 127 registers), 69.4 (5 blocks, 96), 67.6 (6 blocks, 80):
+				   the kernel is bound by its instruction count, not by latency -- left off. */
+#endif
 #define BLOCK_THREADS (WARPS_PER_BLOCK * 32)
 #define FULLMASK 0xffffffffu
 #define NEG32 (-32768)
@@ -1290,6 +1296,13 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 
   if (FULLK) {
     FGeom fg = fgeom(b.rlenL,b.glenL,b.lbandL,b.ubandL);
+#if GMAPDP_BND_GLOBAL
+    /* the stripe boundary row lives in the warp's workspace (L1-resident: 8 B per column, read once and written
+       once per stripe, addresses known in advance), not in shared memory: the kernel's occupancy is then set by
+       its registers alone (4 blocks/SM instead of the 3 that 65 KB of boundary rows per block allowed) */
+    if ((reinterpret_cast<uintptr_t>(wp) & 7) != 0) wp++;
+    bnd = reinterpret_cast<uint2 *>(wp); wp += 2 * (size_t) (b.glenL + 2);
+#endif
     uint32_t *dirs = wp;
     const bool alt = (b.gLalt_off != b.gL_off);
     if (lateL) { if (alt) fill_full<true,true>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb,ka.one);
@@ -1419,7 +1432,7 @@ extern __shared__ __align__(16) unsigned char dyn_smem[];
    no shared memory).  A specialisation carries only its own mode's code, so the warps of an SM share their
    instruction-cache footprint; the four are launched on four streams and share the SMs. */
 #ifndef GMAPDP_FULL_MINB
-#define GMAPDP_FULL_MINB 3
+#define GMAPDP_FULL_MINB (GMAPDP_BND_GLOBAL ? 4 : 3)
 #endif
 #ifndef GMAPDP_TRI_MINB
 #define GMAPDP_TRI_MINB 5
@@ -1613,6 +1626,14 @@ static inline void sort_chunk (std::vector<std::pair<double,int> > &work, int b0
 
 /* geometry and device allocations of a batch (no copies).  work[i] = (key, box id); within a chunk
    the sorted order lists the boxes kind by kind (key offset by -1e12 per kind) and chunk_count[k][kind] counts them. */
+/* dynamic shared memory of a kernel kind: 8 bytes per column and warp (single gaps: the stripe boundary rows,
+   unless they live in the workspace; cdna gaps: the bridge's M and Q tables); the other kinds use none */
+static inline size_t kind_smem (const gmapdp_ctx *ctx, int kind) {
+  if (kind == 0 && GMAPDP_BND_GLOBAL) return 0;
+  if (kind == 1 || kind == 2) return 0;
+  return (size_t) WARPS_PER_BLOCK * ctx->ksmem_cols[kind] * 8;
+}
+
 struct PlanScan { size_t ws_words[GDP_NK], script_need; int maxcols[GDP_NK]; };
 
 /* bytes a box makes the end-to-end path upload (sequences once, alt twins are shared; MaxEnt doubles) */
@@ -1694,8 +1715,8 @@ static int plan_finish (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, si
   for (int kind = 0; kind < GDP_NK; kind++) {
     ctx->kws_words[kind] = (ws_words[kind] + 31) & ~(size_t) 31;
     ctx->ksmem_cols[kind] = (maxcols[kind] + 7) & ~7;
-    size_t smem = (size_t) WARPS_PER_BLOCK * ctx->ksmem_cols[kind] * 8;
-    if ((int) smem > ctx->max_smem) { ctx->err = "box too long for the shared-memory boundary rows"; return GMAPDP_ERR_ARG; }
+    size_t smem = kind_smem(ctx,kind);
+    if ((int) smem > ctx->max_smem) { ctx->err = "box too long for the shared-memory rows"; return GMAPDP_ERR_ARG; }
     int occ = 0;
     if (kind == 0) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<0>,BLOCK_THREADS,smem));
     else if (kind == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<1>,BLOCK_THREADS,smem));
@@ -1752,7 +1773,7 @@ static int launch_chunk (gmapdp_ctx *ctx, int first, const int *cnt, bool timed 
     ka.script = ctx->d_script; ka.script_cap = ctx->cap_script; ka.script_cursor = ctx->d_cursor;
     ka.queue = ctx->d_queue + kind; ka.ws = ctx->d_kws[kind]; ka.ws_words = ctx->kws_words[kind];
     ka.smem_cols = ctx->ksmem_cols[kind]; ka.tables = ctx->d_tables; ka.one = 1u;
-    const size_t smem = (size_t) WARPS_PER_BLOCK * ctx->ksmem_cols[kind] * 8;
+    const size_t smem = kind_smem(ctx,kind);
     const int grid = std::max(1,std::min(ctx->kgrid[kind],(count + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
     CK(cudaMemsetAsync(ctx->d_queue + kind,0,sizeof(int),st));
     if (timed) CK(cudaEventRecord(ctx->evk[kind][0],st));

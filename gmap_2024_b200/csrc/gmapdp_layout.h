@@ -120,6 +120,7 @@ GDP_HD size_t gdp_ws_words (const gmapdp_box &b) {
   if (b.mode == GMAPDP_SINGLE) {
     FGeom f = fgeom(b.rlenL,b.glenL,b.lbandL,b.ubandL);
     w += (size_t) f.nstripes * f.dirW;
+    w += 2 * (size_t) (b.glenL + 2) + 2;					/* stripe boundary row (8 bytes per column) */
   } else {
     const bool scores = (b.mode == GMAPDP_CDNA);	/* genome gaps evaluate their bridge inside the fills */
     TriPacking tp;
