@@ -1,7 +1,7 @@
 /* gmapdp_kernels.cu -- sm_100a kernels and the C ABI of the GMAP alignment-DP engine.
  *
- * One persistent grid; every warp pulls DP boxes (largest first) from a global queue and runs the
- * whole device part of one reference entry point on it:
+ * Four persistent grids, one per kind of box (single / end / genome / cdna gaps); every warp pulls DP boxes
+ * (largest first) from its kind's queue and runs the whole device part of one reference entry point on it:
  *
  *   fill_full    Dynprog_simd_8 / Dynprog_simd_16            (/root/reference/src/dynprog_simd.c:2987 / :6562)
  *                32-row stripes, lane = row, lanes skewed by one column (systolic wavefront): the
@@ -9,10 +9,12 @@
  *                (the reference's scalar F loop, :3391-3471) arrive by one warp shuffle each per step.
  *                Out-of-band lanes are computed exactly as the AVX2 code does (32 int8 lanes = one
  *                warp), which is what makes the 8-bit fill bit-exact.
- *   fill_tri<>   Dynprog_simd_{8,16}_upper / _lower          (:4304,:7714 / :5340,:8586)
- *                lane = row (upper) or column (lower), all lanes on the same step; one shuffle per step.
- *   best_end     find_best_endpoint_* (dynprog_end.c:143-560) fused into the fills.
- *   bridge_*     bridge_intron_gap_*_site_level (dynprog_genome.c:866), bridge_cdna_gap_*_ud (dynprog_cdna.c:123)
+ *   tri_pass<>   Dynprog_simd_{8,16}_upper / _lower          (:4304,:7714 / :5340,:8586)
+ *                lane = band diagonal, all lanes on the same step; one shuffle per step; a branch-free
+ *                interior loop (tri_fast) and a general step for heads, tails and wide fills.
+ *   best end     find_best_endpoint_* (dynprog_end.c:143-560), fused into the fills (end gaps).
+ *   bridges      bridge_intron_gap_*_site_level (dynprog_genome.c:866) evaluated inside the fills (genome gaps),
+ *                bridge_cdna_gap_*_ud (dynprog_cdna.c:123) from prefix-best tables (cdna gaps).
  *   tb_*         Dynprog_traceback_* (dynprog_simd.c:9154-9946) -> run-length edit script.
  *
  * Direction planes are written to HBM as packed 2-bit / 4-bit cells, 128 B per warp store
@@ -934,23 +936,6 @@ __device__ void tb_full (TbAcc &a, const SideSeq &sd, const uint32_t *dirs, cons
 /* ------------------------------------------------------------------------------------------------
  * Bridges
  * ---------------------------------------------------------------------------------------------- */
-struct Cand { int s; double p; unsigned long long ord; int rL, rR, cL, cR; };
-
-__device__ __forceinline__ bool cand_better (const Cand &a, const Cand &b) {	/* a beats b */
-  if (a.s != b.s) return a.s > b.s;
-  if (a.p != b.p) return a.p > b.p;
-  return a.ord < b.ord;
-}
-
-__device__ __forceinline__ Cand cand_shfl (const Cand &a, int srclane) {
-  Cand o;
-  o.s = __shfl_sync(FULLMASK,a.s,srclane); o.p = __shfl_sync(FULLMASK,a.p,srclane);
-  o.ord = __shfl_sync(FULLMASK,a.ord,srclane);
-  o.rL = __shfl_sync(FULLMASK,a.rL,srclane); o.rR = __shfl_sync(FULLMASK,a.rR,srclane);
-  o.cL = __shfl_sync(FULLMASK,a.cL,srclane); o.cR = __shfl_sync(FULLMASK,a.cR,srclane);
-  return o;
-}
-
 __device__ __forceinline__ int intron_points (const int *isc, int ldi, int rdi) {
   const int t = ldi & rdi;
   return t ? isc[31 - __clz(t)] : 0;
@@ -1810,15 +1795,6 @@ static int fork_streams (gmapdp_ctx *ctx, cudaEvent_t ev) {
   for (int k = 1; k < GDP_NK; k++) CK(cudaStreamWaitEvent(ctx->kstream[k],ev,0));
   return GMAPDP_OK;
 }
-/* join: `stream' continues after everything queued on the other kernel streams */
-static int join_streams (gmapdp_ctx *ctx) {
-  for (int k = 1; k < GDP_NK; k++) {
-    CK(cudaEventRecord(ctx->evj[k],ctx->kstream[k]));
-    CK(cudaStreamWaitEvent(ctx->stream,ctx->evj[k],0));
-  }
-  return GMAPDP_OK;
-}
-
 extern "C" int gmapdp_upload (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes,
 			      const uint8_t *seqpool, size_t seqbytes, const double *probpool, size_t nprobs) {
   if (!ctx || nboxes < 0 || (nboxes > 0 && (!boxes || !seqpool))) { if (ctx) ctx->err = "bad argument"; return GMAPDP_ERR_ARG; }
