@@ -5,6 +5,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libgmapdp_b200.so")
+# test build: the genome bridge's per-lane tie lists hold ONE entry, so that their overflow path (the fills
+# repeated with every tie resolved on the spot) runs on ordinary boxes; loaded only by the GPU parity tests
+LIB_TIECAP1 = os.path.join(CSRC, "libgmapdp_b200_tiecap1.so")
 SOURCES = ["gmapdp_kernels.cu", "gmapdp_shim.cpp", "gmapchain_kernels.cu", "gmapchain_shim.cpp"]
 HEADERS = ["gmapdp_layout.h", "gmapdp_tables.h", "gmapdp_internal.h", "../../include/gmapdp_b200.h", "../../include/gmapdp_shim.h",
            "../../include/gmapchain_b200.h"]
@@ -21,8 +24,10 @@ def _stale(target, deps):
 
 def build_native(force=False, verbose=False):
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    nvcc = os.environ.get("NVCC", "nvcc")
     if force or _stale(LIB, deps):
-        nvcc = os.environ.get("NVCC", "nvcc")
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
         subprocess.check_call(cmd, cwd=CSRC)
+    if force or _stale(LIB_TIECAP1, deps):
+        subprocess.check_call([nvcc] + NVCC_FLAGS + ["-DGEN_TIECAP=1", "-o", LIB_TIECAP1] + SOURCES, cwd=CSRC)
     return LIB

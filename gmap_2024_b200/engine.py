@@ -25,16 +25,18 @@ class DeviceResult(C.Structure):
                                          "script_lenB", "cells", "reserved")]
 
 
-_lib = None
+_libs = {}
 
 
-def load_library():
-    """Loads the native library; raises if it has not been built (``__graft_entry__.build()``)."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB):
-            raise EngineError("native library %s is missing: run __graft_entry__.build() (nvcc, sm_100a)" % LIB)
-        lib = C.CDLL(os.environ.get("GMAPDP_LIB") or LIB)	# GMAPDP_LIB: tuning builds of the same sources
+def load_library(path=None):
+    """Loads the native library; raises if it has not been built (``__graft_entry__.build()``).
+    ``path`` (or the environment variable GMAPDP_LIB) selects another build of the same sources: tuning builds
+    (scripts/variants.sh) and the test build with one-entry tie lists (build.LIB_TIECAP1)."""
+    path = path or os.environ.get("GMAPDP_LIB") or LIB
+    if path not in _libs:
+        if not os.path.exists(path):
+            raise EngineError("native library %s is missing: run __graft_entry__.build() (nvcc, sm_100a)" % path)
+        lib = C.CDLL(path)
         lib.gmapdp_last_error.restype = C.c_char_p
         lib.gmapdp_launch_count.restype = C.c_long
         lib.GmapDP_batch_new.restype = C.c_void_p
@@ -55,8 +57,8 @@ def load_library():
         lib.GmapChain_batch_digest.restype = C.c_ulonglong
         for fn in ("gmapdp_destroy", "gmapdp_last_error", "gmapdp_launch_count", "gmapdp_device_info"):
             getattr(lib, fn).argtypes = None
-        _lib = lib
-    return _lib
+        _libs[path] = lib
+    return _libs[path]
 
 
 def _b(s):
@@ -64,8 +66,8 @@ def _b(s):
 
 
 class Engine:
-    def __init__(self, device=0):
-        self.lib = load_library()
+    def __init__(self, device=0, lib_path=None):
+        self.lib = load_library(lib_path)
         self.ctx = C.c_void_p()
         rc = self.lib.gmapdp_create(C.byref(self.ctx), int(device))
         if rc != 0:

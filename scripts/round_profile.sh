@@ -14,6 +14,6 @@ for spec in "1 full" "2 genome"; do
   $CMD2 > gpurun_out/plain_$2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gmapdp -c 1 -o gpurun_out/prof_$2 $CMD2 > gpurun_out/ncu_$2.log 2>&1
 done
 # the overflow path of the bridge's tie lists: the same parity tests against a build with one-entry lists
-[ -f build/variants/lib_tiecap1.so ] && GMAPDP_LIB=build/variants/lib_tiecap1.so python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py tests/test_gpu_bench_workload.py -x -q -k "genome or mixed or golden or workload or medium" 2>&1 | tail -3 > gpurun_out/tiecap1_tests.log
+python -m pytest tests/test_gpu_parity.py -x -q -k tie_list_overflow 2>&1 | tail -3 > gpurun_out/tiecap1_tests.log
 cat gpurun_out/tiecap1_tests.log
 ls -la gpurun_out

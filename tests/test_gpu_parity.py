@@ -112,3 +112,20 @@ def test_low_complexity_ties(engine, oracle, mode):
 def test_low_complexity_large_genome(engine, oracle):
     boxes = dpgen.lowcomplexity_boxes(seed=77, n=40, mode="genome", rmin=600, rmax=1600)
     run_and_compare(engine, oracle, boxes, "low-complexity large genome")
+
+
+def test_tie_list_overflow_path(oracle):
+    """the genome bridge keeps at most GEN_TIECAP tied candidates per lane inside the fills and repeats the fills
+    when a winning lane's list overflowed; a build with one-entry lists takes that path on ordinary boxes"""
+    import os
+    from gmap_2024_b200 import Engine
+    from gmap_2024_b200.build import LIB_TIECAP1
+    assert os.path.exists(LIB_TIECAP1), "run __graft_entry__.build()"
+    eng = Engine(0, lib_path=LIB_TIECAP1)
+    try:
+        boxes = dpgen.synth_boxes(seed=41, n=500, mode="genome", rmin=8, rmax=400)
+        boxes += dpgen.lowcomplexity_boxes(seed=42, n=300, mode="genome", rmin=8, rmax=300)
+        boxes += dpgen.synth_boxes(seed=43, n=12, mode="genome", rmin=900, rmax=1900)
+        run_and_compare(eng, oracle, boxes, "one-entry tie lists")
+    finally:
+        eng.close()
