@@ -229,7 +229,9 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
   const uint8_t *odi = NULL, *pdi = NULL; const short *pdg = NULL;
   int key = 0;
   GenBest g; g.s = 0; g.key = -1; g.cnt = 0; g.p = 0.0; g.ties = NULL;
+  GenCtx gcl; gcl.it0 = 0; gcl.it1 = 0;		/* the intron score table in registers (a store sits between its uses) */
   if (EVAL) {
+    gcl.it0 = gc->it0; gcl.it1 = gc->it1;
     g = *gb;
     const int col = s.lower ? t - s.d : t, rP = gc->rlength - (s.lower ? t : t - s.d);
     odi = s.own_di + col; pdi = s.oth_di + rP; pdg = s.oth_dg + rP;
@@ -273,7 +275,7 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
 	  bs = up ? Hn : bs; btt = up ? tb + u : btt;
 	}
 	if (EVAL) {
-	  const int tot = Hn + gen_points(*gc,(int) odi[u] & (int) pdi[-u]) + (int) pdg[-u];
+	  const int tot = Hn + gen_points(gcl,(int) odi[u] & (int) pdi[-u]) + (int) pdg[-u];
 	  const int ku = key + u * s.kstep;
 	  const bool gt = s.ev_ok && tot > g.s, eq = s.ev_ok && tot == g.s;
 	  if (eq && tieoff < GEN_TIECAP * 128u) *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(g.ties) + tieoff) = (uint32_t) ku;
@@ -431,7 +433,7 @@ __device__ __forceinline__ void tri_pass_body (const TriFill (&F)[GDP_MAXFILLS],
       if (SCORES) { *s.splane = s.sacc; s.splane += 32; s.sacc = 0; }
       if ((t & 15) == 14) { *s.dplane = s.dacc; s.dplane += 32; s.dacc = 0; }
     }
-    if (phase == 0 && hasfast) {
+    if (!WIDE && phase == 0 && hasfast) {
       /* end gaps have one tie rule per box: two lean copies; the two-sided modes mix the rules: one copy, rule per lane */
       if (MODE == 0 && lm == 0) tri_fast<MODE,0>(s,t,F1,open,extend,NEG,POS,negpair,bt,gc,gb);
       else if (MODE == 0 && lm == 1) tri_fast<MODE,1>(s,t,F1,open,extend,NEG,POS,negpair,bt,gc,gb);
@@ -449,14 +451,16 @@ __device__ __noinline__ void tri_pass_call (const TriFill (&F)[GDP_MAXFILLS], in
 			  bool ev_now) {
   tri_pass_body<MODE,WIDE>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok,gc,gb,ev_now);
 }
-#ifndef GMAPDP_END_INLINE
-#define GMAPDP_END_INLINE 1
+#ifndef GMAPDP_TRI_INLINE
+#define GMAPDP_TRI_INLINE 3	/* bit MODE set: that mode's passes are inlined into its kernel.  Measured (500 k boxes): inlining
+				   helps the end and cdna kernels (8.7 -> 8.2 ms, 12.2 -> 11.5 ms) and hurts the genome kernel (30.0 ->
+				   33-35 ms at 4-6 blocks/SM: its pass is the biggest and spills once inlined) */
 #endif
 template <int MODE, bool WIDE>
 __device__ __forceinline__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
 			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok, const GenCtx *gc, GenBest *gb,
 			  bool ev_now) {
-  if (MODE == 0 && GMAPDP_END_INLINE) tri_pass_body<MODE,WIDE>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok,gc,gb,ev_now);
+  if ((GMAPDP_TRI_INLINE >> MODE) & 1) tri_pass_body<MODE,WIDE>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok,gc,gb,ev_now);
   else tri_pass_call<MODE,WIDE>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok,gc,gb,ev_now);
 }
 
@@ -1363,17 +1367,18 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 	gc.it1 = (uint32_t) isc[3] | ((uint32_t) isc[4] << 8) | ((uint32_t) isc[5] << 16);
 	GenBest gb; gb.s = NEG; gb.key = -1; gb.cnt = 0; gb.p = 0.0; gb.ties = wp + lane; wp += GEN_TIECAP * 32;
 	gen_diagonals(LU,RU,dgL,dgR,NEG,POS);
-	tri_fill_all<2>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,&gc,&gb);
-	__syncwarp();
-	if (gb.key >= 0) gb.p = -1.0;				/* no probability has been fetched inside the fills */
-	/* only the lanes that reached the warp's best score can win: their tie lists are the ones that count */
-	int smax = gb.s;
-	for (int off = 16; off > 0; off >>= 1) smax = max(smax,__shfl_xor_sync(FULLMASK,smax,off));
-	if (gb.s < smax) gb.cnt = 0;
-	if (__any_sync(FULLMASK,gb.cnt > GEN_TIECAP)) {		/* such a list overflowed: once more, ties resolved on the spot */
-	  gb.s = NEG; gb.key = -1; gb.cnt = 0; gb.p = 0.0;
-	  tri_fill_all<2>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,&gc,&gb,true);
+	/* one call site (the fills are inlined): the second round runs only if a tie list that counts overflowed */
+	for (int round = 0; round < 2; round++) {
+	  tri_fill_all<2>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,&gc,&gb,round == 1);
 	  __syncwarp();
+	  if (round == 1) break;
+	  if (gb.key >= 0) gb.p = -1.0;				/* no probability has been fetched inside the fills */
+	  /* only the lanes that reached the warp's best score can win: their tie lists are the ones that count */
+	  int smax = gb.s;
+	  for (int off = 16; off > 0; off >>= 1) smax = max(smax,__shfl_xor_sync(FULLMASK,smax,off));
+	  if (gb.s < smax) gb.cnt = 0;
+	  if (!__any_sync(FULLMASK,gb.cnt > GEN_TIECAP)) break;
+	  gb.s = NEG; gb.key = -1; gb.cnt = 0; gb.p = 0.0;	/* such a list overflowed: once more, ties resolved on the spot */
 	}
 	fs = bridge_genome_finish(b,gc,gb,NEG,isc,&brL,&brR,&bcL,&bcR);
 	if (fs < 0) res.status = 1;
