@@ -752,7 +752,11 @@ __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int 
 	*dp = a8; dp += 32; bp += 8; tt += 8; c += 8; \
       } \
       while (tt <= fe) FAST_STEP(FIRSTFLAG); } while (0)
-#define GEN_ONE(U) full_gen<LATE,ALT>(st,isl0,isl31,c + (U),c + (U) - r,rowact && c + (U) >= c0 && c + (U) <= chigh,rlo == 0,rlo + uband, \
+    /* a lane is active on the steps tt = lane .. lane + (chigh - c0) of its stripe (and never past the last row):
+       one subtraction and one unsigned compare per step */
+    const int act_first = rowact ? lane : 0x40000000;
+    const unsigned act_span = (unsigned) (chigh - c0);
+#define GEN_ONE(U) full_gen<LATE,ALT>(st,isl0,isl31,c + (U),c + (U) - r,(unsigned) (tt + (U) - act_first) <= act_span,rlo == 0,rlo + uband, \
 				     lband,uband,open,extend,NEG,POS,plo,p4,bnd)
 #define GEN_STEPS(END) do { \
       while (tt < (END) && (tt & 7)) { acc |= GEN_ONE(0) << (4 * (tt & 7)); if ((tt & 7) == 7) { dst[(tt >> 3) * 32] = acc; acc = 0; } tt++; c++; } \
