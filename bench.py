@@ -355,7 +355,7 @@ def run_ours(args):
         value = tot_cells / (ms_per_step / 1e3) / 1e9
         e2e_value = tot_cells / (e2e_ms_max / args.steps / 1e3) / 1e9
         peak, peak_src = measured_peaks()
-        # roofline of the dominant kernel of a step, gmapdp_dp_kernel<true> (the full fills of the single-gap boxes):
+        # roofline of the dominant kernel of a step, gmapdp_dp_kernel<0> (the full fills of the single-gap boxes):
         # algorithmic bytes of THIS rank's launch / that kernel's own average duration
         cf, cf8 = batch.cells_full()
         algo_bytes = cf8 * BYTES_PER_CELL_8 + (cf - cf8) * BYTES_PER_CELL_16
