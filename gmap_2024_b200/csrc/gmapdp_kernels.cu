@@ -215,7 +215,21 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
 #ifndef GMAPDP_END_UNROLL
 #define GMAPDP_END_UNROLL 1
 #endif
-  constexpr int HALVES_UNROLLED = (MODE == 0) ? GMAPDP_END_UNROLL : 1;
+#ifndef GMAPDP_GENOME_UNROLL
+#define GMAPDP_GENOME_UNROLL 1
+#endif
+#ifndef GMAPDP_GENOME_UNR
+#define GMAPDP_GENOME_UNR 4
+#endif
+#ifndef GMAPDP_CDNA_UNR
+#define GMAPDP_CDNA_UNR 4
+#endif
+#ifndef GMAPDP_END_UNR
+#define GMAPDP_END_UNR 8
+#endif
+  /* steps per unrolled body (8, 4 or 2; 16 / UNR bodies per direction word) */
+  constexpr int UNR = (MODE == 2) ? GMAPDP_GENOME_UNR : ((MODE == 1) ? GMAPDP_CDNA_UNR : GMAPDP_END_UNR);
+  constexpr int HALVES_UNROLLED = (MODE == 0) ? GMAPDP_END_UNROLL : ((MODE == 2) ? GMAPDP_GENOME_UNROLL : 1);
   const uint2 *pq = s.pp + t;
   const uint4 *sq = reinterpret_cast<const uint4 *>(s.sel + t);
   const int la = s.lateadd;
@@ -244,13 +258,15 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
     /* two halves of 8 unrolled steps; the big two-sided kernels keep ONE copy of the half (instruction-cache
        footprint), the small end-gap kernel unrolls both */
 #pragma unroll HALVES_UNROLLED
-    for (int h = 0; h < 2; h++) {
-      const uint4 s4 = sq[h];
-      const uint32_t sw[4] = {s4.x,s4.y,s4.z,s4.w};
+    for (int h = 0; h < 16 / UNR; h++) {
+      uint32_t sw[4];
+      if (UNR == 8) { const uint4 s4 = sq[h]; sw[0] = s4.x; sw[1] = s4.y; sw[2] = s4.z; sw[3] = s4.w; }
+      else if (UNR == 4) { const uint2 s2 = reinterpret_cast<const uint2 *>(sq)[h]; sw[0] = s2.x; sw[1] = s2.y; sw[2] = 0; sw[3] = 0; }
+      else { sw[0] = reinterpret_cast<const uint32_t *>(sq)[h]; sw[1] = 0; sw[2] = 0; sw[3] = 0; }
       uint32_t d8 = 0;
       int Heven = 0;
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
+      for (int u = 0; u < UNR; u++) {
 	uint32_t pk_in = __shfl_up_sync(FULLMASK,pk_out,1);
 	if (isd0) pk_in = negpair;
 	const uint2 p = pq[u];
@@ -284,9 +300,9 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
 	}
 	H = Hn;
       }
-      pq += 8; tb += 8;
-      if (EVAL) { odi += 8; pdi -= 8; pdg -= 8; key += 8 * s.kstep; }
-      dacc |= d8 << (16 * h);
+      pq += UNR; tb += UNR;
+      if (EVAL) { odi += UNR; pdi -= UNR; pdg -= UNR; key += UNR * s.kstep; }
+      dacc |= d8 << (2 * UNR * h);
     }
     sq += 2;
     *dplane = isd0 ? 0u : dacc; dplane += 32;
