@@ -5,4 +5,4 @@ The product is the native library ``csrc/libgmapdp_b200.so`` (C ABI in ``include
 bench.py.  There is no CPU fallback: creating an :class:`Engine` without a CUDA device raises.
 (The package directory is ``gmap_2024_b200`` because ``gmap-2024_b200`` is not importable.)
 """
-from .engine import Engine, Batch, ChainBatch, EngineError, load_library  # noqa: F401
+from .engine import Engine, Batch, ChainBatch, Stream, EngineError, load_library  # noqa: F401

@@ -1480,7 +1480,7 @@ gmapdp_dp_kernel (KernelArgs ka) {
  * ---------------------------------------------------------------------------------------------- */
 #include "gmapdp_internal.h"
 
-#define GDP_NK 4
+#define GDP_NK GDP_NKINDS
 static inline int kind_of (int mode) { return mode == GMAPDP_SINGLE ? 0 : (mode == GMAPDP_GENOME ? 2 : (mode == GMAPDP_CDNA ? 3 : 1)); }
 
 struct gmapdp_ctx {
@@ -1511,6 +1511,7 @@ struct gmapdp_ctx {
   /* resident batch */
   int nboxes; size_t ws_words; int smem_cols; size_t script_need;
   long launches;
+  std::vector<int> occ_cache[GDP_NK];	/* flights: resident blocks per SM by shared-memory size class */
   /* the chaining engine (gmapchain_kernels.cu) hangs its state here */
   void *chain; void (*chain_free) (void *);
 };
@@ -1534,6 +1535,12 @@ static int grow (gmapdp_ctx *ctx, T **p, size_t *cap, size_t need) {
   CK(cudaMalloc((void **) p,n * sizeof(T)));
   *cap = n;
   return GMAPDP_OK;
+}
+
+extern "C" int gmapdp_device_count (void) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return ndev;
 }
 
 extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
@@ -1663,6 +1670,18 @@ static inline size_t kind_smem (const gmapdp_ctx *ctx, int kind) {
 
 struct PlanScan { size_t ws_words[GDP_NK], script_need; int maxcols[GDP_NK]; };
 
+/* The kernels pack rows and columns into 16-bit fields (best cells `r << 16 | c', the bridges' keys, the cDNA
+   bridge's `score << 16 | rR' tables) and the box carries its bands as int16: a side longer than 32767 would
+   corrupt best cells silently, so it is refused here.  Penalties are <= 0 (0 is reachable with --indel-open=0). */
+#define GDP_MAX_SIDE 32767
+static inline bool box_ok (const gmapdp_box &b) {
+  if (b.mode < 0 || b.mode > 4 || (unsigned) b.mismatchtype > 3u || b.open > 0 || b.extend > 0) return false;
+  if (b.rlenL < 0 || b.glenL < 0 || b.rlenR < 0 || b.glenR < 0) return false;
+  if (b.rlenL > GDP_MAX_SIDE || b.glenL > GDP_MAX_SIDE || b.rlenR > GDP_MAX_SIDE || b.glenR > GDP_MAX_SIDE) return false;
+  if (b.lbandL < 0 || b.ubandL < 0 || b.lbandR < 0 || b.ubandR < 0) return false;
+  return true;
+}
+
 /* bytes a box makes the end-to-end path upload (sequences once, alt twins are shared; MaxEnt doubles) */
 static inline uint32_t box_upload_bytes (const gmapdp_box &x) {
   size_t acc = (size_t) x.rlenL + x.rlenR + x.glenL + x.glenR;
@@ -1688,8 +1707,7 @@ static int plan_scan (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, std:
       const int i0 = (int) ((long long) nboxes * t / nthreads), i1 = (int) ((long long) nboxes * (t + 1) / nthreads);
       for (int i = i0; i < i1; i++) {
 	const gmapdp_box &b = boxes[i];
-	if (b.rlenL < 0 || b.glenL < 0 || b.rlenR < 0 || b.glenR < 0 || b.open >= 0 || b.extend >= 0 || b.mode < 0 || b.mode > 4 ||
-	    (unsigned) b.mismatchtype > 3u) { pt.bad = true; return; }
+	if (!box_ok(b)) { pt.bad = true; return; }
 	const int kind = kind_of(b.mode);
 	pt.ws[kind] = std::max(pt.ws[kind],gdp_ws_words(b));
 	pt.script += (size_t) b.rlenL + b.glenL + 4;
@@ -1843,7 +1861,12 @@ extern "C" int gmapdp_run_resident (gmapdp_ctx *ctx, float *kernel_ms) {
   CK(cudaSetDevice(ctx->device));
   if (kernel_ms) *kernel_ms = 0.f;
   if (ctx->nboxes == 0) return GMAPDP_OK;
-  if (ctx->chunk_count.size() < GDP_NK) return GMAPDP_OK;
+  if (ctx->chunk_count.size() != GDP_NK) {
+    /* the plan on the device is the chunked one of gmapdp_run_batch (d_order lists its chunks one after the other):
+       launching "chunk 0" would recompute only a part of the boxes */
+    ctx->err = "gmapdp_run_resident needs a batch uploaded by gmapdp_upload (the last gmapdp_run_batch was pipelined in several chunks)";
+    return GMAPDP_ERR_ARG;
+  }
   const int *cnt = &ctx->chunk_count[0];
   CK(cudaMemsetAsync(ctx->d_cursor,0,sizeof(unsigned long long),ctx->stream));
   CK(cudaEventRecord(ctx->ev0,ctx->stream));
@@ -1975,6 +1998,168 @@ extern "C" int gmapdp_run_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int n
   rc = gmapdp_download(ctx,results,script,script_cap,script_used);
   lap("results downloaded");
   return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Flights: the device half of the streaming runtime (gmapdp_stream.cpp).  gmapdp_run_batch is built for one
+ * large batch (parallel planning, chunked uploads); a drop-in that serves the dependent DP calls of many worker
+ * threads needs the opposite: thousands of small batches per second with a few tens of microseconds of fixed
+ * cost each.  A flight owns pinned host staging that the submitting threads fill in place, device twins of it,
+ * and is run by three H2D copies, one memset, up to four kernels (each kind on its own stream: the kernels of a
+ * small flight do not fill the GPU, so they run side by side) and ONE D2H copy of cursor + results + script.
+ * Nothing is allocated, planned or synchronised per flight besides what follows.
+ * ---------------------------------------------------------------------------------------------- */
+int gdp_bucket_count (void) { return GDP_NK * GDP_WORK_BUCKETS; }
+
+int gdp_box_geometry (const gmapdp_box *b, GdpBoxGeom *g) {
+  if (!box_ok(*b)) return GMAPDP_ERR_ARG;
+  g->kind = kind_of(b->mode);
+  g->bucket = work_bucket(g->kind,box_work(*b));
+  g->cols = (b->mode == GMAPDP_SINGLE || b->mode == GMAPDP_CDNA) ? (int) b->glenL + 2 : 8;
+  g->ws_words = gdp_ws_words(*b);
+  g->script_words = (size_t) b->rlenL + b->glenL + 4;
+  if (b->mode == GMAPDP_GENOME || b->mode == GMAPDP_CDNA) g->script_words += (size_t) b->rlenR + b->glenR + 4;
+  return GMAPDP_OK;
+}
+
+#define FCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    f->ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return GMAPDP_ERR_CUDA; } } while (0)
+
+static inline size_t flight_out_bytes (int nboxes, size_t script_words) { return 16 + (size_t) nboxes * sizeof(gmapdp_result) + script_words * sizeof(uint32_t); }
+
+int gdp_flight_create (gmapdp_ctx *ctx, GdpFlight **out, int max_boxes, size_t seq_cap, size_t prob_cap, size_t script_cap) {
+  GdpFlight *f = new GdpFlight();
+  memset(f,0,sizeof(*f));
+  *out = f;
+  f->ctx = ctx; f->max_boxes = max_boxes; f->seq_cap = seq_cap; f->prob_cap = prob_cap; f->script_cap = script_cap;
+  FCK(cudaSetDevice(ctx->device));
+  const size_t outb = flight_out_bytes(max_boxes,script_cap);
+  FCK(cudaHostAlloc((void **) &f->h_boxes,(size_t) max_boxes * sizeof(gmapdp_box),cudaHostAllocDefault));
+  FCK(cudaHostAlloc((void **) &f->h_order,(size_t) max_boxes * sizeof(int),cudaHostAllocDefault));
+  FCK(cudaHostAlloc((void **) &f->h_seq,seq_cap + 64,cudaHostAllocDefault));
+  FCK(cudaHostAlloc((void **) &f->h_probs,(prob_cap + 8) * sizeof(double),cudaHostAllocDefault));
+  FCK(cudaHostAlloc((void **) &f->h_out,outb,cudaHostAllocDefault));
+  FCK(cudaMalloc((void **) &f->d_boxes,(size_t) max_boxes * sizeof(gmapdp_box)));
+  FCK(cudaMalloc((void **) &f->d_order,(size_t) max_boxes * sizeof(int)));
+  FCK(cudaMalloc((void **) &f->d_seq,seq_cap + 64));
+  FCK(cudaMalloc((void **) &f->d_probs,(prob_cap + 8) * sizeof(double)));
+  FCK(cudaMalloc((void **) &f->d_out,outb));
+  FCK(cudaMalloc((void **) &f->d_ctl,GDP_NK * sizeof(int)));
+  cudaEvent_t e;
+  FCK(cudaEventCreateWithFlags(&e,cudaEventDisableTiming)); f->ev_in = (void *) e;
+  FCK(cudaEventCreateWithFlags(&e,cudaEventDisableTiming | cudaEventBlockingSync)); f->ev_done = (void *) e;	/* the completer sleeps, it does not spin: the host cores belong to the workers */
+  for (int k = 0; k < GDP_NK; k++) { FCK(cudaEventCreateWithFlags(&e,cudaEventDisableTiming)); f->ev_k[k] = (void *) e; }
+  return GMAPDP_OK;
+}
+
+void gdp_flight_destroy (GdpFlight *f) {
+  if (!f) return;
+  cudaSetDevice(f->ctx->device);
+  cudaFreeHost(f->h_boxes); cudaFreeHost(f->h_order); cudaFreeHost(f->h_seq); cudaFreeHost(f->h_probs); cudaFreeHost(f->h_out);
+  cudaFree(f->d_boxes); cudaFree(f->d_order); cudaFree(f->d_seq); cudaFree(f->d_probs); cudaFree(f->d_out); cudaFree(f->d_ctl);
+  if (f->ev_in) cudaEventDestroy((cudaEvent_t) f->ev_in);
+  if (f->ev_done) cudaEventDestroy((cudaEvent_t) f->ev_done);
+  for (int k = 0; k < GDP_NK; k++) if (f->ev_k[k]) cudaEventDestroy((cudaEvent_t) f->ev_k[k]);
+  delete f;
+}
+
+/* resident blocks per SM of a kernel kind at a given dynamic shared-memory size, asked once per size class */
+static int flight_occupancy (gmapdp_ctx *ctx, int kind, size_t smem) {
+  const size_t cls = (smem + 8191) / 8192;
+  std::vector<int> &cache = ctx->occ_cache[kind];
+  if (cache.size() <= cls) cache.resize(cls + 1,0);
+  if (cache[cls] == 0) {
+    int occ = 0;
+    cudaError_t e;
+    if (kind == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<0>,BLOCK_THREADS,cls * 8192);
+    else if (kind == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<1>,BLOCK_THREADS,cls * 8192);
+    else if (kind == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<2>,BLOCK_THREADS,cls * 8192);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<3>,BLOCK_THREADS,cls * 8192);
+    if (e != cudaSuccess) { cudaGetLastError(); occ = 1; }
+    cache[cls] = std::min(std::max(occ,1),8);
+  }
+  return cache[cls];
+}
+
+int gdp_flight_launch (GdpFlight *f, int n, size_t seqbytes, size_t nprobs, size_t script_need,
+		       const size_t *ws_words, const int *maxcols, const int *cnt) {
+  gmapdp_ctx *ctx = f->ctx;
+  if (n <= 0 || n > f->max_boxes || seqbytes > f->seq_cap || nprobs > f->prob_cap || script_need > f->script_cap) {
+    ctx->err = "flight over capacity"; return GMAPDP_ERR_CAPACITY;
+  }
+  FCK(cudaSetDevice(ctx->device));
+  f->n = n; f->script_need = script_need;
+  cudaStream_t s0 = ctx->stream;
+  /* geometry of the kernels this flight needs */
+  int grid[GDP_NK], cols[GDP_NK]; size_t wsw[GDP_NK], smem[GDP_NK];
+  for (int kind = 0; kind < GDP_NK; kind++) {
+    grid[kind] = 0; cols[kind] = 8; wsw[kind] = 0; smem[kind] = 0;
+    if (cnt[kind] == 0) continue;
+    wsw[kind] = (ws_words[kind] + 31) & ~(size_t) 31;
+    cols[kind] = (maxcols[kind] + 7) & ~7;
+    smem[kind] = (kind == 1 || kind == 2 || (kind == 0 && GMAPDP_BND_GLOBAL)) ? 0 : (size_t) WARPS_PER_BLOCK * cols[kind] * 8;
+    if ((int) smem[kind] > ctx->max_smem) { ctx->err = "box too long for the shared-memory rows"; return GMAPDP_ERR_ARG; }
+    const int full = ctx->sm_count * flight_occupancy(ctx,kind,smem[kind]);
+    grid[kind] = std::max(1,std::min(full,(cnt[kind] + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
+    /* the workspace is sized for a full grid once, so that it stops growing after the first large boxes */
+    if (grow(ctx,&ctx->d_kws[kind],&ctx->cap_kws[kind],(size_t) full * WARPS_PER_BLOCK * wsw[kind])) return GMAPDP_ERR_CUDA;
+  }
+  FCK(cudaMemcpyAsync(f->d_boxes,f->h_boxes,(size_t) n * sizeof(gmapdp_box),cudaMemcpyHostToDevice,s0));
+  FCK(cudaMemcpyAsync(f->d_order,f->h_order,(size_t) n * sizeof(int),cudaMemcpyHostToDevice,s0));
+  if (seqbytes) FCK(cudaMemcpyAsync(f->d_seq,f->h_seq,seqbytes,cudaMemcpyHostToDevice,s0));
+  if (nprobs) FCK(cudaMemcpyAsync(f->d_probs,f->h_probs,nprobs * sizeof(double),cudaMemcpyHostToDevice,s0));
+  FCK(cudaMemsetAsync(f->d_ctl,0,GDP_NK * sizeof(int),s0));
+  FCK(cudaMemsetAsync(f->d_out,0,16,s0));
+  FCK(cudaEventRecord((cudaEvent_t) f->ev_in,s0));
+  int nk = 0; for (int kind = 0; kind < GDP_NK; kind++) if (cnt[kind]) nk++;
+  const bool fan = (nk > 1 && n < 32768);		/* small flight: the kinds side by side on their own streams */
+  int start = 0;
+  for (int kind = 0; kind < GDP_NK; kind++) {
+    const int count = cnt[kind], first = start;
+    start += count;
+    if (count == 0) continue;
+    cudaStream_t st = fan ? ctx->kstream[kind] : s0;
+    if (st != s0) FCK(cudaStreamWaitEvent(st,(cudaEvent_t) f->ev_in,0));
+    KernelArgs ka;
+    ka.boxes = f->d_boxes; ka.order = f->d_order + first; ka.nboxes = count;
+    ka.seq = f->d_seq; ka.probs = f->d_probs;
+    ka.results = reinterpret_cast<gmapdp_result *>(f->d_out + 16);
+    ka.script = reinterpret_cast<uint32_t *>(f->d_out + 16 + (size_t) n * sizeof(gmapdp_result)); ka.script_cap = script_need;
+    ka.script_cursor = reinterpret_cast<unsigned long long *>(f->d_out);
+    ka.queue = f->d_ctl + kind; ka.ws = ctx->d_kws[kind]; ka.ws_words = wsw[kind];
+    ka.smem_cols = cols[kind]; ka.tables = ctx->d_tables; ka.one = 1u;
+    if (kind == 0) gmapdp_dp_kernel<0><<<grid[kind],BLOCK_THREADS,smem[kind],st>>>(ka);
+    else if (kind == 1) gmapdp_dp_kernel<1><<<grid[kind],BLOCK_THREADS,smem[kind],st>>>(ka);
+    else if (kind == 2) gmapdp_dp_kernel<2><<<grid[kind],BLOCK_THREADS,smem[kind],st>>>(ka);
+    else gmapdp_dp_kernel<3><<<grid[kind],BLOCK_THREADS,smem[kind],st>>>(ka);
+    FCK(cudaGetLastError());
+    ctx->launches++;
+    if (st != s0) { FCK(cudaEventRecord((cudaEvent_t) f->ev_k[kind],st)); FCK(cudaStreamWaitEvent(s0,(cudaEvent_t) f->ev_k[kind],0)); }
+  }
+  FCK(cudaMemcpyAsync(f->h_out,f->d_out,flight_out_bytes(n,script_need),cudaMemcpyDeviceToHost,s0));
+  FCK(cudaEventRecord((cudaEvent_t) f->ev_done,s0));
+  return GMAPDP_OK;
+}
+
+int gdp_flight_poll (GdpFlight *f) {
+  const cudaError_t e = cudaEventQuery((cudaEvent_t) f->ev_done);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) return 0;
+  f->ctx->err = std::string("flight: ") + cudaGetErrorString(e);
+  return GMAPDP_ERR_CUDA;
+}
+
+int gdp_flight_wait (GdpFlight *f) {
+  FCK(cudaEventSynchronize((cudaEvent_t) f->ev_done));
+  return GMAPDP_OK;
+}
+
+int gdp_flight_results (GdpFlight *f, const gmapdp_result **results, const uint32_t **script) {
+  const unsigned long long used = *reinterpret_cast<const unsigned long long *>(f->h_out);
+  if (used > f->script_need) { f->ctx->err = "device script pool overflow"; return GMAPDP_ERR_CAPACITY; }
+  *results = reinterpret_cast<const gmapdp_result *>(f->h_out + 16);
+  *script = reinterpret_cast<const uint32_t *>(f->h_out + 16 + (size_t) f->n * sizeof(gmapdp_result));
+  return GMAPDP_OK;
 }
 
 /* pinned host memory helpers (so that the shim's pools are DMA-able without a staging copy) */

@@ -19,6 +19,9 @@
 #include <vector>
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
+#include <thread>
+#include <atomic>
 
 namespace {
 
@@ -27,7 +30,8 @@ const int NEG_INFINITY_32 = -32768;
 const int MICROINTRON_LENGTH = 9, LAZY_INDEL = 1, INSERT_PAIRS = 9;
 
 const GdpHostTables &tables () { static GdpHostTables t; return t; }
-const GdpTables &dev_tables () { static GdpTables d; static bool ready = false; if (!ready) { tables().device_tables(&d); ready = true; } return d; }
+struct DevTablesHolder { GdpTables d; DevTablesHolder () { tables().device_tables(&d); } };
+const GdpTables &dev_tables () { static DevTablesHolder h; return h.d; }	/* C++11 magic static: thread-safe */
 double prob_at (const std::vector<double> &v, int k) { return (k >= 0 && (size_t) k < v.size()) ? v[k] : 0.0; }
 
 struct Counts { int score = 0, nmatches = 0, nmismatches = 0, nopens = 0, nindels = 0; };
@@ -194,6 +198,10 @@ struct gmapdp_batch {
   int count_mismatch = 0;
   std::string err;
   bool uploaded = false, overflow = false;
+  /* --indel-open / --indel-extend (user_dynprog_p: dynprog_single.c:470, dynprog_genome.c:3367, dynprog_end.c:1334,1964) */
+  bool user_dynprog = false; int user_open = 0, user_extend = 0;
+  /* registered pool extents (the vectors may move if a call is queued after pinning) */
+  void *pin_boxes = NULL, *pin_seq = NULL, *pin_probs = NULL;
 
   uint32_t add_bytes (const char *p, int n) {
     if (seqpool.size() + (size_t) n + 4 > 0xFFFFFFF0ull) { err = "sequence pool exceeds 4 GiB: split the batch"; overflow = true; return 0; }
@@ -210,16 +218,28 @@ extern "C" void GmapDP_maxlengths (int *max_rlength, int *max_glength, int maxlo
   *max_glength = std::max(*max_rlength + extraquerygap + std::max(extramaterial_end,extramaterial_paired),2000);
 }
 
+/* the kernels pack rows and columns into 16-bit fields (best cells, bridge keys): one box side is at most 32767 long */
+#define GDP_MAX_SIDE 32767
+
 extern "C" gmapdp_batch *GmapDP_batch_new (gmapdp_ctx *ctx, int max_rlength, int max_glength) {
+  if (max_rlength < 0 || max_glength < 0 || max_rlength > GDP_MAX_SIDE || max_glength > GDP_MAX_SIDE) return NULL;
   gmapdp_batch *b = new gmapdp_batch();
   b->ctx = ctx; b->max_rlength = max_rlength; b->max_glength = max_glength;
   return b;
 }
+extern "C" int GmapDP_batch_user_dynprog (gmapdp_batch *b, int user_open, int user_extend, int user_dynprog_p) {
+  /* gmap.c:5425-5445 clamps both to [-127, 0] */
+  if (user_dynprog_p && (user_open > 0 || user_extend > 0 || user_open < -127 || user_extend < -127)) {
+    b->err = "user penalties must be in [-127, 0]"; return GMAPDP_ERR_ARG;
+  }
+  b->user_dynprog = user_dynprog_p != 0; b->user_open = user_open; b->user_extend = user_extend;
+  return GMAPDP_OK;
+}
 static void host_free (gmapdp_batch *b, void *p) { if (b->bufs_pinned) gmapdp_host_free(p); else free(p); }
 static void unpin (gmapdp_batch *b, bool release_buffers) {
   if (b->pinned) {
-    gmapdp_host_unregister(b->boxes.data()); gmapdp_host_unregister(b->seqpool.data());
-    if (!b->probpool.empty()) gmapdp_host_unregister(b->probpool.data());
+    gmapdp_host_unregister(b->pin_boxes); gmapdp_host_unregister(b->pin_seq); gmapdp_host_unregister(b->pin_probs);
+    b->pin_boxes = b->pin_seq = b->pin_probs = NULL;
     b->pinned = false;
   }
   if (release_buffers) {
@@ -227,10 +247,13 @@ static void unpin (gmapdp_batch *b, bool release_buffers) {
     host_free(b,b->script); b->script = NULL; b->script_cap = 0;
   }
 }
+/* a call queued after the pools were page-locked may move them: drop the registration first */
+static inline void begin_queue (gmapdp_batch *b) { if (b->pinned) unpin(b,false); b->uploaded = false; }
 extern "C" void GmapDP_batch_clear (gmapdp_batch *b) {
   unpin(b,/*release_buffers*/false);		/* result / script buffers are reused by the next batch */
   b->calls.clear(); b->boxes.clear(); b->box_call.clear(); b->seqpool.clear(); b->probpool.clear();
   b->script_used = 0; b->cells = 0; b->cells8 = 0; b->cells_full = 0; b->cells8_full = 0; b->uploaded = false; b->overflow = false; b->err.clear();
+  b->count_mismatch = 0;
 }
 extern "C" void GmapDP_batch_free (gmapdp_batch *b) { if (b) { unpin(b,true); delete b; } }
 extern "C" long GmapDP_batch_cells8 (const gmapdp_batch *b) { return b->cells8; }
@@ -261,6 +284,7 @@ extern "C" int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char 
 				  const char *gsequence, const char *gsequence_alt, int jump_late_p,
 				  int extraband_single, int widebandp, double defect_rate) {
   static const int opens[3] = {-8,-7,-6}, extends[3] = {-3,-2,-1};		/* dynprog.h:59-68 */
+  begin_queue(b);
   b->calls.emplace_back();
   Call &c = b->calls.back();
   const int id = (int) b->calls.size() - 1;
@@ -294,7 +318,7 @@ extern "C" int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char 
   x.mode = GMAPDP_SINGLE;
   x.flags = (jump_late_p ? GMAPDP_F_LATE_L : 0) | (use8 ? GMAPDP_F_USE8 : 0);
   x.rlenL = x.rlenR = rlength; x.glenL = x.glenR = glength;
-  x.mismatchtype = (int8_t) mt; x.open = (int8_t) opens[qual]; x.extend = (int8_t) extends[qual];
+  x.mismatchtype = (int8_t) mt; x.open = (int8_t) (b->user_dynprog ? b->user_open : opens[qual]); x.extend = (int8_t) (b->user_dynprog ? b->user_extend : extends[qual]);
   x.lbandL = x.lbandR = (int16_t) lband; x.ubandL = x.ubandR = (int16_t) uband;
   x.qL_off = x.qR_off = b->add_bytes(c.quc.data(),rlength);
   x.gL_off = x.gR_off = b->add_bytes(c.gL.data(),glength);
@@ -309,6 +333,7 @@ static int end_gap (gmapdp_batch *b, bool end5, int dynprogindex, const char *rs
 		    int rlength, int glength, int roffset, int goffset, const char *gseq, const char *galt,
 		    int jump_late_p, int extraband_end, double defect_rate, int endalign, int require_pos_score_p) {
   static const int opens[3] = {-10,-8,-6}, extends[3] = {-2,-2,-2};		/* dynprog_end.c:89-95 */
+  begin_queue(b);
   b->calls.emplace_back();
   Call &c = b->calls.back();
   const int id = (int) b->calls.size() - 1;
@@ -365,7 +390,7 @@ static int end_gap (gmapdp_batch *b, bool end5, int dynprogindex, const char *rs
   x.mode = c.mode;
   x.flags = (late ? GMAPDP_F_LATE_L : 0) | (use8 ? GMAPDP_F_USE8 : 0) | (wide ? 0 : GMAPDP_F_LASTROW);
   x.rlenL = x.rlenR = rlength; x.glenL = x.glenR = glength;
-  x.mismatchtype = (int8_t) mt; x.open = (int8_t) opens[qual]; x.extend = (int8_t) extends[qual];
+  x.mismatchtype = (int8_t) mt; x.open = (int8_t) (b->user_dynprog ? b->user_open : opens[qual]); x.extend = (int8_t) (b->user_dynprog ? b->user_extend : extends[qual]);
   x.lbandL = x.lbandR = (int16_t) lband; x.ubandL = x.ubandR = (int16_t) uband;
   x.qL_off = x.qR_off = b->add_bytes(c.quc.data(),rlength);
   x.gL_off = x.gR_off = b->add_bytes(c.gL.data(),glength);
@@ -402,6 +427,7 @@ extern "C" int GmapDP_genome_gap (gmapdp_batch *b, int dynprogindex, const char 
 				  int maxpeelback, int halfp, int finalp) {
   static const int opens[3] = {-8,-7,-6}, extends[3] = {-3,-2,-1};	/* PAIRED_* == SINGLE_*, dynprog.h:59-75 */
   (void) maxpeelback;
+  begin_queue(b);
   b->calls.emplace_back();
   Call &c = b->calls.back();
   const int id = (int) b->calls.size() - 1;
@@ -485,7 +511,7 @@ extern "C" int GmapDP_genome_gap (gmapdp_batch *b, int dynprogindex, const char 
   x.flags = (jump_late_p ? GMAPDP_F_LATE_L : GMAPDP_F_LATE_R) | (use8 ? GMAPDP_F_USE8 : 0) |
     (finalp ? GMAPDP_F_FINALP : 0) | (halfp ? GMAPDP_F_HALFP : 0);
   x.rlenL = x.rlenR = rlength; x.glenL = glengthL; x.glenR = glengthR;
-  x.mismatchtype = (int8_t) mt; x.open = (int8_t) opens[qual]; x.extend = (int8_t) extends[qual];
+  x.mismatchtype = (int8_t) mt; x.open = (int8_t) (b->user_dynprog ? b->user_open : opens[qual]); x.extend = (int8_t) (b->user_dynprog ? b->user_extend : extends[qual]);
   x.cdna_direction = (int8_t) cdna_direction;
   x.lbandL = (int16_t) lbandL; x.ubandL = (int16_t) ubandL; x.lbandR = (int16_t) lbandR; x.ubandR = (int16_t) ubandR;
   x.qL_off = x.qR_off = b->add_bytes(c.quc.data(),rlength);
@@ -512,6 +538,7 @@ extern "C" int GmapDP_cdna_gap (gmapdp_batch *b, int dynprogindex,
 				const char *gsequence, const char *gsequence_alt,
 				const char *rev_gsequence, const char *rev_gsequence_alt,
 				int jump_late_p, int extraband_paired, double defect_rate) {
+  begin_queue(b);
   b->calls.emplace_back();
   Call &c = b->calls.back();
   const int id = (int) b->calls.size() - 1;
@@ -559,20 +586,19 @@ extern "C" int GmapDP_cdna_gap (gmapdp_batch *b, int dynprogindex,
 /* ------------------------------------------------------------------------------------------------
  * Completion: replay the device results
  * ---------------------------------------------------------------------------------------------- */
-static void check_counts (gmapdp_batch *b, const gmapdp_result &r, const Counts &n) {
+static void check_counts (int *count_mismatch, const gmapdp_result &r, const Counts &n) {
   if (r.tb_score != n.score || r.nmatches != n.nmatches || r.nmismatches != n.nmismatches || r.nopens != n.nopens || r.nindels != n.nindels)
-    b->count_mismatch++;
+    __atomic_fetch_add(count_mismatch,1,__ATOMIC_RELAXED);
 }
 
-static void finish_call (gmapdp_batch *b, Call &c) {
-  const gmapdp_result &r = b->results[c.box];
-  const uint32_t *ops = b->script + r.script_off;
+/* thread-safe: touches only its own call (and the shared mismatch counter, atomically) */
+static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, int *count_mismatch) {
   const int dpi = c.iout[0];
   if (c.mode == GMAPDP_SINGLE) {
     Pushed l; Counts n;
     Side sd = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
     Replayer(l,sd,dpi,n).run(0,c.rlenL,c.glenL,ops,r.script_lenA);
-    check_counts(b,r,n);
+    check_counts(count_mismatch,r,n);
     c.iout[1] = n.score; c.iout[2] = n.nmatches; c.iout[3] = n.nmismatches; c.iout[4] = n.nopens; c.iout[5] = n.nindels;
     bump(c.iout[0]);
     c.pairs.assign(l.begin(),l.end());		/* List_reverse of the consed list = push order */
@@ -584,7 +610,7 @@ static void finish_call (gmapdp_batch *b, Call &c) {
     if (c.end5) sd = Side{c.q.data() + c.rlenL - 1,c.quc.data() + c.rlenL - 1,c.gL.data() + c.glenL - 1,c.gLa.data() + c.glenL - 1,c.roffset,c.goffset,true};
     else sd = Side{c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
     Replayer(l,sd,dpi,n).run(r.bestcL >= r.bestrL ? 1 : 2,r.bestrL,r.bestcL,ops,r.script_lenA);
-    check_counts(b,r,n);
+    check_counts(count_mismatch,r,n);
     c.iout[1] = n.score; c.iout[2] = n.nmatches; c.iout[3] = n.nmismatches; c.iout[4] = n.nopens; c.iout[5] = n.nindels;
     if ((c.endalign == GMAPDP_QUERYEND_GAP || c.endalign == GMAPDP_BEST_LOCAL) && (n.nmatches + 1) < n.nmismatches) {
       c.iout[1] = 0; l.clear();
@@ -613,7 +639,7 @@ static void finish_call (gmapdp_batch *b, Call &c) {
     gp.introntype = c.introntype_in; gp.donor_prob = c.dout[0]; gp.acceptor_prob = c.dout[1];
     Side sl = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
     Replayer(l,sl,dpi,n).run(bestcL >= bestrL ? 1 : 2,bestrL,bestcL,ops + r.script_lenA,r.script_lenB);
-    check_counts(b,r,n);
+    check_counts(count_mismatch,r,n);
     c.iout[3] = n.score; c.iout[4] = n.nmatches; c.iout[5] = n.nmismatches; c.iout[6] = n.nopens; c.iout[7] = n.nindels;
     if (l.size() == 1) l.clear();
     bump(c.iout[0]);
@@ -642,7 +668,7 @@ static void finish_call (gmapdp_batch *b, Call &c) {
     }
     Side sl = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
     Replayer(l,sl,dpi,n).run(bestcL >= bestrL ? 1 : 2,bestrL,bestcL,ops + r.script_lenA,r.script_lenB);
-    check_counts(b,r,n);
+    check_counts(count_mismatch,r,n);
     c.iout[1] = n.score;
     if (l.size() == 1) l.clear();
     bump(c.iout[0]);
@@ -651,13 +677,49 @@ static void finish_call (gmapdp_batch *b, Call &c) {
   }
 }
 
-static int finish_all (gmapdp_batch *b) {
-  for (size_t i = 0; i < b->calls.size(); i++) {
-    Call &c = b->calls[i];
-    if (!c.done && c.box >= 0) { finish_call(b,c); c.done = true; }
+/* The replay of one call touches nothing but that call, so large batches are replayed by several host threads
+   (GMAPDP_REPLAY_THREADS, default: all hardware threads, at most 32). */
+static int finish_all (gmapdp_batch *b, const gmapdp_result *results, const uint32_t *script) {
+  const size_t n = b->calls.size();
+  auto work = [&](size_t i0, size_t i1) {
+    for (size_t i = i0; i < i1; i++) {
+      Call &c = b->calls[i];
+      if (!c.done && c.box >= 0) { const gmapdp_result &r = results[c.box]; finish_call(c,r,script + r.script_off,&b->count_mismatch); c.done = true; }
+    }
+  };
+  int nthreads = 1;
+  if (b->boxes.size() >= 4096) {
+    const char *e = getenv("GMAPDP_REPLAY_THREADS");
+    nthreads = e ? atoi(e) : (int) std::min(32u,std::max(1u,std::thread::hardware_concurrency()));
+    if (nthreads < 1) nthreads = 1;
+  }
+  if (nthreads == 1) work(0,n);
+  else {
+    /* dynamic blocks: boxes differ by three orders of magnitude in pair count */
+    std::atomic<size_t> next(0);
+    const size_t blk = 256;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back([&]() { for (;;) { const size_t i0 = next.fetch_add(blk); if (i0 >= n) break; work(i0,std::min(n,i0 + blk)); } });
+    for (auto &x : th) x.join();
   }
   if (b->count_mismatch) { b->err = "device traceback counts disagree with the host replay"; return GMAPDP_ERR_ARG; }
   return GMAPDP_OK;
+}
+
+/* The device part of the queued calls, for callers that run the boxes themselves (the streaming runtime of
+   gmapdp_stream.h runs them in batches shared with other threads) ... */
+extern "C" int GmapDP_batch_device_view (const gmapdp_batch *b, const gmapdp_box **boxes, int *nboxes, const uint8_t **seqpool, size_t *seqbytes,
+					 const double **probpool, size_t *nprobs) {
+  if (b->overflow) return GMAPDP_ERR_CAPACITY;
+  *boxes = b->boxes.data(); *nboxes = (int) b->boxes.size();
+  *seqpool = b->seqpool.data(); *seqbytes = b->seqpool.size();
+  *probpool = b->probpool.data(); *nprobs = b->probpool.size();
+  return GMAPDP_OK;
+}
+/* ... and their completion from results produced elsewhere: results[k] belongs to box k of the view, its ops start at
+   script[results[k].script_off] */
+extern "C" int GmapDP_batch_complete (gmapdp_batch *b, const gmapdp_result *results, const uint32_t *script) {
+  return finish_all(b,results,script);
 }
 
 static int ensure_host_buffers (gmapdp_batch *b) {
@@ -671,9 +733,10 @@ static int ensure_host_buffers (gmapdp_batch *b) {
   const bool big = (b->seqpool.size() + need * sizeof(uint32_t) > ((size_t) 8 << 20));
   if (big && !b->pinned) {
     /* the pools are complete: pin them in place so every H2D is a straight DMA */
-    gmapdp_host_register(b->boxes.data(),b->boxes.size() * sizeof(gmapdp_box));
-    gmapdp_host_register(b->seqpool.data(),b->seqpool.size());
-    if (!b->probpool.empty()) gmapdp_host_register(b->probpool.data(),b->probpool.size() * sizeof(double));
+    /* (a failed registration only costs speed: the copy is staged) */
+    if (gmapdp_host_register(b->boxes.data(),b->boxes.size() * sizeof(gmapdp_box)) == GMAPDP_OK) b->pin_boxes = b->boxes.data();
+    if (gmapdp_host_register(b->seqpool.data(),b->seqpool.size()) == GMAPDP_OK) b->pin_seq = b->seqpool.data();
+    if (!b->probpool.empty() && gmapdp_host_register(b->probpool.data(),b->probpool.size() * sizeof(double)) == GMAPDP_OK) b->pin_probs = b->probpool.data();
     b->pinned = true;
   }
   if (big != b->bufs_pinned && (b->results || b->script)) {
@@ -743,13 +806,13 @@ extern "C" int GmapDP_batch_download (gmapdp_batch *b) {
 extern "C" int GmapDP_batch_finish (gmapdp_batch *b) {
   int rc = GmapDP_batch_download(b);
   if (rc) return rc;
-  return finish_all(b);
+  return finish_all(b,b->results,b->script);
 }
 
 extern "C" int GmapDP_batch_run (gmapdp_batch *b) {
   int rc = GmapDP_batch_run_device(b);
   if (rc) return rc;
-  return finish_all(b);
+  return finish_all(b,b->results,b->script);
 }
 
 /* order-independent digest of the device results (scores, best cells, counts, scripts): what the
@@ -778,6 +841,18 @@ extern "C" int GmapDP_result (const gmapdp_batch *b, int id, int *iout, double *
   const int n = (int) c.pairs.size();
   for (int k = 0; k < n && k < maxpairs; k++) pairs[k] = c.pairs[k];
   return n;
+}
+
+/* zero-copy view of a completed call's pair list (head first); valid until the batch is cleared */
+extern "C" int GmapDP_result_view (const gmapdp_batch *b, int id, const int **iout, const double **dout, const gmapdp_pair **pairs) {
+  if (id < 0 || id >= (int) b->calls.size()) return -2;
+  const Call &c = b->calls[id];
+  if (!c.done) return -3;
+  if (iout) *iout = c.iout;
+  if (dout) *dout = c.dout;
+  if (c.isnull || c.pairs.empty()) { if (pairs) *pairs = NULL; return -1; }
+  if (pairs) *pairs = c.pairs.data();
+  return (int) c.pairs.size();
 }
 
 extern "C" const gmapdp_result *GmapDP_device_result (const gmapdp_batch *b, int id) {

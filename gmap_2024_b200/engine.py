@@ -49,6 +49,7 @@ def load_library(path=None):
         lib.GmapDP_batch_h2d_bytes.restype = C.c_size_t
         lib.GmapDP_batch_d2h_bytes.restype = C.c_size_t
         lib.GmapDP_device_result.restype = C.POINTER(DeviceResult)
+        lib.gmapdp_stream_error.restype = C.c_char_p
         lib.GmapChain_batch_new.restype = C.c_void_p
         lib.GmapChain_batch_error.restype = C.c_char_p
         lib.GmapChain_batch_nhits.restype = C.c_long
@@ -175,6 +176,21 @@ class Batch:
         if rc != 0:
             raise EngineError(self.lib.GmapDP_batch_error(self.h).decode())
 
+    def set_user_dynprog(self, user_open, user_extend, enabled=True):
+        """--indel-open / --indel-extend (Dynprog_*_setup's user_open, user_extend, user_dynprog_p)"""
+        self._check(self.lib.GmapDP_batch_user_dynprog(self.h, int(user_open), int(user_extend), int(bool(enabled))))
+
+    def device_view(self):
+        """(boxes*, nboxes, seq*, seqbytes, probs*, nprobs) of the queued device boxes, as ctypes values"""
+        boxes, seq, probs = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n, sb, npb = C.c_int(), C.c_size_t(), C.c_size_t()
+        self._check(self.lib.GmapDP_batch_device_view(self.h, C.byref(boxes), C.byref(n), C.byref(seq), C.byref(sb),
+                                                      C.byref(probs), C.byref(npb)))
+        return boxes, n.value, seq, sb.value, probs, npb.value
+
+    def complete(self, results, script):
+        self._check(self.lib.GmapDP_batch_complete(self.h, results, script))
+
     def run(self):
         self._check(self.lib.GmapDP_batch_run(self.h))
 
@@ -238,6 +254,65 @@ class Batch:
     def device_result(self, cid):
         p = self.lib.GmapDP_device_result(self.h, cid)
         return p.contents if p else None
+
+
+class Ticket(C.Structure):
+    _fields_ = [("flight", C.c_void_p), ("index", C.c_int), ("lane", C.c_int)]
+
+
+class Stream:
+    """The batching runtime (gmapdp_stream.h): many host threads submit single boxes, flights carry them to the
+    device(s).  ``call(batch)`` runs the ONE call queued in a private batch made with ``private_batch()``."""
+
+    def __init__(self, devices=(0,), max_boxes=0, lib_path=None):
+        self.lib = load_library(lib_path)
+        self.h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        rc = self.lib.gmapdp_stream_create(C.byref(self.h), devs, len(devices), int(max_boxes))
+        if rc != 0:
+            msg = self.lib.gmapdp_stream_error(self.h).decode() if self.h else "gmapdp_stream_create failed"
+            if self.h:
+                self.lib.gmapdp_stream_destroy(self.h)
+                self.h = C.c_void_p()
+            raise EngineError(msg)
+
+    def close(self):
+        if self.h:
+            self.lib.gmapdp_stream_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def private_batch(self, max_rlength=2000, max_glength=2030):
+        class _NoCtx:
+            pass
+        e = _NoCtx()
+        e.lib, e.ctx = self.lib, C.c_void_p()
+        return Batch(e, max_rlength, max_glength)
+
+    def call(self, batch):
+        """submit + wait + complete + release for the single call queued in ``batch``"""
+        boxes, n, seq, sb, probs, npb = batch.device_view()
+        if n == 0:
+            return
+        assert n == 1
+        t = Ticket()
+        res, ops = C.POINTER(DeviceResult)(), C.POINTER(C.c_uint32)()
+        if self.lib.gmapdp_stream_submit(self.h, boxes, seq, C.c_size_t(sb), probs, C.c_size_t(npb), C.byref(t)) != 0 or \
+           self.lib.gmapdp_stream_wait(self.h, C.byref(t), C.byref(res), C.byref(ops)) != 0:
+            raise EngineError(self.lib.gmapdp_stream_error(self.h).decode())
+        r = DeviceResult()
+        C.memmove(C.byref(r), res, C.sizeof(DeviceResult))
+        r.script_off = 0
+        try:
+            batch.complete(C.byref(r), ops)
+        finally:
+            self.lib.gmapdp_stream_release(self.h, C.byref(t))
+
+    def stats(self):
+        out = (C.c_double * 9)()
+        self.lib.gmapdp_stream_stats(self.h, out)
+        keys = ("boxes", "flights", "largest_flight", "reserved", "flight_seconds", "wait_seconds", "kernel_launches",
+                "h2d_bytes", "d2h_bytes")
+        return dict(zip(keys, [float(x) for x in out]))
 
 
 class ChainBatch:

@@ -50,7 +50,7 @@ enum { GMAPDP_SINGLE = 0, GMAPDP_GENOME = 1, GMAPDP_CDNA = 2, GMAPDP_END5 = 3, G
 #define GMAPDP_F_NOTRACE     0x40	/* end modes: require_pos_score_p => the reference skips the traceback */
 #define GMAPDP_F_BRIDGE_LATE 0x80	/* cdna bridge tie rule: >= (jump_late_p) instead of > */
 
-/* One DP box (80 bytes).  Sequences live in one byte pool; every *_off is an unsigned byte offset into it (pool < 4 GiB).
+/* One DP box (76 bytes).  Sequences live in one byte pool; every *_off is an unsigned byte offset into it (pool < 4 GiB).
  * All sequence arrays are stored FORWARD (ascending memory = ascending coordinate); sides that the
  * reference addresses through "rev_" pointers set the corresponding REV flag bit in `revmask` and
  * are read from their last element backwards, exactly like rev_rsequence / rev_gsequence. */
@@ -88,6 +88,8 @@ typedef struct gmapdp_result {
 
 typedef struct gmapdp_ctx gmapdp_ctx;
 
+/* number of CUDA devices visible to the process (0 if none / no driver) */
+int gmapdp_device_count (void);
 /* Creates an engine on CUDA device `device` (one context per GPU / per process rank). */
 int gmapdp_create (gmapdp_ctx **ctx, int device);
 void gmapdp_destroy (gmapdp_ctx *ctx);

@@ -57,8 +57,14 @@ typedef struct gmapdp_batch gmapdp_batch;
  * extramaterial_paired) would compute (dynprog.c:602-627); GmapDP_maxlengths does that arithmetic. */
 void GmapDP_maxlengths (int *max_rlength, int *max_glength, int maxlookback, int extraquerygap, int maxpeelback,
 			int extramaterial_end, int extramaterial_paired);
+/* NULL if a limit exceeds 32767 (rows and columns travel in 16-bit fields on the device) */
 gmapdp_batch *GmapDP_batch_new (gmapdp_ctx *ctx, int max_rlength, int max_glength);
 void GmapDP_batch_free (gmapdp_batch *b);
+/* --indel-open / --indel-extend: what Dynprog_single_setup / _genome_setup / _end_setup (dynprog_single.c:101,
+ * dynprog_genome.c:192, dynprog_end.c:120) store as user_open / user_extend / user_dynprog_p.  When set, single, genome and
+ * end gaps use these penalties instead of the defect_rate table (dynprog_single.c:470, dynprog_genome.c:3367,
+ * dynprog_end.c:1334,1964); cdna gaps never do (dynprog_cdna.c has no such branch).  Both in [-127, 0] (gmap.c:5425-5445). */
+int GmapDP_batch_user_dynprog (gmapdp_batch *b, int user_open, int user_extend, int user_dynprog_p);
 void GmapDP_batch_clear (gmapdp_batch *b);
 
 int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char *rsequence, const char *rsequenceuc,
@@ -113,8 +119,18 @@ size_t GmapDP_batch_h2d_bytes (const gmapdp_batch *b);
 size_t GmapDP_batch_d2h_bytes (const gmapdp_batch *b);
 const char *GmapDP_batch_error (const gmapdp_batch *b);
 
-/* Returns the number of pairs (list head first), or -1 for the reference's NULL list. */
+/* For callers that execute the device boxes themselves (gmapdp_stream.h: batches shared by many threads): the device
+ * part of the queued calls, and the completion of the calls from results produced elsewhere (results[k] = box k of the
+ * view, its ops at script + results[k].script_off). */
+int GmapDP_batch_device_view (const gmapdp_batch *b, const gmapdp_box **boxes, int *nboxes, const uint8_t **seqpool, size_t *seqbytes,
+			      const double **probpool, size_t *nprobs);
+int GmapDP_batch_complete (gmapdp_batch *b, const gmapdp_result *results, const uint32_t *script);
+
+/* Returns the number of pairs (list head first), or -1 for the reference's NULL list.  If the list is longer than
+ * maxpairs only maxpairs records are copied: compare the return value with maxpairs, or use GmapDP_result_view. */
 int GmapDP_result (const gmapdp_batch *b, int id, int *iout, double *dout, gmapdp_pair *pairs, int maxpairs);
+/* the same without a copy: pointers into the batch, valid until it is cleared */
+int GmapDP_result_view (const gmapdp_batch *b, int id, const int **iout, const double **dout, const gmapdp_pair **pairs);
 /* device-side view of one call (NULL if it never reached the device) */
 const gmapdp_result *GmapDP_device_result (const gmapdp_batch *b, int id);
 

@@ -1,0 +1,72 @@
+/* gmapdp_stream -- the batching runtime of the drop-in: DP boxes submitted by many host threads, one at a
+ * time, are gathered into device batches ("flights") and run on one or more B200s.
+ *
+ * Why it exists.  Behind the reference's call sites (stage3.c traverse_single_gap :8999, traverse_cdna_gap :9181,
+ * traverse_genome_gap :9341, extend_ending5/3 :10281/:10519) every DP call is synchronous and the calls of one
+ * query form a dependent chain, so a batch can only be made of calls of DIFFERENT worker threads
+ * (gmap.c:4867 worker_thread, `gmap -t N').  The reference has no such component: its threads never meet
+ * (gmap.c:4895-4907, per-worker Dynprog_T / Pairpool_T).  This runtime is the meeting point:
+ *
+ *   worker thread                      launcher thread (per GPU)          completer thread (per GPU)
+ *   -------------                      -------------------------          --------------------------
+ *   gmapdp_stream_submit(box)    -->   closes the open flight as soon     waits for the oldest flight's
+ *     reserves a slot in the open      as the GPU can take it (at most    D2H, publishes results, wakes
+ *     flight, copies its sequences     GMAPDP_STREAM_DEPTH flights in     the flight's waiters with one
+ *     into the pinned staging          flight), orders the boxes, issues  futex broadcast
+ *   gmapdp_stream_wait(ticket)         3 H2D + <= 4 kernels + 1 D2H
+ *     sleeps on the flight's futex
+ *   ... replays its own edit script (in parallel with all other workers) ...
+ *   gmapdp_stream_release(ticket)
+ *
+ * Flights are self-clocking: with an idle GPU a flight leaves with whatever it holds (latency), under load the
+ * next one fills while the previous ones run (throughput); no timeouts, no global lock around device work, no
+ * thundering herd (a waiter touches no mutex when it wakes).  Results never depend on how boxes were grouped.
+ *
+ * Multi-GPU: one lane (context, launcher, completer, flights) per device; a worker thread is pinned to one lane
+ * for its lifetime, so the dependent chain of a query stays on one device.  No collective.
+ * There is no CPU fallback: creation fails without an sm_100 device.
+ */
+#ifndef GMAPDP_STREAM_H
+#define GMAPDP_STREAM_H
+
+#include "gmapdp_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gmapdp_stream gmapdp_stream;
+
+typedef struct gmapdp_ticket {
+  void *flight;		/* opaque */
+  int index;		/* box index inside the flight */
+  int lane;
+} gmapdp_ticket;
+
+/* devices[ndevices]: CUDA device ordinals, one lane each.  max_boxes: capacity of a flight (0 = default 8192). */
+int gmapdp_stream_create (gmapdp_stream **s, const int *devices, int ndevices, int max_boxes);
+void gmapdp_stream_destroy (gmapdp_stream *s);
+const char *gmapdp_stream_error (const gmapdp_stream *s);
+int gmapdp_stream_ndevices (const gmapdp_stream *s);
+
+/* Submits one box.  The box's *_off fields are offsets into `seq' / `probs' (as produced by the entry points of
+ * gmapdp_shim.h on a private batch, GmapDP_batch_device_view); both arrays are copied before the call returns.
+ * Blocks only while every flight of the lane is busy. */
+int gmapdp_stream_submit (gmapdp_stream *s, const gmapdp_box *box, const uint8_t *seq, size_t seqbytes,
+			  const double *probs, size_t nprobs, gmapdp_ticket *ticket);
+/* Blocks until the box's flight has completed.  *result and *ops (the box's edit script, result->script_lenA +
+ * script_lenB words; result->script_off is relative to the flight and must be ignored) stay valid until
+ * gmapdp_stream_release. */
+int gmapdp_stream_wait (gmapdp_stream *s, const gmapdp_ticket *ticket, const gmapdp_result **result, const uint32_t **ops);
+void gmapdp_stream_release (gmapdp_stream *s, const gmapdp_ticket *ticket);
+
+/* counters since creation, summed over lanes:
+ *   [0] boxes  [1] flights  [2] largest flight  [3] reserved  [4] seconds a flight spent between launch and completion (sum)
+ *   [5] seconds boxes waited between submit and wake-up (sum)  [6] kernel launches  [7] bytes host->device  [8] bytes device->host */
+#define GMAPDP_STREAM_NSTATS 9
+void gmapdp_stream_stats (const gmapdp_stream *s, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

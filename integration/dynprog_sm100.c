@@ -6,8 +6,8 @@
  * definitions of those five symbols are renamed to ref_* in the object files by the build recipe
  * (integration/Makefile), nothing in /root/reference is edited or copied.
  *
- * The DP calls of all worker threads meet in one shared device batch (rendezvous, below): with
- * `gmap -t N` the batches hold up to N boxes.  What the binding does on the host is exactly what
+ * The DP calls of all worker threads meet in shared device batches (the streaming runtime of
+ * include/gmapdp_stream.h).  What the binding does on the host is exactly what
  * the reference entry points do before and after their fills: fetch the genomic segments with
  * Genome_get_segment_* and, for genome gaps, the MaxEnt splice-site probabilities with Maxent_hr_*.
  */
@@ -28,23 +28,27 @@
 #include "dynprog_genome.h"
 #include "dynprog_cdna.h"
 #include "dynprog_end.h"
+#include <time.h>
+#include "iit-read.h"
+#include "splicetrie_build.h"
+#include "mode.h"
 #include "gmapdp_shim.h"
+#include "gmapdp_stream.h"
 
-/* ---- rendezvous: DP calls of all worker threads are gathered into one device batch ---------------
- * A thread queues its call in the shared batch and waits.  The first thread of a generation is its
- * leader: it waits (bounded) until every thread that is currently inside a DP entry point has queued
- * its call, runs the batch on the GPU, hands each waiter its result, and wakes them.  With one thread
- * this degenerates to one batch per call, with `gmap -t N` (N >> cores: workers only block here) the
- * batches hold up to N boxes.  Results do not depend on batch composition. */
-static gmapdp_ctx *sm100_ctx = NULL;
-static gmapdp_batch *sm100_shared = NULL;
+/* ---- the engine: one streaming runtime for the whole process (include/gmapdp_stream.h) ------------------
+ * Every worker thread prepares its call in a private one-call batch (argument checks, the *_simple shortcuts,
+ * penalties, bands: gmapdp_shim.h), submits the device box -- if there is one -- to the runtime, sleeps until its
+ * flight is back, and replays its own edit script into pairs.  Calls of different threads share flights; nothing
+ * but the submission slot is serialised.  GMAP_SM100_DEVICES="0,1,2,3" (or "all") gives one lane per GPU: a worker
+ * thread stays on one lane, so a query's dependent chain of calls stays on one device (gmap.c:4895-4907 keeps
+ * all per-worker state for the life of the thread). */
+static gmapdp_stream *sm100_stream = NULL;
 static pthread_once_t sm100_once = PTHREAD_ONCE_INIT;
-static pthread_mutex_t sm100_mu = PTHREAD_MUTEX_INITIALIZER;
-static pthread_cond_t sm100_cv_done = PTHREAD_COND_INITIALIZER, sm100_cv_submit = PTHREAD_COND_INITIALIZER;
-static volatile int sm100_inflight = 0;		/* threads inside a DP entry point */
-static long sm100_wait_us = 300;
-static unsigned long sm100_nbatches = 0, sm100_ncalls = 0;
-static double sm100_t_wait = 0.0, sm100_t_run = 0.0, sm100_t_result = 0.0, sm100_cells = 0.0;
+static pthread_key_t sm100_key;
+static int sm100_user_open = 0, sm100_user_extend = 0, sm100_user_dynprog_p = 0;
+static int sm100_devices[64], sm100_ndevices = 0;
+static unsigned long sm100_ncalls = 0, sm100_nhost = 0;
+static double sm100_t0 = 0.0;
 
 static double now_s (void) {
   struct timespec t;
@@ -52,101 +56,140 @@ static double now_s (void) {
   return (double) t.tv_sec + 1e-9 * (double) t.tv_nsec;
 }
 
-typedef struct sm100_slot {
-  int id, done, n, cap, mode;
-  int iout[10];
-  double dout[2];
-  gmapdp_pair *pairs;
-} sm100_slot;
-
-#define SM100_MAXPENDING 4096
-static sm100_slot *sm100_pending[SM100_MAXPENDING];
-static int sm100_npending = 0, sm100_leader = 0;
-static __thread sm100_slot sm100_my = {0,0,0,0,0,{0},{0},NULL};
-
-static void sm100_report (void) {
-  if (getenv("GMAP_SM100_STATS"))
-    fprintf(stderr,"gmap.sm100: %lu DP calls in %lu device batches (%.1f calls per batch)\n",sm100_ncalls,sm100_nbatches,
-	    sm100_nbatches ? (double) sm100_ncalls / (double) sm100_nbatches : 0.0);
-  if (getenv("GMAP_SM100_STATS"))
-    fprintf(stderr,"gmap.sm100 timing: leader wait %.3f s, device batches %.3f s, result replay %.3f s, %.0f DP cells\n",
-	    sm100_t_wait,sm100_t_run,sm100_t_result,sm100_cells);
+static void sm100_die (const char *what) {
+  fprintf(stderr,"gmap.sm100: %s\n",what);
+  exit(9);
 }
 
+static void sm100_report (void) {
+  double st[GMAPDP_STREAM_NSTATS];
+  if (getenv("GMAP_SM100_STATS") == NULL || sm100_stream == NULL) return;
+  gmapdp_stream_stats(sm100_stream,st);
+  fprintf(stderr,"gmap.sm100: %lu DP calls in %.0f device batches (%.1f calls per batch)\n",sm100_ncalls,st[1],
+	  st[1] > 0.0 ? (double) sm100_ncalls / st[1] : 0.0);
+  fprintf(stderr,"gmap.sm100 runtime: %d device(s), %.0f boxes on the device, %lu calls resolved on the host, largest batch %.0f, "
+	  "mean batch latency %.1f us, mean wait per box %.1f us, %.0f kernel launches, %.1f MB up, %.1f MB down, %.3f s since first call\n",
+	  gmapdp_stream_ndevices(sm100_stream),st[0],sm100_nhost,st[2],st[1] > 0.0 ? 1e6 * st[4] / st[1] : 0.0,
+	  st[0] > 0.0 ? 1e6 * st[5] / st[0] : 0.0,st[6],st[7] / 1e6,st[8] / 1e6,now_s() - sm100_t0);
+}
+
+static void sm100_free_mini (void *p) { if (p) GmapDP_batch_free((gmapdp_batch *) p); }
+
 static void sm100_init (void) {
-  const char *dev = getenv("GMAP_SM100_DEVICE"), *w = getenv("GMAP_SM100_WAIT_US");
-  if (w) sm100_wait_us = atol(w);
-  if (gmapdp_create(&sm100_ctx,dev ? atoi(dev) : 0) != GMAPDP_OK) {
-    fprintf(stderr,"gmap.sm100: %s\n",gmapdp_last_error(sm100_ctx));
+  const char *dev = getenv("GMAP_SM100_DEVICES");
+  int devices[64], n = 0, rc;
+  if (dev == NULL) dev = getenv("GMAP_SM100_DEVICE");
+  if (dev == NULL || dev[0] == '\0') devices[n++] = 0;
+  else if (!strcmp(dev,"all")) {
+    int count = gmapdp_device_count();
+    if (count <= 0) sm100_die("no CUDA device: the DP engine has no CPU fallback");
+    for (n = 0; n < count && n < 64; n++) devices[n] = n;
+  } else {
+    const char *q = dev;
+    while (*q && n < 64) {
+      devices[n++] = atoi(q);
+      while (*q && *q != ',') q++;
+      if (*q == ',') q++;
+    }
+  }
+  memcpy(sm100_devices,devices,sizeof(devices)); sm100_ndevices = n;
+  if ((rc = gmapdp_stream_create(&sm100_stream,devices,n,0)) != GMAPDP_OK) {
+    fprintf(stderr,"gmap.sm100: %s\n",gmapdp_stream_error(sm100_stream));
     exit(9);
   }
+  pthread_key_create(&sm100_key,sm100_free_mini);
+  sm100_t0 = now_s();
   atexit(sm100_report);
 }
 
-/* the process-wide engine, also used by the stage 2 binding (stage2_sm100.c) */
-gmapdp_ctx *sm100_context (void) {
+/* the devices of the process, for the chaining engine's groups (stage2_sm100.c): group g lives on device g mod n */
+int sm100_device_of_group (int group) {
   pthread_once(&sm100_once,sm100_init);
-  return sm100_ctx;
+  return sm100_devices[group % sm100_ndevices];
 }
 
-/* called with the mutex held, before queueing: the shared batch is created from the first caller's limits
-   (all Dynprog_T of a gmap run have the same max_rlength / max_glength, gmap.c:4898-4903) */
-static gmapdp_batch *shared_batch (Dynprog_T dynprog) {
-  if (sm100_shared == NULL) sm100_shared = GmapDP_batch_new(sm100_ctx,dynprog->max_rlength,dynprog->max_glength);
-  return sm100_shared;
+/* ---- set-up calls: what the five entry points read from the reference's module statics ---------------------
+ * gmap.c:6348 Dynprog_init(mode), :6547 Dynprog_single_setup, :6548 Dynprog_genome_setup, :6551 Dynprog_end_setup.
+ * The reference's own functions still run (their statics serve the entry points that stay on the host:
+ * Dynprog_microexon_int, Dynprog_end5/3_known, *_splicejunction); here the values the DEVICE path depends on are
+ * recorded, and the settings it does not implement are refused loudly instead of being ignored. */
+extern void ref_Dynprog_init (Mode_T mode);
+extern void ref_Dynprog_single_setup (int user_open_in, int user_extend_in, bool user_dynprog_p_in, bool homopolymerp_in);
+extern void ref_Dynprog_genome_setup (bool novelsplicingp_in, IIT_T splicing_iit_in, int *splicing_divint_crosstable_in,
+				      int donor_typeint_in, int acceptor_typeint_in, int user_open_in, int user_extend_in, bool user_dynprog_p_in);
+extern void ref_Dynprog_end_setup (Univcoord_T *splicesites_in, Splicetype_T *splicetypes_in, Chrpos_T *splicedists_in, int nsplicesites_in,
+				   Trieoffset_T *trieoffsets_obs_in, Triecontent_T *triecontents_obs_in,
+				   Trieoffset_T *trieoffsets_max_in, Triecontent_T *triecontents_max_in,
+				   int user_open_in, int user_extend_in, bool user_dynprog_p_in);
+
+void
+Dynprog_init (Mode_T mode) {
+  if (mode != STANDARD) sm100_die("--mode other than standard (cmet / atoi / ttoc) changes the DP score tables; this build serves the standard tables only");
+  ref_Dynprog_init(mode);
 }
 
-static void slot_reserve (int need_pairs) {
-  if (need_pairs > sm100_my.cap) {
-    free(sm100_my.pairs);
-    sm100_my.cap = need_pairs + 1024;
-    sm100_my.pairs = (gmapdp_pair *) malloc((size_t) sm100_my.cap * sizeof(gmapdp_pair));
+static void sm100_user_penalties (int user_open_in, int user_extend_in, bool user_dynprog_p_in) {
+  sm100_user_open = user_open_in; sm100_user_extend = user_extend_in; sm100_user_dynprog_p = user_dynprog_p_in ? 1 : 0;
+}
+
+void
+Dynprog_single_setup (int user_open_in, int user_extend_in, bool user_dynprog_p_in, bool homopolymerp_in) {
+  if (homopolymerp_in == true) sm100_die("--homopolymer (dynprog_single.c:535) is not served by the device DP; refusing to give different alignments");
+  sm100_user_penalties(user_open_in,user_extend_in,user_dynprog_p_in);
+  ref_Dynprog_single_setup(user_open_in,user_extend_in,user_dynprog_p_in,homopolymerp_in);
+}
+
+void
+Dynprog_genome_setup (bool novelsplicingp_in, IIT_T splicing_iit_in, int *splicing_divint_crosstable_in,
+		      int donor_typeint_in, int acceptor_typeint_in, int user_open_in, int user_extend_in, bool user_dynprog_p_in) {
+  if (splicing_iit_in != NULL) sm100_die("known splice sites (-s / --use-splicing: the intron-level bridge of dynprog_genome.c:615,1489) are not served by the device DP");
+  sm100_user_penalties(user_open_in,user_extend_in,user_dynprog_p_in);
+  ref_Dynprog_genome_setup(novelsplicingp_in,splicing_iit_in,splicing_divint_crosstable_in,donor_typeint_in,acceptor_typeint_in,
+			   user_open_in,user_extend_in,user_dynprog_p_in);
+}
+
+void
+Dynprog_end_setup (Univcoord_T *splicesites_in, Splicetype_T *splicetypes_in, Chrpos_T *splicedists_in, int nsplicesites_in,
+		   Trieoffset_T *trieoffsets_obs_in, Triecontent_T *triecontents_obs_in,
+		   Trieoffset_T *trieoffsets_max_in, Triecontent_T *triecontents_max_in,
+		   int user_open_in, int user_extend_in, bool user_dynprog_p_in) {
+  sm100_user_penalties(user_open_in,user_extend_in,user_dynprog_p_in);
+  ref_Dynprog_end_setup(splicesites_in,splicetypes_in,splicedists_in,nsplicesites_in,trieoffsets_obs_in,triecontents_obs_in,
+			trieoffsets_max_in,triecontents_max_in,user_open_in,user_extend_in,user_dynprog_p_in);
+}
+
+/* this thread's private one-call batch (all Dynprog_T of a gmap run have the same limits, gmap.c:4898-4903) */
+static gmapdp_batch *my_batch (Dynprog_T dynprog) {
+  gmapdp_batch *b;
+  pthread_once(&sm100_once,sm100_init);
+  b = (gmapdp_batch *) pthread_getspecific(sm100_key);
+  if (b == NULL) {
+    if ((b = GmapDP_batch_new(NULL,dynprog->max_rlength,dynprog->max_glength)) == NULL) sm100_die("Dynprog_T limits beyond 32767");
+    if (GmapDP_batch_user_dynprog(b,sm100_user_open,sm100_user_extend,sm100_user_dynprog_p) != GMAPDP_OK) sm100_die(GmapDP_batch_error(b));
+    pthread_setspecific(sm100_key,b);
   }
+  GmapDP_batch_clear(b);
+  return b;
 }
 
-/* called with the mutex held and the call queued under `id`; returns with the result in sm100_my */
-static void rendezvous (int id, int mode) {
-  sm100_slot *me = &sm100_my;
-  int k;
-  me->id = id; me->done = 0; me->mode = mode;
-  if (sm100_npending >= SM100_MAXPENDING) { fprintf(stderr,"gmap.sm100: too many waiting threads\n"); exit(9); }
-  sm100_pending[sm100_npending++] = me;
-  if (!sm100_leader) {
-    struct timespec dl;
-    double t0 = now_s(), t1, t2;
-    sm100_leader = 1;
-    clock_gettime(CLOCK_REALTIME,&dl);
-    dl.tv_nsec += sm100_wait_us * 1000L;
-    while (dl.tv_nsec >= 1000000000L) { dl.tv_nsec -= 1000000000L; dl.tv_sec++; }
-    while (sm100_npending < sm100_inflight && sm100_npending < SM100_MAXPENDING) {
-      if (pthread_cond_timedwait(&sm100_cv_submit,&sm100_mu,&dl) != 0) break;	/* timeout */
-    }
-    t1 = now_s();
-    if (GmapDP_batch_run(sm100_shared) != GMAPDP_OK) {
-      fprintf(stderr,"gmap.sm100: %s\n",GmapDP_batch_error(sm100_shared));
-      exit(9);
-    }
-    t2 = now_s();
-    sm100_cells += (double) GmapDP_batch_cells(sm100_shared);
-    sm100_nbatches++; sm100_ncalls += sm100_npending;
-    for (k = 0; k < sm100_npending; k++) {
-      sm100_slot *s = sm100_pending[k];
-      s->n = GmapDP_result(sm100_shared,s->id,s->iout,s->dout,s->pairs,s->cap);
-      s->done = 1;
-    }
-    sm100_npending = 0;
-    GmapDP_batch_clear(sm100_shared);
-    sm100_t_wait += t1 - t0; sm100_t_run += t2 - t1; sm100_t_result += now_s() - t2;
-    sm100_leader = 0;
-    pthread_cond_broadcast(&sm100_cv_done);
-  } else {
-    pthread_cond_signal(&sm100_cv_submit);
-    while (!me->done) pthread_cond_wait(&sm100_cv_done,&sm100_mu);
-  }
-}
+/* runs the call queued under `id' in this thread's batch; afterwards GmapDP_result_view(b,id,...) has the result */
+static void run_call (gmapdp_batch *b) {
+  const gmapdp_box *boxes; const uint8_t *seq; const double *probs;
+  const gmapdp_result *res; const uint32_t *ops;
+  gmapdp_result r;
+  gmapdp_ticket ticket;
+  size_t seqbytes, nprobs;
+  int nboxes;
 
-#define ENTER() do { pthread_once(&sm100_once,sm100_init); __sync_fetch_and_add(&sm100_inflight,1); } while (0)
-#define LEAVE() __sync_fetch_and_sub(&sm100_inflight,1)
+  __sync_fetch_and_add(&sm100_ncalls,1);
+  if (GmapDP_batch_device_view(b,&boxes,&nboxes,&seq,&seqbytes,&probs,&nprobs) != GMAPDP_OK) sm100_die(GmapDP_batch_error(b));
+  if (nboxes == 0) { __sync_fetch_and_add(&sm100_nhost,1); return; }	/* resolved by the entry point's own shortcuts */
+  if (gmapdp_stream_submit(sm100_stream,&boxes[0],seq,seqbytes,probs,nprobs,&ticket) != GMAPDP_OK ||
+      gmapdp_stream_wait(sm100_stream,&ticket,&res,&ops) != GMAPDP_OK) sm100_die(gmapdp_stream_error(sm100_stream));
+  r = *res; r.script_off = 0;
+  if (GmapDP_batch_complete(b,&r,ops) != GMAPDP_OK) sm100_die(GmapDP_batch_error(b));
+  gmapdp_stream_release(sm100_stream,&ticket);
+}
 
 /* records come head first: cons them from the tail */
 static List_T pairs_to_list (Pairpool_T pool, const gmapdp_pair *p, int n) {
@@ -176,13 +219,13 @@ Dynprog_single_gap (int *dynprogindex, int *traceback_score, int *nmatches, int 
 		    Genome_T genome, Genome_T genomealt, Pairpool_T pairpool,
 		    int extraband_single, bool widebandp, double defect_rate) {
   char *gseq, *galt, empty[1] = {'\0'};
-  int id;
+  int id, n;
   const int *iout;
+  const gmapdp_pair *pairs;
+  gmapdp_batch *b = my_batch(dynprog);
   List_T l;
   bool fetch = (rlength > 0 && glength > 0 && rlength <= dynprog->max_rlength && glength <= dynprog->max_glength);
 
-  ENTER();
-  slot_reserve(rlength + glength + 8);
   if (fetch) {
     gseq = (char *) malloc(glength + 1); galt = (char *) malloc(glength + 1);
     if (watsonp) Genome_get_segment_right(gseq,galt,genome,genomealt,chroffset+goffset,glength,chrhigh,/*revcomp*/false);
@@ -190,17 +233,14 @@ Dynprog_single_gap (int *dynprogindex, int *traceback_score, int *nmatches, int 
   } else {
     gseq = galt = empty;
   }
-  pthread_mutex_lock(&sm100_mu);
-  id = GmapDP_single_gap(shared_batch(dynprog),*dynprogindex,rsequence,rsequenceuc,rlength,glength,roffset,goffset,gseq,galt,
+  id = GmapDP_single_gap(b,*dynprogindex,rsequence,rsequenceuc,rlength,glength,roffset,goffset,gseq,galt,
 			 jump_late_p,extraband_single,widebandp,defect_rate);
-  rendezvous(id,GMAPDP_SINGLE);
-  pthread_mutex_unlock(&sm100_mu);
-  LEAVE();
-  iout = sm100_my.iout;
+  run_call(b);
+  n = GmapDP_result_view(b,id,&iout,NULL,&pairs);
   *dynprogindex = iout[0]; *traceback_score = iout[1]; *nmatches = iout[2]; *nmismatches = iout[3];
   *nopens = iout[4]; *nindels = iout[5];
   if (fetch) { free(galt); free(gseq); }
-  l = (sm100_my.n < 0) ? (List_T) NULL : pairs_to_list(pairpool,sm100_my.pairs,sm100_my.n);
+  l = (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,pairs,n);
   return l;
 }
 
@@ -211,12 +251,12 @@ end_gap (bool end5, int *dynprogindex, int *traceback_score, int *nmatches, int 
 	 Genome_T genome, Genome_T genomealt, Pairpool_T pairpool, int extraband_end, double defect_rate,
 	 Endalign_T endalign, bool require_pos_score_p) {
   char *gseq, *galt, empty[1] = {'\0'};
-  int id, gl = glength;
+  int id, n, gl = glength;
   const int *iout;
+  const gmapdp_pair *pairs;
+  gmapdp_batch *b = my_batch(dynprog);
   bool fetch;
 
-  ENTER();
-  slot_reserve(rlength + glength + 8);
   /* the reference chops before it fetches (dynprog_end.c:1357-1378 / :1986-1999) */
   if (endalign != QUERYEND_NOGAPS && gl > dynprog->max_glength) gl = dynprog->max_glength;
   fetch = (rlength > 0 && gl > 0 && !(end5 && goffset < 0));
@@ -232,19 +272,16 @@ end_gap (bool end5, int *dynprogindex, int *traceback_score, int *nmatches, int 
   } else {
     gseq = galt = empty;
   }
-  pthread_mutex_lock(&sm100_mu);
-  if (end5) id = GmapDP_end5_gap(shared_batch(dynprog),*dynprogindex,rseq,rsequc,rlength,glength,roffset,goffset,gseq,galt,jump_late_p,
+  if (end5) id = GmapDP_end5_gap(b,*dynprogindex,rseq,rsequc,rlength,glength,roffset,goffset,gseq,galt,jump_late_p,
 				 extraband_end,defect_rate,(int) endalign,require_pos_score_p);
-  else id = GmapDP_end3_gap(shared_batch(dynprog),*dynprogindex,rseq,rsequc,rlength,glength,roffset,goffset,gseq,galt,jump_late_p,
+  else id = GmapDP_end3_gap(b,*dynprogindex,rseq,rsequc,rlength,glength,roffset,goffset,gseq,galt,jump_late_p,
 			    extraband_end,defect_rate,(int) endalign,require_pos_score_p);
-  rendezvous(id,end5 ? GMAPDP_END5 : GMAPDP_END3);
-  pthread_mutex_unlock(&sm100_mu);
-  LEAVE();
-  iout = sm100_my.iout;
+  run_call(b);
+  n = GmapDP_result_view(b,id,&iout,NULL,&pairs);
   *dynprogindex = iout[0]; *traceback_score = iout[1]; *nmatches = iout[2]; *nmismatches = iout[3];
   *nopens = iout[4]; *nindels = iout[5];
   if (fetch) { free(galt); free(gseq); }
-  return (sm100_my.n < 0) ? (List_T) NULL : pairs_to_list(pairpool,sm100_my.pairs,sm100_my.n);
+  return (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,pairs,n);
 }
 
 List_T
@@ -293,13 +330,13 @@ Dynprog_genome_gap (int *dynprogindex, int *new_leftgenomepos, int *new_rightgen
   double *lp = NULL, *rp = NULL;
   const double *dout;
   const int *iout;
-  int id, c;
+  const gmapdp_pair *pairs;
+  gmapdp_batch *b = my_batch(dynprogL);
+  int id, n, c;
   Univcoord_T pos;
   bool fetch = (rlength > 1 && rlength <= dynprogL->max_rlength && glengthL <= dynprogL->max_glength &&
 		rlength <= dynprogR->max_rlength && glengthR <= dynprogR->max_glength && glengthL > 0 && glengthR > 0);
 
-  ENTER();
-  slot_reserve(2 * rlength + glengthL + glengthR + 16);
   if (fetch) {
     gL = (char *) malloc(glengthL + 1); gLa = (char *) malloc(glengthL + 1);
     gR = (char *) malloc(glengthR + 1); gRa = (char *) malloc(glengthR + 1);
@@ -334,20 +371,17 @@ Dynprog_genome_gap (int *dynprogindex, int *new_leftgenomepos, int *new_rightgen
   } else {
     gL = gLa = gR = gRa = empty;
   }
-  pthread_mutex_lock(&sm100_mu);
-  id = GmapDP_genome_gap(shared_batch(dynprogL),*dynprogindex,rsequence,rsequenceuc,rlength,glengthL,glengthR,roffset,goffsetL,rev_goffsetR,
+  id = GmapDP_genome_gap(b,*dynprogindex,rsequence,rsequenceuc,rlength,glengthL,glengthR,roffset,goffsetL,rev_goffsetR,
 			 gL,gLa,gR,gRa,lp,rp,cdna_direction,jump_late_p,extraband_paired,defect_rate,maxpeelback,halfp,finalp);
-  rendezvous(id,GMAPDP_GENOME);
-  pthread_mutex_unlock(&sm100_mu);
-  LEAVE();
-  iout = sm100_my.iout; dout = sm100_my.dout;
+  run_call(b);
+  n = GmapDP_result_view(b,id,&iout,&dout,&pairs);
   *dynprogindex = iout[0];
   SET(new_leftgenomepos,iout[1]); SET(new_rightgenomepos,iout[2]); SET(traceback_score,iout[3]);
   *nmatches = iout[4]; *nmismatches = iout[5]; *nopens = iout[6]; *nindels = iout[7];
   SET(exonhead,iout[8]); *introntype = iout[9];
   *left_prob = dout[0]; *right_prob = dout[1];
   if (fetch) { free(rp); free(lp); free(gRa); free(gR); free(gLa); free(gL); }
-  return (sm100_my.n < 0) ? (List_T) NULL : pairs_to_list(pairpool,sm100_my.pairs,sm100_my.n);
+  return (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,pairs,n);
 }
 
 List_T
@@ -362,12 +396,12 @@ Dynprog_cdna_gap (int *dynprogindex, int *traceback_score, bool *incompletep,
 		  int extraband_paired, double defect_rate) {
   char *g, *ga, *rg, *rga, empty[1] = {'\0'};
   const int *iout;
-  int id, rev_goffset = goffset + glength - 1;
+  const gmapdp_pair *pairs;
+  gmapdp_batch *b = my_batch(dynprogL);
+  int id, n, rev_goffset = goffset + glength - 1;
   bool fetch = (glength > 1 && glength <= dynprogR->max_glength && rlengthR <= dynprogR->max_rlength &&
 		glength <= dynprogL->max_glength && rlengthL <= dynprogL->max_rlength);
 
-  ENTER();
-  slot_reserve(rlengthL + rlengthR + 2 * glength + 32);
   if (fetch) {
     g = (char *) malloc(glength + 1); ga = (char *) malloc(glength + 1);
     rg = (char *) malloc(glength + 1); rga = (char *) malloc(glength + 1);
@@ -381,16 +415,13 @@ Dynprog_cdna_gap (int *dynprogindex, int *traceback_score, bool *incompletep,
   } else {
     g = ga = rg = rga = empty;
   }
-  pthread_mutex_lock(&sm100_mu);
-  id = GmapDP_cdna_gap(shared_batch(dynprogL),*dynprogindex,rsequenceL,rsequence_ucL,rev_rsequenceR,rev_rsequence_ucR,rlengthL,rlengthR,glength,
+  id = GmapDP_cdna_gap(b,*dynprogindex,rsequenceL,rsequence_ucL,rev_rsequenceR,rev_rsequence_ucR,rlengthL,rlengthR,glength,
 		       roffsetL,rev_roffsetR,goffset,g,ga,rg,rga,jump_late_p,extraband_paired,defect_rate);
-  rendezvous(id,GMAPDP_CDNA);
-  pthread_mutex_unlock(&sm100_mu);
-  LEAVE();
-  iout = sm100_my.iout;
+  run_call(b);
+  n = GmapDP_result_view(b,id,&iout,NULL,&pairs);
   *dynprogindex = iout[0];
   SET(traceback_score,iout[1]);
   if (iout[2]) *incompletep = true;
   if (fetch) { free(rga); free(rg); free(ga); free(g); }
-  return (sm100_my.n < 0) ? (List_T) NULL : pairs_to_list(pairpool,sm100_my.pairs,sm100_my.n);
+  return (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,pairs,n);
 }

@@ -9,7 +9,10 @@
  * definition (then the reference's own body is compiled under the name ref_align_compute_*) and `mappings` at every call
  * site (then the call goes to the sm100_* functions at the bottom of this file).  Everything else of stage 2 --
  * Oligoindex mappings, Diag bounds, convert_to_nucleotides, the filters -- is the reference's code.
- * What is not on the device yet (use_canonical_p, SNP-tolerant tracebacks) is handed to the reference's own body.
+ * No call is ever handed to the reference's own body (it is compiled under the name ref_align_compute_* only because
+ * the definition is part of stage2.c): what the device does not implement -- the cross-species canonical test
+ * (use_canonical_p), SNP-tolerant mode, the 2-D link matrix that stage2.c itself asserts away (:3734) -- stops the
+ * program with a message instead of silently running on the CPU.
  */
 #include <pthread.h>
 #include "bool.h"
@@ -49,26 +52,61 @@ static List_T sm100_lookforward (CHAIN_PARAMS);
 #undef align_compute_lookforward
 
 /* ---- the device side ------------------------------------------------------------------------------------------ */
-extern gmapdp_ctx *sm100_context (void);		/* dynprog_sm100.c: the process-wide engine */
+extern int sm100_device_of_group (int group);		/* dynprog_sm100.c: the devices of the process */
 
-/* Rendezvous, as for the DP calls (dynprog_sm100.c): the chaining calls of all worker threads are queued in one
-   shared batch; the first thread of a generation is its leader, waits (bounded) for the threads that are inside a
-   chaining call to queue theirs, runs the batch, and every thread then reads its own paths.  The batch is cleared by
-   the last reader; calls that arrive meanwhile wait for that. */
-static pthread_mutex_t chain_mu = PTHREAD_MUTEX_INITIALIZER;
-static pthread_cond_t chain_cv_done = PTHREAD_COND_INITIALIZER, chain_cv_submit = PTHREAD_COND_INITIALIZER,
-  chain_cv_idle = PTHREAD_COND_INITIALIZER;
-static gmapchain_batch *chain_batch = NULL;
-static bool chain_setup_done = false, chain_busy = false, chain_leader = false;
-static int chain_npending = 0, chain_readers = 0;
-static volatile int chain_inflight = 0;
-static unsigned long chain_gen = 0, chain_ncalls = 0, chain_nbatches = 0, chain_nref = 0;
-static long chain_wait_us = 300;
+/* Chaining calls of the worker threads meet in shared device batches, like the DP calls (dynprog_sm100.c), but a
+   chaining problem is a long sequential walk (milliseconds per problem on one warp), so what matters is that many
+   batches are in flight at once.  The threads are spread over GMAP_SM100_CHAIN_GROUPS groups (default 8), each with
+   its own engine context (own stream and device buffers; group g on device g mod #devices) and two batches: one is
+   filled while the other runs or is being read.  The first thread that finds its batch not yet run and the group
+   idle leads it: it runs the batch WITHOUT holding the group's lock; everybody then reads his own paths.  No
+   timeouts; a call never waits for anything but the batch in front of its own. */
+typedef struct chain_group {
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  gmapdp_ctx *ctx;
+  gmapchain_batch *batch[2];
+  int fill;			/* the batch that accepts calls */
+  int npending[2];		/* calls queued in batch k and not yet run */
+  int readers[2];		/* calls of batch k that have not read their paths yet */
+  unsigned long seq[2];		/* completed runs of batch k */
+  bool running;
+} chain_group;
+
+#define CHAIN_MAXGROUPS 64
+static chain_group chain_groups[CHAIN_MAXGROUPS];
+static int chain_ngroups = 0;
+static pthread_once_t chain_once = PTHREAD_ONCE_INIT;
+static unsigned long chain_ncalls = 0, chain_nbatches = 0, chain_next_group = 0;
+static __thread int chain_my_group = -1;
 
 static void chain_report (void) {
   if (getenv("GMAP_SM100_STATS"))
     fprintf(stderr,"gmap.sm100 stage 2: %lu chaining calls on the device in %lu batches, %lu handed to the reference body\n",
-	    chain_ncalls,chain_nbatches,chain_nref);
+	    chain_ncalls,chain_nbatches,0UL);
+}
+
+static void chain_init (void) {
+  const char *e = getenv("GMAP_SM100_CHAIN_GROUPS");
+  int g;
+  chain_ngroups = e ? atoi(e) : 8;
+  if (chain_ngroups < 1) chain_ngroups = 1;
+  if (chain_ngroups > CHAIN_MAXGROUPS) chain_ngroups = CHAIN_MAXGROUPS;
+  for (g = 0; g < chain_ngroups; g++) {
+    chain_group *G = &chain_groups[g];
+    pthread_mutex_init(&G->mu,NULL);
+    pthread_cond_init(&G->cv,NULL);
+    /* the values Stage2_setup stored (stage2.c:129-160, gmap.c:6544) */
+    if (gmapdp_create(&G->ctx,sm100_device_of_group(g)) != GMAPDP_OK ||
+	gmapchain_setup(G->ctx,splicingp,/*cross_species_p*/0,sufflookback,nsufflookback,maxintronlen) != GMAPDP_OK) {
+      fprintf(stderr,"gmap.sm100: %s\n",gmapdp_last_error(G->ctx));
+      exit(9);
+    }
+    G->batch[0] = GmapChain_batch_new(G->ctx); G->batch[1] = GmapChain_batch_new(G->ctx);
+    G->fill = 0; G->npending[0] = G->npending[1] = 0; G->readers[0] = G->readers[1] = 0; G->seq[0] = G->seq[1] = 0;
+    G->running = false;
+  }
+  atexit(chain_report);
 }
 
 typedef struct { int n; int *qpos; uint32_t *gpos; } chain_path_t;
@@ -76,84 +114,73 @@ typedef struct { int n; int *qpos; uint32_t *gpos; } chain_path_t;
 static List_T
 chain_on_device (bool forwardp, CHAIN_PARAMS) {
   List_T all_paths = NULL, path;
-  gmapdp_ctx *ctx = sm100_context();
-  int id, npaths = 0, k, n, t, cap, cell[5];
-  unsigned long mygen;
+  chain_group *G;
+  gmapchain_batch *B;
+  int id, npaths = 0, k, n, t, cap, cell[5], kb;
+  unsigned long myseq;
   chain_path_t *got = NULL;
 
   (void) firstactive; (void) nactive; (void) cellpool; (void) genome; (void) genomealt; (void) chroffset; (void) chrhigh; (void) plusp;
   cap = querylength + 16;
-  __sync_fetch_and_add(&chain_inflight,1);
+  pthread_once(&chain_once,chain_init);
+  if (chain_my_group < 0) chain_my_group = (int) (__sync_fetch_and_add(&chain_next_group,1) % (unsigned long) chain_ngroups);
+  G = &chain_groups[chain_my_group];
 
-  pthread_mutex_lock(&chain_mu);
-  if (chain_setup_done == false) {
-    const char *w = getenv("GMAP_SM100_WAIT_US");
-    if (w) chain_wait_us = atol(w);
-    /* the values Stage2_setup stored (stage2.c:129-160, gmap.c:6544) */
-    if (gmapchain_setup(ctx,splicingp,/*cross_species_p*/0,sufflookback,nsufflookback,maxintronlen) != GMAPDP_OK) {
-      fprintf(stderr,"gmap.sm100: %s\n",gmapdp_last_error(ctx));
-      exit(9);
-    }
-    chain_batch = GmapChain_batch_new(ctx);
-    chain_setup_done = true;
-    atexit(chain_report);
-  }
-  while (chain_busy) pthread_cond_wait(&chain_cv_idle,&chain_mu);	/* the previous generation is still being read */
+  pthread_mutex_lock(&G->mu);
+  while (G->readers[G->fill] > 0) pthread_cond_wait(&G->cv,&G->mu);	/* its previous run is still being read */
+  kb = G->fill; B = G->batch[kb];
   if (forwardp) {
-    id = GmapChain_lookforward(chain_batch,(uint32_t *const *) mappings,npositions,totalpositions,minactive,maxactive,
+    id = GmapChain_lookforward(B,(uint32_t *const *) mappings,npositions,totalpositions,minactive,maxactive,
 			       querylength,querystart,queryend,indexsize,localp,skip_repetitive_p,use_canonical_p,
 			       non_canonical_penalty,favor_right_p,middlep,max_nalignments);
   } else {
-    id = GmapChain_lookback(chain_batch,(uint32_t *const *) mappings,npositions,totalpositions,minactive,maxactive,
+    id = GmapChain_lookback(B,(uint32_t *const *) mappings,npositions,totalpositions,minactive,maxactive,
 			    querylength,querystart,queryend,indexsize,localp,skip_repetitive_p,use_canonical_p,
 			    non_canonical_penalty,favor_right_p,middlep,max_nalignments);
   }
   if (id < 0) {
-    fprintf(stderr,"gmap.sm100: %s\n",GmapChain_batch_error(chain_batch));
+    fprintf(stderr,"gmap.sm100: %s\n",GmapChain_batch_error(B));
     exit(9);
   }
-  chain_npending++;
-  mygen = chain_gen;
-  if (!chain_leader) {
-    struct timespec dl;
-    chain_leader = true;
-    clock_gettime(CLOCK_REALTIME,&dl);
-    dl.tv_nsec += chain_wait_us * 1000L;
-    while (dl.tv_nsec >= 1000000000L) { dl.tv_nsec -= 1000000000L; dl.tv_sec++; }
-    while (chain_npending < chain_inflight) {
-      if (pthread_cond_timedwait(&chain_cv_submit,&chain_mu,&dl) != 0) break;
+  G->npending[kb]++;
+  myseq = G->seq[kb];
+  while (G->seq[kb] == myseq) {
+    if (G->running == false && G->fill == kb) {
+      /* lead: later calls go to the other batch while this one runs */
+      int nrun = G->npending[kb];
+      G->running = true; G->fill = kb ^ 1; G->npending[kb] = 0;
+      pthread_mutex_unlock(&G->mu);
+      if (GmapChain_batch_run(B) != GMAPDP_OK) {
+	fprintf(stderr,"gmap.sm100: %s\n",GmapChain_batch_error(B));
+	exit(9);
+      }
+      pthread_mutex_lock(&G->mu);
+      __sync_fetch_and_add(&chain_ncalls,(unsigned long) nrun); __sync_fetch_and_add(&chain_nbatches,1UL);
+      G->readers[kb] = nrun; G->seq[kb]++; G->running = false;
+      pthread_cond_broadcast(&G->cv);
+    } else {
+      pthread_cond_wait(&G->cv,&G->mu);
     }
-    chain_busy = true;
-    if (GmapChain_batch_run(chain_batch) != GMAPDP_OK) {
-      fprintf(stderr,"gmap.sm100: %s\n",GmapChain_batch_error(chain_batch));
-      exit(9);
-    }
-    chain_ncalls += chain_npending; chain_nbatches++;
-    chain_readers = chain_npending; chain_npending = 0;
-    chain_leader = false; chain_gen++;
-    pthread_cond_broadcast(&chain_cv_done);
-  } else {
-    pthread_cond_signal(&chain_cv_submit);
-    while (chain_gen == mygen) pthread_cond_wait(&chain_cv_done,&chain_mu);
   }
-  /* copy this call's paths out of the shared batch */
-  npaths = GmapChain_npaths(chain_batch,id);
+  pthread_mutex_unlock(&G->mu);
+
+  /* copy this call's paths out of the shared batch (read-only until its last reader clears it) */
+  npaths = GmapChain_npaths(B,id);
   got = (chain_path_t *) MALLOC((npaths + 1) * sizeof(chain_path_t));
   for (k = 0; k < npaths; k++) {
     got[k].qpos = (int *) MALLOC(cap * sizeof(int));
     got[k].gpos = (uint32_t *) MALLOC(cap * sizeof(uint32_t));
-    if ((got[k].n = GmapChain_path(chain_batch,id,k,cell,got[k].qpos,got[k].gpos,cap)) < 0) {
+    if ((got[k].n = GmapChain_path(B,id,k,cell,got[k].qpos,got[k].gpos,cap)) < 0) {
       fprintf(stderr,"gmap.sm100: a stage 2 path is longer than the query\n");
       exit(9);
     }
   }
-  if (--chain_readers == 0) {
-    GmapChain_batch_clear(chain_batch);
-    chain_busy = false;
-    pthread_cond_broadcast(&chain_cv_idle);
+  pthread_mutex_lock(&G->mu);
+  if (--G->readers[kb] == 0) {
+    GmapChain_batch_clear(B);
+    pthread_cond_broadcast(&G->cv);
   }
-  pthread_mutex_unlock(&chain_mu);
-  __sync_fetch_and_sub(&chain_inflight,1);
+  pthread_mutex_unlock(&G->mu);
 
   for (k = 0; k < npaths; k++) {
     /* traceback_one (stage2.c:4265-4272) conses pairs while it walks away from the cell, so the list head is the far
@@ -172,27 +199,30 @@ chain_on_device (bool forwardp, CHAIN_PARAMS) {
   return all_paths;
 }
 
-/* GMAP_SM100_STAGE2=0 keeps stage 2 on the host (the reference's own body) */
-static bool chain_enabled (void) {
-  static int enabled = -1;
-  if (enabled < 0) { const char *e = getenv("GMAP_SM100_STAGE2"); enabled = (e && e[0] == '0') ? 0 : 1; }
-  return enabled == 1;
+/* a configuration the chaining engine does not implement: refuse loudly (there is no CPU fallback) */
+static void chain_refuse (bool use_canonical_p, bool oned_matrix_p) {
+  if (use_canonical_p == true)
+    fprintf(stderr,"gmap.sm100: --cross-species (use_canonical_p: stage2.c:1252,1816,2195,2750) is not served by the device chaining engine\n");
+  else if (snps_p == true)
+    fprintf(stderr,"gmap.sm100: SNP-tolerant alignment (-v) is not served by the device chaining engine\n");
+  else if (oned_matrix_p == false)
+    fprintf(stderr,"gmap.sm100: the 2-D link matrix (oned_matrix_p == false) is not served by the device chaining engine\n");
+  exit(9);
 }
 
 static List_T
 sm100_lookback (CHAIN_PARAMS) {
-  if (use_canonical_p == true || snps_p == true || oned_matrix_p == false || totalpositions <= 0 || !chain_enabled()) {
-    __sync_fetch_and_add(&chain_nref,1);
-    return ref_align_compute_lookback(CHAIN_ARGS);
-  }
+  if (use_canonical_p == true || snps_p == true || oned_matrix_p == false) chain_refuse(use_canonical_p,oned_matrix_p);
+  if (totalpositions <= 0) return (List_T) NULL;	/* no hit, no cell: stage2.c:4464 (ncells == 0) */
   return chain_on_device(/*forwardp*/false,CHAIN_ARGS);
 }
 
 static List_T
 sm100_lookforward (CHAIN_PARAMS) {
-  if (use_canonical_p == true || snps_p == true || oned_matrix_p == false || totalpositions <= 0 || !chain_enabled()) {
-    __sync_fetch_and_add(&chain_nref,1);
-    return ref_align_compute_lookforward(CHAIN_ARGS);
-  }
+  if (use_canonical_p == true || snps_p == true || oned_matrix_p == false) chain_refuse(use_canonical_p,oned_matrix_p);
+  if (totalpositions <= 0) return (List_T) NULL;	/* stage2.c:5124 */
   return chain_on_device(/*forwardp*/true,CHAIN_ARGS);
 }
+
+/* keeps the (never called) reference bodies referenced, so that -Wunused does not hide a renamed seam */
+void *sm100_stage2_reference_bodies[2] = { (void *) ref_align_compute_lookback, (void *) ref_align_compute_lookforward };

@@ -482,8 +482,16 @@ static int dump (plist *l, int headfirst_is_reverse, orc_pair *pairs, int maxpai
 
 static void bump (int *dynprogindex) { *dynprogindex += (*dynprogindex > 0 ? +1 : -1); }
 
+/* --indel-open / --indel-extend: the user_open / user_extend / user_dynprog_p statics that Dynprog_single_setup,
+   Dynprog_genome_setup and Dynprog_end_setup store (dynprog_single.c:101, dynprog_genome.c:192, dynprog_end.c:120);
+   they override the defect_rate table in single, genome and end gaps (dynprog_single.c:470, dynprog_genome.c:3367,
+   dynprog_end.c:1334,1964), not in cdna gaps */
+static int user_open = 0, user_extend = 0, user_dynprog_p = 0;
+void orc_set_user_dynprog (int open, int extend, int enabled) { user_open = open; user_extend = extend; user_dynprog_p = enabled; }
+
 static void penalties (double defect_rate, const int *opens, const int *extends, int *open, int *extend) {
   int q = defect_rate < 0.003 ? 0 : (defect_rate < 0.014 ? 1 : 2);	/* dynprog.h:57-58 */
+  if (user_dynprog_p) { *open = user_open; *extend = user_extend; return; }
   *open = opens[q]; *extend = extends[q];
 }
 static int mismatchtype_of (double defect_rate) { return defect_rate < 0.003 ? ORC_HIGHQ : (defect_rate < 0.014 ? ORC_MEDQ : ORC_LOWQ); }

@@ -32,6 +32,7 @@ enum { ORC_HIGHQ = 0, ORC_MEDQ = 1, ORC_LOWQ = 2, ORC_ENDQ = 3 };
 enum { ORC_QUERYEND_GAP = 0, ORC_QUERYEND_INDELS = 1, ORC_QUERYEND_NOGAPS = 2, ORC_BEST_LOCAL = 3 };
 
 void orc_init (void);						/* Dynprog_init dynprog.c:1007 (STANDARD mode) */
+void orc_set_user_dynprog (int open, int extend, int enabled);	/* --indel-open / --indel-extend (the *_setup statics) */
 int orc_pairdistance (int mismatchtype, int a, int b);
 int orc_consistent (int a, int b);
 int orc_use8p_size (int mismatchtype);

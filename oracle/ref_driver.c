@@ -47,6 +47,13 @@ static Dynprog_T dynL, dynR, dynM;
 static Pairpool_T pool;
 static int inited = 0;
 
+/* --indel-open / --indel-extend: the three set-up calls of gmap.c:6547-6553 with the user's penalties */
+void refdrv_set_user_dynprog (int open, int extend, int enabled) {
+  Dynprog_single_setup(open,extend,enabled ? true : false,false);
+  Dynprog_genome_setup(true,NULL,NULL,-1,-1,open,extend,enabled ? true : false);
+  Dynprog_end_setup(NULL,NULL,NULL,0,NULL,NULL,NULL,NULL,open,extend,enabled ? true : false);
+}
+
 int refdrv_init (int maxlookback, int extraquerygap, int maxpeelback, int extramaterial_end, int extramaterial_paired) {
   if (inited) return 0;
   Dynprog_init(STANDARD);

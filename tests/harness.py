@@ -62,6 +62,10 @@ class Oracle:
         self.lib.orc_cells.restype = C.c_long
         self.buf = (Pair * MAXPAIRS)()
 
+    def set_user_dynprog(self, user_open, user_extend, enabled=True):
+        """--indel-open / --indel-extend"""
+        self.lib.orc_set_user_dynprog(int(user_open), int(user_extend), int(bool(enabled)))
+
     # ---- tables / fills ----------------------------------------------------------------------
     def pairdistance(self, mt, a, b):
         return self.lib.orc_pairdistance(mt, a, b)
@@ -147,6 +151,9 @@ class Ref:
         self.buf = (Pair * MAXPAIRS)()
         self.max_rlength = self.lib.refdrv_max_rlength()
         self.max_glength = self.lib.refdrv_max_glength()
+
+    def set_user_dynprog(self, user_open, user_extend, enabled=True):
+        self.lib.refdrv_set_user_dynprog(int(user_open), int(user_extend), int(bool(enabled)))
 
     def pairdistance(self, mt, a, b):
         return self.lib.refdrv_pairdistance(mt, a, b)

@@ -129,3 +129,47 @@ def test_tie_list_overflow_path(oracle):
         run_and_compare(eng, oracle, boxes, "one-entry tie lists")
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("user_open,user_extend", [(-12, -4), (-5, -1), (-30, -10), (0, -2), (-3, 0)])
+def test_user_dynprog(engine, oracle, user_open, user_extend):
+    """--indel-open / --indel-extend (user_dynprog_p: dynprog_single.c:470, dynprog_genome.c:3367, dynprog_end.c:1334,1964)"""
+    boxes = dpgen.synth_boxes(seed=300 - user_open, n=500, rmin=8, rmax=300)
+    oracle.set_user_dynprog(user_open, user_extend)
+    try:
+        want = [oracle.run(b) for b in boxes]
+    finally:
+        oracle.set_user_dynprog(0, 0, False)
+    batch = engine.batch()
+    batch.set_user_dynprog(user_open, user_extend)
+    ids = [batch.add(b) for b in boxes]
+    batch.run()
+    got = [batch.result(cid, b["mode"]) for b, cid in zip(boxes, ids)]
+    batch.free()
+    bad = [k for k in range(len(boxes)) if got[k] != want[k]]
+    assert not bad, "%d of %d boxes differ with user penalties %d/%d; first mode %s" % (len(bad), len(boxes), user_open, user_extend, boxes[bad[0]]["mode"])
+
+
+def test_resident_run_refused_after_chunked_run(engine):
+    """gmapdp_run_resident must not silently recompute only the first chunk of a pipelined plan"""
+    import os
+    from gmap_2024_b200 import Engine, EngineError
+    os.environ["GMAPDP_CHUNK_MB"] = "1"
+    try:
+        eng = Engine(0)
+    finally:
+        del os.environ["GMAPDP_CHUNK_MB"]
+    try:
+        boxes = dpgen.synth_boxes(seed=88, n=3000, rmin=100, rmax=400)
+        b = eng.batch()
+        for x in boxes:
+            b.add(x)
+        b.run_device()                       # several chunks at 1 MB
+        with pytest.raises(EngineError):
+            b.run_resident()
+        b.upload()                           # a fresh single-chunk plan makes it legal again
+        b.run_resident()
+        b.finish()
+        b.free()
+    finally:
+        eng.close()

@@ -24,7 +24,7 @@ def lib():
 
 def declared_symbols():
     names = []
-    for h in ("gmapdp_b200.h", "gmapdp_shim.h", "gmapchain_b200.h"):
+    for h in ("gmapdp_b200.h", "gmapdp_shim.h", "gmapdp_stream.h", "gmapchain_b200.h"):
         text = open(os.path.join(ROOT, "include", h)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names += re.findall(r"\b((?:gmapdp|GmapDP|gmapchain|GmapChain)_\w+)\s*\(", text)
@@ -33,7 +33,7 @@ def declared_symbols():
 
 def test_exports_every_declared_symbol(lib):
     names = declared_symbols()
-    assert len(names) >= 45 and "gmapchain_run_batch" in names and "GmapChain_lookback" in names
+    assert len(names) >= 55 and "gmapchain_run_batch" in names and "GmapChain_lookback" in names and "gmapdp_stream_submit" in names
     for n in names:
         assert hasattr(lib, n), "missing export " + n
 
@@ -86,3 +86,50 @@ def test_maxlengths(lib):
     assert (mr.value, mg.value) == (660, 2000)          # SURVEY.md section 5 / dynprog.c:602-627
     lib.GmapDP_maxlengths(C.byref(mr), C.byref(mg), 1940, 20, 60, 10, 8)
     assert (mr.value, mg.value) == (2000, 2030)
+
+
+def test_stream_creation_fails_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from gmap_2024_b200 import Stream, EngineError
+    with pytest.raises(EngineError, match="no CPU fallback|CUDA"):
+        Stream(devices=(0,))
+
+
+def test_limits_and_user_penalties_are_validated(lib):
+    """a side longer than 32767 would overflow the kernels' 16-bit row/column fields; user penalties are in [-127, 0]"""
+    lib.GmapDP_batch_new.restype = C.c_void_p
+    assert lib.GmapDP_batch_new(None, 40000, 2000) is None
+    assert lib.GmapDP_batch_new(None, 2000, 32768) is None
+    h = C.c_void_p(lib.GmapDP_batch_new(None, 2000, 2030))
+    assert h
+    assert lib.GmapDP_batch_user_dynprog(h, -12, -4, 1) == 0
+    assert lib.GmapDP_batch_user_dynprog(h, 3, -4, 1) != 0
+    assert lib.GmapDP_batch_user_dynprog(h, -200, -4, 1) != 0
+    lib.GmapDP_batch_free(h)
+
+
+def test_user_penalties_reach_the_box(lib):
+    """host-resolved calls do not depend on the penalties; device boxes carry them (cdna gaps keep CDNA_OPEN/EXTEND)"""
+    from gmap_2024_b200.engine import Batch
+    b = Batch(_NoDevice(lib), 2000, 2030)
+    b.set_user_dynprog(-12, -4)
+    boxes = dpgen.synth_boxes(seed=10, n=400, rmin=20, rmax=120)
+    for x in boxes:
+        b.add(x)
+    ptr, n, _, _, _, _ = b.device_view()
+
+    class Box(C.Structure):
+        _fields_ = [("mode", C.c_int32), ("flags", C.c_int32), ("rlenL", C.c_int32), ("rlenR", C.c_int32), ("glenL", C.c_int32),
+                    ("glenR", C.c_int32), ("mismatchtype", C.c_int8), ("open", C.c_int8), ("extend", C.c_int8), ("cdna_direction", C.c_int8)]
+    seen = set()
+    for k in range(n):
+        x = Box.from_address(ptr.value + 76 * k)
+        seen.add(x.mode)
+        if x.mode == 2:
+            assert (x.open, x.extend) == (-10, -7)
+        else:
+            assert (x.open, x.extend) == (-12, -4)
+    assert seen == {0, 1, 2, 3, 4}
+    b.free()

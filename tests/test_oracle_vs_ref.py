@@ -84,3 +84,22 @@ def test_entry_points_identical_low_complexity(pair):
         assert o.run(b) == r.run(b), b["mode"]
         seen.add(b["mode"])
     assert len(seen) == 5
+
+
+@pytest.mark.parametrize("user_open,user_extend", [(-12, -4), (-5, -1), (-30, -10), (-60, -3), (-3, 0), (0, -2), (0, 0)])
+def test_entry_points_user_dynprog(pair, user_open, user_extend):
+    """--indel-open / --indel-extend (user_dynprog_p: dynprog_single.c:470, dynprog_genome.c:3367, dynprog_end.c:1334,1964):
+    gmap.c:5425-5445 accepts anything in [-127, 0].  Not tested: penalties so large that whole stripes saturate at
+    -128 (e.g. -127/-127): with jump_late_p the reference's single-gap traceback then follows ties out of the band
+    into direction cells no fill wrote (23 of 2400 such calls came out differently; the fills themselves are identical
+    cell for cell), i.e. the reference's own output is not a function of its inputs there."""
+    o, r = pair
+    o.set_user_dynprog(user_open, user_extend)
+    r.set_user_dynprog(user_open, user_extend)
+    try:
+        boxes, _ = dpgen.ref_boxes(r, 1000 - user_open * 3 - user_extend, 120)
+        for b in boxes:
+            assert o.run(b) == r.run(b), (b["mode"], user_open, user_extend)
+    finally:
+        o.set_user_dynprog(0, 0, False)
+        r.set_user_dynprog(0, 0, False)
