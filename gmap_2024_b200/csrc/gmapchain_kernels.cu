@@ -641,9 +641,9 @@ static int chain_state (gmapdp_ctx *ctx, ChainState **out) {
 template <typename T>
 static int growc (GdpCtxView &v, T **p, size_t *cap, size_t need) {
   if (need <= *cap && *p) return GMAPDP_OK;
-  if (*p) CKC(cudaFree(*p));
+  if (*p) v.grave->push_back((void *) *p);	/* freed with the context: cudaFree would synchronise the whole device */
   *p = NULL;
-  const size_t n = need + need / 4 + 64;
+  const size_t n = need + need / 2 + 64;
   CKC(cudaMalloc((void **) p,n * sizeof(T)));
   *cap = n;
   return GMAPDP_OK;
@@ -662,21 +662,13 @@ extern "C" int gmapchain_setup (gmapdp_ctx *ctx, int splicingp, int cross_specie
   return GMAPDP_OK;
 }
 
-extern "C" int gmapchain_upload (gmapdp_ctx *ctx, const gmapchain_problem *problems, int nproblems,
-				 const int32_t *npositions, const uint32_t *cumpositions, const uint32_t *minactive, const uint32_t *maxactive,
-				 size_t nquerypos, const uint32_t *positions, size_t npositions_total) {
+/* device buffers for batches of up to nproblems problems, nquerypos query positions and npositions_total hits;
+   callers that run many small batches (the drop-in) reserve once, so that no buffer is re-allocated in the middle of a run */
+extern "C" int gmapchain_reserve (gmapdp_ctx *ctx, int nproblems, size_t nquerypos, size_t npositions_total) {
   ChainState *s; int rc;
   GdpCtxView v = gmapdp_ctx_view(ctx);
   if ((rc = chain_state(ctx,&s)) != GMAPDP_OK) return rc;
   if (nproblems < 0) { *v.err = "gmapchain: negative problem count"; return GMAPDP_ERR_ARG; }
-  for (int i = 0; i < nproblems; i++) {
-    const gmapchain_problem &p = problems[i];
-    if (p.querylength < 0 || p.totalpositions < 0 || p.q_off + (uint64_t) p.querylength > nquerypos ||
-	p.p_off + (uint64_t) p.totalpositions > npositions_total || p.indexsize <= 0 || p.indexsize > 64 ||
-	p.queryend >= p.querylength || p.querystart < 0) {
-      *v.err = "gmapchain: problem " + std::to_string(i) + " is out of range of its pools"; return GMAPDP_ERR_ARG;
-    }
-  }
   CKC(cudaSetDevice(v.device));
   size_t cq = s->cap_q, cp = s->cap_p;
   if ((rc = growc(v,&s->d_problems,&s->cap_problems,(size_t) nproblems + 1))) return rc;
@@ -701,6 +693,28 @@ extern "C" int gmapchain_upload (gmapdp_ctx *ctx, const gmapchain_problem *probl
     c = cp; if ((rc = growc(v,&s->d_kept,&c,npositions_total + 1))) return rc;
     s->cap_p = c;
   }
+  /* output pools: a first guess, grown on GMAPDP_ERR_CAPACITY */
+  if ((rc = growc(v,&s->d_paths,&s->cap_paths,(size_t) nproblems * 2 + 64))) return rc;
+  if ((rc = growc(v,&s->d_pairs,&s->cap_pairs,2 * (nquerypos + 64)))) return rc;
+  return GMAPDP_OK;
+}
+
+extern "C" int gmapchain_upload (gmapdp_ctx *ctx, const gmapchain_problem *problems, int nproblems,
+				 const int32_t *npositions, const uint32_t *cumpositions, const uint32_t *minactive, const uint32_t *maxactive,
+				 size_t nquerypos, const uint32_t *positions, size_t npositions_total) {
+  ChainState *s; int rc;
+  GdpCtxView v = gmapdp_ctx_view(ctx);
+  if ((rc = chain_state(ctx,&s)) != GMAPDP_OK) return rc;
+  if (nproblems < 0) { *v.err = "gmapchain: negative problem count"; return GMAPDP_ERR_ARG; }
+  for (int i = 0; i < nproblems; i++) {
+    const gmapchain_problem &p = problems[i];
+    if (p.querylength < 0 || p.totalpositions < 0 || p.q_off + (uint64_t) p.querylength > nquerypos ||
+	p.p_off + (uint64_t) p.totalpositions > npositions_total || p.indexsize <= 0 || p.indexsize > 64 ||
+	p.queryend >= p.querylength || p.querystart < 0) {
+      *v.err = "gmapchain: problem " + std::to_string(i) + " is out of range of its pools"; return GMAPDP_ERR_ARG;
+    }
+  }
+  if ((rc = gmapchain_reserve(ctx,nproblems,nquerypos,npositions_total))) return rc;
   /* longest first (LPT): work grows with the hits and with the query length */
   std::vector<int> order(nproblems);
   for (int i = 0; i < nproblems; i++) order[i] = i;
@@ -715,9 +729,6 @@ extern "C" int gmapchain_upload (gmapdp_ctx *ctx, const gmapchain_problem *probl
   CKC(cudaMemcpyAsync(s->d_pos,positions,npositions_total * sizeof(uint32_t),cudaMemcpyHostToDevice,s->stream));
   CKC(cudaStreamSynchronize(s->stream));	/* `order` is a local */
   s->nproblems = nproblems; s->nq = nquerypos; s->np = npositions_total;
-  /* output pools: a first guess, grown by the caller on GMAPDP_ERR_CAPACITY */
-  if ((rc = growc(v,&s->d_paths,&s->cap_paths,(size_t) nproblems * 2 + 64))) return rc;
-  if ((rc = growc(v,&s->d_pairs,&s->cap_pairs,2 * (nquerypos + 64)))) return rc;
   return GMAPDP_OK;
 }
 

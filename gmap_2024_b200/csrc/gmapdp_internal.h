@@ -6,6 +6,7 @@
 #define GMAPDP_INTERNAL_H
 
 #include <string>
+#include <vector>
 #include "../../include/gmapdp_b200.h"
 
 struct GdpCtxView {
@@ -14,6 +15,8 @@ struct GdpCtxView {
   long *launches;
   void **chain;
   void (**chain_free) (void *);
+  std::vector<void *> *grave;	/* outgrown device buffers, freed when the context is destroyed (cudaFree synchronises the
+				   whole device: never while other engines' kernels are in flight) */
 };
 GdpCtxView gmapdp_ctx_view (gmapdp_ctx *ctx);
 
@@ -23,6 +26,8 @@ GdpCtxView gmapdp_ctx_view (gmapdp_ctx *ctx);
 struct GdpBoxGeom {
   int kind;			/* which kernel serves it */
   int bucket;			/* launch-order key: kind, then decreasing work (quantised) */
+  double work;			/* estimate of the box's duration on its warp (arbitrary unit, monotone) */
+  int steps;			/* wavefront steps its warp executes one after the other: stripes x columns, passes x length */
   int cols;			/* shared-memory columns it needs (kinds 0 and 3) */
   size_t ws_words;		/* per-warp workspace */
   size_t script_words;		/* upper bound of its edit script */
@@ -33,23 +38,28 @@ int gdp_bucket_count (void);
 
 struct GdpFlight {
   gmapdp_ctx *ctx;
-  int max_boxes; size_t seq_cap, prob_cap, script_cap;	/* script_cap in words */
-  /* pinned host staging: inputs are written in place by the submitting threads */
-  gmapdp_box *h_boxes; int *h_order; uint8_t *h_seq; double *h_probs;
-  unsigned char *h_out;		/* [16 B: script cursor][results: n x 64 B][script words] -- one D2H copy */
-  /* device twins */
-  gmapdp_box *d_boxes; int *d_order; uint8_t *d_seq; double *d_probs; unsigned char *d_out;
-  int *d_ctl;			/* 4 queue heads */
-  void *ev_in, *ev_k[GDP_NKINDS], *ev_done;	/* cudaEvent_t */
+  int max_boxes; size_t pool_cap, script_cap;	/* bytes; words */
+  /* pinned host staging, filled in place by the submitting threads:
+       h_in   = [32 B control block, zero][boxes: n x 76 B][launch order: n x 4 B]   -- ONE H2D copy of 32 + 80 n bytes
+       h_pool = sequences and MaxEnt probabilities of the boxes (probabilities 8-aligned; a box's prob offsets are in
+                doubles from the start of the pool)                                    -- ONE H2D copy of the used bytes
+       h_out  = [results: n x 64 B][script words]                                      -- ONE D2H copy */
+  unsigned char *h_in, *h_pool, *h_out;
+  unsigned char *d_in, *d_pool, *d_out;
+  void *ev_start, *ev_in, *ev_done;	/* cudaEvent_t */
   int n; size_t script_need;
+  bool timed; float gpu_ms, copy_ms;	/* GMAPDP_STREAM_TIMING: device time of the last flight (all of it / its uploads) */
 };
-int gdp_flight_create (gmapdp_ctx *ctx, GdpFlight **f, int max_boxes, size_t seq_cap, size_t prob_cap, size_t script_cap);
+static inline gmapdp_box *gdp_flight_boxes (GdpFlight *f) { return reinterpret_cast<gmapdp_box *>(f->h_in + 32); }
+static inline int *gdp_flight_order (GdpFlight *f, int n) { return reinterpret_cast<int *>(f->h_in + 32 + (size_t) n * sizeof(gmapdp_box)); }
+int gdp_flight_create (gmapdp_ctx *ctx, GdpFlight **f, int max_boxes, size_t pool_cap, size_t script_cap);
 void gdp_flight_destroy (GdpFlight *f);
-/* asynchronous: H2D of the used parts of the staging, the (up to) four kernels, D2H of cursor + results + script.
-   h_order lists the box ids kind by kind (cnt[kind] of each), each kind by decreasing work. */
-int gdp_flight_launch (GdpFlight *f, int n, size_t seqbytes, size_t nprobs, size_t script_need,
-		       const size_t *ws_words, const int *maxcols, const int *cnt);
+/* asynchronous: two H2D copies, ONE kernel that serves boxes of every kind (a flight is small: what counts is the
+   number of driver calls, not the instruction-cache footprint), one D2H copy, one event.  gdp_flight_order(f,n) lists
+   the box ids by decreasing duration estimate. */
+int gdp_flight_launch (GdpFlight *f, int n, size_t poolbytes, size_t script_need, size_t ws_words, int maxcols);
 int gdp_flight_poll (GdpFlight *f);		/* 1 finished, 0 still running, < 0 error */
+int gdp_flight_started (GdpFlight *f);	/* GMAPDP_STREAM_TIMING: 1 once the device has begun the flight */
 int gdp_flight_wait (GdpFlight *f);		/* blocks; 0 or error */
 /* after completion: the results (n entries) and the script pool in the pinned output buffer */
 int gdp_flight_results (GdpFlight *f, const gmapdp_result **results, const uint32_t **script);

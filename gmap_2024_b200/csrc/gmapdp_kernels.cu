@@ -1475,6 +1475,32 @@ gmapdp_dp_kernel (KernelArgs ka) {
   }
 }
 
+/* One kernel for boxes of every kind: the streaming runtime's flights (gmapdp_stream.cpp) hold tens to hundreds of
+   small boxes, for which the four specialisations above would cost four launches plus the stream joins -- more than the
+   boxes themselves.  Same per-box code, chosen per box; the instruction-cache argument for separate kernels does not
+   apply to a grid that covers a fraction of the SMs for a hundred microseconds. */
+__global__ void __launch_bounds__(BLOCK_THREADS,3)
+gmapdp_dp_kernel_any (KernelArgs ka) {
+  const GdpTables *tb = ka.tables;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint2 *bnd = reinterpret_cast<uint2 *>(dyn_smem) + (size_t) warp * ka.smem_cols;
+  const int gwarp = blockIdx.x * WARPS_PER_BLOCK + warp;
+  uint32_t *ws = ka.ws + (size_t) gwarp * ka.ws_words;
+
+  for (;;) {
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(ka.queue,1);
+    idx = __shfl_sync(FULLMASK,idx,0);
+    if (idx >= ka.nboxes) break;
+    const int bi = ka.order[idx];
+    const int mode = ka.boxes[bi].mode;
+    if (mode == GMAPDP_SINGLE) process_box<0>(ka,bi,ws,bnd,tb);
+    else if (mode == GMAPDP_GENOME) process_box<2>(ka,bi,ws,bnd,tb);
+    else if (mode == GMAPDP_CDNA) process_box<3>(ka,bi,ws,bnd,tb);
+    else process_box<1>(ka,bi,ws,bnd,tb);
+  }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Host side: context, memory, launches (the C ABI of include/gmapdp_b200.h)
  * ---------------------------------------------------------------------------------------------- */
@@ -1511,7 +1537,8 @@ struct gmapdp_ctx {
   /* resident batch */
   int nboxes; size_t ws_words; int smem_cols; size_t script_need;
   long launches;
-  std::vector<int> occ_cache[GDP_NK];	/* flights: resident blocks per SM by shared-memory size class */
+  std::vector<void *> grave;		/* outgrown device buffers (see grow) */
+  int any_occ; bool dev_set;		/* flights: resident blocks per SM of the all-kinds kernel; device already current in the launcher thread */
   /* the chaining engine (gmapchain_kernels.cu) hangs its state here */
   void *chain; void (*chain_free) (void *);
 };
@@ -1519,7 +1546,7 @@ struct gmapdp_ctx {
 GdpCtxView gmapdp_ctx_view (gmapdp_ctx *ctx) {
   GdpCtxView v;
   v.device = ctx->device; v.sm_count = ctx->sm_count; v.err = &ctx->err; v.launches = &ctx->launches;
-  v.chain = &ctx->chain; v.chain_free = &ctx->chain_free;
+  v.chain = &ctx->chain; v.chain_free = &ctx->chain_free; v.grave = &ctx->grave;
   return v;
 }
 
@@ -1529,9 +1556,12 @@ GdpCtxView gmapdp_ctx_view (gmapdp_ctx *ctx) {
 template <typename T>
 static int grow (gmapdp_ctx *ctx, T **p, size_t *cap, size_t need) {
   if (need <= *cap && *p) return GMAPDP_OK;
-  if (*p) CK(cudaFree(*p));
+  /* the outgrown buffer is kept until the context dies: cudaFree waits for every stream of the device -- other lanes'
+     flights, the chaining engine's kernels -- and holds the driver's lock while it does; buffers grow geometrically,
+     so what is parked stays below the final size */
+  if (*p) ctx->grave.push_back((void *) *p);
   *p = NULL;
-  size_t n = need + need / 4 + 64;
+  size_t n = need + need / 2 + 64;
   CK(cudaMalloc((void **) p,n * sizeof(T)));
   *cap = n;
   return GMAPDP_OK;
@@ -1546,7 +1576,7 @@ extern "C" int gmapdp_device_count (void) {
 extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   gmapdp_ctx *ctx = new gmapdp_ctx();
   *out = ctx;
-  ctx->device = device; ctx->launches = 0; ctx->nboxes = 0; ctx->chain = NULL; ctx->chain_free = NULL;
+  ctx->device = device; ctx->launches = 0; ctx->nboxes = 0; ctx->chain = NULL; ctx->chain_free = NULL; ctx->any_occ = 0; ctx->dev_set = false;
   ctx->d_tables = NULL; ctx->d_boxes = NULL; ctx->cap_boxes = 0; ctx->d_order = NULL; ctx->cap_order = 0; ctx->cap_results = 0; ctx->d_seq = NULL; ctx->cap_seq = 0;
   ctx->d_probs = NULL; ctx->cap_probs = 0; ctx->d_results = NULL; ctx->d_script = NULL; ctx->cap_script = 0;
   ctx->d_cursor = NULL; ctx->d_queue = NULL; ctx->d_ws = NULL; ctx->cap_ws = 0; ctx->h_pin = NULL; ctx->cap_pin = 0;
@@ -1558,6 +1588,13 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
     return GMAPDP_ERR_CUDA;
   }
   CK(cudaSetDevice(device));
+  /* Host threads that wait for the device sleep instead of spinning (cudaStreamSynchronize spins by default): in the
+     drop-in hundreds of worker threads share the cores, and a chaining batch keeps its leader waiting for milliseconds.
+     Kernel times are taken from CUDA events and do not depend on this.  GMAPDP_SYNC=spin keeps the driver's default. */
+  {
+    const char *sy = getenv("GMAPDP_SYNC");
+    if (!(sy && !strcmp(sy,"spin")) && cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync) != cudaSuccess) cudaGetLastError();
+  }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop,device));
   ctx->sm_count = prop.multiProcessorCount;
@@ -1590,6 +1627,7 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   CK(cudaFuncSetAttribute(gmapdp_dp_kernel<1>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
   CK(cudaFuncSetAttribute(gmapdp_dp_kernel<2>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
   CK(cudaFuncSetAttribute(gmapdp_dp_kernel<3>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
+  CK(cudaFuncSetAttribute(gmapdp_dp_kernel_any,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
   ctx->grid = 0;
   return GMAPDP_OK;
 }
@@ -1601,6 +1639,7 @@ extern "C" void gmapdp_destroy (gmapdp_ctx *ctx) {
   cudaFree(ctx->d_tables); cudaFree(ctx->d_boxes); cudaFree(ctx->d_order); cudaFree(ctx->d_seq); cudaFree(ctx->d_probs);
   cudaFree(ctx->d_results); cudaFree(ctx->d_script); cudaFree(ctx->d_cursor); cudaFree(ctx->d_queue); cudaFree(ctx->d_ws);
   for (int k = 0; k < GDP_NK; k++) cudaFree(ctx->d_kws[k]);
+  for (void *g : ctx->grave) cudaFree(g);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -2014,9 +2053,19 @@ int gdp_bucket_count (void) { return GDP_NK * GDP_WORK_BUCKETS; }
 int gdp_box_geometry (const gmapdp_box *b, GdpBoxGeom *g) {
   if (!box_ok(*b)) return GMAPDP_ERR_ARG;
   g->kind = kind_of(b->mode);
-  g->bucket = work_bucket(g->kind,box_work(*b));
+  g->work = box_work(*b);
   g->cols = (b->mode == GMAPDP_SINGLE || b->mode == GMAPDP_CDNA) ? (int) b->glenL + 2 : 8;
   g->ws_words = gdp_ws_words(*b);
+  if (b->mode == GMAPDP_SINGLE) {
+    const FGeom f = fgeom(b->rlenL,b->glenL,b->lbandL,b->ubandL);
+    g->steps = f.nstripes * f.T;
+  } else {
+    TriPacking tp;
+    tri_fills_of(*b,tp);
+    g->steps = tp.npasses * (tp.Tmax + 1);
+    if (b->mode == GMAPDP_CDNA) g->steps += (b->glenL / 32 + 1) * (b->lbandL + b->ubandL + 1);	/* the bridge's (cL, rL) loop */
+  }
+  g->bucket = work_bucket(0,(double) g->steps);		/* flights: one queue for all kinds, longest boxes first */
   g->script_words = (size_t) b->rlenL + b->glenL + 4;
   if (b->mode == GMAPDP_GENOME || b->mode == GMAPDP_CDNA) g->script_words += (size_t) b->rlenR + b->glenR + 4;
   return GMAPDP_OK;
@@ -2025,117 +2074,82 @@ int gdp_box_geometry (const gmapdp_box *b, GdpBoxGeom *g) {
 #define FCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     f->ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return GMAPDP_ERR_CUDA; } } while (0)
 
-static inline size_t flight_out_bytes (int nboxes, size_t script_words) { return 16 + (size_t) nboxes * sizeof(gmapdp_result) + script_words * sizeof(uint32_t); }
+static inline size_t flight_in_bytes (int nboxes) { return 32 + (size_t) nboxes * (sizeof(gmapdp_box) + sizeof(int)); }
+static inline size_t flight_out_bytes (int nboxes, size_t script_words) { return (size_t) nboxes * sizeof(gmapdp_result) + script_words * sizeof(uint32_t); }
 
-int gdp_flight_create (gmapdp_ctx *ctx, GdpFlight **out, int max_boxes, size_t seq_cap, size_t prob_cap, size_t script_cap) {
+int gdp_flight_create (gmapdp_ctx *ctx, GdpFlight **out, int max_boxes, size_t pool_cap, size_t script_cap) {
   GdpFlight *f = new GdpFlight();
   memset(f,0,sizeof(*f));
   *out = f;
-  f->ctx = ctx; f->max_boxes = max_boxes; f->seq_cap = seq_cap; f->prob_cap = prob_cap; f->script_cap = script_cap;
+  f->ctx = ctx; f->max_boxes = max_boxes; f->pool_cap = pool_cap; f->script_cap = script_cap;
   FCK(cudaSetDevice(ctx->device));
-  const size_t outb = flight_out_bytes(max_boxes,script_cap);
-  FCK(cudaHostAlloc((void **) &f->h_boxes,(size_t) max_boxes * sizeof(gmapdp_box),cudaHostAllocDefault));
-  FCK(cudaHostAlloc((void **) &f->h_order,(size_t) max_boxes * sizeof(int),cudaHostAllocDefault));
-  FCK(cudaHostAlloc((void **) &f->h_seq,seq_cap + 64,cudaHostAllocDefault));
-  FCK(cudaHostAlloc((void **) &f->h_probs,(prob_cap + 8) * sizeof(double),cudaHostAllocDefault));
+  const size_t inb = flight_in_bytes(max_boxes), outb = flight_out_bytes(max_boxes,script_cap);
+  FCK(cudaHostAlloc((void **) &f->h_in,inb,cudaHostAllocDefault));
+  FCK(cudaHostAlloc((void **) &f->h_pool,pool_cap + 64,cudaHostAllocDefault));
   FCK(cudaHostAlloc((void **) &f->h_out,outb,cudaHostAllocDefault));
-  FCK(cudaMalloc((void **) &f->d_boxes,(size_t) max_boxes * sizeof(gmapdp_box)));
-  FCK(cudaMalloc((void **) &f->d_order,(size_t) max_boxes * sizeof(int)));
-  FCK(cudaMalloc((void **) &f->d_seq,seq_cap + 64));
-  FCK(cudaMalloc((void **) &f->d_probs,(prob_cap + 8) * sizeof(double)));
+  memset(f->h_in,0,32);
+  FCK(cudaMalloc((void **) &f->d_in,inb));
+  FCK(cudaMalloc((void **) &f->d_pool,pool_cap + 64));
   FCK(cudaMalloc((void **) &f->d_out,outb));
-  FCK(cudaMalloc((void **) &f->d_ctl,GDP_NK * sizeof(int)));
   cudaEvent_t e;
-  FCK(cudaEventCreateWithFlags(&e,cudaEventDisableTiming)); f->ev_in = (void *) e;
-  FCK(cudaEventCreateWithFlags(&e,cudaEventDisableTiming | cudaEventBlockingSync)); f->ev_done = (void *) e;	/* the completer sleeps, it does not spin: the host cores belong to the workers */
-  for (int k = 0; k < GDP_NK; k++) { FCK(cudaEventCreateWithFlags(&e,cudaEventDisableTiming)); f->ev_k[k] = (void *) e; }
+  /* GMAPDP_STREAM_TIMING=1: the flight's events keep time stamps, so that the runtime can report the device's share of a
+     flight's latency.  ev_done is polled (cudaEventQuery) by the lane's service thread: no interrupt path, no blocking flag. */
+  f->timed = getenv("GMAPDP_STREAM_TIMING") != NULL;
+  FCK(cudaEventCreateWithFlags(&e,f->timed ? cudaEventDefault : cudaEventDisableTiming)); f->ev_in = (void *) e;
+  FCK(cudaEventCreateWithFlags(&e,f->timed ? cudaEventDefault : cudaEventDisableTiming)); f->ev_done = (void *) e;
+  FCK(cudaEventCreateWithFlags(&e,f->timed ? cudaEventDefault : cudaEventDisableTiming)); f->ev_start = (void *) e;
   return GMAPDP_OK;
 }
 
 void gdp_flight_destroy (GdpFlight *f) {
   if (!f) return;
   cudaSetDevice(f->ctx->device);
-  cudaFreeHost(f->h_boxes); cudaFreeHost(f->h_order); cudaFreeHost(f->h_seq); cudaFreeHost(f->h_probs); cudaFreeHost(f->h_out);
-  cudaFree(f->d_boxes); cudaFree(f->d_order); cudaFree(f->d_seq); cudaFree(f->d_probs); cudaFree(f->d_out); cudaFree(f->d_ctl);
+  cudaFreeHost(f->h_in); cudaFreeHost(f->h_pool); cudaFreeHost(f->h_out);
+  cudaFree(f->d_in); cudaFree(f->d_pool); cudaFree(f->d_out);
   if (f->ev_in) cudaEventDestroy((cudaEvent_t) f->ev_in);
   if (f->ev_done) cudaEventDestroy((cudaEvent_t) f->ev_done);
-  for (int k = 0; k < GDP_NK; k++) if (f->ev_k[k]) cudaEventDestroy((cudaEvent_t) f->ev_k[k]);
+  if (f->ev_start) cudaEventDestroy((cudaEvent_t) f->ev_start);
   delete f;
 }
 
-/* resident blocks per SM of a kernel kind at a given dynamic shared-memory size, asked once per size class */
-static int flight_occupancy (gmapdp_ctx *ctx, int kind, size_t smem) {
-  const size_t cls = (smem + 8191) / 8192;
-  std::vector<int> &cache = ctx->occ_cache[kind];
-  if (cache.size() <= cls) cache.resize(cls + 1,0);
-  if (cache[cls] == 0) {
-    int occ = 0;
-    cudaError_t e;
-    if (kind == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<0>,BLOCK_THREADS,cls * 8192);
-    else if (kind == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<1>,BLOCK_THREADS,cls * 8192);
-    else if (kind == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<2>,BLOCK_THREADS,cls * 8192);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel<3>,BLOCK_THREADS,cls * 8192);
-    if (e != cudaSuccess) { cudaGetLastError(); occ = 1; }
-    cache[cls] = std::min(std::max(occ,1),8);
-  }
-  return cache[cls];
-}
-
-int gdp_flight_launch (GdpFlight *f, int n, size_t seqbytes, size_t nprobs, size_t script_need,
-		       const size_t *ws_words, const int *maxcols, const int *cnt) {
+int gdp_flight_launch (GdpFlight *f, int n, size_t poolbytes, size_t script_need, size_t ws_words, int maxcols) {
   gmapdp_ctx *ctx = f->ctx;
-  if (n <= 0 || n > f->max_boxes || seqbytes > f->seq_cap || nprobs > f->prob_cap || script_need > f->script_cap) {
+  if (n <= 0 || n > f->max_boxes || poolbytes > f->pool_cap || script_need > f->script_cap) {
     ctx->err = "flight over capacity"; return GMAPDP_ERR_CAPACITY;
   }
-  FCK(cudaSetDevice(ctx->device));
+  if (!ctx->dev_set) { FCK(cudaSetDevice(ctx->device)); ctx->dev_set = true; }	/* the launcher thread serves one device */
   f->n = n; f->script_need = script_need;
   cudaStream_t s0 = ctx->stream;
-  /* geometry of the kernels this flight needs */
-  int grid[GDP_NK], cols[GDP_NK]; size_t wsw[GDP_NK], smem[GDP_NK];
-  for (int kind = 0; kind < GDP_NK; kind++) {
-    grid[kind] = 0; cols[kind] = 8; wsw[kind] = 0; smem[kind] = 0;
-    if (cnt[kind] == 0) continue;
-    wsw[kind] = (ws_words[kind] + 31) & ~(size_t) 31;
-    cols[kind] = (maxcols[kind] + 7) & ~7;
-    smem[kind] = (kind == 1 || kind == 2 || (kind == 0 && GMAPDP_BND_GLOBAL)) ? 0 : (size_t) WARPS_PER_BLOCK * cols[kind] * 8;
-    if ((int) smem[kind] > ctx->max_smem) { ctx->err = "box too long for the shared-memory rows"; return GMAPDP_ERR_ARG; }
-    const int full = ctx->sm_count * flight_occupancy(ctx,kind,smem[kind]);
-    grid[kind] = std::max(1,std::min(full,(cnt[kind] + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
-    /* the workspace is sized for a full grid once, so that it stops growing after the first large boxes */
-    if (grow(ctx,&ctx->d_kws[kind],&ctx->cap_kws[kind],(size_t) full * WARPS_PER_BLOCK * wsw[kind])) return GMAPDP_ERR_CUDA;
+  const size_t wsw = (ws_words + 31) & ~(size_t) 31;
+  const int cols = (maxcols + 7) & ~7;
+  const size_t smem = (size_t) WARPS_PER_BLOCK * cols * 8;
+  if ((int) smem > ctx->max_smem) { ctx->err = "box too long for the shared-memory rows"; return GMAPDP_ERR_ARG; }
+  if (ctx->any_occ == 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,gmapdp_dp_kernel_any,BLOCK_THREADS,(size_t) ctx->max_smem / 3) != cudaSuccess) { cudaGetLastError(); occ = 1; }
+    ctx->any_occ = std::min(std::max(occ,1),3);
   }
-  FCK(cudaMemcpyAsync(f->d_boxes,f->h_boxes,(size_t) n * sizeof(gmapdp_box),cudaMemcpyHostToDevice,s0));
-  FCK(cudaMemcpyAsync(f->d_order,f->h_order,(size_t) n * sizeof(int),cudaMemcpyHostToDevice,s0));
-  if (seqbytes) FCK(cudaMemcpyAsync(f->d_seq,f->h_seq,seqbytes,cudaMemcpyHostToDevice,s0));
-  if (nprobs) FCK(cudaMemcpyAsync(f->d_probs,f->h_probs,nprobs * sizeof(double),cudaMemcpyHostToDevice,s0));
-  FCK(cudaMemsetAsync(f->d_ctl,0,GDP_NK * sizeof(int),s0));
-  FCK(cudaMemsetAsync(f->d_out,0,16,s0));
-  FCK(cudaEventRecord((cudaEvent_t) f->ev_in,s0));
-  int nk = 0; for (int kind = 0; kind < GDP_NK; kind++) if (cnt[kind]) nk++;
-  const bool fan = (nk > 1 && n < 32768);		/* small flight: the kinds side by side on their own streams */
-  int start = 0;
-  for (int kind = 0; kind < GDP_NK; kind++) {
-    const int count = cnt[kind], first = start;
-    start += count;
-    if (count == 0) continue;
-    cudaStream_t st = fan ? ctx->kstream[kind] : s0;
-    if (st != s0) FCK(cudaStreamWaitEvent(st,(cudaEvent_t) f->ev_in,0));
-    KernelArgs ka;
-    ka.boxes = f->d_boxes; ka.order = f->d_order + first; ka.nboxes = count;
-    ka.seq = f->d_seq; ka.probs = f->d_probs;
-    ka.results = reinterpret_cast<gmapdp_result *>(f->d_out + 16);
-    ka.script = reinterpret_cast<uint32_t *>(f->d_out + 16 + (size_t) n * sizeof(gmapdp_result)); ka.script_cap = script_need;
-    ka.script_cursor = reinterpret_cast<unsigned long long *>(f->d_out);
-    ka.queue = f->d_ctl + kind; ka.ws = ctx->d_kws[kind]; ka.ws_words = wsw[kind];
-    ka.smem_cols = cols[kind]; ka.tables = ctx->d_tables; ka.one = 1u;
-    if (kind == 0) gmapdp_dp_kernel<0><<<grid[kind],BLOCK_THREADS,smem[kind],st>>>(ka);
-    else if (kind == 1) gmapdp_dp_kernel<1><<<grid[kind],BLOCK_THREADS,smem[kind],st>>>(ka);
-    else if (kind == 2) gmapdp_dp_kernel<2><<<grid[kind],BLOCK_THREADS,smem[kind],st>>>(ka);
-    else gmapdp_dp_kernel<3><<<grid[kind],BLOCK_THREADS,smem[kind],st>>>(ka);
-    FCK(cudaGetLastError());
-    ctx->launches++;
-    if (st != s0) { FCK(cudaEventRecord((cudaEvent_t) f->ev_k[kind],st)); FCK(cudaStreamWaitEvent(s0,(cudaEvent_t) f->ev_k[kind],0)); }
-  }
+  const int full = ctx->sm_count * ctx->any_occ;
+  const int grid = std::max(1,std::min(full,(n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
+  /* the workspace is sized for a full grid, so that it stops growing after the first large boxes */
+  if (grow(ctx,&ctx->d_kws[0],&ctx->cap_kws[0],(size_t) full * WARPS_PER_BLOCK * wsw)) return GMAPDP_ERR_CUDA;
+  if (f->timed) FCK(cudaEventRecord((cudaEvent_t) f->ev_start,s0));
+  FCK(cudaMemcpyAsync(f->d_in,f->h_in,flight_in_bytes(n),cudaMemcpyHostToDevice,s0));
+  if (poolbytes) FCK(cudaMemcpyAsync(f->d_pool,f->h_pool,poolbytes,cudaMemcpyHostToDevice,s0));
+  if (f->timed) FCK(cudaEventRecord((cudaEvent_t) f->ev_in,s0));
+  KernelArgs ka;
+  ka.boxes = reinterpret_cast<const gmapdp_box *>(f->d_in + 32);
+  ka.order = reinterpret_cast<const int *>(f->d_in + 32 + (size_t) n * sizeof(gmapdp_box)); ka.nboxes = n;
+  ka.seq = f->d_pool; ka.probs = reinterpret_cast<const double *>(f->d_pool);
+  ka.results = reinterpret_cast<gmapdp_result *>(f->d_out);
+  ka.script = reinterpret_cast<uint32_t *>(f->d_out + (size_t) n * sizeof(gmapdp_result)); ka.script_cap = script_need;
+  ka.queue = reinterpret_cast<int *>(f->d_in);						/* control block: queue head ... */
+  ka.script_cursor = reinterpret_cast<unsigned long long *>(f->d_in + 8);		/* ... and script cursor, zeroed by the upload */
+  ka.ws = ctx->d_kws[0]; ka.ws_words = wsw;
+  ka.smem_cols = cols; ka.tables = ctx->d_tables; ka.one = 1u;
+  gmapdp_dp_kernel_any<<<grid,BLOCK_THREADS,smem,s0>>>(ka);
+  FCK(cudaGetLastError());
+  ctx->launches++;
   FCK(cudaMemcpyAsync(f->h_out,f->d_out,flight_out_bytes(n,script_need),cudaMemcpyDeviceToHost,s0));
   FCK(cudaEventRecord((cudaEvent_t) f->ev_done,s0));
   return GMAPDP_OK;
@@ -2149,16 +2163,25 @@ int gdp_flight_poll (GdpFlight *f) {
   return GMAPDP_ERR_CUDA;
 }
 
+/* GMAPDP_STREAM_TIMING: has the device begun this flight?  (1 yes, 0 not yet) */
+int gdp_flight_started (GdpFlight *f) {
+  if (!f->timed) return 1;
+  return cudaEventQuery((cudaEvent_t) f->ev_start) == cudaSuccess ? 1 : 0;
+}
+
 int gdp_flight_wait (GdpFlight *f) {
   FCK(cudaEventSynchronize((cudaEvent_t) f->ev_done));
+  f->gpu_ms = f->copy_ms = 0.f;
+  if (f->timed) {
+    FCK(cudaEventElapsedTime(&f->gpu_ms,(cudaEvent_t) f->ev_start,(cudaEvent_t) f->ev_done));
+    FCK(cudaEventElapsedTime(&f->copy_ms,(cudaEvent_t) f->ev_start,(cudaEvent_t) f->ev_in));
+  }
   return GMAPDP_OK;
 }
 
 int gdp_flight_results (GdpFlight *f, const gmapdp_result **results, const uint32_t **script) {
-  const unsigned long long used = *reinterpret_cast<const unsigned long long *>(f->h_out);
-  if (used > f->script_need) { f->ctx->err = "device script pool overflow"; return GMAPDP_ERR_CAPACITY; }
-  *results = reinterpret_cast<const gmapdp_result *>(f->h_out + 16);
-  *script = reinterpret_cast<const uint32_t *>(f->h_out + 16 + (size_t) f->n * sizeof(gmapdp_result));
+  *results = reinterpret_cast<const gmapdp_result *>(f->h_out);
+  *script = reinterpret_cast<const uint32_t *>(f->h_out + (size_t) f->n * sizeof(gmapdp_result));
   return GMAPDP_OK;
 }
 

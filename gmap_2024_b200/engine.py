@@ -310,7 +310,7 @@ class Stream:
     def stats(self):
         out = (C.c_double * 9)()
         self.lib.gmapdp_stream_stats(self.h, out)
-        keys = ("boxes", "flights", "largest_flight", "reserved", "flight_seconds", "wait_seconds", "kernel_launches",
+        keys = ("boxes", "flights", "largest_flight", "device_seconds", "flight_seconds", "wait_seconds", "kernel_launches",
                 "h2d_bytes", "d2h_bytes")
         return dict(zip(keys, [float(x) for x in out]))
 

@@ -66,6 +66,9 @@ typedef struct gmapchain_path {		/* 32 bytes: the Cell_T the path starts from, a
  * cross_species_p must be 0. */
 int gmapchain_setup (gmapdp_ctx *ctx, int splicingp, int cross_species_p, int sufflookback, int nsufflookback, int maxintronlen);
 
+/* Optional: allocates the device buffers for batches of up to these sizes once (they otherwise grow on demand). */
+int gmapchain_reserve (gmapdp_ctx *ctx, int nproblems, size_t nquerypos, size_t npositions_total);
+
 /* Host-buffer path: H2D of the pools, chaining + ranking + tracebacks on the device, D2H of results.
  * Pairs come in traceback order (highest querypos first).  Returns GMAPDP_ERR_CAPACITY, with *paths_used /
  * *pairs_used = what is needed, if an output pool is too small. */

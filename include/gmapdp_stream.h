@@ -11,10 +11,10 @@
  *   -------------                      -------------------------          --------------------------
  *   gmapdp_stream_submit(box)    -->   closes the open flight as soon     waits for the oldest flight's
  *     reserves a slot in the open      as the GPU can take it (at most    D2H, publishes results, wakes
- *     flight, copies its sequences     GMAPDP_STREAM_DEPTH flights in     the flight's waiters with one
- *     into the pinned staging          flight), orders the boxes, issues  futex broadcast
- *   gmapdp_stream_wait(ticket)         3 H2D + <= 4 kernels + 1 D2H
- *     sleeps on the flight's futex
+ *     flight, copies its sequences     GMAPDP_STREAM_DEPTH flights in     
+ *     into the pinned staging          flight), orders the boxes, issues
+ *   gmapdp_stream_wait(ticket)         2 H2D + 1 kernel + 1 D2H      the first waiters; every waiter
+ *     sleeps on its box's futex                                           wakes two more (tree)
  *   ... replays its own edit script (in parallel with all other workers) ...
  *   gmapdp_stream_release(ticket)
  *
@@ -22,8 +22,9 @@
  * next one fills while the previous ones run (throughput); no timeouts, no global lock around device work, no
  * thundering herd (a waiter touches no mutex when it wakes).  Results never depend on how boxes were grouped.
  *
- * Multi-GPU: one lane (context, launcher, completer, flights) per device; a worker thread is pinned to one lane
- * for its lifetime, so the dependent chain of a query stays on one device.  No collective.
+ * Multi-GPU: every device has its own lanes (context, launcher, completer, flights -- one lane per box size class); a
+ * worker thread is pinned to one device for its lifetime, so the dependent chain of a query stays on one device
+ * (SURVEY.md section 8e).  No collective.
  * There is no CPU fallback: creation fails without an sm_100 device.
  */
 #ifndef GMAPDP_STREAM_H
@@ -61,10 +62,20 @@ int gmapdp_stream_wait (gmapdp_stream *s, const gmapdp_ticket *ticket, const gma
 void gmapdp_stream_release (gmapdp_stream *s, const gmapdp_ticket *ticket);
 
 /* counters since creation, summed over lanes:
- *   [0] boxes  [1] flights  [2] largest flight  [3] reserved  [4] seconds a flight spent between launch and completion (sum)
+ *   [0] boxes  [1] flights  [2] largest flight  [3] seconds of device time (with GMAPDP_STREAM_TIMING=1)  [4] seconds a flight spent between launch and completion (sum)
  *   [5] seconds boxes waited between submit and wake-up (sum)  [6] kernel launches  [7] bytes host->device  [8] bytes device->host */
 #define GMAPDP_STREAM_NSTATS 9
 void gmapdp_stream_stats (const gmapdp_stream *s, double *out);
+/* Lanes: every device has one lane per box size class (small boxes never share a flight with a large one, whose warp
+ * would keep the whole flight waiting).  out[11] = boxes, flights, largest flight, mean flight latency (us), mean device
+ * time per flight (us; needs GMAPDP_STREAM_TIMING=1), mean upload time per flight (us), then the host stages of a flight
+ * (us): closed -> launch call, the launch call, launch returned -> completion seen, root wake-ups,
+ * launch returned -> device seen to have begun (GMAPDP_STREAM_TIMING=1).
+ * Lane = device index x classes + class. */
+int gmapdp_stream_nlanes (const gmapdp_stream *s);
+/* how the lanes' service threads are scheduled: 1 SCHED_FIFO (GMAPDP_STREAM_RT=1 and permitted), 2 short EEVDF slices, 3 default */
+int gmapdp_stream_sched_mode (const gmapdp_stream *s);
+int gmapdp_stream_lane_stats (const gmapdp_stream *s, int lane, double *out);
 
 #ifdef __cplusplus
 }

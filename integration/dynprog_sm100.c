@@ -48,13 +48,23 @@ static pthread_key_t sm100_key;
 static int sm100_user_open = 0, sm100_user_extend = 0, sm100_user_dynprog_p = 0;
 static int sm100_devices[64], sm100_ndevices = 0;
 static unsigned long sm100_ncalls = 0, sm100_nhost = 0;
-static double sm100_t0 = 0.0;
+static double sm100_t0 = 0.0, sm100_t_init = 0.0;
 
 static double now_s (void) {
   struct timespec t;
   clock_gettime(CLOCK_MONOTONIC,&t);
   return (double) t.tv_sec + 1e-9 * (double) t.tv_nsec;
 }
+
+/* GMAP_SM100_STATS: where the host time of the five entry points goes (time-stamp counter, summed over all threads):
+   0 segment fetch + MaxEnt, 1 call preparation (shim), 2 submit, 3 asleep waiting for the flight, 4 script replay, 5 pairs -> List_T */
+#define SM100_NPROF 6
+static int sm100_prof_on = 0;
+static unsigned long long sm100_prof[SM100_NPROF], sm100_tsc0 = 0;
+static __thread unsigned long long sm100_prof_last;
+static inline unsigned long long sm100_tsc (void) { unsigned int lo, hi; __asm__ __volatile__("rdtsc" : "=a"(lo), "=d"(hi)); return ((unsigned long long) hi << 32) | lo; }
+#define PROF_BEGIN() do { if (sm100_prof_on) sm100_prof_last = sm100_tsc(); } while (0)
+#define PROF_MARK(k) do { if (sm100_prof_on) { unsigned long long t_ = sm100_tsc(); __sync_fetch_and_add(&sm100_prof[k],t_ - sm100_prof_last); sm100_prof_last = t_; } } while (0)
 
 static void sm100_die (const char *what) {
   fprintf(stderr,"gmap.sm100: %s\n",what);
@@ -71,6 +81,24 @@ static void sm100_report (void) {
 	  "mean batch latency %.1f us, mean wait per box %.1f us, %.0f kernel launches, %.1f MB up, %.1f MB down, %.3f s since first call\n",
 	  gmapdp_stream_ndevices(sm100_stream),st[0],sm100_nhost,st[2],st[1] > 0.0 ? 1e6 * st[4] / st[1] : 0.0,
 	  st[0] > 0.0 ? 1e6 * st[5] / st[0] : 0.0,st[6],st[7] / 1e6,st[8] / 1e6,now_s() - sm100_t0);
+  if (sm100_prof_on) {
+    const double hz = (double) (sm100_tsc() - sm100_tsc0) / (now_s() - sm100_t0);
+    fprintf(stderr,"gmap.sm100 host time in the entry points (thread-seconds): fetch+MaxEnt %.2f, prepare %.2f, submit %.2f, asleep %.2f, replay %.2f, list %.2f\n",
+	    sm100_prof[0] / hz,sm100_prof[1] / hz,sm100_prof[2] / hz,sm100_prof[3] / hz,sm100_prof[4] / hz,sm100_prof[5] / hz);
+  }
+  fprintf(stderr,"gmap.sm100 start-up: %.3f s to create the runtime (contexts, pinned staging, device buffers)\n",sm100_t_init);
+  fprintf(stderr,"gmap.sm100 service threads: scheduling mode %d (1 FIFO, 2 short slices, 3 default)\n",gmapdp_stream_sched_mode(sm100_stream));
+  {
+    int lane, nl = gmapdp_stream_nlanes(sm100_stream);
+    double ls[11];
+    for (lane = 0; lane < nl; lane++) {
+      gmapdp_stream_lane_stats(sm100_stream,lane,ls);
+      if (ls[1] > 0.0)
+	fprintf(stderr,"gmap.sm100 lane %d: %.0f boxes in %.0f batches (largest %.0f), batch latency %.1f us, device %.1f us, upload %.1f us; "
+		"host stages: close->launch %.1f, launch call %.1f, launched->seen %.1f (device begun after %.1f), root wake-ups %.1f us\n",
+		lane,ls[0],ls[1],ls[2],ls[3],ls[4],ls[5],ls[6],ls[7],ls[8],ls[10],ls[9]);
+    }
+  }
 }
 
 static void sm100_free_mini (void *p) { if (p) GmapDP_batch_free((gmapdp_batch *) p); }
@@ -93,12 +121,15 @@ static void sm100_init (void) {
     }
   }
   memcpy(sm100_devices,devices,sizeof(devices)); sm100_ndevices = n;
+  sm100_t_init = now_s();
   if ((rc = gmapdp_stream_create(&sm100_stream,devices,n,0)) != GMAPDP_OK) {
     fprintf(stderr,"gmap.sm100: %s\n",gmapdp_stream_error(sm100_stream));
     exit(9);
   }
   pthread_key_create(&sm100_key,sm100_free_mini);
-  sm100_t0 = now_s();
+  sm100_t0 = now_s(); sm100_tsc0 = sm100_tsc();
+  sm100_t_init = sm100_t0 - sm100_t_init;
+  sm100_prof_on = getenv("GMAP_SM100_STATS") != NULL;
   atexit(sm100_report);
 }
 
@@ -184,15 +215,30 @@ static void run_call (gmapdp_batch *b) {
   __sync_fetch_and_add(&sm100_ncalls,1);
   if (GmapDP_batch_device_view(b,&boxes,&nboxes,&seq,&seqbytes,&probs,&nprobs) != GMAPDP_OK) sm100_die(GmapDP_batch_error(b));
   if (nboxes == 0) { __sync_fetch_and_add(&sm100_nhost,1); return; }	/* resolved by the entry point's own shortcuts */
-  if (gmapdp_stream_submit(sm100_stream,&boxes[0],seq,seqbytes,probs,nprobs,&ticket) != GMAPDP_OK ||
-      gmapdp_stream_wait(sm100_stream,&ticket,&res,&ops) != GMAPDP_OK) sm100_die(gmapdp_stream_error(sm100_stream));
+  if (gmapdp_stream_submit(sm100_stream,&boxes[0],seq,seqbytes,probs,nprobs,&ticket) != GMAPDP_OK) {
+    fprintf(stderr,"gmap.sm100: DP submit: %s\n",gmapdp_stream_error(sm100_stream)); exit(9);
+  }
+  PROF_MARK(2);
+  if (gmapdp_stream_wait(sm100_stream,&ticket,&res,&ops) != GMAPDP_OK) {
+    fprintf(stderr,"gmap.sm100: DP wait: %s\n",gmapdp_stream_error(sm100_stream)); exit(9);
+  }
+  PROF_MARK(3);
   r = *res; r.script_off = 0;
-  if (GmapDP_batch_complete(b,&r,ops) != GMAPDP_OK) sm100_die(GmapDP_batch_error(b));
+  if (GmapDP_batch_complete(b,&r,ops) != GMAPDP_OK) {
+    fprintf(stderr,"gmap.sm100: DP replay: %s\n",GmapDP_batch_error(b)); exit(9);
+  }
   gmapdp_stream_release(sm100_stream,&ticket);
+  PROF_MARK(4);
 }
 
 /* records come head first: cons them from the tail */
+static List_T pairs_to_list_raw (Pairpool_T pool, const gmapdp_pair *p, int n);
 static List_T pairs_to_list (Pairpool_T pool, const gmapdp_pair *p, int n) {
+  List_T l = pairs_to_list_raw(pool,p,n);
+  PROF_MARK(5);
+  return l;
+}
+static List_T pairs_to_list_raw (Pairpool_T pool, const gmapdp_pair *p, int n) {
   List_T l = NULL;
   Pair_T g;
   int k;
@@ -226,6 +272,7 @@ Dynprog_single_gap (int *dynprogindex, int *traceback_score, int *nmatches, int 
   List_T l;
   bool fetch = (rlength > 0 && glength > 0 && rlength <= dynprog->max_rlength && glength <= dynprog->max_glength);
 
+  PROF_BEGIN();
   if (fetch) {
     gseq = (char *) malloc(glength + 1); galt = (char *) malloc(glength + 1);
     if (watsonp) Genome_get_segment_right(gseq,galt,genome,genomealt,chroffset+goffset,glength,chrhigh,/*revcomp*/false);
@@ -233,8 +280,10 @@ Dynprog_single_gap (int *dynprogindex, int *traceback_score, int *nmatches, int 
   } else {
     gseq = galt = empty;
   }
+  PROF_MARK(0);
   id = GmapDP_single_gap(b,*dynprogindex,rsequence,rsequenceuc,rlength,glength,roffset,goffset,gseq,galt,
 			 jump_late_p,extraband_single,widebandp,defect_rate);
+  PROF_MARK(1);
   run_call(b);
   n = GmapDP_result_view(b,id,&iout,NULL,&pairs);
   *dynprogindex = iout[0]; *traceback_score = iout[1]; *nmatches = iout[2]; *nmismatches = iout[3];
@@ -260,6 +309,7 @@ end_gap (bool end5, int *dynprogindex, int *traceback_score, int *nmatches, int 
   /* the reference chops before it fetches (dynprog_end.c:1357-1378 / :1986-1999) */
   if (endalign != QUERYEND_NOGAPS && gl > dynprog->max_glength) gl = dynprog->max_glength;
   fetch = (rlength > 0 && gl > 0 && !(end5 && goffset < 0));
+  PROF_BEGIN();
   if (fetch) {
     gseq = (char *) malloc(gl + 1); galt = (char *) malloc(gl + 1);
     if (end5) {
@@ -272,10 +322,12 @@ end_gap (bool end5, int *dynprogindex, int *traceback_score, int *nmatches, int 
   } else {
     gseq = galt = empty;
   }
+  PROF_MARK(0);
   if (end5) id = GmapDP_end5_gap(b,*dynprogindex,rseq,rsequc,rlength,glength,roffset,goffset,gseq,galt,jump_late_p,
 				 extraband_end,defect_rate,(int) endalign,require_pos_score_p);
   else id = GmapDP_end3_gap(b,*dynprogindex,rseq,rsequc,rlength,glength,roffset,goffset,gseq,galt,jump_late_p,
 			    extraband_end,defect_rate,(int) endalign,require_pos_score_p);
+  PROF_MARK(1);
   run_call(b);
   n = GmapDP_result_view(b,id,&iout,NULL,&pairs);
   *dynprogindex = iout[0]; *traceback_score = iout[1]; *nmatches = iout[2]; *nmismatches = iout[3];
@@ -337,6 +389,7 @@ Dynprog_genome_gap (int *dynprogindex, int *new_leftgenomepos, int *new_rightgen
   bool fetch = (rlength > 1 && rlength <= dynprogL->max_rlength && glengthL <= dynprogL->max_glength &&
 		rlength <= dynprogR->max_rlength && glengthR <= dynprogR->max_glength && glengthL > 0 && glengthR > 0);
 
+  PROF_BEGIN();
   if (fetch) {
     gL = (char *) malloc(glengthL + 1); gLa = (char *) malloc(glengthL + 1);
     gR = (char *) malloc(glengthR + 1); gRa = (char *) malloc(glengthR + 1);
@@ -371,8 +424,10 @@ Dynprog_genome_gap (int *dynprogindex, int *new_leftgenomepos, int *new_rightgen
   } else {
     gL = gLa = gR = gRa = empty;
   }
+  PROF_MARK(0);
   id = GmapDP_genome_gap(b,*dynprogindex,rsequence,rsequenceuc,rlength,glengthL,glengthR,roffset,goffsetL,rev_goffsetR,
 			 gL,gLa,gR,gRa,lp,rp,cdna_direction,jump_late_p,extraband_paired,defect_rate,maxpeelback,halfp,finalp);
+  PROF_MARK(1);
   run_call(b);
   n = GmapDP_result_view(b,id,&iout,&dout,&pairs);
   *dynprogindex = iout[0];
@@ -402,6 +457,7 @@ Dynprog_cdna_gap (int *dynprogindex, int *traceback_score, bool *incompletep,
   bool fetch = (glength > 1 && glength <= dynprogR->max_glength && rlengthR <= dynprogR->max_rlength &&
 		glength <= dynprogL->max_glength && rlengthL <= dynprogL->max_rlength);
 
+  PROF_BEGIN();
   if (fetch) {
     g = (char *) malloc(glength + 1); ga = (char *) malloc(glength + 1);
     rg = (char *) malloc(glength + 1); rga = (char *) malloc(glength + 1);
@@ -415,8 +471,10 @@ Dynprog_cdna_gap (int *dynprogindex, int *traceback_score, bool *incompletep,
   } else {
     g = ga = rg = rga = empty;
   }
+  PROF_MARK(0);
   id = GmapDP_cdna_gap(b,*dynprogindex,rsequenceL,rsequence_ucL,rev_rsequenceR,rev_rsequence_ucR,rlengthL,rlengthR,glength,
 		       roffsetL,rev_roffsetR,goffset,g,ga,rg,rga,jump_late_p,extraband_paired,defect_rate);
+  PROF_MARK(1);
   run_call(b);
   n = GmapDP_result_view(b,id,&iout,NULL,&pairs);
   *dynprogindex = iout[0];

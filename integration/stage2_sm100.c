@@ -15,6 +15,7 @@
  * program with a message instead of silently running on the CPU.
  */
 #include <pthread.h>
+#include <time.h>
 #include "bool.h"
 #include "types.h"
 #include "genomicpos.h"
@@ -71,6 +72,7 @@ typedef struct chain_group {
   int readers[2];		/* calls of batch k that have not read their paths yet */
   unsigned long seq[2];		/* completed runs of batch k */
   bool running;
+  double t_run;			/* seconds spent in GmapChain_batch_run */
 } chain_group;
 
 #define CHAIN_MAXGROUPS 64
@@ -80,14 +82,27 @@ static pthread_once_t chain_once = PTHREAD_ONCE_INIT;
 static unsigned long chain_ncalls = 0, chain_nbatches = 0, chain_next_group = 0;
 static __thread int chain_my_group = -1;
 
+static double chain_t_init = 0.0;
+static double chain_now (void) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC,&t);
+  return (double) t.tv_sec + 1e-9 * (double) t.tv_nsec;
+}
+
 static void chain_report (void) {
-  if (getenv("GMAP_SM100_STATS"))
-    fprintf(stderr,"gmap.sm100 stage 2: %lu chaining calls on the device in %lu batches, %lu handed to the reference body\n",
-	    chain_ncalls,chain_nbatches,0UL);
+  double t = 0.0;
+  int g;
+  if (getenv("GMAP_SM100_STATS") == NULL) return;
+  for (g = 0; g < chain_ngroups; g++) t += chain_groups[g].t_run;
+  fprintf(stderr,"gmap.sm100 stage 2: %lu chaining calls on the device in %lu batches, %lu handed to the reference body\n",
+	  chain_ncalls,chain_nbatches,0UL);
+  fprintf(stderr,"gmap.sm100 stage 2 runtime: %d groups, mean batch latency %.1f us, start-up %.3f s\n",chain_ngroups,
+	  chain_nbatches ? 1e6 * t / (double) chain_nbatches : 0.0,chain_t_init);
 }
 
 static void chain_init (void) {
   const char *e = getenv("GMAP_SM100_CHAIN_GROUPS");
+  const double t_begin = chain_now();
   int g;
   chain_ngroups = e ? atoi(e) : 8;
   if (chain_ngroups < 1) chain_ngroups = 1;
@@ -102,10 +117,16 @@ static void chain_init (void) {
       fprintf(stderr,"gmap.sm100: %s\n",gmapdp_last_error(G->ctx));
       exit(9);
     }
+    /* room for a few dozen queries of ordinary size per batch: device buffers are then not re-allocated mid-run */
+    if (gmapchain_reserve(G->ctx,64,(size_t) 1 << 18,(size_t) 1 << 21) != GMAPDP_OK) {
+      fprintf(stderr,"gmap.sm100: %s\n",gmapdp_last_error(G->ctx));
+      exit(9);
+    }
     G->batch[0] = GmapChain_batch_new(G->ctx); G->batch[1] = GmapChain_batch_new(G->ctx);
     G->fill = 0; G->npending[0] = G->npending[1] = 0; G->readers[0] = G->readers[1] = 0; G->seq[0] = G->seq[1] = 0;
-    G->running = false;
+    G->running = false; G->t_run = 0.0;
   }
+  chain_t_init = chain_now() - t_begin;
   atexit(chain_report);
 }
 
@@ -139,7 +160,7 @@ chain_on_device (bool forwardp, CHAIN_PARAMS) {
 			    non_canonical_penalty,favor_right_p,middlep,max_nalignments);
   }
   if (id < 0) {
-    fprintf(stderr,"gmap.sm100: %s\n",GmapChain_batch_error(B));
+    fprintf(stderr,"gmap.sm100: chaining call refused (%d): %s\n",id,GmapChain_batch_error(B));
     exit(9);
   }
   G->npending[kb]++;
@@ -148,13 +169,18 @@ chain_on_device (bool forwardp, CHAIN_PARAMS) {
     if (G->running == false && G->fill == kb) {
       /* lead: later calls go to the other batch while this one runs */
       int nrun = G->npending[kb];
+      double t0;
+      int rc;
       G->running = true; G->fill = kb ^ 1; G->npending[kb] = 0;
       pthread_mutex_unlock(&G->mu);
-      if (GmapChain_batch_run(B) != GMAPDP_OK) {
-	fprintf(stderr,"gmap.sm100: %s\n",GmapChain_batch_error(B));
+      t0 = chain_now();
+      if ((rc = GmapChain_batch_run(B)) != GMAPDP_OK) {
+	fprintf(stderr,"gmap.sm100: chaining batch failed (%d): %s\n",rc,GmapChain_batch_error(B));
 	exit(9);
       }
+      t0 = chain_now() - t0;
       pthread_mutex_lock(&G->mu);
+      G->t_run += t0;
       __sync_fetch_and_add(&chain_ncalls,(unsigned long) nrun); __sync_fetch_and_add(&chain_nbatches,1UL);
       G->readers[kb] = nrun; G->seq[kb]++; G->running = false;
       pthread_cond_broadcast(&G->cv);
