@@ -177,6 +177,8 @@ struct Call {
   int roffset = 0, goffset = 0, roffsetR = 0, goffsetR = 0;
   int endalign = 0, introntype_in = 0;
   bool require_pos = false, end5 = false;
+  int iout_q[10]; double dout_q[2];	/* the out-parameters as they stood when the box was queued (GmapDP_batch_rewind) */
+  void queued () { for (int i = 0; i < 10; i++) iout_q[i] = iout[i]; dout_q[0] = dout[0]; dout_q[1] = dout[1]; }
   Call () { for (int i = 0; i < 10; i++) iout[i] = 0; dout[0] = dout[1] = 0.0; }
 };
 
@@ -324,7 +326,7 @@ extern "C" int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char 
   x.gL_off = x.gR_off = b->add_bytes(c.gL.data(),glength);
   x.gLalt_off = x.gRalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
   add_cells(b,gdp_cells_full(rlength,glength,lband,uband),use8,true);
-  c.box = (int) b->boxes.size();
+  c.box = (int) b->boxes.size(); c.queued();
   b->boxes.push_back(x); b->box_call.push_back(id);
   return id;
 }
@@ -397,7 +399,7 @@ static int end_gap (gmapdp_batch *b, bool end5, int dynprogindex, const char *rs
   x.gLalt_off = x.gRalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
   x.revmask = end5 ? 1 : 0;
   add_cells(b,gdp_cells_tri(rlength,glength,uband) + gdp_cells_tri(glength,rlength,lband),use8);
-  c.box = (int) b->boxes.size();
+  c.box = (int) b->boxes.size(); c.queued();
   b->boxes.push_back(x); b->box_call.push_back(id);
   return id;
 }
@@ -525,7 +527,7 @@ extern "C" int GmapDP_genome_gap (gmapdp_batch *b, int dynprogindex, const char 
   x.revmask = 2;
   add_cells(b,gdp_cells_tri(rlength,glengthL,ubandL) + gdp_cells_tri(glengthL,rlength,lbandL) +
 	    gdp_cells_tri(rlength,glengthR,ubandR) + gdp_cells_tri(glengthR,rlength,lbandR),use8);
-  c.box = (int) b->boxes.size();
+  c.box = (int) b->boxes.size(); c.queued();
   b->boxes.push_back(x); b->box_call.push_back(id);
   return id;
 }
@@ -578,7 +580,7 @@ extern "C" int GmapDP_cdna_gap (gmapdp_batch *b, int dynprogindex,
   x.revmask = 2;
   add_cells(b,gdp_cells_tri(rlengthL,glength,ubandL) + gdp_cells_tri(glength,rlengthL,lbandL) +
 	    gdp_cells_tri(rlengthR,glength,ubandR) + gdp_cells_tri(glength,rlengthR,lbandR),use8);
-  c.box = (int) b->boxes.size();
+  c.box = (int) b->boxes.size(); c.queued();
   b->boxes.push_back(x); b->box_call.push_back(id);
   return id;
 }
@@ -704,6 +706,18 @@ static int finish_all (gmapdp_batch *b, const gmapdp_result *results, const uint
   }
   if (b->count_mismatch) { b->err = "device traceback counts disagree with the host replay"; return GMAPDP_ERR_ARG; }
   return GMAPDP_OK;
+}
+
+/* Puts the device calls back into their queued state (results and pair lists dropped), so that the same batch can be
+   completed again: benchmarks time GmapDP_batch_run -- device and replay -- repeatedly on one batch. */
+extern "C" void GmapDP_batch_rewind (gmapdp_batch *b) {
+  for (Call &c : b->calls) {
+    if (c.box < 0) continue;
+    c.done = false; c.isnull = true; c.pairs.clear();
+    for (int i = 0; i < 10; i++) c.iout[i] = c.iout_q[i];
+    c.dout[0] = c.dout_q[0]; c.dout[1] = c.dout_q[1];
+  }
+  b->count_mismatch = 0;
 }
 
 /* The device part of the queued calls, for callers that run the boxes themselves (the streaming runtime of

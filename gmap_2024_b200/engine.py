@@ -194,6 +194,10 @@ class Batch:
     def run(self):
         self._check(self.lib.GmapDP_batch_run(self.h))
 
+    def rewind(self):
+        """device calls back to their queued state (run() can then be repeated and timed)"""
+        self.lib.GmapDP_batch_rewind(self.h)
+
     def upload(self):
         self._check(self.lib.GmapDP_batch_upload(self.h))
 

@@ -99,8 +99,11 @@ int GmapDP_cdna_gap (gmapdp_batch *b, int dynprogindex,
 		     const char *rev_gsequence, const char *rev_gsequence_alt,
 		     int jump_late_p, int extraband_paired, double defect_rate);
 
-/* Runs every queued device box (one gmapdp_run_batch) and completes all calls. */
+/* Runs every queued device box (one gmapdp_run_batch) and completes all calls: the edit scripts are replayed into pair
+ * lists (large batches: on several host threads, GMAPDP_REPLAY_THREADS). */
 int GmapDP_batch_run (gmapdp_batch *b);
+/* Puts the device calls back into their queued state, so that GmapDP_batch_run can be repeated on the same batch. */
+void GmapDP_batch_rewind (gmapdp_batch *b);
 /* resident variant for benchmarks: pack + upload once, then time the kernel alone */
 int GmapDP_batch_upload (gmapdp_batch *b);
 int GmapDP_batch_run_resident (gmapdp_batch *b, float *kernel_ms);

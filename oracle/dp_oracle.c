@@ -288,12 +288,23 @@ static void fill_full (const seqs_t *s, int open, int extend, int lband, int uba
 #undef MI
 }
 
+/* Algorithmic in-band cells of the fills run since the last orc_cells_reset(): how the CPU arms of
+   bench.py count their work without the product library.  In count-only mode the entry points follow their control
+   flow up to the fills (the no-fill shortcuts count zero cells), count, and return -1 without filling anything. */
+static long cells_filled = 0;
+static int count_only = 0;
+void orc_cells_reset (void) { cells_filled = 0; }
+long orc_cells_filled (void) { return cells_filled; }
+void orc_set_count_only (int on) { count_only = on; }
+
 int orc_fill (int kind, int bits, const char *rseq, const char *gseq, const char *galt,
 	      int rlength, int glength, int mismatchtype, int open, int extend,
 	      int lband, int uband, int jump_late_p, int revp,
 	      short *H, signed char *dN, signed char *dE, signed char *dF) {
   seqs_t s;
   orc_init();
+  cells_filled += orc_cells(kind,rlength,glength,lband,uband);
+  if (count_only) return 0;
   s.bits = bits; s.NEG = bits == 8 ? -128 : -32768; s.POS = bits == 8 ? 127 : 32767;
   s.rs = rseq; s.gs = gseq; s.ga = galt; s.rlength = rlength; s.glength = glength; s.revp = revp; s.mt = mismatchtype;
   if (kind == 0) fill_full(&s,open,extend,lband,uband,jump_late_p,bits == 8 ? 32 : 16,H,dN,dE,dF);
@@ -540,6 +551,7 @@ int orc_single_gap (int *iout, const char *queryseq, const char *queryuc,
   H = (short *) calloc(ncell,sizeof(short)); dN = (signed char *) calloc(ncell,1);
   dE = (signed char *) calloc(ncell,1); dF = (signed char *) calloc(ncell,1);
   orc_fill(0,bits,rsequence,gseg,gseg_alt,rlength,glength,mt,open,extend,lband,uband,jump_late_p,0,H,dN,dE,dF);
+  if (count_only) { free(H); free(dN); free(dE); free(dF); return -1; }
   traceback_full(&l,&t,dN,dE,dF,glength+1,rlength,glength);
   free(H); free(dN); free(dE); free(dF);
   iout[1] = t.score; iout[2] = t.nmatches; iout[3] = t.nmismatches; iout[4] = t.nopens; iout[5] = t.nindels;
@@ -605,9 +617,14 @@ int orc_end_gap (int end5p, int *iout, const char *queryseq, const char *queryuc
     int wide = (endalign != ORC_QUERYEND_INDELS);
     orc_compute_bands(&lband,&uband,rlength,glength,extraband_end,wide);
     bits = (rlength < use8p[ORC_ENDQ] || glength < use8p[ORC_ENDQ]) ? 8 : 16;
+    const long cells_before = cells_filled;
     ul_alloc(&m,rlength,glength); have_m = 1;
     orc_fill(1,bits,rs_fwd,gs_fwd,ga_fwd,rlength,glength,ORC_ENDQ,open,extend,lband,uband,late,end5p,m.Hu,m.dNu,m.dEu,NULL);
     orc_fill(2,bits,rs_fwd,gs_fwd,ga_fwd,rlength,glength,ORC_ENDQ,open,extend,lband,uband,late,end5p,m.Hl,m.dNl,m.dEl,NULL);
+    /* require_pos_score_p: the reference runs these fills and then throws the result away (dynprog_end.c:1558-1574);
+       SURVEY.md section 8d counts such calls with zero cells */
+    if (require_pos_score_p) cells_filled = cells_before;
+    if (count_only) { ul_free(&m); return -1; }
     best_endpoint(&finalscore,&bestr,&bestc,&m,rlength,glength,lband,uband,late,!wide,bits == 8 ? -128 : -32768);
   } else {
     bestr = bestc = (glength < rlength) ? glength : rlength;	/* dynprog_end.c:577 */
@@ -780,6 +797,7 @@ int orc_genome_gap (int *iout, double *dout, const char *queryseq, const char *q
     ul_alloc(&R,rlength,glengthR);
     orc_fill(1,bits,rsequence,gsegR,gsegR_alt,rlength,glengthR,mt,open,extend,lbandR,ubandR,!jump_late_p,1,R.Hu,R.dNu,R.dEu,NULL);
     orc_fill(2,bits,rsequence,gsegR,gsegR_alt,rlength,glengthR,mt,open,extend,lbandR,ubandR,!jump_late_p,1,R.Hl,R.dNl,R.dEl,NULL);
+    if (count_only) { ul_free(&L); ul_free(&R); free(leftdi); free(rightdi); return -1; }
 
     /* bridge_intron_gap_{8,16}_site_level, dynprog_genome.c:866/1742 */
     for (cL = 0; cL < glengthL - 1; cL++) leftdi[cL] = left_dinucl(gsegL[cL],gsegL_alt[cL],gsegL[cL+1],gsegL_alt[cL+1]);
@@ -924,6 +942,7 @@ int orc_cdna_gap (int *iout, const char *queryseq, const char *queryuc,
     orc_fill(1,bits,rR_fwd,rev_gseg,rev_gseg_alt,rlengthR,glength,mt,open,extend,lbandR,ubandR,!jump_late_p,1,R.Hu,R.dNu,R.dEu,NULL);
     orc_fill(2,bits,rR_fwd,rev_gseg,rev_gseg_alt,rlengthR,glength,mt,open,extend,lbandR,ubandR,!jump_late_p,1,R.Hl,R.dNl,R.dEl,NULL);
   }
+  if (count_only) { ul_free(&L); ul_free(&R); return -1; }
 
   /* bridge_cdna_gap_{8,16}_ud, dynprog_cdna.c:123/387 */
   bestscore = NEG;

@@ -48,6 +48,11 @@ int orc_fill (int kind, int bits, const char *rseq, const char *gseq, const char
 
 /* Algorithmic in-band cells of one fill. */
 long orc_cells (int kind, int rlength, int glength, int lband, int uband);
+/* cells of the fills run by the entry points since the last reset; count-only mode: the entry points count and return -1
+   without filling (used by bench.py's CPU arms, which must not count their work with the product library) */
+void orc_cells_reset (void);
+long orc_cells_filled (void);
+void orc_set_count_only (int on);
 
 /* The five entry points.  Genomic segments are passed as the char arrays the reference fetches
  * with Genome_get_segment_right/left (always in ascending memory order; "rev" users read them from

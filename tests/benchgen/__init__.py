@@ -26,9 +26,11 @@ def build(force=False):
     src = os.path.join(HERE, "benchgen.cpp")
     lib = os.path.join(ROOT, "gmap_2024_b200", "csrc", "libgmapdp_b200.so")
     if force or not os.path.exists(SO) or os.path.getmtime(src) > os.path.getmtime(SO) or os.path.getmtime(lib) > os.path.getmtime(SO):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO, src,
+        tmp = "%s.%d.tmp" % (SO, os.getpid())           # atomic: several processes may find the library stale at once
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", tmp, src,
                                "-L" + os.path.dirname(lib), "-lgmapdp_b200",
                                "-Wl,-rpath,$ORIGIN/../../gmap_2024_b200/csrc"])
+        os.replace(tmp, SO)
     return SO
 
 

@@ -51,8 +51,8 @@ def build_oracle():
     return so
 
 
-def ref_available():
-    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "ref_driver.so"))
+def ref_available(noflush=False):
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "ref_driver_noflush.so" if noflush else "ref_driver.so"))
 
 
 class Oracle:
@@ -65,6 +65,18 @@ class Oracle:
     def set_user_dynprog(self, user_open, user_extend, enabled=True):
         """--indel-open / --indel-extend"""
         self.lib.orc_set_user_dynprog(int(user_open), int(user_extend), int(bool(enabled)))
+
+    def count_cells(self, box):
+        """algorithmic in-band cells of the fills this call would run (0 if an entry-point shortcut resolves it):
+        the entry point's own control flow up to the fills, nothing filled"""
+        self.lib.orc_cells_filled.restype = C.c_long
+        self.lib.orc_cells_reset()
+        self.lib.orc_set_count_only(1)
+        try:
+            self.run(box)
+        finally:
+            self.lib.orc_set_count_only(0)
+        return self.lib.orc_cells_filled()
 
     # ---- tables / fills ----------------------------------------------------------------------
     def pairdistance(self, mt, a, b):
@@ -143,8 +155,9 @@ class Ref:
     """The compiled reference.  A *world* is one in-memory genome (one chromosome occupying
     [chroffset, chrhigh) of it); boxes carry world coordinates under box['world']."""
 
-    def __init__(self, maxlookback=1940, extraquerygap=20, maxpeelback=60, extramaterial_end=10, extramaterial_paired=8):
-        self.lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "ref_driver.so"))
+    def __init__(self, maxlookback=1940, extraquerygap=20, maxpeelback=60, extramaterial_end=10, extramaterial_paired=8, noflush=False):
+        # noflush: the same sources with dynprog_simd.c's per-column _mm_clflush defined away (oracle/refbuild/noflush.h)
+        self.lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "ref_driver_noflush.so" if noflush else "ref_driver.so"))
         self.lib.refdrv_init(maxlookback, extraquerygap, maxpeelback, extramaterial_end, extramaterial_paired)
         self.lib.refdrv_genome_new.restype = C.c_void_p
         self.lib.refdrv_maxent.restype = C.c_double

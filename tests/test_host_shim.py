@@ -133,3 +133,20 @@ def test_user_penalties_reach_the_box(lib):
             assert (x.open, x.extend) == (-12, -4)
     assert seen == {0, 1, 2, 3, 4}
     b.free()
+
+
+def test_cell_counts_of_shim_and_oracle_agree(lib):
+    """the product's cell counter (GCUPS numerator of bench.py) against the oracle's independent count"""
+    from gmap_2024_b200.engine import Batch
+    o = Oracle()
+    boxes = dpgen.synth_boxes(seed=12, n=1200, rmin=2, rmax=300)
+    b = Batch(_NoDevice(lib), 2000, 2030)
+    total = 0
+    for x in boxes:
+        before = b.cells()
+        b.add(x)
+        mine = b.cells() - before
+        assert mine == o.count_cells(x), x["mode"]
+        total += mine
+    assert total > 1000000
+    b.free()

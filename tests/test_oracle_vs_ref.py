@@ -103,3 +103,19 @@ def test_entry_points_user_dynprog(pair, user_open, user_extend):
     finally:
         o.set_user_dynprog(0, 0, False)
         r.set_user_dynprog(0, 0, False)
+
+
+def test_noflush_variant_gives_the_same_results(pair):
+    """the fairness build (per-column _mm_clflush of dynprog_simd.c defined away) is the same program"""
+    import subprocess, sys, os, json
+    from harness import ref_available
+    if not ref_available(noflush=True):
+        pytest.skip("oracle/_ref/ref_driver_noflush.so not built")
+    # the two builds export the same symbols: run the variant in its own process
+    code = ("import sys, json; sys.path.insert(0, %r); import dpgen; from harness import Ref; r = Ref(noflush=True); "
+            "boxes, _ = dpgen.ref_boxes(r, 17, 150); print(json.dumps([repr(r.run(b)) for b in boxes]))") % os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, check=True).stdout
+    got = json.loads(out)
+    o, r = pair
+    boxes, _ = dpgen.ref_boxes(r, 17, 150)
+    assert got == [repr(r.run(b)) for b in boxes]
