@@ -79,6 +79,9 @@ def decorate_query(rng, q):
 ERR_LEVELS = [(0.0, 0.001), (0.001, 0.001), (0.01, 0.01), (0.05, 0.05), (0.15, 0.15)]
 
 
+CDNA_GRANGE = None      # (lo, hi): overrides the genomic length of cdna boxes
+
+
 def gen_spec(rng, mode=None, rmin=15, rmax=150, large=False):
     """Returns a spec: everything about a box except the fetched segments."""
     mode = mode or rng.choice(["single", "genome", "cdna", "end5", "end3"])
@@ -159,6 +162,8 @@ def gen_spec(rng, mode=None, rmin=15, rmax=150, large=False):
         # the cDNA bridge is O(g^2 band^2) on the CPU (dynprog_cdna.c:149-375): keep g small
         glo = min(max(4, rmin // 2), 100)
         g = rng.randrange(glo, max(glo + 1, min(rmax, 140)))
+        if CDNA_GRANGE is not None:     # long cDNA gaps: production allows rL = rR = g + 8 <= 660 (dynprog_cdna.c:869-892, stage3.c:9276)
+            g = rng.randrange(CDNA_GRANGE[0], CDNA_GRANGE[1] + 1)
         core = rand_dna(rng, g)
         k = rng.randrange(1, g)
         ins = rand_dna(rng, rng.randrange(10, 40), 0)

@@ -72,3 +72,29 @@ def test_device_counts_match_host_replay(engine):
     b.run()                                  # raises EngineError on a count mismatch
     assert b.nboxes() > 2000
     b.free()
+
+
+def test_benchmark_100k_boxes_bit_exact_vs_oracle(engine):
+    """BASELINE config 2 says "bit-exact score and traceback check": the first 40 000 - 100 000 boxes of the benchmark's own
+    generator and seed (what bench.py times), every out-parameter and every pair record, against the oracle run on all
+    host cores (digests cross the process boundary, the comparison is of the full results)."""
+    import os
+    import parallel_oracle
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n = min(100000, 2500 * cores)            # ~90 s of oracle time whatever the box has: 40 000 boxes on 16 cores, 80 000 on 32
+    seed = 20241018
+    b = engine.batch()
+    ids, modes = [], []
+    box = benchgen.Box()
+    lib = benchgen.lib()
+    import ctypes as C
+    for i in range(n):
+        lib.benchgen_make(C.c_uint64(seed), C.c_long(i), C.byref(box), 0)
+        ids.append(lib.benchgen_add(b.h, C.byref(box)))
+        modes.append(benchgen.MODES[box.mode])
+    b.run()
+    got = parallel_oracle.gpu_digests(b, ids, modes)
+    b.free()
+    want = parallel_oracle.bench_digests(seed, n)
+    bad = [i for i in range(n) if got[i] != want[i]]
+    assert not bad, "%d of %d benchmark boxes differ from the oracle; first: box %d (%s)" % (len(bad), n, bad[0], modes[bad[0]])

@@ -173,3 +173,42 @@ def test_resident_run_refused_after_chunked_run(engine):
         b.free()
     finally:
         eng.close()
+
+
+def test_long_cdna_gaps(engine):
+    """cDNA gaps up to the production limit rL = rR = g + 8 <= 660 (dynprog_cdna.c:869-892, stage3.c:9276): the device
+    bridge is a re-derivation (prefix-best tables, O(g band)) of the reference's O(g^2 band^2) scan, so it is checked
+    where the two could drift apart -- long segments, many columns, ties between columns far apart.  The oracle runs
+    the quartic scan; all host cores share the work."""
+    import parallel_oracle
+    sets = [("synth", 501, 160, (200, 652)), ("lowcomplexity", 502, 60, (200, 652)), ("synth", 503, 24, (640, 652))]
+    for kind, seed, n, grange in sets:
+        dpgen.CDNA_GRANGE = grange
+        try:
+            boxes = dpgen.lowcomplexity_boxes(seed, n, "cdna", 15, 150) if kind == "lowcomplexity" else dpgen.synth_boxes(seed, n, "cdna", 15, 150)
+        finally:
+            dpgen.CDNA_GRANGE = None
+        assert all(grange[0] <= b["glength"] <= grange[1] for b in boxes)
+        want = parallel_oracle.dpgen_digests(kind, seed, n, "cdna", 15, 150, grange)
+        batch = engine.batch()
+        ids = [batch.add(b) for b in boxes]
+        batch.run()
+        got = parallel_oracle.gpu_digests(batch, ids, [b["mode"] for b in boxes])
+        batch.free()
+        bad = [k for k in range(n) if got[k] != want[k]]
+        assert not bad, "%s seed %d: %d of %d long cdna boxes differ, first glength %d" % (kind, seed, len(bad), n, boxes[bad[0]]["glength"])
+
+
+def test_genome_gaps_with_real_maxent(engine, oracle):
+    """splice-site probabilities from the reference's own MaxEnt model (oracle/_ref, where it travelled) instead of the
+    synthetic arrays: real probability landscapes decide the bridge's tie-breaks and the 0.85 / 0.90 thresholds"""
+    from harness import Ref, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref not present on this machine")
+    ref = Ref()
+    boxes = []
+    for seed in (41, 42, 43):
+        bx, _ = dpgen.ref_boxes(ref, seed, 250, mode="genome", rmin=20, rmax=400)
+        boxes += bx
+    run_and_compare(engine, oracle, boxes, "genome gaps, real MaxEnt")
+    assert any(max(b["left_probs"]) > 0.9 for b in boxes)
