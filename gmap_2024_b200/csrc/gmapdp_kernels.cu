@@ -1607,7 +1607,8 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   }
   CK(cudaStreamCreateWithFlags(&ctx->stream,cudaStreamNonBlocking));
   ctx->kstream[0] = ctx->stream;
-  for (int k = 1; k < GDP_NK; k++) CK(cudaStreamCreateWithFlags(&ctx->kstream[k],cudaStreamNonBlocking));
+  /* kstream[1..3] (one stream per kernel kind, GMAPDP_STREAMS=1) are created when first asked for: every stream takes a
+     hardware queue, and the drop-in runs a dozen contexts per device */
   for (int k = 0; k < GDP_NK; k++) {
     CK(cudaEventCreateWithFlags(&ctx->evj[k],cudaEventDisableTiming));
     CK(cudaEventCreate(&ctx->evk[k][0])); CK(cudaEventCreate(&ctx->evk[k][1]));
@@ -1646,7 +1647,7 @@ extern "C" void gmapdp_destroy (gmapdp_ctx *ctx) {
   for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (int k = 0; k < GDP_NK; k++) {
-    if (k > 0 && ctx->kstream[k]) cudaStreamDestroy(ctx->kstream[k]);
+    if (k > 0 && ctx->kstream[k] && ctx->kstream[k] != ctx->stream) cudaStreamDestroy(ctx->kstream[k]);
     if (ctx->evj[k]) cudaEventDestroy(ctx->evj[k]);
     if (ctx->evk[k][0]) cudaEventDestroy(ctx->evk[k][0]);
     if (ctx->evk[k][1]) cudaEventDestroy(ctx->evk[k][1]);
@@ -1874,7 +1875,12 @@ static int launch_chunk (gmapdp_ctx *ctx, int first, const int *cnt, bool timed 
 
 /* fork: the other kernel streams start after an event on `stream' */
 static int fork_streams (gmapdp_ctx *ctx, cudaEvent_t ev) {
-  for (int k = 1; k < GDP_NK; k++) CK(cudaStreamWaitEvent(ctx->kstream[k],ev,0));
+  static const bool use_streams = getenv("GMAPDP_STREAMS") != NULL;
+  for (int k = 1; k < GDP_NK; k++) {
+    if (!use_streams) { ctx->kstream[k] = ctx->stream; continue; }		/* everything on the one stream */
+    if (ctx->kstream[k] == 0 || ctx->kstream[k] == ctx->stream) CK(cudaStreamCreateWithFlags(&ctx->kstream[k],cudaStreamNonBlocking));
+    CK(cudaStreamWaitEvent(ctx->kstream[k],ev,0));
+  }
   return GMAPDP_OK;
 }
 extern "C" int gmapdp_upload (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes,
@@ -2119,7 +2125,7 @@ int gdp_flight_launch (GdpFlight *f, int n, size_t poolbytes, size_t script_need
   }
   if (!ctx->dev_set) { FCK(cudaSetDevice(ctx->device)); ctx->dev_set = true; }	/* the launcher thread serves one device */
   f->n = n; f->script_need = script_need;
-  cudaStream_t s0 = ctx->stream;
+  cudaStream_t s0 = ctx->stream;		/* the flights of a lane run one after the other on its stream and share its workspace */
   const size_t wsw = (ws_words + 31) & ~(size_t) 31;
   const int cols = (maxcols + 7) & ~7;
   const size_t smem = (size_t) WARPS_PER_BLOCK * cols * 8;
@@ -2131,7 +2137,8 @@ int gdp_flight_launch (GdpFlight *f, int n, size_t poolbytes, size_t script_need
   }
   const int full = ctx->sm_count * ctx->any_occ;
   const int grid = std::max(1,std::min(full,(n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
-  /* the workspace is sized for a full grid, so that it stops growing after the first large boxes */
+  /* the workspace is sized for a full grid, so that it stops growing after the first large boxes (grown geometrically,
+     the outgrown buffer parked: the previous flight may still be using it) */
   if (grow(ctx,&ctx->d_kws[0],&ctx->cap_kws[0],(size_t) full * WARPS_PER_BLOCK * wsw)) return GMAPDP_ERR_CUDA;
   if (f->timed) FCK(cudaEventRecord((cudaEvent_t) f->ev_start,s0));
   FCK(cudaMemcpyAsync(f->d_in,f->h_in,flight_in_bytes(n),cudaMemcpyHostToDevice,s0));

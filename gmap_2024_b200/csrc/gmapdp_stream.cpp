@@ -1,6 +1,16 @@
 /* gmapdp_stream.cpp -- the batching runtime (include/gmapdp_stream.h): host threads submit single DP boxes,
  * flights carry them to the device.  Plain C++ and pthreads; everything CUDA is behind the GdpFlight functions
- * of gmapdp_kernels.cu (gmapdp_internal.h).  No DP cell is computed here. */
+ * of gmapdp_kernels.cu (gmapdp_internal.h).  No DP cell is computed here.
+ *
+ * Life of a flight, all of it inside its lane's service thread:
+ *   open      submitters reserve a slot under the lane mutex and copy their box, sequences and probabilities into the
+ *             pinned staging outside it
+ *   out       closed, ordered, launched (two H2D copies, one kernel, one D2H copy, one event) on the lane's stream
+ *   landed    the event has fired: every box's result and edit script is copied into its owner's MAILBOX, the owners
+ *             are woken (as a tree), and the flight goes back to the free list at once
+ * A flight never waits for a worker thread: with hundreds of workers on a few cores the slowest owner of a flight can
+ * be a scheduling quantum late, and a flight held until then was what starved the submitters of open flights.
+ */
 #include "../../include/gmapdp_stream.h"
 #include "gmapdp_internal.h"
 
@@ -31,8 +41,16 @@ double now_s () {
 inline size_t align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
 long env_long (const char *name, long dflt) { const char *e = getenv(name); return (e && *e) ? atol(e) : dflt; }
 
+inline std::atomic<int> *state_of (gmapdp_mailbox *mb) { return reinterpret_cast<std::atomic<int> *>(&mb->state); }
+
 void futex_wait (std::atomic<int> *w, int expected) {
   syscall(SYS_futex,reinterpret_cast<int *>(w),FUTEX_WAIT_PRIVATE,expected,NULL,NULL,0);
+}
+
+/* tells a mailbox's owner that its box is back (state 1) or lost (state 2) */
+void wake_mailbox (gmapdp_mailbox *mb, int state) {
+  state_of(mb)->store(state,std::memory_order_release);
+  syscall(SYS_futex,&mb->state,FUTEX_WAKE_PRIVATE,1,NULL,NULL,0);
 }
 
 struct Lane;
@@ -44,39 +62,32 @@ struct Flight {
   int n = 0; bool full = false;
   size_t pool_used = 0, script_need = 0, ws_words = 0;
   int maxcols = 8;
-  std::vector<int> bucket;		/* per box: launch-order key */
-  std::vector<double> t_submit;
-  std::atomic<int> writers{0};		/* submitters still copying into the staging */
-  /* completion */
-  std::atomic<int> done{0};		/* 0 in progress, 1 results ready, 2 failed */
-  std::atomic<int> *woken = NULL;	/* per box: futex word its owner sleeps on (0 asleep / not yet told, 1 told) */
-  std::atomic<int> readers{0};		/* boxes not yet released by their owners */
+  std::vector<int> bucket;			/* per box: launch-order key */
+  std::vector<gmapdp_mailbox *> owner;		/* per box: where its result goes */
+  std::atomic<int> writers{0};			/* submitters still copying into the staging */
   int rc = 0;
-  const gmapdp_result *results = NULL; const uint32_t *script = NULL;
   double t_first = 0.0, t_close = 0.0, t_launch = 0.0, t_launched = 0.0, t_started = 0.0;
-  void reset () {
-    n = 0; full = false; pool_used = script_need = ws_words = 0; maxcols = 8;
-    done.store(0,std::memory_order_relaxed); rc = 0; results = NULL; script = NULL;
-  }
+  void reset () { n = 0; full = false; pool_used = script_need = ws_words = 0; maxcols = 8; rc = 0; }
 };
 
 struct Lane {
   gmapdp_stream *owner = NULL;
   gmapdp_ctx *ctx = NULL;
-  int device = 0, depth = 2;
+  int device = 0, depth = 2, max_flights = 6;
   pthread_mutex_t mu;
   pthread_cond_t cv_work, cv_open;
   Flight *open = NULL;
   std::deque<Flight *> free_list;
   std::vector<Flight *> all;
-  int inflight = 0;
   bool stop = false, failed = false;
   pthread_t service;
   bool threads_started = false;
   long spin_us = 400;
+  double ema_flight = 150e-6;			/* running estimate of launch -> landed */
   /* statistics, under mu */
   double boxes = 0, flights = 0, largest = 0, t_flight = 0, t_wait = 0, h2d = 0, d2h = 0, gpu_s = 0, copy_s = 0;
-  double t_stage[5] = {0,0,0,0,0};	/* close -> launch call, launch call, launch returned -> completion seen, root wake-ups */
+  double t_stage[5] = {0,0,0,0,0};	/* close -> launch call, launch call, launch returned -> landed, distribution + root wake-ups, launch returned -> begun */
+  long launches = 0;
   std::string err;
 };
 
@@ -97,12 +108,8 @@ namespace {
 
 thread_local std::string tls_err;	/* errors of the per-call functions are per thread (hundreds of threads share one stream) */
 const int WAKE_ROOTS = 2;
-void wake_box (Flight *F, int i) {
-  F->woken[i].store(1,std::memory_order_release);
-  syscall(SYS_futex,reinterpret_cast<int *>(&F->woken[i]),FUTEX_WAKE_PRIVATE,1,NULL,NULL,0);
-}
 
-/* kind by kind, each kind by decreasing work: counting sort over the boxes' bucket keys (stable) */
+/* longest boxes first: counting sort over the boxes' bucket keys (stable) */
 void build_order (Flight *F, std::vector<int> &count) {
   const int nb = gdp_bucket_count();
   count.assign((size_t) nb + 1,0);
@@ -112,98 +119,125 @@ void build_order (Flight *F, std::vector<int> &count) {
   for (int i = 0; i < F->n; i++) order[count[F->bucket[i]]++] = i;
 }
 
-/* The launcher and the completer of a lane are latency-critical and almost always asleep, while hundreds of worker
-   threads compete for the cores.  Linux's EEVDF scheduler (6.6+) lets a thread ask for a short time slice: it is then
-   picked -- and, from 6.12, preempts -- ahead of threads with the default 3 ms slice.  Unprivileged; ignored by older
-   kernels.  GMAPDP_STREAM_RT=1 asks for SCHED_FIFO instead (needs CAP_SYS_NICE). */
+/* The service thread of a lane is latency-critical, while hundreds of worker threads compete for the cores.  Linux's
+   EEVDF scheduler (6.6+) lets a thread ask for a short time slice: it is then picked -- and, from 6.12, preempts --
+   ahead of threads with the default 3 ms slice.  Unprivileged; ignored by older kernels. */
 struct sched_attr_v1 {
   uint32_t size, sched_policy; uint64_t sched_flags; int32_t sched_nice; uint32_t sched_priority;
   uint64_t sched_runtime, sched_deadline, sched_period; uint32_t sched_util_min, sched_util_max;
 };
-std::atomic<int> sched_mode{0};		/* what the service threads got: 1 SCHED_FIFO, 2 short slices, 3 nothing */
+std::atomic<int> sched_mode{0};		/* what the service threads got: 2 short slices, 3 nothing */
 void service_thread_priority () {
-  static const bool rt = getenv("GMAPDP_STREAM_RT") != NULL;
   sched_attr_v1 a;
   memset(&a,0,sizeof(a));
   a.size = sizeof(a);
-  if (rt) {
-    a.sched_policy = 1 /* SCHED_FIFO */; a.sched_priority = 10;
-    if (syscall(SYS_sched_setattr,0,&a,0) == 0) { sched_mode.store(1); return; }
-    memset(&a,0,sizeof(a)); a.size = sizeof(a);
-  }
   a.sched_policy = 0 /* SCHED_OTHER */; a.sched_runtime = 100 * 1000;	/* 100 us slices */
   sched_mode.store(syscall(SYS_sched_setattr,0,&a,0) == 0 ? 2 : 3);
 }
 
-/* One service thread per lane: launcher and completer in one loop, so that no hand-over between threads sits in a
-   flight's critical path.  While a flight is out the thread polls its event (and keeps launching the next flight as
-   soon as the rules below allow); only when the lane is idle does it sleep on the condition variable.
+Flight *new_flight (Lane *L) {		/* lane mutex held, or the lane not yet shared */
+  gmapdp_stream *s = L->owner;
+  Flight *F = new Flight();
+  F->lane = L;
+  if (gdp_flight_create(L->ctx,&F->dev,s->max_boxes,s->pool_cap,s->script_cap) != GMAPDP_OK) {
+    if (F->dev) gdp_flight_destroy(F->dev);
+    delete F;
+    return NULL;
+  }
+  F->bucket.resize(s->max_boxes); F->owner.resize(s->max_boxes);
+  F->reset();
+  L->all.push_back(F);
+  return F;
+}
 
-   When to close the open flight and launch it:
-     - nothing is in flight: at once, with whatever it holds (latency);
-     - otherwise (at most `depth' flights in flight): when it has grown to `fill_boxes' boxes, or its first box has waited
-       `linger_us' -- the boxes that arrive while a flight is out would otherwise leave one by one.  */
-void complete_flight (Lane *L, Flight *F, int rc) {
-  if (rc == GMAPDP_OK) rc = gdp_flight_wait(F->dev);		/* the event has fired (or the poll gave up): returns at once, reads the timings */
-  if (rc == GMAPDP_OK) rc = gdp_flight_results(F->dev,&F->results,&F->script);
-  F->rc = rc;
+/* the flight's event has fired (or its launch failed): results into the mailboxes, owners woken, flight recycled */
+void land_flight (Lane *L, Flight *F, int rc) {
+  const gmapdp_result *results = NULL; const uint32_t *script = NULL;
+  if (rc == GMAPDP_OK) rc = gdp_flight_wait(F->dev);		/* returns at once; reads the device timings */
+  if (rc == GMAPDP_OK) rc = gdp_flight_results(F->dev,&results,&script);
   const double t1 = now_s();
-  /* everything this thread still needs from the flight is read NOW: once its last owner has been told, the flight
-     can be released, reopened and refilled before this thread runs again */
   const int n = F->n;
   double waited = 0.0;
-  for (int i = 0; i < n; i++) waited += t1 - F->t_submit[i];
-  const double st0 = F->t_launch - F->t_close, st1 = F->t_launched - F->t_launch, st2 = t1 - F->t_launched, t_launch = F->t_launch;
-  const double gpu_s = 1e-3 * F->dev->gpu_ms, copy_s = 1e-3 * F->dev->copy_ms;
-  const double st4 = (F->t_started > 0.0) ? F->t_started - F->t_launched : 0.0;
   if (rc != GMAPDP_OK) {
     pthread_mutex_lock(&L->mu);
     L->failed = true; L->err = gmapdp_last_error(L->ctx);
     pthread_mutex_unlock(&L->mu);
   }
-  F->done.store(rc == GMAPDP_OK ? 1 : 2,std::memory_order_release);
-  /* Wake-ups fan out as a tree: this thread tells the first WAKE_ROOTS boxes' owners, every owner tells two more before
-     it goes on (box i -> boxes WAKE_ROOTS + 2i and WAKE_ROOTS + 2i + 1).  Waking a sleeping thread costs a few microseconds of
-     kernel time in the waker; hundreds of them from this one thread would serialise the whole runtime. */
-  if (n > 1) wake_box(F,1);		/* box 0's owner last: with n == 1 it is the one that can release the flight */
-  wake_box(F,0);
+  /* Wake-ups fan out as a tree: this thread wakes the owners of boxes 0 and 1, the owner of box i wakes those of boxes
+     2 + 2i and 3 + 2i before it goes on.  Waking a sleeping thread costs a few microseconds of kernel time in the waker:
+     hundreds of them from this one thread would serialise the whole runtime.  The tree hangs off the mailboxes, not
+     off the flight, which is free again as soon as this function returns. */
+  for (int i = 0; i < n; i++) {
+    gmapdp_mailbox *mb = F->owner[i];
+    waited += t1 - mb->t_submit;
+    mb->rc = rc;
+    if (rc == GMAPDP_OK) {
+      const gmapdp_result &r = results[i];
+      const size_t len = (size_t) r.script_lenA + (size_t) r.script_lenB;
+      if (r.script_off < 0 || (size_t) r.script_off + len > F->script_need || len > mb->ops_cap) mb->rc = GMAPDP_ERR_CAPACITY;
+      else { mb->result = r; mb->result.script_off = 0; memcpy(mb->ops,script + r.script_off,len * sizeof(uint32_t)); }
+    }
+    const int c = WAKE_ROOTS + 2 * i;
+    mb->wake[0] = (c < n) ? F->owner[c] : NULL;
+    mb->wake[1] = (c + 1 < n) ? F->owner[c + 1] : NULL;
+  }
+  for (int i = 0; i < WAKE_ROOTS && i < n; i++) wake_mailbox(F->owner[i],rc == GMAPDP_OK ? 1 : 2);
   const double t2 = now_s();
+  const double st4 = (F->t_started > 0.0) ? F->t_started - F->t_launched : 0.0;
   pthread_mutex_lock(&L->mu);
-  L->inflight--;
-  L->t_flight += t1 - t_launch; L->t_wait += waited;
-  L->t_stage[0] += st0; L->t_stage[1] += st1; L->t_stage[2] += st2; L->t_stage[3] += t2 - t1; L->t_stage[4] += st4;
-  L->gpu_s += gpu_s; L->copy_s += copy_s;
+  L->t_flight += t1 - F->t_launch; L->t_wait += waited;
+  L->t_stage[0] += F->t_launch - F->t_close; L->t_stage[1] += F->t_launched - F->t_launch; L->t_stage[2] += t1 - F->t_launched;
+  L->t_stage[3] += t2 - t1; L->t_stage[4] += st4;
+  L->gpu_s += 1e-3 * F->dev->gpu_ms; L->copy_s += 1e-3 * F->dev->copy_ms;
+  L->ema_flight = 0.9 * L->ema_flight + 0.1 * (t1 - F->t_launched);
+  F->reset();
+  if (L->open == NULL) { L->open = F; pthread_cond_broadcast(&L->cv_open); }
+  else L->free_list.push_back(F);
   pthread_mutex_unlock(&L->mu);
 }
 
+/* One service thread per lane: launcher and completer in one loop, so that no hand-over between threads sits in a
+   flight's critical path.  While a flight is out the thread polls its event (and launches the next flight when the
+   rules below say so); only when the lane is idle does it sleep on the condition variable.
+
+   The flights of a lane run one after the other on the lane's stream.  When to close the open flight and launch it:
+     - nothing is out: at once, with whatever it holds (latency);
+     - one flight is out: when the open one has grown to `fill_boxes' boxes, or when the flight that is out is
+       expected back within a fraction of its usual duration -- the next flight is then queued behind it in time and
+       carries everything that arrived meanwhile (throughput; the duration is a running average);
+     - `depth' flights are out: never.  */
 void *service_main (void *arg) {
   Lane *L = (Lane *) arg;
   service_thread_priority();
   std::vector<int> count;
-  std::deque<Flight *> out;		/* launched, oldest first (this thread only) */
-  const double linger = 1e-6 * (double) env_long("GMAPDP_STREAM_LINGER_US",40);
-  const int fill_boxes = (int) env_long("GMAPDP_STREAM_FILL",64);
+  std::vector<Flight *> out;		/* launched and not yet landed, oldest first (this thread only) */
+  const double linger_frac = 1e-2 * (double) env_long("GMAPDP_STREAM_LINGER_PCT",60);
+  const int fill_boxes = (int) env_long("GMAPDP_STREAM_FILL",512);
   pthread_mutex_lock(&L->mu);
   for (;;) {
     if (L->stop && out.empty()) break;
     Flight *F = L->open;
     bool go = false;
     if (F && F->n > 0 && (int) out.size() < L->depth && !L->stop) {
-      go = out.empty() || F->full || F->n >= fill_boxes || now_s() - F->t_first >= linger;
+      go = out.empty() || F->full || F->n >= fill_boxes || now_s() - out.back()->t_launched >= linger_frac * L->ema_flight;
     }
     if (go) {
       L->open = NULL;
+      if (L->free_list.empty() && (int) L->all.size() < L->max_flights) {
+	/* flights are created on demand (pinned staging is slow to allocate: a run that needs three never pays for more) */
+	Flight *N = new_flight(L);
+	if (N) L->free_list.push_back(N);
+      }
       if (!L->free_list.empty()) { L->open = L->free_list.front(); L->free_list.pop_front(); pthread_cond_broadcast(&L->cv_open); }
-      L->inflight++;
       L->boxes += F->n; L->flights += 1; if (F->n > L->largest) L->largest = F->n;
       L->h2d += 32.0 + (double) F->n * (sizeof(gmapdp_box) + sizeof(int)) + (double) F->pool_used;
       L->d2h += 64.0 * F->n + 4.0 * (double) F->script_need;
+      L->launches++;
       pthread_mutex_unlock(&L->mu);
       F->t_close = now_s();
       while (F->writers.load(std::memory_order_acquire) != 0) sched_yield();	/* submitters finishing their copies */
       build_order(F,count);
       F->t_launch = now_s();
-      F->readers.store(F->n,std::memory_order_relaxed);
       F->rc = gdp_flight_launch(F->dev,F->n,F->pool_used,F->script_need,F->ws_words,F->maxcols);
       F->t_launched = now_s(); F->t_started = 0.0;
       out.push_back(F);
@@ -211,14 +245,16 @@ void *service_main (void *arg) {
       continue;
     }
     if (!out.empty()) {
-      /* something is out: poll it; the lock is dropped, submitters are never held up by this loop */
+      /* something is out: poll the oldest (one stream: they land in order); the lock is dropped, submitters are never
+	 held up by this loop */
       pthread_mutex_unlock(&L->mu);
       Flight *O = out.front();
-      if (O->t_started == 0.0 && O->rc == GMAPDP_OK && gdp_flight_started(O->dev)) O->t_started = now_s();
-      int p = (O->rc == GMAPDP_OK) ? gdp_flight_poll(O->dev) : 1;
-      if (p != 0) { out.pop_front(); complete_flight(L,O,p < 0 ? p : O->rc); }
-      else if (now_s() - O->t_launched > 1e-6 * (double) L->spin_us) {
-	/* a long flight (a large box): stop burning the core, look again every 50 us (GMAPDP_STREAM_SPIN_US, default 400) */
+      const double t_now = now_s();
+      if (O->t_started == 0.0 && O->rc == GMAPDP_OK && gdp_flight_started(O->dev)) O->t_started = t_now;
+      const int p = (O->rc == GMAPDP_OK) ? gdp_flight_poll(O->dev) : 1;
+      if (p != 0) { out.erase(out.begin()); land_flight(L,O,p < 0 ? p : O->rc); }
+      else if (t_now - O->t_launched > 1e-6 * (double) L->spin_us) {
+	/* a long flight (a large box): stop burning the core, look again every 50 us (GMAPDP_STREAM_SPIN_US) */
 	struct timespec ts = {0, 50000};
 	nanosleep(&ts,NULL);
       }
@@ -241,7 +277,7 @@ void lane_destroy (Lane *L) {
     pthread_mutex_unlock(&L->mu);
     pthread_join(L->service,NULL);
   }
-  for (Flight *F : L->all) { if (F->dev) gdp_flight_destroy(F->dev); delete[] F->woken; delete F; }
+  for (Flight *F : L->all) { if (F->dev) gdp_flight_destroy(F->dev); delete F; }
   if (L->ctx) gmapdp_destroy(L->ctx);
   pthread_mutex_destroy(&L->mu);
   pthread_cond_destroy(&L->cv_work); pthread_cond_destroy(&L->cv_open);
@@ -255,13 +291,14 @@ extern "C" int gmapdp_stream_create (gmapdp_stream **out, const int *devices, in
   *out = s;
   if (ndevices <= 0 || !devices) { s->err = "gmapdp_stream_create: no device given"; return GMAPDP_ERR_ARG; }
   s->max_boxes = max_boxes > 0 ? max_boxes : (int) env_long("GMAPDP_STREAM_BOXES",2048);
-  /* capacities of a flight: a box needs at most ~10 KB of sequence and ~5.4 K script words (660 x 2000 per side) */
+  /* capacities of a flight: a box needs at most ~10 KB of sequence, ~40 KB of probabilities and ~5.4 K script words
+     (660 x 2000 per side) */
   s->pool_cap = (size_t) env_long("GMAPDP_STREAM_POOL_MB",4) << 20;		/* sequences + MaxEnt probabilities */
   s->script_cap = (size_t) env_long("GMAPDP_STREAM_SCRIPT_MB",2) << 18;	/* words */
-  const int nflights = (int) env_long("GMAPDP_STREAM_FLIGHTS",12), depth = (int) env_long("GMAPDP_STREAM_DEPTH",2);
+  const int nflights = (int) env_long("GMAPDP_STREAM_FLIGHTS",6), depth = (int) env_long("GMAPDP_STREAM_DEPTH",2);
   /* Size classes.  A flight is back when its SLOWEST box is: one warp per box, and a 660 x 990 end gap (eleven 32-diagonal
      passes of ~1000 steps) keeps its warp busy a hundred times longer than the 100 x 110 boxes that make up 95 % of the
-     calls.  So every device has one lane per class -- own context, stream, workspaces, flights -- and their kernels
+     calls.  So every device has one lane per class -- own context, stream, workspace, flights -- and their kernels
      run side by side: small boxes never wait for a large one.  GMAPDP_STREAM_CLASSES="a,b" sets the step limits. */
   {
     const char *e = getenv("GMAPDP_STREAM_CLASSES");
@@ -289,16 +326,10 @@ extern "C" int gmapdp_stream_create (gmapdp_stream **out, const int *devices, in
     pthread_cond_init(&L->cv_work,NULL); pthread_cond_init(&L->cv_open,NULL);
     int rc = gmapdp_create(&L->ctx,devices[d]);
     if (rc != GMAPDP_OK) { s->err = gmapdp_last_error(L->ctx); return rc; }
-    for (int k = 0; k < (nflights < 3 ? 3 : nflights); k++) {
-      Flight *F = new Flight();
-      L->all.push_back(F);
-      F->lane = L;
-      rc = gdp_flight_create(L->ctx,&F->dev,s->max_boxes,s->pool_cap,s->script_cap);
-      if (rc != GMAPDP_OK) { s->err = gmapdp_last_error(L->ctx); return rc; }
-      F->bucket.resize(s->max_boxes); F->t_submit.resize(s->max_boxes);
-      F->woken = new std::atomic<int>[s->max_boxes];
-      for (int i = 0; i < s->max_boxes; i++) F->woken[i].store(0,std::memory_order_relaxed);
-      F->reset();
+    L->max_flights = nflights < 3 ? 3 : nflights;
+    for (int k = 0; k < 2; k++) {
+      Flight *F = new_flight(L);
+      if (!F) { s->err = gmapdp_last_error(L->ctx); return GMAPDP_ERR_CUDA; }
       if (k == 0) L->open = F; else L->free_list.push_back(F);
     }
     L->spin_us = env_long("GMAPDP_STREAM_SPIN_US",400);
@@ -324,12 +355,13 @@ extern "C" const char *gmapdp_stream_error (const gmapdp_stream *s) {
 extern "C" int gmapdp_stream_ndevices (const gmapdp_stream *s) { return s->ndevices; }
 
 extern "C" int gmapdp_stream_submit (gmapdp_stream *s, const gmapdp_box *box, const uint8_t *seq, size_t seqbytes,
-				     const double *probs, size_t nprobs, gmapdp_ticket *ticket) {
+				     const double *probs, size_t nprobs, gmapdp_mailbox *mb) {
   GdpBoxGeom g;
   if (gdp_box_geometry(box,&g) != GMAPDP_OK) { tls_err = "bad box"; return GMAPDP_ERR_ARG; }
   /* the box's share of the flight's pool: its sequences, then (8-aligned) its probabilities */
   const size_t sb = align16(seqbytes), need = sb + nprobs * sizeof(double);
   if (need > s->pool_cap || g.script_words > s->script_cap) { tls_err = "box larger than a flight"; return GMAPDP_ERR_CAPACITY; }
+  if (!mb || !mb->ops || mb->ops_cap < g.script_words) { tls_err = "mailbox too small for the box's edit script"; return GMAPDP_ERR_ARG; }
   /* a thread stays on one device for its lifetime; the lane there follows the box's size class */
   int di = (int) (intptr_t) pthread_getspecific(s->lane_key) - 1;
   if (di < 0) {
@@ -338,8 +370,9 @@ extern "C" int gmapdp_stream_submit (gmapdp_stream *s, const gmapdp_box *box, co
   }
   int cls = 0;
   while (g.steps >= s->class_limit[cls]) cls++;
-  const int li = di * s->nclasses + cls;
-  Lane *L = s->lanes[li];
+  Lane *L = s->lanes[(size_t) di * s->nclasses + cls];
+  state_of(mb)->store(0,std::memory_order_relaxed);
+  mb->rc = 0; mb->wake[0] = mb->wake[1] = NULL;
 
   pthread_mutex_lock(&L->mu);
   Flight *F;
@@ -356,13 +389,13 @@ extern "C" int gmapdp_stream_submit (gmapdp_stream *s, const gmapdp_box *box, co
   if (g.ws_words > F->ws_words) F->ws_words = g.ws_words;
   if (g.cols > F->maxcols) F->maxcols = g.cols;
   F->bucket[idx] = g.bucket;
-  F->woken[idx].store(0,std::memory_order_relaxed);
+  F->owner[idx] = mb;
   F->writers.fetch_add(1,std::memory_order_relaxed);
   const double t_now = now_s();
   if (idx == 0) { F->t_first = t_now; pthread_cond_signal(&L->cv_work); }
   pthread_mutex_unlock(&L->mu);
 
-  F->t_submit[idx] = t_now;
+  mb->t_submit = t_now;
   gmapdp_box x = *box;
   x.qL_off += (uint32_t) sbase; x.qR_off += (uint32_t) sbase; x.gL_off += (uint32_t) sbase; x.gLalt_off += (uint32_t) sbase;
   x.gR_off += (uint32_t) sbase; x.gRalt_off += (uint32_t) sbase;
@@ -371,41 +404,23 @@ extern "C" int gmapdp_stream_submit (gmapdp_stream *s, const gmapdp_box *box, co
   if (seqbytes) memcpy(F->dev->h_pool + sbase,seq,seqbytes);
   if (nprobs) memcpy(F->dev->h_pool + sbase + sb,probs,nprobs * sizeof(double));
   F->writers.fetch_sub(1,std::memory_order_release);
-  ticket->flight = F; ticket->index = idx; ticket->lane = li;
   return GMAPDP_OK;
 }
 
-extern "C" int gmapdp_stream_wait (gmapdp_stream *s, const gmapdp_ticket *ticket, const gmapdp_result **result, const uint32_t **ops) {
-  Flight *F = (Flight *) ticket->flight;
-  const int i = ticket->index;
-  while (F->woken[i].load(std::memory_order_acquire) == 0) futex_wait(&F->woken[i],0);
-  /* pass the news on before doing anything else (see completer_main) */
-  for (int c = WAKE_ROOTS + 2 * i; c <= WAKE_ROOTS + 2 * i + 1 && c < F->n; c++) wake_box(F,c);
-  const int d = F->done.load(std::memory_order_acquire);
-  if (d == 0) { tls_err = "internal error: a box's owner was woken before its flight completed"; return GMAPDP_ERR_ARG; }
-  if (d != 1) { tls_err = "flight failed: " + F->lane->err; return F->rc ? F->rc : GMAPDP_ERR_CUDA; }
-  const gmapdp_result *r = F->results + ticket->index;
-  if (r->script_off < 0 || (size_t) r->script_off + (size_t) r->script_lenA + (size_t) r->script_lenB > F->script_need) {
-    tls_err = "device script pool overflow"; return GMAPDP_ERR_CAPACITY;
-  }
-  *result = r; *ops = F->script + r->script_off;
-  return GMAPDP_OK;
-}
-
-extern "C" void gmapdp_stream_release (gmapdp_stream *s, const gmapdp_ticket *ticket) {
+extern "C" int gmapdp_stream_wait (gmapdp_stream *s, gmapdp_mailbox *mb) {
   (void) s;
-  Flight *F = (Flight *) ticket->flight;
-  if (F->readers.fetch_sub(1,std::memory_order_acq_rel) == 1) {
-    Lane *L = F->lane;
-    pthread_mutex_lock(&L->mu);
-    F->reset();
-    if (L->open == NULL) { L->open = F; pthread_cond_broadcast(&L->cv_open); }
-    else L->free_list.push_back(F);
-    pthread_mutex_unlock(&L->mu);
+  int st;
+  while ((st = state_of(mb)->load(std::memory_order_acquire)) == 0) futex_wait(state_of(mb),0);
+  /* pass the news on before doing anything else (see land_flight) */
+  for (int k = 0; k < 2; k++) if (mb->wake[k]) { gmapdp_mailbox *c = mb->wake[k]; mb->wake[k] = NULL; wake_mailbox(c,st); }
+  if (st != 1 || mb->rc != GMAPDP_OK) {
+    tls_err = (mb->rc == GMAPDP_ERR_CAPACITY) ? "device script pool overflow" : "flight failed (CUDA error on its lane)";
+    return mb->rc ? mb->rc : GMAPDP_ERR_CUDA;
   }
+  return GMAPDP_OK;
 }
 
-/* per lane: boxes, flights, largest flight, mean flight latency (us), mean device time (us, GMAPDP_STREAM_TIMING), mean upload time (us) */
+/* per lane: boxes, flights, largest flight, mean flight latency (us), mean device time (us, GMAPDP_STREAM_TIMING), mean upload time (us), stages */
 extern "C" int gmapdp_stream_lane_stats (const gmapdp_stream *s, int lane, double *out) {
   if (lane < 0 || lane >= (int) s->lanes.size()) return GMAPDP_ERR_ARG;
   Lane *L = s->lanes[lane];
@@ -427,7 +442,7 @@ extern "C" void gmapdp_stream_stats (const gmapdp_stream *s, double *out) {
     pthread_mutex_lock(&L->mu);
     out[0] += L->boxes; out[1] += L->flights; if (L->largest > out[2]) out[2] = L->largest;
     out[3] += L->gpu_s;
-    out[4] += L->t_flight; out[5] += L->t_wait; out[6] += (double) gmapdp_launch_count(L->ctx);
+    out[4] += L->t_flight; out[5] += L->t_wait; out[6] += (double) L->launches;
     out[7] += L->h2d; out[8] += L->d2h;
     pthread_mutex_unlock(&L->mu);
   }

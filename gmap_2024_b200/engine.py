@@ -260,8 +260,12 @@ class Batch:
         return p.contents if p else None
 
 
-class Ticket(C.Structure):
-    _fields_ = [("flight", C.c_void_p), ("index", C.c_int), ("lane", C.c_int)]
+class Mailbox(C.Structure):
+    pass
+
+
+Mailbox._fields_ = [("result", DeviceResult), ("ops", C.POINTER(C.c_uint32)), ("ops_cap", C.c_size_t), ("state", C.c_int), ("rc", C.c_int),
+                    ("wake", C.POINTER(Mailbox) * 2), ("t_submit", C.c_double)]
 
 
 class Stream:
@@ -290,26 +294,25 @@ class Stream:
             pass
         e = _NoCtx()
         e.lib, e.ctx = self.lib, C.c_void_p()
-        return Batch(e, max_rlength, max_glength)
+        b = Batch(e, max_rlength, max_glength)
+        cap = 2 * (max_rlength + max_glength) + 64
+        b._ops = (C.c_uint32 * cap)()
+        b._mailbox = Mailbox()
+        b._mailbox.ops = C.cast(b._ops, C.POINTER(C.c_uint32))
+        b._mailbox.ops_cap = cap
+        return b
 
     def call(self, batch):
-        """submit + wait + complete + release for the single call queued in ``batch``"""
+        """submit + wait + complete for the single call queued in ``batch`` (made by private_batch)"""
         boxes, n, seq, sb, probs, npb = batch.device_view()
         if n == 0:
             return
         assert n == 1
-        t = Ticket()
-        res, ops = C.POINTER(DeviceResult)(), C.POINTER(C.c_uint32)()
-        if self.lib.gmapdp_stream_submit(self.h, boxes, seq, C.c_size_t(sb), probs, C.c_size_t(npb), C.byref(t)) != 0 or \
-           self.lib.gmapdp_stream_wait(self.h, C.byref(t), C.byref(res), C.byref(ops)) != 0:
+        mb = batch._mailbox
+        if self.lib.gmapdp_stream_submit(self.h, boxes, seq, C.c_size_t(sb), probs, C.c_size_t(npb), C.byref(mb)) != 0 or \
+           self.lib.gmapdp_stream_wait(self.h, C.byref(mb)) != 0:
             raise EngineError(self.lib.gmapdp_stream_error(self.h).decode())
-        r = DeviceResult()
-        C.memmove(C.byref(r), res, C.sizeof(DeviceResult))
-        r.script_off = 0
-        try:
-            batch.complete(C.byref(r), ops)
-        finally:
-            self.lib.gmapdp_stream_release(self.h, C.byref(t))
+        batch.complete(C.byref(mb.result), mb.ops)
 
     def stats(self):
         out = (C.c_double * 9)()

@@ -7,22 +7,23 @@
  * (gmap.c:4867 worker_thread, `gmap -t N').  The reference has no such component: its threads never meet
  * (gmap.c:4895-4907, per-worker Dynprog_T / Pairpool_T).  This runtime is the meeting point:
  *
- *   worker thread                      launcher thread (per GPU)          completer thread (per GPU)
- *   -------------                      -------------------------          --------------------------
- *   gmapdp_stream_submit(box)    -->   closes the open flight as soon     waits for the oldest flight's
- *     reserves a slot in the open      as the GPU can take it (at most    D2H, publishes results, wakes
- *     flight, copies its sequences     GMAPDP_STREAM_DEPTH flights in     
- *     into the pinned staging          flight), orders the boxes, issues
- *   gmapdp_stream_wait(ticket)         2 H2D + 1 kernel + 1 D2H      the first waiters; every waiter
- *     sleeps on its box's futex                                           wakes two more (tree)
+ *   worker thread                          service thread of a lane (one lane per GPU and box size class)
+ *   -------------                          ---------------------------------------------------------------
+ *   gmapdp_stream_submit(box, mailbox) --> closes the open flight when the rules of gmapdp_stream.cpp say so (at once
+ *     reserves a slot in the open flight,  if the lane is idle; otherwise in time to queue behind the flight that is
+ *     copies its sequences into the        out), orders the boxes, issues 2 H2D copies + 1 kernel + 1 D2H copy;
+ *     pinned staging                       polls the flight's event; when it has fired, copies every box's result and
+ *   gmapdp_stream_wait(mailbox)            edit script into its owner's mailbox, wakes the first two owners and
+ *     sleeps on the mailbox's futex;       recycles the flight
+ *     once woken, wakes two more owners
+ *     (tree), then reads its mailbox
  *   ... replays its own edit script (in parallel with all other workers) ...
- *   gmapdp_stream_release(ticket)
  *
  * Flights are self-clocking: with an idle GPU a flight leaves with whatever it holds (latency), under load the
- * next one fills while the previous ones run (throughput); no timeouts, no global lock around device work, no
- * thundering herd (a waiter touches no mutex when it wakes).  Results never depend on how boxes were grouped.
+ * next one fills while the previous one runs (throughput); no timeouts, no global lock around device work, no
+ * thundering herd, and a flight never waits for a worker thread.  Results never depend on how boxes were grouped.
  *
- * Multi-GPU: every device has its own lanes (context, launcher, completer, flights -- one lane per box size class); a
+ * Multi-GPU: every device has its own lanes (context, stream, service thread, flights -- one lane per box size class); a
  * worker thread is pinned to one device for its lifetime, so the dependent chain of a query stays on one device
  * (SURVEY.md section 8e).  No collective.
  * There is no CPU fallback: creation fails without an sm_100 device.
@@ -38,13 +39,20 @@ extern "C" {
 
 typedef struct gmapdp_stream gmapdp_stream;
 
-typedef struct gmapdp_ticket {
-  void *flight;		/* opaque */
-  int index;		/* box index inside the flight */
-  int lane;
-} gmapdp_ticket;
+/* Where a box's result lands.  The caller owns it (one per thread is enough) and provides the script buffer; everything
+ * else is written by the runtime.  After gmapdp_stream_wait: `result' (its script_off is 0) and `ops' (script_lenA +
+ * script_lenB words) stay valid until the mailbox is submitted again. */
+typedef struct gmapdp_mailbox {
+  gmapdp_result result;
+  uint32_t *ops;		/* caller's buffer for the edit script */
+  size_t ops_cap;		/* its capacity in words: at least rlenL + glenL + rlenR + glenR + 8 of the box */
+  int state;			/* futex word: 0 pending, 1 landed, 2 lost */
+  int rc;
+  struct gmapdp_mailbox *wake[2];	/* owners this one wakes when it is woken (the runtime's wake-up tree) */
+  double t_submit;
+} gmapdp_mailbox;
 
-/* devices[ndevices]: CUDA device ordinals, one lane each.  max_boxes: capacity of a flight (0 = default 8192). */
+/* devices[ndevices]: CUDA device ordinals.  max_boxes: capacity of a flight (0 = default 2048). */
 int gmapdp_stream_create (gmapdp_stream **s, const int *devices, int ndevices, int max_boxes);
 void gmapdp_stream_destroy (gmapdp_stream *s);
 const char *gmapdp_stream_error (const gmapdp_stream *s);
@@ -52,14 +60,11 @@ int gmapdp_stream_ndevices (const gmapdp_stream *s);
 
 /* Submits one box.  The box's *_off fields are offsets into `seq' / `probs' (as produced by the entry points of
  * gmapdp_shim.h on a private batch, GmapDP_batch_device_view); both arrays are copied before the call returns.
- * Blocks only while every flight of the lane is busy. */
+ * Blocks only while no flight of the lane can take the box.  A thread may have several mailboxes in flight. */
 int gmapdp_stream_submit (gmapdp_stream *s, const gmapdp_box *box, const uint8_t *seq, size_t seqbytes,
-			  const double *probs, size_t nprobs, gmapdp_ticket *ticket);
-/* Blocks until the box's flight has completed.  *result and *ops (the box's edit script, result->script_lenA +
- * script_lenB words; result->script_off is relative to the flight and must be ignored) stay valid until
- * gmapdp_stream_release. */
-int gmapdp_stream_wait (gmapdp_stream *s, const gmapdp_ticket *ticket, const gmapdp_result **result, const uint32_t **ops);
-void gmapdp_stream_release (gmapdp_stream *s, const gmapdp_ticket *ticket);
+			  const double *probs, size_t nprobs, gmapdp_mailbox *mailbox);
+/* Blocks until the box's flight has landed; the mailbox then holds the result. */
+int gmapdp_stream_wait (gmapdp_stream *s, gmapdp_mailbox *mailbox);
 
 /* counters since creation, summed over lanes:
  *   [0] boxes  [1] flights  [2] largest flight  [3] seconds of device time (with GMAPDP_STREAM_TIMING=1)  [4] seconds a flight spent between launch and completion (sum)

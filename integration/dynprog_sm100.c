@@ -101,8 +101,8 @@ static void sm100_report (void) {
   }
 }
 
-static void sm100_free_mini (void *p) { if (p) GmapDP_batch_free((gmapdp_batch *) p); }
 
+static void sm100_free_thread_fwd (void *p);
 static void sm100_init (void) {
   const char *dev = getenv("GMAP_SM100_DEVICES");
   int devices[64], n = 0, rc;
@@ -126,12 +126,26 @@ static void sm100_init (void) {
     fprintf(stderr,"gmap.sm100: %s\n",gmapdp_stream_error(sm100_stream));
     exit(9);
   }
-  pthread_key_create(&sm100_key,sm100_free_mini);
+  pthread_key_create(&sm100_key,sm100_free_thread_fwd);
   sm100_t0 = now_s(); sm100_tsc0 = sm100_tsc();
   sm100_t_init = sm100_t0 - sm100_t_init;
   sm100_prof_on = getenv("GMAP_SM100_STATS") != NULL;
   atexit(sm100_report);
 }
+
+/* The runtime is created on a background thread started from Dynprog_init (gmap.c:6348: early in main, before the
+   genome index is loaded), so that CUDA context creation and the pinned allocations overlap the program's own start-up;
+   the first DP call waits for it. */
+static pthread_t sm100_init_thread;
+static int sm100_init_started = 0;
+static void *sm100_init_main (void *arg) { (void) arg; pthread_once(&sm100_once,sm100_init); return NULL; }
+static void sm100_start_init (void) {
+  if (__sync_bool_compare_and_swap(&sm100_init_started,0,1)) {
+    if (pthread_create(&sm100_init_thread,NULL,sm100_init_main,NULL) != 0) sm100_init_started = 2;
+    else pthread_detach(sm100_init_thread);
+  }
+}
+static void sm100_wait_ready (void) { pthread_once(&sm100_once,sm100_init); }	/* joins the background thread's once, or runs it */
 
 /* the devices of the process, for the chaining engine's groups (stage2_sm100.c): group g lives on device g mod n */
 int sm100_device_of_group (int group) {
@@ -157,6 +171,7 @@ void
 Dynprog_init (Mode_T mode) {
   if (mode != STANDARD) sm100_die("--mode other than standard (cmet / atoi / ttoc) changes the DP score tables; this build serves the standard tables only");
   ref_Dynprog_init(mode);
+  sm100_start_init();
 }
 
 static void sm100_user_penalties (int user_open_in, int user_extend_in, bool user_dynprog_p_in) {
@@ -189,45 +204,59 @@ Dynprog_end_setup (Univcoord_T *splicesites_in, Splicetype_T *splicetypes_in, Ch
 			trieoffsets_max_in,triecontents_max_in,user_open_in,user_extend_in,user_dynprog_p_in);
 }
 
-/* this thread's private one-call batch (all Dynprog_T of a gmap run have the same limits, gmap.c:4898-4903) */
-static gmapdp_batch *my_batch (Dynprog_T dynprog) {
-  gmapdp_batch *b;
-  pthread_once(&sm100_once,sm100_init);
-  b = (gmapdp_batch *) pthread_getspecific(sm100_key);
-  if (b == NULL) {
-    if ((b = GmapDP_batch_new(NULL,dynprog->max_rlength,dynprog->max_glength)) == NULL) sm100_die("Dynprog_T limits beyond 32767");
-    if (GmapDP_batch_user_dynprog(b,sm100_user_open,sm100_user_extend,sm100_user_dynprog_p) != GMAPDP_OK) sm100_die(GmapDP_batch_error(b));
-    pthread_setspecific(sm100_key,b);
-  }
-  GmapDP_batch_clear(b);
-  return b;
+/* per worker thread: a private one-call batch (all Dynprog_T of a gmap run have the same limits, gmap.c:4898-4903)
+   and the mailbox its boxes' results land in */
+typedef struct sm100_thread {
+  gmapdp_batch *batch;
+  gmapdp_mailbox mailbox;
+} sm100_thread;
+
+static void sm100_free_thread_fwd (void *p);
+static void sm100_free_thread (void *p) {
+  sm100_thread *t = (sm100_thread *) p;
+  if (t) { GmapDP_batch_free(t->batch); free(t->mailbox.ops); free(t); }
 }
 
-/* runs the call queued under `id' in this thread's batch; afterwards GmapDP_result_view(b,id,...) has the result */
+static void sm100_free_thread_fwd (void *p) { sm100_free_thread(p); }
+
+static sm100_thread *my_thread (Dynprog_T dynprog) {
+  sm100_thread *t;
+  sm100_wait_ready();
+  t = (sm100_thread *) pthread_getspecific(sm100_key);
+  if (t == NULL) {
+    t = (sm100_thread *) calloc(1,sizeof(sm100_thread));
+    if ((t->batch = GmapDP_batch_new(NULL,dynprog->max_rlength,dynprog->max_glength)) == NULL) sm100_die("Dynprog_T limits beyond 32767");
+    if (GmapDP_batch_user_dynprog(t->batch,sm100_user_open,sm100_user_extend,sm100_user_dynprog_p) != GMAPDP_OK) sm100_die(GmapDP_batch_error(t->batch));
+    t->mailbox.ops_cap = 2 * ((size_t) dynprog->max_rlength + (size_t) dynprog->max_glength) + 64;
+    t->mailbox.ops = (uint32_t *) malloc(t->mailbox.ops_cap * sizeof(uint32_t));
+    pthread_setspecific(sm100_key,t);
+  }
+  GmapDP_batch_clear(t->batch);
+  return t;
+}
+static gmapdp_batch *my_batch (Dynprog_T dynprog) { return my_thread(dynprog)->batch; }
+
+/* runs the call queued in this thread's batch; afterwards GmapDP_result_view(b,id,...) has the result */
 static void run_call (gmapdp_batch *b) {
   const gmapdp_box *boxes; const uint8_t *seq; const double *probs;
-  const gmapdp_result *res; const uint32_t *ops;
-  gmapdp_result r;
-  gmapdp_ticket ticket;
+  sm100_thread *t = (sm100_thread *) pthread_getspecific(sm100_key);
   size_t seqbytes, nprobs;
   int nboxes;
 
   __sync_fetch_and_add(&sm100_ncalls,1);
   if (GmapDP_batch_device_view(b,&boxes,&nboxes,&seq,&seqbytes,&probs,&nprobs) != GMAPDP_OK) sm100_die(GmapDP_batch_error(b));
   if (nboxes == 0) { __sync_fetch_and_add(&sm100_nhost,1); return; }	/* resolved by the entry point's own shortcuts */
-  if (gmapdp_stream_submit(sm100_stream,&boxes[0],seq,seqbytes,probs,nprobs,&ticket) != GMAPDP_OK) {
+  if (gmapdp_stream_submit(sm100_stream,&boxes[0],seq,seqbytes,probs,nprobs,&t->mailbox) != GMAPDP_OK) {
     fprintf(stderr,"gmap.sm100: DP submit: %s\n",gmapdp_stream_error(sm100_stream)); exit(9);
   }
   PROF_MARK(2);
-  if (gmapdp_stream_wait(sm100_stream,&ticket,&res,&ops) != GMAPDP_OK) {
+  if (gmapdp_stream_wait(sm100_stream,&t->mailbox) != GMAPDP_OK) {
     fprintf(stderr,"gmap.sm100: DP wait: %s\n",gmapdp_stream_error(sm100_stream)); exit(9);
   }
   PROF_MARK(3);
-  r = *res; r.script_off = 0;
-  if (GmapDP_batch_complete(b,&r,ops) != GMAPDP_OK) {
+  if (GmapDP_batch_complete(b,&t->mailbox.result,t->mailbox.ops) != GMAPDP_OK) {
     fprintf(stderr,"gmap.sm100: DP replay: %s\n",GmapDP_batch_error(b)); exit(9);
   }
-  gmapdp_stream_release(sm100_stream,&ticket);
   PROF_MARK(4);
 }
 

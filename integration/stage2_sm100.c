@@ -71,7 +71,7 @@ typedef struct chain_group {
   int npending[2];		/* calls queued in batch k and not yet run */
   int readers[2];		/* calls of batch k that have not read their paths yet */
   unsigned long seq[2];		/* completed runs of batch k */
-  bool running;
+  bool running, inited;
   double t_run;			/* seconds spent in GmapChain_batch_run */
 } chain_group;
 
@@ -83,6 +83,7 @@ static unsigned long chain_ncalls = 0, chain_nbatches = 0, chain_next_group = 0;
 static __thread int chain_my_group = -1;
 
 static double chain_t_init = 0.0;
+static unsigned long chain_init_us = 0;
 static double chain_now (void) {
   struct timespec t;
   clock_gettime(CLOCK_MONOTONIC,&t);
@@ -93,11 +94,11 @@ static void chain_report (void) {
   double t = 0.0;
   int g;
   if (getenv("GMAP_SM100_STATS") == NULL) return;
-  for (g = 0; g < chain_ngroups; g++) t += chain_groups[g].t_run;
+  for (g = 0; g < chain_ngroups; g++) if (chain_groups[g].inited) t += chain_groups[g].t_run;
   fprintf(stderr,"gmap.sm100 stage 2: %lu chaining calls on the device in %lu batches, %lu handed to the reference body\n",
 	  chain_ncalls,chain_nbatches,0UL);
   fprintf(stderr,"gmap.sm100 stage 2 runtime: %d groups, mean batch latency %.1f us, start-up %.3f s\n",chain_ngroups,
-	  chain_nbatches ? 1e6 * t / (double) chain_nbatches : 0.0,chain_t_init);
+	  chain_nbatches ? 1e6 * t / (double) chain_nbatches : 0.0,chain_t_init + 1e-6 * (double) chain_init_us);
 }
 
 static void chain_init (void) {
@@ -111,23 +112,32 @@ static void chain_init (void) {
     chain_group *G = &chain_groups[g];
     pthread_mutex_init(&G->mu,NULL);
     pthread_cond_init(&G->cv,NULL);
-    /* the values Stage2_setup stored (stage2.c:129-160, gmap.c:6544) */
-    if (gmapdp_create(&G->ctx,sm100_device_of_group(g)) != GMAPDP_OK ||
-	gmapchain_setup(G->ctx,splicingp,/*cross_species_p*/0,sufflookback,nsufflookback,maxintronlen) != GMAPDP_OK) {
-      fprintf(stderr,"gmap.sm100: %s\n",gmapdp_last_error(G->ctx));
-      exit(9);
-    }
-    /* room for a few dozen queries of ordinary size per batch: device buffers are then not re-allocated mid-run */
-    if (gmapchain_reserve(G->ctx,64,(size_t) 1 << 18,(size_t) 1 << 21) != GMAPDP_OK) {
-      fprintf(stderr,"gmap.sm100: %s\n",gmapdp_last_error(G->ctx));
-      exit(9);
-    }
-    G->batch[0] = GmapChain_batch_new(G->ctx); G->batch[1] = GmapChain_batch_new(G->ctx);
-    G->fill = 0; G->npending[0] = G->npending[1] = 0; G->readers[0] = G->readers[1] = 0; G->seq[0] = G->seq[1] = 0;
-    G->running = false; G->t_run = 0.0;
+    G->inited = false;
   }
   chain_t_init = chain_now() - t_begin;
   atexit(chain_report);
+}
+
+/* a group's engine is created by the first call that lands on it (group mutex held): a run with few threads never
+   pays for contexts it does not use */
+static void chain_group_init (chain_group *G, int g) {
+  const double t_begin = chain_now();
+  /* the values Stage2_setup stored (stage2.c:129-160, gmap.c:6544) */
+  if (gmapdp_create(&G->ctx,sm100_device_of_group(g)) != GMAPDP_OK ||
+      gmapchain_setup(G->ctx,splicingp,/*cross_species_p*/0,sufflookback,nsufflookback,maxintronlen) != GMAPDP_OK) {
+    fprintf(stderr,"gmap.sm100: %s\n",gmapdp_last_error(G->ctx));
+    exit(9);
+  }
+  /* room for a few dozen queries of ordinary size per batch: device buffers are then not re-allocated mid-run */
+  if (gmapchain_reserve(G->ctx,64,(size_t) 1 << 16,(size_t) 1 << 19) != GMAPDP_OK) {
+    fprintf(stderr,"gmap.sm100: %s\n",gmapdp_last_error(G->ctx));
+    exit(9);
+  }
+  G->batch[0] = GmapChain_batch_new(G->ctx); G->batch[1] = GmapChain_batch_new(G->ctx);
+  G->fill = 0; G->npending[0] = G->npending[1] = 0; G->readers[0] = G->readers[1] = 0; G->seq[0] = G->seq[1] = 0;
+  G->running = false; G->t_run = 0.0;
+  G->inited = true;
+  __sync_fetch_and_add(&chain_init_us,(unsigned long) (1e6 * (chain_now() - t_begin)));
 }
 
 typedef struct { int n; int *qpos; uint32_t *gpos; } chain_path_t;
@@ -148,6 +158,7 @@ chain_on_device (bool forwardp, CHAIN_PARAMS) {
   G = &chain_groups[chain_my_group];
 
   pthread_mutex_lock(&G->mu);
+  if (G->inited == false) chain_group_init(G,chain_my_group);
   while (G->readers[G->fill] > 0) pthread_cond_wait(&G->cv,&G->mu);	/* its previous run is still being read */
   kb = G->fill; B = G->batch[kb];
   if (forwardp) {
