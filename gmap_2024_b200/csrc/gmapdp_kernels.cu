@@ -819,8 +819,216 @@ __device__ void fill_full (const SideSeq &sd, int lband, int uband, int mt, int 
   }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * fill_full_pk -- Dynprog_simd_16 (dynprog_simd.c:6562) on packed s16x2 arithmetic: TWO 32-row stripes per warp.
+ *
+ * Lane l holds rows rlo + l (low halfword, "A") and rlo + 32 + l (high halfword, "B") of a 64-row stripe pair; the
+ * pair is one 64-stage systolic array: at step t half A of lane l is on column c0 + t - l, half B on the column 32 to
+ * the left.  The travelling words (final H and the vertical-gap carry) ROTATE down the lanes: lane 0's B half takes
+ * what lane 31's A half produced one step earlier, its A half the entry the previous pair's last row left in shared
+ * memory.  One VIMNMX.S16x2 gives the maximum of both halves AND both comparison predicates (the direction bits:
+ * predicated IMADs on the FMA pipe, as in full_fast), VIADDMNMX.S16x2 adds and floors both halves: 16 ALU-pipe
+ * instructions per 64 cells where full_fast needs 19 per 32.
+ *
+ * Why the halves may floor at PK_FLOOR instead of replaying the reference's saturation at -32768.  The 16-bit fills
+ * are exact per cell, and a traceback only ever visits cells whose score derives from H(0,0):
+ * such a score is at least -(5 min(r,c) + |open| + 3 |r - c|) >= -20 012 for sides up to GDP_PK_MAXSIDE (the path
+ * along the main diagonal and then along the row or column stays inside the band), whereas a value that derives from
+ * a minus-infinity start (cells outside the band, row -1, column -1) is at most floor + 3 min(r,c): -32 768 + 7 500
+ * in the reference, PK_FLOOR + 7 500 here.  Both stay below every real score, so every comparison a traceback can
+ * read has the same outcome; no halfword ever wraps because every sum is floored before it is used again.  The band
+ * edges then need no forced directions: left of its band a row is held at the floor (its first cell sees E = floor,
+ * i.e. the reference's forced DIAG at the bottom of the band, :6980-7002); on the top edge of the band the inputs
+ * from the row above are floored (no vertical gap into the top cell, :7019-7031); past the band a row computes
+ * values nobody reads.  Column 0 scores 0 against every row (H(0,0) = 0 comes from the initial diagonal value,
+ * H(r,0) from the vertical gap).
+ *
+ * Shared memory, 8 bytes per column (the same array as fill_full's, GDP_PK_PAD entries before column 0):
+ *   .x = H of the previous pair's last row | its vertical-gap carry << 16      (lane 31 rewrites it, 63 columns behind lane 0)
+ *   .y = PRMT selector of the column's class for half A | selector of column c - 32 for half B << 16
+ * ---------------------------------------------------------------------------------------------- */
+#define PK_FLOOR (-30000)
+#define PK_F2 0x8AD08AD0u	/* PK_FLOOR in both halves */
+
+__device__ __forceinline__ uint32_t pk_prmt (uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+struct PkLane {
+  uint32_t E, H, diag, cg;		/* s16x2: A | B << 16 */
+};
+struct PkConst {
+  uint32_t open2, ext2, selH, selC, ploA, p4A, ploB, p4B, one;
+  int tA0, tB0, tAtop, tBtop;
+  bool isl31;
+};
+
+/* max of both halves; the bits C_LO / C_HI are added to accA / accB where (LATE ? a >= b : a > b) holds in the low / high
+   half.  One VIMNMX.S16x2 with both predicate outputs (the PTX below is the pattern ptxas fuses into it, as in
+   __vibmax_s16x2: the predicate is "the maximum equals the first operand") and two predicated IMADs on the FMA pipe
+   (`one' is the kernel argument 1, see add_if). */
+template <bool LATE, uint32_t C_LO, uint32_t C_HI>
+__device__ __forceinline__ uint32_t pk_max_bits (uint32_t a, uint32_t b, uint32_t &accA, uint32_t &accB, const uint32_t one) {
+  uint32_t m;
+  if (LATE) {
+    asm("{\n\t.reg .pred pu, pv;\n\t.reg .s16 rs0, rs1, rs2, rs3;\n\t"
+	"max.s16x2 %0, %3, %4;\n\t"
+	"mov.b32 {rs0, rs1}, %0;\n\t"
+	"mov.b32 {rs2, rs3}, %3;\n\t"
+	"setp.eq.s16 pv, rs0, rs2;\n\t"
+	"setp.eq.s16 pu, rs1, rs3;\n\t"
+	"@pv mad.lo.u32 %1, %5, %6, %1;\n\t"
+	"@pu mad.lo.u32 %2, %5, %7, %2;\n\t}"
+	: "=r"(m), "+r"(accA), "+r"(accB) : "r"(a), "r"(b), "r"(one), "n"(C_LO), "n"(C_HI));
+  } else {
+    /* a > b  <=>  not (b >= a) */
+    asm("{\n\t.reg .pred pu, pv;\n\t.reg .s16 rs0, rs1, rs2, rs3;\n\t"
+	"max.s16x2 %0, %4, %3;\n\t"
+	"mov.b32 {rs0, rs1}, %0;\n\t"
+	"mov.b32 {rs2, rs3}, %4;\n\t"
+	"setp.eq.s16 pv, rs0, rs2;\n\t"
+	"setp.eq.s16 pu, rs1, rs3;\n\t"
+	"@!pv mad.lo.u32 %1, %5, %6, %1;\n\t"
+	"@!pu mad.lo.u32 %2, %5, %7, %2;\n\t}"
+	: "=r"(m), "+r"(accA), "+r"(accB) : "r"(a), "r"(b), "r"(one), "n"(C_LO), "n"(C_HI));
+  }
+  return m;
+}
+
+/* one step of the pair; GEN: lanes may be left of their band (held at the floor) or on its top edge */
+template <bool LATE, bool GEN, int U>
+__device__ __forceinline__ void pk_step (PkLane &st, uint32_t &accA, uint32_t &accB, const PkConst &k, const int src, const int t, uint2 *sp) {
+  const uint32_t hS = __shfl_sync(FULLMASK,st.H,src);
+  const uint32_t cgS = __shfl_sync(FULLMASK,st.cg,src);
+  const uint2 e = sp[U];
+  uint32_t hIn = pk_prmt(e.x,hS,k.selH);		/* lane 0: boundary H | lane 31's A half << 16; others: the lane above */
+  uint32_t cgIn = pk_prmt(e.x,cgS,k.selC);
+  if (GEN) {
+    const uint32_t mTop = ((t + U == k.tAtop) ? 0xffffu : 0u) | ((t + U == k.tBtop) ? 0xffff0000u : 0u);
+    hIn = (hIn & ~mTop) | (PK_F2 & mTop);
+    cgIn = (cgIn & ~mTop) | (PK_F2 & mTop);
+  }
+  const uint32_t sc = pk_prmt(k.ploA,k.p4A,e.y) | pk_prmt(k.ploB,k.p4B,e.y >> 16);
+  constexpr uint32_t S = 4u * U;
+  /* E (horizontal gap) */
+  const uint32_t T1 = __viaddmax_s16x2(st.H,k.open2,PK_F2);
+  const uint32_t mE = pk_max_bits<LATE,(4u << S),(4u << S)>(st.E,T1,accA,accB,k.one);
+  uint32_t E = __viaddmax_s16x2(mE,k.ext2,PK_F2);
+  /* diagonal */
+  const uint32_t Hd = __viaddmax_s16x2(st.diag,sc,PK_F2);
+  const uint32_t H1 = pk_max_bits<LATE,(1u << S),(1u << S)>(E,Hd,accA,accB,k.one);
+  /* F (vertical gap) */
+  const uint32_t score = __viaddmax_s16x2(hIn,k.open2,PK_F2);
+  const uint32_t cgm = pk_max_bits<LATE,(8u << S),(8u << S)>(cgIn,score,accA,accB,k.one);
+  uint32_t cg = __viaddmax_s16x2(cgm,k.ext2,PK_F2);
+  uint32_t H = pk_max_bits<LATE,(2u << S),(2u << S)>(cg,H1,accA,accB,k.one);
+  if (GEN) {
+    const uint32_t mPre = ((t + U < k.tA0) ? 0xffffu : 0u) | ((t + U < k.tB0) ? 0xffff0000u : 0u);
+    E = (E & ~mPre) | (PK_F2 & mPre);
+    H = (H & ~mPre) | (PK_F2 & mPre);
+    cg = (cg & ~mPre) | (PK_F2 & mPre);
+  }
+  st.diag = hIn; st.E = E; st.H = H; st.cg = cg;
+  if (k.isl31) sp[U - 32].x = pk_prmt(H,cg,0x7632u);		/* the B halves: H | carry << 16 */
+}
+
+template <bool LATE, bool GEN>
+__device__ __forceinline__ void pk_chunk (PkLane &st, const PkConst &k, const int src, const int t, uint2 *sp, uint32_t *dp) {
+  uint32_t accA = 0, accB = 0;
+  pk_step<LATE,GEN,0>(st,accA,accB,k,src,t,sp);
+  pk_step<LATE,GEN,1>(st,accA,accB,k,src,t,sp);
+  pk_step<LATE,GEN,2>(st,accA,accB,k,src,t,sp);
+  pk_step<LATE,GEN,3>(st,accA,accB,k,src,t,sp);
+  pk_step<LATE,GEN,4>(st,accA,accB,k,src,t,sp);
+  pk_step<LATE,GEN,5>(st,accA,accB,k,src,t,sp);
+  pk_step<LATE,GEN,6>(st,accA,accB,k,src,t,sp);
+  pk_step<LATE,GEN,7>(st,accA,accB,k,src,t,sp);
+  dp[0] = accA; dp[32] = accB;
+}
+
+template <bool LATE>
+__device__ void fill_full_pk (const SideSeq &sd, const int lband, const int uband, const int mt, const int open, const int extend,
+			      uint32_t *dirs, const FGeom &fg, uint2 *bnd, const GdpTables *tb, const uint32_t one) {
+  const int lane = threadIdx.x & 31;
+  const int rlen = sd.rlen, glen = sd.glen;
+  uint2 *col = bnd + GDP_PK_PAD;			/* col[c], c = -GDP_PK_PAD .. glen + 64 + 15 */
+  for (int c = lane - GDP_PK_PAD; c < glen + 64 + 16; c += 32) {
+    const int cb = c - 32;
+    const uint32_t ka = (c >= 1 && c <= glen) ? (uint32_t) nt_class(sd.g(c)) : 5u;		/* 5: a zero byte of the profile */
+    const uint32_t kb = (cb >= 1 && cb <= glen) ? (uint32_t) nt_class(sd.g(cb)) : 5u;
+    const uint32_t selA = (ka == 5u) ? 0x5555u : (0x5500u | ((ka | 8u) << 4) | ka);
+    const uint32_t selB = (kb == 5u) ? 0x5555u : (0x0055u | (kb << 8) | ((kb | 8u) << 12));
+    col[c] = make_uint2(PK_F2,selA | (selB << 16));
+  }
+  __syncwarp();
+  PkConst k;
+  k.one = one;
+  k.open2 = ((uint32_t) open & 0xffffu) * 0x10001u; k.ext2 = ((uint32_t) extend & 0xffffu) * 0x10001u;
+  k.selH = (lane == 0) ? 0x5410u : 0x7654u;		/* lane 0: e.x low half | shuffled low half << 16 */
+  k.selC = (lane == 0) ? 0x5432u : 0x7654u;		/* lane 0: e.x high half | shuffled low half << 16 */
+  k.isl31 = (lane == 31);
+  const int src = (lane + 31) & 31;
+  for (int p = 0, rlo = 0; rlo <= rlen; rlo += 64, p++) {
+    const int v = min(63,rlen - rlo);			/* last row of the pair that exists */
+    const int c0 = max(0,rlo - lband);
+    const int chigh = min(rlo + v + uband,glen);
+    if (c0 > chigh) continue;
+    const int nsteps = chigh - c0 + v + 1;
+    const int rA = rlo + lane, rB = rA + 32;
+    {
+      const int qa = (rA == 0) ? 'N' : ((rA <= rlen) ? sd.q(rA) : 0);
+      const int qb = (rB <= rlen) ? sd.q(rB) : 0;
+      const uint2 pa = *reinterpret_cast<const uint2 *>(&tb->U[mt][qa & 127][0]);
+      const uint2 pb = *reinterpret_cast<const uint2 *>(&tb->U[mt][qb & 127][0]);
+      k.ploA = (rA <= rlen) ? pa.x : 0u; k.p4A = (rA <= rlen) ? (pa.y & 0xffu) : 0u;
+      k.ploB = (rB <= rlen) ? pb.x : 0u; k.p4B = (rB <= rlen) ? (pb.y & 0xffu) : 0u;
+    }
+    /* first step on which a half is inside its band, and its step on the top edge of the band */
+    k.tA0 = lane + max(0,rA - lband) - c0;
+    k.tB0 = lane + 32 + max(0,rB - lband) - c0;
+    k.tAtop = rA + uband - c0 + lane;
+    k.tBtop = rB + uband - c0 + lane + 32;
+    PkLane st;
+    st.E = PK_F2; st.H = PK_F2; st.cg = PK_F2; st.diag = PK_F2;
+    if (lane == 0) {
+      /* H(rlo - 1, c0 - 1): 0 stands in for it at the origin, so that H(0,0) = 0 */
+      const uint32_t d = (p == 0) ? 0u : ((c0 > 0) ? (col[c0 - 1].x & 0xffffu) : (PK_F2 & 0xffffu));
+      st.diag = (PK_F2 & 0xffff0000u) | d;
+    }
+    /* interior steps: every half inside its band and below its top edge */
+    const int fs = (63 + max(0,rlo + 63 - lband) - c0 + 7) & ~7;
+    const int fe = (rlo + uband - c0) & ~7;					/* exclusive */
+    const int nsteps8 = (nsteps + 7) & ~7;
+    uint2 *sp = col + (c0 - lane);
+    uint32_t *dp = dirs + (size_t) p * fg.dirW2 + lane;
+    int t = 0;
+    const int g1 = (fs < fe) ? min(fs,nsteps8) : nsteps8;
+#pragma unroll 1
+    for (int seg = 0; seg < 2; seg++) {		/* one copy of the general chunk: before and after the interior chunks */
+      const int gend = seg ? nsteps8 : g1;
+#pragma unroll 1
+      for (; t < gend; t += 8, sp += 8, dp += 64) pk_chunk<LATE,true>(st,k,src,t,sp,dp);
+      if (seg == 0) {
+	const int fend = min(fe,nsteps8);
+#pragma unroll 1
+	for (; t < fend; t += 8, sp += 8, dp += 64) pk_chunk<LATE,false>(st,k,src,t,sp,dp);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __device__ __forceinline__ uint32_t full_dir (const uint32_t *dirs, const FGeom &fg, int r, int c) {
   if (r < c - fg.uband || r > c + fg.lband) return 0;
+  if (fg.pk) {
+    const int p = r >> 6, hb = (r >> 5) & 1, l = r & 31;
+    const int c0 = max(0,(p << 6) - fg.lband);
+    const int t = c - c0 + l + 32 * hb;
+    const uint32_t w = dirs[(size_t) p * fg.dirW2 + (t >> 3) * 64 + hb * 32 + l];
+    return (w >> (4 * (t & 7))) & 15u;
+  }
   const int s = r >> 5, l = r & 31;
   const int c0 = max(0,(s << 5) - fg.lband);
   const int tt = c - c0 + l;
@@ -1310,11 +1518,15 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
        once per stripe, addresses known in advance), not in shared memory: the kernel's occupancy is then set by
        its registers alone (4 blocks/SM instead of the 3 that 65 KB of boundary rows per block allowed) */
     if ((reinterpret_cast<uintptr_t>(wp) & 7) != 0) wp++;
-    bnd = reinterpret_cast<uint2 *>(wp); wp += 2 * (size_t) (b.glenL + 2);
+    bnd = reinterpret_cast<uint2 *>(wp); wp += 2 * (size_t) (b.glenL + 2 + GDP_PK_EXTRA);
 #endif
     uint32_t *dirs = wp;
     const bool alt = (b.gLalt_off != b.gL_off);
-    if (lateL) { if (alt) fill_full<true,true>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb,ka.one);
+    fg.pk = gdp_full_packed(b) ? 1 : 0;
+    if (fg.pk) {
+      if (lateL) fill_full_pk<true>(L,b.lbandL,b.ubandL,mt,open,extend,dirs,fg,bnd,tb,ka.one);
+      else fill_full_pk<false>(L,b.lbandL,b.ubandL,mt,open,extend,dirs,fg,bnd,tb,ka.one);
+    } else if (lateL) { if (alt) fill_full<true,true>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb,ka.one);
 		 else fill_full<true,false>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb,ka.one); }
     else { if (alt) fill_full<false,true>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb,ka.one);
 	   else fill_full<false,false>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb,ka.one); }
@@ -1518,7 +1730,9 @@ struct gmapdp_ctx {
   size_t chunk_bytes;			/* pipelining granularity of gmapdp_run_batch (GMAPDP_CHUNK_MB, default 384) */
   std::vector<int> chunk_count;		/* [chunk][kind] boxes */
   cudaStream_t stream, copy_stream;
-  std::vector<cudaEvent_t> chunk_events;
+  std::vector<cudaEvent_t> chunk_events, chunk_done;
+  cudaStream_t d2h_stream = 0;
+  unsigned long long *h_cursors = NULL; size_t cap_cursors = 0;		/* pinned: the script cursor after each chunk */
   cudaEvent_t ev0, ev1;
   std::string err;
   GdpTables *d_tables;
@@ -1645,6 +1859,9 @@ extern "C" void gmapdp_destroy (gmapdp_ctx *ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->chunk_done) cudaEventDestroy(e);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+  if (ctx->h_cursors) cudaFreeHost(ctx->h_cursors);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (int k = 0; k < GDP_NK; k++) {
     if (k > 0 && ctx->kstream[k] && ctx->kstream[k] != ctx->stream) cudaStreamDestroy(ctx->kstream[k]);
@@ -1752,7 +1969,7 @@ static int plan_scan (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, std:
 	pt.ws[kind] = std::max(pt.ws[kind],gdp_ws_words(b));
 	pt.script += (size_t) b.rlenL + b.glenL + 4;
 	if (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA) pt.script += (size_t) b.rlenR + b.glenR + 4;
-	if (b.mode == GMAPDP_SINGLE) pt.cols[0] = std::max(pt.cols[0],(int) b.glenL + 2);
+	if (b.mode == GMAPDP_SINGLE) pt.cols[0] = std::max(pt.cols[0],(int) b.glenL + 2 + GDP_PK_EXTRA);
 	else if (b.mode == GMAPDP_CDNA) pt.cols[3] = std::max(pt.cols[3],(int) b.glenL + 2);	/* M and Q tables: 2 words per column */
 	work[i] = std::make_pair((double) work_bucket(kind,box_work(b)),i);
 	if (upload_bytes) (*upload_bytes)[i] = box_upload_bytes(b);
@@ -1962,6 +2179,17 @@ extern "C" int gmapdp_download (gmapdp_ctx *ctx, gmapdp_result *results, uint32_
 extern "C" int gmapdp_run_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes,
 				 const uint8_t *seqpool, size_t seqbytes, const double *probpool, size_t nprobs,
 				 gmapdp_result *results, uint32_t *script, size_t script_cap, size_t *script_used) {
+  return gmapdp_run_batch_chunks(ctx,boxes,nboxes,seqpool,seqbytes,probpool,nprobs,results,script,script_cap,script_used,NULL,NULL);
+}
+
+/* The same with a completion callback per chunk: as soon as the results and edit scripts of boxes [first, first + n) are
+   in the caller's buffers, on_chunk(user,first,n) is called (on the calling thread, chunks in order) while the device
+   works on the following chunks -- the caller's post-processing (the shim's replay into pair lists) then overlaps the
+   kernels instead of following them. */
+extern "C" int gmapdp_run_batch_chunks (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes,
+					const uint8_t *seqpool, size_t seqbytes, const double *probpool, size_t nprobs,
+					gmapdp_result *results, uint32_t *script, size_t script_cap, size_t *script_used,
+					gmapdp_chunk_fn on_chunk, void *user) {
   if (!ctx || nboxes < 0 || (nboxes > 0 && (!boxes || !seqpool))) { if (ctx) ctx->err = "bad argument"; return GMAPDP_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   ctx->nboxes = nboxes;
@@ -2004,6 +2232,21 @@ extern "C" int gmapdp_run_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int n
   while ((int) ctx->chunk_events.size() < nchunks) {
     cudaEvent_t e; CK(cudaEventCreateWithFlags(&e,cudaEventDisableTiming)); ctx->chunk_events.push_back(e);
   }
+  /* per-chunk completion needs the kernels of a chunk to be over before the next chunk's begin: the one-stream order */
+  static const bool multi_streams = getenv("GMAPDP_STREAMS") != NULL;
+  const bool per_chunk = (on_chunk != NULL) && !multi_streams && nchunks > 1;
+  if (per_chunk) {
+    if (ctx->d2h_stream == 0) CK(cudaStreamCreateWithFlags(&ctx->d2h_stream,cudaStreamNonBlocking));
+    while ((int) ctx->chunk_done.size() < nchunks) {
+      cudaEvent_t e; CK(cudaEventCreateWithFlags(&e,cudaEventDisableTiming | cudaEventBlockingSync)); ctx->chunk_done.push_back(e);
+    }
+    if (ctx->cap_cursors < (size_t) nchunks) {
+      if (ctx->h_cursors) cudaFreeHost(ctx->h_cursors);
+      ctx->h_cursors = NULL; ctx->cap_cursors = 0;
+      CK(cudaHostAlloc((void **) &ctx->h_cursors,(size_t) (nchunks + 16) * sizeof(unsigned long long),cudaHostAllocDefault));
+      ctx->cap_cursors = (size_t) nchunks + 16;
+    }
+  }
   CK(cudaMemsetAsync(ctx->d_cursor,0,sizeof(unsigned long long),ctx->stream));
   CK(cudaEventRecord(ctx->evj[0],ctx->stream));
   rc = fork_streams(ctx,ctx->evj[0]);
@@ -2034,14 +2277,40 @@ extern "C" int gmapdp_run_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int n
     for (int kk = 0; kk < GDP_NK; kk++) CK(cudaStreamWaitEvent(ctx->kstream[kk],ctx->chunk_events[k],0));
     rc = launch_chunk(ctx,b0,&ctx->chunk_count[(size_t) k * GDP_NK]);
     if (rc) return rc;
+    if (per_chunk) {
+      /* the cursor as this chunk left it (its scripts end there), then its results on the download stream */
+      CK(cudaMemcpyAsync(&ctx->h_cursors[k],ctx->d_cursor,sizeof(unsigned long long),cudaMemcpyDeviceToHost,ctx->stream));
+      CK(cudaEventRecord(ctx->chunk_done[k],ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->d2h_stream,ctx->chunk_done[k],0));
+      CK(cudaMemcpyAsync(results + b0,ctx->d_results + b0,(size_t) n * sizeof(gmapdp_result),cudaMemcpyDeviceToHost,ctx->d2h_stream));
+    }
     if (k == 0) lap("first chunk launched");
   }
   lap("all chunks launched");
+  if (per_chunk) {
+    unsigned long long done_words = 0;
+    for (int k = 0; k < nchunks; k++) {
+      CK(cudaEventSynchronize(ctx->chunk_done[k]));
+      const unsigned long long used = ctx->h_cursors[k];
+      if (script_used) *script_used = (size_t) used;
+      if (used > ctx->cap_script) { ctx->err = "device script pool overflow"; cudaDeviceSynchronize(); return GMAPDP_ERR_CAPACITY; }
+      if (used > script_cap) { ctx->err = "script buffer too small"; cudaDeviceSynchronize(); return GMAPDP_ERR_CAPACITY; }
+      if (used > done_words)
+	CK(cudaMemcpyAsync(script + done_words,ctx->d_script + done_words,(size_t) (used - done_words) * sizeof(uint32_t),cudaMemcpyDeviceToHost,ctx->d2h_stream));
+      done_words = used;
+      CK(cudaStreamSynchronize(ctx->d2h_stream));
+      on_chunk(user,chunk_begin[k],chunk_begin[k+1] - chunk_begin[k]);
+    }
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    lap("chunks completed");
+    return GMAPDP_OK;
+  }
   for (int kk = 0; kk < GDP_NK; kk++) CK(cudaStreamSynchronize(ctx->kstream[kk]));
   CK(cudaStreamSynchronize(ctx->copy_stream));
   lap("kernels done");
   rc = gmapdp_download(ctx,results,script,script_cap,script_used);
   lap("results downloaded");
+  if (rc == GMAPDP_OK && on_chunk) on_chunk(user,0,nboxes);
   return rc;
 }
 
@@ -2060,7 +2329,7 @@ int gdp_box_geometry (const gmapdp_box *b, GdpBoxGeom *g) {
   if (!box_ok(*b)) return GMAPDP_ERR_ARG;
   g->kind = kind_of(b->mode);
   g->work = box_work(*b);
-  g->cols = (b->mode == GMAPDP_SINGLE || b->mode == GMAPDP_CDNA) ? (int) b->glenL + 2 : 8;
+  g->cols = (b->mode == GMAPDP_SINGLE) ? (int) b->glenL + 2 + GDP_PK_EXTRA : (b->mode == GMAPDP_CDNA ? (int) b->glenL + 2 : 8);
   g->ws_words = gdp_ws_words(*b);
   if (b->mode == GMAPDP_SINGLE) {
     const FGeom f = fgeom(b->rlenL,b->glenL,b->lbandL,b->ubandL);

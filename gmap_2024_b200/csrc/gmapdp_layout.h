@@ -89,7 +89,17 @@ GDP_HD void tri_fills_of (const gmapdp_box &b, TriPacking &tp) {
 struct FGeom {		/* one full fill */
   int rlen, glen, lband, uband;
   int nstripes, T, dirW;
+  /* packed layout (16-bit boxes on the s16x2 path, fill_full_pk): stripe PAIRS of 64 rows, lane l holds rows l and l + 32
+     of the pair, step t = (c - c0) + l + 32 * half; per pair ceil(T2/8) x 2 x 32 words */
+  int pk, npairs, T2, dirW2;
 };
+
+/* padding of the full fill's per-warp column entries in shared memory: the packed path indexes them with columns
+   -64 .. glen + 64 + 7 (lanes ahead of / behind the band read harmless entries instead of testing their column) */
+#define GDP_PK_PAD 64
+#define GDP_PK_EXTRA (GDP_PK_PAD + 64 + 16)
+/* sides up to which the packed path's floor argument holds (fill_full_pk) */
+#define GDP_PK_MAXSIDE 2500
 
 GDP_HD FGeom fgeom (int rlen, int glen, int lband, int uband) {
   FGeom g;
@@ -99,7 +109,18 @@ GDP_HD FGeom fgeom (int rlen, int glen, int lband, int uband) {
   if (w > glen + 1) w = glen + 1;
   g.T = w + 31;
   g.dirW = ((g.T + 7) / 8) * 32;
+  int w2 = 64 + lband + uband;
+  if (w2 > glen + 1) w2 = glen + 1;
+  g.npairs = (rlen + 64) / 64;
+  g.T2 = w2 + 63;
+  g.dirW2 = ((g.T2 + 7) / 8) * 64;
+  g.pk = 0;
   return g;
+}
+
+/* which single-gap boxes take the packed path: 16-bit arithmetic, no alternate genome, sides within the floor argument */
+GDP_HD bool gdp_full_packed (const gmapdp_box &b) {
+  return (b.flags & GMAPDP_F_USE8) == 0 && b.gLalt_off == b.gL_off && b.rlenL <= GDP_PK_MAXSIDE && b.glenL <= GDP_PK_MAXSIDE;
 }
 
 GDP_HD size_t gdp_align4 (size_t x) { return (x + 3) & ~(size_t) 3; }
@@ -119,8 +140,9 @@ GDP_HD size_t gdp_ws_words (const gmapdp_box &b) {
   w += (size_t) (b.rlenL + b.glenL + b.rlenR + b.glenR + 16);
   if (b.mode == GMAPDP_SINGLE) {
     FGeom f = fgeom(b.rlenL,b.glenL,b.lbandL,b.ubandL);
-    w += (size_t) f.nstripes * f.dirW;
-    w += 2 * (size_t) (b.glenL + 2) + 2;					/* stripe boundary row (8 bytes per column) */
+    const size_t d1 = (size_t) f.nstripes * f.dirW, d2 = (size_t) f.npairs * f.dirW2;
+    w += d1 > d2 ? d1 : d2;
+    w += 2 * (size_t) (b.glenL + 2 + GDP_PK_EXTRA) + 2;			/* stripe boundary row (8 bytes per column) */
   } else {
     const bool scores = (b.mode == GMAPDP_CDNA);	/* genome gaps evaluate their bridge inside the fills */
     TriPacking tp;

@@ -22,6 +22,8 @@
 #include <cstdlib>
 #include <thread>
 #include <atomic>
+#include <mutex>
+#include <condition_variable>
 
 namespace {
 
@@ -36,25 +38,62 @@ double prob_at (const std::vector<double> &v, int k) { return (k >= 0 && (size_t
 
 struct Counts { int score = 0, nmatches = 0, nmismatches = 0, nopens = 0, nindels = 0; };
 
-/* a list under construction: elements in push order (the reference conses, so its head is back()) */
-typedef std::vector<gmapdp_pair> Pushed;
+/* A pair list under construction, elements in push order (the reference conses, so its head is back()), and the
+   finished list of a call.  A plain array that is never value-initialised and keeps its memory when cleared: the replay
+   of a large batch writes a few hundred million pairs, and every pass over them (zero-filling, growing by copying,
+   copying the finished list into the call) costs as much as the replay itself. */
+struct Pushed {
+  gmapdp_pair *buf = NULL;
+  size_t first = 0, n = 0, cap = 0;		/* elements buf[first .. first + n) */
+  Pushed () {}
+  Pushed (const Pushed &) = delete;
+  Pushed &operator= (const Pushed &) = delete;
+  Pushed (Pushed &&o) noexcept : buf(o.buf), first(o.first), n(o.n), cap(o.cap) { o.buf = NULL; o.first = o.n = o.cap = 0; }
+  Pushed &operator= (Pushed &&o) noexcept {
+    if (this != &o) { free(buf); buf = o.buf; first = o.first; n = o.n; cap = o.cap; o.buf = NULL; o.first = o.n = o.cap = 0; }
+    return *this;
+  }
+  ~Pushed () { free(buf); }
+  void reserve (size_t want) {
+    if (want <= cap) return;
+    gmapdp_pair *nb = (gmapdp_pair *) realloc(buf,want * sizeof(gmapdp_pair));
+    if (!nb) abort();
+    buf = nb; cap = want;
+  }
+  void clear () { first = n = 0; }
+  size_t size () const { return n; }
+  bool empty () const { return n == 0; }
+  gmapdp_pair *data () { return buf + first; }
+  const gmapdp_pair *data () const { return buf + first; }
+  gmapdp_pair *begin () { return buf + first; }
+  gmapdp_pair *end () { return buf + first + n; }
+  gmapdp_pair &operator[] (size_t i) { return buf[first + i]; }
+  const gmapdp_pair &operator[] (size_t i) const { return buf[first + i]; }
+  gmapdp_pair &back () { return buf[first + n - 1]; }
+  gmapdp_pair &push () {
+    if (first + n == cap) reserve(cap ? 2 * cap : 64);
+    return buf[first + n++];
+  }
+  void drop_front (size_t k) { first += k; n -= k; }
+  void reverse () { std::reverse(begin(),end()); }
+};
 
-void push_pair (Pushed &l, int querypos, int genomepos, char cdna, char comp, char genome, char genomealt, int dynprogindex) {
+inline void push_pair (Pushed &l, int querypos, int genomepos, char cdna, char comp, char genome, char genomealt, int dynprogindex) {
   if (querypos < 0 || genomepos < 0) return;		/* Pairpool_push, pairpool.c:190 */
-  gmapdp_pair p;
-  memset(&p,0,sizeof(p));
-  p.querypos = querypos; p.genomepos = genomepos; p.cdna = cdna; p.comp = comp; p.genome = genome; p.genomealt = genomealt;
-  p.dynprogindex = dynprogindex;
-  l.push_back(p);
+  gmapdp_pair &p = l.push();
+  p.querypos = querypos; p.genomepos = genomepos; p.queryjump = 0; p.genomejump = 0;
+  p.dynprogindex = dynprogindex; p.introntype = 0; p.gapp = 0;
+  p.cdna = cdna; p.comp = comp; p.genome = genome; p.genomealt = genomealt;
+  p.donor_prob = 0.0; p.acceptor_prob = 0.0;
 }
 
-gmapdp_pair &push_gapholder (Pushed &l, int queryjump, int genomejump) {
-  gmapdp_pair p;
-  memset(&p,0,sizeof(p));
-  p.querypos = p.genomepos = -1; p.cdna = p.comp = p.genome = p.genomealt = ' ';
-  p.gapp = 1; p.queryjump = queryjump; p.genomejump = genomejump;
-  l.push_back(p);
-  return l.back();
+inline gmapdp_pair &push_gapholder (Pushed &l, int queryjump, int genomejump) {
+  gmapdp_pair &p = l.push();
+  p.querypos = p.genomepos = -1; p.queryjump = queryjump; p.genomejump = genomejump;
+  p.dynprogindex = 0; p.introntype = 0; p.gapp = 1;
+  p.cdna = p.comp = p.genome = p.genomealt = ' ';
+  p.donor_prob = 0.0; p.acceptor_prob = 0.0;
+  return p;
 }
 
 /* one traced side, with the reference's pointer conventions */
@@ -65,14 +104,13 @@ struct Side {
 };
 
 struct Replayer {
-  Pushed &l; const Side &sd; int dynprogindex; Counts &n;
-  Replayer (Pushed &l_, const Side &sd_, int dpi, Counts &n_) : l(l_), sd(sd_), dynprogindex(dpi), n(n_) {}
+  Pushed &l; const Side &sd; int dynprogindex; Counts &n; const GdpHostTables &t;
+  Replayer (Pushed &l_, const Side &sd_, int dpi, Counts &n_) : l(l_), sd(sd_), dynprogindex(dpi), n(n_), t(tables()) {}
 
   void diag (int r, int c) {
     int qc = r - 1, gc = c - 1;
     if (sd.revp) { qc = -qc; gc = -gc; }
     const char c1 = sd.rseq[qc], c1uc = sd.rsequc[qc], c2 = sd.gseq[gc], c2a = sd.galt[gc];
-    const GdpHostTables &t = tables();
     if (c2 == '*') return;
     if (c1uc == c2 || c1uc == c2a) {
       n.score += 1; n.nmatches++;
@@ -124,18 +162,21 @@ struct Replayer {
   }
 };
 
-int maxnegscore_headfirst (const std::vector<gmapdp_pair> &hf) {	/* Pair_maxnegscore, pair.c:8528 */
+int maxnegscore_headfirst (const Pushed &l) {	/* Pair_maxnegscore, pair.c:8528; the list's head is its last pushed element */
   int maxneg = 0, prevhigh = 0, score = 0;
-  size_t i = 0, n = hf.size();
+  const size_t n = l.size();
+  size_t i = 0;
+#define HF(I) l[n - 1 - (I)]
   while (i < n) {
-    if (hf[i].gapp) i++;
-    else if (hf[i].comp == COMP_MISMATCH) { score += -3; maxneg = std::min(maxneg,score - prevhigh); i++; }
-    else if (hf[i].comp == COMP_INDEL) {
+    if (HF(i).gapp) i++;
+    else if (HF(i).comp == COMP_MISMATCH) { score += -3; maxneg = std::min(maxneg,score - prevhigh); i++; }
+    else if (HF(i).comp == COMP_INDEL) {
       score += -3 + -1; i++;
-      while (i < n && hf[i].comp == COMP_INDEL) { score += -1; i++; }
+      while (i < n && HF(i).comp == COMP_INDEL) { score += -1; i++; }
       maxneg = std::min(maxneg,score - prevhigh);
     } else { score += 1; prevhigh = std::max(prevhigh,score); i++; }
   }
+#undef HF
   return maxneg;
 }
 
@@ -169,7 +210,7 @@ struct Call {
   int box = -1;			/* index into the device batch */
   bool isnull = true;
   int iout[10]; double dout[2];
-  std::vector<gmapdp_pair> pairs;	/* head first */
+  Pushed pairs;			/* head first */
   /* copies of the caller's sequences: forward arrays */
   std::string q, quc, qR, qRuc, gL, gLa, gR, gRa;
   std::vector<double> lp, rp;
@@ -308,7 +349,7 @@ extern "C" int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char 
     if (n.nmismatches <= 1 && !l.empty()) {
       c.iout[1] = n.score; c.iout[2] = n.nmatches; c.iout[3] = n.nmismatches; c.iout[4] = c.iout[5] = 0;
       bump(c.iout[0]);
-      c.pairs.assign(l.rbegin(),l.rend()); c.isnull = false; c.done = true;
+      l.reverse(); c.pairs = std::move(l); c.isnull = false; c.done = true;
       return id;
     }
   }
@@ -371,7 +412,8 @@ static int end_gap (gmapdp_batch *b, bool end5, int dynprogindex, const char *rs
     bump(c.iout[0]);
     if (!l.empty()) {
       c.isnull = false;
-      if (end5) c.pairs.assign(l.rbegin(),l.rend()); else c.pairs.assign(l.begin(),l.end());
+      if (end5) l.reverse();
+      c.pairs = std::move(l);
     }
     c.done = true;
     return id;
@@ -498,7 +540,7 @@ extern "C" int GmapDP_genome_gap (gmapdp_batch *b, int dynprogindex, const char 
       for (int r = bestrR; r > 0; r--) diag_only(l,sr,dynprogindex,n,r,r);
       *tbscore = n.score; *nmatches = n.nmatches; *nmismatches = n.nmismatches;
       bump(*dynprogindex_p);
-      c.pairs.assign(l.rbegin(),l.rend()); c.isnull = false; c.done = true;
+      l.reverse(); c.pairs = std::move(l); c.isnull = false; c.done = true;
       return id;
     }
   }
@@ -596,18 +638,21 @@ static void check_counts (int *count_mismatch, const gmapdp_result &r, const Cou
 /* thread-safe: touches only its own call (and the shared mismatch counter, atomically) */
 static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, int *count_mismatch) {
   const int dpi = c.iout[0];
+  /* the list is built in place in the call's own array (its memory survives GmapDP_batch_rewind / _clear) */
+  Pushed &l = c.pairs;
+  l.clear();
+  l.reserve((size_t) c.rlenL + c.glenL + c.rlenR + c.glenR + 2 * INSERT_PAIRS + 8);
   if (c.mode == GMAPDP_SINGLE) {
-    Pushed l; Counts n;
+    Counts n;
     Side sd = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
     Replayer(l,sd,dpi,n).run(0,c.rlenL,c.glenL,ops,r.script_lenA);
     check_counts(count_mismatch,r,n);
     c.iout[1] = n.score; c.iout[2] = n.nmatches; c.iout[3] = n.nmismatches; c.iout[4] = n.nopens; c.iout[5] = n.nindels;
     bump(c.iout[0]);
-    c.pairs.assign(l.begin(),l.end());		/* List_reverse of the consed list = push order */
-    c.isnull = l.empty();
+    c.isnull = l.empty();			/* List_reverse of the consed list = push order */
 
   } else if (c.mode == GMAPDP_END5 || c.mode == GMAPDP_END3) {
-    Pushed l; Counts n;
+    Counts n;
     Side sd;
     if (c.end5) sd = Side{c.q.data() + c.rlenL - 1,c.quc.data() + c.rlenL - 1,c.gL.data() + c.glenL - 1,c.gLa.data() + c.glenL - 1,c.roffset,c.goffset,true};
     else sd = Side{c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
@@ -619,11 +664,11 @@ static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, i
     } else {
       size_t k = 0;
       while (k < l.size() && l[k].comp == COMP_INDEL) k++;	/* leading indels of the reversed list */
-      l.erase(l.begin(),l.begin() + k);
+      l.drop_front(k);
     }
     bump(c.iout[0]);
     c.isnull = l.empty();
-    if (c.end5) c.pairs.assign(l.rbegin(),l.rend()); else c.pairs.assign(l.begin(),l.end());
+    if (c.end5) l.reverse();
 
   } else if (c.mode == GMAPDP_GENOME) {
     if (r.status != 0) { c.iout[3] = -100; c.isnull = true; return; }
@@ -633,10 +678,10 @@ static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, i
     c.iout[1] = c.goffset + (bestcL - 1);
     c.iout[2] = c.goffsetR - (bestcR - 1);
     c.iout[8] = rev_roffset - (bestrR - 1);
-    Pushed l; Counts n;
+    Counts n;
     Side sr = {c.q.data() + rlength - 1,c.quc.data() + rlength - 1,c.gR.data() + c.glenR - 1,c.gRa.data() + c.glenR - 1,rev_roffset,c.goffsetR,true};
     Replayer(l,sr,dpi,n).run(bestcR >= bestrR ? 1 : 2,bestrR,bestcR,ops,r.script_lenA);
-    std::reverse(l.begin(),l.end());
+    l.reverse();
     gmapdp_pair &gp = push_gapholder(l,(rev_roffset - bestrR) - (c.roffset + bestrL) + 1,c.iout[2] - c.iout[1] - 1);
     gp.introntype = c.introntype_in; gp.donor_prob = c.dout[0]; gp.acceptor_prob = c.dout[1];
     Side sl = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
@@ -645,18 +690,16 @@ static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, i
     c.iout[3] = n.score; c.iout[4] = n.nmatches; c.iout[5] = n.nmismatches; c.iout[6] = n.nopens; c.iout[7] = n.nindels;
     if (l.size() == 1) l.clear();
     bump(c.iout[0]);
-    std::vector<gmapdp_pair> hf(l.rbegin(),l.rend());
-    if (maxnegscore_headfirst(hf) < -10) { c.iout[3] = -100; c.isnull = true; return; }
-    c.pairs.assign(l.begin(),l.end());
+    if (maxnegscore_headfirst(l) < -10) { c.iout[3] = -100; c.isnull = true; l.clear(); return; }
     c.isnull = l.empty();
 
   } else {	/* cdna */
     const int bestrL = r.bestrL, bestrR = r.bestrR, bestcL = r.bestcL, bestcR = r.bestcR;
     const int rev_goffset = c.goffset + c.glenL - 1;
-    Pushed l; Counts n;
+    Counts n;
     Side sr = {c.qR.data() + c.rlenR - 1,c.qRuc.data() + c.rlenR - 1,c.gR.data() + c.glenL - 1,c.gRa.data() + c.glenL - 1,c.roffsetR,rev_goffset,true};
     Replayer(l,sr,dpi,n).run(bestcR >= bestrR ? 1 : 2,bestrR,bestcR,ops,r.script_lenA);
-    std::reverse(l.begin(),l.end());
+    l.reverse();
     const int queryjump = (c.roffsetR - bestrR) - (c.roffset + bestrL) + 1;
     const int genomejump = (rev_goffset - bestcR) - (c.goffset + bestcL) + 1;
     if (queryjump == INSERT_PAIRS && genomejump == INSERT_PAIRS) {
@@ -674,9 +717,14 @@ static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, i
     c.iout[1] = n.score;
     if (l.size() == 1) l.clear();
     bump(c.iout[0]);
-    c.pairs.assign(l.begin(),l.end());
     c.isnull = l.empty();
   }
+}
+
+static int replay_threads () {
+  const char *e = getenv("GMAPDP_REPLAY_THREADS");
+  int n = e ? atoi(e) : (int) std::min(32u,std::max(1u,std::thread::hardware_concurrency()));
+  return n < 1 ? 1 : n;
 }
 
 /* The replay of one call touches nothing but that call, so large batches are replayed by several host threads
@@ -689,12 +737,7 @@ static int finish_all (gmapdp_batch *b, const gmapdp_result *results, const uint
       if (!c.done && c.box >= 0) { const gmapdp_result &r = results[c.box]; finish_call(c,r,script + r.script_off,&b->count_mismatch); c.done = true; }
     }
   };
-  int nthreads = 1;
-  if (b->boxes.size() >= 4096) {
-    const char *e = getenv("GMAPDP_REPLAY_THREADS");
-    nthreads = e ? atoi(e) : (int) std::min(32u,std::max(1u,std::thread::hardware_concurrency()));
-    if (nthreads < 1) nthreads = 1;
-  }
+  const int nthreads = (b->boxes.size() >= 4096) ? replay_threads() : 1;
   if (nthreads == 1) work(0,n);
   else {
     /* dynamic blocks: boxes differ by three orders of magnitude in pair count */
@@ -823,10 +866,69 @@ extern "C" int GmapDP_batch_finish (gmapdp_batch *b) {
   return finish_all(b,b->results,b->script);
 }
 
+/* Replay that overlaps the device: the batch runs chunk by chunk (gmapdp_run_batch_chunks), and as soon as a chunk's
+   results and scripts are on the host its calls are replayed by the pool's threads while the device works on the next
+   chunks.  Chunks complete in box order, so "ready" is a prefix of the boxes. */
+namespace {
+struct ReplayPool {
+  gmapdp_batch *b;
+  int nboxes, ready = 0;
+  bool stop = false;
+  std::mutex mu; std::condition_variable cv;
+  std::atomic<int> next{0};
+  std::vector<std::thread> th;
+
+  static void on_chunk (void *user, int first, int n) {
+    ReplayPool *P = (ReplayPool *) user;
+    { std::lock_guard<std::mutex> g(P->mu); if (first + n > P->ready) P->ready = first + n; }
+    P->cv.notify_all();
+  }
+  void work () {
+    const int blk = 128;
+    for (;;) {
+      const int i0 = next.fetch_add(blk);
+      if (i0 >= nboxes) return;
+      const int i1 = std::min(nboxes,i0 + blk);
+      {
+	std::unique_lock<std::mutex> g(mu);
+	cv.wait(g,[&]() { return ready >= i1 || stop; });
+	if (stop) return;
+      }
+      for (int k = i0; k < i1; k++) {
+	Call &c = b->calls[b->box_call[k]];
+	if (!c.done) { const gmapdp_result &r = b->results[k]; finish_call(c,r,b->script + r.script_off,&b->count_mismatch); c.done = true; }
+      }
+    }
+  }
+  void start (int nthreads) { for (int t = 0; t < nthreads; t++) th.emplace_back([this]() { work(); }); }
+  void finish (bool ok) {
+    { std::lock_guard<std::mutex> g(mu); if (ok) ready = nboxes; else stop = true; }
+    cv.notify_all();
+    for (auto &x : th) x.join();
+  }
+};
+}
+
 extern "C" int GmapDP_batch_run (gmapdp_batch *b) {
-  int rc = GmapDP_batch_run_device(b);
+  if (b->boxes.size() < 4096) {
+    int rc = GmapDP_batch_run_device(b);
+    if (rc) return rc;
+    return finish_all(b,b->results,b->script);
+  }
+  if (!b->ctx) { b->err = "no device context: the DP engine has no CPU fallback"; return GMAPDP_ERR_CUDA; }
+  int rc = ensure_host_buffers(b);
   if (rc) return rc;
-  return finish_all(b,b->results,b->script);
+  ReplayPool P;
+  P.b = b; P.nboxes = (int) b->boxes.size();
+  P.start(replay_threads());
+  rc = gmapdp_run_batch_chunks(b->ctx,b->boxes.data(),(int) b->boxes.size(),b->seqpool.data(),b->seqpool.size(),
+			       b->probpool.data(),b->probpool.size(),b->results,b->script,b->script_cap,&b->script_used,
+			       ReplayPool::on_chunk,&P);
+  P.finish(rc == GMAPDP_OK);
+  if (rc) { b->err = gmapdp_last_error(b->ctx); b->uploaded = false; return rc; }
+  b->uploaded = true;
+  if (b->count_mismatch) { b->err = "device traceback counts disagree with the host replay"; return GMAPDP_ERR_ARG; }
+  return GMAPDP_OK;
 }
 
 /* order-independent digest of the device results (scores, best cells, counts, scripts): what the

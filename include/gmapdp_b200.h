@@ -104,6 +104,16 @@ int gmapdp_run_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes,
 		      const uint8_t *seqpool, size_t seqbytes, const double *probpool, size_t nprobs,
 		      gmapdp_result *results, uint32_t *script, size_t script_cap, size_t *script_used);
 
+/* The same with a completion callback: on_chunk(user,first,n) is called on the calling thread as soon as results[first ..
+ * first + n) and their edit scripts are in the caller's buffers -- chunk by chunk, in order, while the device works on the
+ * following chunks -- so that the caller's post-processing overlaps the kernels.  A batch that runs as one chunk gets
+ * one call at the end. */
+typedef void (*gmapdp_chunk_fn) (void *user, int first_box, int nboxes);
+int gmapdp_run_batch_chunks (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes,
+			     const uint8_t *seqpool, size_t seqbytes, const double *probpool, size_t nprobs,
+			     gmapdp_result *results, uint32_t *script, size_t script_cap, size_t *script_used,
+			     gmapdp_chunk_fn on_chunk, void *user);
+
 /* Resident path (benchmarks, pipelined callers): upload once, run any number of times with the
  * inputs already in HBM, download when wanted.  kernel_ms (may be NULL) receives the CUDA-event
  * time of the DP kernel alone, measured on the stream it was launched on. */

@@ -16,6 +16,21 @@ template <int OP> __device__ __forceinline__ int step (int a, int b, int c) {
   if (OP == 5) { int r; asm volatile("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }	// LOP3
   if (OP == 6) return __shfl_up_sync(0xffffffffu,a,1);				// SHFL.UP
   if (OP == 7) return __vimax3_s32(a,b,c);					// VIMNMX3
+  if (OP == 8) return (int) __vmaxs2((unsigned) a,(unsigned) b);			// VIMNMX.S16x2, two inputs
+  if (OP == 9) {									// VIMNMX.S16x2 with both predicates + two predicated IMADs
+    bool ph, pl; unsigned m = __vibmax_s16x2((unsigned) a,(unsigned) b,&ph,&pl);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q mad.lo.u32 %0, %2, 16, %0;\n\t}" : "+r"(m) : "r"((unsigned) ph), "r"(c));
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q mad.lo.u32 %0, %2, 1, %0;\n\t}" : "+r"(m) : "r"((unsigned) pl), "r"(c));
+    return (int) m;
+  }
+  if (OP == 10) return (int) __vadd2((unsigned) a,(unsigned) b);			// VIADD.16x2
+  if (OP == 11) { int r; asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }	// PRMT
+  if (OP == 12) { int r; asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }	// IMAD
+  if (OP == 13) {									// ISETP + predicated IMAD (the full fill's direction bits)
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %1, %2;\n\t@q mad.lo.u32 %0, %3, 16, %0;\n\t}" : "+r"(a) : "r"(b), "r"(a), "r"(c));
+    return a;
+  }
+  if (OP == 14) { int r; asm volatile("shf.r.s32 %0, %1, 16, %1;" : "=r"(r) : "r"(a)); return r ^ b; }	// SHF + LOP
   return a;
 }
 
@@ -26,7 +41,7 @@ template <int OP> __global__ void __launch_bounds__(256) k (int *out, int seed) 
   for (int it = 0; it < ITERS; it++) {
 #pragma unroll
     for (int i = 0; i < CHAINS; i++) v[i] = step<OP>(v[i],b,c);
-    if (OP != 0 && OP != 1 && OP != 5) { b ^= it; c += it; }	// fresh operands every round: no collapsing of the chains
+    if (OP != 0 && OP != 1 && OP != 5 && OP != 10) { b ^= it; c += it; }	// fresh operands every round: no collapsing of the chains
   }
   int s = 0;
 #pragma unroll
@@ -63,6 +78,12 @@ int main () {
   run<3>(d,blocks,"vimnmx3_s16x2",false);
   run<4>(d,blocks,"viaddmnmx_s16x2",false);
   run<5>(d,blocks,"lop3",false);
+  run<8>(d,blocks,"vimnmx_s16x2",false);
+  run<9>(d,blocks,"vimnmx_s16x2_2pred_plus_2_predicated_imad",false);
+  run<10>(d,blocks,"viadd_16x2",false);
+  run<11>(d,blocks,"prmt",false);
+  run<12>(d,blocks,"imad",false);
+  run<13>(d,blocks,"isetp_plus_predicated_imad",false);
   run<6>(d,blocks,"shfl_up",true);
   printf("}\n");
   return cudaGetLastError() != cudaSuccess;
