@@ -24,6 +24,9 @@
 #include <atomic>
 #include <mutex>
 #include <condition_variable>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace {
 
@@ -38,62 +41,78 @@ double prob_at (const std::vector<double> &v, int k) { return (k >= 0 && (size_t
 
 struct Counts { int score = 0, nmatches = 0, nmismatches = 0, nopens = 0, nindels = 0; };
 
-/* A pair list under construction, elements in push order (the reference conses, so its head is back()), and the
-   finished list of a call.  A plain array that is never value-initialised and keeps its memory when cleared: the replay
-   of a large batch writes a few hundred million pairs, and every pass over them (zero-filling, growing by copying,
-   copying the finished list into the call) costs as much as the replay itself. */
+/* A pair list under construction and the finished list of a call: compact records (gmapdp_cpair, 16 bytes) in a plain
+   array that is never value-initialised and keeps its memory when cleared, plus the side table of its gap holders.
+   The reference conses, so a list's head is the element pushed last; the entry points hand out some lists (or parts:
+   the right-hand side of a genome / cdna gap, a 5' end) in reversed order.  Those parts are written BACKWARDS from a
+   middle mark instead of being reversed afterwards: every pass over the ~10^9 pairs of a large batch costs as much as
+   writing them (the records are written with non-temporal stores for the same reason: no read-for-ownership). */
 struct Pushed {
-  gmapdp_pair *buf = NULL;
-  size_t first = 0, n = 0, cap = 0;		/* elements buf[first .. first + n) */
+  gmapdp_cpair *buf = NULL;
+  size_t lo = 0, hi = 0, cap = 0;		/* elements buf[lo .. hi) */
+  std::vector<gmapdp_gapinfo> gaps;
   Pushed () {}
   Pushed (const Pushed &) = delete;
   Pushed &operator= (const Pushed &) = delete;
-  Pushed (Pushed &&o) noexcept : buf(o.buf), first(o.first), n(o.n), cap(o.cap) { o.buf = NULL; o.first = o.n = o.cap = 0; }
+  Pushed (Pushed &&o) noexcept : buf(o.buf), lo(o.lo), hi(o.hi), cap(o.cap), gaps(std::move(o.gaps)) { o.buf = NULL; o.lo = o.hi = o.cap = 0; }
   Pushed &operator= (Pushed &&o) noexcept {
-    if (this != &o) { free(buf); buf = o.buf; first = o.first; n = o.n; cap = o.cap; o.buf = NULL; o.first = o.n = o.cap = 0; }
+    if (this != &o) { free(buf); buf = o.buf; lo = o.lo; hi = o.hi; cap = o.cap; gaps = std::move(o.gaps); o.buf = NULL; o.lo = o.hi = o.cap = 0; }
     return *this;
   }
   ~Pushed () { free(buf); }
-  void reserve (size_t want) {
-    if (want <= cap) return;
-    gmapdp_pair *nb = (gmapdp_pair *) realloc(buf,want * sizeof(gmapdp_pair));
-    if (!nb) abort();
-    buf = nb; cap = want;
+  /* empties the list; room for `back' elements pushed backwards and `fwd' pushed forwards */
+  void start (size_t back, size_t fwd) {
+    if (back + fwd > cap) {
+      free(buf);
+      buf = NULL;
+      if (posix_memalign((void **) &buf,64,(back + fwd) * sizeof(gmapdp_cpair)) != 0) abort();
+      cap = back + fwd;
+    }
+    lo = hi = back;
+    gaps.clear();
   }
-  void clear () { first = n = 0; }
-  size_t size () const { return n; }
-  bool empty () const { return n == 0; }
-  gmapdp_pair *data () { return buf + first; }
-  const gmapdp_pair *data () const { return buf + first; }
-  gmapdp_pair *begin () { return buf + first; }
-  gmapdp_pair *end () { return buf + first + n; }
-  gmapdp_pair &operator[] (size_t i) { return buf[first + i]; }
-  const gmapdp_pair &operator[] (size_t i) const { return buf[first + i]; }
-  gmapdp_pair &back () { return buf[first + n - 1]; }
-  gmapdp_pair &push () {
-    if (first + n == cap) reserve(cap ? 2 * cap : 64);
-    return buf[first + n++];
+  void clear () { lo = hi = 0; gaps.clear(); }
+  size_t size () const { return hi - lo; }
+  bool empty () const { return hi == lo; }
+  const gmapdp_cpair *data () const { return buf + lo; }
+  const gmapdp_cpair &operator[] (size_t i) const { return buf[lo + i]; }
+  void grow_fwd () {		/* lists of unknown length (host-resolved calls): amortised doubling */
+    const size_t ncap = cap ? 2 * cap : 64;
+    gmapdp_cpair *nb = NULL;
+    if (posix_memalign((void **) &nb,64,ncap * sizeof(gmapdp_cpair)) != 0) abort();
+    if (hi > lo) memcpy(nb + lo,buf + lo,(hi - lo) * sizeof(gmapdp_cpair));
+    free(buf); buf = nb; cap = ncap;
   }
-  void drop_front (size_t k) { first += k; n -= k; }
-  void reverse () { std::reverse(begin(),end()); }
+  gmapdp_cpair *slot (bool back) {
+    if (back) { if (lo == 0) abort(); return &buf[--lo]; }
+    if (hi == cap) grow_fwd();
+    return &buf[hi++];
+  }
+  void drop_front (size_t k) { lo += k; }
+  void drop_back (size_t k) { hi -= k; }
+  void reverse () { std::reverse(buf + lo,buf + hi); }
 };
 
-inline void push_pair (Pushed &l, int querypos, int genomepos, char cdna, char comp, char genome, char genomealt, int dynprogindex) {
-  if (querypos < 0 || genomepos < 0) return;		/* Pairpool_push, pairpool.c:190 */
-  gmapdp_pair &p = l.push();
-  p.querypos = querypos; p.genomepos = genomepos; p.queryjump = 0; p.genomejump = 0;
-  p.dynprogindex = dynprogindex; p.introntype = 0; p.gapp = 0;
-  p.cdna = cdna; p.comp = comp; p.genome = genome; p.genomealt = genomealt;
-  p.donor_prob = 0.0; p.acceptor_prob = 0.0;
+inline void store_pair (gmapdp_cpair *p, int querypos, int genomepos, char cdna, char comp, char genome, char genomealt, int gap) {
+#if defined(__SSE2__) && !defined(GMAPDP_NO_NT_STORES)
+  const uint32_t chars = (uint32_t) (uint8_t) cdna | ((uint32_t) (uint8_t) comp << 8) | ((uint32_t) (uint8_t) genome << 16) | ((uint32_t) (uint8_t) genomealt << 24);
+  _mm_stream_si128(reinterpret_cast<__m128i *>(p),_mm_set_epi32(gap,(int) chars,genomepos,querypos));
+#else
+  p->querypos = querypos; p->genomepos = genomepos; p->cdna = cdna; p->comp = comp; p->genome = genome; p->genomealt = genomealt; p->gap = gap;
+#endif
 }
 
-inline gmapdp_pair &push_gapholder (Pushed &l, int queryjump, int genomejump) {
-  gmapdp_pair &p = l.push();
-  p.querypos = p.genomepos = -1; p.queryjump = queryjump; p.genomejump = genomejump;
-  p.dynprogindex = 0; p.introntype = 0; p.gapp = 1;
-  p.cdna = p.comp = p.genome = p.genomealt = ' ';
-  p.donor_prob = 0.0; p.acceptor_prob = 0.0;
-  return p;
+inline void push_pair (Pushed &l, bool back, int querypos, int genomepos, char cdna, char comp, char genome, char genomealt) {
+  if (querypos < 0 || genomepos < 0) return;		/* Pairpool_push, pairpool.c:190 */
+  store_pair(l.slot(back),querypos,genomepos,cdna,comp,genome,genomealt,-1);
+}
+
+inline gmapdp_gapinfo &push_gapholder (Pushed &l, bool back, int queryjump, int genomejump) {
+  gmapdp_gapinfo g;
+  g.queryjump = queryjump; g.genomejump = genomejump; g.introntype = 0; g.pad_ = 0; g.donor_prob = 0.0; g.acceptor_prob = 0.0;
+  l.gaps.push_back(g);
+  store_pair(l.slot(back),-1,-1,' ',' ',' ',' ',(int) l.gaps.size() - 1);
+  return l.gaps.back();
 }
 
 /* one traced side, with the reference's pointer conventions */
@@ -104,8 +123,9 @@ struct Side {
 };
 
 struct Replayer {
-  Pushed &l; const Side &sd; int dynprogindex; Counts &n; const GdpHostTables &t;
-  Replayer (Pushed &l_, const Side &sd_, int dpi, Counts &n_) : l(l_), sd(sd_), dynprogindex(dpi), n(n_), t(tables()) {}
+  Pushed &l; const Side &sd; Counts &n; const GdpHostTables &t; const bool back;
+  /* back: the list wanted is the reverse of the push order -- written backwards */
+  Replayer (Pushed &l_, const Side &sd_, Counts &n_, bool back_ = false) : l(l_), sd(sd_), n(n_), t(tables()), back(back_) {}
 
   void diag (int r, int c) {
     int qc = r - 1, gc = c - 1;
@@ -114,13 +134,13 @@ struct Replayer {
     if (c2 == '*') return;
     if (c1uc == c2 || c1uc == c2a) {
       n.score += 1; n.nmatches++;
-      push_pair(l,sd.queryoffset + qc,sd.genomeoffset + gc,c1,COMP_DYNMATCH,c2,c2a,dynprogindex);
+      push_pair(l,back,sd.queryoffset + qc,sd.genomeoffset + gc,c1,COMP_DYNMATCH,c2,c2a);
     } else if (t.cons[c1uc & 127][c2 & 127] || t.cons[c1uc & 127][c2a & 127]) {
       n.score += 1; n.nmatches++;
-      push_pair(l,sd.queryoffset + qc,sd.genomeoffset + gc,c1,COMP_AMBIG,c2,c2a,dynprogindex);
+      push_pair(l,back,sd.queryoffset + qc,sd.genomeoffset + gc,c1,COMP_AMBIG,c2,c2a);
     } else {
       n.score += -3; n.nmismatches++;
-      push_pair(l,sd.queryoffset + qc,sd.genomeoffset + gc,c1,COMP_MISMATCH,c2,c2a,dynprogindex);
+      push_pair(l,back,sd.queryoffset + qc,sd.genomeoffset + gc,c1,COMP_MISMATCH,c2,c2a);
     }
   }
   void hgap (int r, int c, int dist) {		/* Pairpool_add_genomeskip */
@@ -129,24 +149,50 @@ struct Replayer {
     if (dist < MICROINTRON_LENGTH) {
       int gc = sd.revp ? left : right;
       for (int j = 0; j < dist; j++, gc += step)
-	push_pair(l,sd.queryoffset + qc,sd.genomeoffset + gc,' ',COMP_INDEL,sd.gseq[gc],sd.galt[gc],dynprogindex);
+	push_pair(l,back,sd.queryoffset + qc,sd.genomeoffset + gc,' ',COMP_INDEL,sd.gseq[gc],sd.galt[gc]);
       n.score += -3 - dist; n.nopens++; n.nindels += dist;
     } else {
-      push_gapholder(l,0,dist);
+      push_gapholder(l,back,0,dist);
     }
   }
   void vgap (int r, int c, int dist) {		/* Pairpool_add_queryskip */
     int qc = r - 1, gc = c - 1, step = -1;
     if (sd.revp) { qc = -qc; gc = -gc; step = +1; }
     for (int j = 0; j < dist; j++, qc += step)
-      push_pair(l,sd.queryoffset + qc,sd.genomeoffset + gc,sd.rseq[qc],COMP_INDEL,' ',' ',dynprogindex);
+      push_pair(l,back,sd.queryoffset + qc,sd.genomeoffset + gc,sd.rseq[qc],COMP_INDEL,' ',' ');
     n.score += -3 - dist; n.nopens++; n.nindels += dist;
+  }
+  /* `len' diagonal steps from (r,c): diag() in one loop over four pointers.  Only for lists whose room was reserved by
+     Pushed::start (every device call: a side pushes at most rlength + glength pairs). */
+  void diag_run (int r, int c, int len) {
+    int qc = r - 1, gc = c - 1, step = -1;
+    if (sd.revp) { qc = -qc; gc = -gc; step = +1; }
+    const char *rs = sd.rseq + qc, *ru = sd.rsequc + qc, *gs = sd.gseq + gc, *ga = sd.galt + gc;
+    int qpos = sd.queryoffset + qc, gpos = sd.genomeoffset + gc;
+    gmapdp_cpair *out = l.buf + (back ? l.lo : l.hi);
+    const int ostep = back ? -1 : +1;
+    if (back) out--;
+    int nm = 0, nx = 0;
+    for (int j = 0; j < len; j++, rs += step, ru += step, gs += step, ga += step, qpos += step, gpos += step) {
+      const char c2 = *gs;
+      if (c2 == '*') continue;
+      const char c1uc = *ru, c2a = *ga;
+      char comp;
+      if (c1uc == c2 || c1uc == c2a) { comp = COMP_DYNMATCH; nm++; }
+      else if (t.cons[c1uc & 127][c2 & 127] || t.cons[c1uc & 127][c2a & 127]) { comp = COMP_AMBIG; nm++; }
+      else { comp = COMP_MISMATCH; nx++; }
+      if (qpos < 0 || gpos < 0) continue;			/* Pairpool_push, pairpool.c:190 */
+      store_pair(out,qpos,gpos,*rs,comp,c2,c2a,-1);
+      out += ostep;
+    }
+    if (back) l.lo = (size_t) (out + 1 - l.buf); else l.hi = (size_t) (out - l.buf);
+    n.score += nm - 3 * nx; n.nmatches += nm; n.nmismatches += nx;
   }
   /* kind: 0 full, 1 upper, 2 lower */
   void run (int kind, int r, int c, const uint32_t *ops, int nops) {
     for (int k = 0; k < nops; k++) {
       const int len = (int) (ops[k] >> 2), what = (int) (ops[k] & 3u);
-      if (what == 0) { for (int j = 0; j < len; j++) { diag(r,c); r--; c--; } }
+      if (what == 0) { diag_run(r,c,len); r -= len; c -= len; }
       else if (what == 1) { hgap(r,c,len); c -= len; }
       else { vgap(r,c,len); r -= len; }
     }
@@ -168,7 +214,7 @@ int maxnegscore_headfirst (const Pushed &l) {	/* Pair_maxnegscore, pair.c:8528; 
   size_t i = 0;
 #define HF(I) l[n - 1 - (I)]
   while (i < n) {
-    if (HF(i).gapp) i++;
+    if (HF(i).gap >= 0) i++;
     else if (HF(i).comp == COMP_MISMATCH) { score += -3; maxneg = std::min(maxneg,score - prevhigh); i++; }
     else if (HF(i).comp == COMP_INDEL) {
       score += -3 + -1; i++;
@@ -211,6 +257,7 @@ struct Call {
   bool isnull = true;
   int iout[10]; double dout[2];
   Pushed pairs;			/* head first */
+  int dpi = 0;			/* dynprogindex of the call's ordinary pairs */
   /* copies of the caller's sequences: forward arrays */
   std::string q, quc, qR, qRuc, gL, gLa, gR, gRa;
   std::vector<double> lp, rp;
@@ -319,7 +366,7 @@ extern "C" long GmapDP_batch_cells8_full (const gmapdp_batch *b) { return b->cel
 
 static gmapdp_box blank_box () { gmapdp_box x; memset(&x,0,sizeof(x)); return x; }
 
-static void diag_only (Pushed &l, const Side &sd, int dpi, Counts &n, int r, int c) { Replayer rp(l,sd,dpi,n); rp.diag(r,c); }
+static void diag_only (Pushed &l, const Side &sd, Counts &n, int r, int c) { Replayer rp(l,sd,n); rp.diag(r,c); }
 
 /* ------------------------------------------------------------------------------------------------ */
 extern "C" int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char *rsequence, const char *rsequenceuc,
@@ -332,7 +379,7 @@ extern "C" int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char 
   Call &c = b->calls.back();
   const int id = (int) b->calls.size() - 1;
   c.mode = GMAPDP_SINGLE;
-  c.iout[0] = dynprogindex;
+  c.iout[0] = dynprogindex; c.dpi = dynprogindex;
   const int qual = quality(defect_rate), mt = qual;
   if (rlength <= 0 || glength <= 0 || rlength > b->max_rlength || glength > b->max_glength) {
     c.iout[1] = NEG_INFINITY_32; bump(c.iout[0]); c.done = true; return id;
@@ -345,7 +392,7 @@ extern "C" int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char 
   if (glength == rlength) {			/* single_gap_simple */
     Pushed l; Counts n;
     Side sd = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),roffset,goffset,false};
-    for (int r = 1; r <= rlength; r++) diag_only(l,sd,dynprogindex,n,r,r);
+    for (int r = 1; r <= rlength; r++) diag_only(l,sd,n,r,r);
     if (n.nmismatches <= 1 && !l.empty()) {
       c.iout[1] = n.score; c.iout[2] = n.nmatches; c.iout[3] = n.nmismatches; c.iout[4] = c.iout[5] = 0;
       bump(c.iout[0]);
@@ -382,7 +429,7 @@ static int end_gap (gmapdp_batch *b, bool end5, int dynprogindex, const char *rs
   const int id = (int) b->calls.size() - 1;
   c.mode = end5 ? GMAPDP_END5 : GMAPDP_END3;
   c.end5 = end5; c.endalign = endalign; c.require_pos = require_pos_score_p != 0;
-  c.iout[0] = dynprogindex;
+  c.iout[0] = dynprogindex; c.dpi = dynprogindex;
   const int qual = quality(defect_rate);
   /* early exits leave traceback_score = 0 and the counts = 0, dynprogindex untouched */
   if (rlength <= 0) { c.done = true; return id; }
@@ -406,7 +453,7 @@ static int end_gap (gmapdp_batch *b, bool end5, int dynprogindex, const char *rs
     Side sd;
     if (end5) sd = Side{c.q.data() + rlength - 1,c.quc.data() + rlength - 1,c.gL.data() + glength - 1,c.gLa.data() + glength - 1,roffset,goffset,true};
     else sd = Side{c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),roffset,goffset,false};
-    for (int r = best, cc = best; r > 0 && cc > 0; r--, cc--) diag_only(l,sd,dynprogindex,n,r,cc);
+    for (int r = best, cc = best; r > 0 && cc > 0; r--, cc--) diag_only(l,sd,n,r,cc);
     c.iout[1] = n.score; c.iout[2] = n.nmatches; c.iout[3] = n.nmismatches;
     /* no (nmatches+1 < nmismatches) filter for NOGAPS; strip leading INDEL_COMP pairs: there are none */
     bump(c.iout[0]);
@@ -478,6 +525,7 @@ extern "C" int GmapDP_genome_gap (gmapdp_batch *b, int dynprogindex, const char 
   c.mode = GMAPDP_GENOME;
   int *dynprogindex_p = &c.iout[0], *new_left = &c.iout[1], *new_right = &c.iout[2], *tbscore = &c.iout[3];
   int *nmatches = &c.iout[4], *nmismatches = &c.iout[5], *exonhead = &c.iout[8], *introntype = &c.iout[9];
+  c.dpi = dynprogindex;
   /* out-parameters the reference may leave unwritten keep the caller's sentinel */
   for (int k = 1; k < 10; k++) c.iout[k] = GMAPDP_UNSET;
   *dynprogindex_p = dynprogindex;
@@ -530,14 +578,14 @@ extern "C" int GmapDP_genome_gap (gmapdp_batch *b, int dynprogindex, const char 
     if (result) {
       Pushed l; Counts n;
       Side sl = {c.q.data(),c.quc.data(),gl,gla,roffset,goffsetL,false};
-      for (int r = 1; r <= bestrL; r++) diag_only(l,sl,dynprogindex,n,r,r);
+      for (int r = 1; r <= bestrL; r++) diag_only(l,sl,n,r,r);
       *new_left = goffsetL + (bestrL - 1);
       *new_right = *exonhead = rev_goffsetR - (bestrR - 1);
-      gmapdp_pair &gp = push_gapholder(l,0,(*new_right) - (*new_left) - 1);
+      gmapdp_gapinfo &gp = push_gapholder(l,false,0,(*new_right) - (*new_left) - 1);
       gp.introntype = itype;		/* the LAST iteration's introntype (dynprog_genome.c:3230) */
       gp.donor_prob = c.dout[0]; gp.acceptor_prob = c.dout[1];
       Side sr = {c.q.data() + rlength - 1,c.quc.data() + rlength - 1,rgr,rgra,rev_roffset,rev_goffsetR,true};
-      for (int r = bestrR; r > 0; r--) diag_only(l,sr,dynprogindex,n,r,r);
+      for (int r = bestrR; r > 0; r--) diag_only(l,sr,n,r,r);
       *tbscore = n.score; *nmatches = n.nmatches; *nmismatches = n.nmismatches;
       bump(*dynprogindex_p);
       l.reverse(); c.pairs = std::move(l); c.isnull = false; c.done = true;
@@ -587,7 +635,7 @@ extern "C" int GmapDP_cdna_gap (gmapdp_batch *b, int dynprogindex,
   Call &c = b->calls.back();
   const int id = (int) b->calls.size() - 1;
   c.mode = GMAPDP_CDNA;
-  c.iout[0] = dynprogindex; c.iout[1] = GMAPDP_UNSET; c.iout[2] = 0;
+  c.iout[0] = dynprogindex; c.dpi = dynprogindex; c.iout[1] = GMAPDP_UNSET; c.iout[2] = 0;
   if (glength <= 1) { c.done = true; return id; }
   const int mt = quality(defect_rate);
   if (glength > b->max_glength || rlengthR > b->max_rlength || rlengthL > b->max_rlength) { bump(c.iout[0]); c.done = true; return id; }
@@ -637,15 +685,15 @@ static void check_counts (int *count_mismatch, const gmapdp_result &r, const Cou
 
 /* thread-safe: touches only its own call (and the shared mismatch counter, atomically) */
 static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, int *count_mismatch) {
-  const int dpi = c.iout[0];
-  /* the list is built in place in the call's own array (its memory survives GmapDP_batch_rewind / _clear) */
+  c.dpi = c.iout[0];
+  /* the list is built in place in the call's own array (its memory survives GmapDP_batch_rewind) */
   Pushed &l = c.pairs;
-  l.clear();
-  l.reserve((size_t) c.rlenL + c.glenL + c.rlenR + c.glenR + 2 * INSERT_PAIRS + 8);
+  const size_t sideL = (size_t) c.rlenL + c.glenL + 4, sideR = (size_t) c.rlenR + c.glenR + 4;
   if (c.mode == GMAPDP_SINGLE) {
     Counts n;
+    l.start(0,sideL);
     Side sd = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
-    Replayer(l,sd,dpi,n).run(0,c.rlenL,c.glenL,ops,r.script_lenA);
+    Replayer(l,sd,n).run(0,c.rlenL,c.glenL,ops,r.script_lenA);
     check_counts(count_mismatch,r,n);
     c.iout[1] = n.score; c.iout[2] = n.nmatches; c.iout[3] = n.nmismatches; c.iout[4] = n.nopens; c.iout[5] = n.nindels;
     bump(c.iout[0]);
@@ -654,24 +702,26 @@ static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, i
   } else if (c.mode == GMAPDP_END5 || c.mode == GMAPDP_END3) {
     Counts n;
     Side sd;
-    if (c.end5) sd = Side{c.q.data() + c.rlenL - 1,c.quc.data() + c.rlenL - 1,c.gL.data() + c.glenL - 1,c.gLa.data() + c.glenL - 1,c.roffset,c.goffset,true};
-    else sd = Side{c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
-    Replayer(l,sd,dpi,n).run(r.bestcL >= r.bestrL ? 1 : 2,r.bestrL,r.bestcL,ops,r.script_lenA);
+    /* 5' ends hand out the reversed list: written backwards, so the pairs pushed first are its tail */
+    if (c.end5) { l.start(sideL,0); sd = Side{c.q.data() + c.rlenL - 1,c.quc.data() + c.rlenL - 1,c.gL.data() + c.glenL - 1,c.gLa.data() + c.glenL - 1,c.roffset,c.goffset,true}; }
+    else { l.start(0,sideL); sd = Side{c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false}; }
+    Replayer(l,sd,n,c.end5).run(r.bestcL >= r.bestrL ? 1 : 2,r.bestrL,r.bestcL,ops,r.script_lenA);
     check_counts(count_mismatch,r,n);
     c.iout[1] = n.score; c.iout[2] = n.nmatches; c.iout[3] = n.nmismatches; c.iout[4] = n.nopens; c.iout[5] = n.nindels;
     if ((c.endalign == GMAPDP_QUERYEND_GAP || c.endalign == GMAPDP_BEST_LOCAL) && (n.nmatches + 1) < n.nmismatches) {
       c.iout[1] = 0; l.clear();
     } else {
+      /* leading indels of the list in push order */
+      const size_t sz = l.size();
       size_t k = 0;
-      while (k < l.size() && l[k].comp == COMP_INDEL) k++;	/* leading indels of the reversed list */
-      l.drop_front(k);
+      if (c.end5) { while (k < sz && l[sz - 1 - k].comp == COMP_INDEL) k++; l.drop_back(k); }
+      else { while (k < sz && l[k].comp == COMP_INDEL) k++; l.drop_front(k); }
     }
     bump(c.iout[0]);
     c.isnull = l.empty();
-    if (c.end5) l.reverse();
 
   } else if (c.mode == GMAPDP_GENOME) {
-    if (r.status != 0) { c.iout[3] = -100; c.isnull = true; return; }
+    if (r.status != 0) { c.iout[3] = -100; c.isnull = true; l.clear(); return; }
     const int rlength = c.rlenL, rev_roffset = c.roffset + rlength - 1;
     const int bestrL = r.bestrL, bestrR = r.bestrR, bestcL = r.bestcL, bestcR = r.bestcR;
     c.dout[0] = prob_at(c.lp,bestcL); c.dout[1] = prob_at(c.rp,bestcR);
@@ -679,13 +729,14 @@ static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, i
     c.iout[2] = c.goffsetR - (bestcR - 1);
     c.iout[8] = rev_roffset - (bestrR - 1);
     Counts n;
+    l.start(sideR,sideL + 1);
+    /* the right-hand side reversed (written backwards), the gap holder, the left-hand side */
     Side sr = {c.q.data() + rlength - 1,c.quc.data() + rlength - 1,c.gR.data() + c.glenR - 1,c.gRa.data() + c.glenR - 1,rev_roffset,c.goffsetR,true};
-    Replayer(l,sr,dpi,n).run(bestcR >= bestrR ? 1 : 2,bestrR,bestcR,ops,r.script_lenA);
-    l.reverse();
-    gmapdp_pair &gp = push_gapholder(l,(rev_roffset - bestrR) - (c.roffset + bestrL) + 1,c.iout[2] - c.iout[1] - 1);
+    Replayer(l,sr,n,true).run(bestcR >= bestrR ? 1 : 2,bestrR,bestcR,ops,r.script_lenA);
+    gmapdp_gapinfo &gp = push_gapholder(l,false,(rev_roffset - bestrR) - (c.roffset + bestrL) + 1,c.iout[2] - c.iout[1] - 1);
     gp.introntype = c.introntype_in; gp.donor_prob = c.dout[0]; gp.acceptor_prob = c.dout[1];
     Side sl = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
-    Replayer(l,sl,dpi,n).run(bestcL >= bestrL ? 1 : 2,bestrL,bestcL,ops + r.script_lenA,r.script_lenB);
+    Replayer(l,sl,n).run(bestcL >= bestrL ? 1 : 2,bestrL,bestcL,ops + r.script_lenA,r.script_lenB);
     check_counts(count_mismatch,r,n);
     c.iout[3] = n.score; c.iout[4] = n.nmatches; c.iout[5] = n.nmismatches; c.iout[6] = n.nopens; c.iout[7] = n.nindels;
     if (l.size() == 1) l.clear();
@@ -697,28 +748,31 @@ static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, i
     const int bestrL = r.bestrL, bestrR = r.bestrR, bestcL = r.bestcL, bestcR = r.bestcR;
     const int rev_goffset = c.goffset + c.glenL - 1;
     Counts n;
+    l.start(sideR,sideL + 2 * INSERT_PAIRS + 2);
     Side sr = {c.qR.data() + c.rlenR - 1,c.qRuc.data() + c.rlenR - 1,c.gR.data() + c.glenL - 1,c.gRa.data() + c.glenL - 1,c.roffsetR,rev_goffset,true};
-    Replayer(l,sr,dpi,n).run(bestcR >= bestrR ? 1 : 2,bestrR,bestcR,ops,r.script_lenA);
-    l.reverse();
+    Replayer(l,sr,n,true).run(bestcR >= bestrR ? 1 : 2,bestrR,bestcR,ops,r.script_lenA);
     const int queryjump = (c.roffsetR - bestrR) - (c.roffset + bestrL) + 1;
     const int genomejump = (rev_goffset - bestcR) - (c.goffset + bestcL) + 1;
     if (queryjump == INSERT_PAIRS && genomejump == INSERT_PAIRS) {
       for (int k = c.roffsetR - bestrR; k >= c.roffset + bestrL; k--)
-	push_pair(l,k,rev_goffset - bestcR + 1,c.q[k - c.roffset],COMP_SHORTGAP,' ',' ',dpi);
+	push_pair(l,false,k,rev_goffset - bestcR + 1,c.q[k - c.roffset],COMP_SHORTGAP,' ',' ');
       for (int k = rev_goffset - bestcR; k >= c.goffset + bestcL; k--)
-	push_pair(l,c.roffset + bestrL,k,' ',COMP_SHORTGAP,c.gL[k - c.goffset],c.gLa[k - c.goffset],dpi);
+	push_pair(l,false,c.roffset + bestrL,k,' ',COMP_SHORTGAP,c.gL[k - c.goffset],c.gLa[k - c.goffset]);
     } else {
-      push_gapholder(l,queryjump,genomejump);
+      push_gapholder(l,false,queryjump,genomejump);
       c.iout[2] = 1;
     }
     Side sl = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
-    Replayer(l,sl,dpi,n).run(bestcL >= bestrL ? 1 : 2,bestrL,bestcL,ops + r.script_lenA,r.script_lenB);
+    Replayer(l,sl,n).run(bestcL >= bestrL ? 1 : 2,bestrL,bestcL,ops + r.script_lenA,r.script_lenB);
     check_counts(count_mismatch,r,n);
     c.iout[1] = n.score;
     if (l.size() == 1) l.clear();
     bump(c.iout[0]);
     c.isnull = l.empty();
   }
+#if defined(__SSE2__) && !defined(GMAPDP_NO_NT_STORES)
+  _mm_sfence();		/* the records were written with non-temporal stores: visible before the call is marked done */
+#endif
 }
 
 static int replay_threads () {
@@ -955,17 +1009,30 @@ extern "C" int GmapDP_result (const gmapdp_batch *b, int id, int *iout, double *
   if (dout && c.mode == GMAPDP_GENOME) { dout[0] = c.dout[0]; dout[1] = c.dout[1]; }
   if (c.isnull || c.pairs.empty()) return -1;
   const int n = (int) c.pairs.size();
-  for (int k = 0; k < n && k < maxpairs; k++) pairs[k] = c.pairs[k];
+  for (int k = 0; k < n && k < maxpairs; k++) {		/* the compact records spelled out */
+    const gmapdp_cpair &s = c.pairs[k];
+    gmapdp_pair &p = pairs[k];
+    memset(&p,0,sizeof(p));
+    p.querypos = s.querypos; p.genomepos = s.genomepos; p.cdna = s.cdna; p.comp = s.comp; p.genome = s.genome; p.genomealt = s.genomealt;
+    if (s.gap >= 0) {
+      const gmapdp_gapinfo &g = c.pairs.gaps[s.gap];
+      p.gapp = 1; p.queryjump = g.queryjump; p.genomejump = g.genomejump; p.introntype = g.introntype;
+      p.donor_prob = g.donor_prob; p.acceptor_prob = g.acceptor_prob;
+    } else p.dynprogindex = c.dpi;
+  }
   return n;
 }
 
 /* zero-copy view of a completed call's pair list (head first); valid until the batch is cleared */
-extern "C" int GmapDP_result_view (const gmapdp_batch *b, int id, const int **iout, const double **dout, const gmapdp_pair **pairs) {
+extern "C" int GmapDP_result_view (const gmapdp_batch *b, int id, const int **iout, const double **dout, const gmapdp_cpair **pairs,
+				   const gmapdp_gapinfo **gaps, int *dynprogindex) {
   if (id < 0 || id >= (int) b->calls.size()) return -2;
   const Call &c = b->calls[id];
   if (!c.done) return -3;
   if (iout) *iout = c.iout;
   if (dout) *dout = c.dout;
+  if (dynprogindex) *dynprogindex = c.dpi;
+  if (gaps) *gaps = c.pairs.gaps.data();
   if (c.isnull || c.pairs.empty()) { if (pairs) *pairs = NULL; return -1; }
   if (pairs) *pairs = c.pairs.data();
   return (int) c.pairs.size();

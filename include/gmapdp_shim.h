@@ -46,6 +46,23 @@ typedef struct gmapdp_pair {
   double donor_prob, acceptor_prob;
 } gmapdp_pair;
 
+/* How the lists are stored and handed out without a copy (GmapDP_result_view): one 16-byte record per pair -- the fields
+ * that differ from pair to pair -- and, for the few gap holders of a list (Pairpool_push_gapholder, pairpool.c:375), an entry
+ * in a side table.  The other fields of a gmapdp_pair follow: gapp = (gap >= 0); an ordinary pair has queryjump =
+ * genomejump = introntype = 0, both probabilities 0.0 and the call's dynprogindex; a gap holder has querypos = genomepos =
+ * -1, blank chars, dynprogindex 0 and the jumps / introntype / probabilities of gaps[gap].  (A large batch writes ~10^9
+ * pairs: at 48 bytes each the host's memory bandwidth, not the GPU, set the end-to-end rate.) */
+typedef struct gmapdp_cpair {
+  int querypos, genomepos;
+  char cdna, comp, genome, genomealt;
+  int gap;			/* -1, or index into the call's gap table */
+} gmapdp_cpair;
+
+typedef struct gmapdp_gapinfo {
+  int queryjump, genomejump, introntype, pad_;
+  double donor_prob, acceptor_prob;
+} gmapdp_gapinfo;
+
 #define GMAPDP_UNSET (-999)
 
 /* Endalign_T, dynprog.h:27 */
@@ -132,8 +149,10 @@ int GmapDP_batch_complete (gmapdp_batch *b, const gmapdp_result *results, const 
 /* Returns the number of pairs (list head first), or -1 for the reference's NULL list.  If the list is longer than
  * maxpairs only maxpairs records are copied: compare the return value with maxpairs, or use GmapDP_result_view. */
 int GmapDP_result (const gmapdp_batch *b, int id, int *iout, double *dout, gmapdp_pair *pairs, int maxpairs);
-/* the same without a copy: pointers into the batch, valid until it is cleared */
-int GmapDP_result_view (const gmapdp_batch *b, int id, const int **iout, const double **dout, const gmapdp_pair **pairs);
+/* the same without a copy: pointers into the batch, valid until it is cleared; *dynprogindex = the index the call's
+   ordinary pairs carry */
+int GmapDP_result_view (const gmapdp_batch *b, int id, const int **iout, const double **dout, const gmapdp_cpair **pairs,
+			const gmapdp_gapinfo **gaps, int *dynprogindex);
 /* device-side view of one call (NULL if it never reached the device) */
 const gmapdp_result *GmapDP_device_result (const gmapdp_batch *b, int id);
 
