@@ -9,7 +9,7 @@ LIB = os.path.join(CSRC, "libgmapdp_b200.so")
 # repeated with every tie resolved on the spot) runs on ordinary boxes; loaded only by the GPU parity tests
 LIB_TIECAP1 = os.path.join(CSRC, "libgmapdp_b200_tiecap1.so")
 SOURCES = ["gmapdp_kernels.cu", "gmapdp_shim.cpp", "gmapdp_stream.cpp", "gmapchain_kernels.cu", "gmapchain_shim.cpp"]
-HEADERS = ["gmapdp_layout.h", "gmapdp_tables.h", "gmapdp_internal.h", "../../include/gmapdp_b200.h", "../../include/gmapdp_shim.h",
+HEADERS = ["gmapdp_layout.h", "gmapdp_tables.h", "gmapdp_internal.h", "gmapdp_genome.h", "../../include/gmapdp_b200.h", "../../include/gmapdp_shim.h",
            "../../include/gmapchain_b200.h", "../../include/gmapdp_stream.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

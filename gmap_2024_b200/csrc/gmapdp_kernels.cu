@@ -28,11 +28,13 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <mutex>
 #include <thread>
 #include <chrono>
 #include <algorithm>
 
 #include "gmapdp_layout.h"
+#include "gmapdp_genome.h"
 #include "gmapdp_tables.h"
 
 #define WARPS_PER_BLOCK 4
@@ -152,6 +154,20 @@ struct GenCtx {
   const short *dgL, *dgR;		/* main-diagonal scores of the upper fills */
   const double *lp, *rp;
   int rlength, lim;
+  /* MaxEnt on the device (GMAPDP_G_PROBS): entry c of the left / right array is the probability of kind lkind / rkind at
+     coordinate lpos0 + lstep c / rpos0 + rstep c, for c < glength - 1, else 0 (the arrays of dynprog_genome.c:970-1061) */
+  bool devp;
+  GdpGenome genome; const double *me;
+  uint32_t lpos0, rpos0, chroffset;
+  int lstep, rstep, lkind, rkind, nlp, nrp;
+  __device__ __forceinline__ double lprob (int c) const {
+    if (!devp) return lp[c];
+    return (c >= 0 && c < nlp) ? gdp_maxent_prob(lkind,genome,me,lpos0 + (uint32_t) (lstep * c),chroffset) : 0.0;
+  }
+  __device__ __forceinline__ double rprob (int c) const {
+    if (!devp) return rp[c];
+    return (c >= 0 && c < nrp) ? gdp_maxent_prob(rkind,genome,me,rpos0 + (uint32_t) (rstep * c),chroffset) : 0.0;
+  }
   uint32_t it0, it1;			/* intron scores as a byte table: byte k+1 = score of bit k, byte 0 = 0 */
 };
 
@@ -165,9 +181,9 @@ __device__ __forceinline__ int gen_points (const GenCtx &g, int di) {
 /* probability sum of the candidate behind a key */
 __device__ __forceinline__ double gen_key_prob (const GenCtx &g, int key) {
   const int rL = key >> 15, seg = (key >> 12) & 7, col = key & 4095;
-  if (seg == 0) return g.lp[rL] + g.rp[g.rlength - rL];
-  if (seg <= 2) return g.lp[rL] + g.rp[col];
-  return g.lp[col] + g.rp[g.rlength - rL];
+  if (seg == 0) return g.lprob(rL) + g.rprob(g.rlength - rL);
+  if (seg <= 2) return g.lprob(rL) + g.rprob(col);
+  return g.lprob(col) + g.rprob(g.rlength - rL);
 }
 
 __device__ __forceinline__ void gen_tie (const GenCtx &g, GenBest &b, int key) {	/* same score as the lane's best */
@@ -1229,7 +1245,7 @@ __device__ int bridge_genome_finish (const gmapdp_box &b, const GenCtx &g, GenBe
     if (score > gb.s) { gb.s = score; gb.key = key; gb.p = -1.0; }
     else if (score == gb.s) gen_tie(g,gb,key);
     if (scoreI > 0) {
-      const double ps = g.lp[rL] + g.rp[rR];
+      const double ps = g.lprob(rL) + g.rprob(rR);
       if (ps > dnp) { dns = score; dnp = ps; dnkey = key; }
     }
   }
@@ -1419,6 +1435,8 @@ struct KernelArgs {
   int smem_cols;		/* boundary-row capacity per warp */
   uint32_t one;			/* the value 1 (see add_if) */
   const GdpTables *tables;
+  GdpGenome genome;		/* resident genome (blocks == NULL: none attached) */
+  const double *maxent;		/* packed MaxEnt tables (gmapdp_genome.h) */
 };
 
 /* KIND: 0 single gaps (full fill), 1 end5/end3 (E-only fills + endpoint search), 2 genome gaps, 3 cdna gaps */
@@ -1452,6 +1470,24 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
   uint16_t *gselR = reinterpret_cast<uint16_t *>(bytes); bytes += gdp_align16(2 * (size_t) (b.glenR + 2));
   short *dgL = reinterpret_cast<short *>(bytes); bytes += gdp_align16(2 * (size_t) (b.rlenL + 2));
   short *dgR = reinterpret_cast<short *>(bytes); bytes += gdp_align16(2 * (size_t) (b.rlenR + 2));
+  /* segments of resident-genome boxes: decoded once into the workspace (Genome_get_segment_right / _left, genome.c:11023,
+     :11079), everything downstream reads them like uploaded ones; genomealt == genome */
+  if (b.gflags & GMAPDP_G_SEG_L) {
+    uint8_t *seg = bytes; bytes += gdp_align16(b.glenL + 2);
+    const int dir = (b.gflags & GMAPDP_G_NEG_L) ? -1 : +1;
+    const bool left = (b.gflags & GMAPDP_G_LEFT_L) != 0;
+    for (int i = lane; i < b.glenL; i += 32) seg[i] = (uint8_t) gdp_segment_char(ka.genome,b.gL_off,dir,i,left ? b.chroffset : 0u,left ? 0xffffffffu : b.chrhigh);
+    L.G = L.Ga = seg;
+    if (!twosided || !(b.gflags & GMAPDP_G_SEG_R)) { R.G = R.Ga = seg; }		/* single / end / cdna: one segment */
+  }
+  if (twosided && (b.gflags & GMAPDP_G_SEG_R)) {
+    uint8_t *seg = bytes; bytes += gdp_align16(b.glenR + 2);
+    const int dir = (b.gflags & GMAPDP_G_NEG_R) ? -1 : +1;
+    const bool left = (b.gflags & GMAPDP_G_LEFT_R) != 0;
+    for (int i = lane; i < b.glenR; i += 32) seg[i] = (uint8_t) gdp_segment_char(ka.genome,b.gR_off,dir,i,left ? b.chroffset : 0u,left ? 0xffffffffu : b.chrhigh);
+    R.G = R.Ga = seg;
+  }
+  if (b.gflags & (GMAPDP_G_SEG_L | GMAPDP_G_SEG_R)) __syncwarp();
   uint32_t *wp = reinterpret_cast<uint32_t *>(bytes);
   uint32_t *stage = wp; wp += b.rlenL + b.glenL + b.rlenR + b.glenR + 16;
 
@@ -1595,6 +1631,11 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 	gc.ldi = ldi; gc.rdi = rdi; gc.dgL = dgL; gc.dgR = dgR;
 	gc.lp = ka.probs + b.probL_off; gc.rp = ka.probs + b.probR_off;
 	gc.rlength = b.rlenL; gc.lim = b.offdiff;
+	gc.devp = (b.gflags & GMAPDP_G_PROBS) != 0;
+	gc.genome = ka.genome; gc.me = ka.maxent; gc.chroffset = b.chroffset;
+	gc.lpos0 = b.probL_off; gc.rpos0 = b.probR_off;
+	gc.lstep = (b.gflags & GMAPDP_G_PSTEP_NEG_L) ? -1 : +1; gc.rstep = (b.gflags & GMAPDP_G_PSTEP_NEG_R) ? -1 : +1;
+	gc.lkind = b.probkindL; gc.rkind = b.probkindR; gc.nlp = b.glenL - 1; gc.nrp = b.glenR - 1;
 	gc.it0 = ((uint32_t) isc[0] << 8) | ((uint32_t) isc[1] << 16) | ((uint32_t) isc[2] << 24);
 	gc.it1 = (uint32_t) isc[3] | ((uint32_t) isc[4] << 8) | ((uint32_t) isc[5] << 16);
 	GenBest gb; gb.s = NEG; gb.key = -1; gb.cnt = 0; gb.p = 0.0; gb.ties = wp + lane; wp += GEN_TIECAP * 32;
@@ -1721,6 +1762,12 @@ gmapdp_dp_kernel_any (KernelArgs ka) {
 #define GDP_NK GDP_NKINDS
 static inline int kind_of (int mode) { return mode == GMAPDP_SINGLE ? 0 : (mode == GMAPDP_GENOME ? 2 : (mode == GMAPDP_CDNA ? 3 : 1)); }
 
+struct gmapdp_genome {
+  int device;
+  uint32_t *d_blocks; size_t nwords;
+  double *d_maxent;
+};
+
 struct gmapdp_ctx {
   int device, sm_count, grid, max_smem;
   int kgrid[GDP_NK], ksmem_cols[GDP_NK]; size_t kws_words[GDP_NK];	/* per kernel kind: 0 single, 1 end, 2 genome, 3 cdna */
@@ -1731,6 +1778,7 @@ struct gmapdp_ctx {
   std::vector<int> chunk_count;		/* [chunk][kind] boxes */
   cudaStream_t stream, copy_stream;
   std::vector<cudaEvent_t> chunk_events, chunk_done;
+  const gmapdp_genome *genome = NULL;		/* attached resident genome + MaxEnt tables */
   cudaStream_t d2h_stream = 0;
   unsigned long long *h_cursors = NULL; size_t cap_cursors = 0;		/* pinned: the script cursor after each chunk */
   cudaEvent_t ev0, ev1;
@@ -1941,8 +1989,10 @@ static inline bool box_ok (const gmapdp_box &b) {
 
 /* bytes a box makes the end-to-end path upload (sequences once, alt twins are shared; MaxEnt doubles) */
 static inline uint32_t box_upload_bytes (const gmapdp_box &x) {
-  size_t acc = (size_t) x.rlenL + x.rlenR + x.glenL + x.glenR;
-  if (x.mode == GMAPDP_GENOME) acc += 8 * ((size_t) x.glenL + x.glenR);
+  size_t acc = (size_t) x.rlenL + x.rlenR;
+  if (!(x.gflags & GMAPDP_G_SEG_L)) acc += x.glenL;
+  if (!(x.gflags & GMAPDP_G_SEG_R)) acc += x.glenR;
+  if (x.mode == GMAPDP_GENOME && !(x.gflags & GMAPDP_G_PROBS)) acc += 8 * ((size_t) x.glenL + x.glenR);
   return (uint32_t) acc;
 }
 
@@ -1964,7 +2014,7 @@ static int plan_scan (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, std:
       const int i0 = (int) ((long long) nboxes * t / nthreads), i1 = (int) ((long long) nboxes * (t + 1) / nthreads);
       for (int i = i0; i < i1; i++) {
 	const gmapdp_box &b = boxes[i];
-	if (!box_ok(b)) { pt.bad = true; return; }
+	if (!box_ok(b) || (b.gflags && !ctx->genome)) { pt.bad = true; return; }
 	const int kind = kind_of(b.mode);
 	pt.ws[kind] = std::max(pt.ws[kind],gdp_ws_words(b));
 	pt.script += (size_t) b.rlenL + b.glenL + 4;
@@ -2075,6 +2125,7 @@ static int launch_chunk (gmapdp_ctx *ctx, int first, const int *cnt, bool timed 
     ka.script = ctx->d_script; ka.script_cap = ctx->cap_script; ka.script_cursor = ctx->d_cursor;
     ka.queue = ctx->d_queue + kind; ka.ws = ctx->d_kws[kind]; ka.ws_words = ctx->kws_words[kind];
     ka.smem_cols = ctx->ksmem_cols[kind]; ka.tables = ctx->d_tables; ka.one = 1u;
+    ka.genome.blocks = ctx->genome ? ctx->genome->d_blocks : NULL; ka.genome.nwords = ctx->genome ? ctx->genome->nwords : 0; ka.maxent = ctx->genome ? ctx->genome->d_maxent : NULL;
     const size_t smem = kind_smem(ctx,kind);
     const int grid = std::max(1,std::min(ctx->kgrid[kind],(count + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
     CK(cudaMemsetAsync(ctx->d_queue + kind,0,sizeof(int),st));
@@ -2100,6 +2151,92 @@ static int fork_streams (gmapdp_ctx *ctx, cudaEvent_t ev) {
   }
   return GMAPDP_OK;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Resident genome + MaxEnt tables (include/gmapdp_b200.h, csrc/gmapdp_genome.h)
+ * ---------------------------------------------------------------------------------------------- */
+static void pack_maxent (const gmapdp_maxent_tables *t, std::vector<double> &v) {
+  v.assign(GDP_ME_NDOUBLES,0.0);
+  const double *big[12] = {t->donor_plus,t->acc1_plus,t->acc2_plus,t->acc3_plus,t->acc467_plus,t->acc589_plus,
+			   t->donor_minus,t->acc1_minus,t->acc2_minus,t->acc3_minus,t->acc467_minus,t->acc589_minus};
+  for (int k = 0; k < 12; k++) memcpy(&v[(size_t) k * 16384],big[k],16384 * sizeof(double));
+  memcpy(&v[GDP_ME_DONOR_DI_P],t->donor_di_plus,16 * sizeof(double)); memcpy(&v[GDP_ME_ACC_DI_P],t->acc_di_plus,16 * sizeof(double));
+  memcpy(&v[GDP_ME_DONOR_DI_M],t->donor_di_minus,16 * sizeof(double)); memcpy(&v[GDP_ME_ACC_DI_M],t->acc_di_minus,16 * sizeof(double));
+}
+
+extern "C" int gmapdp_genome_create (gmapdp_genome **out, int device, const uint32_t *blocks, size_t nwords, const gmapdp_maxent_tables *maxent) {
+  *out = NULL;
+  if (!blocks || nwords == 0 || !maxent) return GMAPDP_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return GMAPDP_ERR_CUDA;
+  gmapdp_genome *g = new gmapdp_genome();
+  g->device = device; g->d_blocks = NULL; g->d_maxent = NULL; g->nwords = nwords;
+  std::vector<double> packed;
+  pack_maxent(maxent,packed);
+  if (cudaMalloc((void **) &g->d_blocks,nwords * sizeof(uint32_t)) != cudaSuccess ||
+      cudaMalloc((void **) &g->d_maxent,packed.size() * sizeof(double)) != cudaSuccess ||
+      cudaMemcpy(g->d_blocks,blocks,nwords * sizeof(uint32_t),cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(g->d_maxent,packed.data(),packed.size() * sizeof(double),cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(g->d_blocks); cudaFree(g->d_maxent); delete g;
+    return GMAPDP_ERR_CUDA;
+  }
+  *out = g;
+  return GMAPDP_OK;
+}
+
+extern "C" void gmapdp_genome_destroy (gmapdp_genome *g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  cudaFree(g->d_blocks); cudaFree(g->d_maxent);
+  delete g;
+}
+
+extern "C" int gmapdp_genome_attach (gmapdp_ctx *ctx, const gmapdp_genome *g) {
+  if (!ctx) return GMAPDP_ERR_ARG;
+  if (g && g->device != ctx->device) { ctx->err = "genome lives on another device"; return GMAPDP_ERR_ARG; }
+  ctx->genome = g;
+  return GMAPDP_OK;
+}
+
+extern "C" int gmapdp_genome_host_char (const uint32_t *blocks, size_t nwords, uint32_t pos) {
+  GdpGenome g; g.blocks = blocks; g.nwords = nwords;
+  return gdp_genome_char(g,pos);
+}
+
+extern "C" double gmapdp_maxent_host_prob (const uint32_t *blocks, size_t nwords, const gmapdp_maxent_tables *maxent, int kind, uint32_t splice_pos, uint32_t chroffset) {
+  /* the packed copy is built once per table set (callers pass the same one for the life of the process) */
+  static std::mutex mu;
+  static const gmapdp_maxent_tables *cached = NULL;
+  static std::vector<double> packed;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cached != maxent) { pack_maxent(maxent,packed); cached = maxent; }
+  }
+  GdpGenome g; g.blocks = blocks; g.nwords = nwords;
+  return gdp_maxent_prob(kind,g,packed.data(),splice_pos,chroffset);
+}
+
+__global__ void gmapdp_maxent_kernel (GdpGenome g, const double *me, const int *kind, const uint32_t *pos, uint32_t chroffset, int n, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = gdp_maxent_prob(kind[i],g,me,pos[i],chroffset);
+}
+
+extern "C" int gmapdp_maxent_eval (gmapdp_ctx *ctx, const int *kind, const uint32_t *pos, uint32_t chroffset, int n, double *probs) {
+  if (!ctx || !ctx->genome || n < 0) { if (ctx) ctx->err = "no genome attached"; return GMAPDP_ERR_ARG; }
+  if (n == 0) return GMAPDP_OK;
+  CK(cudaSetDevice(ctx->device));
+  int *dk = NULL; uint32_t *dp = NULL; double *dout = NULL;
+  CK(cudaMalloc((void **) &dk,(size_t) n * sizeof(int))); CK(cudaMalloc((void **) &dp,(size_t) n * sizeof(uint32_t))); CK(cudaMalloc((void **) &dout,(size_t) n * sizeof(double)));
+  CK(cudaMemcpy(dk,kind,(size_t) n * sizeof(int),cudaMemcpyHostToDevice)); CK(cudaMemcpy(dp,pos,(size_t) n * sizeof(uint32_t),cudaMemcpyHostToDevice));
+  GdpGenome g; g.blocks = ctx->genome->d_blocks; g.nwords = ctx->genome->nwords;
+  gmapdp_maxent_kernel<<<(n + 127) / 128,128,0,ctx->stream>>>(g,ctx->genome->d_maxent,dk,dp,chroffset,n,dout);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaMemcpyAsync(probs,dout,(size_t) n * sizeof(double),cudaMemcpyDeviceToHost,ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dk); cudaFree(dp); cudaFree(dout);
+  return GMAPDP_OK;
+}
+
 extern "C" int gmapdp_upload (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes,
 			      const uint8_t *seqpool, size_t seqbytes, const double *probpool, size_t nprobs) {
   if (!ctx || nboxes < 0 || (nboxes > 0 && (!boxes || !seqpool))) { if (ctx) ctx->err = "bad argument"; return GMAPDP_ERR_ARG; }
@@ -2259,8 +2396,10 @@ extern "C" int gmapdp_run_batch_chunks (gmapdp_ctx *ctx, const gmapdp_box *boxes
       const gmapdp_box &x = boxes[i];
       const size_t offs[6] = {x.qL_off, x.qR_off, x.gL_off, x.gLalt_off, x.gR_off, x.gRalt_off};
       const size_t lens[6] = {(size_t) x.rlenL, (size_t) x.rlenR, (size_t) x.glenL, (size_t) x.glenL, (size_t) x.glenR, (size_t) x.glenR};
-      for (int j = 0; j < 6; j++) { slo = std::min(slo,offs[j]); shi = std::max(shi,offs[j] + lens[j]); }
-      if (x.mode == GMAPDP_GENOME) {
+      /* segments that come from the resident genome are coordinates, not pool offsets */
+      const bool inpool[6] = {true, true, !(x.gflags & GMAPDP_G_SEG_L), !(x.gflags & GMAPDP_G_SEG_L), !(x.gflags & GMAPDP_G_SEG_R), !(x.gflags & GMAPDP_G_SEG_R)};
+      for (int j = 0; j < 6; j++) if (inpool[j]) { slo = std::min(slo,offs[j]); shi = std::max(shi,offs[j] + lens[j]); }
+      if (x.mode == GMAPDP_GENOME && !(x.gflags & GMAPDP_G_PROBS)) {
 	plo = std::min(plo,std::min((size_t) x.probL_off,(size_t) x.probR_off));
 	phi = std::max(phi,std::max((size_t) x.probL_off + x.glenL,(size_t) x.probR_off + x.glenR));
       }
@@ -2423,6 +2562,7 @@ int gdp_flight_launch (GdpFlight *f, int n, size_t poolbytes, size_t script_need
   ka.script_cursor = reinterpret_cast<unsigned long long *>(f->d_in + 8);		/* ... and script cursor, zeroed by the upload */
   ka.ws = ctx->d_kws[0]; ka.ws_words = wsw;
   ka.smem_cols = cols; ka.tables = ctx->d_tables; ka.one = 1u;
+  ka.genome.blocks = ctx->genome ? ctx->genome->d_blocks : NULL; ka.genome.nwords = ctx->genome ? ctx->genome->nwords : 0; ka.maxent = ctx->genome ? ctx->genome->d_maxent : NULL;
   gmapdp_dp_kernel_any<<<grid,BLOCK_THREADS,smem,s0>>>(ka);
   FCK(cudaGetLastError());
   ctx->launches++;

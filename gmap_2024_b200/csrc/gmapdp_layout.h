@@ -133,6 +133,9 @@ GDP_HD size_t gdp_ws_words (const gmapdp_box &b) {
   size_t bytes = gdp_align16(b.rlenL + 2) + gdp_align16(b.rlenR + 2) + 2 * gdp_align16(b.glenL + 2) + 2 * gdp_align16(b.glenR + 2);
   /* ready-made PRMT selectors (uint16) of the same positions, read 16 at a time by the interior steps of the E-only fills */
   bytes += gdp_align16(2 * (size_t) (b.rlenL + 2)) + gdp_align16(2 * (size_t) (b.rlenR + 2)) + gdp_align16(2 * (size_t) (b.glenL + 2)) + gdp_align16(2 * (size_t) (b.glenR + 2));
+  /* segments decoded from the resident genome */
+  if (b.gflags & GMAPDP_G_SEG_L) bytes += gdp_align16(b.glenL + 2);
+  if (b.gflags & GMAPDP_G_SEG_R) bytes += gdp_align16(b.glenR + 2);
   /* genome gaps: main-diagonal scores of the two upper fills (int16) */
   bytes += gdp_align16(2 * (size_t) (b.rlenL + 2)) + gdp_align16(2 * (size_t) (b.rlenR + 2));
   w += bytes / 4;

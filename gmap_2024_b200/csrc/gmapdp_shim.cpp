@@ -258,6 +258,8 @@ struct Call {
   int iout[10]; double dout[2];
   Pushed pairs;			/* head first */
   int dpi = 0;			/* dynprogindex of the call's ordinary pairs */
+  bool devp = false; gmapdp_coords co;	/* genome gap whose probabilities come from MaxEnt over the resident genome */
+  const gmapdp_batch *owner = NULL;
   /* copies of the caller's sequences: forward arrays */
   std::string q, quc, qR, qRuc, gL, gLa, gR, gRa;
   std::vector<double> lp, rp;
@@ -280,6 +282,9 @@ struct gmapdp_batch {
   std::vector<int> box_call;
   std::vector<uint8_t> seqpool;
   std::vector<double> probpool;
+  /* resident genome (GmapDP_batch_genome) and the coordinates of the next queued call (GmapDP_batch_next_coords) */
+  const uint32_t *g_blocks = NULL; size_t g_nwords = 0; const gmapdp_maxent_tables *g_tables = NULL;
+  gmapdp_coords next_co, cur_co; bool has_next_co = false, has_cur_co = false;
   gmapdp_result *results = NULL; size_t nresults = 0;	/* pinned */
   uint32_t *script = NULL; size_t script_cap = 0;	/* pinned */
   size_t script_used = 0;
@@ -338,7 +343,55 @@ static void unpin (gmapdp_batch *b, bool release_buffers) {
   }
 }
 /* a call queued after the pools were page-locked may move them: drop the registration first */
-static inline void begin_queue (gmapdp_batch *b) { if (b->pinned) unpin(b,false); b->uploaded = false; }
+static inline void begin_queue (gmapdp_batch *b) {
+  if (b->pinned) unpin(b,false);
+  b->uploaded = false;
+  /* coordinates announced by GmapDP_batch_next_coords belong to this call, whatever becomes of it */
+  b->has_cur_co = b->has_next_co; b->cur_co = b->next_co; b->has_next_co = false;
+}
+
+/* Resident-genome form of a box: the genomic segment(s) as coordinates (and, for genome gaps, the MaxEnt probabilities
+   as coordinates of their first entries) instead of bytes in the pools.  Only when the call came with coordinates and
+   has no alternate genome; returns false otherwise (the caller then uploads the characters as usual). */
+static bool take_coords (gmapdp_batch *b, Call &c, gmapdp_box &x, bool twosegments) {
+  if (!b->has_cur_co || !b->g_blocks) return false;
+  if (c.gLa != c.gL || (twosegments && c.gRa != c.gR)) return false;
+  const gmapdp_coords &co = b->cur_co;
+  x.chroffset = co.chroffset; x.chrhigh = co.chrhigh;
+  x.gL_off = x.gLalt_off = co.gposL;
+  x.gflags |= GMAPDP_G_SEG_L | (co.negL ? GMAPDP_G_NEG_L : 0) | (co.leftL ? GMAPDP_G_LEFT_L : 0);
+  if (twosegments) {
+    x.gR_off = x.gRalt_off = co.gposR;
+    x.gflags |= GMAPDP_G_SEG_R | (co.negR ? GMAPDP_G_NEG_R : 0) | (co.leftR ? GMAPDP_G_LEFT_R : 0);
+  }
+  if (c.devp) {
+    x.gflags |= GMAPDP_G_PROBS | (co.probnegL ? GMAPDP_G_PSTEP_NEG_L : 0) | (co.probnegR ? GMAPDP_G_PSTEP_NEG_R : 0);
+    x.probL_off = co.probposL; x.probR_off = co.probposR;
+    x.probkindL = (uint8_t) co.probkindL; x.probkindR = (uint8_t) co.probkindR;
+  }
+  return true;
+}
+
+/* entry k of a genome gap's left / right probability array (0.0 beyond glength - 2, as in the calloc'ed arrays of
+   dynprog_genome.c:970-1061) */
+static double call_prob (const Call &c, bool right, int k) {
+  if (!c.devp) return prob_at(right ? c.rp : c.lp,k);
+  const int n = (right ? c.glenR : c.glenL) - 1;
+  if (k < 0 || k >= n) return 0.0;
+  const gmapdp_coords &co = c.co;
+  const uint32_t pos = right ? (co.probnegR ? co.probposR - (uint32_t) k : co.probposR + (uint32_t) k)
+			     : (co.probnegL ? co.probposL - (uint32_t) k : co.probposL + (uint32_t) k);
+  return gmapdp_maxent_host_prob(c.owner->g_blocks,c.owner->g_nwords,c.owner->g_tables,right ? co.probkindR : co.probkindL,pos,co.chroffset);
+}
+
+extern "C" int GmapDP_batch_genome (gmapdp_batch *b, const uint32_t *blocks, size_t nwords, const gmapdp_maxent_tables *tables) {
+  b->g_blocks = blocks; b->g_nwords = nwords; b->g_tables = tables;
+  return GMAPDP_OK;
+}
+extern "C" void GmapDP_batch_next_coords (gmapdp_batch *b, const gmapdp_coords *co) {
+  if (co) { b->next_co = *co; b->has_next_co = true; } else b->has_next_co = false;
+}
+
 extern "C" void GmapDP_batch_clear (gmapdp_batch *b) {
   unpin(b,/*release_buffers*/false);		/* result / script buffers are reused by the next batch */
   b->calls.clear(); b->boxes.clear(); b->box_call.clear(); b->seqpool.clear(); b->probpool.clear();
@@ -411,8 +464,11 @@ extern "C" int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char 
   x.mismatchtype = (int8_t) mt; x.open = (int8_t) (b->user_dynprog ? b->user_open : opens[qual]); x.extend = (int8_t) (b->user_dynprog ? b->user_extend : extends[qual]);
   x.lbandL = x.lbandR = (int16_t) lband; x.ubandL = x.ubandR = (int16_t) uband;
   x.qL_off = x.qR_off = b->add_bytes(c.quc.data(),rlength);
-  x.gL_off = x.gR_off = b->add_bytes(c.gL.data(),glength);
-  x.gLalt_off = x.gRalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
+  if (take_coords(b,c,x,false)) x.gR_off = x.gRalt_off = x.gL_off;
+  else {
+    x.gL_off = x.gR_off = b->add_bytes(c.gL.data(),glength);
+    x.gLalt_off = x.gRalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
+  }
   add_cells(b,gdp_cells_full(rlength,glength,lband,uband),use8,true);
   c.box = (int) b->boxes.size(); c.queued();
   b->boxes.push_back(x); b->box_call.push_back(id);
@@ -484,8 +540,11 @@ static int end_gap (gmapdp_batch *b, bool end5, int dynprogindex, const char *rs
   x.mismatchtype = (int8_t) mt; x.open = (int8_t) (b->user_dynprog ? b->user_open : opens[qual]); x.extend = (int8_t) (b->user_dynprog ? b->user_extend : extends[qual]);
   x.lbandL = x.lbandR = (int16_t) lband; x.ubandL = x.ubandR = (int16_t) uband;
   x.qL_off = x.qR_off = b->add_bytes(c.quc.data(),rlength);
-  x.gL_off = x.gR_off = b->add_bytes(c.gL.data(),glength);
-  x.gLalt_off = x.gRalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
+  if (take_coords(b,c,x,false)) x.gR_off = x.gRalt_off = x.gL_off;
+  else {
+    x.gL_off = x.gR_off = b->add_bytes(c.gL.data(),glength);
+    x.gLalt_off = x.gRalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
+  }
   x.revmask = end5 ? 1 : 0;
   add_cells(b,gdp_cells_tri(rlength,glength,uband) + gdp_cells_tri(glength,rlength,lband),use8);
   c.box = (int) b->boxes.size(); c.queued();
@@ -541,8 +600,13 @@ extern "C" int GmapDP_genome_gap (gmapdp_batch *b, int dynprogindex, const char 
   c.q.assign(rsequence,rlength); c.quc.assign(rsequenceuc,rlength);
   c.gL.assign(gsequenceL,glengthL); c.gLa.assign(gsequenceL_alt,glengthL);
   c.gR.assign(rev_gsequenceR,glengthR); c.gRa.assign(rev_gsequenceR_alt,glengthR);
-  c.lp.assign(left_probabilities,left_probabilities + std::max(glengthL - 1,0));
-  c.rp.assign(right_probabilities,right_probabilities + std::max(glengthR - 1,0));
+  c.owner = b;
+  if (b->has_cur_co && b->cur_co.probs && b->g_blocks && b->g_tables && gsequenceL_alt && strncmp(gsequenceL,gsequenceL_alt,glengthL) == 0 && strncmp(rev_gsequenceR,rev_gsequenceR_alt,glengthR) == 0) { c.devp = true; c.co = b->cur_co; }
+  else {
+    if (!left_probabilities || !right_probabilities) { b->err = "GmapDP_genome_gap: no probability arrays and no resident genome"; c.done = true; *tbscore = NEG_INFINITY_32; return id; }
+    c.lp.assign(left_probabilities,left_probabilities + std::max(glengthL - 1,0));
+    c.rp.assign(right_probabilities,right_probabilities + std::max(glengthR - 1,0));
+  }
   c.rlenL = rlength; c.glenL = glengthL; c.glenR = glengthR; c.roffset = roffset; c.goffset = goffsetL; c.goffsetR = rev_goffsetR;
   const int rev_roffset = roffset + rlength - 1;
   const GdpHostTables &T = tables();
@@ -571,7 +635,7 @@ extern "C" int GmapDP_genome_gap (gmapdp_batch *b, int dynprogindex, const char 
     const int finalscore = halfp ? bestscore - bestscoreI / 2 : bestscore;
     bool result = finalscore > 0;
     if (result) {
-      c.dout[0] = prob_at(c.lp,bestrL); c.dout[1] = prob_at(c.rp,bestrR);		/* get_splicesite_probs at (bestrL, bestrR) */
+      c.dout[0] = call_prob(c,false,bestrL); c.dout[1] = call_prob(c,true,bestrR);		/* get_splicesite_probs at (bestrL, bestrR) */
       if (c.dout[0] < 0.90 || c.dout[1] < 0.90) result = false;
     }
     *tbscore = *nmatches = *nmismatches = 0;
@@ -607,12 +671,16 @@ extern "C" int GmapDP_genome_gap (gmapdp_batch *b, int dynprogindex, const char 
   x.cdna_direction = (int8_t) cdna_direction;
   x.lbandL = (int16_t) lbandL; x.ubandL = (int16_t) ubandL; x.lbandR = (int16_t) lbandR; x.ubandR = (int16_t) ubandR;
   x.qL_off = x.qR_off = b->add_bytes(c.quc.data(),rlength);
-  x.gL_off = b->add_bytes(c.gL.data(),glengthL);
-  x.gLalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glengthL);
-  x.gR_off = b->add_bytes(c.gR.data(),glengthR);
-  x.gRalt_off = (c.gRa == c.gR) ? x.gR_off : b->add_bytes(c.gRa.data(),glengthR);
-  x.probL_off = (uint32_t) b->probpool.size(); b->probpool.insert(b->probpool.end(),c.lp.begin(),c.lp.end()); b->probpool.push_back(0.0);
-  x.probR_off = (uint32_t) b->probpool.size(); b->probpool.insert(b->probpool.end(),c.rp.begin(),c.rp.end()); b->probpool.push_back(0.0);
+  if (!take_coords(b,c,x,true)) {
+    x.gL_off = b->add_bytes(c.gL.data(),glengthL);
+    x.gLalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glengthL);
+    x.gR_off = b->add_bytes(c.gR.data(),glengthR);
+    x.gRalt_off = (c.gRa == c.gR) ? x.gR_off : b->add_bytes(c.gRa.data(),glengthR);
+  }
+  if (!c.devp) {
+    x.probL_off = (uint32_t) b->probpool.size(); b->probpool.insert(b->probpool.end(),c.lp.begin(),c.lp.end()); b->probpool.push_back(0.0);
+    x.probR_off = (uint32_t) b->probpool.size(); b->probpool.insert(b->probpool.end(),c.rp.begin(),c.rp.end()); b->probpool.push_back(0.0);
+  }
   x.offdiff = rev_goffsetR - goffsetL;
   x.revmask = 2;
   add_cells(b,gdp_cells_tri(rlength,glengthL,ubandL) + gdp_cells_tri(glengthL,rlength,lbandL) +
@@ -662,10 +730,13 @@ extern "C" int GmapDP_cdna_gap (gmapdp_batch *b, int dynprogindex,
   x.lbandL = (int16_t) lbandL; x.ubandL = (int16_t) ubandL; x.lbandR = (int16_t) lbandR; x.ubandR = (int16_t) ubandR;
   x.qL_off = b->add_bytes(c.quc.data(),rlengthL);
   x.qR_off = b->add_bytes(c.qRuc.data(),rlengthR);
-  x.gL_off = b->add_bytes(c.gL.data(),glength);
-  x.gLalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
-  x.gR_off = (c.gR == c.gL) ? x.gL_off : b->add_bytes(c.gR.data(),glength);
-  x.gRalt_off = (c.gRa == c.gR) ? x.gR_off : b->add_bytes(c.gRa.data(),glength);
+  if (c.gR == c.gL && take_coords(b,c,x,false)) x.gR_off = x.gRalt_off = x.gL_off;
+  else {
+    x.gL_off = b->add_bytes(c.gL.data(),glength);
+    x.gLalt_off = (c.gLa == c.gL) ? x.gL_off : b->add_bytes(c.gLa.data(),glength);
+    x.gR_off = (c.gR == c.gL) ? x.gL_off : b->add_bytes(c.gR.data(),glength);
+    x.gRalt_off = (c.gRa == c.gR) ? x.gR_off : b->add_bytes(c.gRa.data(),glength);
+  }
   x.offdiff = rev_roffsetR - roffsetL;
   x.revmask = 2;
   add_cells(b,gdp_cells_tri(rlengthL,glength,ubandL) + gdp_cells_tri(glength,rlengthL,lbandL) +
@@ -724,7 +795,7 @@ static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, i
     if (r.status != 0) { c.iout[3] = -100; c.isnull = true; l.clear(); return; }
     const int rlength = c.rlenL, rev_roffset = c.roffset + rlength - 1;
     const int bestrL = r.bestrL, bestrR = r.bestrR, bestcL = r.bestcL, bestcR = r.bestcR;
-    c.dout[0] = prob_at(c.lp,bestcL); c.dout[1] = prob_at(c.rp,bestcR);
+    c.dout[0] = call_prob(c,false,bestcL); c.dout[1] = call_prob(c,true,bestcR);
     c.iout[1] = c.goffset + (bestcL - 1);
     c.iout[2] = c.goffsetR - (bestcR - 1);
     c.iout[8] = rev_roffset - (bestrR - 1);

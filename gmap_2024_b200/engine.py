@@ -19,6 +19,30 @@ class Pair(C.Structure):
                 ("genomealt", C.c_char), ("donor_prob", C.c_double), ("acceptor_prob", C.c_double)]
 
 
+class Box(C.Structure):
+    """gmapdp_box (include/gmapdp_b200.h)"""
+    _fields_ = [("mode", C.c_int32), ("flags", C.c_int32), ("rlenL", C.c_int32), ("rlenR", C.c_int32), ("glenL", C.c_int32),
+                ("glenR", C.c_int32), ("mismatchtype", C.c_int8), ("open", C.c_int8), ("extend", C.c_int8), ("cdna_direction", C.c_int8),
+                ("lbandL", C.c_int16), ("ubandL", C.c_int16), ("lbandR", C.c_int16), ("ubandR", C.c_int16),
+                ("qL_off", C.c_uint32), ("qR_off", C.c_uint32), ("gL_off", C.c_uint32), ("gLalt_off", C.c_uint32),
+                ("gR_off", C.c_uint32), ("gRalt_off", C.c_uint32), ("probL_off", C.c_uint32), ("probR_off", C.c_uint32),
+                ("offdiff", C.c_int32), ("revmask", C.c_int32),
+                ("chroffset", C.c_uint32), ("chrhigh", C.c_uint32), ("gflags", C.c_uint16), ("probkindL", C.c_uint8), ("probkindR", C.c_uint8)]
+
+
+class Coords(C.Structure):
+    """gmapdp_coords (include/gmapdp_shim.h)"""
+    _fields_ = [("chroffset", C.c_uint32), ("chrhigh", C.c_uint32), ("gposL", C.c_uint32), ("gposR", C.c_uint32),
+                ("negL", C.c_int), ("negR", C.c_int), ("leftL", C.c_int), ("leftR", C.c_int), ("probs", C.c_int),
+                ("probposL", C.c_uint32), ("probposR", C.c_uint32), ("probnegL", C.c_int), ("probnegR", C.c_int),
+                ("probkindL", C.c_int), ("probkindR", C.c_int)]
+
+
+class MaxentTables(C.Structure):
+    """gmapdp_maxent_tables (include/gmapdp_b200.h): sixteen table pointers"""
+    _fields_ = [("t", C.c_void_p * 16)]
+
+
 class DeviceResult(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("status", "finalscore", "bestrL", "bestcL", "bestrR", "bestcR", "tb_score",
                                          "nmatches", "nmismatches", "nopens", "nindels", "script_off", "script_lenA",
@@ -102,7 +126,36 @@ class Engine:
         return {"sm_count": sm.value, "grid_blocks": grid.value, "block_threads": bt.value}
 
     def batch(self, max_rlength=2000, max_glength=2030):
-        return Batch(self, max_rlength, max_glength)
+        b = Batch(self, max_rlength, max_glength)
+        if getattr(self, "_genome", None):
+            b.set_genome(*self._genome_host)
+        return b
+
+    def genome_attach(self, blocks, nwords, tables):
+        """Resident genome: ``blocks`` = address of the reference's Genomecomp_T words (high, low, flags per 32 nt),
+        ``tables`` = sixteen addresses of the MaxEnt tables in the order of gmapdp_maxent_tables.  The caller keeps both alive."""
+        mt = MaxentTables()
+        for k in range(16):
+            mt.t[k] = tables[k]
+        g = C.c_void_p()
+        self.lib.gmapdp_device_info  # (library loaded)
+        rc = self.lib.gmapdp_genome_create(C.byref(g), self.device, C.c_void_p(blocks), C.c_size_t(nwords), C.byref(mt))
+        if rc != 0:
+            raise EngineError("gmapdp_genome_create failed (%d)" % rc)
+        if self.lib.gmapdp_genome_attach(self.ctx, g) != 0:
+            raise EngineError(self.lib.gmapdp_last_error(self.ctx).decode())
+        old = getattr(self, "_genome", None)
+        self._genome, self._genome_host = g, (blocks, nwords, mt)
+        if old:
+            self.lib.gmapdp_genome_destroy(old)
+
+    def maxent_eval(self, kinds, positions, chroffset):
+        """Maxent_hr_*_prob on the device for (kind, position) pairs: list of floats"""
+        n = len(kinds)
+        ka, pa, out = (C.c_int * n)(*kinds), (C.c_uint32 * n)(*positions), (C.c_double * n)()
+        if self.lib.gmapdp_maxent_eval(self.ctx, ka, pa, C.c_uint32(chroffset), n, out) != 0:
+            raise EngineError(self.lib.gmapdp_last_error(self.ctx).decode())
+        return list(out)
 
     def chain_setup(self, splicingp=1, cross_species_p=0, sufflookback=60, nsufflookback=5, maxintronlen=500000):
         """Stage2_setup (stage2.c:129) for the chaining engine; defaults are gmap's (gmap.c:269,270,347)."""
@@ -135,8 +188,16 @@ class Batch:
         self.lib.GmapDP_batch_clear(self.h)
         self._keep = []
 
+    def set_genome(self, blocks, nwords, tables):
+        self._genome_keep = tables
+        self.lib.GmapDP_batch_genome(self.h, C.c_void_p(blocks), C.c_size_t(nwords), C.byref(tables))
+
     def add(self, box):
         m = box["mode"]
+        co = box.get("coords")
+        if co is not None:              # resident-genome form of the call (tests/dpgen.coords_of)
+            cs = Coords(**co)
+            self.lib.GmapDP_batch_next_coords(self.h, C.byref(cs))
         q = _b(box["queryseq"])
         quc = q.upper()
         qb, qucb = C.create_string_buffer(q, len(q) + 1), C.create_string_buffer(quc, len(quc) + 1)
@@ -155,8 +216,11 @@ class Batch:
                       _b(box["gseg_alt"]), box["jump_late_p"], box["extraband"], dr, box["endalign"],
                       box["require_pos_score_p"])
         if m == "genome":
-            lp = (C.c_double * len(box["left_probs"]))(*box["left_probs"])
-            rp = (C.c_double * len(box["right_probs"]))(*box["right_probs"])
+            if co is not None and co.get("probs"):
+                lp = rp = None          # MaxEnt on the device
+            else:
+                lp = (C.c_double * len(box["left_probs"]))(*box["left_probs"])
+                rp = (C.c_double * len(box["right_probs"]))(*box["right_probs"])
             return self.lib.GmapDP_genome_gap(self.h, box["dynprogindex"], C.c_void_p(base + box["roffset"]),
                                               C.c_void_p(baseuc + box["roffset"]), box["rlength"], box["glengthL"],
                                               box["glengthR"], box["roffset"], box["goffsetL"], box["rev_goffsetR"],

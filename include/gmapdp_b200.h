@@ -50,7 +50,19 @@ enum { GMAPDP_SINGLE = 0, GMAPDP_GENOME = 1, GMAPDP_CDNA = 2, GMAPDP_END5 = 3, G
 #define GMAPDP_F_NOTRACE     0x40	/* end modes: require_pos_score_p => the reference skips the traceback */
 #define GMAPDP_F_BRIDGE_LATE 0x80	/* cdna bridge tie rule: >= (jump_late_p) instead of > */
 
-/* One DP box (76 bytes).  Sequences live in one byte pool; every *_off is an unsigned byte offset into it (pool < 4 GiB).
+/* gmapdp_box.gflags: where the genomic data of a box come from (see gmapdp_genome_attach) */
+#define GMAPDP_G_SEG_L      0x01	/* the L (or only) segment is read from the resident genome: gL_off = coordinate of its char 0 */
+#define GMAPDP_G_SEG_R      0x02	/* the same for the R segment (gR_off) */
+#define GMAPDP_G_NEG_L      0x04	/* L segment runs towards lower coordinates and is complemented (revcomp fetch) */
+#define GMAPDP_G_NEG_R      0x08
+#define GMAPDP_G_LEFT_L     0x10	/* L segment was fetched "leftwards" (Genome_get_segment_left: '*' below chroffset); else */
+#define GMAPDP_G_LEFT_R     0x20	/*   "rightwards" (Genome_get_segment_right: '*' from chrhigh on) */
+#define GMAPDP_G_PROBS      0x40	/* genome mode: MaxEnt probabilities are computed on the device: probL_off / probR_off = */
+					/*   splice coordinate of entry 0 of the left / right array */
+#define GMAPDP_G_PSTEP_NEG_L 0x80	/* entry c of the left array is the coordinate probL_off - c (else + c) */
+#define GMAPDP_G_PSTEP_NEG_R 0x100
+
+/* One DP box (88 bytes).  Sequences live in one byte pool; every *_off is an unsigned byte offset into it (pool < 4 GiB).
  * All sequence arrays are stored FORWARD (ascending memory = ascending coordinate); sides that the
  * reference addresses through "rev_" pointers set the corresponding REV flag bit in `revmask` and
  * are read from their last element backwards, exactly like rev_rsequence / rev_gsequence. */
@@ -67,6 +79,10 @@ typedef struct gmapdp_box {
   uint32_t probL_off, probR_off;	/* genome mode: offsets (in doubles) of left/right MaxEnt probabilities, glen-1 entries each */
   int32_t offdiff;		/* genome: rev_goffsetR - goffsetL ; cdna: rev_roffsetR - roffsetL (bridge constraint) */
   int32_t revmask;		/* bit0: L side is read reversed (end5) ; bit1: R side is read reversed (genome, cdna) */
+  /* resident-genome boxes (all zero otherwise) */
+  uint32_t chroffset, chrhigh;	/* bounds of the chromosome the segments lie on (Univcoord_T) */
+  uint16_t gflags;		/* GMAPDP_G_* */
+  uint8_t  probkindL, probkindR;	/* 0 donor, 1 acceptor, 2 antidonor, 3 antiacceptor (Maxent_hr_*_prob) */
 } gmapdp_box;
 
 /* Edit script: one uint32 per op, in traceback order (from the best cell back to the origin).
@@ -113,6 +129,27 @@ int gmapdp_run_batch_chunks (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxe
 			     const uint8_t *seqpool, size_t seqbytes, const double *probpool, size_t nprobs,
 			     gmapdp_result *results, uint32_t *script, size_t script_cap, size_t *script_used,
 			     gmapdp_chunk_fn on_chunk, void *user);
+
+/* Resident genome and splice-site model.  `blocks' is the reference's compressed genome
+ * exactly as genome.c reads it (three 32-bit words -- high, low, flags -- per 32 nt; uncompress_mmap, genome.c:8985): it
+ * is copied to the device once and stays there.  `maxent' holds the parameters of the reference's MaxEnt model (the static
+ * arrays of maxent_hr.c; 16384 doubles per score table, 16 per dinucleotide table).  One genome object serves every
+ * context of its device (gmapdp_genome_attach).  Boxes with gflags then carry genome COORDINATES instead of genomic
+ * characters and probability arrays: segments are decoded and Maxent_hr_{donor,acceptor,antidonor,antiacceptor}_prob
+ * (maxent_hr.c:27357-27650) evaluated on the device, bit-identically (IEEE double).  Only genomealt == genome. */
+typedef struct gmapdp_maxent_tables {
+  const double *donor_plus, *donor_di_plus, *acc1_plus, *acc2_plus, *acc3_plus, *acc_di_plus, *acc467_plus, *acc589_plus;
+  const double *donor_minus, *donor_di_minus, *acc1_minus, *acc2_minus, *acc3_minus, *acc_di_minus, *acc467_minus, *acc589_minus;
+} gmapdp_maxent_tables;
+typedef struct gmapdp_genome gmapdp_genome;
+int gmapdp_genome_create (gmapdp_genome **g, int device, const uint32_t *blocks, size_t nwords, const gmapdp_maxent_tables *maxent);
+void gmapdp_genome_destroy (gmapdp_genome *g);
+int gmapdp_genome_attach (gmapdp_ctx *ctx, const gmapdp_genome *g);	/* g must outlive ctx's last run */
+/* the same arithmetic on the host (for callers that need single values): char of one position, one probability */
+int gmapdp_genome_host_char (const uint32_t *blocks, size_t nwords, uint32_t pos);
+double gmapdp_maxent_host_prob (const uint32_t *blocks, size_t nwords, const gmapdp_maxent_tables *maxent, int kind, uint32_t splice_pos, uint32_t chroffset);
+/* device check of the same: probs[k] = probability `kind[k]' at pos[k] (testing; n values) */
+int gmapdp_maxent_eval (gmapdp_ctx *ctx, const int *kind, const uint32_t *pos, uint32_t chroffset, int n, double *probs);
 
 /* Resident path (benchmarks, pipelined callers): upload once, run any number of times with the
  * inputs already in HBM, download when wanted.  kernel_ms (may be NULL) receives the CUDA-event

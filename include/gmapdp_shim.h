@@ -65,6 +65,24 @@ typedef struct gmapdp_gapinfo {
 
 #define GMAPDP_UNSET (-999)
 
+/* Resident genome (device side: gmapdp_genome_create / _attach in gmapdp_b200.h).  The
+ * entry points keep their character arguments -- the replay needs the characters for the pairs -- but a call announced
+ * by GmapDP_batch_next_coords sends the device COORDINATES instead: where char 0 of each segment array lies in the
+ * genome and in which direction the array runs, and for genome gaps where entry 0 of each probability array lies, its
+ * direction and which of Maxent_hr_{donor,acceptor,antidonor,antiacceptor}_prob (0..3) fills it (the arrays of
+ * dynprog_genome.c:970-1061; the entry point's own two lookups are then served by the same arithmetic on the host, and
+ * left_probabilities / right_probabilities may be NULL).  Ignored for calls with an alternate genome. */
+typedef struct gmapdp_coords {
+  uint32_t chroffset, chrhigh;
+  uint32_t gposL, gposR;	/* genome coordinate of element 0 of the L (or only) / R segment array */
+  int negL, negR;		/* the array runs towards lower coordinates and is complemented (revcomp fetch) */
+  int leftL, leftR;		/* fetched with Genome_get_segment_left ('*' below chroffset), else _right ('*' from chrhigh) */
+  int probs;			/* genome gaps: probabilities from the MaxEnt model */
+  uint32_t probposL, probposR;	/* splice coordinate of entry 0 of the left / right array */
+  int probnegL, probnegR;	/* entry c lies at probpos - c (else + c) */
+  int probkindL, probkindR;	/* 0 donor, 1 acceptor, 2 antidonor, 3 antiacceptor */
+} gmapdp_coords;
+
 /* Endalign_T, dynprog.h:27 */
 enum { GMAPDP_QUERYEND_GAP = 0, GMAPDP_QUERYEND_INDELS = 1, GMAPDP_QUERYEND_NOGAPS = 2, GMAPDP_BEST_LOCAL = 3 };
 
@@ -83,6 +101,10 @@ void GmapDP_batch_free (gmapdp_batch *b);
  * dynprog_end.c:1334,1964); cdna gaps never do (dynprog_cdna.c has no such branch).  Both in [-127, 0] (gmap.c:5425-5445). */
 int GmapDP_batch_user_dynprog (gmapdp_batch *b, int user_open, int user_extend, int user_dynprog_p);
 void GmapDP_batch_clear (gmapdp_batch *b);
+/* the host's view of the genome the batch's context has attached (blocks and tables must stay valid) */
+int GmapDP_batch_genome (gmapdp_batch *b, const uint32_t *blocks, size_t nwords, const gmapdp_maxent_tables *tables);
+/* the next entry-point call queued on b refers to these coordinates (NULL: cancel) */
+void GmapDP_batch_next_coords (gmapdp_batch *b, const gmapdp_coords *co);
 
 int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char *rsequence, const char *rsequenceuc,
 		       int rlength, int glength, int roffset, int goffset,

@@ -94,6 +94,13 @@ void refdrv_get_segment (void *gh, int leftp, unsigned int coord, int length, un
   }
 }
 
+/* the compressed genome as the reference holds it (Genomecomp_T: high, low, flags per 32 nt) */
+const unsigned int *refdrv_genome_blocks (void *gh, unsigned long *nwords) {
+  refdrv_genome *g = (refdrv_genome *) gh;
+  *nwords = ((unsigned long) g->length / 32UL + 1UL) * 3UL;
+  return (const unsigned int *) Genome_blocks(g->genome);
+}
+
 /* which: 0 donor, 1 acceptor, 2 antidonor, 3 antiacceptor */
 double refdrv_maxent (void *gh, int which, unsigned int pos, unsigned int chroffset) {
   refdrv_genome *g = (refdrv_genome *) gh;

@@ -394,6 +394,44 @@ def finalize_with_ref(ref, rng, world, s):
     return b
 
 
+def coords_of(box, probs=True):
+    """The resident-genome form of a ref_boxes() box (gmapdp_coords, include/gmapdp_shim.h): where element 0 of each
+    segment array lies in the genome, its direction and which fetch produced it -- the fetches of fetch_fwd / fetch_rev
+    above, i.e. of the reference's entry points -- and for genome gaps the coordinates of maxent_arrays()."""
+    w = box["world"]
+    co, ch, wp, m = w["chroffset"], w["chrhigh"], w["watsonp"], box["mode"]
+
+    def fwd(goffset):                   # fetch_fwd: (gpos, neg, left)
+        return (co + goffset, 0, 0) if wp else (ch - goffset, 1, 1)
+
+    def rev(rev_goffset, g):            # fetch_rev
+        return (co + rev_goffset + 1 - g, 0, 1) if wp else (ch - rev_goffset + g - 1, 1, 0)
+
+    c = dict(chroffset=co, chrhigh=ch, gposL=0, gposR=0, negL=0, negR=0, leftL=0, leftR=0, probs=0,
+             probposL=0, probposR=0, probnegL=0, probnegR=0, probkindL=0, probkindR=0)
+    if m in ("single", "end3", "cdna"):
+        c["gposL"], c["negL"], c["leftL"] = fwd(box["goffset"])
+    elif m == "end5":
+        c["gposL"], c["negL"], c["leftL"] = rev(box["goffset"], box["glength"])
+    else:
+        c["gposL"], c["negL"], c["leftL"] = fwd(box["goffsetL"])
+        c["gposR"], c["negR"], c["leftR"] = rev(box["rev_goffsetR"], box["glengthR"])
+        if probs:
+            d = box["cdna_direction"]
+            c["probs"] = 1
+            if wp:
+                c["probkindL"], c["probkindR"] = (0, 1) if d > 0 else (3, 2)
+                c["probposL"], c["probnegL"] = co + box["goffsetL"], 0
+                c["probposR"], c["probnegR"] = co + box["rev_goffsetR"] + 1, 1
+            else:
+                c["probkindL"], c["probkindR"] = (2, 3) if d > 0 else (1, 0)
+                c["probposL"], c["probnegL"] = ch - box["goffsetL"] + 1, 1
+                c["probposR"], c["probnegR"] = ch - box["rev_goffsetR"], 0
+    for k in ("gposL", "gposR", "probposL", "probposR"):
+        c[k] &= 0xFFFFFFFF
+    return c
+
+
 def ref_boxes(ref, seed, n, mode=None, rmin=15, rmax=150, edge=False):
     rng = random.Random(seed)
     specs = [gen_spec(rng, mode, rmin, rmax) for _ in range(n)]

@@ -187,6 +187,21 @@ class Ref:
         self.lib.refdrv_get_segment(gh, int(leftp), C.c_uint(coord), length, C.c_uint(bound), int(revcomp), seg, alt)
         return seg.raw[:length], alt.raw[:length]
 
+    def genome_blocks(self, gh):
+        """(address, nwords) of the reference's compressed genome (Genomecomp_T words)"""
+        n = C.c_ulong()
+        self.lib.refdrv_genome_blocks.restype = C.c_void_p
+        p = self.lib.refdrv_genome_blocks(gh, C.byref(n))
+        return p, n.value
+
+    def maxent_tables(self):
+        """sixteen addresses of the reference's MaxEnt tables (oracle/_ref/ref_maxent.so: maxent_hr.c compiled in place)"""
+        if not hasattr(self, "_me"):
+            self._me = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "ref_maxent.so"))
+        t = (C.c_void_p * 16)()
+        self._me.refme_tables(t)
+        return list(t)
+
     def maxent(self, gh, which, pos, chroffset):
         return self.lib.refdrv_maxent(gh, which, C.c_uint(pos), C.c_uint(chroffset))
 

@@ -120,12 +120,11 @@ def test_user_penalties_reach_the_box(lib):
         b.add(x)
     ptr, n, _, _, _, _ = b.device_view()
 
-    class Box(C.Structure):
-        _fields_ = [("mode", C.c_int32), ("flags", C.c_int32), ("rlenL", C.c_int32), ("rlenR", C.c_int32), ("glenL", C.c_int32),
-                    ("glenR", C.c_int32), ("mismatchtype", C.c_int8), ("open", C.c_int8), ("extend", C.c_int8), ("cdna_direction", C.c_int8)]
+    from gmap_2024_b200.engine import Box
+    assert C.sizeof(Box) == 88
     seen = set()
     for k in range(n):
-        x = Box.from_address(ptr.value + 76 * k)
+        x = Box.from_address(ptr.value + C.sizeof(Box) * k)
         seen.add(x.mode)
         if x.mode == 2:
             assert (x.open, x.extend) == (-10, -7)
