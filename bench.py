@@ -101,10 +101,12 @@ class ClockSampler(threading.Thread):
 # CPU arm: the reference's own DP on the host cores
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    kind, seed, start, stride, budget_s, small = args
+    kind, seed, start, stride, budget_s, small, resident = args
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import benchgen
+    if resident:
+        benchgen.resident_tables_only(seed)     # the boxes' probability arrays = the MaxEnt values of the resident form
     from harness import Oracle, Ref
     counter = Oracle()                      # cells are counted by the oracle's own entry-point control flow, not by the product
     runner = Oracle() if kind == "port" else Ref(noflush=(kind == "reference_noflush"))
@@ -126,7 +128,7 @@ def _cpu_worker(args):
     return nboxes, cells, busy, time.perf_counter() - t0
 
 
-def cpu_arm(seed, budget_s, small, offset=0, noflush=False):
+def cpu_arm(seed, budget_s, small, offset=0, noflush=False, resident=True):
     """the reference's own five entry points (compiled from the unmodified sources) on all host cores, one process per
     core; `noflush` = the fairness build without dynprog_simd.c's per-column _mm_clflush"""
     import multiprocessing as mp
@@ -137,7 +139,7 @@ def cpu_arm(seed, budget_s, small, offset=0, noflush=False):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(kind, seed, offset + w, cores, budget_s, small) for w in range(cores)])
+        res = pool.map(_cpu_worker, [(kind, seed, offset + w, cores, budget_s, small, resident) for w in range(cores)])
     nboxes = sum(r[0] for r in res)
     cells = sum(r[1] for r in res)
     wall = max(r[3] for r in res)
@@ -151,7 +153,10 @@ def cpu_arm(seed, budget_s, small, offset=0, noflush=False):
 def bench_config(args):
     """the workload both arms are run on (the reference arm times a bounded sample of the same generator and seed)"""
     return {"workload": WORKLOAD, "boxes_per_gpu": args.boxes, "seed": args.seed, "modemask": args.modemask,
-            "stratum": "production 15-150 bp" if args.small else "BASELINE configs[1] 50-2000 bp"}
+            "stratum": "production 15-150 bp" if args.small else "BASELINE configs[1] 50-2000 bp",
+            "genome": "uploaded with every box (characters + probability arrays)" if args.upload_genome else
+                      "resident on the device in the reference's compressed layout; boxes carry coordinates, MaxEnt evaluated on the device "
+                      "(synthetic model tables)"}
 
 
 def run_reference(args):
@@ -161,7 +166,7 @@ def run_reference(args):
     vals = []
     last = None
     for step in range(args.warmup + args.steps):
-        last = cpu_arm(args.seed, args.ref_step_seconds, args.small, offset=step * 100003)
+        last = cpu_arm(args.seed, args.ref_step_seconds, args.small, offset=step * 100003, resident=not args.upload_genome)
         if step >= args.warmup:
             vals.append(last)
     cells = sum(v["cells"] for v in vals)
@@ -178,7 +183,7 @@ def run_reference(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     if not args.no_cpu_baseline:
-        nf = cpu_arm(args.seed, args.ref_step_seconds, args.small, offset=7 * 100003, noflush=True)
+        nf = cpu_arm(args.seed, args.ref_step_seconds, args.small, offset=7 * 100003, noflush=True, resident=not args.upload_genome)
         if nf["variant"] == "reference_noflush":
             line["cpu_baseline"]["noflush"] = {"value": nf["gcups"], "unit": UNIT, "cores": nf["cores"],
                                                "sample": "%d boxes, same sources with the _mm_clflush statements of dynprog_simd.c defined away "
@@ -403,7 +408,14 @@ def run_ours(args):
     batch = eng.batch(2000, 2030)
     t0 = time.time()
     i0, i1 = shard_range(rank, world, args.boxes)
-    benchgen.fill_batch(batch, args.seed, i0, i1 - i0, 1, args.small, args.modemask)    # untimed: synthetic input
+    resident = not args.upload_genome
+    genome_bytes = 0
+    if resident:                            # the rank's genome: laid out while the boxes are queued, uploaded once (untimed)
+        benchgen.resident_begin(batch, args.seed, min(4000000000, (i1 - i0) * 2600 + 1000000))
+    if benchgen.fill_batch(batch, args.seed, i0, i1 - i0, 1, args.small, args.modemask) < 0:    # untimed: synthetic input
+        raise SystemExit("bench.py: the synthetic genome outgrew its buffer")
+    if resident:
+        genome_bytes = benchgen.resident_attach(eng)
     gen_s = time.time() - t0
     cells, cells8 = batch.cells(), batch.cells8()
 
@@ -430,7 +442,12 @@ def run_ours(args):
     if args.stratum_boxes > 0 and not args.small:
         sb = eng.batch(2000, 2030)
         j0, j1 = shard_range(rank, world, args.stratum_boxes)
-        benchgen.fill_batch(sb, args.seed, j0, j1 - j0, 1, True, args.modemask)
+        if resident:
+            benchgen.resident_begin(sb, args.seed, (j1 - j0) * 400 + 1000000)
+        if benchgen.fill_batch(sb, args.seed, j0, j1 - j0, 1, True, args.modemask) < 0:
+            raise SystemExit("bench.py: the synthetic genome outgrew its buffer")
+        if resident:
+            benchgen.resident_attach(eng)
         s_cells, s_calls, s_boxes = sb.cells(), sb.ncalls(), sb.nboxes()
         sm = measure_batch(eng, sb, args, barrier)
         s_dev, s_e2e, s_e2e_dev = allreduce(sm["dev_ms"], MAX), allreduce(sm["e2e_ms"], MAX), allreduce(sm["e2e_dev_ms"], MAX)
@@ -501,7 +518,8 @@ def run_ours(args):
                 "config": bench_config(args),
                 "run": {"calls": int(tot_calls), "device_boxes": int(tot_boxes), "cells_per_step": int(tot_cells), "l2": "inputs_exceed_l2" if not args.small else "small",
                         "grid_blocks": info["grid_blocks"], "block_threads": info["block_threads"], "parallelism": "shard%d" % world,
-                        "wall_ms_per_step": wall_ms_max / args.steps, "input_generation_s": gen_s},
+                        "wall_ms_per_step": wall_ms_max / args.steps, "input_generation_s": gen_s,
+                        "resident_genome_bytes": int(genome_bytes)},
                 "roofline": {"bound": "int", "achieved": achieved_int, "peak": ipeak, "unit": "Tera int ops/s", "frac": achieved_int / ipeak,
                              "traffic": traffic, "peak_source": ipeak_src, "ops_per_cell": dom_ops,
                              "kernel": "gmapdp_dp_kernel<0> (single gaps: full fills)" if full_ms > 0 else "all kernels",
@@ -527,12 +545,12 @@ def run_ours(args):
         if program is not None:
             line["program"] = program
         if world == 1 and not args.no_cpu_baseline:
-            c = cpu_arm(args.seed, args.cpu_seconds, args.small)
+            c = cpu_arm(args.seed, args.cpu_seconds, args.small, resident=not args.upload_genome)
             line["cpu_baseline"] = {"value": c["gcups"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"],
                                     "sample": "first %d boxes of the same generator and seed, %.0f s on %d processes%s; cells counted by the oracle" % (
                                         c["boxes"], args.cpu_seconds, c["cores"],
                                         " (stock reference DP incl. its per-column _mm_clflush, SURVEY.md F5)" if c["kind"] == "reference" else "")}
-            nf = cpu_arm(args.seed, args.cpu_seconds / 2, args.small, noflush=True)
+            nf = cpu_arm(args.seed, args.cpu_seconds / 2, args.small, noflush=True, resident=not args.upload_genome)
             if nf["variant"] == "reference_noflush":
                 line["cpu_baseline"]["noflush"] = {"value": nf["gcups"], "unit": UNIT, "cores": nf["cores"],
                                                    "sample": "%d boxes; same sources with the _mm_clflush statements of dynprog_simd.c defined away "
@@ -551,6 +569,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--boxes", type=int, default=1000000, help="boxes per GPU (BASELINE.json configs[1]: 1M)")
     ap.add_argument("--seed", type=int, default=20241018)
+    ap.add_argument("--upload-genome", action="store_true", help="send genomic characters and probability arrays with every box instead of "
+                    "coordinates into a genome resident on the device (the round-1 form of the workload)")
     ap.add_argument("--small", action="store_true", help="run the main measurement on the production-size stratum (15-150 bp) instead")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-step-seconds", type=float, default=8.0)

@@ -154,22 +154,21 @@ struct GenCtx {
   const short *dgL, *dgR;		/* main-diagonal scores of the upper fills */
   const double *lp, *rp;
   int rlength, lim;
-  /* MaxEnt on the device (GMAPDP_G_PROBS): entry c of the left / right array is the probability of kind lkind / rkind at
-     coordinate lpos0 + lstep c / rpos0 + rstep c, for c < glength - 1, else 0 (the arrays of dynprog_genome.c:970-1061) */
-  bool devp;
+  /* MaxEnt from the resident genome (GMAPDP_G_PROBS): entry c of the left / right array is the probability of kind
+     lkind / rkind at coordinate lpos0 + lstep c / rpos0 + rstep c for c < glength - 1, 0 beyond (the arrays of
+     dynprog_genome.c:970-1061); a pre-pass of the box evaluates them into the workspace (gen_maxent), lp / rp point there.
+     (Evaluating only the few entries the bridge's last step reads was measured slower: 114 vs 98 ms for the genome
+     kernel of the benchmark launch -- single lanes walking dependent L2 loads -- against 57 ms with uploaded arrays.) */
   GdpGenome genome; const double *me;
   uint32_t lpos0, rpos0, chroffset;
   int lstep, rstep, lkind, rkind, nlp, nrp;
-  __device__ __forceinline__ double lprob (int c) const {
-    if (!devp) return lp[c];
-    return (c >= 0 && c < nlp) ? gdp_maxent_prob(lkind,genome,me,lpos0 + (uint32_t) (lstep * c),chroffset) : 0.0;
-  }
-  __device__ __forceinline__ double rprob (int c) const {
-    if (!devp) return rp[c];
-    return (c >= 0 && c < nrp) ? gdp_maxent_prob(rkind,genome,me,rpos0 + (uint32_t) (rstep * c),chroffset) : 0.0;
-  }
   uint32_t it0, it1;			/* intron scores as a byte table: byte k+1 = score of bit k, byte 0 = 0 */
 };
+
+__device__ __noinline__ double gen_maxent (const GenCtx &g, int right, int c) {
+  if (right) return (c >= 0 && c < g.nrp) ? gdp_maxent_prob(g.rkind,g.genome,g.me,g.rpos0 + (uint32_t) (g.rstep * c),g.chroffset) : 0.0;
+  return (c >= 0 && c < g.nlp) ? gdp_maxent_prob(g.lkind,g.genome,g.me,g.lpos0 + (uint32_t) (g.lstep * c),g.chroffset) : 0.0;
+}
 
 __device__ __forceinline__ int gen_points (const GenCtx &g, int di) {
   uint32_t pos, d;
@@ -181,9 +180,9 @@ __device__ __forceinline__ int gen_points (const GenCtx &g, int di) {
 /* probability sum of the candidate behind a key */
 __device__ __forceinline__ double gen_key_prob (const GenCtx &g, int key) {
   const int rL = key >> 15, seg = (key >> 12) & 7, col = key & 4095;
-  if (seg == 0) return g.lprob(rL) + g.rprob(g.rlength - rL);
-  if (seg <= 2) return g.lprob(rL) + g.rprob(col);
-  return g.lprob(col) + g.rprob(g.rlength - rL);
+  if (seg == 0) return g.lp[rL] + g.rp[g.rlength - rL];
+  if (seg <= 2) return g.lp[rL] + g.rp[col];
+  return g.lp[col] + g.rp[g.rlength - rL];
 }
 
 __device__ __forceinline__ void gen_tie (const GenCtx &g, GenBest &b, int key) {	/* same score as the lane's best */
@@ -1245,7 +1244,7 @@ __device__ int bridge_genome_finish (const gmapdp_box &b, const GenCtx &g, GenBe
     if (score > gb.s) { gb.s = score; gb.key = key; gb.p = -1.0; }
     else if (score == gb.s) gen_tie(g,gb,key);
     if (scoreI > 0) {
-      const double ps = g.lprob(rL) + g.rprob(rR);
+      const double ps = g.lp[rL] + g.rp[rR];
       if (ps > dnp) { dns = score; dnp = ps; dnkey = key; }
     }
   }
@@ -1631,11 +1630,19 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 	gc.ldi = ldi; gc.rdi = rdi; gc.dgL = dgL; gc.dgR = dgR;
 	gc.lp = ka.probs + b.probL_off; gc.rp = ka.probs + b.probR_off;
 	gc.rlength = b.rlenL; gc.lim = b.offdiff;
-	gc.devp = (b.gflags & GMAPDP_G_PROBS) != 0;
-	gc.genome = ka.genome; gc.me = ka.maxent; gc.chroffset = b.chroffset;
-	gc.lpos0 = b.probL_off; gc.rpos0 = b.probR_off;
-	gc.lstep = (b.gflags & GMAPDP_G_PSTEP_NEG_L) ? -1 : +1; gc.rstep = (b.gflags & GMAPDP_G_PSTEP_NEG_R) ? -1 : +1;
-	gc.lkind = b.probkindL; gc.rkind = b.probkindR; gc.nlp = b.glenL - 1; gc.nrp = b.glenR - 1;
+	if (b.gflags & GMAPDP_G_PROBS) {
+	  gc.genome = ka.genome; gc.me = ka.maxent; gc.chroffset = b.chroffset;
+	  gc.lpos0 = b.probL_off; gc.rpos0 = b.probR_off;
+	  gc.lstep = (b.gflags & GMAPDP_G_PSTEP_NEG_L) ? -1 : +1; gc.rstep = (b.gflags & GMAPDP_G_PSTEP_NEG_R) ? -1 : +1;
+	  gc.lkind = b.probkindL; gc.rkind = b.probkindR; gc.nlp = b.glenL - 1; gc.nrp = b.glenR - 1;
+	  if ((reinterpret_cast<uintptr_t>(wp) & 7) != 0) wp++;
+	  double *lpb = reinterpret_cast<double *>(wp); wp += 2 * (size_t) (b.glenL + 1);
+	  double *rpb = reinterpret_cast<double *>(wp); wp += 2 * (size_t) (b.glenR + 1);
+	  for (int c = lane; c <= b.glenL; c += 32) lpb[c] = gen_maxent(gc,0,c);
+	  for (int c = lane; c <= b.glenR; c += 32) rpb[c] = gen_maxent(gc,1,c);
+	  gc.lp = lpb; gc.rp = rpb;
+	  __syncwarp();
+	}
 	gc.it0 = ((uint32_t) isc[0] << 8) | ((uint32_t) isc[1] << 16) | ((uint32_t) isc[2] << 24);
 	gc.it1 = (uint32_t) isc[3] | ((uint32_t) isc[4] << 8) | ((uint32_t) isc[5] << 16);
 	GenBest gb; gb.s = NEG; gb.key = -1; gb.cnt = 0; gb.p = 0.0; gb.ties = wp + lane; wp += GEN_TIECAP * 32;

@@ -154,6 +154,7 @@ GDP_HD size_t gdp_ws_words (const gmapdp_box &b) {
     w += (size_t) tp.npasses * (tp.dirPW + (scores ? tp.scPW : 0));
     w += (size_t) tp.maxA + 2;							/* edge array of wide fills */
     if (b.mode == GMAPDP_GENOME) w += 8 * 32;					/* tie lists of the bridge (GEN_TIECAP keys per lane) */
+    if (b.mode == GMAPDP_GENOME && (b.gflags & GMAPDP_G_PROBS)) w += 2 * (size_t) (b.glenL + b.glenR + 2) + 2;	/* MaxEnt arrays */
     if (b.mode == GMAPDP_CDNA) w += (size_t) (b.glenL + 1 + b.rlenL + 1) * (b.lbandR + b.ubandR + 1);	/* prefix-best tables of the cDNA bridge: per column, per rL */
   }
   return w + 64;

@@ -93,10 +93,19 @@ struct Pushed {
   void reverse () { std::reverse(buf + lo,buf + hi); }
 };
 
+#if defined(__SSE2__) && !defined(GMAPDP_NO_NT_STORES)
+/* non-temporal or ordinary 16-byte store of one record (GMAPDP_NT_STORES=0 selects ordinary stores: which one is faster
+   depends on how many threads share the memory controllers) */
+const bool g_nt_stores = !(getenv("GMAPDP_NT_STORES") && atoi(getenv("GMAPDP_NT_STORES")) == 0);
+inline void store16 (gmapdp_cpair *p, __m128i v) {
+  if (g_nt_stores) _mm_stream_si128(reinterpret_cast<__m128i *>(p),v); else _mm_store_si128(reinterpret_cast<__m128i *>(p),v);
+}
+#endif
+
 inline void store_pair (gmapdp_cpair *p, int querypos, int genomepos, char cdna, char comp, char genome, char genomealt, int gap) {
 #if defined(__SSE2__) && !defined(GMAPDP_NO_NT_STORES)
   const uint32_t chars = (uint32_t) (uint8_t) cdna | ((uint32_t) (uint8_t) comp << 8) | ((uint32_t) (uint8_t) genome << 16) | ((uint32_t) (uint8_t) genomealt << 24);
-  _mm_stream_si128(reinterpret_cast<__m128i *>(p),_mm_set_epi32(gap,(int) chars,genomepos,querypos));
+  store16(p,_mm_set_epi32(gap,(int) chars,genomepos,querypos));
 #else
   p->querypos = querypos; p->genomepos = genomepos; p->cdna = cdna; p->comp = comp; p->genome = genome; p->genomealt = genomealt; p->gap = gap;
 #endif
@@ -173,7 +182,61 @@ struct Replayer {
     const int ostep = back ? -1 : +1;
     if (back) out--;
     int nm = 0, nx = 0;
-    for (int j = 0; j < len; j++, rs += step, ru += step, gs += step, ga += step, qpos += step, gpos += step) {
+    int j = 0;
+#if defined(__SSE2__) && !defined(GMAPDP_NO_NT_STORES)
+    /* Eight pairs at a time.  Whichever way a side is walked -- forwards in memory and written backwards (rev sides), or
+       backwards in memory and written forwards -- the record of the input byte at ascending memory index m goes to the
+       descending output slot base - m, with querypos q0 + m and genomepos g0 + m.  Chunks with a '*' (chromosome edge)
+       or a negative position take the scalar loop below. */
+    if ((step > 0) == back) {
+      const __m128i star = _mm_set1_epi8('*'), dyn = _mm_set1_epi8((char) COMP_DYNMATCH), mis = _mm_set1_epi8((char) COMP_MISMATCH);
+      const __m128i minus1 = _mm_set1_epi32(-1), iota = _mm_set_epi32(3,2,1,0), four = _mm_set1_epi32(4);
+      for (; len - j >= 8; j += 8, rs += 8 * step, ru += 8 * step, gs += 8 * step, ga += 8 * step, qpos += 8 * step, gpos += 8 * step, out += 8 * ostep) {
+	const int lowoff = (step > 0) ? 0 : -7;			/* ascending-memory start of the chunk */
+	const int q0 = qpos + lowoff, g0 = gpos + lowoff;
+	if ((q0 | g0) < 0) break;
+	const __m128i vru = _mm_loadl_epi64(reinterpret_cast<const __m128i *>(ru + lowoff));
+	const __m128i vgs = _mm_loadl_epi64(reinterpret_cast<const __m128i *>(gs + lowoff));
+	const __m128i vga = _mm_loadl_epi64(reinterpret_cast<const __m128i *>(ga + lowoff));
+	const __m128i vrs = _mm_loadl_epi64(reinterpret_cast<const __m128i *>(rs + lowoff));
+	if (_mm_movemask_epi8(_mm_cmpeq_epi8(vgs,star)) & 0xff) break;
+	const __m128i eq = _mm_or_si128(_mm_cmpeq_epi8(vru,vgs),_mm_cmpeq_epi8(vru,vga));
+	__m128i comp = _mm_or_si128(_mm_and_si128(eq,dyn),_mm_andnot_si128(eq,mis));
+	const int neq = (~_mm_movemask_epi8(eq)) & 0xff;
+	int good = 8;
+	if (neq) {						/* the bytes that differ: ambiguous (consistent) or mismatch */
+	  alignas(16) char cb[16];
+	  _mm_store_si128(reinterpret_cast<__m128i *>(cb),comp);
+	  for (int m = 0; m < 8; m++) if ((neq >> m) & 1) {
+	    const int a = ru[lowoff + m] & 127;
+	    if (t.cons[a][gs[lowoff + m] & 127] || t.cons[a][ga[lowoff + m] & 127]) cb[m] = (char) COMP_AMBIG; else good--;
+	  }
+	  comp = _mm_load_si128(reinterpret_cast<const __m128i *>(cb));
+	}
+	nm += good; nx += 8 - good;
+	/* chars words (cdna | comp << 8 | genome << 16 | genomealt << 24) of bytes 0-3 and 4-7 */
+	const __m128i rc = _mm_unpacklo_epi8(vrs,comp), gg = _mm_unpacklo_epi8(vgs,vga);
+	const __m128i c03 = _mm_unpacklo_epi16(rc,gg), c47 = _mm_unpackhi_epi16(rc,gg);
+	const __m128i vq = _mm_add_epi32(_mm_set1_epi32(q0),iota), vg = _mm_add_epi32(_mm_set1_epi32(g0),iota);
+	const __m128i vq4 = _mm_add_epi32(vq,four), vg4 = _mm_add_epi32(vg,four);
+	gmapdp_cpair *base = (step > 0) ? out : out + 7;	/* slot of memory index 0 */
+	__m128i pos, chm;
+	pos = _mm_unpacklo_epi32(vq,vg); chm = _mm_unpacklo_epi32(c03,minus1);
+	store16(base,_mm_unpacklo_epi64(pos,chm));
+	store16(base - 1,_mm_unpackhi_epi64(pos,chm));
+	pos = _mm_unpackhi_epi32(vq,vg); chm = _mm_unpackhi_epi32(c03,minus1);
+	store16(base - 2,_mm_unpacklo_epi64(pos,chm));
+	store16(base - 3,_mm_unpackhi_epi64(pos,chm));
+	pos = _mm_unpacklo_epi32(vq4,vg4); chm = _mm_unpacklo_epi32(c47,minus1);
+	store16(base - 4,_mm_unpacklo_epi64(pos,chm));
+	store16(base - 5,_mm_unpackhi_epi64(pos,chm));
+	pos = _mm_unpackhi_epi32(vq4,vg4); chm = _mm_unpackhi_epi32(c47,minus1);
+	store16(base - 6,_mm_unpacklo_epi64(pos,chm));
+	store16(base - 7,_mm_unpackhi_epi64(pos,chm));
+      }
+    }
+#endif
+    for (; j < len; j++, rs += step, ru += step, gs += step, ga += step, qpos += step, gpos += step) {
       const char c2 = *gs;
       if (c2 == '*') continue;
       const char c1uc = *ru, c2a = *ga;

@@ -46,6 +46,40 @@ def lib():
     return _lib
 
 
+def resident_begin(batch, seed, capacity_nt):
+    """Starts the resident-genome form of the workload on `batch`: fill_batch then queues coordinates into one synthetic
+    genome; resident_attach uploads it afterwards."""
+    L = lib()
+    if L.benchgen_resident_begin(C.c_uint64(seed), C.c_uint64(capacity_nt)) != 0:
+        raise MemoryError("benchgen_resident_begin")
+    L.benchgen_resident_blocks.restype = C.c_void_p
+    L.benchgen_resident_tables.restype = C.c_void_p
+    used, cap = C.c_uint64(), C.c_uint64()
+    blocks = L.benchgen_resident_blocks(C.byref(used), C.byref(cap))
+    batch.lib.GmapDP_batch_genome(batch.h, C.c_void_p(blocks), C.c_size_t(cap.value), C.c_void_p(L.benchgen_resident_tables()))
+
+
+def resident_attach(engine):
+    """uploads the genome laid out by fill_batch (and the synthetic MaxEnt tables) to the engine's device"""
+    from gmap_2024_b200.engine import MaxentTables
+    L = lib()
+    used, cap = C.c_uint64(), C.c_uint64()
+    blocks = L.benchgen_resident_blocks(C.byref(used), C.byref(cap))
+    mt = MaxentTables.from_address(L.benchgen_resident_tables())
+    engine.genome_attach(blocks, used.value, [mt.t[k] for k in range(16)])
+    return used.value * 4
+
+
+def resident_end():
+    """back to the plain form (make() returns the u^3 probability arrays again)"""
+    lib().benchgen_resident_end()
+
+
+def resident_tables_only(seed):
+    """CPU workers: benchgen.make fills left_probs / right_probs with the resident form's MaxEnt values"""
+    lib().benchgen_resident_tables_only(C.c_uint64(seed))
+
+
 def fill_batch(batch, seed, i0, n, stride=1, small=False, modemask=31):
     return lib().benchgen_fill_batch(batch.h, C.c_uint64(seed), C.c_long(i0), C.c_long(n), C.c_long(stride), int(small),
                                      int(modemask))

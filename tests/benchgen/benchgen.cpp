@@ -10,12 +10,23 @@
  *   end5/3 : rlength ~ U[50,1990], glength = rlength + 10, endalign GAP / INDELS / NOGAPS in thirds
  *   per-base error 0.1 / 1 / 5 / 15 % (60 % substitution, 20 % deletion, 20 % insertion), defect_rate equal to it
  * Box i depends only on (seed, i).
+ *
+ * Resident-genome form (benchgen_resident_begin; bench.py's default): the genomic segments of the boxes are laid out,
+ * each between 32-nt pads, in one synthetic genome in the reference's compressed block layout; boxes are queued as
+ * COORDINATES into it (GmapDP_batch_next_coords) and the splice-site probabilities of genome gaps are MaxEnt values
+ * (gmapdp_genome.h arithmetic over SYNTHETIC tables: log-normal factors, consensus dinucleotides favoured -- the
+ * reference's own tables are not available to the product) instead of the u^3 arrays.  benchgen_make then fills
+ * left_probs / right_probs with exactly those values (the pads make them independent of the neighbours), so the CPU
+ * checkers see the same box.
  */
 #include <stdint.h>
 #include <string.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <math.h>
+#include <vector>
 #include "../../include/gmapdp_shim.h"
+#include "../../gmap_2024_b200/csrc/gmapdp_genome.h"
 
 #define BG_MAXSEQ 2304
 
@@ -72,6 +83,88 @@ void probs (Rng &r, double *p, int n, int hot) {
   for (int k = hot - 1; k <= hot + 1; k++) if (k >= 0 && k < n) p[k] = 0.9 + 0.0999 * r.unit();
 }
 }
+
+/* ---- resident genome ------------------------------------------------------------------------------ */
+namespace {
+const int PAD = 32;
+struct Resident {
+  bool on = false;
+  std::vector<double> packed;		/* GDP_ME_NDOUBLES, the layout of gmapdp_genome.h */
+  gmapdp_maxent_tables tables;
+  uint32_t *blocks = NULL; size_t cap_words = 0; uint64_t used_nt = 0;
+} RES;
+
+void synth_tables (uint64_t seed) {
+  Rng r(seed ^ 0x4D41584Eull);
+  RES.packed.assign(GDP_ME_NDOUBLES,0.0);
+  auto normal = [&]() { double u1 = r.unit(), u2 = r.unit(); if (u1 < 1e-12) u1 = 1e-12; return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2); };
+  for (int t = 0; t < 12; t++) {
+    const bool donor = (t == 0 || t == 6);
+    const double mu = donor ? -3.0 : -0.6, sd = donor ? 2.1 : 0.86;		/* donors: one factor; acceptors: five */
+    for (int k = 0; k < 16384; k++) RES.packed[(size_t) t * 16384 + k] = exp(mu + sd * normal());
+  }
+  for (int k = 0; k < 16; k++) {
+    RES.packed[GDP_ME_DONOR_DI_P + k] = (k == 14) ? 1.0 : 0.004;		/* GT */
+    RES.packed[GDP_ME_ACC_DI_P + k] = (k == 8) ? 1.0 : 0.004;		/* AG */
+    RES.packed[GDP_ME_DONOR_DI_M + k] = (k == 4) ? 1.0 : 0.004;		/* AC */
+    RES.packed[GDP_ME_ACC_DI_M + k] = (k == 13) ? 1.0 : 0.004;		/* CT */
+  }
+  const double *p = RES.packed.data();
+  gmapdp_maxent_tables &T = RES.tables;
+  T.donor_plus = p + GDP_ME_DONOR_P; T.acc1_plus = p + GDP_ME_ACC1_P; T.acc2_plus = p + GDP_ME_ACC2_P; T.acc3_plus = p + GDP_ME_ACC3_P;
+  T.acc467_plus = p + GDP_ME_ACC467_P; T.acc589_plus = p + GDP_ME_ACC589_P; T.donor_di_plus = p + GDP_ME_DONOR_DI_P; T.acc_di_plus = p + GDP_ME_ACC_DI_P;
+  T.donor_minus = p + GDP_ME_DONOR_M; T.acc1_minus = p + GDP_ME_ACC1_M; T.acc2_minus = p + GDP_ME_ACC2_M; T.acc3_minus = p + GDP_ME_ACC3_M;
+  T.acc467_minus = p + GDP_ME_ACC467_M; T.acc589_minus = p + GDP_ME_ACC589_M; T.donor_di_minus = p + GDP_ME_DONOR_DI_M; T.acc_di_minus = p + GDP_ME_ACC_DI_M;
+}
+
+inline void put_nt (uint32_t *blocks, uint64_t pos, char ch) {
+  const uint64_t ptr = (pos >> 5) * 3; const uint32_t j = (uint32_t) (pos & 31);
+  uint32_t code = 0;
+  switch (ch) { case 'A': code = 0; break; case 'C': code = 1; break; case 'G': code = 2; break; case 'T': code = 3; break;
+    default: blocks[ptr + 2] |= 1u << j; break; }
+  if (j < 16) blocks[ptr + 1] |= code << (2 * j); else blocks[ptr] |= code << (2 * (j - 16));
+}
+
+/* appends pad + seg + pad; returns the coordinate of seg[0] (-1: out of room) */
+int64_t place (uint32_t *blocks, size_t cap_words, uint64_t &used, const char *seg, int n) {
+  if (((used + (uint64_t) n + 2 * PAD) / 32 + 2) * 3 > cap_words) return -1;
+  used += PAD;				/* pads are 'A' = code 0 = the zero-filled state */
+  const uint64_t at = used;
+  for (int k = 0; k < n; k++) put_nt(blocks,at + k,seg[k]);
+  used += (uint64_t) n + PAD;
+  return (int64_t) at;
+}
+
+/* MaxEnt entries of a genome-gap box whose segments lie at posL / posR (the binding's mapping on the Watson strand,
+   integration/dynprog_sm100.c; dynprog_genome.c:970-1061) */
+void box_coords (const benchgen_box *b, uint64_t posL, uint64_t posR, uint64_t chrhigh, gmapdp_coords *co) {
+  memset(co,0,sizeof(*co));
+  co->chroffset = 0; co->chrhigh = (uint32_t) chrhigh;
+  co->gposL = (uint32_t) posL; co->gposR = (uint32_t) posR;
+  if (b->mode == GMAPDP_GENOME) {
+    co->probs = 1;
+    co->probkindL = b->cdna_direction > 0 ? GDP_ME_DONOR : GDP_ME_ANTIACCEPTOR; co->probposL = (uint32_t) posL; co->probnegL = 0;
+    co->probkindR = b->cdna_direction > 0 ? GDP_ME_ACCEPTOR : GDP_ME_ANTIDONOR; co->probposR = (uint32_t) (posR + b->glengthR); co->probnegR = 1;
+  }
+}
+}
+
+extern "C" int benchgen_resident_begin (uint64_t seed, uint64_t capacity_nt) {
+  free(RES.blocks);
+  RES.cap_words = (size_t) (capacity_nt / 32 + 4) * 3;
+  RES.blocks = (uint32_t *) calloc(RES.cap_words,sizeof(uint32_t));
+  RES.used_nt = 0;
+  synth_tables(seed);
+  RES.on = (RES.blocks != NULL);
+  return RES.on ? 0 : -1;
+}
+extern "C" void benchgen_resident_tables_only (uint64_t seed) { synth_tables(seed); RES.on = true; }	/* CPU workers: benchgen_make only */
+extern "C" void benchgen_resident_end (void) { free(RES.blocks); RES.blocks = NULL; RES.cap_words = 0; RES.used_nt = 0; RES.on = false; }
+extern "C" const uint32_t *benchgen_resident_blocks (uint64_t *used_words, uint64_t *cap_words) {
+  *used_words = (RES.used_nt / 32 + 2) * 3; *cap_words = RES.cap_words;
+  return RES.blocks;
+}
+extern "C" const gmapdp_maxent_tables *benchgen_resident_tables (void) { return &RES.tables; }
 
 extern "C" void benchgen_make (uint64_t seed, long i, benchgen_box *b, int small) {
   Rng r(seed * 1000003ull + (uint64_t) i);
@@ -133,6 +226,20 @@ extern "C" void benchgen_make (uint64_t seed, long i, benchgen_box *b, int small
     b->cdna_direction = k < 77 ? 1 : (k < 89 ? -1 : 0);
     b->extraband = 14; b->finalp = r.below(10) == 0; b->halfp = 0;
     probs(r,b->left_probs,gl - 1,a); probs(r,b->right_probs,gl - 1,bb);
+    if (RES.on) {
+      /* the MaxEnt values this box has in the resident genome: its two segments between pads, nothing else in reach */
+      uint32_t mini[((2 * BG_MAXSEQ + 4 * PAD) / 32 + 4) * 3];
+      memset(mini,0,sizeof(mini));
+      uint64_t used = 0;
+      const int64_t pL = place(mini,sizeof(mini) / 4,used,b->gsegL,gl), pR = place(mini,sizeof(mini) / 4,used,b->gsegR,gl);
+      gmapdp_coords co;
+      box_coords(b,(uint64_t) pL,(uint64_t) pR,used,&co);
+      GdpGenome G; G.blocks = mini; G.nwords = sizeof(mini) / 4;
+      for (int c = 0; c < gl - 1; c++) {
+	b->left_probs[c] = gdp_maxent_prob(co.probkindL,G,RES.packed.data(),co.probposL + (uint32_t) c,0);
+	b->right_probs[c] = gdp_maxent_prob(co.probkindR,G,RES.packed.data(),co.probposR - (uint32_t) c,0);
+      }
+    }
 
   } else {	/* cdna */
     const int g = r.range(lo,small ? 100 : 200), k = r.range(1,g - 1), ins = r.range(10,40);
@@ -189,7 +296,16 @@ extern "C" long benchgen_fill_batch (gmapdp_batch *batch, uint64_t seed, long i0
   for (long k = 0; k < n; k++) {
     const long i = i0 + k * stride;
     if (!((modemask >> (int) (i % 5)) & 1)) continue;	/* diagnostic runs on a subset of the modes */
-    benchgen_make(seed,i,b,small); benchgen_add(batch,b); added++;
+    benchgen_make(seed,i,b,small);
+    if (RES.on && RES.blocks) {
+      const int64_t pL = place(RES.blocks,RES.cap_words,RES.used_nt,b->gsegL,b->glength);
+      const int64_t pR = (b->mode == GMAPDP_GENOME) ? place(RES.blocks,RES.cap_words,RES.used_nt,b->gsegR,b->glengthR) : pL;
+      if (pL < 0 || pR < 0) { free(b); return -1; }
+      gmapdp_coords co;
+      box_coords(b,(uint64_t) pL,(uint64_t) pR,(uint64_t) (RES.cap_words / 3) * 32,&co);
+      GmapDP_batch_next_coords(batch,&co);
+    }
+    benchgen_add(batch,b); added++;
   }
   free(b);
   return added;

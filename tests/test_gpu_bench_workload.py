@@ -32,6 +32,30 @@ def test_benchmark_boxes_bit_exact_vs_oracle(engine):
     batch.free()
 
 
+def test_resident_form_of_the_workload_bit_exact_vs_oracle(engine):
+    """bench.py's default form: the boxes' segments in one synthetic genome resident on the device, boxes queued as
+    coordinates, MaxEnt (synthetic tables) evaluated on the device; the oracle gets the same boxes with characters and
+    the same probabilities as arrays"""
+    o = Oracle()
+    seed, n = 20241018, 400
+    batch = engine.batch()
+    try:
+        benchgen.resident_begin(batch, seed, n * 2600 + 1000000)
+        assert benchgen.fill_batch(batch, seed, 0, n, 1, False) == n
+        gbytes = benchgen.resident_attach(engine)
+        assert batch.h2d_bytes() < 2 * gbytes          # queries and box records only
+        batch.run()
+        hot = 0
+        for i in range(n):
+            box = benchgen.make(seed, i, small=False)
+            assert batch.result(i, box["mode"]) == o.run(box), (i, box["mode"])
+            hot += box["mode"] == "genome" and max(box["left_probs"]) > 0.9
+        assert hot > 10
+    finally:
+        benchgen.resident_end()
+        batch.free()
+
+
 def test_checksum_repeatable_and_chunking_independent(engine):
     import os
     from gmap_2024_b200 import Engine
