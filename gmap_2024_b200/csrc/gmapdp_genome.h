@@ -81,39 +81,52 @@ GDPG_HD uint64_t gdp_genome_window (const GdpGenome &g, uint32_t startpos) {
   return (cur >> (2u * shift)) | (nxt << (64u - 2u * shift));
 }
 
-GDPG_HD double gdp_maxent_prob (int kind, const GdpGenome &g, const double *T, uint32_t splice_pos, uint32_t chroffset) {
-  double odds;
-  if (kind == GDP_ME_DONOR) {
-    if (splice_pos < chroffset + 3u) return 0.0;
-    const uint32_t seq = (uint32_t) gdp_genome_window(g,splice_pos - 3u);
-    odds = T[GDP_ME_DONOR_P + ((seq & 0x3Fu) | ((seq >> 4) & 0x3FC0u))] * T[GDP_ME_DONOR_DI_P + ((seq >> 6) & 0x0Fu)];
-  } else if (kind == GDP_ME_ANTIDONOR) {
-    if (splice_pos < chroffset + 6u) return 0.0;
-    const uint32_t seq = (uint32_t) gdp_genome_window(g,splice_pos - 6u);
-    odds = T[GDP_ME_DONOR_M + ((seq & 0xFFu) | ((seq >> 4) & 0x3F00u))] * T[GDP_ME_DONOR_DI_M + ((seq >> 8) & 0x0Fu)];
-  } else if (kind == GDP_ME_ACCEPTOR) {
-    if (splice_pos < chroffset + 20u) return 0.0;
-    const uint64_t W = gdp_genome_window(g,splice_pos - 20u);
-    uint32_t seq;
-    odds = T[GDP_ME_ACC1_P + ((uint32_t) W & 0x3FFFu)];				/* 7-mer at +0 */
-    odds *= T[GDP_ME_ACC2_P + ((uint32_t) (W >> 14) & 0x3FFFu)];			/* 7-mer at +7 */
-    seq = (uint32_t) (W >> 28);								/* 9-mer at +14: 4 nt, skip 2, 3 nt */
-    odds *= T[GDP_ME_ACC3_P + ((seq & 0xFFu) | ((seq >> 4) & 0x3F00u))];
-    odds *= T[GDP_ME_ACC_DI_P + ((seq >> 8) & 0x0Fu)];
-    odds *= T[GDP_ME_ACC467_P + ((uint32_t) (W >> 8) & 0x3FFFu)];			/* 7-mer at +4 */
-    odds *= T[GDP_ME_ACC589_P + ((uint32_t) (W >> 22) & 0x3FFFu)];			/* 7-mer at +11 */
-  } else {
-    if (splice_pos < chroffset + 3u) return 0.0;
-    const uint64_t W = gdp_genome_window(g,splice_pos - 3u);
-    uint32_t seq;
-    odds = T[GDP_ME_ACC1_M + ((uint32_t) (W >> 32) & 0x3FFFu)];			/* 7-mer at +16 */
-    odds *= T[GDP_ME_ACC2_M + ((uint32_t) (W >> 18) & 0x3FFFu)];			/* 7-mer at +9 */
-    seq = (uint32_t) W;									/* 9-mer at +0: 3 nt, skip 2, 4 nt */
-    odds *= T[GDP_ME_ACC3_M + ((seq & 0x3Fu) | ((seq >> 4) & 0x3FC0u))];
-    odds *= T[GDP_ME_ACC_DI_M + ((seq >> 6) & 0x0Fu)];
-    odds *= T[GDP_ME_ACC467_M + ((uint32_t) (W >> 24) & 0x3FFFu)];			/* 7-mer at +12 */
-    odds *= T[GDP_ME_ACC589_M + ((uint32_t) (W >> 10) & 0x3FFFu)];			/* 7-mer at +5 */
+/* The evaluation as a sequence of passes, one large table per pass (the batch path evaluates all positions of all boxes
+   pass by pass with that table in shared memory, gmapdp_maxent_pass_kernel; gdp_maxent_prob below runs the same steps
+   back to back): window start = splice_pos - margin(kind); pass p multiplies the running odds by its table entry (and,
+   where the reference does, by the dinucleotide entry right after it); the last pass returns odds / (1 + odds). */
+GDPG_HD int gdp_maxent_margin (int kind) { return kind == GDP_ME_DONOR ? 3 : (kind == GDP_ME_ACCEPTOR ? 20 : (kind == GDP_ME_ANTIDONOR ? 6 : 3)); }
+GDPG_HD int gdp_maxent_npasses (int kind) { return (kind == GDP_ME_DONOR || kind == GDP_ME_ANTIDONOR) ? 1 : 5; }
+/* offset (in doubles) of the large table pass `pass' of `kind' reads */
+GDPG_HD int gdp_maxent_table (int kind, int pass) {
+  if (kind == GDP_ME_DONOR) return GDP_ME_DONOR_P;
+  if (kind == GDP_ME_ANTIDONOR) return GDP_ME_DONOR_M;
+  if (kind == GDP_ME_ACCEPTOR) return pass == 0 ? GDP_ME_ACC1_P : (pass == 1 ? GDP_ME_ACC2_P : (pass == 2 ? GDP_ME_ACC3_P : (pass == 3 ? GDP_ME_ACC467_P : GDP_ME_ACC589_P)));
+  return pass == 0 ? GDP_ME_ACC1_M : (pass == 1 ? GDP_ME_ACC2_M : (pass == 2 ? GDP_ME_ACC3_M : (pass == 3 ? GDP_ME_ACC467_M : GDP_ME_ACC589_M)));
+}
+/* big = the pass's large table (wherever it lives), T = the packed array (for the 16-entry dinucleotide tables) */
+GDPG_HD double gdp_maxent_step (int kind, int pass, uint64_t W, const double *big, const double *T, double odds) {
+  const uint32_t seq = (uint32_t) W;
+  if (kind == GDP_ME_DONOR) return big[(seq & 0x3Fu) | ((seq >> 4) & 0x3FC0u)] * T[GDP_ME_DONOR_DI_P + ((seq >> 6) & 0x0Fu)];
+  if (kind == GDP_ME_ANTIDONOR) return big[(seq & 0xFFu) | ((seq >> 4) & 0x3F00u)] * T[GDP_ME_DONOR_DI_M + ((seq >> 8) & 0x0Fu)];
+  if (kind == GDP_ME_ACCEPTOR) {
+    if (pass == 0) return big[seq & 0x3FFFu];						/* 7-mer at +0 */
+    if (pass == 1) return odds * big[(uint32_t) (W >> 14) & 0x3FFFu];			/* 7-mer at +7 */
+    if (pass == 2) {									/* 9-mer at +14: 4 nt, skip 2, 3 nt */
+      const uint32_t s9 = (uint32_t) (W >> 28);
+      odds *= big[(s9 & 0xFFu) | ((s9 >> 4) & 0x3F00u)];
+      return odds * T[GDP_ME_ACC_DI_P + ((s9 >> 8) & 0x0Fu)];
+    }
+    if (pass == 3) return odds * big[(uint32_t) (W >> 8) & 0x3FFFu];			/* 7-mer at +4 */
+    return odds * big[(uint32_t) (W >> 22) & 0x3FFFu];					/* 7-mer at +11 */
   }
+  if (pass == 0) return big[(uint32_t) (W >> 32) & 0x3FFFu];				/* 7-mer at +16 */
+  if (pass == 1) return odds * big[(uint32_t) (W >> 18) & 0x3FFFu];			/* 7-mer at +9 */
+  if (pass == 2) {									/* 9-mer at +0: 3 nt, skip 2, 4 nt */
+    odds *= big[(seq & 0x3Fu) | ((seq >> 4) & 0x3FC0u)];
+    return odds * T[GDP_ME_ACC_DI_M + ((seq >> 6) & 0x0Fu)];
+  }
+  if (pass == 3) return odds * big[(uint32_t) (W >> 24) & 0x3FFFu];			/* 7-mer at +12 */
+  return odds * big[(uint32_t) (W >> 10) & 0x3FFFu];					/* 7-mer at +5 */
+}
+
+GDPG_HD double gdp_maxent_prob (int kind, const GdpGenome &g, const double *T, uint32_t splice_pos, uint32_t chroffset) {
+  const uint32_t margin = (uint32_t) gdp_maxent_margin(kind);
+  if (splice_pos < chroffset + margin) return 0.0;
+  const uint64_t W = gdp_genome_window(g,splice_pos - margin);
+  const int np = gdp_maxent_npasses(kind);
+  double odds = 0.0;
+  for (int p = 0; p < np; p++) odds = gdp_maxent_step(kind,p,W,T + gdp_maxent_table(kind,p),T,odds);
   return odds / (1 + odds);
 }
 

@@ -40,7 +40,7 @@ struct GdpFlight {
   gmapdp_ctx *ctx;
   int max_boxes; size_t pool_cap, script_cap;	/* bytes; words */
   /* pinned host staging, filled in place by the submitting threads:
-       h_in   = [32 B control block, zero][boxes: n x 88 B][launch order: n x 4 B]   -- ONE H2D copy of 32 + 92 n bytes
+       h_in   = [32 B control block, zero][boxes: n x 96 B][launch order: n x 4 B]   -- ONE H2D copy of 32 + 100 n bytes
        h_pool = sequences and MaxEnt probabilities of the boxes (probabilities 8-aligned; a box's prob offsets are in
                 doubles from the start of the pool)                                    -- ONE H2D copy of the used bytes
        h_out  = [results: n x 64 B][script words]                                      -- ONE D2H copy */

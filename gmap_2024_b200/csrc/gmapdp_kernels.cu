@@ -1436,10 +1436,11 @@ struct KernelArgs {
   const GdpTables *tables;
   GdpGenome genome;		/* resident genome (blocks == NULL: none attached) */
   const double *maxent;		/* packed MaxEnt tables (gmapdp_genome.h) */
+  double *devprobs;		/* device-side pool of the MaxEnt arrays of GMAPDP_G_PROBS boxes (batch path) */
 };
 
 /* KIND: 0 single gaps (full fill), 1 end5/end3 (E-only fills + endpoint search), 2 genome gaps, 3 cdna gaps */
-template <int KIND>
+template <int KIND, bool INK>
 __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *bnd, const GdpTables *tb) {
   constexpr bool FULLK = (KIND == 0);
   constexpr bool twosided = (KIND >= 2);
@@ -1631,17 +1632,23 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 	gc.lp = ka.probs + b.probL_off; gc.rp = ka.probs + b.probR_off;
 	gc.rlength = b.rlenL; gc.lim = b.offdiff;
 	if (b.gflags & GMAPDP_G_PROBS) {
-	  gc.genome = ka.genome; gc.me = ka.maxent; gc.chroffset = b.chroffset;
-	  gc.lpos0 = b.probL_off; gc.rpos0 = b.probR_off;
-	  gc.lstep = (b.gflags & GMAPDP_G_PSTEP_NEG_L) ? -1 : +1; gc.rstep = (b.gflags & GMAPDP_G_PSTEP_NEG_R) ? -1 : +1;
-	  gc.lkind = b.probkindL; gc.rkind = b.probkindR; gc.nlp = b.glenL - 1; gc.nrp = b.glenR - 1;
-	  if ((reinterpret_cast<uintptr_t>(wp) & 7) != 0) wp++;
-	  double *lpb = reinterpret_cast<double *>(wp); wp += 2 * (size_t) (b.glenL + 1);
-	  double *rpb = reinterpret_cast<double *>(wp); wp += 2 * (size_t) (b.glenR + 1);
-	  for (int c = lane; c <= b.glenL; c += 32) lpb[c] = gen_maxent(gc,0,c);
-	  for (int c = lane; c <= b.glenR; c += 32) rpb[c] = gen_maxent(gc,1,c);
-	  gc.lp = lpb; gc.rp = rpb;
-	  __syncwarp();
+	  if (INK) {
+	    /* flights: the two arrays are evaluated here, into the workspace */
+	    gc.genome = ka.genome; gc.me = ka.maxent; gc.chroffset = b.chroffset;
+	    gc.lpos0 = b.probposL; gc.rpos0 = b.probposR;
+	    gc.lstep = (b.gflags & GMAPDP_G_PSTEP_NEG_L) ? -1 : +1; gc.rstep = (b.gflags & GMAPDP_G_PSTEP_NEG_R) ? -1 : +1;
+	    gc.lkind = b.probkindL; gc.rkind = b.probkindR; gc.nlp = b.glenL - 1; gc.nrp = b.glenR - 1;
+	    if ((reinterpret_cast<uintptr_t>(wp) & 7) != 0) wp++;
+	    double *lpb = reinterpret_cast<double *>(wp); wp += 2 * (size_t) (b.glenL + 1);
+	    double *rpb = reinterpret_cast<double *>(wp); wp += 2 * (size_t) (b.glenR + 1);
+	    for (int c = lane; c <= b.glenL; c += 32) lpb[c] = gen_maxent(gc,0,c);
+	    for (int c = lane; c <= b.glenR; c += 32) rpb[c] = gen_maxent(gc,1,c);
+	    gc.lp = lpb; gc.rp = rpb;
+	    __syncwarp();
+	  } else {
+	    /* batches: gmapdp_maxent_pass_kernel filled them in the context's device-side pool before this kernel started */
+	    gc.lp = ka.devprobs + b.probL_off; gc.rp = ka.devprobs + b.probR_off;
+	  }
 	}
 	gc.it0 = ((uint32_t) isc[0] << 8) | ((uint32_t) isc[1] << 16) | ((uint32_t) isc[2] << 24);
 	gc.it1 = (uint32_t) isc[3] | ((uint32_t) isc[4] << 8) | ((uint32_t) isc[5] << 16);
@@ -1731,7 +1738,7 @@ gmapdp_dp_kernel (KernelArgs ka) {
     if (lane == 0) idx = atomicAdd(ka.queue,1);
     idx = __shfl_sync(FULLMASK,idx,0);
     if (idx >= ka.nboxes) break;
-    process_box<KIND>(ka,ka.order[idx],ws,bnd,tb);
+    process_box<KIND,false>(ka,ka.order[idx],ws,bnd,tb);
   }
 }
 
@@ -1754,10 +1761,63 @@ gmapdp_dp_kernel_any (KernelArgs ka) {
     if (idx >= ka.nboxes) break;
     const int bi = ka.order[idx];
     const int mode = ka.boxes[bi].mode;
-    if (mode == GMAPDP_SINGLE) process_box<0>(ka,bi,ws,bnd,tb);
-    else if (mode == GMAPDP_GENOME) process_box<2>(ka,bi,ws,bnd,tb);
-    else if (mode == GMAPDP_CDNA) process_box<3>(ka,bi,ws,bnd,tb);
-    else process_box<1>(ka,bi,ws,bnd,tb);
+    if (mode == GMAPDP_SINGLE) process_box<0,true>(ka,bi,ws,bnd,tb);
+    else if (mode == GMAPDP_GENOME) process_box<2,true>(ka,bi,ws,bnd,tb);
+    else if (mode == GMAPDP_CDNA) process_box<3,true>(ka,bi,ws,bnd,tb);
+    else process_box<1,true>(ka,bi,ws,bnd,tb);
+  }
+}
+
+/* MaxEnt arrays of the genome-gap boxes of a batch, one large table per launch (gmapdp_genome.h: the passes of a kind).
+   The 128 KB table of the pass sits in shared memory -- the look-ups are what bounded the in-kernel evaluation (random
+   8-byte reads of 1.5 MB of tables through L2) -- and one warp walks one array, 32 consecutive positions per step:
+   genome words and the running odds (read-modify-write in the device-side pool) are coalesced.  One block per SM
+   (the table takes more than half of its shared memory).  kind: which of donor / acceptor / antidonor / antiacceptor
+   this launch serves; arrays of other kinds are skipped. */
+#define ME_PASS_THREADS 1024
+__global__ void __launch_bounds__(ME_PASS_THREADS,1)
+gmapdp_maxent_pass_kernel (const gmapdp_box *boxes, const int *order, int nboxes, GdpGenome g, const double *me, double *pool, int kind, int pass) {
+  extern __shared__ __align__(16) double me_table[];
+  {
+    const double *src = me + gdp_maxent_table(kind,pass);
+    for (int i = threadIdx.x; i < 16384; i += ME_PASS_THREADS) me_table[i] = src[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, nwarps = ME_PASS_THREADS / 32;
+  const int gw = blockIdx.x * nwarps + (threadIdx.x >> 5), stride = gridDim.x * nwarps;
+  const int last = gdp_maxent_npasses(kind) - 1;
+  const uint32_t margin = (uint32_t) gdp_maxent_margin(kind);
+  for (int a = gw; a < 2 * nboxes; a += stride) {		/* array a: side a & 1 of box order[a >> 1] */
+    const gmapdp_box &b = boxes[order[a >> 1]];
+    if (!(b.gflags & GMAPDP_G_PROBS)) continue;
+    const bool right = (a & 1) != 0;
+    if ((int) (right ? b.probkindR : b.probkindL) != kind) continue;
+    const int glen = right ? b.glenR : b.glenL;
+    const uint32_t pos0 = right ? b.probposR : b.probposL;
+    const int step = (b.gflags & (right ? GMAPDP_G_PSTEP_NEG_R : GMAPDP_G_PSTEP_NEG_L)) ? -1 : +1;
+    double * __restrict__ out = pool + (right ? b.probR_off : b.probL_off);
+    const uint32_t chroffset = b.chroffset;
+    /* four positions per lane and step, all loads issued before the first use: the walk is bound by the latency of
+       the genome words and of the running odds, not by arithmetic */
+    for (int c0 = lane; c0 <= glen; c0 += 128) {
+      uint64_t W[4]; double odds[4]; bool live[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+	const int c = c0 + 32 * u;
+	const uint32_t pos = pos0 + (uint32_t) (step * c);
+	live[u] = (c < glen - 1) && (pos >= chroffset + margin);
+	W[u] = live[u] ? gdp_genome_window(g,pos - margin) : 0ull;
+	odds[u] = (live[u] && pass > 0) ? out[c] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+	const int c = c0 + 32 * u;
+	if (live[u]) {
+	  const double o = gdp_maxent_step(kind,pass,W[u],me_table,me,odds[u]);
+	  out[c] = (pass == last) ? o / (1 + o) : o;
+	} else if (c <= glen && (c >= glen - 1 ? pass == 0 : pass == last)) out[c] = 0.0;	/* the calloc'ed tail of the reference's arrays; left of the chromosome */
+      }
+    }
   }
 }
 
@@ -1786,6 +1846,8 @@ struct gmapdp_ctx {
   cudaStream_t stream, copy_stream;
   std::vector<cudaEvent_t> chunk_events, chunk_done;
   const gmapdp_genome *genome = NULL;		/* attached resident genome + MaxEnt tables */
+  double *d_devprobs = NULL; size_t cap_devprobs = 0;	/* MaxEnt arrays evaluated on the device (GMAPDP_G_PROBS boxes) */
+  int me_kinds = 0;				/* bit k: some box of the planned batch has a probability array of kind k */
   cudaStream_t d2h_stream = 0;
   unsigned long long *h_cursors = NULL; size_t cap_cursors = 0;		/* pinned: the script cursor after each chunk */
   cudaEvent_t ev0, ev1;
@@ -1898,6 +1960,7 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   CK(cudaFuncSetAttribute(gmapdp_dp_kernel<2>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
   CK(cudaFuncSetAttribute(gmapdp_dp_kernel<3>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
   CK(cudaFuncSetAttribute(gmapdp_dp_kernel_any,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
+  CK(cudaFuncSetAttribute(gmapdp_maxent_pass_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,16384 * (int) sizeof(double)));
   ctx->grid = 0;
   return GMAPDP_OK;
 }
@@ -1906,7 +1969,7 @@ extern "C" void gmapdp_destroy (gmapdp_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->chain && ctx->chain_free) ctx->chain_free(ctx->chain);
-  cudaFree(ctx->d_tables); cudaFree(ctx->d_boxes); cudaFree(ctx->d_order); cudaFree(ctx->d_seq); cudaFree(ctx->d_probs);
+  cudaFree(ctx->d_tables); cudaFree(ctx->d_boxes); cudaFree(ctx->d_order); cudaFree(ctx->d_seq); cudaFree(ctx->d_probs); cudaFree(ctx->d_devprobs);
   cudaFree(ctx->d_results); cudaFree(ctx->d_script); cudaFree(ctx->d_cursor); cudaFree(ctx->d_queue); cudaFree(ctx->d_ws);
   for (int k = 0; k < GDP_NK; k++) cudaFree(ctx->d_kws[k]);
   for (void *g : ctx->grave) cudaFree(g);
@@ -1980,7 +2043,7 @@ static inline size_t kind_smem (const gmapdp_ctx *ctx, int kind) {
   return (size_t) WARPS_PER_BLOCK * ctx->ksmem_cols[kind] * 8;
 }
 
-struct PlanScan { size_t ws_words[GDP_NK], script_need; int maxcols[GDP_NK]; };
+struct PlanScan { size_t ws_words[GDP_NK], script_need, devprob_need; int maxcols[GDP_NK], me_kinds; };
 
 /* The kernels pack rows and columns into 16-bit fields (best cells `r << 16 | c', the bridges' keys, the cDNA
    bridge's `score << 16 | rR' tables) and the box carries its bands as int16: a side longer than 32767 would
@@ -2005,23 +2068,28 @@ static inline uint32_t box_upload_bytes (const gmapdp_box &x) {
 
 static int plan_scan (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, std::vector<std::pair<double,int> > &work,
 		      std::vector<uint32_t> *upload_bytes, PlanScan &ps) {
-  size_t ws_words[GDP_NK] = {0,0,0,0}, script_need = 0; int maxcols[GDP_NK] = {8,8,8,8};
+  size_t ws_words[GDP_NK] = {0,0,0,0}, script_need = 0, devprob_need = 0; int maxcols[GDP_NK] = {8,8,8,8}, me_kinds = 0;
   work.resize(nboxes);
   if (upload_bytes) upload_bytes->resize(nboxes);
   {
     /* per-box geometry (workspace words, script bound, work estimate) is the host's serial cost in front of the
        first launch of the end-to-end path: spread it over a few threads for large batches */
-    struct Part { size_t ws[GDP_NK], script; int cols[GDP_NK]; bool bad; };
+    struct Part { size_t ws[GDP_NK], script, devprob; int cols[GDP_NK], kinds; bool bad; };
     const int nthreads = (nboxes >= 65536) ? (int) std::min<unsigned>(8u,std::max(1u,std::thread::hardware_concurrency())) : 1;
     std::vector<Part> parts(nthreads);
     auto scan = [&](int t) {
       Part &pt = parts[t];
       for (int k = 0; k < GDP_NK; k++) { pt.ws[k] = 0; pt.cols[k] = 8; }
-      pt.script = 0; pt.bad = false;
+      pt.script = 0; pt.bad = false; pt.devprob = 0; pt.kinds = 0;
       const int i0 = (int) ((long long) nboxes * t / nthreads), i1 = (int) ((long long) nboxes * (t + 1) / nthreads);
       for (int i = i0; i < i1; i++) {
 	const gmapdp_box &b = boxes[i];
 	if (!box_ok(b) || (b.gflags && !ctx->genome)) { pt.bad = true; return; }
+	if (b.mode == GMAPDP_GENOME && (b.gflags & GMAPDP_G_PROBS)) {
+	  if (b.probkindL > 3 || b.probkindR > 3) { pt.bad = true; return; }
+	  pt.devprob = std::max(pt.devprob,std::max((size_t) b.probL_off + b.glenL + 1,(size_t) b.probR_off + b.glenR + 1));
+	  pt.kinds |= (1 << b.probkindL) | (1 << b.probkindR);
+	}
 	const int kind = kind_of(b.mode);
 	pt.ws[kind] = std::max(pt.ws[kind],gdp_ws_words(b));
 	pt.script += (size_t) b.rlenL + b.glenL + 4;
@@ -2042,10 +2110,11 @@ static int plan_scan (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, std:
       if (pt.bad) { ctx->err = "bad box"; return GMAPDP_ERR_ARG; }
       for (int kind = 0; kind < GDP_NK; kind++) { ws_words[kind] = std::max(ws_words[kind],pt.ws[kind]); maxcols[kind] = std::max(maxcols[kind],pt.cols[kind]); }
       script_need += pt.script;
+      devprob_need = std::max(devprob_need,pt.devprob); me_kinds |= pt.kinds;
     }
   }
   for (int k = 0; k < GDP_NK; k++) { ps.ws_words[k] = ws_words[k]; ps.maxcols[k] = maxcols[k]; }
-  ps.script_need = script_need;
+  ps.script_need = script_need; ps.devprob_need = devprob_need; ps.me_kinds = me_kinds;
   return GMAPDP_OK;
 }
 
@@ -2095,6 +2164,8 @@ static int plan_finish (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, si
   if (grow(ctx,&ctx->d_results,&ctx->cap_results,(size_t) nboxes)) return GMAPDP_ERR_CUDA;
   if (grow(ctx,&ctx->d_seq,&ctx->cap_seq,seqbytes + 16)) return GMAPDP_ERR_CUDA;
   if (grow(ctx,&ctx->d_probs,&ctx->cap_probs,nprobs + 2)) return GMAPDP_ERR_CUDA;
+  if (ps.devprob_need && grow(ctx,&ctx->d_devprobs,&ctx->cap_devprobs,ps.devprob_need + 2)) return GMAPDP_ERR_CUDA;
+  ctx->me_kinds = ps.me_kinds;
   if (grow(ctx,&ctx->d_script,&ctx->cap_script,script_need + 64)) return GMAPDP_ERR_CUDA;
   return GMAPDP_OK;
 }
@@ -2132,11 +2203,23 @@ static int launch_chunk (gmapdp_ctx *ctx, int first, const int *cnt, bool timed 
     ka.script = ctx->d_script; ka.script_cap = ctx->cap_script; ka.script_cursor = ctx->d_cursor;
     ka.queue = ctx->d_queue + kind; ka.ws = ctx->d_kws[kind]; ka.ws_words = ctx->kws_words[kind];
     ka.smem_cols = ctx->ksmem_cols[kind]; ka.tables = ctx->d_tables; ka.one = 1u;
-    ka.genome.blocks = ctx->genome ? ctx->genome->d_blocks : NULL; ka.genome.nwords = ctx->genome ? ctx->genome->nwords : 0; ka.maxent = ctx->genome ? ctx->genome->d_maxent : NULL;
+    ka.genome.blocks = ctx->genome ? ctx->genome->d_blocks : NULL; ka.genome.nwords = ctx->genome ? ctx->genome->nwords : 0; ka.maxent = ctx->genome ? ctx->genome->d_maxent : NULL; ka.devprobs = ctx->d_devprobs;
     const size_t smem = kind_smem(ctx,kind);
     const int grid = std::max(1,std::min(ctx->kgrid[kind],(count + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
     CK(cudaMemsetAsync(ctx->d_queue + kind,0,sizeof(int),st));
     if (timed) CK(cudaEventRecord(ctx->evk[kind][0],st));
+    if (kind == 2 && ctx->me_kinds && ctx->genome) {
+      /* the MaxEnt arrays of this chunk's genome gaps, pass by pass (counted with the genome kernel's time) */
+      for (int mk = 0; mk < 4; mk++) {
+	if (!((ctx->me_kinds >> mk) & 1)) continue;
+	for (int pass = 0; pass < gdp_maxent_npasses(mk); pass++) {
+	  gmapdp_maxent_pass_kernel<<<ctx->sm_count,ME_PASS_THREADS,16384 * sizeof(double),st>>>(ctx->d_boxes,ka.order,count,ka.genome,ka.maxent,
+												      ctx->d_devprobs,mk,pass);
+	  CK(cudaGetLastError());
+	  ctx->launches++;
+	}
+      }
+    }
     if (kind == 0) gmapdp_dp_kernel<0><<<grid,BLOCK_THREADS,smem,st>>>(ka);
     else if (kind == 1) gmapdp_dp_kernel<1><<<grid,BLOCK_THREADS,smem,st>>>(ka);
     else if (kind == 2) gmapdp_dp_kernel<2><<<grid,BLOCK_THREADS,smem,st>>>(ka);
@@ -2569,7 +2652,7 @@ int gdp_flight_launch (GdpFlight *f, int n, size_t poolbytes, size_t script_need
   ka.script_cursor = reinterpret_cast<unsigned long long *>(f->d_in + 8);		/* ... and script cursor, zeroed by the upload */
   ka.ws = ctx->d_kws[0]; ka.ws_words = wsw;
   ka.smem_cols = cols; ka.tables = ctx->d_tables; ka.one = 1u;
-  ka.genome.blocks = ctx->genome ? ctx->genome->d_blocks : NULL; ka.genome.nwords = ctx->genome ? ctx->genome->nwords : 0; ka.maxent = ctx->genome ? ctx->genome->d_maxent : NULL;
+  ka.genome.blocks = ctx->genome ? ctx->genome->d_blocks : NULL; ka.genome.nwords = ctx->genome ? ctx->genome->nwords : 0; ka.maxent = ctx->genome ? ctx->genome->d_maxent : NULL; ka.devprobs = ctx->d_devprobs;
   gmapdp_dp_kernel_any<<<grid,BLOCK_THREADS,smem,s0>>>(ka);
   FCK(cudaGetLastError());
   ctx->launches++;

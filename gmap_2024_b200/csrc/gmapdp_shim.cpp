@@ -348,6 +348,7 @@ struct gmapdp_batch {
   /* resident genome (GmapDP_batch_genome) and the coordinates of the next queued call (GmapDP_batch_next_coords) */
   const uint32_t *g_blocks = NULL; size_t g_nwords = 0; const gmapdp_maxent_tables *g_tables = NULL;
   gmapdp_coords next_co, cur_co; bool has_next_co = false, has_cur_co = false;
+  size_t devprob_need = 0;			/* doubles of device-evaluated probability arrays the queued boxes refer to */
   gmapdp_result *results = NULL; size_t nresults = 0;	/* pinned */
   uint32_t *script = NULL; size_t script_cap = 0;	/* pinned */
   size_t script_used = 0;
@@ -429,8 +430,12 @@ static bool take_coords (gmapdp_batch *b, Call &c, gmapdp_box &x, bool twosegmen
   }
   if (c.devp) {
     x.gflags |= GMAPDP_G_PROBS | (co.probnegL ? GMAPDP_G_PSTEP_NEG_L : 0) | (co.probnegR ? GMAPDP_G_PSTEP_NEG_R : 0);
-    x.probL_off = co.probposL; x.probR_off = co.probposR;
+    x.probposL = co.probposL; x.probposR = co.probposR;
     x.probkindL = (uint8_t) co.probkindL; x.probkindR = (uint8_t) co.probkindR;
+    /* room for the two arrays in the context's device-side pool (nothing is uploaded for them) */
+    x.probL_off = (uint32_t) b->devprob_need; b->devprob_need += (size_t) x.glenL + 1;
+    x.probR_off = (uint32_t) b->devprob_need; b->devprob_need += (size_t) x.glenR + 1;
+    if (b->devprob_need > 0xffffffffull) b->overflow = true;
   }
   return true;
 }
@@ -457,7 +462,7 @@ extern "C" void GmapDP_batch_next_coords (gmapdp_batch *b, const gmapdp_coords *
 
 extern "C" void GmapDP_batch_clear (gmapdp_batch *b) {
   unpin(b,/*release_buffers*/false);		/* result / script buffers are reused by the next batch */
-  b->calls.clear(); b->boxes.clear(); b->box_call.clear(); b->seqpool.clear(); b->probpool.clear();
+  b->calls.clear(); b->boxes.clear(); b->box_call.clear(); b->seqpool.clear(); b->probpool.clear(); b->devprob_need = 0;
   b->script_used = 0; b->cells = 0; b->cells8 = 0; b->cells_full = 0; b->cells8_full = 0; b->uploaded = false; b->overflow = false; b->err.clear();
   b->count_mismatch = 0;
 }

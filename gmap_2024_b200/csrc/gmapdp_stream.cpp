@@ -102,6 +102,8 @@ struct gmapdp_stream {
   size_t pool_cap = 0, script_cap = 0;
   std::string err;
   pthread_key_t lane_key; bool have_key = false;
+  std::vector<gmapdp_genome *> genomes;	/* one per device (gmapdp_stream_genome) */
+  std::atomic<int> genome_ready{0};
 };
 
 namespace {
@@ -344,6 +346,7 @@ extern "C" int gmapdp_stream_create (gmapdp_stream **out, const int *devices, in
 extern "C" void gmapdp_stream_destroy (gmapdp_stream *s) {
   if (!s) return;
   for (Lane *L : s->lanes) lane_destroy(L);
+  for (gmapdp_genome *g : s->genomes) gmapdp_genome_destroy(g);
   if (s->have_key) pthread_key_delete(s->lane_key);
   delete s;
 }
@@ -354,6 +357,28 @@ extern "C" const char *gmapdp_stream_error (const gmapdp_stream *s) {
 }
 extern "C" int gmapdp_stream_ndevices (const gmapdp_stream *s) { return s->ndevices; }
 
+/* Resident genome for every lane: one device copy per GPU (gmapdp_genome_create), attached to all of its lanes.  Call it
+   once, before the first box with gflags is submitted. */
+extern "C" int gmapdp_stream_genome (gmapdp_stream *s, const uint32_t *blocks, size_t nwords, const gmapdp_maxent_tables *maxent) {
+  if (s->genome_ready.load()) { s->err = "gmapdp_stream_genome: a genome is already resident"; return GMAPDP_ERR_ARG; }
+  for (int d = 0; d < s->ndevices; d++) {
+    Lane *L0 = s->lanes[(size_t) d * s->nclasses];
+    gmapdp_genome *g = NULL;
+    int rc = gmapdp_genome_create(&g,L0->device,blocks,nwords,maxent);
+    if (rc != GMAPDP_OK) { s->err = "gmapdp_stream_genome: upload failed"; return rc; }
+    s->genomes.push_back(g);
+    for (int c = 0; c < s->nclasses; c++) {
+      Lane *L = s->lanes[(size_t) d * s->nclasses + c];
+      pthread_mutex_lock(&L->mu);
+      rc = gmapdp_genome_attach(L->ctx,g);
+      pthread_mutex_unlock(&L->mu);
+      if (rc != GMAPDP_OK) { s->err = gmapdp_last_error(L->ctx); return rc; }
+    }
+  }
+  s->genome_ready.store(1);
+  return GMAPDP_OK;
+}
+
 extern "C" int gmapdp_stream_submit (gmapdp_stream *s, const gmapdp_box *box, const uint8_t *seq, size_t seqbytes,
 				     const double *probs, size_t nprobs, gmapdp_mailbox *mb) {
   GdpBoxGeom g;
@@ -362,6 +387,7 @@ extern "C" int gmapdp_stream_submit (gmapdp_stream *s, const gmapdp_box *box, co
   const size_t sb = align16(seqbytes), need = sb + nprobs * sizeof(double);
   if (need > s->pool_cap || g.script_words > s->script_cap) { tls_err = "box larger than a flight"; return GMAPDP_ERR_CAPACITY; }
   if (!mb || !mb->ops || mb->ops_cap < g.script_words) { tls_err = "mailbox too small for the box's edit script"; return GMAPDP_ERR_ARG; }
+  if (box->gflags && !s->genome_ready.load(std::memory_order_acquire)) { tls_err = "box refers to a resident genome, none was given (gmapdp_stream_genome)"; return GMAPDP_ERR_ARG; }
   /* a thread stays on one device for its lifetime; the lane there follows the box's size class */
   int di = (int) (intptr_t) pthread_getspecific(s->lane_key) - 1;
   if (di < 0) {
@@ -397,9 +423,11 @@ extern "C" int gmapdp_stream_submit (gmapdp_stream *s, const gmapdp_box *box, co
 
   mb->t_submit = t_now;
   gmapdp_box x = *box;
-  x.qL_off += (uint32_t) sbase; x.qR_off += (uint32_t) sbase; x.gL_off += (uint32_t) sbase; x.gLalt_off += (uint32_t) sbase;
-  x.gR_off += (uint32_t) sbase; x.gRalt_off += (uint32_t) sbase;
-  x.probL_off += (uint32_t) pbase; x.probR_off += (uint32_t) pbase;
+  x.qL_off += (uint32_t) sbase; x.qR_off += (uint32_t) sbase;
+  /* segments / probabilities that come from the resident genome are coordinates, not offsets into the flight's pool */
+  if (!(x.gflags & GMAPDP_G_SEG_L)) { x.gL_off += (uint32_t) sbase; x.gLalt_off += (uint32_t) sbase; }
+  if (!(x.gflags & GMAPDP_G_SEG_R)) { x.gR_off += (uint32_t) sbase; x.gRalt_off += (uint32_t) sbase; }
+  if (!(x.gflags & GMAPDP_G_PROBS)) { x.probL_off += (uint32_t) pbase; x.probR_off += (uint32_t) pbase; }
   gdp_flight_boxes(F->dev)[idx] = x;
   if (seqbytes) memcpy(F->dev->h_pool + sbase,seq,seqbytes);
   if (nprobs) memcpy(F->dev->h_pool + sbase + sb,probs,nprobs * sizeof(double));

@@ -27,7 +27,8 @@ class Box(C.Structure):
                 ("qL_off", C.c_uint32), ("qR_off", C.c_uint32), ("gL_off", C.c_uint32), ("gLalt_off", C.c_uint32),
                 ("gR_off", C.c_uint32), ("gRalt_off", C.c_uint32), ("probL_off", C.c_uint32), ("probR_off", C.c_uint32),
                 ("offdiff", C.c_int32), ("revmask", C.c_int32),
-                ("chroffset", C.c_uint32), ("chrhigh", C.c_uint32), ("gflags", C.c_uint16), ("probkindL", C.c_uint8), ("probkindR", C.c_uint8)]
+                ("chroffset", C.c_uint32), ("chrhigh", C.c_uint32), ("gflags", C.c_uint16), ("probkindL", C.c_uint8), ("probkindR", C.c_uint8),
+                ("probposL", C.c_uint32), ("probposR", C.c_uint32)]
 
 
 class Coords(C.Structure):

@@ -57,12 +57,13 @@ enum { GMAPDP_SINGLE = 0, GMAPDP_GENOME = 1, GMAPDP_CDNA = 2, GMAPDP_END5 = 3, G
 #define GMAPDP_G_NEG_R      0x08
 #define GMAPDP_G_LEFT_L     0x10	/* L segment was fetched "leftwards" (Genome_get_segment_left: '*' below chroffset); else */
 #define GMAPDP_G_LEFT_R     0x20	/*   "rightwards" (Genome_get_segment_right: '*' from chrhigh on) */
-#define GMAPDP_G_PROBS      0x40	/* genome mode: MaxEnt probabilities are computed on the device: probL_off / probR_off = */
-					/*   splice coordinate of entry 0 of the left / right array */
-#define GMAPDP_G_PSTEP_NEG_L 0x80	/* entry c of the left array is the coordinate probL_off - c (else + c) */
+#define GMAPDP_G_PROBS      0x40	/* genome mode: MaxEnt probabilities are computed on the device (probposL / probposR, probkindL / R); */
+					/*   probL_off / probR_off = offsets (doubles) of the two arrays (glength + 1 entries each) in the */
+					/*   context's device-side probability pool (batch path; flights evaluate into the workspace) */
+#define GMAPDP_G_PSTEP_NEG_L 0x80	/* entry c of the left array is the coordinate probposL - c (else + c) */
 #define GMAPDP_G_PSTEP_NEG_R 0x100
 
-/* One DP box (88 bytes).  Sequences live in one byte pool; every *_off is an unsigned byte offset into it (pool < 4 GiB).
+/* One DP box (96 bytes).  Sequences live in one byte pool; every *_off is an unsigned byte offset into it (pool < 4 GiB).
  * All sequence arrays are stored FORWARD (ascending memory = ascending coordinate); sides that the
  * reference addresses through "rev_" pointers set the corresponding REV flag bit in `revmask` and
  * are read from their last element backwards, exactly like rev_rsequence / rev_gsequence. */
@@ -83,6 +84,7 @@ typedef struct gmapdp_box {
   uint32_t chroffset, chrhigh;	/* bounds of the chromosome the segments lie on (Univcoord_T) */
   uint16_t gflags;		/* GMAPDP_G_* */
   uint8_t  probkindL, probkindR;	/* 0 donor, 1 acceptor, 2 antidonor, 3 antiacceptor (Maxent_hr_*_prob) */
+  uint32_t probposL, probposR;	/* GMAPDP_G_PROBS: splice coordinate of entry 0 of the left / right probability array */
 } gmapdp_box;
 
 /* Edit script: one uint32 per op, in traceback order (from the best cell back to the origin).

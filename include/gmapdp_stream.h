@@ -57,6 +57,9 @@ int gmapdp_stream_create (gmapdp_stream **s, const int *devices, int ndevices, i
 void gmapdp_stream_destroy (gmapdp_stream *s);
 const char *gmapdp_stream_error (const gmapdp_stream *s);
 int gmapdp_stream_ndevices (const gmapdp_stream *s);
+/* Resident genome and MaxEnt tables for every device of the stream (gmapdp_genome_create in gmapdp_b200.h): boxes may
+ * then carry genome coordinates (gflags).  Once, before the first such box. */
+int gmapdp_stream_genome (gmapdp_stream *s, const uint32_t *blocks, size_t nwords, const gmapdp_maxent_tables *maxent);
 
 /* Submits one box.  The box's *_off fields are offsets into `seq' / `probs' (as produced by the entry points of
  * gmapdp_shim.h on a private batch, GmapDP_batch_device_view); both arrays are copied before the call returns.

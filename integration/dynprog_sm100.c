@@ -71,6 +71,7 @@ static void sm100_die (const char *what) {
   exit(9);
 }
 
+static void sm100_report_genome (void);
 static void sm100_report (void) {
   double st[GMAPDP_STREAM_NSTATS];
   if (getenv("GMAP_SM100_STATS") == NULL || sm100_stream == NULL) return;
@@ -86,6 +87,7 @@ static void sm100_report (void) {
     fprintf(stderr,"gmap.sm100 host time in the entry points (thread-seconds): fetch+MaxEnt %.2f, prepare %.2f, submit %.2f, asleep %.2f, replay %.2f, list %.2f\n",
 	    sm100_prof[0] / hz,sm100_prof[1] / hz,sm100_prof[2] / hz,sm100_prof[3] / hz,sm100_prof[4] / hz,sm100_prof[5] / hz);
   }
+  sm100_report_genome();
   fprintf(stderr,"gmap.sm100 start-up: %.3f s to create the runtime (contexts, pinned staging, device buffers)\n",sm100_t_init);
   fprintf(stderr,"gmap.sm100 service threads: scheduling mode %d (1 FIFO, 2 short slices, 3 default)\n",gmapdp_stream_sched_mode(sm100_stream));
   {
@@ -209,6 +211,7 @@ Dynprog_end_setup (Univcoord_T *splicesites_in, Splicetype_T *splicetypes_in, Ch
 typedef struct sm100_thread {
   gmapdp_batch *batch;
   gmapdp_mailbox mailbox;
+  int has_genome;		/* the batch knows the resident genome (GmapDP_batch_genome) */
 } sm100_thread;
 
 static void sm100_free_thread_fwd (void *p);
@@ -235,6 +238,72 @@ static sm100_thread *my_thread (Dynprog_T dynprog) {
   return t;
 }
 static gmapdp_batch *my_batch (Dynprog_T dynprog) { return my_thread(dynprog)->batch; }
+static sm100_thread *cur_thread (void) { return (sm100_thread *) pthread_getspecific(sm100_key); }	/* after my_batch */
+
+/* ------------------------------------------------------------------------------------------------
+ * Resident genome.  The first DP call hands the process's genome -- the reference's own
+ * compressed blocks, Genome_blocks(genome), read in place -- and the MaxEnt tables (maxent_sm100.c) to the runtime, which
+ * copies them to every device once.  From then on a call announces genome COORDINATES (GmapDP_batch_next_coords) and
+ * the device decodes the segments and evaluates Maxent_hr_*_prob itself: nothing genomic is uploaded per call, and the
+ * binding no longer computes the probability arrays of dynprog_genome.c:970-1061 on the host.  The characters are
+ * still fetched here: the pair lists carry them.  Only when genomealt == genome (no SNP-tolerant alignment) and the
+ * blocks are in memory; GMAP_SM100_RESIDENT=0 keeps the upload form.
+ * ---------------------------------------------------------------------------------------------- */
+extern void sm100_maxent_tables (gmapdp_maxent_tables *t);
+static pthread_mutex_t sm100_genome_mu = PTHREAD_MUTEX_INITIALIZER;
+static const Genomecomp_T *sm100_gblocks = NULL;
+static size_t sm100_gwords = 0;
+static volatile int sm100_genome_state = 0;		/* 0 not tried yet, 1 resident, -1 not available */
+static unsigned long sm100_ncoords = 0;			/* calls announced as genome coordinates */
+static gmapdp_maxent_tables sm100_me;
+
+static bool sm100_resident (sm100_thread *t, Genome_T genome, Genome_T genomealt) {
+  const Genomecomp_T *blocks;
+  if (sm100_genome_state < 0 || genome == NULL) return false;
+  blocks = Genome_blocks(genome);
+  if (blocks == NULL || (genomealt != genome && Genome_blocks(genomealt) != blocks)) return false;
+  if (sm100_genome_state == 0) {
+    pthread_mutex_lock(&sm100_genome_mu);
+    if (sm100_genome_state == 0) {
+      const char *e = getenv("GMAP_SM100_RESIDENT");
+      if (e && atoi(e) == 0) sm100_genome_state = -1;
+      else {
+	const size_t nwords = (((size_t) Genome_genomelength(genome) + 31) / 32) * 3;
+	sm100_maxent_tables(&sm100_me);
+	if (gmapdp_stream_genome(sm100_stream,(const uint32_t *) blocks,nwords,&sm100_me) == GMAPDP_OK) {
+	  sm100_gblocks = blocks; sm100_gwords = nwords;
+	  __sync_synchronize();
+	  sm100_genome_state = 1;
+	} else {
+	  fprintf(stderr,"gmap.sm100: genome not made resident (%s): genomic segments are uploaded per call\n",gmapdp_stream_error(sm100_stream));
+	  sm100_genome_state = -1;
+	}
+      }
+    }
+    pthread_mutex_unlock(&sm100_genome_mu);
+  }
+  if (sm100_genome_state != 1 || blocks != sm100_gblocks) return false;
+  if (!t->has_genome) { GmapDP_batch_genome(t->batch,(const uint32_t *) sm100_gblocks,sm100_gwords,&sm100_me); t->has_genome = 1; }
+  __sync_fetch_and_add(&sm100_ncoords,1);
+  return true;
+}
+
+static void sm100_report_genome (void) {
+  fprintf(stderr,"gmap.sm100 genome: %s, %lu calls sent as coordinates (%.1f MB of blocks per device)\n",
+	  sm100_genome_state == 1 ? "resident on the device" : "uploaded per call",sm100_ncoords,4e-6 * (double) sm100_gwords);
+}
+
+/* where the arrays of the fetches below lie in the genome: "forward" = the segment fetched from goffset on
+   (Genome_get_segment_right on the Watson strand, _left + revcomp on the Crick strand), "backward" = the segment that
+   ends at rev_goffset */
+static void sm100_seg_forward (bool watsonp, Univcoord_T chroffset, Univcoord_T chrhigh, int goffset, uint32_t *gpos, int *neg, int *left) {
+  if (watsonp) { *gpos = (uint32_t) (chroffset + goffset); *neg = 0; *left = 0; }
+  else { *gpos = (uint32_t) (chrhigh - goffset); *neg = 1; *left = 1; }
+}
+static void sm100_seg_backward (bool watsonp, Univcoord_T chroffset, Univcoord_T chrhigh, int rev_goffset, int glength, uint32_t *gpos, int *neg, int *left) {
+  if (watsonp) { *gpos = (uint32_t) (chroffset + rev_goffset + 1 - glength); *neg = 0; *left = 1; }
+  else { *gpos = (uint32_t) (chrhigh - rev_goffset + glength - 1); *neg = 1; *left = 0; }
+}
 
 /* runs the call queued in this thread's batch; afterwards GmapDP_result_view(b,id,...) has the result */
 static void run_call (gmapdp_batch *b) {
@@ -308,6 +377,13 @@ Dynprog_single_gap (int *dynprogindex, int *traceback_score, int *nmatches, int 
   } else {
     gseq = galt = empty;
   }
+  if (fetch && sm100_resident(cur_thread(),genome,genomealt)) {
+    gmapdp_coords co;
+    memset(&co,0,sizeof(co));
+    co.chroffset = (uint32_t) chroffset; co.chrhigh = (uint32_t) chrhigh;
+    sm100_seg_forward(watsonp,chroffset,chrhigh,goffset,&co.gposL,&co.negL,&co.leftL);
+    GmapDP_batch_next_coords(b,&co);
+  }
   PROF_MARK(0);
   id = GmapDP_single_gap(b,*dynprogindex,rsequence,rsequenceuc,rlength,glength,roffset,goffset,gseq,galt,
 			 jump_late_p,extraband_single,widebandp,defect_rate);
@@ -351,6 +427,14 @@ end_gap (bool end5, int *dynprogindex, int *traceback_score, int *nmatches, int 
     }
   } else {
     gseq = galt = empty;
+  }
+  if (fetch && sm100_resident(cur_thread(),genome,genomealt)) {
+    gmapdp_coords co;
+    memset(&co,0,sizeof(co));
+    co.chroffset = (uint32_t) chroffset; co.chrhigh = (uint32_t) chrhigh;
+    if (end5) sm100_seg_backward(watsonp,chroffset,chrhigh,goffset,gl,&co.gposL,&co.negL,&co.leftL);
+    else sm100_seg_forward(watsonp,chroffset,chrhigh,goffset,&co.gposL,&co.negL,&co.leftL);
+    GmapDP_batch_next_coords(b,&co);
   }
   PROF_MARK(0);
   if (end5) id = GmapDP_end5_gap(b,*dynprogindex,rseq,rsequc,rlength,glength,roffset,goffset,gseq,galt,jump_late_p,
@@ -425,7 +509,6 @@ Dynprog_genome_gap (int *dynprogindex, int *new_leftgenomepos, int *new_rightgen
   if (fetch) {
     gL = (char *) malloc(glengthL + 1); gLa = (char *) malloc(glengthL + 1);
     gR = (char *) malloc(glengthR + 1); gRa = (char *) malloc(glengthR + 1);
-    lp = (double *) calloc(glengthL + 1,sizeof(double)); rp = (double *) calloc(glengthR + 1,sizeof(double));
     if (watsonp) {
       Genome_get_segment_right(gL,gLa,genome,genomealt,chroffset+goffsetL,glengthL,chrhigh,/*revcomp*/false);
       Genome_get_segment_left(gR,gRa,genome,genomealt,chroffset+rev_goffsetR+1,glengthR,chroffset,/*revcomp*/false);
@@ -433,6 +516,25 @@ Dynprog_genome_gap (int *dynprogindex, int *new_leftgenomepos, int *new_rightgen
       Genome_get_segment_left(gL,gLa,genome,genomealt,chrhigh-goffsetL+1,glengthL,chroffset,/*revcomp*/true);
       Genome_get_segment_right(gR,gRa,genome,genomealt,chrhigh-rev_goffsetR,glengthR,chrhigh,/*revcomp*/true);
     }
+    if (sm100_resident(cur_thread(),genome,genomealt)) {
+      /* the probability arrays of dynprog_genome.c:970-1061 as coordinates: entry c of the left / right array is the
+	 probability of the given kind at probpos +- c; the device evaluates them (gmapdp_genome.h) */
+      gmapdp_coords co;
+      memset(&co,0,sizeof(co));
+      co.chroffset = (uint32_t) chroffset; co.chrhigh = (uint32_t) chrhigh;
+      sm100_seg_forward(watsonp,chroffset,chrhigh,goffsetL,&co.gposL,&co.negL,&co.leftL);
+      sm100_seg_backward(watsonp,chroffset,chrhigh,rev_goffsetR,glengthR,&co.gposR,&co.negR,&co.leftR);
+      co.probs = 1;
+      if (watsonp) {
+	co.probposL = (uint32_t) (chroffset + goffsetL); co.probnegL = 0; co.probkindL = (cdna_direction > 0) ? 0 : 3;
+	co.probposR = (uint32_t) (chroffset + rev_goffsetR + 1); co.probnegR = 1; co.probkindR = (cdna_direction > 0) ? 1 : 2;
+      } else {
+	co.probposL = (uint32_t) (chrhigh - goffsetL + 1); co.probnegL = 1; co.probkindL = (cdna_direction > 0) ? 2 : 1;
+	co.probposR = (uint32_t) (chrhigh - rev_goffsetR); co.probnegR = 0; co.probkindR = (cdna_direction > 0) ? 3 : 0;
+      }
+      GmapDP_batch_next_coords(b,&co);
+    } else {
+    lp = (double *) calloc(glengthL + 1,sizeof(double)); rp = (double *) calloc(glengthR + 1,sizeof(double));
     /* the probability arrays of dynprog_genome.c:970-1061 */
     if (watsonp) {
       for (c = 0; c < glengthL - 1; c++) {
@@ -452,6 +554,7 @@ Dynprog_genome_gap (int *dynprogindex, int *new_leftgenomepos, int *new_rightgen
 	pos = chrhigh - rev_goffsetR + c;
 	rp[c] = (cdna_direction > 0) ? Maxent_hr_antiacceptor_prob(genome,genomealt,pos,chroffset) : Maxent_hr_donor_prob(genome,genomealt,pos,chroffset);
       }
+    }
     }
   } else {
     gL = gLa = gR = gRa = empty;
@@ -504,6 +607,13 @@ Dynprog_cdna_gap (int *dynprogindex, int *traceback_score, bool *incompletep,
     }
   } else {
     g = ga = rg = rga = empty;
+  }
+  if (fetch && sm100_resident(cur_thread(),genome,genomealt)) {
+    gmapdp_coords co;
+    memset(&co,0,sizeof(co));
+    co.chroffset = (uint32_t) chroffset; co.chrhigh = (uint32_t) chrhigh;
+    sm100_seg_forward(watsonp,chroffset,chrhigh,goffset,&co.gposL,&co.negL,&co.leftL);
+    GmapDP_batch_next_coords(b,&co);		/* taken only if both fetches gave the same characters (no chromosome edge) */
   }
   PROF_MARK(0);
   id = GmapDP_cdna_gap(b,*dynprogindex,rsequenceL,rsequence_ucL,rev_rsequenceR,rev_rsequence_ucR,rlengthL,rlengthR,glength,

@@ -121,7 +121,7 @@ def test_user_penalties_reach_the_box(lib):
     ptr, n, _, _, _, _ = b.device_view()
 
     from gmap_2024_b200.engine import Box
-    assert C.sizeof(Box) == 88
+    assert C.sizeof(Box) == 96
     seen = set()
     for k in range(n):
         x = Box.from_address(ptr.value + C.sizeof(Box) * k)
