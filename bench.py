@@ -467,6 +467,32 @@ def run_ours(args):
                                      "genome": sm["kind_ms"][2] / args.steps, "cdna": sm["kind_ms"][3] / args.steps}}
         sb.free()
 
+    # third stratum: the input decorations of SURVEY.md section 8d (N in the genome, lower-case / IUPAC query characters,
+    # tandem repeats) on the same generator
+    decorated = None
+    if args.decorated_boxes > 0 and not args.small:
+        db = eng.batch(2000, 2030)
+        j0, j1 = shard_range(rank, world, args.decorated_boxes)
+        if resident:
+            benchgen.resident_begin(db, args.seed, (j1 - j0) * 2600 + 1000000)
+        if benchgen.fill_batch(db, args.seed, j0, j1 - j0, 1, False, args.modemask, decor=True) < 0:
+            raise SystemExit("bench.py: the synthetic genome outgrew its buffer")
+        if resident:
+            benchgen.resident_attach(eng)
+        d_cells = db.cells()
+        dm = measure_batch(eng, db, args, barrier)
+        d_dev, d_e2e = allreduce(dm["dev_ms"], MAX), allreduce(dm["e2e_ms"], MAX)
+        d_tot = allreduce(d_cells, SUM)
+        tot_launches += allreduce(dm["launches"], SUM)
+        if rank == 0:
+            decorated = {"config": {"workload": "the same generator with 0.3 % N in the genomic segments, 0.2 % lower-case and 0.1 % IUPAC query "
+                                                "characters, 5 % of the single gaps tandem repeats (SURVEY.md section 8d)",
+                                    "boxes_per_gpu": args.decorated_boxes, "cells_per_step": int(d_tot)},
+                         "value": d_tot / (d_dev / args.steps / 1e3) / 1e9, "unit": UNIT, "ms_per_step": d_dev / args.steps,
+                         "e2e": {"value": d_tot / (d_e2e / args.steps / 1e3) / 1e9, "unit": UNIT, "ms_per_step": d_e2e / args.steps},
+                         "digest": "%016x" % dm["digest"]}
+        db.free()
+
     chain = None
     if args.chain_problems > 0:
         chain = chain_section(eng, args, rank, world, barrier, allreduce, MAX, SUM)
@@ -539,6 +565,8 @@ def run_ours(args):
                 "gpu_launches": int(tot_launches), "clocks": clocks, "digest": "%016x" % m["digest"]}
         if stratum is not None:
             line["strata"] = {"production": stratum}
+        if decorated is not None:
+            line.setdefault("strata", {})["decorated"] = decorated
         if chain is not None:
             line["chain"] = chain
             line["gpu_launches"] += chain["gpu_launches"]
@@ -579,6 +607,7 @@ def main():
     ap.add_argument("--chain-distinct", type=int, default=256)
     ap.add_argument("--chain-cpu-seconds", type=float, default=5.0)
     ap.add_argument("--stratum-boxes", type=int, default=1000000, help="production-size boxes per GPU for strata.production (0 = skip)")
+    ap.add_argument("--decorated-boxes", type=int, default=200000, help="boxes per GPU for strata.decorated (0 = skip)")
     ap.add_argument("--program-cdnas", type=int, default=3000, help="whole-program leg: synthetic cDNAs (0 = skip)")
     ap.add_argument("--program-genome-mb", type=int, default=20)
     ap.add_argument("--program-threads", default="128,256", help="gmap.sm100 -t values to try (the best identical run is reported)")

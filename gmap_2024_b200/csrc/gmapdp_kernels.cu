@@ -1439,6 +1439,14 @@ struct KernelArgs {
   double *devprobs;		/* device-side pool of the MaxEnt arrays of GMAPDP_G_PROBS boxes (batch path) */
 };
 
+/* one segment of a resident-genome box into the workspace, lanes over positions (out of line: its registers are not
+   the box loop's) */
+__device__ __noinline__ void decode_segment (GdpGenome g, uint32_t p0, int n, bool neg, bool left, uint32_t chroffset, uint32_t chrhigh, uint8_t *seg) {
+  const int dir = neg ? -1 : +1;
+  const uint32_t lo = left ? chroffset : 0u, hi = left ? 0xffffffffu : chrhigh;
+  for (int i = (int) (threadIdx.x & 31); i < n; i += 32) seg[i] = (uint8_t) gdp_segment_char(g,p0,dir,i,lo,hi);
+}
+
 /* KIND: 0 single gaps (full fill), 1 end5/end3 (E-only fills + endpoint search), 2 genome gaps, 3 cdna gaps */
 template <int KIND, bool INK>
 __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *bnd, const GdpTables *tb) {
@@ -1474,17 +1482,13 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
      :11079), everything downstream reads them like uploaded ones; genomealt == genome */
   if (b.gflags & GMAPDP_G_SEG_L) {
     uint8_t *seg = bytes; bytes += gdp_align16(b.glenL + 2);
-    const int dir = (b.gflags & GMAPDP_G_NEG_L) ? -1 : +1;
-    const bool left = (b.gflags & GMAPDP_G_LEFT_L) != 0;
-    for (int i = lane; i < b.glenL; i += 32) seg[i] = (uint8_t) gdp_segment_char(ka.genome,b.gL_off,dir,i,left ? b.chroffset : 0u,left ? 0xffffffffu : b.chrhigh);
+    decode_segment(ka.genome,b.gL_off,b.glenL,(b.gflags & GMAPDP_G_NEG_L) != 0,(b.gflags & GMAPDP_G_LEFT_L) != 0,b.chroffset,b.chrhigh,seg);
     L.G = L.Ga = seg;
     if (!twosided || !(b.gflags & GMAPDP_G_SEG_R)) { R.G = R.Ga = seg; }		/* single / end / cdna: one segment */
   }
   if (twosided && (b.gflags & GMAPDP_G_SEG_R)) {
     uint8_t *seg = bytes; bytes += gdp_align16(b.glenR + 2);
-    const int dir = (b.gflags & GMAPDP_G_NEG_R) ? -1 : +1;
-    const bool left = (b.gflags & GMAPDP_G_LEFT_R) != 0;
-    for (int i = lane; i < b.glenR; i += 32) seg[i] = (uint8_t) gdp_segment_char(ka.genome,b.gR_off,dir,i,left ? b.chroffset : 0u,left ? 0xffffffffu : b.chrhigh);
+    decode_segment(ka.genome,b.gR_off,b.glenR,(b.gflags & GMAPDP_G_NEG_R) != 0,(b.gflags & GMAPDP_G_LEFT_R) != 0,b.chroffset,b.chrhigh,seg);
     R.G = R.Ga = seg;
   }
   if (b.gflags & (GMAPDP_G_SEG_L | GMAPDP_G_SEG_R)) __syncwarp();
@@ -1707,7 +1711,7 @@ extern __shared__ __align__(16) unsigned char dyn_smem[];
 /* Four specialisations of one persistent kernel, one per kind of box: single gaps (full fill: needs the big
    shared-memory boundary rows, 3 blocks/SM), end gaps, genome gaps, cdna gaps (E-only fills, bridges: almost
    no shared memory).  A specialisation carries only its own mode's code, so the warps of an SM share their
-   instruction-cache footprint; the four are launched on four streams and share the SMs. */
+   instruction-cache footprint; the four are queued back to back on one stream (launch_chunk). */
 #ifndef GMAPDP_FULL_MINB
 #define GMAPDP_FULL_MINB (GMAPDP_BND_GLOBAL ? 4 : 3)
 #endif
@@ -2179,7 +2183,7 @@ static int plan_batch (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, siz
   return plan_finish(ctx,boxes,nboxes,seqbytes,nprobs,chunk_begin,order,work,sort_now,ps);
 }
 
-/* launches the (up to) four kernels of one chunk, each on its own stream (kstream[0] == stream); all four
+/* launches the (up to) four kernels of one chunk (on one stream unless GMAPDP_STREAMS is set; kstream[0] == stream); all
    streams must already be ordered after the chunk's uploads.  cnt[kind] boxes of each kind, laid out kind
    by kind in `order' from `first'. */
 static int launch_chunk (gmapdp_ctx *ctx, int first, const int *cnt, bool timed = false) {
@@ -2548,8 +2552,8 @@ extern "C" int gmapdp_run_batch_chunks (gmapdp_ctx *ctx, const gmapdp_box *boxes
  * large batch (parallel planning, chunked uploads); a drop-in that serves the dependent DP calls of many worker
  * threads needs the opposite: thousands of small batches per second with a few tens of microseconds of fixed
  * cost each.  A flight owns pinned host staging that the submitting threads fill in place, device twins of it,
- * and is run by three H2D copies, one memset, up to four kernels (each kind on its own stream: the kernels of a
- * small flight do not fill the GPU, so they run side by side) and ONE D2H copy of cursor + results + script.
+ * and is run by two H2D copies, ONE all-kinds kernel (gmapdp_dp_kernel_any: a small flight does not fill the GPU, so
+ * its boxes of all kinds share one grid) and ONE D2H copy of cursor + results + script.
  * Nothing is allocated, planned or synchronised per flight besides what follows.
  * ---------------------------------------------------------------------------------------------- */
 int gdp_bucket_count (void) { return GDP_NK * GDP_WORK_BUCKETS; }

@@ -1,6 +1,6 @@
 """Rank sharding of a box stream: boxes are independent, so rank k of N owns a
 contiguous block of box indices; the only cross-rank traffic is the reduction of a few scalars
-(timing, cell counts, digests) -- `torch.distributed` all_reduce on whatever backend the job runs
+(timing, cell counts; 64-bit digests are compared per rank, not reduced: the reduction goes through float64) -- `torch.distributed` all_reduce on whatever backend the job runs
 (NCCL on the GPU box, gloo in the CPU tests)."""
 
 

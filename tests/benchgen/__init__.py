@@ -80,14 +80,15 @@ def resident_tables_only(seed):
     lib().benchgen_resident_tables_only(C.c_uint64(seed))
 
 
-def fill_batch(batch, seed, i0, n, stride=1, small=False, modemask=31):
-    return lib().benchgen_fill_batch(batch.h, C.c_uint64(seed), C.c_long(i0), C.c_long(n), C.c_long(stride), int(small),
+def fill_batch(batch, seed, i0, n, stride=1, small=False, modemask=31, decor=False):
+    """decor: the decorated stratum (N in the genome, lower-case / IUPAC query characters, tandem repeats)"""
+    return lib().benchgen_fill_batch(batch.h, C.c_uint64(seed), C.c_long(i0), C.c_long(n), C.c_long(stride), int(bool(small)) | (2 if decor else 0),
                                      int(modemask))
 
 
-def make(seed, i, small=False, max_r=2000, max_g=2030):
+def make(seed, i, small=False, max_r=2000, max_g=2030, decor=False):
     b = Box()
-    lib().benchgen_make(C.c_uint64(seed), C.c_long(i), C.byref(b), int(small))
+    lib().benchgen_make(C.c_uint64(seed), C.c_long(i), C.byref(b), int(bool(small)) | (2 if decor else 0))
     m = MODES[b.mode]
     q = b.query[:b.querylength] if isinstance(b.query, bytes) else bytes(b.query)[:b.querylength]
     d = {"mode": m, "queryseq": q.decode("latin1"), "defect_rate": b.defect_rate, "jump_late_p": b.jump_late_p,

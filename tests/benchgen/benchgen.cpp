@@ -11,6 +11,11 @@
  *   per-base error 0.1 / 1 / 5 / 15 % (60 % substitution, 20 % deletion, 20 % insertion), defect_rate equal to it
  * Box i depends only on (seed, i).
  *
+ * Decorated stratum (`small' bit 1; SURVEY.md section 8d's input decorations): 0.3 % N in the genomic segments, 0.2 %
+ * lower-case and 0.1 % IUPAC characters in the query, and 5 % of the single-gap boxes tandem repeats (unit 16-24 nt, the
+ * query rotated by 7-9 units of the band so that the matching diagonal sits below it: what exposes the 8-bit stripe
+ * artefact F11).
+ *
  * Resident-genome form (benchgen_resident_begin; bench.py's default): the genomic segments of the boxes are laid out,
  * each between 32-nt pads, in one synthetic genome in the reference's compressed block layout; boxes are queued as
  * COORDINATES into it (GmapDP_batch_next_coords) and the splice-site probabilities of genome gaps are MaxEnt values
@@ -166,7 +171,23 @@ extern "C" const uint32_t *benchgen_resident_blocks (uint64_t *used_words, uint6
 }
 extern "C" const gmapdp_maxent_tables *benchgen_resident_tables (void) { return &RES.tables; }
 
-extern "C" void benchgen_make (uint64_t seed, long i, benchgen_box *b, int small) {
+namespace {
+void decorate_genome (Rng &r, char *g, int n) {
+  for (int k = 0; k < n; k++) if (r.below(1000) < 3) g[k] = 'N';
+}
+void decorate_query (Rng &r, char *q, char *quc, int n) {
+  static const char iupac[7] = {'R','Y','W','S','M','K','N'};
+  for (int k = 0; k < n; k++) {
+    const int x = r.below(1000);
+    if (x < 1) { q[k] = quc[k] = iupac[r.below(7)]; }
+    else if (x < 3) q[k] = (char) (quc[k] | 0x20);		/* lower case in the query, upper case in its uc twin */
+  }
+}
+}
+
+extern "C" void benchgen_make (uint64_t seed, long i, benchgen_box *b, int small_flags) {
+  const int small = small_flags & 1;
+  const bool decor = (small_flags & 2) != 0;
   Rng r(seed * 1000003ull + (uint64_t) i);
   static const double errs[4] = {0.001, 0.01, 0.05, 0.15};
   memset(b,0,offsetof(benchgen_box,query));
@@ -183,6 +204,12 @@ extern "C" void benchgen_make (uint64_t seed, long i, benchgen_box *b, int small
   if (b->mode == GMAPDP_SINGLE) {
     const int g = r.range(lo,hi);
     rand_dna(r,b->gsegL,g);
+    if (decor && r.below(20) == 0) {	/* tandem repeats: the query is the same repeat, rotated */
+      const int unit = r.range(16,24), rot = r.range(7,9);
+      for (int k = unit; k < g; k++) b->gsegL[k] = b->gsegL[k % unit];
+      for (int k = 0; k < g; k++) tmp[k] = b->gsegL[(k + rot) % unit];
+      qn = mutate(r,tmp,g,e,q,BG_MAXSEQ);
+    } else
     qn = mutate(r,b->gsegL,g,e,q,BG_MAXSEQ);
     if (r.below(2)) {			/* independent rlength: wide band */
       const int want = r.range(lo,hi);
@@ -226,20 +253,6 @@ extern "C" void benchgen_make (uint64_t seed, long i, benchgen_box *b, int small
     b->cdna_direction = k < 77 ? 1 : (k < 89 ? -1 : 0);
     b->extraband = 14; b->finalp = r.below(10) == 0; b->halfp = 0;
     probs(r,b->left_probs,gl - 1,a); probs(r,b->right_probs,gl - 1,bb);
-    if (RES.on) {
-      /* the MaxEnt values this box has in the resident genome: its two segments between pads, nothing else in reach */
-      uint32_t mini[((2 * BG_MAXSEQ + 4 * PAD) / 32 + 4) * 3];
-      memset(mini,0,sizeof(mini));
-      uint64_t used = 0;
-      const int64_t pL = place(mini,sizeof(mini) / 4,used,b->gsegL,gl), pR = place(mini,sizeof(mini) / 4,used,b->gsegR,gl);
-      gmapdp_coords co;
-      box_coords(b,(uint64_t) pL,(uint64_t) pR,used,&co);
-      GdpGenome G; G.blocks = mini; G.nwords = sizeof(mini) / 4;
-      for (int c = 0; c < gl - 1; c++) {
-	b->left_probs[c] = gdp_maxent_prob(co.probkindL,G,RES.packed.data(),co.probposL + (uint32_t) c,0);
-	b->right_probs[c] = gdp_maxent_prob(co.probkindR,G,RES.packed.data(),co.probposR - (uint32_t) c,0);
-      }
-    }
 
   } else {	/* cdna */
     const int g = r.range(lo,small ? 100 : 200), k = r.range(1,g - 1), ins = r.range(10,40);
@@ -258,8 +271,28 @@ extern "C" void benchgen_make (uint64_t seed, long i, benchgen_box *b, int small
   b->querylength = prefix + qn + suffix;
   b->query[b->querylength] = '\0';
   for (int j = 0; j <= b->querylength; j++) b->queryuc[j] = b->query[j];	/* generated upper case already */
+  if (decor) {
+    decorate_query(r,b->query,b->queryuc,b->querylength);
+    decorate_genome(r,b->gsegL,b->glength);
+    if (b->mode == GMAPDP_GENOME) decorate_genome(r,b->gsegR,b->glengthR);
+  }
   b->gsegL[b->glength] = '\0';
   if (b->mode == GMAPDP_GENOME) b->gsegR[b->glengthR] = '\0';
+  if (RES.on && b->mode == GMAPDP_GENOME) {
+      /* the MaxEnt values this box has in the resident genome: its two segments between pads, nothing else in reach */
+      uint32_t mini[((2 * BG_MAXSEQ + 4 * PAD) / 32 + 4) * 3];
+      memset(mini,0,sizeof(mini));
+      uint64_t used = 0;
+      const int gl = b->glength;
+      const int64_t pL = place(mini,sizeof(mini) / 4,used,b->gsegL,gl), pR = place(mini,sizeof(mini) / 4,used,b->gsegR,gl);
+      gmapdp_coords co;
+      box_coords(b,(uint64_t) pL,(uint64_t) pR,used,&co);
+      GdpGenome G; G.blocks = mini; G.nwords = sizeof(mini) / 4;
+      for (int c = 0; c < gl - 1; c++) {
+	b->left_probs[c] = gdp_maxent_prob(co.probkindL,G,RES.packed.data(),co.probposL + (uint32_t) c,0);
+	b->right_probs[c] = gdp_maxent_prob(co.probkindR,G,RES.packed.data(),co.probposR - (uint32_t) c,0);
+      }
+    }
 }
 
 /* queues box i into a shim batch; returns the call id */

@@ -56,6 +56,32 @@ def test_resident_form_of_the_workload_bit_exact_vs_oracle(engine):
         batch.free()
 
 
+@pytest.mark.parametrize("resident", [False, True])
+def test_decorated_stratum_bit_exact_vs_oracle(engine, resident):
+    """SURVEY.md section 8d's input decorations on the benchmark generator: N in the genomic segments, lower-case and
+    IUPAC characters in the query, tandem repeats (8-bit stripe artefact F11 on the small boxes); both forms"""
+    o = Oracle()
+    seed = 99
+    for small, n in ((False, 300), (True, 600)):
+        batch = engine.batch()
+        try:
+            if resident:
+                benchgen.resident_begin(batch, seed, n * 2600 + 1000000)
+            assert benchgen.fill_batch(batch, seed, 0, n, 1, small, 31, decor=True) == n
+            if resident:
+                benchgen.resident_attach(engine)
+            batch.run()
+            nN = 0
+            for i in range(n):
+                box = benchgen.make(seed, i, small=small, decor=True)
+                assert batch.result(i, box["mode"]) == o.run(box), (i, box["mode"], small)
+                nN += "N" in box.get("gseg", box.get("gsegL", ""))
+            assert nN > n // 20
+        finally:
+            benchgen.resident_end()
+            batch.free()
+
+
 def test_checksum_repeatable_and_chunking_independent(engine):
     import os
     from gmap_2024_b200 import Engine
