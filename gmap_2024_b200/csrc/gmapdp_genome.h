@@ -94,18 +94,23 @@ GDPG_HD int gdp_maxent_table (int kind, int pass) {
   if (kind == GDP_ME_ACCEPTOR) return pass == 0 ? GDP_ME_ACC1_P : (pass == 1 ? GDP_ME_ACC2_P : (pass == 2 ? GDP_ME_ACC3_P : (pass == 3 ? GDP_ME_ACC467_P : GDP_ME_ACC589_P)));
   return pass == 0 ? GDP_ME_ACC1_M : (pass == 1 ? GDP_ME_ACC2_M : (pass == 2 ? GDP_ME_ACC3_M : (pass == 3 ? GDP_ME_ACC467_M : GDP_ME_ACC589_M)));
 }
-/* big = the pass's large table (wherever it lives), T = the packed array (for the 16-entry dinucleotide tables) */
-GDPG_HD double gdp_maxent_step (int kind, int pass, uint64_t W, const double *big, const double *T, double odds) {
+/* big = the pass's large table (wherever it lives), di = the four 16-entry dinucleotide tables (the 64 doubles at
+   GDP_ME_DONOR_DI_P of the packed array) */
+#define GDP_DI_DONOR_P 0
+#define GDP_DI_ACC_P 16
+#define GDP_DI_DONOR_M 32
+#define GDP_DI_ACC_M 48
+GDPG_HD double gdp_maxent_step (int kind, int pass, uint64_t W, const double *big, const double *di, double odds) {
   const uint32_t seq = (uint32_t) W;
-  if (kind == GDP_ME_DONOR) return big[(seq & 0x3Fu) | ((seq >> 4) & 0x3FC0u)] * T[GDP_ME_DONOR_DI_P + ((seq >> 6) & 0x0Fu)];
-  if (kind == GDP_ME_ANTIDONOR) return big[(seq & 0xFFu) | ((seq >> 4) & 0x3F00u)] * T[GDP_ME_DONOR_DI_M + ((seq >> 8) & 0x0Fu)];
+  if (kind == GDP_ME_DONOR) return big[(seq & 0x3Fu) | ((seq >> 4) & 0x3FC0u)] * di[GDP_DI_DONOR_P + ((seq >> 6) & 0x0Fu)];
+  if (kind == GDP_ME_ANTIDONOR) return big[(seq & 0xFFu) | ((seq >> 4) & 0x3F00u)] * di[GDP_DI_DONOR_M + ((seq >> 8) & 0x0Fu)];
   if (kind == GDP_ME_ACCEPTOR) {
     if (pass == 0) return big[seq & 0x3FFFu];						/* 7-mer at +0 */
     if (pass == 1) return odds * big[(uint32_t) (W >> 14) & 0x3FFFu];			/* 7-mer at +7 */
     if (pass == 2) {									/* 9-mer at +14: 4 nt, skip 2, 3 nt */
       const uint32_t s9 = (uint32_t) (W >> 28);
       odds *= big[(s9 & 0xFFu) | ((s9 >> 4) & 0x3F00u)];
-      return odds * T[GDP_ME_ACC_DI_P + ((s9 >> 8) & 0x0Fu)];
+      return odds * di[GDP_DI_ACC_P + ((s9 >> 8) & 0x0Fu)];
     }
     if (pass == 3) return odds * big[(uint32_t) (W >> 8) & 0x3FFFu];			/* 7-mer at +4 */
     return odds * big[(uint32_t) (W >> 22) & 0x3FFFu];					/* 7-mer at +11 */
@@ -114,7 +119,7 @@ GDPG_HD double gdp_maxent_step (int kind, int pass, uint64_t W, const double *bi
   if (pass == 1) return odds * big[(uint32_t) (W >> 18) & 0x3FFFu];			/* 7-mer at +9 */
   if (pass == 2) {									/* 9-mer at +0: 3 nt, skip 2, 4 nt */
     odds *= big[(seq & 0x3Fu) | ((seq >> 4) & 0x3FC0u)];
-    return odds * T[GDP_ME_ACC_DI_M + ((seq >> 6) & 0x0Fu)];
+    return odds * di[GDP_DI_ACC_M + ((seq >> 6) & 0x0Fu)];
   }
   if (pass == 3) return odds * big[(uint32_t) (W >> 24) & 0x3FFFu];			/* 7-mer at +12 */
   return odds * big[(uint32_t) (W >> 10) & 0x3FFFu];					/* 7-mer at +5 */
@@ -126,7 +131,7 @@ GDPG_HD double gdp_maxent_prob (int kind, const GdpGenome &g, const double *T, u
   const uint64_t W = gdp_genome_window(g,splice_pos - margin);
   const int np = gdp_maxent_npasses(kind);
   double odds = 0.0;
-  for (int p = 0; p < np; p++) odds = gdp_maxent_step(kind,p,W,T + gdp_maxent_table(kind,p),T,odds);
+  for (int p = 0; p < np; p++) odds = gdp_maxent_step(kind,p,W,T + gdp_maxent_table(kind,p),T + GDP_ME_DONOR_DI_P,odds);
   return odds / (1 + odds);
 }
 

@@ -1817,7 +1817,7 @@ gmapdp_maxent_pass_kernel (const gmapdp_box *boxes, const int *order, int nboxes
       for (int u = 0; u < 4; u++) {
 	const int c = c0 + 32 * u;
 	if (live[u]) {
-	  const double o = gdp_maxent_step(kind,pass,W[u],me_table,me,odds[u]);
+	  const double o = gdp_maxent_step(kind,pass,W[u],me_table,me + GDP_ME_DONOR_DI_P,odds[u]);
 	  out[c] = (pass == last) ? o / (1 + o) : o;
 	} else if (c <= glen && (c >= glen - 1 ? pass == 0 : pass == last)) out[c] = 0.0;	/* the calloc'ed tail of the reference's arrays; left of the chromosome */
       }
@@ -2296,17 +2296,21 @@ extern "C" int gmapdp_genome_host_char (const uint32_t *blocks, size_t nwords, u
   return gdp_genome_char(g,pos);
 }
 
-extern "C" double gmapdp_maxent_host_prob (const uint32_t *blocks, size_t nwords, const gmapdp_maxent_tables *maxent, int kind, uint32_t splice_pos, uint32_t chroffset) {
-  /* the packed copy is built once per table set (callers pass the same one for the life of the process) */
-  static std::mutex mu;
-  static const gmapdp_maxent_tables *cached = NULL;
-  static std::vector<double> packed;
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (cached != maxent) { pack_maxent(maxent,packed); cached = maxent; }
-  }
+extern "C" double gmapdp_maxent_host_prob (const uint32_t *blocks, size_t nwords, const gmapdp_maxent_tables *t, int kind, uint32_t splice_pos, uint32_t chroffset) {
+  /* straight from the caller's tables (no cached copy: a caller may refill its tables in place), same steps as the device */
+  const double *big[4][5] = {{t->donor_plus,NULL,NULL,NULL,NULL}, {t->acc1_plus,t->acc2_plus,t->acc3_plus,t->acc467_plus,t->acc589_plus},
+			     {t->donor_minus,NULL,NULL,NULL,NULL}, {t->acc1_minus,t->acc2_minus,t->acc3_minus,t->acc467_minus,t->acc589_minus}};
+  if (kind < 0 || kind > 3) return 0.0;
+  const uint32_t margin = (uint32_t) gdp_maxent_margin(kind);
+  if (splice_pos < chroffset + margin) return 0.0;
+  double di[64];
+  memcpy(di + GDP_DI_DONOR_P,t->donor_di_plus,16 * sizeof(double)); memcpy(di + GDP_DI_ACC_P,t->acc_di_plus,16 * sizeof(double));
+  memcpy(di + GDP_DI_DONOR_M,t->donor_di_minus,16 * sizeof(double)); memcpy(di + GDP_DI_ACC_M,t->acc_di_minus,16 * sizeof(double));
   GdpGenome g; g.blocks = blocks; g.nwords = nwords;
-  return gdp_maxent_prob(kind,g,packed.data(),splice_pos,chroffset);
+  const uint64_t W = gdp_genome_window(g,splice_pos - margin);
+  double odds = 0.0;
+  for (int p = 0; p < gdp_maxent_npasses(kind); p++) odds = gdp_maxent_step(kind,p,W,big[kind][p],di,odds);
+  return odds / (1 + odds);
 }
 
 __global__ void gmapdp_maxent_kernel (GdpGenome g, const double *me, const int *kind, const uint32_t *pos, uint32_t chroffset, int n, double *out) {
