@@ -92,6 +92,12 @@ void probs (Rng &r, double *p, int n, int hot) {
 /* ---- resident genome ------------------------------------------------------------------------------ */
 namespace {
 const int PAD = 32;
+/* consensus contexts of the planted sites: donor = 3 exon nt + GT + 4 intron nt; acceptor = 18 intron nt + AG + 3 exon nt;
+   the minus-strand twins are their reverse complements */
+const char BG_DONOR9[] = "CAGGTAAGT";
+const char BG_ANTIDONOR9[] = "ACTTACCTG";
+const char BG_ACC23[] = "TTTCTTTTCTTTTTTTCCAGGAA";
+const char BG_ANTIACC23[] = "TTCCTGGAAAAAAAGAAAAGAAA";
 struct Resident {
   bool on = false;
   std::vector<double> packed;		/* GDP_ME_NDOUBLES, the layout of gmapdp_genome.h */
@@ -113,6 +119,32 @@ void synth_tables (uint64_t seed) {
     RES.packed[GDP_ME_ACC_DI_P + k] = (k == 8) ? 1.0 : 0.004;		/* AG */
     RES.packed[GDP_ME_DONOR_DI_M + k] = (k == 4) ? 1.0 : 0.004;		/* AC */
     RES.packed[GDP_ME_ACC_DI_M + k] = (k == 13) ? 1.0 : 0.004;		/* CT */
+  }
+  /* the planted splice sites carry consensus contexts (benchgen_make), and those contexts score high -- like true sites
+     under the real model, so that the entry point's shortcut for clean introns (genome_gap_simple, dynprog_genome.c:3005:
+     both probabilities >= 0.90) fires about as often as on real data */
+  {
+    auto code = [](char c) { return c == 'A' ? 0ull : (c == 'C' ? 1ull : (c == 'G' ? 2ull : 3ull)); };
+    auto window = [&](const char *str, int n) { uint64_t W = 0; for (int k = 0; k < n; k++) W |= code(str[k]) << (2 * k); return W; };
+    double *P = RES.packed.data();
+    const double hi1 = 60.0, hi5 = 2.3;				/* odds 60 in one factor / over five factors */
+    for (int gc = 0; gc < 2; gc++) {				/* GT and GC donors share the table entry (the dinucleotide is skipped) */
+      const uint32_t seq = (uint32_t) window(BG_DONOR9,9);
+      P[GDP_ME_DONOR_P + ((seq & 0x3Fu) | ((seq >> 4) & 0x3FC0u))] = hi1;
+    }
+    { const uint32_t seq = (uint32_t) window(BG_ANTIDONOR9,9); P[GDP_ME_DONOR_M + ((seq & 0xFFu) | ((seq >> 4) & 0x3F00u))] = hi1; }
+    {
+      const uint64_t W = window(BG_ACC23,23); const uint32_t s9 = (uint32_t) (W >> 28);
+      P[GDP_ME_ACC1_P + (W & 0x3FFFu)] = hi5; P[GDP_ME_ACC2_P + ((W >> 14) & 0x3FFFu)] = hi5;
+      P[GDP_ME_ACC3_P + ((s9 & 0xFFu) | ((s9 >> 4) & 0x3F00u))] = hi5;
+      P[GDP_ME_ACC467_P + ((W >> 8) & 0x3FFFu)] = hi5; P[GDP_ME_ACC589_P + ((W >> 22) & 0x3FFFu)] = hi5;
+    }
+    {
+      const uint64_t W = window(BG_ANTIACC23,23); const uint32_t seq = (uint32_t) W;
+      P[GDP_ME_ACC1_M + ((W >> 32) & 0x3FFFu)] = hi5; P[GDP_ME_ACC2_M + ((W >> 18) & 0x3FFFu)] = hi5;
+      P[GDP_ME_ACC3_M + ((seq & 0x3Fu) | ((seq >> 4) & 0x3FC0u))] = hi5;
+      P[GDP_ME_ACC467_M + ((W >> 24) & 0x3FFFu)] = hi5; P[GDP_ME_ACC589_M + ((W >> 10) & 0x3FFFu)] = hi5;
+    }
   }
   const double *p = RES.packed.data();
   gmapdp_maxent_tables &T = RES.tables;
@@ -243,6 +275,17 @@ extern "C" void benchgen_make (uint64_t seed, long i, benchgen_box *b, int small
     const int k = r.below(100);
     const char *d = k < 65 ? "GTAG" : (k < 77 ? "GCAG" : (k < 89 ? "CTAC" : NULL));
     if (d) { b->gsegL[a] = d[0]; b->gsegL[a+1] = d[1]; b->gsegR[gl-bb-2] = d[2]; b->gsegR[gl-bb-1] = d[3]; }
+    if (d && RES.on) {
+      /* resident form: the sites' consensus contexts around the dinucleotides (which stay as planted) */
+      const int sR = gl - bb - 2;			/* position of the right site's first nt */
+      if (k < 77) {					/* GT-AG / GC-AG: donor on the left, acceptor on the right */
+	if (a >= 3 && a + 6 <= gl) { memcpy(b->gsegL + a - 3,BG_DONOR9,3); memcpy(b->gsegL + a + 2,BG_DONOR9 + 5,4); }
+	if (sR >= 18 && sR + 5 <= gl) { memcpy(b->gsegR + sR - 18,BG_ACC23,18); memcpy(b->gsegR + sR + 2,BG_ACC23 + 20,3); }
+      } else {						/* CT-AC: antiacceptor on the left, antidonor on the right */
+	if (a >= 3 && a + 20 <= gl) { memcpy(b->gsegL + a - 3,BG_ANTIACC23,3); memcpy(b->gsegL + a + 2,BG_ANTIACC23 + 5,18); }
+	if (sR >= 4 && sR + 5 <= gl) { memcpy(b->gsegR + sR - 4,BG_ANTIDONOR9,4); memcpy(b->gsegR + sR + 2,BG_ANTIDONOR9 + 6,3); }
+      }
+    }
     int m1 = mutate(r,b->gsegL,a,e,tmp,2 * BG_MAXSEQ);
     int m2 = mutate(r,b->gsegR + gl - bb,bb,e,tmp + m1,2 * BG_MAXSEQ - m1);
     int m = m1 + m2;
