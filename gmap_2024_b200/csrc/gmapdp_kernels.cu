@@ -1439,9 +1439,9 @@ struct KernelArgs {
   double *devprobs;		/* device-side pool of the MaxEnt arrays of GMAPDP_G_PROBS boxes (batch path) */
 };
 
-/* one segment of a resident-genome box into the workspace, lanes over positions (out of line: its registers are not
-   the box loop's) */
-__device__ __noinline__ void decode_segment (GdpGenome g, uint32_t p0, int n, bool neg, bool left, uint32_t chroffset, uint32_t chrhigh, uint8_t *seg) {
+/* one segment of a resident-genome box into the workspace, lanes over positions (inlined: out of line it cost the
+   single-gap and end kernels 1-2 ms per step) */
+__device__ __forceinline__ void decode_segment (GdpGenome g, uint32_t p0, int n, bool neg, bool left, uint32_t chroffset, uint32_t chrhigh, uint8_t *seg) {
   const int dir = neg ? -1 : +1;
   const uint32_t lo = left ? chroffset : 0u, hi = left ? 0xffffffffu : chrhigh;
   for (int i = (int) (threadIdx.x & 31); i < n; i += 32) seg[i] = (uint8_t) gdp_segment_char(g,p0,dir,i,lo,hi);

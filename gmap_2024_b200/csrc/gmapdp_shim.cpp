@@ -94,6 +94,13 @@ struct Pushed {
 };
 
 #if defined(__SSE2__) && !defined(GMAPDP_NO_NT_STORES)
+/* software prefetch distance of the replay's five streams, in bytes of input (0: none, the default).  It is host
+   dependent: on the development container 256 took the eight-thread replay of 100 k end gaps from 141 to 20 ms, on the
+   GPU box's host it made the end-to-end step slower (431-454 vs 399 ms). */
+#ifndef GMAPDP_REPLAY_PREFETCH
+#define GMAPDP_REPLAY_PREFETCH 0
+#endif
+
 /* non-temporal or ordinary 16-byte store of one record (GMAPDP_NT_STORES=0 selects ordinary stores: which one is faster
    depends on how many threads share the memory controllers) */
 const bool g_nt_stores = !(getenv("GMAPDP_NT_STORES") && atoi(getenv("GMAPDP_NT_STORES")) == 0);
@@ -195,6 +202,11 @@ struct Replayer {
 	const int lowoff = (step > 0) ? 0 : -7;			/* ascending-memory start of the chunk */
 	const int q0 = qpos + lowoff, g0 = gpos + lowoff;
 	if ((q0 | g0) < 0) break;
+#if GMAPDP_REPLAY_PREFETCH
+	__builtin_prefetch(ru + step * GMAPDP_REPLAY_PREFETCH,0,0); __builtin_prefetch(gs + step * GMAPDP_REPLAY_PREFETCH,0,0);
+	__builtin_prefetch(ga + step * GMAPDP_REPLAY_PREFETCH,0,0); __builtin_prefetch(rs + step * GMAPDP_REPLAY_PREFETCH,0,0);
+	__builtin_prefetch(out + ostep * (GMAPDP_REPLAY_PREFETCH / 4),1,0);
+#endif
 	const __m128i vru = _mm_loadl_epi64(reinterpret_cast<const __m128i *>(ru + lowoff));
 	const __m128i vgs = _mm_loadl_epi64(reinterpret_cast<const __m128i *>(gs + lowoff));
 	const __m128i vga = _mm_loadl_epi64(reinterpret_cast<const __m128i *>(ga + lowoff));
