@@ -152,6 +152,7 @@ struct GenBest { int s, key, cnt; double p; uint32_t *ties; };	/* p < 0: not fet
 struct GenCtx {
   const uint8_t *ldi, *rdi;		/* dinucleotide classes per genomic position */
   const short *dgL, *dgR;		/* main-diagonal scores of the upper fills */
+  const uint32_t *entL, *entR;		/* dg << 16 | di per position: what the staged interior steps read */
   const double *lp, *rp;
   int rlength, lim;
   /* MaxEnt from the resident genome (GMAPDP_G_PROBS): entry c of the left / right array is the probability of kind
@@ -196,7 +197,79 @@ __device__ __forceinline__ void gen_tie (const GenCtx &g, GenBest &b, int key) {
   if (pc > b.p || (pc == b.p && key < b.key)) { b.key = key; b.p = pc; }
 }
 
+/* ---- Shared-memory staging of the interior steps' operands --------------------------------------------------------
+ * The interior steps of an E-only fill (tri_fast) read, per step and lane, an 8-byte score profile, a PRMT selector and
+ * -- genome gaps -- the dinucleotide class / diagonal score of the lane's own column and of its partner row.  These are
+ * per-box arrays in the warp's HBM workspace; read with LDG in the steps' dependent chain they cost the kernels their
+ * issue slots (long-scoreboard stalls, ncu).  They are staged instead: per pass, the steps run in blocks of STG_B; the
+ * windows of the arrays that a block's steps touch are copied into the warp's shared-memory slots by bulk async copies
+ * (cp.async.bulk global -> shared, completion counted by an mbarrier), one block ahead of their use (two buffers), and
+ * the steps read them with LDS.  A pass holds at most two fills (GDP_PASS_FILLS): two slots per buffer.
+ *
+ * Window of block [t0, t0 + STG_B) (t0 a multiple of 16; lane diagonals d <= 31):
+ *   profiles   prof[t0 - 32 .. t0 + STG_B)                    read at prof[t - d]
+ *   selectors  sel[t0 .. t0 + STG_B)                          read at sel[t]
+ *   own        ent_own[t0 - 32 .. t0 + STG_B)                 read at col = lower ? t - d : t
+ *   partner    ent_oth[w0 .. w0 + STG_B + 36), w0 = ((rlength + 1) & ~3) - t0 - STG_B      read at rP = rlength - row
+ * ent = diagonal score << 16 | dinucleotide class, one word per position (process_box).  All sources are 16-byte aligned
+ * and all sizes multiples of 16, as the bulk copy requires.
+ * Per-warp region: two mbarriers (16 bytes), the barriers' phase bits (a word), padding to 32 bytes, two buffers. */
+/* Measured (B200, the 1 M-box benchmark launch; results and scripts identical): with staging the end / genome / cdna
+   kernels take 20.9 / 86.3 / 23.2 ms, without 19.5 / 79.1 / 21.9 ms, the production-size stratum 35.0 vs 31.6 ms: the copies
+   cost more issue slots (one UBLKCP per lane and array, serialised through uniform registers, plus the barrier traffic
+   per 64 steps) than the LDS reads save over L1-hit LDGs, and the 116 - 164 KB of shared memory per SM come out of the
+   L1 that the general steps, the bridges and the tracebacks live on.  So it is a build option, off by default
+   (-DGMAPDP_STAGE=1; the parity suite passes in both builds). */
+#ifndef GMAPDP_STAGE
+#define GMAPDP_STAGE 0
+#endif
+#define STG_B 64
+#define STG_PROF_BYTES ((STG_B + 32) * 8)
+#define STG_SEL_BYTES (STG_B * 2)
+#define STG_OWN_BYTES ((STG_B + 32) * 4)
+#define STG_PAR_BYTES ((STG_B + 36) * 4)
+template <bool EVAL> struct StgGeom {
+  static constexpr int NARR = EVAL ? 4 : 2;
+  static constexpr uint32_t SLOT = STG_PROF_BYTES + STG_SEL_BYTES + (EVAL ? STG_OWN_BYTES + STG_PAR_BYTES : 0);
+  static constexpr uint32_t BUF = GDP_PASS_FILLS * SLOT;
+  static constexpr uint32_t WARP_BYTES = 32 + 2 * BUF;
+};
+#define STG_WARP_BYTES_MAX (StgGeom<true>::WARP_BYTES)
+
+__device__ __forceinline__ uint32_t smem_u32 (const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init (uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx (uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait (uint32_t bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+	       :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s (uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	       :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+/* a pointer the compiler knows to be shared memory (LDS with immediate offsets), from a shared-window address */
+template <typename T> __device__ __forceinline__ const T *smem_ptr (uint32_t a) {
+  return reinterpret_cast<const T *>(__cvta_shared_to_generic((size_t) a));
+}
+/* once per kernel and warp: the staging region's barriers */
+__device__ __forceinline__ void stage_init (uint32_t stg) {
+  if ((threadIdx.x & 31) == 0) {
+    mbar_init(stg,1); mbar_init(stg + 8,1);
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(stg + 16), "r"(0u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+}
+
 struct TriLane {
+  /* staging (GMAPDP_STAGE): the warp's region, this lane's slot, and -- lanes 0 .. ncopies-1 -- the copy this lane issues per block */
+  uint32_t stg; int slot, ncopies;
+  const char *cp_src; int cp_stride; uint32_t cp_dst, cp_bytes, cp_total;
+  const uint32_t *ent_own, *ent_oth;
   /* genome gaps: this lane's side of the bridge */
   const uint8_t *own_di, *oth_di; const short *oth_dg;
   int ev_lo, ev_hi, key0, kstep; bool ev_ok;
@@ -245,8 +318,6 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
   /* steps per unrolled body (8, 4 or 2; 16 / UNR bodies per direction word) */
   constexpr int UNR = (MODE == 2) ? GMAPDP_GENOME_UNR : ((MODE == 1) ? GMAPDP_CDNA_UNR : GMAPDP_END_UNR);
   constexpr int HALVES_UNROLLED = (MODE == 0) ? GMAPDP_END_UNROLL : ((MODE == 2) ? GMAPDP_GENOME_UNROLL : 1);
-  const uint2 *pq = s.pp + t;
-  const uint4 *sq = reinterpret_cast<const uint4 *>(s.sel + t);
   const int la = s.lateadd;
   const bool isd0 = s.isd0;
   int H = s.Hprev;
@@ -254,11 +325,40 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
   uint32_t *dplane = s.dplane, *splane = s.splane;
   int bs = 0, btt = -1;
   if (TRACK) bs = bt->bs;
-  /* genome gaps: col advances with t, the partner row goes down */
-  const uint8_t *odi = NULL, *pdi = NULL; const short *pdg = NULL;
   int key = 0;
   GenBest g; g.s = 0; g.key = -1; g.cnt = 0; g.p = 0.0; g.ties = NULL;
   GenCtx gcl; gcl.it0 = 0; gcl.it1 = 0;		/* the intron score table in registers (a store sits between its uses) */
+#if GMAPDP_STAGE
+  /* operands from the warp's staging region (see StgGeom): block 0 is copied now, block k + 1 while block k computes */
+  using SG = StgGeom<EVAL>;
+  const int lane = threadIdx.x & 31;
+  const uint32_t stg = s.stg;
+  const int dl = max(s.d,0);				/* idle lanes read slot data of diagonal 0 */
+  const uint32_t slotbase = stg + 32 + (uint32_t) s.slot * SG::SLOT;
+  const char *cpsrc = s.cp_src;
+  uint32_t phases;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(phases) : "r"(stg + 16) : "memory");
+  __syncwarp();
+  if (lane == 0) mbar_expect_tx(stg,s.cp_total);
+  if (lane < s.ncopies) { bulk_g2s(stg + 32 + s.cp_dst,cpsrc,s.cp_bytes,stg); cpsrc += s.cp_stride; }
+  const uint2 *pq = smem_ptr<uint2>(slotbase + (uint32_t) (32 - dl) * 8u);
+  const uint32_t *sq = smem_ptr<uint32_t>(slotbase + STG_PROF_BYTES);
+  const uint32_t *oent = NULL, *pent = NULL;
+  if (EVAL) {
+    gcl.it0 = gc->it0; gcl.it1 = gc->it1;
+    g = *gb;
+    /* col = lower ? t - d : t;  partner row rP = rlength - (lower ? t : t - d), window start w0 = ((rlength + 1) & ~3) - t - STG_B */
+    oent = smem_ptr<uint32_t>(slotbase + STG_PROF_BYTES + STG_SEL_BYTES + (uint32_t) (s.lower ? 32 - dl : 32) * 4u);
+    pent = smem_ptr<uint32_t>(slotbase + STG_PROF_BYTES + STG_SEL_BYTES + STG_OWN_BYTES
+			      + (uint32_t) (gc->rlength - ((gc->rlength + 1) & ~3) + STG_B + (s.lower ? 0 : dl)) * 4u);
+    key = s.key0 + t * s.kstep;
+  }
+  int flip = (int) SG::BUF;				/* bytes from this block's buffer to the next block's */
+#else
+  const uint2 *pq = s.pp + t;
+  const uint32_t *sq = reinterpret_cast<const uint32_t *>(s.sel + t);
+  /* genome gaps: col advances with t, the partner row goes down */
+  const uint8_t *odi = NULL, *pdi = NULL; const short *pdg = NULL;
   if (EVAL) {
     gcl.it0 = gc->it0; gcl.it1 = gc->it1;
     g = *gb;
@@ -266,18 +366,38 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
     odi = s.own_di + col; pdi = s.oth_di + rP; pdg = s.oth_dg + rP;
     key = s.key0 + t * s.kstep;
   }
+#endif
   uint32_t tieoff = (uint32_t) g.cnt * 128u;		/* byte offset of the lane's next tie slot */
   int tb = t;
+#if GMAPDP_STAGE
+  for (int blk = 0; t + 16 <= tstop; blk++) {
+    const int tblk = min(t + STG_B,tstop);
+    __syncwarp();					/* every lane is done with the buffer the next copies overwrite */
+    if (tblk + 16 <= tstop) {
+      const uint32_t nb = (uint32_t) (~blk & 1);
+      if (lane == 0) mbar_expect_tx(stg + 8u * nb,s.cp_total);
+      if (lane < s.ncopies) { bulk_g2s(stg + 32 + nb * SG::BUF + s.cp_dst,cpsrc,s.cp_bytes,stg + 8u * nb); cpsrc += s.cp_stride; }
+    }
+    {
+      const uint32_t cb = (uint32_t) (blk & 1);
+      mbar_wait(stg + 8u * cb,(phases >> cb) & 1u);
+      phases ^= 1u << cb;
+    }
+  for (; t + 16 <= tblk; t += 16) {
+#else
+  {
   for (; t + 16 <= tstop; t += 16) {
+#endif
     uint32_t dacc = 0;
     /* two halves of 8 unrolled steps; the big two-sided kernels keep ONE copy of the half (instruction-cache
        footprint), the small end-gap kernel unrolls both */
 #pragma unroll HALVES_UNROLLED
     for (int h = 0; h < 16 / UNR; h++) {
       uint32_t sw[4];
-      if (UNR == 8) { const uint4 s4 = sq[h]; sw[0] = s4.x; sw[1] = s4.y; sw[2] = s4.z; sw[3] = s4.w; }
-      else if (UNR == 4) { const uint2 s2 = reinterpret_cast<const uint2 *>(sq)[h]; sw[0] = s2.x; sw[1] = s2.y; sw[2] = 0; sw[3] = 0; }
-      else { sw[0] = reinterpret_cast<const uint32_t *>(sq)[h]; sw[1] = 0; sw[2] = 0; sw[3] = 0; }
+      if (UNR == 8) { const uint4 s4 = *reinterpret_cast<const uint4 *>(sq); sw[0] = s4.x; sw[1] = s4.y; sw[2] = s4.z; sw[3] = s4.w; }
+      else if (UNR == 4) { const uint2 s2 = *reinterpret_cast<const uint2 *>(sq); sw[0] = s2.x; sw[1] = s2.y; sw[2] = 0; sw[3] = 0; }
+      else { sw[0] = *sq; sw[1] = 0; sw[2] = 0; sw[3] = 0; }
+      sq += UNR / 2;
       uint32_t d8 = 0;
       int Heven = 0;
 #pragma unroll
@@ -306,7 +426,13 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
 	  bs = up ? Hn : bs; btt = up ? tb + u : btt;
 	}
 	if (EVAL) {
+#if GMAPDP_STAGE
+	  /* ent = diagonal score << 16 | dinucleotide class: the own class is a byte, so the AND needs no mask */
+	  const uint32_t pe = pent[-u];
+	  const int tot = Hn + gen_points(gcl,(int) (reinterpret_cast<const uint8_t *>(oent + u)[0] & pe)) + (((int) pe) >> 16);
+#else
 	  const int tot = Hn + gen_points(gcl,(int) odi[u] & (int) pdi[-u]) + (int) pdg[-u];
+#endif
 	  const int ku = key + u * s.kstep;
 	  const bool gt = s.ev_ok && tot > g.s, eq = s.ev_ok && tot == g.s;
 	  if (eq && tieoff < GEN_TIECAP * 128u) *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(g.ties) + tieoff) = (uint32_t) ku;
@@ -316,12 +442,30 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
 	H = Hn;
       }
       pq += UNR; tb += UNR;
+#if GMAPDP_STAGE
+      if (EVAL) { oent += UNR; pent -= UNR; key += UNR * s.kstep; }
+#else
       if (EVAL) { odi += UNR; pdi -= UNR; pdg -= UNR; key += UNR * s.kstep; }
+#endif
       dacc |= d8 << (2 * UNR * h);
     }
-    sq += 2;
     *dplane = isd0 ? 0u : dacc; dplane += 32;
   }
+#if GMAPDP_STAGE
+    /* on to the other buffer: within a block the addresses moved by STG_B entries */
+    pq = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(pq) + (flip - STG_B * 8));
+    sq = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(sq) + (flip - STG_B * 2));
+    if (EVAL) {
+      oent = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(oent) + (flip - STG_B * 4));
+      pent = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(pent) + (flip + STG_B * 4));
+    }
+    flip = -flip;
+#endif
+  }
+#if GMAPDP_STAGE
+  __syncwarp();
+  if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" :: "r"(stg + 16), "r"(phases) : "memory");
+#endif
   if (EVAL) g.cnt = (int) (tieoff >> 7);
   s.Hprev = H; s.H = H; s.pk_out = pk_out; s.dplane = dplane; s.splane = splane;
   if (EVAL) *gb = g;
@@ -337,11 +481,14 @@ __device__ __forceinline__ void tri_fast (TriLane &s, int &t, const int tstop, c
 template <int MODE, bool WIDE>
 __device__ __forceinline__ void tri_pass_body (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
 			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok, const GenCtx *gc, GenBest *gb,
-			  bool ev_now) {
+			  bool ev_now, uint32_t stg) {
   constexpr bool SCORES = (MODE == 1), TRACK = (MODE == 0), EVAL = (MODE == 2);
   const int lane = threadIdx.x & 31;
   /* lane configuration */
   TriLane s;
+  s.stg = stg; s.slot = 0; s.ncopies = 0; s.cp_src = NULL; s.cp_stride = 0; s.cp_dst = 0; s.cp_bytes = 0; s.cp_total = 0;
+  s.ent_own = NULL; s.ent_oth = NULL;
+  int nslots = 0, cp_arr = -1;				/* fills of this pass so far; which array this lane copies (staging) */
   int nA = -1, nB = -1, thi = -1, tlo = 0x7fffffff;
   int maxstart = 0, minend = 0x7fffffff, lm = -1;
   s.d = -1; s.lateadd = 0; s.lower = false; s.edge_in = false; s.edge_out = false;
@@ -362,8 +509,35 @@ __device__ __forceinline__ void tri_pass_body (const TriFill (&F)[GDP_MAXFILLS],
       prof0 = F[f].prof; sel0 = F[f].sel;
       s.dplane = F[f].dirs + (size_t) p * F[f].dirPW;		/* the pass's planes are shared by its fills */
       s.splane = SCORES ? F[f].sc + (size_t) p * F[f].scPW : NULL;
+#if GMAPDP_STAGE
+      if (!WIDE) {
+	/* staging: this fill takes the pass's next slot; lanes slot * NARR .. slot * NARR + NARR - 1 copy its arrays (bases
+	   here, the block offsets below).  Idle lanes read the last slot. */
+	using SG = StgGeom<EVAL>;
+	const int sl = min(nslots,GDP_PASS_FILLS - 1);
+	nslots++;
+	if (s.d < 0) s.slot = sl;
+	const int ca = lane - sl * SG::NARR;
+	if (ca >= 0 && ca < SG::NARR) {
+	  cp_arr = ca;
+	  s.cp_dst = (uint32_t) sl * SG::SLOT;
+	  if (ca == 0) { s.cp_src = reinterpret_cast<const char *>(F[f].prof); s.cp_bytes = STG_PROF_BYTES; s.cp_stride = STG_B * 8; }
+	  else if (ca == 1) { s.cp_src = reinterpret_cast<const char *>(F[f].sel); s.cp_bytes = STG_SEL_BYTES; s.cp_stride = STG_B * 2; s.cp_dst += STG_PROF_BYTES; }
+	  else if (EVAL && ca == 2) {
+	    s.cp_src = reinterpret_cast<const char *>(F[f].right ? gc->entR : gc->entL); s.cp_bytes = STG_OWN_BYTES; s.cp_stride = STG_B * 4;
+	    s.cp_dst += STG_PROF_BYTES + STG_SEL_BYTES;
+	  } else if (EVAL) {
+	    s.cp_src = reinterpret_cast<const char *>(F[f].right ? gc->entL : gc->entR); s.cp_bytes = STG_PAR_BYTES; s.cp_stride = -STG_B * 4;
+	    s.cp_dst += STG_PROF_BYTES + STG_SEL_BYTES + STG_OWN_BYTES;
+	  }
+	}
+      }
+#endif
       if (lane >= F[f].lane0 && dd <= F[f].band && (F[f].npass > 1 || lane - F[f].lane0 <= F[f].band)) {
 	s.d = dd; nA = F[f].nA; nB = F[f].nB; s.lateadd = F[f].lateadd; s.lower = F[f].lower;
+#if GMAPDP_STAGE
+	s.slot = min(nslots - 1,GDP_PASS_FILLS - 1);
+#endif
 	prof = F[f].prof; s.code = F[f].code; s.sel = F[f].sel;
 	s.edge_in = WIDE && (p > 0 && lane == 0);
 	s.edge_out = WIDE && (p + 1 < F[f].npass && lane == 31);
@@ -405,6 +579,18 @@ __device__ __forceinline__ void tri_pass_body (const TriFill (&F)[GDP_MAXFILLS],
   if (EVAL) minend -= 1;				/* keeps the interior steps inside columns <= glength - 2 */
   if (!WIDE && fastok) while (F1 + 16 <= minend) F1 += 16;
   const bool hasfast = (F1 > F0);
+#if GMAPDP_STAGE
+  if (!WIDE && hasfast) {
+    /* the copies of block 0 = [F0, F0 + STG_B): see the windows at StgGeom */
+    using SG = StgGeom<EVAL>;
+    s.ncopies = min(nslots,GDP_PASS_FILLS) * SG::NARR;
+    s.cp_total = (uint32_t) min(nslots,GDP_PASS_FILLS) * SG::SLOT;
+    if (cp_arr == 0) s.cp_src += (ptrdiff_t) (F0 - 32) * 8;
+    else if (cp_arr == 1) s.cp_src += (ptrdiff_t) F0 * 2;
+    else if (cp_arr == 2) s.cp_src += (ptrdiff_t) (F0 - 32) * 4;
+    else if (cp_arr == 3) s.cp_src += (ptrdiff_t) (((gc->rlength + 1) & ~3) - F0 - STG_B) * 4;
+  }
+#endif
 
   int t = tlo;
   for (int phase = 0; phase < 2; phase++) {
@@ -479,8 +665,8 @@ __device__ __forceinline__ void tri_pass_body (const TriFill (&F)[GDP_MAXFILLS],
 template <int MODE, bool WIDE>
 __device__ __noinline__ void tri_pass_call (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
 			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok, const GenCtx *gc, GenBest *gb,
-			  bool ev_now) {
-  tri_pass_body<MODE,WIDE>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok,gc,gb,ev_now);
+			  bool ev_now, uint32_t stg) {
+  tri_pass_body<MODE,WIDE>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok,gc,gb,ev_now,stg);
 }
 #ifndef GMAPDP_TRI_INLINE
 #define GMAPDP_TRI_INLINE 3	/* bit MODE set: that mode's passes are inlined into its kernel.  Measured (500 k boxes): inlining
@@ -490,22 +676,22 @@ __device__ __noinline__ void tri_pass_call (const TriFill (&F)[GDP_MAXFILLS], in
 template <int MODE, bool WIDE>
 __device__ __forceinline__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int nf, int pass, int open, int extend, int NEG, int POS,
 			  BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok, const GenCtx *gc, GenBest *gb,
-			  bool ev_now) {
-  if ((GMAPDP_TRI_INLINE >> MODE) & 1) tri_pass_body<MODE,WIDE>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok,gc,gb,ev_now);
-  else tri_pass_call<MODE,WIDE>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok,gc,gb,ev_now);
+			  bool ev_now, uint32_t stg) {
+  if ((GMAPDP_TRI_INLINE >> MODE) & 1) tri_pass_body<MODE,WIDE>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok,gc,gb,ev_now,stg);
+  else tri_pass_call<MODE,WIDE>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok,gc,gb,ev_now,stg);
 }
 
 /* all passes of a box's E-only fills */
 template <int MODE>
 __device__ void tri_fill_all (const TriFill (&F)[GDP_MAXFILLS], int nf, int npasses, int open, int extend, int NEG, int POS,
 			      BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok, const GenCtx *gc, GenBest *gb,
-			      bool ev_now = false) {
+			      uint32_t stg, bool ev_now = false) {
   bool wide = false;
 #pragma unroll
   for (int f = 0; f < GDP_MAXFILLS; f++) if (f < nf && F[f].npass > 1) wide = true;
   for (int pass = 0; pass < npasses; pass++) {
-    if (wide) tri_pass<MODE,true>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,false,gc,gb,ev_now);
-    else tri_pass<MODE,false>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok && !ev_now,gc,gb,ev_now);
+    if (wide) tri_pass<MODE,true>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,false,gc,gb,ev_now,stg);
+    else tri_pass<MODE,false>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok && !ev_now,gc,gb,ev_now,stg);
   }
 }
 
@@ -1449,7 +1635,7 @@ __device__ __forceinline__ void decode_segment (GdpGenome g, uint32_t p0, int n,
 
 /* KIND: 0 single gaps (full fill), 1 end5/end3 (E-only fills + endpoint search), 2 genome gaps, 3 cdna gaps */
 template <int KIND, bool INK>
-__device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *bnd, const GdpTables *tb) {
+__device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *bnd, const GdpTables *tb, uint32_t stg) {
   constexpr bool FULLK = (KIND == 0);
   constexpr bool twosided = (KIND >= 2);
 
@@ -1478,6 +1664,12 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
   uint16_t *gselR = reinterpret_cast<uint16_t *>(bytes); bytes += gdp_align16(2 * (size_t) (b.glenR + 2));
   short *dgL = reinterpret_cast<short *>(bytes); bytes += gdp_align16(2 * (size_t) (b.rlenL + 2));
   short *dgR = reinterpret_cast<short *>(bytes); bytes += gdp_align16(2 * (size_t) (b.rlenR + 2));
+  uint32_t *entL = NULL, *entR = NULL;			/* genome gaps: dg << 16 | di per position (staged interior steps) */
+  if (KIND == 2) {
+    const size_t eb = gdp_align16(4 * (size_t) (GDP_ENT_PAD + gdp_ent_len(b)));
+    entL = reinterpret_cast<uint32_t *>(bytes) + GDP_ENT_PAD; bytes += eb;
+    entR = reinterpret_cast<uint32_t *>(bytes) + GDP_ENT_PAD; bytes += eb;
+  }
   /* segments of resident-genome boxes: decoded once into the workspace (Genome_get_segment_right / _left, genome.c:11023,
      :11079), everything downstream reads them like uploaded ones; genomealt == genome */
   if (b.gflags & GMAPDP_G_SEG_L) {
@@ -1579,7 +1771,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
     tri_fills_of(b,tp);
     TriFill F[GDP_MAXFILLS];
     const bool noalt = (b.gLalt_off == b.gL_off) && (!twosided || b.gRalt_off == b.gR_off);	/* selectors carry one class */
-    if ((reinterpret_cast<uintptr_t>(wp) & 7) != 0) wp++;
+    while ((reinterpret_cast<uintptr_t>(wp) & 15) != 0) wp++;		/* the profile tables are sources of 16-byte bulk copies */
     constexpr int NF = twosided ? 4 : 2;		/* = tp.nf; constant indices keep tp in registers */
 #pragma unroll
     for (int f = 0; f < GDP_MAXFILLS; f++) {
@@ -1595,7 +1787,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
       F[f].prof = reinterpret_cast<const uint2 *>(wp) + 32;	/* 32 entries of look-ahead padding in front */
       F[f].dirPW = tp.dirPW; F[f].scPW = tp.scPW;
       tri_profiles(F[f],right ? R : L,mt,use8,reinterpret_cast<uint2 *>(wp) + 32,tb);
-      wp += 2 * (size_t) (tp.nA[f] + 2 + 32);
+      wp += 2 * (size_t) ((tp.nA[f] + 2 + 32 + 1) & ~1);
     }
     uint32_t *dbase = wp; wp += (size_t) tp.npasses * tp.dirPW;
     uint32_t *sbase = NULL;
@@ -1613,7 +1805,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
       const bool lastrow = (b.flags & GMAPDP_F_LASTROW) != 0;
       BestTrack bt;
       if (lastrow) { bt.bs = NEG; bt.bk = (b.rlenL << 16); } else { bt.bs = 0; bt.bk = 0; }
-      tri_fill_all<0>(F,tp.nf,tp.npasses,open,extend,NEG,POS,&bt,b.rlenL,lastrow,edge,noalt,NULL,NULL);
+      tri_fill_all<0>(F,tp.nf,tp.npasses,open,extend,NEG,POS,&bt,b.rlenL,lastrow,edge,noalt,NULL,NULL,stg);
       for (int off = 16; off > 0; off >>= 1) {
 	const int os = __shfl_xor_sync(FULLMASK,bt.bs,off), ok = __shfl_xor_sync(FULLMASK,bt.bk,off);
 	if (os > bt.bs || (os == bt.bs && (lateL ? ok > bt.bk : ok < bt.bk))) { bt.bs = os; bt.bk = ok; }
@@ -1658,9 +1850,21 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 	gc.it1 = (uint32_t) isc[3] | ((uint32_t) isc[4] << 8) | ((uint32_t) isc[5] << 16);
 	GenBest gb; gb.s = NEG; gb.key = -1; gb.cnt = 0; gb.p = 0.0; gb.ties = wp + lane; wp += GEN_TIECAP * 32;
 	gen_diagonals(LU,RU,dgL,dgR,NEG,POS);
+	{
+	  /* one word per position for the staged interior steps: the main-diagonal score of the side's upper fill at row i
+	     (meaningful up to the shorter side) and the dinucleotide class at column i */
+	  const int ne = gdp_ent_len(b), nL = min(b.rlenL,b.glenL), nR = min(b.rlenR,b.glenR);
+	  for (int i = lane; i < ne; i += 32) {
+	    const uint32_t dl_ = (i <= nL) ? (uint32_t) (uint16_t) dgL[i] : 0u, dr_ = (i <= nR) ? (uint32_t) (uint16_t) dgR[i] : 0u;
+	    entL[i] = (dl_ << 16) | ((i <= b.glenL) ? (uint32_t) ldi[i] : 0u);
+	    entR[i] = (dr_ << 16) | ((i <= b.glenR) ? (uint32_t) rdi[i] : 0u);
+	  }
+	  gc.entL = entL; gc.entR = entR;
+	  __syncwarp();
+	}
 	/* one call site (the fills are inlined): the second round runs only if a tie list that counts overflowed */
 	for (int round = 0; round < 2; round++) {
-	  tri_fill_all<2>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,&gc,&gb,round == 1);
+	  tri_fill_all<2>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,&gc,&gb,stg,round == 1);
 	  __syncwarp();
 	  if (round == 1) break;
 	  if (gb.key >= 0) gb.p = -1.0;				/* no probability has been fetched inside the fills */
@@ -1674,7 +1878,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 	fs = bridge_genome_finish(b,gc,gb,NEG,isc,&brL,&brR,&bcL,&bcR);
 	if (fs < 0) res.status = 1;
       } else {
-	tri_fill_all<1>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,NULL,NULL);
+	tri_fill_all<1>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,NULL,NULL,stg);
 	__syncwarp();
 	fs = bridge_cdna(b,LU,LL,RU,RL,NEG,wp,wp + (size_t) (b.glenL + 1) * (b.lbandR + b.ubandR + 1),reinterpret_cast<uint32_t *>(bnd),&bcL,&bcR,&brL,&brR);
       }
@@ -1736,13 +1940,19 @@ gmapdp_dp_kernel (KernelArgs ka) {
   uint2 *bnd = reinterpret_cast<uint2 *>(dyn_smem) + (size_t) warp * ka.smem_cols;
   const int gwarp = blockIdx.x * WARPS_PER_BLOCK + warp;
   uint32_t *ws = ka.ws + (size_t) gwarp * ka.ws_words;
+  /* E-only kinds: the warp's staging region behind the boundary rows (StgGeom) */
+  uint32_t stg = 0;
+  if (KIND != 0 && GMAPDP_STAGE) {
+    stg = smem_u32(dyn_smem + (size_t) WARPS_PER_BLOCK * ka.smem_cols * 8) + (uint32_t) warp * StgGeom<KIND == 2>::WARP_BYTES;
+    stage_init(stg);
+  }
 
   for (;;) {
     int idx = 0;
     if (lane == 0) idx = atomicAdd(ka.queue,1);
     idx = __shfl_sync(FULLMASK,idx,0);
     if (idx >= ka.nboxes) break;
-    process_box<KIND,false>(ka,ka.order[idx],ws,bnd,tb);
+    process_box<KIND,false>(ka,ka.order[idx],ws,bnd,tb,stg);
   }
 }
 
@@ -1757,6 +1967,11 @@ gmapdp_dp_kernel_any (KernelArgs ka) {
   uint2 *bnd = reinterpret_cast<uint2 *>(dyn_smem) + (size_t) warp * ka.smem_cols;
   const int gwarp = blockIdx.x * WARPS_PER_BLOCK + warp;
   uint32_t *ws = ka.ws + (size_t) gwarp * ka.ws_words;
+  uint32_t stg = 0;
+  if (GMAPDP_STAGE) {
+    stg = smem_u32(dyn_smem + (size_t) WARPS_PER_BLOCK * ka.smem_cols * 8) + (uint32_t) warp * STG_WARP_BYTES_MAX;
+    stage_init(stg);
+  }
 
   for (;;) {
     int idx = 0;
@@ -1765,10 +1980,10 @@ gmapdp_dp_kernel_any (KernelArgs ka) {
     if (idx >= ka.nboxes) break;
     const int bi = ka.order[idx];
     const int mode = ka.boxes[bi].mode;
-    if (mode == GMAPDP_SINGLE) process_box<0,true>(ka,bi,ws,bnd,tb);
-    else if (mode == GMAPDP_GENOME) process_box<2,true>(ka,bi,ws,bnd,tb);
-    else if (mode == GMAPDP_CDNA) process_box<3,true>(ka,bi,ws,bnd,tb);
-    else process_box<1,true>(ka,bi,ws,bnd,tb);
+    if (mode == GMAPDP_SINGLE) process_box<0,true>(ka,bi,ws,bnd,tb,stg);
+    else if (mode == GMAPDP_GENOME) process_box<2,true>(ka,bi,ws,bnd,tb,stg);
+    else if (mode == GMAPDP_CDNA) process_box<3,true>(ka,bi,ws,bnd,tb,stg);
+    else process_box<1,true>(ka,bi,ws,bnd,tb,stg);
   }
 }
 
@@ -2041,10 +2256,13 @@ static inline void sort_chunk (std::vector<std::pair<double,int> > &work, int b0
    the sorted order lists the boxes kind by kind (key offset by -1e12 per kind) and chunk_count[k][kind] counts them. */
 /* dynamic shared memory of a kernel kind: 8 bytes per column and warp (single gaps: the stripe boundary rows,
    unless they live in the workspace; cdna gaps: the bridge's M and Q tables); the other kinds use none */
+static inline size_t stage_smem (int kind) {	/* staging regions of a block's warps (E-only kinds) */
+  if (!GMAPDP_STAGE || kind == 0) return 0;
+  return (size_t) WARPS_PER_BLOCK * (kind == 2 ? StgGeom<true>::WARP_BYTES : StgGeom<false>::WARP_BYTES);
+}
 static inline size_t kind_smem (const gmapdp_ctx *ctx, int kind) {
   if (kind == 0 && GMAPDP_BND_GLOBAL) return 0;
-  if (kind == 1 || kind == 2) return 0;
-  return (size_t) WARPS_PER_BLOCK * ctx->ksmem_cols[kind] * 8;
+  return (size_t) WARPS_PER_BLOCK * ctx->ksmem_cols[kind] * 8 + stage_smem(kind);
 }
 
 struct PlanScan { size_t ws_words[GDP_NK], script_need, devprob_need; int maxcols[GDP_NK], me_kinds; };
@@ -2634,7 +2852,7 @@ int gdp_flight_launch (GdpFlight *f, int n, size_t poolbytes, size_t script_need
   cudaStream_t s0 = ctx->stream;		/* the flights of a lane run one after the other on its stream and share its workspace */
   const size_t wsw = (ws_words + 31) & ~(size_t) 31;
   const int cols = (maxcols + 7) & ~7;
-  const size_t smem = (size_t) WARPS_PER_BLOCK * cols * 8;
+  const size_t smem = (size_t) WARPS_PER_BLOCK * cols * 8 + (GMAPDP_STAGE ? (size_t) WARPS_PER_BLOCK * STG_WARP_BYTES_MAX : 0);
   if ((int) smem > ctx->max_smem) { ctx->err = "box too long for the shared-memory rows"; return GMAPDP_ERR_ARG; }
   if (ctx->any_occ == 0) {
     int occ = 0;

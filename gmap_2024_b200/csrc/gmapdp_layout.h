@@ -39,8 +39,11 @@ struct TriPacking {
   int dirPW, scPW;		/* words per pass plane */
 };
 
+/* at most GDP_PASS_FILLS fills share a pass: the interior steps stage each fill's operands in its own shared-memory slot
+   (bulk async copies, tri_fast in gmapdp_kernels.cu) and a warp has two slots per buffer */
+#define GDP_PASS_FILLS 2
 GDP_HD void tri_pack (TriPacking &tp) {
-  int used = 0, pass = -1;
+  int used = 0, pass = -1, inpass = 0;
   tp.Tmax = 0; tp.maxA = 0;
   /* fixed trip count and guards instead of `f < tp.nf' in the loop header: on the device the arrays then
      stay in registers (every index is a compile-time constant after unrolling) */
@@ -54,11 +57,11 @@ GDP_HD void tri_pack (TriPacking &tp) {
       if (tp.nA[f] > tp.maxA) tp.maxA = tp.nA[f];
       if (w > 32) {
 	tp.pass0[f] = pass + 1; tp.npass[f] = (w + 31) / 32; tp.lane0[f] = 0;
-	pass += tp.npass[f]; used = 32;
-      } else if (pass >= 0 && used + w <= 32) {
-	tp.pass0[f] = pass; tp.npass[f] = 1; tp.lane0[f] = used; used += w;
+	pass += tp.npass[f]; used = 32; inpass = GDP_PASS_FILLS;
+      } else if (pass >= 0 && used + w <= 32 && inpass < GDP_PASS_FILLS) {
+	tp.pass0[f] = pass; tp.npass[f] = 1; tp.lane0[f] = used; used += w; inpass++;
       } else {
-	pass++; tp.pass0[f] = pass; tp.npass[f] = 1; tp.lane0[f] = 0; used = w;
+	pass++; tp.pass0[f] = pass; tp.npass[f] = 1; tp.lane0[f] = 0; used = w; inpass = 1;
       }
     }
   }
@@ -123,6 +126,15 @@ GDP_HD bool gdp_full_packed (const gmapdp_box &b) {
   return (b.flags & GMAPDP_F_USE8) == 0 && b.gLalt_off == b.gL_off && b.rlenL <= GDP_PK_MAXSIDE && b.glenL <= GDP_PK_MAXSIDE;
 }
 
+#define GDP_ENT_PAD 128
+GDP_HD int gdp_ent_len (const gmapdp_box &b) {
+  int n = b.rlenL;
+  if (b.rlenR > n) n = b.rlenR;
+  if (b.glenL > n) n = b.glenL;
+  if (b.glenR > n) n = b.glenR;
+  return n + 4;
+}
+
 GDP_HD size_t gdp_align4 (size_t x) { return (x + 3) & ~(size_t) 3; }
 GDP_HD size_t gdp_align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
 
@@ -138,6 +150,9 @@ GDP_HD size_t gdp_ws_words (const gmapdp_box &b) {
   if (b.gflags & GMAPDP_G_SEG_R) bytes += gdp_align16(b.glenR + 2);
   /* genome gaps: main-diagonal scores of the two upper fills (int16) */
   bytes += gdp_align16(2 * (size_t) (b.rlenL + 2)) + gdp_align16(2 * (size_t) (b.rlenR + 2));
+  /* genome gaps: the same scores and the dinucleotide classes as one word per position (what the staged interior steps
+     read), GDP_ENT_PAD entries in front of each array: a staged window may begin before entry 0 */
+  if (b.mode == GMAPDP_GENOME) bytes += 2 * gdp_align16(4 * (size_t) (GDP_ENT_PAD + gdp_ent_len(b)));
   w += bytes / 4;
   /* script staging */
   w += (size_t) (b.rlenL + b.glenL + b.rlenR + b.glenR + 16);
@@ -150,7 +165,7 @@ GDP_HD size_t gdp_ws_words (const gmapdp_box &b) {
     const bool scores = (b.mode == GMAPDP_CDNA);	/* genome gaps evaluate their bridge inside the fills */
     TriPacking tp;
     tri_fills_of(b,tp);
-    for (int f = 0; f < tp.nf; f++) w += 2 * (size_t) (tp.nA[f] + 2 + 32);	/* profile tables (+ look-ahead padding) */
+    for (int f = 0; f < tp.nf; f++) w += 2 * (size_t) (tp.nA[f] + 2 + 32) + 2;	/* profile tables (+ look-ahead padding), 16-byte aligned */
     w += (size_t) tp.npasses * (tp.dirPW + (scores ? tp.scPW : 0));
     w += (size_t) tp.maxA + 2;							/* edge array of wide fills */
     if (b.mode == GMAPDP_GENOME) w += 8 * 32;					/* tie lists of the bridge (GEN_TIECAP keys per lane) */
