@@ -198,6 +198,9 @@ def run_reference(args):
 CHAIN_BYTES_PER_HIT = 28        # 4 B position + 4 B score + 20 B link per (querypos, hit)
 
 
+CHAIN_SM_COUNT, CHAIN_CLOCK_GHZ, CHAIN_WARP_INSTR_PER_HIT = 148, 1.965, 770.0
+
+
 def chain_section(eng, args, rank, world, barrier, allreduce, MAX, SUM):
     """`--chain-problems` synthetic chaining problems per GPU (cDNAs of 2-11 exons, 1 % error, against 50-200 kb
     regions, k = 8: tests/chaingen.py), `--chain-distinct` distinct ones tiled.  Device-resident time per step from CUDA
@@ -256,9 +259,18 @@ def chain_section(eng, args, rank, world, barrier, allreduce, MAX, SUM):
                "config": {"workload": "stage-2 chaining: synthetic spliced cDNAs (2-11 exons of 80-400 nt, 1 % error) against 50-200 kb "
                                       "regions, 8-mer hits, lookback direction, gmap defaults", "problems_per_gpu": n,
                           "distinct_problems": nd, "hits_per_gpu": int(hits), "kernel": "gmapchain_kernel (one warp per problem)"},
-               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": None, "peak_source": peak_src,
-                            "note": "latency-bound pointer walk: algorithmic bytes = hits x 28 B (SURVEY.md section 8d)"},
+               # the kernel is a dependent walk bound by instruction issue, not by bytes (ncu, profiles/r01s2_chain_kernel_metrics.csv:
+               # 27.6 G warp instructions for 35.6 M hits = ~770 per hit, issue slots 66.5 % active, DRAM 3.4 GB per launch):
+               # the model is hits/s at one warp instruction per scheduler and clock; the HBM figure of SURVEY.md section 8d
+               # (hits x 28 B) is kept beside it
+               "roofline": {"bound": "issue", "achieved": tot_hits / world / (ms / 1e3) / 1e9,
+                            "peak": CHAIN_SM_COUNT * 4 * CHAIN_CLOCK_GHZ / CHAIN_WARP_INSTR_PER_HIT, "unit": "G hits/s",
+                            "frac": (tot_hits / world / (ms / 1e3) / 1e9) / (CHAIN_SM_COUNT * 4 * CHAIN_CLOCK_GHZ / CHAIN_WARP_INSTR_PER_HIT),
+                            "traffic": None,
+                            "peak_source": "model: 148 SMs x 4 schedulers x 1.965 GHz / 770 warp instructions per hit (measured by ncu, "
+                                           "profiles/r01s2_chain_kernel_metrics.csv)",
+                            "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                                    "note": "algorithmic bytes = hits x 28 B (SURVEY.md section 8d): not the bound"}},
                "e2e": {"value": tot_problems / (e2e_ms_max / args.steps / 1e3), "unit": "align_compute_lookback calls/s",
                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps},
                "gpu_launches": int(launches), "digest": "%016x" % digest}
@@ -608,7 +620,7 @@ def main():
     ap.add_argument("--chain-cpu-seconds", type=float, default=5.0)
     ap.add_argument("--stratum-boxes", type=int, default=1000000, help="production-size boxes per GPU for strata.production (0 = skip)")
     ap.add_argument("--decorated-boxes", type=int, default=200000, help="boxes per GPU for strata.decorated (0 = skip)")
-    ap.add_argument("--program-cdnas", type=int, default=3000, help="whole-program leg: synthetic cDNAs (0 = skip)")
+    ap.add_argument("--program-cdnas", type=int, default=10000, help="whole-program leg: synthetic cDNAs (0 = skip)")
     ap.add_argument("--program-genome-mb", type=int, default=20)
     ap.add_argument("--program-threads", default="128,256", help="gmap.sm100 -t values to try (the best identical run is reported)")
     ap.add_argument("--modemask", type=int, default=31, help="diagnostics: bit k keeps mode k (single,genome,cdna,end5,end3); 31 = the benchmark config")

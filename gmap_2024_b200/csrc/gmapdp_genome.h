@@ -81,9 +81,8 @@ GDPG_HD uint64_t gdp_genome_window (const GdpGenome &g, uint32_t startpos) {
   return (cur >> (2u * shift)) | (nxt << (64u - 2u * shift));
 }
 
-/* The evaluation as a sequence of passes, one large table per pass (the batch path evaluates all positions of all boxes
-   pass by pass with that table in shared memory, gmapdp_maxent_pass_kernel; gdp_maxent_prob below runs the same steps
-   back to back): window start = splice_pos - margin(kind); pass p multiplies the running odds by its table entry (and,
+/* The evaluation as a sequence of steps, one large table per step (gdp_maxent_prob below runs them back to back; the
+   look-ups of the steps are independent loads, only the multiplications are ordered): window start = splice_pos - margin(kind); pass p multiplies the running odds by its table entry (and,
    where the reference does, by the dinucleotide entry right after it); the last pass returns odds / (1 + odds). */
 GDPG_HD int gdp_maxent_margin (int kind) { return kind == GDP_ME_DONOR ? 3 : (kind == GDP_ME_ACCEPTOR ? 20 : (kind == GDP_ME_ANTIDONOR ? 6 : 3)); }
 GDPG_HD int gdp_maxent_npasses (int kind) { return (kind == GDP_ME_DONOR || kind == GDP_ME_ANTIDONOR) ? 1 : 5; }

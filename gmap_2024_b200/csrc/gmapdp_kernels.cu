@@ -1493,10 +1493,19 @@ __device__ int bridge_cdna (const gmapdp_box &b, const TriFill &LU, const TriFil
     const int lo = max(cR - ubandR,1), hi = min(cR + lbandR,rlengthR - 1);
     uint32_t *row = pb + (size_t) cR * PBW - (cR - ubandR);
     int bs = 0, br = 0; bool have = false;
-    for (int rR = lo; rR <= hi; rR++) {
-      const int sc = (rR < cR) ? tri_score(RU,rR,cR) : tri_score(RL,cR,rR);
-      if (!have || (late ? sc >= bs : sc > bs)) { bs = sc; br = rR; have = true; }
-      row[rR] = ((uint32_t) (bs + 32768) << 16) | (uint32_t) br;
+    /* four score loads in flight per round (they do not depend on the running best) */
+    for (int rR0 = lo; rR0 <= hi; rR0 += 4) {
+      int sc4[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int rR = min(rR0 + u,hi); sc4[u] = (rR < cR) ? tri_score(RU,rR,cR) : tri_score(RL,cR,rR); }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+	const int rR = rR0 + u, sc = sc4[u];
+	if (rR <= hi) {
+	  if (!have || (late ? sc >= bs : sc > bs)) { bs = sc; br = rR; have = true; }
+	  row[rR] = ((uint32_t) (bs + 32768) << 16) | (uint32_t) br;
+	}
+      }
     }
     M[cR] = have ? (((uint32_t) (bs + 32768) << 16) | (uint32_t) br) : NONE;
   }
@@ -1635,7 +1644,10 @@ __device__ __forceinline__ void decode_segment (GdpGenome g, uint32_t p0, int n,
 
 /* KIND: 0 single gaps (full fill), 1 end5/end3 (E-only fills + endpoint search), 2 genome gaps, 3 cdna gaps */
 template <int KIND, bool INK>
-__device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *bnd, const GdpTables *tb, uint32_t stg) {
+__device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *bnd, const GdpTables *tb, uint32_t stg, const bool bsync) {
+  /* bsync: the warps of the block walk through their boxes in step (BOX_PHASE: a block barrier in front of the fills,
+     behind them and in front of the publication) -- see gmapdp_dp_kernel */
+#define BOX_PHASE() do { if (bsync) __syncthreads(); } while (0)
   constexpr bool FULLK = (KIND == 0);
   constexpr bool twosided = (KIND >= 2);
 
@@ -1755,6 +1767,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
     uint32_t *dirs = wp;
     const bool alt = (b.gLalt_off != b.gL_off);
     fg.pk = gdp_full_packed(b) ? 1 : 0;
+    BOX_PHASE();
     if (fg.pk) {
       if (lateL) fill_full_pk<true>(L,b.lbandL,b.ubandL,mt,open,extend,dirs,fg,bnd,tb,ka.one);
       else fill_full_pk<false>(L,b.lbandL,b.ubandL,mt,open,extend,dirs,fg,bnd,tb,ka.one);
@@ -1763,6 +1776,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
     else { if (alt) fill_full<false,true>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb,ka.one);
 	   else fill_full<false,false>(L,b.lbandL,b.ubandL,mt,open,extend,NEG,POS,dirs,fg,bnd,tb,ka.one); }
     __syncwarp();
+    BOX_PHASE();
     tb_full(acc,L,dirs,fg,b.rlenL,b.glenL,tb); lenA = acc.nops;
 
   } else {
@@ -1805,7 +1819,9 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
       const bool lastrow = (b.flags & GMAPDP_F_LASTROW) != 0;
       BestTrack bt;
       if (lastrow) { bt.bs = NEG; bt.bk = (b.rlenL << 16); } else { bt.bs = 0; bt.bk = 0; }
+      BOX_PHASE();
       tri_fill_all<0>(F,tp.nf,tp.npasses,open,extend,NEG,POS,&bt,b.rlenL,lastrow,edge,noalt,NULL,NULL,stg);
+      BOX_PHASE();
       for (int off = 16; off > 0; off >>= 1) {
 	const int os = __shfl_xor_sync(FULLMASK,bt.bs,off), ok = __shfl_xor_sync(FULLMASK,bt.bk,off);
 	if (os > bt.bs || (os == bt.bs && (lateL ? ok > bt.bk : ok < bt.bk))) { bt.bs = os; bt.bk = ok; }
@@ -1842,7 +1858,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 	    gc.lp = lpb; gc.rp = rpb;
 	    __syncwarp();
 	  } else {
-	    /* batches: gmapdp_maxent_pass_kernel filled them in the context's device-side pool before this kernel started */
+	    /* batches: gmapdp_maxent_kernel_batch filled them in the context's device-side pool before this kernel started */
 	    gc.lp = ka.devprobs + b.probL_off; gc.rp = ka.devprobs + b.probR_off;
 	  }
 	}
@@ -1862,6 +1878,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 	  gc.entL = entL; gc.entR = entR;
 	  __syncwarp();
 	}
+	BOX_PHASE();
 	/* one call site (the fills are inlined): the second round runs only if a tie list that counts overflowed */
 	for (int round = 0; round < 2; round++) {
 	  tri_fill_all<2>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,&gc,&gb,stg,round == 1);
@@ -1875,11 +1892,14 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 	  if (!__any_sync(FULLMASK,gb.cnt > GEN_TIECAP)) break;
 	  gb.s = NEG; gb.key = -1; gb.cnt = 0; gb.p = 0.0;	/* such a list overflowed: once more, ties resolved on the spot */
 	}
+	BOX_PHASE();
 	fs = bridge_genome_finish(b,gc,gb,NEG,isc,&brL,&brR,&bcL,&bcR);
 	if (fs < 0) res.status = 1;
       } else {
+	BOX_PHASE();
 	tri_fill_all<1>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,NULL,NULL,stg);
 	__syncwarp();
+	BOX_PHASE();
 	fs = bridge_cdna(b,LU,LL,RU,RL,NEG,wp,wp + (size_t) (b.glenL + 1) * (b.lbandR + b.ubandR + 1),reinterpret_cast<uint32_t *>(bnd),&bcL,&bcR,&brL,&brR);
       }
       res.finalscore = fs; res.bestrL = brL; res.bestcL = bcL; res.bestrR = brR; res.bestcR = bcR;
@@ -1894,6 +1914,8 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 
   /* publish: allocate script space, copy, write the result */
   __syncwarp();
+  BOX_PHASE();
+#undef BOX_PHASE
   const int ntot = lenA + lenB;
   unsigned long long off = 0;
   if (lane == 0) off = atomicAdd(ka.script_cursor,(unsigned long long) ntot);
@@ -1916,6 +1938,12 @@ extern __shared__ __align__(16) unsigned char dyn_smem[];
    shared-memory boundary rows, 3 blocks/SM), end gaps, genome gaps, cdna gaps (E-only fills, bridges: almost
    no shared memory).  A specialisation carries only its own mode's code, so the warps of an SM share their
    instruction-cache footprint; the four are queued back to back on one stream (launch_chunk). */
+#ifndef GMAPDP_BLOCKSYNC
+#define GMAPDP_BLOCKSYNC 1
+#endif
+#ifndef GMAPDP_SYNC_FULL_CELLS
+#define GMAPDP_SYNC_FULL_CELLS (256 * 256)	/* single gaps: boxes below this many cells (rlength x glength) are processed in step */
+#endif
 #ifndef GMAPDP_FULL_MINB
 #define GMAPDP_FULL_MINB (GMAPDP_BND_GLOBAL ? 4 : 3)
 #endif
@@ -1947,13 +1975,47 @@ gmapdp_dp_kernel (KernelArgs ka) {
     stage_init(stg);
   }
 
+#if GMAPDP_BLOCKSYNC
+  /* The block takes WARPS_PER_BLOCK consecutive boxes of the work-sorted queue -- near-identical work -- and its warps
+     walk through them in step (process_box: BOX_PHASE).  The kernels are 5 - 13 k instructions; a warp alone runs most
+     of them once per box, and the warps of an SM sitting in different phases evict each other's code: on production-size
+     boxes instruction fetch was the first stall reason (ncu: no_instruction 5 - 7 per issue).  In step, the four warps of
+     a block share what they fetch. */
+  if (KIND == 0) {
+    /* Large single gaps first, every warp on its own (measured on the benchmark launch: 70.5 ms in step -- a full fill's
+       duration depends on more than the work the queue is sorted by, and the block waits for its slowest warp -- against
+       66.6 ms), until the warp meets a box below GMAPDP_SYNC_FULL_CELLS: the queue is sorted by decreasing work, so from
+       there on the boxes are small and the block goes on in step (production-size single gaps: 5.8 -> 4.2 ms per million calls). */
+    for (;;) {
+      int idx = 0;
+      if (lane == 0) idx = atomicAdd(ka.queue,1);
+      idx = __shfl_sync(FULLMASK,idx,0);
+      if (idx >= ka.nboxes) break;
+      const int bi = ka.order[idx];
+      const bool small = ((long long) ka.boxes[bi].rlenL * ka.boxes[bi].glenL < GMAPDP_SYNC_FULL_CELLS);
+      process_box<KIND,false>(ka,bi,ws,bnd,tb,stg,false);
+      if (small) break;
+    }
+  }
+  __shared__ int s_idx;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_idx = atomicAdd(ka.queue,WARPS_PER_BLOCK);
+    __syncthreads();
+    const int idx0 = s_idx;
+    if (idx0 >= ka.nboxes) break;
+    const bool step = (idx0 + WARPS_PER_BLOCK <= ka.nboxes);		/* a block without a box for every warp runs unsynchronised */
+    if (idx0 + warp < ka.nboxes) process_box<KIND,false>(ka,ka.order[idx0 + warp],ws,bnd,tb,stg,step);
+  }
+#else
   for (;;) {
     int idx = 0;
     if (lane == 0) idx = atomicAdd(ka.queue,1);
     idx = __shfl_sync(FULLMASK,idx,0);
     if (idx >= ka.nboxes) break;
-    process_box<KIND,false>(ka,ka.order[idx],ws,bnd,tb,stg);
+    process_box<KIND,false>(ka,ka.order[idx],ws,bnd,tb,stg,false);
   }
+#endif
 }
 
 /* One kernel for boxes of every kind: the streaming runtime's flights (gmapdp_stream.cpp) hold tens to hundreds of
@@ -1980,62 +2042,47 @@ gmapdp_dp_kernel_any (KernelArgs ka) {
     if (idx >= ka.nboxes) break;
     const int bi = ka.order[idx];
     const int mode = ka.boxes[bi].mode;
-    if (mode == GMAPDP_SINGLE) process_box<0,true>(ka,bi,ws,bnd,tb,stg);
-    else if (mode == GMAPDP_GENOME) process_box<2,true>(ka,bi,ws,bnd,tb,stg);
-    else if (mode == GMAPDP_CDNA) process_box<3,true>(ka,bi,ws,bnd,tb,stg);
-    else process_box<1,true>(ka,bi,ws,bnd,tb,stg);
+    if (mode == GMAPDP_SINGLE) process_box<0,true>(ka,bi,ws,bnd,tb,stg,false);
+    else if (mode == GMAPDP_GENOME) process_box<2,true>(ka,bi,ws,bnd,tb,stg,false);
+    else if (mode == GMAPDP_CDNA) process_box<3,true>(ka,bi,ws,bnd,tb,stg,false);
+    else process_box<1,true>(ka,bi,ws,bnd,tb,stg,false);
   }
 }
 
-/* MaxEnt arrays of the genome-gap boxes of a batch, one large table per launch (gmapdp_genome.h: the passes of a kind).
-   The 128 KB table of the pass sits in shared memory -- the look-ups are what bounded the in-kernel evaluation (random
-   8-byte reads of 1.5 MB of tables through L2) -- and one warp walks one array, 32 consecutive positions per step:
-   genome words and the running odds (read-modify-write in the device-side pool) are coalesced.  One block per SM
-   (the table takes more than half of its shared memory).  kind: which of donor / acceptor / antidonor / antiacceptor
-   this launch serves; arrays of other kinds are skipped. */
-#define ME_PASS_THREADS 1024
-__global__ void __launch_bounds__(ME_PASS_THREADS,1)
-gmapdp_maxent_pass_kernel (const gmapdp_box *boxes, const int *order, int nboxes, GdpGenome g, const double *me, double *pool, int kind, int pass) {
-  extern __shared__ __align__(16) double me_table[];
-  {
-    const double *src = me + gdp_maxent_table(kind,pass);
-    for (int i = threadIdx.x; i < 16384; i += ME_PASS_THREADS) me_table[i] = src[i];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, nwarps = ME_PASS_THREADS / 32;
+/* MaxEnt arrays of the genome-gap boxes of a batch (resident genome): one launch in front of the genome kernel evaluates
+   every entry of both arrays of every box into the device-side pool (`probL_off / probR_off', glength + 1 doubles per
+   array), which the genome kernel then reads like uploaded arrays.  One warp walks one array, 32 consecutive positions
+   per step and two steps in flight: the genome words are coalesced, the 2 (donor kinds) or 6 (acceptor kinds) table
+   entries of a position are independent loads from the 1.5 MB of model tables, which stay in L2 / L1 (nothing else
+   competes for them in this kernel: the same look-ups inside the genome kernel were what slowed it down, and a first
+   version that ran one launch per large table -- the table in shared memory, the running odds read and rewritten per
+   pass -- took 13.4 ms for the benchmark launch's 8 * 10^8 entries).  Entry c of an array is the probability at coordinate
+   pos0 + step * c for c < glength - 1 and 0 beyond (the calloc'ed tail of dynprog_genome.c:970-1061), gdp_maxent_prob
+   (gmapdp_genome.h): the arithmetic of Maxent_hr_*_prob in the reference's order. */
+#define ME_THREADS 256
+__global__ void __launch_bounds__(ME_THREADS,6)
+gmapdp_maxent_kernel_batch (const gmapdp_box *boxes, const int *order, int nboxes, GdpGenome g, const double *me, double *pool) {
+  const int lane = threadIdx.x & 31, nwarps = ME_THREADS / 32;
   const int gw = blockIdx.x * nwarps + (threadIdx.x >> 5), stride = gridDim.x * nwarps;
-  const int last = gdp_maxent_npasses(kind) - 1;
-  const uint32_t margin = (uint32_t) gdp_maxent_margin(kind);
   for (int a = gw; a < 2 * nboxes; a += stride) {		/* array a: side a & 1 of box order[a >> 1] */
     const gmapdp_box &b = boxes[order[a >> 1]];
     if (!(b.gflags & GMAPDP_G_PROBS)) continue;
     const bool right = (a & 1) != 0;
-    if ((int) (right ? b.probkindR : b.probkindL) != kind) continue;
+    const int kind = (int) (right ? b.probkindR : b.probkindL);
     const int glen = right ? b.glenR : b.glenL;
     const uint32_t pos0 = right ? b.probposR : b.probposL;
     const int step = (b.gflags & (right ? GMAPDP_G_PSTEP_NEG_R : GMAPDP_G_PSTEP_NEG_L)) ? -1 : +1;
     double * __restrict__ out = pool + (right ? b.probR_off : b.probL_off);
     const uint32_t chroffset = b.chroffset;
-    /* four positions per lane and step, all loads issued before the first use: the walk is bound by the latency of
-       the genome words and of the running odds, not by arithmetic */
-    for (int c0 = lane; c0 <= glen; c0 += 128) {
-      uint64_t W[4]; double odds[4]; bool live[4];
+    for (int c0 = lane; c0 <= glen; c0 += 64) {
+      double pr[2];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < 2; u++) {
 	const int c = c0 + 32 * u;
-	const uint32_t pos = pos0 + (uint32_t) (step * c);
-	live[u] = (c < glen - 1) && (pos >= chroffset + margin);
-	W[u] = live[u] ? gdp_genome_window(g,pos - margin) : 0ull;
-	odds[u] = (live[u] && pass > 0) ? out[c] : 0.0;
+	pr[u] = (c < glen - 1) ? gdp_maxent_prob(kind,g,me,pos0 + (uint32_t) (step * c),chroffset) : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-	const int c = c0 + 32 * u;
-	if (live[u]) {
-	  const double o = gdp_maxent_step(kind,pass,W[u],me_table,me + GDP_ME_DONOR_DI_P,odds[u]);
-	  out[c] = (pass == last) ? o / (1 + o) : o;
-	} else if (c <= glen && (c >= glen - 1 ? pass == 0 : pass == last)) out[c] = 0.0;	/* the calloc'ed tail of the reference's arrays; left of the chromosome */
-      }
+      for (int u = 0; u < 2; u++) if (c0 + 32 * u <= glen) out[c0 + 32 * u] = pr[u];
     }
   }
 }
@@ -2148,7 +2195,7 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop,device));
   ctx->sm_count = prop.multiProcessorCount;
-  ctx->max_smem = (int) prop.sharedMemPerBlockOptin;
+  ctx->max_smem = (int) prop.sharedMemPerBlockOptin - 256;	/* dynamic shared memory: the kernels hold a few bytes of static shared memory (the block's queue slot) */
   cudaFuncAttributes fa;
   cudaError_t fe = cudaFuncGetAttributes(&fa,gmapdp_dp_kernel<0>);
   if (fe != cudaSuccess) {
@@ -2179,7 +2226,6 @@ extern "C" int gmapdp_create (gmapdp_ctx **out, int device) {
   CK(cudaFuncSetAttribute(gmapdp_dp_kernel<2>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
   CK(cudaFuncSetAttribute(gmapdp_dp_kernel<3>,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
   CK(cudaFuncSetAttribute(gmapdp_dp_kernel_any,cudaFuncAttributeMaxDynamicSharedMemorySize,ctx->max_smem));
-  CK(cudaFuncSetAttribute(gmapdp_maxent_pass_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,16384 * (int) sizeof(double)));
   ctx->grid = 0;
   return GMAPDP_OK;
 }
@@ -2431,16 +2477,11 @@ static int launch_chunk (gmapdp_ctx *ctx, int first, const int *cnt, bool timed 
     CK(cudaMemsetAsync(ctx->d_queue + kind,0,sizeof(int),st));
     if (timed) CK(cudaEventRecord(ctx->evk[kind][0],st));
     if (kind == 2 && ctx->me_kinds && ctx->genome) {
-      /* the MaxEnt arrays of this chunk's genome gaps, pass by pass (counted with the genome kernel's time) */
-      for (int mk = 0; mk < 4; mk++) {
-	if (!((ctx->me_kinds >> mk) & 1)) continue;
-	for (int pass = 0; pass < gdp_maxent_npasses(mk); pass++) {
-	  gmapdp_maxent_pass_kernel<<<ctx->sm_count,ME_PASS_THREADS,16384 * sizeof(double),st>>>(ctx->d_boxes,ka.order,count,ka.genome,ka.maxent,
-												      ctx->d_devprobs,mk,pass);
-	  CK(cudaGetLastError());
-	  ctx->launches++;
-	}
-      }
+      /* the MaxEnt arrays of this chunk's genome gaps (counted with the genome kernel's time) */
+      const int mgrid = std::max(1,std::min(ctx->sm_count * 6,(2 * count + ME_THREADS / 32 - 1) / (ME_THREADS / 32)));
+      gmapdp_maxent_kernel_batch<<<mgrid,ME_THREADS,0,st>>>(ctx->d_boxes,ka.order,count,ka.genome,ka.maxent,ctx->d_devprobs);
+      CK(cudaGetLastError());
+      ctx->launches++;
     }
     if (kind == 0) gmapdp_dp_kernel<0><<<grid,BLOCK_THREADS,smem,st>>>(ka);
     else if (kind == 1) gmapdp_dp_kernel<1><<<grid,BLOCK_THREADS,smem,st>>>(ka);

@@ -1,0 +1,17 @@
+#!/bin/bash
+# block-synchronous box processing (GMAPDP_BLOCKSYNC) + the one-launch MaxEnt kernel: parity tests, then the bench against the
+# same sources built with GMAPDP_BLOCKSYNC=0
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_bench_workload.py tests/test_resident_genome.py tests/test_gpu_golden.py -m gpu -x -q > gpurun_out/sy_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/sy_tests.log
+B="--no-cpu-baseline --chain-problems 0 --program-cdnas 0 --decorated-boxes 0"
+timeout 600 python bench.py $B > gpurun_out/sy_bench.json 2> gpurun_out/sy_bench.err; echo "bench rc=$?"
+GMAPDP_LIB=build/variants/lib_nosync.so timeout 600 python bench.py $B > gpurun_out/sy_bench_nosync.json 2> gpurun_out/sy_bench_nosync.err; echo "bench nosync rc=$?"
+python - <<'PY'
+import json
+for f in ("sy_bench","sy_bench_nosync"):
+    try:
+        d=json.loads(open("gpurun_out/%s.json"%f).read().strip().splitlines()[-1])
+        r=d["roofline"]; p=d["strata"]["production"]
+        print(f,"ms",round(d["ms_per_step"],2),"single",round(r["kernel_ms"],2),"end/genome/cdna",[round(x,2) for x in r["other_kernels"]["ms"]],"e2e",round(d["e2e"]["ms_per_step"],1),"digest",d["digest"],"prod",round(p["ms_per_step"],2),{k:round(v,2) for k,v in p["kernel_ms"].items()},"prod e2e",round(p["e2e"]["ms_per_step"],1))
+    except Exception as e: print(f,"unreadable",e)
+PY

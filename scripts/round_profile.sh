@@ -13,9 +13,9 @@ for spec in "1 full" "2 genome" "4 cdna" "24 end"; do
   CMD2="python bench.py --boxes 100000 --steps 1 --warmup 0 --no-cpu-baseline --chain-problems 0 --program-cdnas 0 --stratum-boxes 0 --decorated-boxes 0 --modemask $1"
   $CMD2 > gpurun_out/plain_$2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gmapdp_dp_kernel -c 1 -o gpurun_out/prof_$2 $CMD2 > gpurun_out/ncu_$2.log 2>&1
 done
-# the MaxEnt pass kernel (resident genome): the first acceptor pass of the genome-only batch
+# the MaxEnt kernel (resident genome) of the genome-only batch
 CMD3="python bench.py --boxes 100000 --steps 1 --warmup 0 --no-cpu-baseline --chain-problems 0 --program-cdnas 0 --stratum-boxes 0 --decorated-boxes 0 --modemask 2"
-ncu --set full --clock-control none --import-source on -k regex:maxent_pass -s 1 -c 1 -o gpurun_out/prof_mepass $CMD3 > gpurun_out/ncu_mepass.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:maxent_kernel_batch -c 1 -o gpurun_out/prof_mepass $CMD3 > gpurun_out/ncu_mepass.log 2>&1
 # the overflow path of the bridge's tie lists: the same parity tests against a build with one-entry lists
 python -m pytest tests/test_gpu_parity.py -x -q -k tie_list_overflow 2>&1 | tail -3 > gpurun_out/tiecap1_tests.log
 cat gpurun_out/tiecap1_tests.log
