@@ -37,7 +37,9 @@
 #include "gmapdp_genome.h"
 #include "gmapdp_tables.h"
 
+#ifndef WARPS_PER_BLOCK
 #define WARPS_PER_BLOCK 4
+#endif
 #ifndef GMAPDP_BND_GLOBAL
 #define GMAPDP_BND_GLOBAL 0	/* 1: single-gap kernel keeps its stripe boundary rows in the HBM workspace (L1) instead of shared
 				   memory, which lifts its occupancy from 3 to 4-6 blocks/SM.  Measured (500 k single-gap boxes):
@@ -1941,8 +1943,8 @@ extern __shared__ __align__(16) unsigned char dyn_smem[];
 #ifndef GMAPDP_BLOCKSYNC
 #define GMAPDP_BLOCKSYNC 1
 #endif
-#ifndef GMAPDP_SYNC_FULL_CELLS
-#define GMAPDP_SYNC_FULL_CELLS (256 * 256)	/* single gaps: boxes below this many cells (rlength x glength) are processed in step */
+#ifndef GMAPDP_SYNC_FULL_WORK
+#define GMAPDP_SYNC_FULL_WORK 40000	/* single gaps: boxes below this work estimate (box_work: rows x steps per stripe) are processed in step */
 #endif
 #ifndef GMAPDP_FULL_MINB
 #define GMAPDP_FULL_MINB (GMAPDP_BND_GLOBAL ? 4 : 3)
@@ -1951,10 +1953,12 @@ extern __shared__ __align__(16) unsigned char dyn_smem[];
 #define GMAPDP_TRI_MINB 5
 #endif
 #ifndef GMAPDP_END_MINB
-#define GMAPDP_END_MINB 8		/* measured: 8 blocks/SM (64 registers) beat 5 for the end-gap kernel, 6 for genome gaps */
+#define GMAPDP_END_MINB 8		/* measured: 8 blocks/SM (64 registers) beat 5 for the end-gap kernel */
 #endif
 #ifndef GMAPDP_GENOME_MINB
-#define GMAPDP_GENOME_MINB 6
+#define GMAPDP_GENOME_MINB 8		/* with the boxes of a block in step: 8 blocks/SM (64 registers) 29.7 ms per 100 k genome gaps, 6 blocks 30.9,
+					   5 blocks 33.4 (before, on per-warp queues, 6 beat 8); an 8-step interior body (GMAPDP_GENOME_UNR=8) 32.5,
+					   passes inlined (GMAPDP_TRI_INLINE=7) 30.9; 256-thread blocks for all kinds 32.3 */
 #endif
 #ifndef GMAPDP_CDNA_MINB
 #define GMAPDP_CDNA_MINB GMAPDP_TRI_MINB
@@ -1981,31 +1985,37 @@ gmapdp_dp_kernel (KernelArgs ka) {
      of them once per box, and the warps of an SM sitting in different phases evict each other's code: on production-size
      boxes instruction fetch was the first stall reason (ncu: no_instruction 5 - 7 per issue).  In step, the four warps of
      a block share what they fetch. */
-  if (KIND == 0) {
-    /* Large single gaps first, every warp on its own (measured on the benchmark launch: 70.5 ms in step -- a full fill's
-       duration depends on more than the work the queue is sorted by, and the block waits for its slowest warp -- against
-       66.6 ms), until the warp meets a box below GMAPDP_SYNC_FULL_CELLS: the queue is sorted by decreasing work, so from
-       there on the boxes are small and the block goes on in step (production-size single gaps: 5.8 -> 4.2 ms per million calls). */
-    for (;;) {
-      int idx = 0;
-      if (lane == 0) idx = atomicAdd(ka.queue,1);
-      idx = __shfl_sync(FULLMASK,idx,0);
-      if (idx >= ka.nboxes) break;
-      const int bi = ka.order[idx];
-      const bool small = ((long long) ka.boxes[bi].rlenL * ka.boxes[bi].glenL < GMAPDP_SYNC_FULL_CELLS);
-      process_box<KIND,false>(ka,bi,ws,bnd,tb,stg,false);
-      if (small) break;
-    }
-  }
+  /* Large single gaps first, every warp on its own (measured on the benchmark launch: 70.5 ms in step -- a full fill's
+     duration depends on more than the work the queue is sorted by, and the block waits for its slowest warp -- against
+     66.6 ms), until the warp meets a box below GMAPDP_SYNC_FULL_WORK: the queue is sorted by decreasing work, so from
+     there on the boxes are small and the block goes on in step (production-size single gaps: 5.8 -> 4.2 ms per million
+     calls).  One loop and ONE call site of process_box for both regimes (two call sites made it a real call, with the
+     kernel arguments on the stack). */
+  bool solo = (KIND == 0);
   __shared__ int s_idx;
   for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_idx = atomicAdd(ka.queue,WARPS_PER_BLOCK);
-    __syncthreads();
-    const int idx0 = s_idx;
-    if (idx0 >= ka.nboxes) break;
-    const bool step = (idx0 + WARPS_PER_BLOCK <= ka.nboxes);		/* a block without a box for every warp runs unsynchronised */
-    if (idx0 + warp < ka.nboxes) process_box<KIND,false>(ka,ka.order[idx0 + warp],ws,bnd,tb,stg,step);
+    int idx;
+    bool step = false, last_solo = false;
+    if (solo) {
+      idx = 0;
+      if (lane == 0) idx = atomicAdd(ka.queue,1);
+      idx = __shfl_sync(FULLMASK,idx,0);
+      if (idx >= ka.nboxes) { solo = false; continue; }		/* joins the block (which then finds the queue empty) */
+      /* the work estimate the queue is sorted by (box_work): monotone along the queue */
+      const gmapdp_box &bq = ka.boxes[ka.order[idx]];
+      last_solo = ((long long) (bq.rlenL + 32) * (min((int) bq.glenL + 1,32 + bq.lbandL + bq.ubandL) + 31) < GMAPDP_SYNC_FULL_WORK);
+    } else {
+      __syncthreads();
+      if (threadIdx.x == 0) s_idx = atomicAdd(ka.queue,WARPS_PER_BLOCK);
+      __syncthreads();
+      const int idx0 = s_idx;
+      if (idx0 >= ka.nboxes) break;
+      step = (idx0 + WARPS_PER_BLOCK <= ka.nboxes);		/* a block without a box for every warp runs unsynchronised */
+      idx = idx0 + warp;
+      if (idx >= ka.nboxes) continue;
+    }
+    process_box<KIND,false>(ka,ka.order[idx],ws,bnd,tb,stg,step);
+    if (last_solo) solo = false;
   }
 #else
   for (;;) {

@@ -39,7 +39,8 @@ def main(prefix):
                          "%.2f GB read + %.2f GB written" % (prefix, rd / 1e9, wr / 1e9)},
               open(os.path.join(P, "roofline_traffic.json"), "w"), indent=1)
     for rep, name in (("prof_full", "single_kernel_100k"), ("prof_genome", "genome_kernel_100k"), ("prof_cdna", "cdna_kernel_100k"),
-                      ("prof_end", "end_kernel_100k"), ("prof_mepass", "maxent_kernel_100k")):
+                      ("prof_end", "end_kernel_100k"), ("prof_mepass", "maxent_kernel_100k"),
+                      ("prof_small2_genome", "small_genome_kernel_in_step"), ("prof_small2_end", "small_end_kernel_in_step")):
         path = os.path.join(G, rep + ".ncu-rep")
         if not os.path.exists(path):
             continue

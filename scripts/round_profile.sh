@@ -16,6 +16,12 @@ done
 # the MaxEnt kernel (resident genome) of the genome-only batch
 CMD3="python bench.py --boxes 100000 --steps 1 --warmup 0 --no-cpu-baseline --chain-problems 0 --program-cdnas 0 --stratum-boxes 0 --decorated-boxes 0 --modemask 2"
 ncu --set full --clock-control none --import-source on -k regex:maxent_kernel_batch -c 1 -o gpurun_out/prof_mepass $CMD3 > gpurun_out/ncu_mepass.log 2>&1
+# production-size stratum (15-150 bp boxes): the genome and end kernels again, now that the boxes of a block run in step
+for spec in "2 genome" "24 end"; do
+  set -- $spec
+  CMD4="python bench.py --small --boxes 300000 --steps 1 --warmup 0 --no-cpu-baseline --chain-problems 0 --program-cdnas 0 --stratum-boxes 0 --decorated-boxes 0 --modemask $1"
+  $CMD4 > gpurun_out/plain_small2_$2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gmapdp_dp_kernel -c 1 -o gpurun_out/prof_small2_$2 $CMD4 > gpurun_out/ncu_small2_$2.log 2>&1
+done
 # the overflow path of the bridge's tie lists: the same parity tests against a build with one-entry lists
 python -m pytest tests/test_gpu_parity.py -x -q -k tie_list_overflow 2>&1 | tail -3 > gpurun_out/tiecap1_tests.log
 cat gpurun_out/tiecap1_tests.log
