@@ -684,14 +684,23 @@ __device__ __forceinline__ void tri_pass (const TriFill (&F)[GDP_MAXFILLS], int 
 }
 
 /* all passes of a box's E-only fills */
+#ifndef GMAPDP_PASS_SYNC
+#define GMAPDP_PASS_SYNC 0	/* 1: boxes in step (bsync) also meet in front of each of their first GDP_MAXFILLS passes */
+#endif
 template <int MODE>
 __device__ void tri_fill_all (const TriFill (&F)[GDP_MAXFILLS], int nf, int npasses, int open, int extend, int NEG, int POS,
 			      BestTrack *bt, int track_rlen, bool lastrow, uint32_t *edge, bool fastok, const GenCtx *gc, GenBest *gb,
-			      uint32_t stg, bool ev_now = false) {
+			      uint32_t stg, bool ev_now = false, bool bsync = false) {
   bool wide = false;
 #pragma unroll
   for (int f = 0; f < GDP_MAXFILLS; f++) if (f < nf && F[f].npass > 1) wide = true;
+#if GMAPDP_PASS_SYNC
+  if (bsync) for (int p = npasses; p < GDP_MAXFILLS; p++) __syncthreads();	/* every box: exactly GDP_MAXFILLS pass barriers */
+#endif
   for (int pass = 0; pass < npasses; pass++) {
+#if GMAPDP_PASS_SYNC
+    if (bsync && pass > 0 && pass < GDP_MAXFILLS) __syncthreads();
+#endif
     if (wide) tri_pass<MODE,true>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,false,gc,gb,ev_now,stg);
     else tri_pass<MODE,false>(F,nf,pass,open,extend,NEG,POS,bt,track_rlen,lastrow,edge,fastok && !ev_now,gc,gb,ev_now,stg);
   }
@@ -1822,7 +1831,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
       BestTrack bt;
       if (lastrow) { bt.bs = NEG; bt.bk = (b.rlenL << 16); } else { bt.bs = 0; bt.bk = 0; }
       BOX_PHASE();
-      tri_fill_all<0>(F,tp.nf,tp.npasses,open,extend,NEG,POS,&bt,b.rlenL,lastrow,edge,noalt,NULL,NULL,stg);
+      tri_fill_all<0>(F,tp.nf,tp.npasses,open,extend,NEG,POS,&bt,b.rlenL,lastrow,edge,noalt,NULL,NULL,stg,false,bsync);
       BOX_PHASE();
       for (int off = 16; off > 0; off >>= 1) {
 	const int os = __shfl_xor_sync(FULLMASK,bt.bs,off), ok = __shfl_xor_sync(FULLMASK,bt.bk,off);
@@ -1883,7 +1892,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 	BOX_PHASE();
 	/* one call site (the fills are inlined): the second round runs only if a tie list that counts overflowed */
 	for (int round = 0; round < 2; round++) {
-	  tri_fill_all<2>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,&gc,&gb,stg,round == 1);
+	  tri_fill_all<2>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,&gc,&gb,stg,round == 1,bsync && round == 0);
 	  __syncwarp();
 	  if (round == 1) break;
 	  if (gb.key >= 0) gb.p = -1.0;				/* no probability has been fetched inside the fills */
@@ -1899,7 +1908,7 @@ __device__ void process_box (const KernelArgs &ka, int bi, uint32_t *ws, uint2 *
 	if (fs < 0) res.status = 1;
       } else {
 	BOX_PHASE();
-	tri_fill_all<1>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,NULL,NULL,stg);
+	tri_fill_all<1>(F,tp.nf,tp.npasses,open,extend,NEG,POS,NULL,0,false,edge,noalt,NULL,NULL,stg,false,bsync);
 	__syncwarp();
 	BOX_PHASE();
 	fs = bridge_cdna(b,LU,LL,RU,RL,NEG,wp,wp + (size_t) (b.glenL + 1) * (b.lbandR + b.ubandR + 1),reinterpret_cast<uint32_t *>(bnd),&bcL,&bcR,&brL,&brR);
@@ -2299,8 +2308,21 @@ static inline int work_bucket (int kind, double w) {
   if (q > GDP_WORK_BUCKETS - 1) q = GDP_WORK_BUCKETS - 1;
   return kind * GDP_WORK_BUCKETS + (GDP_WORK_BUCKETS - 1 - q);	/* ascending bucket = kind, then decreasing work */
 }
+/* Boxes of one work bucket are grouped by the code variant they run (GDP_VARIANTS per bucket): the four warps of a block
+   take consecutive boxes and go through them in step (gmapdp_dp_kernel), so neighbours should run the same instantiation
+   -- single gaps: packed 16-bit / int32 fill, jump-late or not; end gaps: the tie rule the interior steps are templated on.
+   GMAPDP_SORT_VARIANT=0 switches the sub-key off. */
+#define GDP_VARIANTS 4
+static inline int box_variant (const gmapdp_box &b) {
+  static const bool on = !(getenv("GMAPDP_SORT_VARIANT") && atoi(getenv("GMAPDP_SORT_VARIANT")) == 0);
+  if (!on) return 0;
+  const int late = (b.flags & GMAPDP_F_LATE_L) ? 1 : 0;
+  if (b.mode == GMAPDP_SINGLE) return (gdp_full_packed(b) ? 0 : 2) | late;
+  if (b.mode == GMAPDP_END5 || b.mode == GMAPDP_END3) return late;
+  return 0;
+}
 static inline void sort_chunk (std::vector<std::pair<double,int> > &work, int b0, int b1) {
-  std::vector<int> count(GDP_NK * GDP_WORK_BUCKETS + 1,0);
+  std::vector<int> count(GDP_NK * GDP_WORK_BUCKETS * GDP_VARIANTS + 1,0);
   for (int i = b0; i < b1; i++) count[(int) work[i].first + 1]++;
   for (size_t k = 1; k < count.size(); k++) count[k] += count[k-1];
   std::vector<std::pair<double,int> > out(b1 - b0);
@@ -2374,7 +2396,7 @@ static int plan_scan (gmapdp_ctx *ctx, const gmapdp_box *boxes, int nboxes, std:
 	if (b.mode == GMAPDP_GENOME || b.mode == GMAPDP_CDNA) pt.script += (size_t) b.rlenR + b.glenR + 4;
 	if (b.mode == GMAPDP_SINGLE) pt.cols[0] = std::max(pt.cols[0],(int) b.glenL + 2 + GDP_PK_EXTRA);
 	else if (b.mode == GMAPDP_CDNA) pt.cols[3] = std::max(pt.cols[3],(int) b.glenL + 2);	/* M and Q tables: 2 words per column */
-	work[i] = std::make_pair((double) work_bucket(kind,box_work(b)),i);
+	work[i] = std::make_pair((double) (work_bucket(kind,box_work(b)) * GDP_VARIANTS + box_variant(b)),i);
 	if (upload_bytes) (*upload_bytes)[i] = box_upload_bytes(b);
       }
     };
