@@ -2741,13 +2741,19 @@ extern "C" int gmapdp_run_batch_chunks (gmapdp_ctx *ctx, const gmapdp_box *boxes
   lap("box scan");
   /* Chunks grow geometrically from CHUNK_BYTES / 4: a short first chunk lets the device start early, and since a
      chunk uploads faster than it computes, the next one may be larger and still arrive in time -- fewer chunk
-     boundaries, where the persistent grids drain and refill. */
+     boundaries, where the persistent grids drain and refill.  GMAPDP_EQUAL_CHUNKS=1 keeps them small and equal
+     (CHUNK_BYTES / 8) when a per-chunk consumer is attached, so that less of its work is left for the end; measured with
+     the shim's replay on all 16 host threads it is SLOWER (200 k benchmark boxes: 113 vs 85 ms end to end, 1 M boxes: 540
+     vs 385 ms): every chunk is handed over by this thread (event, script copy, callback), which then competes with the
+     replay threads for a core. */
   std::vector<int> chunk_begin(1,0);
   {
-    size_t acc = 0, limit = CHUNK_BYTES / 4;
+    static const bool equal_on = (getenv("GMAPDP_EQUAL_CHUNKS") && atoi(getenv("GMAPDP_EQUAL_CHUNKS")) != 0);
+    const bool equal_chunks = (on_chunk != NULL) && equal_on;
+    size_t acc = 0, limit = equal_chunks ? CHUNK_BYTES / 8 : CHUNK_BYTES / 4;
     for (int i = 0; i < nboxes; i++) {
       acc += upbytes[i];
-      if (acc >= limit || i == nboxes - 1) { chunk_begin.push_back(i + 1); acc = 0; limit = std::min(limit * 2,CHUNK_BYTES * 8); }
+      if (acc >= limit || i == nboxes - 1) { chunk_begin.push_back(i + 1); acc = 0; if (!equal_chunks) limit = std::min(limit * 2,CHUNK_BYTES * 8); }
     }
   }
   const int nchunks = (int) chunk_begin.size() - 1;

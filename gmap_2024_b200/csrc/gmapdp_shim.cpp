@@ -51,12 +51,17 @@ struct Pushed {
   gmapdp_cpair *buf = NULL;
   size_t lo = 0, hi = 0, cap = 0;		/* elements buf[lo .. hi) */
   std::vector<gmapdp_gapinfo> gaps;
+  /* the records hold positions relative to the side they lie on (include/gmapdp_shim.h): the bases, and the side the
+     pairs pushed next belong to */
+  gmapdp_pairbase base = {{0,0},{0,0}};
+  int side = 0;
+  void use_side (int k, int qbase, int gbase) { side = k; base.q[k] = qbase; base.g[k] = gbase; }
   Pushed () {}
   Pushed (const Pushed &) = delete;
   Pushed &operator= (const Pushed &) = delete;
-  Pushed (Pushed &&o) noexcept : buf(o.buf), lo(o.lo), hi(o.hi), cap(o.cap), gaps(std::move(o.gaps)) { o.buf = NULL; o.lo = o.hi = o.cap = 0; }
+  Pushed (Pushed &&o) noexcept : buf(o.buf), lo(o.lo), hi(o.hi), cap(o.cap), gaps(std::move(o.gaps)), base(o.base), side(o.side) { o.buf = NULL; o.lo = o.hi = o.cap = 0; }
   Pushed &operator= (Pushed &&o) noexcept {
-    if (this != &o) { free(buf); buf = o.buf; lo = o.lo; hi = o.hi; cap = o.cap; gaps = std::move(o.gaps); o.buf = NULL; o.lo = o.hi = o.cap = 0; }
+    if (this != &o) { free(buf); buf = o.buf; lo = o.lo; hi = o.hi; cap = o.cap; gaps = std::move(o.gaps); base = o.base; side = o.side; o.buf = NULL; o.lo = o.hi = o.cap = 0; }
     return *this;
   }
   ~Pushed () { free(buf); }
@@ -101,35 +106,53 @@ struct Pushed {
 #define GMAPDP_REPLAY_PREFETCH 0
 #endif
 
-/* non-temporal or ordinary 16-byte store of one record (GMAPDP_NT_STORES=0 selects ordinary stores: which one is faster
+/* non-temporal or ordinary stores of the records (GMAPDP_NT_STORES=0 selects ordinary stores: which one is faster
    depends on how many threads share the memory controllers) */
 const bool g_nt_stores = !(getenv("GMAPDP_NT_STORES") && atoi(getenv("GMAPDP_NT_STORES")) == 0);
-inline void store16 (gmapdp_cpair *p, __m128i v) {
-  if (g_nt_stores) _mm_stream_si128(reinterpret_cast<__m128i *>(p),v); else _mm_store_si128(reinterpret_cast<__m128i *>(p),v);
+/* two records (16 bytes) at p; p is 8-byte aligned */
+inline void store2 (gmapdp_cpair *p, __m128i v) {
+  if (!g_nt_stores) _mm_storeu_si128(reinterpret_cast<__m128i *>(p),v);
+  else if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) _mm_stream_si128(reinterpret_cast<__m128i *>(p),v);
+  else {
+    _mm_stream_si64(reinterpret_cast<long long *>(p),_mm_cvtsi128_si64(v));
+    _mm_stream_si64(reinterpret_cast<long long *>(p + 1),_mm_cvtsi128_si64(_mm_unpackhi_epi64(v,v)));
+  }
 }
 #endif
 
-inline void store_pair (gmapdp_cpair *p, int querypos, int genomepos, char cdna, char comp, char genome, char genomealt, int gap) {
+/* one record: positions relative to the list's current side, the side in the top bit of comp */
+inline void store_pair (Pushed &l, gmapdp_cpair *p, int querypos, int genomepos, char cdna, char comp, char genome, char genomealt) {
+  const unsigned qrel = (unsigned) (querypos - l.base.q[l.side]), grel = (unsigned) (genomepos - l.base.g[l.side]);
+  if (qrel >= GMAPDP_CPAIR_GAP || grel > 0xffffu) abort();	/* a position outside its side: never with sides <= 32767 */
+  const uint64_t rec = (uint64_t) qrel | ((uint64_t) grel << 16) | ((uint64_t) (uint8_t) cdna << 32)
+    | ((uint64_t) (uint8_t) (comp | (l.side ? 0x80 : 0)) << 40) | ((uint64_t) (uint8_t) genome << 48) | ((uint64_t) (uint8_t) genomealt << 56);
 #if defined(__SSE2__) && !defined(GMAPDP_NO_NT_STORES)
-  const uint32_t chars = (uint32_t) (uint8_t) cdna | ((uint32_t) (uint8_t) comp << 8) | ((uint32_t) (uint8_t) genome << 16) | ((uint32_t) (uint8_t) genomealt << 24);
-  store16(p,_mm_set_epi32(gap,(int) chars,genomepos,querypos));
-#else
-  p->querypos = querypos; p->genomepos = genomepos; p->cdna = cdna; p->comp = comp; p->genome = genome; p->genomealt = genomealt; p->gap = gap;
+  if (g_nt_stores) { _mm_stream_si64(reinterpret_cast<long long *>(p),(long long) rec); return; }
 #endif
+  memcpy(p,&rec,sizeof(rec));
 }
 
 inline void push_pair (Pushed &l, bool back, int querypos, int genomepos, char cdna, char comp, char genome, char genomealt) {
   if (querypos < 0 || genomepos < 0) return;		/* Pairpool_push, pairpool.c:190 */
-  store_pair(l.slot(back),querypos,genomepos,cdna,comp,genome,genomealt,-1);
+  store_pair(l,l.slot(back),querypos,genomepos,cdna,comp,genome,genomealt);
 }
 
 inline gmapdp_gapinfo &push_gapholder (Pushed &l, bool back, int queryjump, int genomejump) {
   gmapdp_gapinfo g;
   g.queryjump = queryjump; g.genomejump = genomejump; g.introntype = 0; g.pad_ = 0; g.donor_prob = 0.0; g.acceptor_prob = 0.0;
   l.gaps.push_back(g);
-  store_pair(l.slot(back),-1,-1,' ',' ',' ',' ',(int) l.gaps.size() - 1);
+  if (l.gaps.size() > 0xffffu) abort();
+  const uint64_t rec = (uint64_t) GMAPDP_CPAIR_GAP | ((uint64_t) (l.gaps.size() - 1) << 16) | 0x2020202000000000ull;
+  gmapdp_cpair *p = l.slot(back);
+#if defined(__SSE2__) && !defined(GMAPDP_NO_NT_STORES)
+  if (g_nt_stores) { _mm_stream_si64(reinterpret_cast<long long *>(p),(long long) rec); return l.gaps.back(); }
+#endif
+  memcpy(p,&rec,sizeof(rec));
   return l.gaps.back();
 }
+
+inline bool cpair_is_gap (const gmapdp_cpair &p) { return p.qrel == GMAPDP_CPAIR_GAP; }
+inline char cpair_comp (const gmapdp_cpair &p) { return (char) (p.comp & 0x7f); }
 
 /* one traced side, with the reference's pointer conventions */
 struct Side {
@@ -141,7 +164,10 @@ struct Side {
 struct Replayer {
   Pushed &l; const Side &sd; Counts &n; const GdpHostTables &t; const bool back;
   /* back: the list wanted is the reverse of the push order -- written backwards */
-  Replayer (Pushed &l_, const Side &sd_, Counts &n_, bool back_ = false) : l(l_), sd(sd_), n(n_), t(tables()), back(back_) {}
+  /* side: which of the call's (up to two) sides sd is; the records of a reversed side are relative to 32767 below its offsets */
+  Replayer (Pushed &l_, const Side &sd_, Counts &n_, bool back_ = false, int side = 0) : l(l_), sd(sd_), n(n_), t(tables()), back(back_) {
+    l.use_side(side,sd.queryoffset - (sd.revp ? 32767 : 0),sd.genomeoffset - (sd.revp ? 32767 : 0));
+  }
 
   void diag (int r, int c) {
     int qc = r - 1, gc = c - 1;
@@ -197,7 +223,9 @@ struct Replayer {
        or a negative position take the scalar loop below. */
     if ((step > 0) == back) {
       const __m128i star = _mm_set1_epi8('*'), dyn = _mm_set1_epi8((char) COMP_DYNMATCH), mis = _mm_set1_epi8((char) COMP_MISMATCH);
-      const __m128i minus1 = _mm_set1_epi32(-1), iota = _mm_set_epi32(3,2,1,0), four = _mm_set1_epi32(4);
+      const __m128i sidebit = _mm_set1_epi8(l.side ? (char) 0x80 : (char) 0);
+      const __m128i iota16 = _mm_set_epi16(7,6,5,4,3,2,1,0);
+      const int qb = l.base.q[l.side], gb = l.base.g[l.side];
       for (; len - j >= 8; j += 8, rs += 8 * step, ru += 8 * step, gs += 8 * step, ga += 8 * step, qpos += 8 * step, gpos += 8 * step, out += 8 * ostep) {
 	const int lowoff = (step > 0) ? 0 : -7;			/* ascending-memory start of the chunk */
 	const int q0 = qpos + lowoff, g0 = gpos + lowoff;
@@ -226,25 +254,19 @@ struct Replayer {
 	  comp = _mm_load_si128(reinterpret_cast<const __m128i *>(cb));
 	}
 	nm += good; nx += 8 - good;
+	comp = _mm_or_si128(comp,sidebit);
 	/* chars words (cdna | comp << 8 | genome << 16 | genomealt << 24) of bytes 0-3 and 4-7 */
 	const __m128i rc = _mm_unpacklo_epi8(vrs,comp), gg = _mm_unpacklo_epi8(vgs,vga);
 	const __m128i c03 = _mm_unpacklo_epi16(rc,gg), c47 = _mm_unpackhi_epi16(rc,gg);
-	const __m128i vq = _mm_add_epi32(_mm_set1_epi32(q0),iota), vg = _mm_add_epi32(_mm_set1_epi32(g0),iota);
-	const __m128i vq4 = _mm_add_epi32(vq,four), vg4 = _mm_add_epi32(vg,four);
+	/* position words (qrel | grel << 16) of bytes 0-3 and 4-7 */
+	const __m128i vq = _mm_add_epi16(_mm_set1_epi16((short) (q0 - qb)),iota16), vg = _mm_add_epi16(_mm_set1_epi16((short) (g0 - gb)),iota16);
+	const __m128i p03 = _mm_unpacklo_epi16(vq,vg), p47 = _mm_unpackhi_epi16(vq,vg);
+	/* the record of memory index m goes to slot base - m: two records per 16-byte store, the higher index first */
 	gmapdp_cpair *base = (step > 0) ? out : out + 7;	/* slot of memory index 0 */
-	__m128i pos, chm;
-	pos = _mm_unpacklo_epi32(vq,vg); chm = _mm_unpacklo_epi32(c03,minus1);
-	store16(base,_mm_unpacklo_epi64(pos,chm));
-	store16(base - 1,_mm_unpackhi_epi64(pos,chm));
-	pos = _mm_unpackhi_epi32(vq,vg); chm = _mm_unpackhi_epi32(c03,minus1);
-	store16(base - 2,_mm_unpacklo_epi64(pos,chm));
-	store16(base - 3,_mm_unpackhi_epi64(pos,chm));
-	pos = _mm_unpacklo_epi32(vq4,vg4); chm = _mm_unpacklo_epi32(c47,minus1);
-	store16(base - 4,_mm_unpacklo_epi64(pos,chm));
-	store16(base - 5,_mm_unpackhi_epi64(pos,chm));
-	pos = _mm_unpackhi_epi32(vq4,vg4); chm = _mm_unpackhi_epi32(c47,minus1);
-	store16(base - 6,_mm_unpacklo_epi64(pos,chm));
-	store16(base - 7,_mm_unpackhi_epi64(pos,chm));
+	store2(base - 1,_mm_shuffle_epi32(_mm_unpacklo_epi32(p03,c03),_MM_SHUFFLE(1,0,3,2)));
+	store2(base - 3,_mm_shuffle_epi32(_mm_unpackhi_epi32(p03,c03),_MM_SHUFFLE(1,0,3,2)));
+	store2(base - 5,_mm_shuffle_epi32(_mm_unpacklo_epi32(p47,c47),_MM_SHUFFLE(1,0,3,2)));
+	store2(base - 7,_mm_shuffle_epi32(_mm_unpackhi_epi32(p47,c47),_MM_SHUFFLE(1,0,3,2)));
       }
     }
 #endif
@@ -257,7 +279,7 @@ struct Replayer {
       else if (t.cons[c1uc & 127][c2 & 127] || t.cons[c1uc & 127][c2a & 127]) { comp = COMP_AMBIG; nm++; }
       else { comp = COMP_MISMATCH; nx++; }
       if (qpos < 0 || gpos < 0) continue;			/* Pairpool_push, pairpool.c:190 */
-      store_pair(out,qpos,gpos,*rs,comp,c2,c2a,-1);
+      store_pair(l,out,qpos,gpos,*rs,comp,c2,c2a);
       out += ostep;
     }
     if (back) l.lo = (size_t) (out + 1 - l.buf); else l.hi = (size_t) (out - l.buf);
@@ -289,11 +311,11 @@ int maxnegscore_headfirst (const Pushed &l) {	/* Pair_maxnegscore, pair.c:8528; 
   size_t i = 0;
 #define HF(I) l[n - 1 - (I)]
   while (i < n) {
-    if (HF(i).gap >= 0) i++;
-    else if (HF(i).comp == COMP_MISMATCH) { score += -3; maxneg = std::min(maxneg,score - prevhigh); i++; }
-    else if (HF(i).comp == COMP_INDEL) {
+    if (cpair_is_gap(HF(i))) i++;
+    else if (cpair_comp(HF(i)) == COMP_MISMATCH) { score += -3; maxneg = std::min(maxneg,score - prevhigh); i++; }
+    else if (cpair_comp(HF(i)) == COMP_INDEL) {
       score += -3 + -1; i++;
-      while (i < n && HF(i).comp == COMP_INDEL) { score += -1; i++; }
+      while (i < n && !cpair_is_gap(HF(i)) && cpair_comp(HF(i)) == COMP_INDEL) { score += -1; i++; }
       maxneg = std::min(maxneg,score - prevhigh);
     } else { score += 1; prevhigh = std::max(prevhigh,score); i++; }
   }
@@ -499,7 +521,7 @@ extern "C" long GmapDP_batch_cells8_full (const gmapdp_batch *b) { return b->cel
 
 static gmapdp_box blank_box () { gmapdp_box x; memset(&x,0,sizeof(x)); return x; }
 
-static void diag_only (Pushed &l, const Side &sd, Counts &n, int r, int c) { Replayer rp(l,sd,n); rp.diag(r,c); }
+static void diag_only (Pushed &l, const Side &sd, Counts &n, int r, int c, int side = 0) { Replayer rp(l,sd,n,false,side); rp.diag(r,c); }
 
 /* ------------------------------------------------------------------------------------------------ */
 extern "C" int GmapDP_single_gap (gmapdp_batch *b, int dynprogindex, const char *rsequence, const char *rsequenceuc,
@@ -729,7 +751,7 @@ extern "C" int GmapDP_genome_gap (gmapdp_batch *b, int dynprogindex, const char 
       gp.introntype = itype;		/* the LAST iteration's introntype (dynprog_genome.c:3230) */
       gp.donor_prob = c.dout[0]; gp.acceptor_prob = c.dout[1];
       Side sr = {c.q.data() + rlength - 1,c.quc.data() + rlength - 1,rgr,rgra,rev_roffset,rev_goffsetR,true};
-      for (int r = bestrR; r > 0; r--) diag_only(l,sr,n,r,r);
+      for (int r = bestrR; r > 0; r--) diag_only(l,sr,n,r,r,1);
       *tbscore = n.score; *nmatches = n.nmatches; *nmismatches = n.nmismatches;
       bump(*dynprogindex_p);
       l.reverse(); c.pairs = std::move(l); c.isnull = false; c.done = true;
@@ -865,8 +887,8 @@ static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, i
       /* leading indels of the list in push order */
       const size_t sz = l.size();
       size_t k = 0;
-      if (c.end5) { while (k < sz && l[sz - 1 - k].comp == COMP_INDEL) k++; l.drop_back(k); }
-      else { while (k < sz && l[k].comp == COMP_INDEL) k++; l.drop_front(k); }
+      if (c.end5) { while (k < sz && cpair_comp(l[sz - 1 - k]) == COMP_INDEL) k++; l.drop_back(k); }
+      else { while (k < sz && cpair_comp(l[k]) == COMP_INDEL) k++; l.drop_front(k); }
     }
     bump(c.iout[0]);
     c.isnull = l.empty();
@@ -883,7 +905,7 @@ static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, i
     l.start(sideR,sideL + 1);
     /* the right-hand side reversed (written backwards), the gap holder, the left-hand side */
     Side sr = {c.q.data() + rlength - 1,c.quc.data() + rlength - 1,c.gR.data() + c.glenR - 1,c.gRa.data() + c.glenR - 1,rev_roffset,c.goffsetR,true};
-    Replayer(l,sr,n,true).run(bestcR >= bestrR ? 1 : 2,bestrR,bestcR,ops,r.script_lenA);
+    Replayer(l,sr,n,true,1).run(bestcR >= bestrR ? 1 : 2,bestrR,bestcR,ops,r.script_lenA);
     gmapdp_gapinfo &gp = push_gapholder(l,false,(rev_roffset - bestrR) - (c.roffset + bestrL) + 1,c.iout[2] - c.iout[1] - 1);
     gp.introntype = c.introntype_in; gp.donor_prob = c.dout[0]; gp.acceptor_prob = c.dout[1];
     Side sl = {c.q.data(),c.quc.data(),c.gL.data(),c.gLa.data(),c.roffset,c.goffset,false};
@@ -901,10 +923,11 @@ static void finish_call (Call &c, const gmapdp_result &r, const uint32_t *ops, i
     Counts n;
     l.start(sideR,sideL + 2 * INSERT_PAIRS + 2);
     Side sr = {c.qR.data() + c.rlenR - 1,c.qRuc.data() + c.rlenR - 1,c.gR.data() + c.glenL - 1,c.gRa.data() + c.glenL - 1,c.roffsetR,rev_goffset,true};
-    Replayer(l,sr,n,true).run(bestcR >= bestrR ? 1 : 2,bestrR,bestcR,ops,r.script_lenA);
+    Replayer(l,sr,n,true,1).run(bestcR >= bestrR ? 1 : 2,bestrR,bestcR,ops,r.script_lenA);
     const int queryjump = (c.roffsetR - bestrR) - (c.roffset + bestrL) + 1;
     const int genomejump = (rev_goffset - bestcR) - (c.goffset + bestcL) + 1;
     if (queryjump == INSERT_PAIRS && genomejump == INSERT_PAIRS) {
+      l.use_side(0,c.roffset,c.goffset);			/* the inserted pairs lie next to the left-hand side */
       for (int k = c.roffsetR - bestrR; k >= c.roffset + bestrL; k--)
 	push_pair(l,false,k,rev_goffset - bestcR + 1,c.q[k - c.roffset],COMP_SHORTGAP,' ',' ');
       for (int k = rev_goffset - bestcR; k >= c.goffset + bestcL; k--)
@@ -1164,19 +1187,24 @@ extern "C" int GmapDP_result (const gmapdp_batch *b, int id, int *iout, double *
     const gmapdp_cpair &s = c.pairs[k];
     gmapdp_pair &p = pairs[k];
     memset(&p,0,sizeof(p));
-    p.querypos = s.querypos; p.genomepos = s.genomepos; p.cdna = s.cdna; p.comp = s.comp; p.genome = s.genome; p.genomealt = s.genomealt;
-    if (s.gap >= 0) {
-      const gmapdp_gapinfo &g = c.pairs.gaps[s.gap];
+    p.cdna = s.cdna; p.comp = cpair_comp(s); p.genome = s.genome; p.genomealt = s.genomealt;
+    if (cpair_is_gap(s)) {
+      const gmapdp_gapinfo &g = c.pairs.gaps[s.grel];
+      p.querypos = p.genomepos = -1;
       p.gapp = 1; p.queryjump = g.queryjump; p.genomejump = g.genomejump; p.introntype = g.introntype;
       p.donor_prob = g.donor_prob; p.acceptor_prob = g.acceptor_prob;
-    } else p.dynprogindex = c.dpi;
+    } else {
+      const int side = ((unsigned char) s.comp >> 7) & 1;
+      p.querypos = c.pairs.base.q[side] + (int) s.qrel; p.genomepos = c.pairs.base.g[side] + (int) s.grel;
+      p.dynprogindex = c.dpi;
+    }
   }
   return n;
 }
 
 /* zero-copy view of a completed call's pair list (head first); valid until the batch is cleared */
 extern "C" int GmapDP_result_view (const gmapdp_batch *b, int id, const int **iout, const double **dout, const gmapdp_cpair **pairs,
-				   const gmapdp_gapinfo **gaps, int *dynprogindex) {
+				   const gmapdp_gapinfo **gaps, const gmapdp_pairbase **base, int *dynprogindex) {
   if (id < 0 || id >= (int) b->calls.size()) return -2;
   const Call &c = b->calls[id];
   if (!c.done) return -3;
@@ -1184,6 +1212,7 @@ extern "C" int GmapDP_result_view (const gmapdp_batch *b, int id, const int **io
   if (dout) *dout = c.dout;
   if (dynprogindex) *dynprogindex = c.dpi;
   if (gaps) *gaps = c.pairs.gaps.data();
+  if (base) *base = &c.pairs.base;
   if (c.isnull || c.pairs.empty()) { if (pairs) *pairs = NULL; return -1; }
   if (pairs) *pairs = c.pairs.data();
   return (int) c.pairs.size();

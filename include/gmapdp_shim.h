@@ -46,17 +46,27 @@ typedef struct gmapdp_pair {
   double donor_prob, acceptor_prob;
 } gmapdp_pair;
 
-/* How the lists are stored and handed out without a copy (GmapDP_result_view): one 16-byte record per pair -- the fields
+/* How the lists are stored and handed out without a copy (GmapDP_result_view): one 8-BYTE record per pair -- the fields
  * that differ from pair to pair -- and, for the few gap holders of a list (Pairpool_push_gapholder, pairpool.c:375), an entry
- * in a side table.  The other fields of a gmapdp_pair follow: gapp = (gap >= 0); an ordinary pair has queryjump =
- * genomejump = introntype = 0, both probabilities 0.0 and the call's dynprogindex; a gap holder has querypos = genomepos =
- * -1, blank chars, dynprogindex 0 and the jumps / introntype / probabilities of gaps[gap].  (A large batch writes ~10^9
- * pairs: at 48 bytes each the host's memory bandwidth, not the GPU, set the end-to-end rate.) */
+ * in a side table.  Positions are relative to the side of the call the pair lies on (a genome / cdna gap has two, up to
+ * 32767 long each; every other call one):
+ *     side      = (comp >> 7) & 1                    (the COMP_* characters are 7-bit)
+ *     querypos  = base->q[side] + qrel,   genomepos = base->g[side] + grel,   comp = comp & 0x7f
+ * qrel == GMAPDP_CPAIR_GAP marks a gap holder: querypos = genomepos = -1, blank chars, dynprogindex 0, and the jumps /
+ * introntype / probabilities of gaps[grel].  The other fields of a gmapdp_pair follow: gapp = (gap holder); an ordinary
+ * pair has queryjump = genomejump = introntype = 0, both probabilities 0.0 and the call's dynprogindex.
+ * (A large batch writes ~10^9 pairs.  At 48 bytes each the host's memory traffic, not the GPU, set the end-to-end rate;
+ * at 16 bytes -- absolute positions -- the replay of the benchmark step still took 320 ms on 16 host threads next to the
+ * device's 206 ms.) */
+#define GMAPDP_CPAIR_GAP 0xffffu
 typedef struct gmapdp_cpair {
-  int querypos, genomepos;
+  uint16_t qrel, grel;
   char cdna, comp, genome, genomealt;
-  int gap;			/* -1, or index into the call's gap table */
 } gmapdp_cpair;
+
+typedef struct gmapdp_pairbase {
+  int q[2], g[2];		/* per side: what the relative positions of its pairs are relative to */
+} gmapdp_pairbase;
 
 typedef struct gmapdp_gapinfo {
   int queryjump, genomejump, introntype, pad_;
@@ -174,7 +184,7 @@ int GmapDP_result (const gmapdp_batch *b, int id, int *iout, double *dout, gmapd
 /* the same without a copy: pointers into the batch, valid until it is cleared; *dynprogindex = the index the call's
    ordinary pairs carry */
 int GmapDP_result_view (const gmapdp_batch *b, int id, const int **iout, const double **dout, const gmapdp_cpair **pairs,
-			const gmapdp_gapinfo **gaps, int *dynprogindex);
+			const gmapdp_gapinfo **gaps, const gmapdp_pairbase **base, int *dynprogindex);
 /* device-side view of one call (NULL if it never reached the device) */
 const gmapdp_result *GmapDP_device_result (const gmapdp_batch *b, int id);
 

@@ -329,20 +329,23 @@ static void run_call (gmapdp_batch *b) {
   PROF_MARK(4);
 }
 
-/* records come head first: cons them from the tail (compact records, gmapdp_shim.h: gap holders carry an index into the
-   call's gap table, ordinary pairs the call's dynprogindex) */
-static List_T pairs_to_list (Pairpool_T pool, const gmapdp_cpair *p, const gmapdp_gapinfo *gaps, int dpi, int n) {
+/* records come head first: cons them from the tail (compact 8-byte records, gmapdp_shim.h: positions relative to the side
+   of the call the pair lies on, the side in the top bit of comp; gap holders carry an index into the call's gap table,
+   ordinary pairs the call's dynprogindex) */
+static List_T pairs_to_list (Pairpool_T pool, const gmapdp_cpair *p, const gmapdp_gapinfo *gaps, const gmapdp_pairbase *base, int dpi, int n) {
   List_T l = NULL;
   Pair_T g;
   int k;
   for (k = n - 1; k >= 0; k--) {
-    if (p[k].gap >= 0) {
-      const gmapdp_gapinfo *gi = &gaps[p[k].gap];
+    if (p[k].qrel == GMAPDP_CPAIR_GAP) {
+      const gmapdp_gapinfo *gi = &gaps[p[k].grel];
       l = Pairpool_push_gapholder(l,pool,gi->queryjump,gi->genomejump,/*leftpair*/NULL,/*rightpair*/NULL,/*knownp*/false);
       g = (Pair_T) List_head(l);
       g->introntype = gi->introntype; g->donor_prob = gi->donor_prob; g->acceptor_prob = gi->acceptor_prob;
     } else {
-      l = Pairpool_push(l,pool,p[k].querypos,p[k].genomepos,p[k].cdna,p[k].comp,p[k].genome,p[k].genomealt,dpi);
+      const int side = ((unsigned char) p[k].comp >> 7) & 1;
+      l = Pairpool_push(l,pool,base->q[side] + (int) p[k].qrel,base->g[side] + (int) p[k].grel,p[k].cdna,(char) (p[k].comp & 0x7f),
+			p[k].genome,p[k].genomealt,dpi);
     }
   }
   PROF_MARK(5);
@@ -363,6 +366,7 @@ Dynprog_single_gap (int *dynprogindex, int *traceback_score, int *nmatches, int 
   int id, n;
   const int *iout;
   const gmapdp_cpair *pairs;
+  const gmapdp_pairbase *base;
   const gmapdp_gapinfo *gaps;
   int dpi;
   gmapdp_batch *b = my_batch(dynprog);
@@ -389,11 +393,11 @@ Dynprog_single_gap (int *dynprogindex, int *traceback_score, int *nmatches, int 
 			 jump_late_p,extraband_single,widebandp,defect_rate);
   PROF_MARK(1);
   run_call(b);
-  n = GmapDP_result_view(b,id,&iout,NULL,&pairs,&gaps,&dpi);
+  n = GmapDP_result_view(b,id,&iout,NULL,&pairs,&gaps,&base,&dpi);
   *dynprogindex = iout[0]; *traceback_score = iout[1]; *nmatches = iout[2]; *nmismatches = iout[3];
   *nopens = iout[4]; *nindels = iout[5];
   if (fetch) { free(galt); free(gseq); }
-  l = (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,pairs,gaps,dpi,n);
+  l = (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,pairs,gaps,base,dpi,n);
   return l;
 }
 
@@ -407,6 +411,7 @@ end_gap (bool end5, int *dynprogindex, int *traceback_score, int *nmatches, int 
   int id, n, gl = glength;
   const int *iout;
   const gmapdp_cpair *pairs;
+  const gmapdp_pairbase *base;
   const gmapdp_gapinfo *gaps;
   int dpi;
   gmapdp_batch *b = my_batch(dynprog);
@@ -443,11 +448,11 @@ end_gap (bool end5, int *dynprogindex, int *traceback_score, int *nmatches, int 
 			    extraband_end,defect_rate,(int) endalign,require_pos_score_p);
   PROF_MARK(1);
   run_call(b);
-  n = GmapDP_result_view(b,id,&iout,NULL,&pairs,&gaps,&dpi);
+  n = GmapDP_result_view(b,id,&iout,NULL,&pairs,&gaps,&base,&dpi);
   *dynprogindex = iout[0]; *traceback_score = iout[1]; *nmatches = iout[2]; *nmismatches = iout[3];
   *nopens = iout[4]; *nindels = iout[5];
   if (fetch) { free(galt); free(gseq); }
-  return (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,pairs,gaps,dpi,n);
+  return (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,pairs,gaps,base,dpi,n);
 }
 
 List_T
@@ -497,6 +502,7 @@ Dynprog_genome_gap (int *dynprogindex, int *new_leftgenomepos, int *new_rightgen
   const double *dout;
   const int *iout;
   const gmapdp_cpair *pairs;
+  const gmapdp_pairbase *base;
   const gmapdp_gapinfo *gaps;
   int dpi;
   gmapdp_batch *b = my_batch(dynprogL);
@@ -564,14 +570,14 @@ Dynprog_genome_gap (int *dynprogindex, int *new_leftgenomepos, int *new_rightgen
 			 gL,gLa,gR,gRa,lp,rp,cdna_direction,jump_late_p,extraband_paired,defect_rate,maxpeelback,halfp,finalp);
   PROF_MARK(1);
   run_call(b);
-  n = GmapDP_result_view(b,id,&iout,&dout,&pairs,&gaps,&dpi);
+  n = GmapDP_result_view(b,id,&iout,&dout,&pairs,&gaps,&base,&dpi);
   *dynprogindex = iout[0];
   SET(new_leftgenomepos,iout[1]); SET(new_rightgenomepos,iout[2]); SET(traceback_score,iout[3]);
   *nmatches = iout[4]; *nmismatches = iout[5]; *nopens = iout[6]; *nindels = iout[7];
   SET(exonhead,iout[8]); *introntype = iout[9];
   *left_prob = dout[0]; *right_prob = dout[1];
   if (fetch) { free(rp); free(lp); free(gRa); free(gR); free(gLa); free(gL); }
-  return (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,pairs,gaps,dpi,n);
+  return (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,pairs,gaps,base,dpi,n);
 }
 
 List_T
@@ -587,6 +593,7 @@ Dynprog_cdna_gap (int *dynprogindex, int *traceback_score, bool *incompletep,
   char *g, *ga, *rg, *rga, empty[1] = {'\0'};
   const int *iout;
   const gmapdp_cpair *pairs;
+  const gmapdp_pairbase *base;
   const gmapdp_gapinfo *gaps;
   int dpi;
   gmapdp_batch *b = my_batch(dynprogL);
@@ -620,10 +627,10 @@ Dynprog_cdna_gap (int *dynprogindex, int *traceback_score, bool *incompletep,
 		       roffsetL,rev_roffsetR,goffset,g,ga,rg,rga,jump_late_p,extraband_paired,defect_rate);
   PROF_MARK(1);
   run_call(b);
-  n = GmapDP_result_view(b,id,&iout,NULL,&pairs,&gaps,&dpi);
+  n = GmapDP_result_view(b,id,&iout,NULL,&pairs,&gaps,&base,&dpi);
   *dynprogindex = iout[0];
   SET(traceback_score,iout[1]);
   if (iout[2]) *incompletep = true;
   if (fetch) { free(rga); free(rg); free(ga); free(g); }
-  return (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,pairs,gaps,dpi,n);
+  return (n < 0) ? (List_T) NULL : pairs_to_list(pairpool,pairs,gaps,base,dpi,n);
 }

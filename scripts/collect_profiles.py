@@ -1,6 +1,7 @@
 """Turns what scripts/round_profile.sh left in gpurun_out/ into the tracked summaries under profiles/:
     python scripts/collect_profiles.py r02        # writes profiles/r02_*.{json,csv,txt} and roofline_traffic.json
-Needs ncu (reads the .ncu-rep files with `ncu -i`)."""
+Needs ncu (reads the .ncu-rep files with `ncu -i`).  COLLECT_OUT=<dir> writes there instead: the reports of a round exceed
+what gpurun copies back (64 MiB), so scripts/r2_final2.sh summarises them on the GPU box and deletes them."""
 import csv
 import io
 import json
@@ -9,7 +10,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+G, P = os.path.join(ROOT, "gpurun_out"), os.environ.get("COLLECT_OUT") or os.path.join(ROOT, "profiles")
+os.makedirs(P, exist_ok=True)
 KEEP = ("dram__bytes", "gpu__dram_throughput", "gpu__time_duration", "l1tex__t_sector_hit_rate", "lts__t_sector_hit_rate",
         "launch__", "sm__inst_executed", "sm__pipe_", "sm__warps_active", "smsp__average_warps_issue_stalled",
         "smsp__issue_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed", "sm__throughput",

@@ -149,3 +149,72 @@ def test_cell_counts_of_shim_and_oracle_agree(lib):
         total += mine
     assert total > 1000000
     b.free()
+
+
+def _random_script(rng, r, c):
+    """a random but well-formed edit script from cell (r, c): ops (len << 2 | kind), kind 0 diagonal run, 1 genome skip,
+    2 query skip, in traceback order"""
+    ops = []
+    while r > 0 and c > 0 and len(ops) < 64:
+        u = rng.random()
+        if u < 0.7:
+            n = rng.randint(1, min(r, c)); ops.append(n << 2); r -= n; c -= n
+        elif u < 0.85:
+            n = rng.randint(1, min(c, 4)); ops.append((n << 2) | 1); c -= n
+        else:
+            n = rng.randint(1, min(r, 4)); ops.append((n << 2) | 2); r -= n
+    return ops
+
+
+def test_replay_vector_path_equals_scalar_path(lib, tmp_path):
+    """The replay writes eight 8-byte pair records per iteration with SSE2 (positions relative to the call's sides, reversed
+    sides written backwards).  The same shim compiled without that path (-DGMAPDP_NO_NT_STORES: one record at a time) must
+    hand out identical lists for the same device results -- here random well-formed edit scripts for every device box
+    of a mixed batch, completed through GmapDP_batch_complete (no GPU involved)."""
+    import random
+    import subprocess
+    from gmap_2024_b200.build import CSRC
+    from gmap_2024_b200.engine import Batch, Box, DeviceResult, load_library
+    scalar = str(tmp_path / "libshim_scalar.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-msse2", "-DGMAPDP_NO_NT_STORES", "-o", scalar,
+                           os.path.join(CSRC, "gmapdp_shim.cpp"), "-L" + CSRC, "-lgmapdp_b200", "-Wl,-rpath," + CSRC, "-lpthread"])
+    boxes = [x for x in dpgen.synth_boxes(seed=21, n=900, rmin=20, rmax=400) if x["mode"] != "cdna"]
+    outs = []
+    for L in (lib, load_library(scalar)):
+        b = Batch(_NoDevice(L), 2000, 2030)
+        ids = [b.add(x) for x in boxes]
+        ptr, n, _, _, _, _ = b.device_view()
+        assert n > 300
+        rng = random.Random(5)
+        results = (DeviceResult * n)()
+        script = []
+        for k in range(n):
+            x = Box.from_address(ptr.value + C.sizeof(Box) * k)
+            r = results[k]
+            r.status = 0
+            r.script_off = len(script)
+            if x.mode == 0:
+                a = _random_script(rng, x.rlenL, x.glenL)
+                r.script_lenA, r.script_lenB = len(a), 0
+                script += a
+            elif x.mode in (3, 4):
+                r.bestrL, r.bestcL = rng.randint(1, x.rlenL), rng.randint(1, x.glenL)
+                a = _random_script(rng, r.bestrL, r.bestcL)
+                r.script_lenA, r.script_lenB = len(a), 0
+                script += a
+            else:
+                r.bestrL, r.bestcL = rng.randint(1, x.rlenL - 1), rng.randint(1, x.glenL - 2)
+                r.bestrR, r.bestcR = x.rlenL - r.bestrL, rng.randint(1, x.glenR - 2)
+                a, bb = _random_script(rng, r.bestrR, r.bestcR), _random_script(rng, r.bestrL, r.bestcL)
+                r.script_lenA, r.script_lenB = len(a), len(bb)
+                script += a + bb
+        sc = (C.c_uint32 * max(len(script), 1))(*script)
+        L.GmapDP_batch_complete(b.h, results, sc)          # the counts of a random script differ from the device's: not an error here
+        outs.append([b.result(cid, x["mode"]) for cid, x in zip(ids, boxes)])
+        b.free()
+    assert len(outs[0]) == len(outs[1])
+    npairs = 0
+    for got, want in zip(*outs):
+        assert got == want
+        npairs += max(got[0], 0)
+    assert npairs > 20000
