@@ -2743,9 +2743,9 @@ extern "C" int gmapdp_run_batch_chunks (gmapdp_ctx *ctx, const gmapdp_box *boxes
      chunk uploads faster than it computes, the next one may be larger and still arrive in time -- fewer chunk
      boundaries, where the persistent grids drain and refill.  GMAPDP_EQUAL_CHUNKS=1 keeps them small and equal
      (CHUNK_BYTES / 8) when a per-chunk consumer is attached, so that less of its work is left for the end; measured with
-     the shim's replay on all 16 host threads it is SLOWER (200 k benchmark boxes: 113 vs 85 ms end to end, 1 M boxes: 540
-     vs 385 ms): every chunk is handed over by this thread (event, script copy, callback), which then competes with the
-     replay threads for a core. */
+     the shim's replay it is SLOWER (200 k benchmark boxes: 113 vs 85 ms end to end, 1 M boxes: 540 vs 385 ms; not a matter
+     of the handing-over thread lacking a core: with 15 or 14 replay threads on the 16 cores 116 / 117 ms) -- every boundary
+     drains four persistent grids whose largest boxes run for milliseconds. */
   std::vector<int> chunk_begin(1,0);
   {
     static const bool equal_on = (getenv("GMAPDP_EQUAL_CHUNKS") && atoi(getenv("GMAPDP_EQUAL_CHUNKS")) != 0);
