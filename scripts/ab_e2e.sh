@@ -1,5 +1,6 @@
 #!/bin/bash
-# what bounds the end-to-end step: record stores (NT / ordinary) and chunk granularity, 200 k boxes
+# A/B of the end-to-end step (GmapDP_batch_run incl. pair lists) on 200 k boxes under run-time switches: chunk granularity
+# (GMAPDP_EQUAL_CHUNKS) and replay threads (GMAPDP_REPLAY_THREADS): does the thread that hands the chunks over need a core?
 mkdir -p gpurun_out
 B="--no-cpu-baseline --chain-problems 0 --program-cdnas 0 --decorated-boxes 0 --stratum-boxes 0 --boxes 200000 --steps 2 --warmup 1"
 run () { v=$1; shift
@@ -13,7 +14,7 @@ try:
 except Exception as e: print(v,"unreadable",e)
 PY
 }
-run default X=1
-run geometric GMAPDP_EQUAL_CHUNKS=0
-run plainstores GMAPDP_NT_STORES=0
-run geo_plain GMAPDP_EQUAL_CHUNKS=0 GMAPDP_NT_STORES=0
+run geo16 X=1
+run eq15 GMAPDP_EQUAL_CHUNKS=1 GMAPDP_REPLAY_THREADS=15
+run geo15 GMAPDP_REPLAY_THREADS=15
+run eq14 GMAPDP_EQUAL_CHUNKS=1 GMAPDP_REPLAY_THREADS=14

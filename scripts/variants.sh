@@ -6,6 +6,6 @@ mkdir -p build/variants
 i=0
 for flags in "$@"; do
   (cd gmap_2024_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared $flags \
-     -o ../../build/variants/lib_$i.so gmapdp_kernels.cu gmapdp_shim.cpp gmapchain_kernels.cu gmapchain_shim.cpp) && echo "build/variants/lib_$i.so: $flags"
+     -o ../../build/variants/lib_$i.so gmapdp_kernels.cu gmapdp_shim.cpp gmapdp_stream.cpp gmapchain_kernels.cu gmapchain_shim.cpp) && echo "build/variants/lib_$i.so: $flags"
   i=$((i+1))
 done
