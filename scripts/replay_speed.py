@@ -38,13 +38,14 @@ def main():
     ap.add_argument("--threads", default="1,8")
     ap.add_argument("--lib", default=None)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--decorated", action="store_true", help="the decorated stratum of the generator (N, IUPAC, lower case: not plain A C G T)")
     ap.add_argument("--runlen", type=float, default=60.0, help="mean length of a diagonal run between gaps")
     a = ap.parse_args()
     import benchgen
     from gmap_2024_b200.engine import Batch, Box, DeviceResult, load_library
     lib = load_library(a.lib)
     b = Batch(NoDevice(lib), 2000, 2030)
-    benchgen.fill_batch(b, 20241018, 0, a.boxes)
+    benchgen.fill_batch(b, 20241018, 0, a.boxes, decor=a.decorated)
     ptr, n, _, _, _, _ = b.device_view()
     rng = np.random.default_rng(1)
     results = (DeviceResult * n)()
