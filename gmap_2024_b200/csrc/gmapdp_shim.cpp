@@ -230,11 +230,13 @@ struct Replayer {
       const __m128i sidebit = _mm_set1_epi8(l.side ? (char) 0x80 : (char) 0);
       const __m128i iota16 = _mm_set_epi16(7,6,5,4,3,2,1,0);
       const int qb = l.base.q[l.side], gb = l.base.g[l.side];
-      if (sd.plain) {
-	/* Sixteen pairs at a time when both sequences are plain A C G T (Call::plain_p): comp is a blend of the two
-	   characters, no '*', no table look-ups.  3.5 instructions per pair instead of 5.5 plus the fix-up loop.  A run of
+      {
+	/* Sixteen pairs at a time: comp is a blend of the compare mask.  A call whose sequences are plain A C G T
+	   (Call::plain_p) needs nothing else; otherwise the block leaves a chromosome edge ('*') to the careful loops below
+	   and looks the FEW mismatching bytes up in the consistency table (an ambiguity match needs an IUPAC code).  A run of
 	   16 or more ends with one more block laid over its last sixteen pairs (the records it rewrites are the same; only
 	   the new lanes are counted) instead of up to fifteen scalar steps. */
+	const bool plain = sd.plain;
 	const __m128i mis_s = _mm_or_si128(mis,sidebit), dynxmis = _mm_xor_si128(dyn,mis), eight = _mm_set1_epi16(8);
 	for (;;) {
 	  unsigned lanes = 0xffffu;			/* memory lanes of this block that are new */
@@ -252,10 +254,26 @@ struct Replayer {
 	  const __m128i vgs = _mm_loadu_si128(reinterpret_cast<const __m128i *>(gs_ + lowoff));
 	  const __m128i vga = _mm_loadu_si128(reinterpret_cast<const __m128i *>(ga_ + lowoff));
 	  const __m128i vrs = _mm_loadu_si128(reinterpret_cast<const __m128i *>(rs_ + lowoff));
+	  if (!plain && _mm_movemask_epi8(_mm_cmpeq_epi8(vgs,star)) != 0) break;
 	  const __m128i eq = _mm_or_si128(_mm_cmpeq_epi8(vru,vgs),_mm_cmpeq_epi8(vru,vga));
-	  const __m128i comp = _mm_xor_si128(mis_s,_mm_and_si128(eq,dynxmis));
+	  __m128i comp = _mm_xor_si128(mis_s,_mm_and_si128(eq,dynxmis));
+	  unsigned okbits = (unsigned) _mm_movemask_epi8(eq);
+	  if (!plain && okbits != 0xffffu) {
+	    unsigned amb = 0;
+	    for (unsigned w = ~okbits & 0xffffu; w; w &= w - 1) {
+	      const int m = __builtin_ctz(w), a = ru_[lowoff + m] & 127;
+	      if (t.cons[a][gs_[lowoff + m] & 127] || t.cons[a][ga_[lowoff + m] & 127]) amb |= 1u << m;
+	    }
+	    if (amb) {
+	      alignas(16) char cb[16];
+	      _mm_store_si128(reinterpret_cast<__m128i *>(cb),comp);
+	      for (unsigned w = amb; w; w &= w - 1) cb[__builtin_ctz(w)] = (char) (COMP_AMBIG | (l.side ? 0x80 : 0));
+	      comp = _mm_load_si128(reinterpret_cast<const __m128i *>(cb));
+	      okbits |= amb;
+	    }
+	  }
 	  const int nnew = 16 - back16;
-	  const int good = __builtin_popcount((unsigned) _mm_movemask_epi8(eq) & lanes);
+	  const int good = __builtin_popcount(okbits & lanes);
 	  nm += good; nx += nnew - good;
 	  const __m128i rcl = _mm_unpacklo_epi8(vrs,comp), rch = _mm_unpackhi_epi8(vrs,comp);
 	  const __m128i ggl = _mm_unpacklo_epi8(vgs,vga), ggh = _mm_unpackhi_epi8(vgs,vga);
