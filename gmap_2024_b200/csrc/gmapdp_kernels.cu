@@ -491,6 +491,7 @@ __device__ __forceinline__ void tri_pass_body (const TriFill (&F)[GDP_MAXFILLS],
   s.stg = stg; s.slot = 0; s.ncopies = 0; s.cp_src = NULL; s.cp_stride = 0; s.cp_dst = 0; s.cp_bytes = 0; s.cp_total = 0;
   s.ent_own = NULL; s.ent_oth = NULL;
   int nslots = 0, cp_arr = -1;				/* fills of this pass so far; which array this lane copies (staging) */
+  (void) nslots; (void) cp_arr;
   int nA = -1, nB = -1, thi = -1, tlo = 0x7fffffff;
   int maxstart = 0, minend = 0x7fffffff, lm = -1;
   s.d = -1; s.lateadd = 0; s.lower = false; s.edge_in = false; s.edge_out = false;
