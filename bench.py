@@ -394,6 +394,11 @@ def run_ours(args):
     from gmap_2024_b200 import Engine
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    # the ranks of one node share its host cores: each rank's replay (the host half of `e2e`) gets its share of them instead
+    # of one thread per core per rank (GMAPDP_REPLAY_THREADS is the library's own knob; default: all cores)
+    cores_all = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if world > 1 and "GMAPDP_REPLAY_THREADS" not in os.environ:
+        os.environ["GMAPDP_REPLAY_THREADS"] = str(max(2, cores_all // env_int("LOCAL_WORLD_SIZE", world)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the DP engine has no CPU fallback)")
     torch.cuda.set_device(local)
@@ -556,6 +561,7 @@ def run_ours(args):
                 "config": bench_config(args),
                 "run": {"calls": int(tot_calls), "device_boxes": int(tot_boxes), "cells_per_step": int(tot_cells), "l2": "inputs_exceed_l2" if not args.small else "small",
                         "grid_blocks": info["grid_blocks"], "block_threads": info["block_threads"], "parallelism": "shard%d" % world,
+                        "host_cores": cores_all, "replay_threads_per_rank": os.environ.get("GMAPDP_REPLAY_THREADS", "all cores"),
                         "wall_ms_per_step": wall_ms_max / args.steps, "input_generation_s": gen_s,
                         "resident_genome_bytes": int(genome_bytes)},
                 "roofline": {"bound": "int", "achieved": achieved_int, "peak": ipeak, "unit": "Tera int ops/s", "frac": achieved_int / ipeak,
