@@ -218,3 +218,54 @@ def test_replay_vector_path_equals_scalar_path(lib, tmp_path):
         assert got == want
         npairs += max(got[0], 0)
     assert npairs > 20000
+
+
+def test_replay_reads_identical_streams_once(lib):
+    """Where the query is its own upper case the replay reads it once (and likewise the alt segment where there is no alt
+    genome).  The same calls with the query in lower case -- two distinct streams -- must give the same lists, the cdna
+    character in lower case being the only difference."""
+    import random
+    from gmap_2024_b200.engine import Batch, Box, DeviceResult
+    base = [x for x in dpgen.synth_boxes(seed=33, n=600, rmin=20, rmax=300) if x["mode"] != "cdna"]
+    upper = [dict(x, queryseq=x["queryseq"].upper()) for x in base]
+    lower = [dict(x, queryseq=x["queryseq"].lower()) for x in base]
+    outs = []
+    for boxes in (upper, lower):
+        b = Batch(_NoDevice(lib), 2000, 2030)
+        ids = [b.add(x) for x in boxes]
+        ptr, n, _, _, _, _ = b.device_view()
+        rng = random.Random(7)
+        results = (DeviceResult * n)()
+        script = []
+        for k in range(n):
+            x = Box.from_address(ptr.value + C.sizeof(Box) * k)
+            r = results[k]
+            r.status = 0
+            r.script_off = len(script)
+            if x.mode == 0:
+                a = _random_script(rng, x.rlenL, x.glenL)
+                r.script_lenA, r.script_lenB = len(a), 0
+                script += a
+            elif x.mode in (3, 4):
+                r.bestrL, r.bestcL = rng.randint(1, x.rlenL), rng.randint(1, x.glenL)
+                a = _random_script(rng, r.bestrL, r.bestcL)
+                r.script_lenA, r.script_lenB = len(a), 0
+                script += a
+            else:
+                r.bestrL, r.bestcL = rng.randint(1, x.rlenL - 1), rng.randint(1, x.glenL - 2)
+                r.bestrR, r.bestcR = x.rlenL - r.bestrL, rng.randint(1, x.glenR - 2)
+                a, bb = _random_script(rng, r.bestrR, r.bestcR), _random_script(rng, r.bestrL, r.bestcL)
+                r.script_lenA, r.script_lenB = len(a), len(bb)
+                script += a + bb
+        sc = (C.c_uint32 * max(len(script), 1))(*script)
+        lib.GmapDP_batch_complete(b.h, results, sc)
+        outs.append((n, [b.result(cid, x["mode"]) for cid, x in zip(ids, boxes)]))
+        b.free()
+    assert outs[0][0] == outs[1][0]                      # the same calls reach the device either way
+    npairs = 0
+    for (nu, iu, du, pu), (nl, il, dl, pl) in zip(outs[0][1], outs[1][1]):
+        assert (nu, iu, du) == (nl, il, dl)
+        for a, bb in zip(pu, pl):
+            assert a[:2] == bb[:2] and a[3:] == bb[3:] and a[2].upper() == bb[2].upper()
+        npairs += max(nu, 0)
+    assert npairs > 10000
